@@ -1,0 +1,158 @@
+/*
+ * contact_oracle.h -- ORACLE (test infrastructure, not product code).
+ *
+ * CPU restatement (plain C, double precision) of the hot path of eve70a/CONTACT: influence-coefficient
+ * product (AijPj / VecAijPj), NormCG / snorm, tangential solvers and subsurface stresses.  Every function
+ * cites the reference file:line it follows.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may use anything in oracle/.
+ *
+ * Parity status: the reference (Intel Fortran + static MKL) cannot be built here (no Fortran compiler), so the
+ * oracle is pinned against the reference's golden files (examples .ref_out, testbank .ref_fx, ...) to their
+ * printed precision (3-6 digits, exact element pictures and iteration counts) -- see tests/test_oracle_*.py.
+ * At 1e-9 the FFT product is pinned only by the restatement's own direct-sum twin (AijPj): "parity unpinned"
+ * by the reference's tests at that precision.
+ */
+#ifndef CONTACT_ORACLE_H
+#define CONTACT_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* element states and selectors: /root/reference/src/m_gridfunc.f90:30-37 */
+enum { CO_EXTER = 0, CO_ADHES = 1, CO_SLIP = 2, CO_PLAST = 3 };
+enum { CO_ALLELM = -9, CO_ALLINT = -8, CO_ALLEXT = -7 };
+/* coordinate directions: ikXDIR=1, ikYDIR=2, ikZDIR=3; jkALL=-3, jkTANG=-2 */
+enum { CO_X = 1, CO_Y = 2, CO_Z = 3, CO_TANG = -2, CO_ALL = -3 };
+
+#define CO_PI   3.14159265358979323846   /* m_globals.f90: pi = 4*atan(1) */
+#define CO_TINY 1e-20                    /* m_globals.f90: tiny */
+
+typedef struct { double re, im; } co_cplx;
+
+/* ---- FFT (co_fft.c) ---- */
+#define CO_MAXPLAN 24
+typedef struct co_fftplan {
+    int n, nfac, fac[40];
+    co_cplx *tw, *scratch, *work;
+} co_fftplan;
+typedef struct { int nplan; co_fftplan *plans[CO_MAXPLAN]; } co_plancache;
+
+co_fftplan *co_fft_plan(int n);
+void        co_fft_free(co_fftplan *pl);
+co_fftplan *co_fft_cached(co_plancache *pc, int n);
+void        co_plancache_clear(co_plancache *pc);
+void        co_fft_c2c(const co_fftplan *pl, const co_cplx *in, int in_stride, co_cplx *out, int isign);
+void        co_fft2_r2c(co_plancache *pc, int n1, int n2, const double *a, co_cplx *A);
+void        co_fft2_c2r(co_plancache *pc, int n1, int n2, co_cplx *A, double *a, double scale);
+
+/* ---- element division: t_eldiv, m_gridfunc.f90:116-139 ---- */
+typedef struct {
+    int  mx, my;
+    int *el;              /* (npot) */
+    int *row1st, *rowlst; /* (my), 1-based ix, empty row: first=mx, last=0 */
+    int  ixmin, ixmax, iymin, iymax;
+} co_eldiv;
+
+/* ---- influence coefficients: t_inflcf, m_inflcf.f90:49-106 ---- */
+typedef struct {
+    int     cf_mx, cf_my;
+    double *cf;           /* cf(-mx:mx-1, -my:my-1, 3, 3), x fastest, stored x G */
+    double  dx, dy, dq;
+    int     nt_cpl;
+    double  ga, ga_inv;
+    int     use_3bl, use_flxz;
+    double  flx_3bl, flx_z;
+    int     fft_ok[3][3];
+    int     fft_mx, fft_my;
+    co_cplx *fft_cf[3][3];
+    long    fft_len;
+    /* statistics (not in the reference) */
+    long    n_cfft;       /* number of coefficient transforms performed */
+} co_inflcf;
+
+static inline double *co_cf_ptr(const co_inflcf *c, int ik, int jk)
+{   /* block (ik,jk), 1-based; returns pointer to element (ix=-mx, iy=-my) */
+    return c->cf + (long) ((jk - 1) * 3 + (ik - 1)) * (4L * c->cf_mx * c->cf_my);
+}
+#define CO_CF(c, blk, ix, iy) ((blk)[((long)((iy) + (c)->cf_my)) * (2 * (c)->cf_mx) + ((ix) + (c)->cf_mx)])
+
+/* ---- material: t_material subset, m_hierarch_data.f90 ---- */
+typedef struct {
+    double gg[2], poiss[2];
+    double ga, nu, ak;        /* combined */
+} co_mater;
+
+/* ---- work counters ---- */
+typedef struct {
+    long n_prod;          /* single-block FFT products (fft_VecAijPj calls) */
+    long n_rowsum;        /* AijPj calls */
+    double alg_bytes;     /* algorithmic bytes of products, SURVEY 8(d) */
+    double alg_flops;
+} co_stats;
+
+/* ---- context: per-thread scratch (replaces the reference's threadprivate descriptors) ---- */
+typedef struct {
+    co_plancache pc;
+    co_stats     st;
+    int          fullbox;     /* 1: always use the full-grid box (GPU convention); 0: reference bbox rule */
+} co_ctx;
+
+co_ctx *co_ctx_new(void);
+void    co_ctx_free(co_ctx *cx);
+
+/* ---- gridfunc (co_gridfunc.c) ---- */
+void   co_eldiv_init(co_eldiv *e, int mx, int my);
+void   co_eldiv_free(co_eldiv *e);
+void   co_areas(co_eldiv *e);
+
+/* ---- coefficients (co_inflcf.c) ---- */
+void   co_combin_mater(co_mater *m);
+void   co_inflcf_init(co_inflcf *c, int mx, int my, double dx, double dy);
+void   co_inflcf_free(co_inflcf *c);
+void   co_inflcf_mater(co_inflcf *c, const co_mater *m);
+void   co_elascf_pcwcns(double akv, double nuv, int mx, int my, double dx, double dy, double xshft, double yshft,
+                        co_inflcf *cs);
+/* sgencr for elastic materials (M=0), C=2: cs, cv, csv (+ ms allocated). is_roll: T=2,3 */
+void   co_sgencr(const co_mater *m, int mx, int my, double dx, double dy, int is_roll, double chi, double dq,
+                 co_inflcf *cs, co_inflcf *cv, co_inflcf *csv, co_inflcf *ms);
+
+/* ---- influence product (co_aijpj.c) ---- */
+int    co_opt_fft_size(int n);
+double co_aijpj(int ii, int ik, const double *p, const co_eldiv *pel, int jkarg, const co_inflcf *c);
+void   co_vecaijpj(co_ctx *cx, const co_eldiv *igs, int iigs, double *u, int ikarg, const double *p,
+                   const co_eldiv *pel, int jkarg, co_inflcf *c);
+void   co_vecaijpj_direct(const co_eldiv *igs, int iigs, double *u, int ikarg, const double *p,
+                   const co_eldiv *pel, int jkarg, const co_inflcf *c);
+void   co_fft_makeprec(co_ctx *cx, int ik, co_inflcf *c, int jk, co_inflcf *m);
+
+/* ---- normal problem (co_norm.c) ---- */
+typedef struct {
+    int    maxgs, maxin, maxnr, maxout;
+    double eps;
+} co_solv;
+
+typedef struct {
+    int    itcg;       /* total CG iterations */
+    int    itnorm;     /* NORM iterations (-1: maxin reached) */
+    int    diverged;   /* normcg hit its abort_run condition */
+} co_norm_info;
+
+int    co_normcg(co_ctx *cx, int ic_norm, int npot, double dxdy, int use_fftprec, int maxcg, double eps,
+                 co_inflcf *cs, co_inflcf *ms, const double *hstot, double *pen, double fntrue,
+                 co_eldiv *igs, double *ps, int *itcg, double *err);
+void   co_snorm(co_ctx *cx, int ic_norm, int mx, int my, double dxdy, const co_solv *solv, const double *hs,
+                co_inflcf *cs, co_inflcf *ms, double *pen, double *fntrue, co_eldiv *igs, double *ps,
+                co_norm_info *info);
+
+/* ---- solver inputs (co_sdis.c) ---- */
+void   co_grid_coords(int mx, int my, double xl, double yl, double dx, double dy, double *x, double *y);
+void   co_set_norm_rhs(int ibase, int iplan, int npot, const double *x, const double *y, int nn,
+                       const double *prmudf, const double *prmpln, double *hs_n);
+void   co_eldiv0(int ic_norm, int mx, int my, double dx, double dy, int ibase, const double *prmudf,
+                 const co_mater *m, double fntrue, double *pen, const double *hs_n, co_eldiv *igs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

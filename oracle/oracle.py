@@ -1,0 +1,196 @@
+"""ctypes loader for the ORACLE (test infrastructure, not product code).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+Builds oracle/_build/libcontact_oracle.so on demand with the committed Makefile.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libcontact_oracle.so")
+_lib = None
+
+c_int_p = C.POINTER(C.c_int)
+c_dbl_p = C.POINTER(C.c_double)
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h")) or f == "Makefile"]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"], stdout=subprocess.DEVNULL)
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.co_opt_fft_size.restype = C.c_int
+        _lib.co_ctx_new.restype = C.c_void_p
+    return _lib
+
+
+def _d(a):
+    return a.ctypes.data_as(c_dbl_p)
+
+
+def _i(a):
+    return a.ctypes.data_as(c_int_p)
+
+
+def opt_fft_size(n):
+    return int(lib().co_opt_fft_size(C.c_int(n)))
+
+
+def fft2_r2c(a):
+    """a: (n2, n1) real, x (n1) fastest. Returns (n2, n1//2+1) complex, unscaled forward transform."""
+    L = lib()
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    n2, n1 = a.shape
+    out = np.zeros((n2, n1 // 2 + 1), dtype=np.complex128)
+    pc = (C.c_char * 4096)()
+    L.co_fft2_r2c(C.byref(pc), C.c_int(n1), C.c_int(n2), _d(a), out.ctypes.data_as(C.c_void_p))
+    L.co_plancache_clear(C.byref(pc))
+    return out
+
+
+def fft2_c2r(A, n1, scale=1.0):
+    L = lib()
+    A = np.array(A, dtype=np.complex128, order="C")
+    n2 = A.shape[0]
+    out = np.zeros((n2, n1), dtype=np.float64)
+    pc = (C.c_char * 4096)()
+    L.co_fft2_c2r(C.byref(pc), C.c_int(n1), C.c_int(n2), A.ctypes.data_as(C.c_void_p), _d(out), C.c_double(scale))
+    L.co_plancache_clear(C.byref(pc))
+    return out
+
+
+class Inflcf(C.Structure):
+    _fields_ = [("cf_mx", C.c_int), ("cf_my", C.c_int), ("cf", c_dbl_p),
+                ("dx", C.c_double), ("dy", C.c_double), ("dq", C.c_double),
+                ("nt_cpl", C.c_int), ("ga", C.c_double), ("ga_inv", C.c_double),
+                ("use_3bl", C.c_int), ("use_flxz", C.c_int), ("flx_3bl", C.c_double), ("flx_z", C.c_double),
+                ("fft_ok", C.c_int * 9), ("fft_mx", C.c_int), ("fft_my", C.c_int),
+                ("fft_cf", C.c_void_p * 9), ("fft_len", C.c_long), ("n_cfft", C.c_long)]
+
+    def block(self, ik, jk):
+        """numpy view of cf(-mx:mx-1, -my:my-1, ik, jk) as array [iy+my, ix+mx]."""
+        n = 4 * self.cf_mx * self.cf_my
+        arr = np.ctypeslib.as_array(self.cf, shape=(9 * n,))
+        b = arr[((jk - 1) * 3 + (ik - 1)) * n:((jk - 1) * 3 + ik) * n]
+        return b.reshape(2 * self.cf_my, 2 * self.cf_mx)
+
+
+class Mater(C.Structure):
+    _fields_ = [("gg", C.c_double * 2), ("poiss", C.c_double * 2),
+                ("ga", C.c_double), ("nu", C.c_double), ("ak", C.c_double)]
+
+
+class Eldiv(C.Structure):
+    _fields_ = [("mx", C.c_int), ("my", C.c_int), ("el", c_int_p), ("row1st", c_int_p), ("rowlst", c_int_p),
+                ("ixmin", C.c_int), ("ixmax", C.c_int), ("iymin", C.c_int), ("iymax", C.c_int)]
+
+
+def mater(gg=(82000.0, 82000.0), poiss=(0.28, 0.28)):
+    m = Mater()
+    m.gg[0], m.gg[1] = gg
+    m.poiss[0], m.poiss[1] = poiss
+    lib().co_combin_mater(C.byref(m))
+    return m
+
+
+def sgencr(m, mx, my, dx, dy, is_roll=False, chi=0.0, dq=1.0):
+    """Returns (cs, cv, csv, ms) Inflcf structures (caller keeps them alive; free with inflcf_free)."""
+    cs, cv, csv, ms = Inflcf(), Inflcf(), Inflcf(), Inflcf()
+    lib().co_sgencr(C.byref(m), C.c_int(mx), C.c_int(my), C.c_double(dx), C.c_double(dy), C.c_int(int(is_roll)),
+                    C.c_double(chi), C.c_double(dq), C.byref(cs), C.byref(cv), C.byref(csv), C.byref(ms))
+    return cs, cv, csv, ms
+
+
+def inflcf_free(*cs):
+    for c in cs:
+        lib().co_inflcf_free(C.byref(c))
+
+
+class Ctx:
+    def __init__(self, fullbox=False):
+        self.p = C.c_void_p(lib().co_ctx_new())
+        # co_ctx layout: plancache (int + pad + 24 ptrs), stats (2 long, 2 double), int fullbox
+        self._set_fullbox(fullbox)
+
+    def _set_fullbox(self, v):
+        off = 8 + 8 * 24 + 32
+        C.c_int.from_address(self.p.value + off).value = int(v)
+
+    def stats(self):
+        off = 8 + 8 * 24
+        n_prod = C.c_long.from_address(self.p.value + off).value
+        n_rowsum = C.c_long.from_address(self.p.value + off + 8).value
+        ab = C.c_double.from_address(self.p.value + off + 16).value
+        af = C.c_double.from_address(self.p.value + off + 24).value
+        return dict(n_prod=n_prod, n_rowsum=n_rowsum, alg_bytes=ab, alg_flops=af)
+
+    def close(self):
+        if self.p:
+            lib().co_ctx_free(self.p)
+            self.p = None
+
+    def __del__(self):
+        self.close()
+
+
+class EldivBuf:
+    """Owns an element division; el is a numpy int32 array of (npot,)."""
+
+    def __init__(self, mx, my, el=None):
+        self.mx, self.my = mx, my
+        self.el = np.zeros(mx * my, dtype=np.int32) if el is None else np.ascontiguousarray(el, dtype=np.int32).copy()
+        self.row1st = np.zeros(my, dtype=np.int32)
+        self.rowlst = np.zeros(my, dtype=np.int32)
+        self.s = Eldiv(mx, my, _i(self.el), _i(self.row1st), _i(self.rowlst), mx, 1, my, 1)
+        self.areas()
+
+    def areas(self):
+        lib().co_areas(C.byref(self.s))
+
+
+def vecaijpj(ctx, igs, iigs, u, ikarg, p, jkarg, c, pel=None):
+    """u, p: (3, npot) float64 arrays (column ik-1 = direction ik)."""
+    pel = igs if pel is None else pel
+    lib().co_vecaijpj(ctx.p, C.byref(igs.s), C.c_int(iigs), _d(u), C.c_int(ikarg), _d(p), C.byref(pel.s),
+                      C.c_int(jkarg), C.byref(c))
+
+
+def vecaijpj_direct(igs, iigs, u, ikarg, p, jkarg, c, pel=None):
+    pel = igs if pel is None else pel
+    lib().co_vecaijpj_direct(C.byref(igs.s), C.c_int(iigs), _d(u), C.c_int(ikarg), _d(p), C.byref(pel.s),
+                             C.c_int(jkarg), C.byref(c))
+
+
+def fft_makeprec(ctx, ik, c, jk, m):
+    lib().co_fft_makeprec(ctx.p, C.c_int(ik), C.byref(c), C.c_int(jk), C.byref(m))
+
+
+def norm_case(mx, my, xl, yl, dx, dy, gg, poiss, ibase, prmudf, ic_norm, pen=0.0, fn=0.0,
+              maxgs=999, maxin=20, eps=1e-5, fullbox=False, nn=0):
+    """One module-3 normal-contact case (T=0, IPOTCN=1, I=0). Returns dict."""
+    npot = mx * my
+    prm = np.ascontiguousarray(prmudf, dtype=np.float64)
+    el = np.zeros(npot, dtype=np.int32)
+    pn = np.zeros(npot, dtype=np.float64)
+    pen_o, fn_o = C.c_double(), C.c_double()
+    itcg, itnorm = C.c_int(), C.c_int()
+    stats = np.zeros(4)
+    L = lib()
+    L.co_norm_case.restype = C.c_int
+    ierr = L.co_norm_case(C.c_int(mx), C.c_int(my), C.c_double(xl), C.c_double(yl), C.c_double(dx), C.c_double(dy),
+                          C.c_double(gg[0]), C.c_double(gg[1]), C.c_double(poiss[0]), C.c_double(poiss[1]),
+                          C.c_int(ibase), C.c_int(nn), _d(prm), C.c_int(ic_norm), C.c_double(pen), C.c_double(fn),
+                          C.c_int(maxgs), C.c_int(maxin), C.c_double(eps), C.c_int(int(fullbox)),
+                          _i(el), _d(pn), C.byref(pen_o), C.byref(fn_o), C.byref(itcg), C.byref(itnorm), _d(stats))
+    return dict(ierror=ierr, el=el, pn=pn, pen=pen_o.value, fn=fn_o.value, itcg=itcg.value, itnorm=itnorm.value,
+                n_prod=int(stats[0]), n_rowsum=int(stats[1]), alg_bytes=stats[2], alg_flops=stats[3])

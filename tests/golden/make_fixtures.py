@@ -1,0 +1,66 @@
+"""Generate golden fixtures from the reference tree (/root/reference, only available in the build container).
+
+Run once here; the outputs are committed so that nothing under tests/, smoke() or bench.py reads /root/reference
+at run time.  Sources: perfc_test/norm_problm_1p.inp (IBASE=2 height table of the Manchester-benchmark right
+wheel at 6.2 mm, used by the whole perf suite), perfc_test/get_times.ref_out (iteration counts),
+examples/cattaneo.ref_out (element picture, statistics).
+"""
+import json
+import os
+import re
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def mbench_profile():
+    lines = open(os.path.join(REF, "perfc_test/norm_problm_1p.inp")).read().splitlines()
+    i0 = next(i for i, l in enumerate(lines) if "NN, XM" in l)
+    hdr = lines[i0].split("%")[0].split()
+    nn, xm, rm, y1, dy1 = int(hdr[0]), float(hdr[1]), float(hdr[2]), float(hdr[3]), float(hdr[4])
+    vals = []
+    for l in lines[i0 + 1:]:
+        t = l.split("%")[0].split()
+        if not t:
+            break
+        vals += [float(v) for v in t]
+        if len(vals) >= nn:
+            break
+    assert len(vals) == nn
+    return dict(nn=nn, xm=xm, rm=rm, y1=y1, dy1=dy1, heights=vals, pen=0.02084,
+                source="perfc_test/norm_problm_1p.inp:16-71")
+
+
+def get_times():
+    out = {}
+    for l in open(os.path.join(REF, "perfc_test/get_times.ref_out")):
+        m = re.match(r"\s*(\w+)\s*:\s*ncon=\s*(\d+), ItCG=\s*(\d+)", l)
+        if m:
+            out[m.group(1)] = dict(ncon=int(m.group(2)), itcg=int(m.group(3)))
+        m = re.match(r"\s*(\w+)\s*:\s*nslp=\s*(\d+), ItGS=\s*(\d+)", l)
+        if m:
+            out[m.group(1)] = dict(nslp=int(m.group(2)), itgs=int(m.group(3)))
+    return out
+
+
+def cattaneo():
+    txt = open(os.path.join(REF, "examples/cattaneo.ref_out")).read().splitlines()
+    pics = []
+    i = 0
+    while i < len(txt):
+        if "FORM OF THE CONTACT" in txt[i]:
+            rows = []
+            i += 1
+            while re.match(r"\s+\d+\s+[o.*S|]", txt[i]):
+                rows.append(txt[i].split()[1:])
+                i += 1
+            pics.append(rows[::-1])     # row iy=1 first
+        i += 1
+    return dict(pictures=pics, source="examples/cattaneo.ref_out")
+
+
+if __name__ == "__main__":
+    json.dump(mbench_profile(), open(os.path.join(HERE, "mbench_profile.json"), "w"))
+    json.dump(get_times(), open(os.path.join(HERE, "get_times.json"), "w"), indent=1)
+    json.dump(cattaneo(), open(os.path.join(HERE, "cattaneo_pictures.json"), "w"))
+    print("fixtures written")
