@@ -1,0 +1,728 @@
+// api_cntc.cuh -- the reference's cntc_* / subs_* C-ABI for module-3 contact problems, backed by the B200 engine.
+//
+// State model as in the reference (/root/reference/src/m_caddon_data.f90:89-225): result elements ire in [1,999]
+// are created lazily on first touch, each holds contact problems icp in [1,9]; a case is set-calls ->
+// cntc_calculate -> get-calls; state persists between cases.  Units handling follows cntc_select_units
+// (m_global_data.f90:463-526).  Control digits outside the B200 hot-path scope are rejected with an error code
+// (never abort): see DESIGN.md "scope".
+#pragma once
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <memory>
+#include "api_lowlevel.cuh"
+
+namespace cb200 {
+
+// magic numbers of /root/reference/src/caddon_flags.inc:13-178 (interface constants)
+enum {
+    CNTC_if_units = 1933, CNTC_un_cntc = 1934, CNTC_un_spck = 1935, CNTC_un_si = 1936, CNTC_un_imper = 1937,
+    CNTC_ic_config = 1967, CNTC_ic_pvtime = 1970, CNTC_ic_bound = 1971, CNTC_ic_tang = 1972, CNTC_ic_norm = 1973,
+    CNTC_ic_force = 1974, CNTC_ic_frclaw = 1976, CNTC_ic_discns = 1977, CNTC_ic_inflcf = 1978, CNTC_ic_mater = 1979,
+    CNTC_ic_exrhs = 1980, CNTC_ic_xflow = 1981, CNTC_ic_heat = 1982, CNTC_ic_iestim = 1983, CNTC_ic_output = 1984,
+    CNTC_ic_flow = 1985, CNTC_ic_return = 1986, CNTC_ic_matfil = 1987, CNTC_ic_sens = 1988, CNTC_ic_ifmeth = 1989,
+    CNTC_ic_ifvari = 1990, CNTC_ic_sbsout = 1991, CNTC_ic_sbsfil = 1992, CNTC_ic_npomax = 1993,
+    CNTC_if_idebug = 2000, CNTC_if_licdbg = 2001, CNTC_if_wrtinp = 2002, CNTC_if_openmp = 2003, CNTC_if_timers = 2004,
+    CNTC_if_ncase = 2005,
+    CNTC_fld_h = 1, CNTC_fld_mu = 2, CNTC_fld_px = 3, CNTC_fld_py = 4, CNTC_fld_pn = 5, CNTC_fld_ux = 7, CNTC_fld_uy = 8,
+    CNTC_fld_un = 9, CNTC_fld_taucrt = 11, CNTC_fld_uplsx = 12, CNTC_fld_uplsy = 13, CNTC_fld_sx = 15, CNTC_fld_sy = 16,
+    CNTC_fld_temp1 = 20, CNTC_fld_temp2 = 21, CNTC_fld_wx = 22, CNTC_fld_wy = 23,
+    CNTC_err_allow = -12, CNTC_err_norm = -27, CNTC_err_tang = -28, CNTC_err_icp = -31, CNTC_err_discr = -34,
+    CNTC_err_input = -39, CNTC_err_other = -99
+};
+
+struct Scaling { int units = CNTC_un_cntc; double len = 1, area = 1, forc = 1, veloc = 1, angle = 1, body = 1; };
+
+struct Problem {
+    // control digits (t_ic, m_hierarch_data.f90:134-409), defaults of ic_init for the library
+    int pvtime = 2, bound = 0, tang = 0, norm = 0, force3 = 0, stress = 0;
+    int frclaw = 0, discns = 2, gencr = 2, mater = 0, rznorm = 2, rztang = 0;
+    int gausei = 0, iestim = 0, matfil = 0, output = 0, flow = 0, ret = 1, sens = 0, wrtinp = 0;
+    Scaling scl;
+    Material mat = { { 82000.0, 82000.0 }, { 0.28, 0.28 }, 0, 0, 0 };
+    // potential contact (t_potcon)
+    int ipotcn = 1, mx = 1, my = 1;
+    double xl = 0, yl = 0, dx = 1, dy = 1, xh = 0, yh = 0, xc1 = 0, yc1 = 0, xcm = 0, ycm = 0;
+    // hertz
+    double hz_aa = 0, hz_bb = 0, hz_a1 = 0, hz_b1 = 0, hz_aob = 0, hz_scale = 1;
+    // geometry
+    int ibase = 1, iplan = 1, nn = 0;
+    std::vector<double> prmudf = std::vector<double>(10, 0.0);
+    // kinematics
+    double pen = 0, fntrue = 0, cksi = 0, ceta = 0, cphi = 0, fxrel = 0, fyrel = 0, chi = 0, dq = 1, veloc = 1, dt = 1;
+    // friction (L = 0)
+    double fstat = 0.3, fkin = 0.3;
+    // solver settings (solv_init, m_hierarch_data.f90:1722-1751)
+    int maxgs = 999, maxin = 20, maxnr = 25, maxout = 1;
+    double eps = 1e-5;
+    // results
+    int ncase = 0, itnorm = 0, ittang = 0, itcg = 0, ncon = 0, nadh = 0, nslip = 0, status = 0;
+    std::vector<int> el;
+    std::vector<double> ps, us, hs;      // [3][npot]
+    double fcntc[3] = { 0, 0, 0 }, mztrue = 0;
+    double t_wall = 0, t_cpu = 0;
+    bool solved = false;
+    // subsurface blocks
+    struct SubsBlock { int isubs = 0; std::vector<double> x, y, z; std::vector<double> table; int nx = 0, ny = 0, nz = 0; };
+    std::map<int, SubsBlock> subs;
+};
+
+struct ResultElement { int imodul = 3; std::map<int, std::unique_ptr<Problem>> cps; };
+
+struct Registry {
+    std::mutex mu;
+    std::map<int, std::unique_ptr<ResultElement>> res;
+    int idebug = 1;
+};
+
+inline Registry &registry() { static Registry r; return r; }
+
+// cntc_activate (m_caddon_data.f90:89-225): lazily create; error codes -101.. for invalid ids
+inline Problem *activate(int ire, int icp, int *ierror)
+{
+    Registry &R = registry();
+    if (ierror) *ierror = 0;
+    if (ire < 1 || ire > 999) { if (ierror) *ierror = -101; last_error() = "invalid result element id"; return nullptr; }
+    if (icp < 1 || icp > 9) { if (ierror) *ierror = CNTC_err_icp; last_error() = "invalid contact problem id (module 1, icp=-1, is outside the hot-path scope)"; return nullptr; }
+    std::lock_guard<std::mutex> lk(R.mu);
+    auto &re = R.res[ire];
+    if (!re) re.reset(new ResultElement());
+    auto &cp = re->cps[icp];
+    if (!cp) cp.reset(new Problem());
+    return cp.get();
+}
+
+inline void select_units(Scaling &s, int iunits)
+{   // m_global_data.f90:463-526
+    if (iunits == CNTC_un_cntc || iunits == CNTC_un_imper) { s = Scaling(); s.units = iunits; }
+    else if (iunits == CNTC_un_spck) { s.units = iunits; s.len = 1e3; s.area = 1e6; s.forc = 1; s.veloc = 1e3; s.angle = 1; s.body = -1; }
+    else if (iunits == CNTC_un_si) { s.units = iunits; s.len = 1e3; s.area = 1e6; s.forc = 1; s.veloc = 1e3; s.angle = 1; s.body = 1; }
+}
+
+inline void potcon_fill(Problem &p)
+{   // m_hierarch_data.f90:1801-1859
+    const int t = p.ipotcn;
+    if (t == 2) { p.dx = (p.xh - p.xl) / p.mx; p.dy = (p.yh - p.yl) / p.my; }
+    else if (t == 4) { p.dx = (p.xcm - p.xc1) / std::max(1, p.mx - 1); p.dy = (p.ycm - p.yc1) / std::max(1, p.my - 1); }
+    if (t == 3 || t == 4) { p.xl = p.xc1 - 0.5 * p.dx; p.yl = p.yc1 - 0.5 * p.dy; }
+    else { p.xc1 = p.xl + 0.5 * p.dx; p.yc1 = p.yl + 0.5 * p.dy; }
+    if (t == 1 || t == 3 || t == 4) { p.xh = p.xl + p.mx * p.dx; p.yh = p.yl + p.my * p.dy; }
+    if (t >= 1 && t <= 3) { p.xcm = p.xc1 + (p.mx - 1) * p.dx; p.ycm = p.yc1 + (p.my - 1) * p.dy; }
+}
+
+// ---- solver inputs on the host: set_norm_rhs (m_sdis.f90:321-494), eldiv0 (m_sdis.f90:818-1007) ----
+inline void undeformed_distance(const Problem &p, std::vector<double> &h)
+{
+    const int npot = p.mx * p.my;
+    h.assign(npot, 0.0);
+    const double *b = p.prmudf.data();
+    for (int iy = 0; iy < p.my; iy++)
+        for (int ix = 0; ix < p.mx; ix++) {
+            const double x = p.xc1 + ix * p.dx, y = p.yc1 + iy * p.dy;
+            const int ii = iy * p.mx + ix;
+            double v = 0.0;
+            if (p.ibase == 1) {
+                v = b[0] * x * x + b[1] * x * y + b[2] * y * y + b[3] * x + b[4] * y + b[5];
+            } else if (p.ibase == 2) {
+                const double xm = b[1], rm = b[2], y1 = b[3], dy1 = b[4], yn = y1 + (p.nn - 1) * dy1;
+                int mleft; double yleft;
+                if (y < y1) { yleft = y1; mleft = 1; }
+                else if (y >= yn) { yleft = yn - dy1; mleft = p.nn - 1; }
+                else { mleft = (int) ((y - y1) / dy1) + 1; yleft = y1 + (mleft - 1) * dy1; }
+                mleft += 5;
+                const double rc = (b[mleft] - b[mleft - 1]) / dy1;
+                v = b[mleft - 1] + rc * (y - yleft);
+                v = v + (x - xm) * (x - xm) / (2.0 * rm);
+            } else if (p.ibase == 3) {
+                v = b[0] * sin(b[1] * (x - b[2])) - b[3] * sin(b[4] * (x - b[5])) + x * x / b[6] + y * y / b[7];
+            } else if (p.ibase == 9) {
+                v = b[ii];
+            }
+            h[ii] = v;
+        }
+}
+
+inline void initial_eldiv(Problem &p, const std::vector<double> &h, std::vector<int> &el, double &pen)
+{
+    const int npot = p.mx * p.my;
+    const double facpen = (double) 0.60f, reltol = (double) 0.01f;      // REAL(4) literals, m_sdis.f90:832
+    const double dxdy = p.dx * p.dy, fnscal = p.fntrue / p.mat.ga;
+    const double pi = 3.14159265358979323846;
+    double hsmin = h[0];
+    for (int i = 1; i < npot; i++) if (h[i] < hsmin) hsmin = h[i];
+    double pentru = pen - hsmin;
+    auto count_below = [&](double thr) { int c = 0; for (int i = 0; i < npot; i++) if (h[i] - hsmin < thr) c++; return c; };
+    if (p.norm == 1 && p.my == 1) {
+        double rm = 1.0;
+        if (p.ibase == 1) rm = 0.5 / std::max(1e-6, p.prmudf[0]);
+        else if (p.ibase == 2) rm = p.prmudf[2];
+        else if (p.ibase == 3) rm = 0.5 * p.prmudf[6];
+        const double cdy = 0.35 - 0.05 * (log(p.dy) - log(200.0));
+        pentru = pow(fnscal / p.dy * (1.0 - p.mat.nu) / 0.6 / cdy / pow(rm, (double) 0.1f), (double) 0.926f);
+        pen = pentru + hsmin;
+    } else if (p.norm == 1) {
+        const double fac = 0.75 * sqrt(pi) * (1.0 - p.mat.nu);
+        double penmin = 0.0, fnmin = 0.0, penmax = fac * fnscal / sqrt(dxdy);
+        double fnmax = penmax * sqrt(dxdy * count_below(facpen * penmax)) / fac;
+        for (int iter = 0; iter < 50 && fabs(fnmax - fnmin) > reltol * fnscal; iter++) {
+            const double penmid = 0.5 * (penmax + penmin);
+            const double fnmid = penmid * sqrt(dxdy * count_below(facpen * penmid)) / fac;
+            if (fnmid < fnscal) { penmin = penmid; fnmin = fnmid; } else { penmax = penmid; fnmax = fnmid; }
+        }
+        pentru = penmax;
+        pen = pentru + hsmin;
+    }
+    el.resize(npot);
+    for (int i = 0; i < npot; i++) el[i] = (h[i] - hsmin < facpen * pentru) ? 1 : 0;
+    for (int i = 0; i < npot; i++) if (h[i] > (double) 1e29f) el[i] = 0;          // m_sdis.f90:748-750
+}
+
+inline int count_at_boundary(const Problem &p)
+{   // eldiv_count_atbnd(igs, 0), m_gridfunc.f90:437-490
+    const int nx = p.mx, ny = p.my;
+    int cnt = 0;
+    const int iystep = (nx >= 3) ? 1 : std::max(1, ny - 1);
+    for (int iy = 1; iy <= ny; iy += iystep) {
+        const int ixstep = (ny >= 3 && (iy == 1 || iy == ny)) ? 1 : std::max(1, nx - 1);
+        for (int ix = 1; ix <= nx; ix += ixstep) if (p.el[(iy - 1) * nx + ix - 1] >= 1) cnt++;
+    }
+    return cnt;
+}
+
+// check_case / scope check: returns 0 or an error code
+inline int check_scope(const Problem &p)
+{
+    if (p.tang != 0) { last_error() = "T-digit: tangential problems are not yet served by the B200 path"; return CNTC_err_other; }
+    if (p.mater != 0) { last_error() = "M-digit: only the elastic half-space (M=0) is in the hot-path scope"; return CNTC_err_other; }
+    if (p.gencr != 2 && p.gencr != 1) { last_error() = "C-digit: only piecewise-constant analytical coefficients (C=2)"; return CNTC_err_other; }
+    if (p.bound != 0) { last_error() = "B-digit: only the full normal problem (B=0)"; return CNTC_err_other; }
+    if (p.ipotcn < 1 || p.ipotcn > 4) { last_error() = "IPOTCN: Hertzian input is not yet served by the B200 path"; return CNTC_err_other; }
+    if (p.iplan != 1) { last_error() = "IPLAN: only the unrestricted planform"; return CNTC_err_other; }
+    if (p.ibase != 1 && p.ibase != 2 && p.ibase != 3 && p.ibase != 9) { last_error() = "invalid IBASE"; return CNTC_err_input; }
+    if (p.ibase == 9 && (int) p.prmudf.size() < p.mx * p.my) { last_error() = "IBASE=9 needs npot values"; return CNTC_err_input; }
+    return 0;
+}
+
+// contac (m_scontc.f90:37-216) for a batch of problems: host set-up, ONE device launch per coefficient class, gather
+inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int> &ierr)
+{
+    const size_t nb = probs.size();
+    ierr.assign(nb, 0);
+    std::map<CoefSet *, std::vector<size_t>> groups;
+    std::vector<std::vector<double>> hs(nb);
+    std::vector<std::vector<int>> el0(nb);
+    std::vector<double> pen0(nb);
+    const auto t0 = std::chrono::steady_clock::now();
+    for (size_t k = 0; k < nb; k++) {
+        Problem &p = *probs[k];
+        p.ncase++;
+        if ((ierr[k] = check_scope(p))) continue;
+        combine_material(p.mat);
+        if (p.ncase <= 1) p.pvtime = 2;                                   // check_case, m_scontc.f90:268-274
+        undeformed_distance(p, hs[k]);
+        const int npot = p.mx * p.my;
+        double pen = p.pen;
+        if (p.iestim == 0 || (int) p.el.size() != npot) {
+            initial_eldiv(p, hs[k], el0[k], pen);
+            p.ps.assign(3 * (size_t) npot, 0.0);
+        } else {
+            el0[k] = p.el;                                                // I>=1: keep element division and tractions
+        }
+        pen0[k] = pen;
+        if (p.ret > 1) { ierr[k] = 0; continue; }                        // R=2,3: checks only
+        CoefSet *cs = nullptr;
+        int rc = get_coefset(p.mx, p.my, p.dx, p.dy, p.mat, 0, 0.0, 1.0, 0, &cs);
+        if (rc) { ierr[k] = rc; continue; }
+        if (!cs->hp.fits) { last_error() = "grid too large for the single-CTA solver"; ierr[k] = CNTC_err_discr; continue; }
+        groups[cs].push_back(k);
+    }
+    for (auto &g : groups) {
+        CoefSet &cs = *g.first;
+        const std::vector<size_t> &idx = g.second;
+        const int nc = (int) idx.size(), npot = cs.mx * cs.my;
+        // all cases of a launch share ic_norm / solver settings: split further if they differ
+        std::map<std::tuple<int, int, int, double>, std::vector<size_t>> sub;
+        for (size_t k : idx) sub[std::make_tuple(probs[k]->norm, probs[k]->maxgs, probs[k]->maxin, probs[k]->eps)].push_back(k);
+        (void) nc;
+        for (auto &s : sub) {
+            const std::vector<size_t> &ks = s.second;
+            const int n = (int) ks.size();
+            std::vector<double> h_hs((size_t) n * npot), h_pn((size_t) n * npot), h_scal((size_t) n * 8, 0.0);
+            std::vector<int> h_el((size_t) n * npot);
+            for (int i = 0; i < n; i++) {
+                const size_t k = ks[i];
+                std::copy(hs[k].begin(), hs[k].end(), h_hs.begin() + (size_t) i * npot);
+                std::copy(el0[k].begin(), el0[k].end(), h_el.begin() + (size_t) i * npot);
+                std::copy(probs[k]->ps.begin() + 2 * (size_t) npot, probs[k]->ps.begin() + 3 * (size_t) npot, h_pn.begin() + (size_t) i * npot);
+                h_scal[i * 8 + 0] = pen0[k]; h_scal[i * 8 + 1] = probs[k]->fntrue;
+            }
+            double *d_hs = nullptr, *d_pn = nullptr, *d_un = nullptr, *d_scal = nullptr; int *d_el = nullptr;
+            int rc = 0;
+            auto fail = [&](int code) { for (size_t k : ks) ierr[k] = code; };
+            if (cudaMalloc(&d_hs, sizeof(double) * n * npot) != cudaSuccess || cudaMalloc(&d_pn, sizeof(double) * n * npot) != cudaSuccess ||
+                cudaMalloc(&d_un, sizeof(double) * n * npot) != cudaSuccess || cudaMalloc(&d_scal, sizeof(double) * n * 8) != cudaSuccess ||
+                cudaMalloc(&d_el, sizeof(int) * n * npot) != cudaSuccess) { last_error() = "device allocation failed"; fail(CNTC_err_other); rc = -1; }
+            if (!rc) {
+                cudaMemcpy(d_hs, h_hs.data(), sizeof(double) * n * npot, cudaMemcpyHostToDevice);
+                cudaMemcpy(d_pn, h_pn.data(), sizeof(double) * n * npot, cudaMemcpyHostToDevice);
+                cudaMemcpy(d_el, h_el.data(), sizeof(int) * n * npot, cudaMemcpyHostToDevice);
+                cudaMemcpy(d_scal, h_scal.data(), sizeof(double) * n * 8, cudaMemcpyHostToDevice);
+                rc = snorm_batch_dev(cs, n, std::get<0>(s.first), std::get<1>(s.first), std::get<2>(s.first), std::get<3>(s.first),
+                                     d_hs, d_el, d_pn, d_un, d_scal, 0);
+                if (rc) fail(rc);
+            }
+            if (!rc) {
+                std::vector<double> h_un((size_t) n * npot);
+                cudaError_t e = cudaMemcpy(h_pn.data(), d_pn, sizeof(double) * n * npot, cudaMemcpyDeviceToHost);
+                if (e == cudaSuccess) e = cudaMemcpy(h_un.data(), d_un, sizeof(double) * n * npot, cudaMemcpyDeviceToHost);
+                if (e == cudaSuccess) e = cudaMemcpy(h_el.data(), d_el, sizeof(int) * n * npot, cudaMemcpyDeviceToHost);
+                if (e == cudaSuccess) e = cudaMemcpy(h_scal.data(), d_scal, sizeof(double) * n * 8, cudaMemcpyDeviceToHost);
+                if (e != cudaSuccess) { last_error() = cudaGetErrorString(e); fail(CNTC_err_other); }
+                else for (int i = 0; i < n; i++) {
+                    Problem &p = *probs[ks[i]];
+                    p.el.assign(h_el.begin() + (size_t) i * npot, h_el.begin() + (size_t) (i + 1) * npot);
+                    p.ps.assign(3 * (size_t) npot, 0.0);
+                    p.us.assign(3 * (size_t) npot, 0.0);
+                    std::copy(h_pn.begin() + (size_t) i * npot, h_pn.begin() + (size_t) (i + 1) * npot, p.ps.begin() + 2 * (size_t) npot);
+                    std::copy(h_un.begin() + (size_t) i * npot, h_un.begin() + (size_t) (i + 1) * npot, p.us.begin() + 2 * (size_t) npot);
+                    p.hs.assign(3 * (size_t) npot, 0.0);
+                    std::copy(hs[ks[i]].begin(), hs[ks[i]].end(), p.hs.begin() + 2 * (size_t) npot);
+                    const double *sc = &h_scal[i * 8];
+                    p.pen = sc[0]; p.fntrue = sc[1]; p.itcg = (int) sc[2]; p.itnorm = (int) sc[3]; p.ncon = (int) sc[4];
+                    p.status = (int) sc[5]; p.ittang = 0; p.nadh = p.ncon; p.nslip = 0;
+                    p.fcntc[0] = 0.0; p.fcntc[1] = 0.0; p.fcntc[2] = p.fntrue; p.mztrue = 0.0;
+                    p.solved = true;
+                    if (p.itnorm < 0 || (p.status & 1)) ierr[ks[i]] = CNTC_err_norm;
+                    else ierr[ks[i]] = count_at_boundary(p);              // contact_addon.f90:3885-3891
+                }
+            }
+            cudaFree(d_hs); cudaFree(d_pn); cudaFree(d_un); cudaFree(d_scal); cudaFree(d_el);
+        }
+    }
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    for (size_t k = 0; k < nb; k++) { probs[k]->t_wall += dt / (double) nb; probs[k]->t_cpu += dt / (double) nb; }
+}
+
+}  // namespace cb200
+
+extern "C" {
+
+void cntc_initializefirst(int *ifcver, int *ierror, int *ioutput, const char *, const char *, const char *, int *, int *, int *)
+{
+    (void) ioutput;
+    if (ifcver) *ifcver = 2400;                 // library interface version reported by the reference family
+    if (ierror) *ierror = 0;
+}
+
+void cntc_initializefirst_new(int *ifcver, int *ierror, int *ioutput, const char *a, const char *b, const char *c, int *la, int *lb, int *lc)
+{ cntc_initializefirst(ifcver, ierror, ioutput, a, b, c, la, lb, lc); }
+
+void cntc_initialize(int *ire, int *imodul, int *ifcver, int *ierror, const char *, int *)
+{
+    if (ifcver) *ifcver = 2400;
+    if (ierror) *ierror = 0;
+    if (imodul && *imodul != 3) { if (ierror) *ierror = CNTC_err_other; last_error() = "only module 3 (contact on a given grid) is in the hot-path scope"; return; }
+    Registry &R = registry();
+    if (*ire < 1 || *ire > 999) { if (ierror) *ierror = -101; return; }
+    std::lock_guard<std::mutex> lk(R.mu);
+    auto &re = R.res[*ire];
+    if (!re) re.reset(new ResultElement());
+}
+
+void cntc_setglobalflags(int *lenflg, int *params, int *values)
+{
+    for (int i = 0; i < *lenflg; i++) if (params[i] == CNTC_if_idebug) registry().idebug = values[i];
+}
+
+void cntc_setflags(int *ire, int *icp, int *lenflg, int *params, int *values)
+{
+    int ierr; Problem *p = activate(*ire, *icp, &ierr);
+    if (!p) return;
+    auto clampi = [](int v, int lo, int hi) { return std::max(lo, std::min(hi, v)); };
+    for (int i = 0; i < *lenflg; i++) {
+        const int c = params[i], v = values[i];
+        if (c == 0) continue;
+        else if (c == CNTC_if_units) select_units(p->scl, v);
+        else if (c == CNTC_ic_pvtime) p->pvtime = clampi(v, 0, 3);
+        else if (c == CNTC_ic_bound) p->bound = clampi(v, 0, 6);
+        else if (c == CNTC_ic_tang) p->tang = clampi(v, 0, 3);
+        else if (c == CNTC_ic_norm) p->norm = clampi(v, 0, 1);
+        else if (c == CNTC_ic_force) p->force3 = clampi(v, 0, 2);
+        else if (c == CNTC_ic_sens) p->sens = clampi(v, 0, 3);
+        else if (c == CNTC_ic_inflcf) { if (v >= 0 && v <= 4) p->gencr = v; }
+        else if (c == CNTC_ic_exrhs) p->rztang = clampi(v, 0, 3);
+        else if (c == CNTC_ic_iestim) p->iestim = clampi(v, 0, 3);
+        else if (c == CNTC_ic_matfil) p->matfil = (v < 0 || v > 2) ? 0 : v;
+        else if (c == CNTC_ic_output) p->output = clampi(v, 0, 5);
+        else if (c == CNTC_ic_flow) p->flow = clampi(v, 0, 9);
+        else if (c == CNTC_ic_return) p->ret = clampi(v, 0, 3);
+        else if (c == CNTC_if_wrtinp) p->wrtinp = v;
+        else if (c == CNTC_if_ncase) p->ncase = std::max(0, v - 1);
+        else if (c == CNTC_if_idebug) registry().idebug = v;
+        /* other codes (config, discns, npomax, ifmeth, sbsout, ... ) concern module 1 or file output: accepted, ignored */
+    }
+}
+
+void cntc_getflags(int *ire, int *icp, int *lenflg, int *params, int *values)
+{
+    int ierr; Problem *p = activate(*ire, *icp, &ierr);
+    if (!p) return;
+    for (int i = 0; i < *lenflg; i++) {
+        const int c = params[i];
+        int v = 0;
+        if (c == CNTC_if_units) v = p->scl.units; else if (c == CNTC_ic_pvtime) v = p->pvtime;
+        else if (c == CNTC_ic_bound) v = p->bound; else if (c == CNTC_ic_tang) v = p->tang;
+        else if (c == CNTC_ic_norm) v = p->norm; else if (c == CNTC_ic_force) v = p->force3;
+        else if (c == CNTC_ic_frclaw) v = p->frclaw; else if (c == CNTC_ic_discns) v = p->discns;
+        else if (c == CNTC_ic_inflcf) v = p->gencr; else if (c == CNTC_ic_mater) v = p->mater;
+        else if (c == CNTC_ic_exrhs) v = p->rztang; else if (c == CNTC_ic_iestim) v = p->iestim;
+        else if (c == CNTC_ic_output) v = p->output; else if (c == CNTC_ic_flow) v = p->flow;
+        else if (c == CNTC_ic_return) v = p->ret; else if (c == CNTC_ic_matfil) v = p->matfil;
+        else if (c == CNTC_ic_sens) v = p->sens; else if (c == CNTC_if_ncase) v = p->ncase;
+        else if (c == CNTC_if_wrtinp) v = p->wrtinp; else if (c == CNTC_if_idebug) v = registry().idebug;
+        values[i] = v;
+    }
+}
+
+void cntc_setmetadata(int *ire, int *icp, int *, int *, double *) { int e; activate(*ire, *icp, &e); }
+
+void cntc_setsolverflags(int *ire, int *icp, int *gdigit, int *nints, int *iparam, int *nreals, double *rparam)
+{
+    int ierr; Problem *p = activate(*ire, *icp, &ierr);
+    if (!p) return;
+    static const int ni[7] = { 4, 0, 5, 5, 5, 5, 1 }, nr[7] = { 1, 0, 4, 4, 2, 8, 1 };
+    const int g = *gdigit;
+    if (g < 0 || g > 6 || *nints != ni[g] || *nreals != nr[g]) { last_error() = "cntc_setsolverflags: wrong G-digit or parameter count"; return; }
+    if (g >= 0 && g <= 5) p->gausei = g;
+    if (g != 1 && g != 6) {
+        p->eps = std::max(1e-20, rparam[0]);
+        p->maxgs = std::max(1, iparam[0]); p->maxin = std::max(1, iparam[1]);
+        p->maxnr = std::max(1, iparam[2]); p->maxout = std::max(1, iparam[3]);
+    }
+}
+
+void cntc_setmaterialparameters(int *ire, int *icp, int *mdigit, int *nparam, double *rparam)
+{
+    int ierr; Problem *p = activate(*ire, *icp, &ierr);
+    if (!p) return;
+    static const int np[8] = { 4, 8, 8, 7, 8, 7, 4, 4 };
+    if (*mdigit < 0 || *mdigit > 7 || *nparam != np[*mdigit]) { last_error() = "cntc_setmaterialparameters: wrong M-digit or parameter count"; return; }
+    p->mater = *mdigit;
+    p->mat.poiss[0] = rparam[0]; p->mat.poiss[1] = rparam[1];
+    p->mat.gg[0] = rparam[2] * p->scl.forc / p->scl.area;
+    p->mat.gg[1] = rparam[3] * p->scl.forc / p->scl.area;
+}
+
+void cntc_settimestep(int *ire, int *icp, double *dt) { int e; Problem *p = activate(*ire, *icp, &e); if (p) p->dt = *dt; }
+
+void cntc_setreferencevelocity(int *ire, int *icp, double *veloc)
+{ int e; Problem *p = activate(*ire, *icp, &e); if (p) p->veloc = *veloc * p->scl.veloc; }
+
+void cntc_setrollingstepsize(int *ire, int *icp, double *chi, double *dq)
+{ int e; Problem *p = activate(*ire, *icp, &e); if (p) { p->chi = *chi * p->scl.angle; p->dq = *dq * p->scl.len; } }
+
+void cntc_setfrictionmethod(int *ire, int *icp, int *imeth, int *nparam, double *params)
+{
+    int e; Problem *p = activate(*ire, *icp, &e);
+    if (!p) return;
+    p->frclaw = *imeth;
+    if (*imeth == 0 && *nparam >= 2) { p->fstat = params[0]; p->fkin = params[1]; }
+}
+
+void cntc_sethertzcontact(int *ire, int *icp, int *ipotcn, int *nparam, double *prm)
+{
+    int e; Problem *p = activate(*ire, *icp, &e);
+    if (!p) return;
+    const int t = *ipotcn;
+    if (t < -6 || t > -1 || *nparam != (t == -6 ? 6 : 5)) { last_error() = "cntc_sethertzcontact: wrong IPOTCN or parameter count"; return; }
+    p->ipotcn = t;
+    p->mx = std::max(1, (int) lround(prm[0])); p->my = std::max(1, (int) lround(prm[1]));
+    if (t == -3) { p->hz_aa = std::max(1e-6, prm[2]) * p->scl.len; p->hz_bb = std::max(1e-6, prm[3]) * p->scl.len; }
+    else if (t == -2) { p->hz_a1 = std::max(1e-12, prm[2]) / p->scl.len; p->hz_aob = std::max(1e-6, prm[3]); }
+    else if (t == -1) { p->hz_a1 = std::max(1e-12, prm[2]) / p->scl.len; p->hz_b1 = std::max(1e-12, prm[3]) / p->scl.len; }
+    p->hz_scale = std::max(1e-6, prm[4]);
+}
+
+void cntc_setpotcontact(int *ire, int *icp, int *ipotcn, int *nparam, double *prm)
+{
+    int e; Problem *p = activate(*ire, *icp, &e);
+    if (!p) return;
+    const int t = *ipotcn;
+    if (t < 1 || t > 4 || *nparam != 6) { last_error() = "cntc_setpotcontact: wrong IPOTCN or parameter count"; return; }
+    const double L = p->scl.len;
+    p->ipotcn = t;
+    p->mx = std::max(1, (int) lround(prm[0])); p->my = std::max(1, (int) lround(prm[1]));
+    if (t == 1) { p->xl = prm[2] * L; p->yl = prm[3] * L; p->dx = std::max(1e-12, prm[4]) * L; p->dy = std::max(1e-12, prm[5]) * L; }
+    else if (t == 2) { p->xl = prm[2] * L; p->yl = prm[3] * L; p->xh = prm[4] * L; p->yh = prm[5] * L; }
+    else if (t == 3) { p->xc1 = prm[2] * L; p->yc1 = prm[3] * L; p->dx = std::max(1e-12, prm[4]) * L; p->dy = std::max(1e-12, prm[5]) * L; }
+    else { p->xc1 = prm[2] * L; p->yc1 = prm[3] * L; p->xcm = prm[4] * L; p->ycm = prm[5] * L; }
+    potcon_fill(*p);
+}
+
+void cntc_setpenetration(int *ire, int *icp, double *pen)
+{ int e; Problem *p = activate(*ire, *icp, &e); if (p) { p->norm = 0; p->pen = *pen * p->scl.len; } }
+
+void cntc_setnormalforce(int *ire, int *icp, double *fn)
+{ int e; Problem *p = activate(*ire, *icp, &e); if (p) { p->norm = 1; p->fntrue = *fn; } }
+
+void cntc_setundeformeddistc(int *ire, int *icp, int *ibase, int *nparam, double *prm)
+{
+    int e; Problem *p = activate(*ire, *icp, &e);
+    if (!p) return;
+    const double L = p->scl.len;
+    const int b = *ibase, npot = p->mx * p->my;
+    int nn = 0, need;
+    if (b == 2) nn = (int) lround(prm[0]);
+    if (b == 1) need = 6; else if (b == 2) need = 5 + nn; else if (b == 3) need = 8; else if (b == 9) need = npot;
+    else { last_error() = "cntc_setundeformeddistc: invalid IBASE"; return; }
+    if (*nparam != need) { last_error() = "cntc_setundeformeddistc: wrong parameter count"; return; }
+    p->ibase = b;
+    if (b == 1) {
+        p->prmudf.assign(10, 0.0);
+        for (int i = 0; i < 3; i++) p->prmudf[i] = prm[i] / L;
+        p->prmudf[3] = prm[3]; p->prmudf[4] = prm[4]; p->prmudf[5] = prm[5] * L;
+    } else if (b == 2) {
+        p->prmudf.assign(5 + nn, 0.0);
+        p->nn = nn;
+        p->prmudf[0] = nn;
+        for (int i = 1; i < 5 + nn; i++) p->prmudf[i] = prm[i] * L;
+    } else if (b == 3) {
+        p->prmudf.assign(10, 0.0);
+        p->prmudf[0] = prm[0] * L; p->prmudf[1] = prm[1] / L; p->prmudf[2] = prm[2] * L; p->prmudf[3] = prm[3] * L;
+        p->prmudf[4] = prm[4] / L; p->prmudf[5] = prm[5] * L; p->prmudf[6] = prm[6] * L; p->prmudf[7] = prm[7] * L;
+    } else {
+        p->prmudf.assign(npot + 10, 0.0);
+        for (int i = 0; i < npot; i++) p->prmudf[i] = prm[i] * L;
+    }
+}
+
+void cntc_setcreepages(int *ire, int *icp, double *vx, double *vy, double *phi)
+{
+    int e; Problem *p = activate(*ire, *icp, &e);
+    if (!p) return;
+    // contact_addon.f90:2491-2530: shifts [length] for T=1, creepages [-] for T=2,3; sign by body convention
+    const bool shift = (p->tang == 1);
+    p->cksi = *vx * p->scl.body * (shift ? p->scl.len : 1.0);
+    p->ceta = *vy * p->scl.body * (shift ? p->scl.len : 1.0);
+    p->cphi = *phi * p->scl.body * (shift ? p->scl.angle : p->scl.angle / p->scl.len);
+}
+
+void cntc_settangentialforces(int *ire, int *icp, double *fx, double *fy)
+{ int e; Problem *p = activate(*ire, *icp, &e); if (p) { p->fxrel = *fx * p->scl.body; p->fyrel = *fy * p->scl.body; } }
+
+void cntc_calculate(int *ire, int *icp, int *ierror)
+{
+    Problem *p = activate(*ire, *icp, ierror);
+    if (!p) return;
+    std::vector<Problem *> v(1, p);
+    std::vector<int> ie;
+    int rc = engine_init();
+    if (rc) { *ierror = rc; return; }
+    calculate_batch(v, ie);
+    *ierror = ie[0];
+}
+
+void cntc_calculate_batch(int *nre, int *ire, int *icp, int *ierror)
+{
+    std::vector<Problem *> v;
+    std::vector<int> pos;
+    for (int k = 0; k < *nre; k++) {
+        Problem *p = activate(ire[k], *icp, &ierror[k]);
+        if (p) { v.push_back(p); pos.push_back(k); }
+    }
+    int rc = engine_init();
+    if (rc) { for (int k = 0; k < *nre; k++) ierror[k] = rc; return; }
+    std::vector<int> ie;
+    calculate_batch(v, ie);
+    for (size_t i = 0; i < v.size(); i++) ierror[pos[i]] = ie[i];
+}
+
+void cntc_getnumelements(int *ire, int *icp, int *mx, int *my)
+{ int e; Problem *p = activate(*ire, *icp, &e); if (p) { *mx = p->mx; *my = p->my; } }
+
+void cntc_getgriddiscretization(int *ire, int *icp, double *dx, double *dy)
+{ int e; Problem *p = activate(*ire, *icp, &e); if (p) { *dx = p->dx / p->scl.len; *dy = p->dy / p->scl.len; } }
+
+void cntc_getpotcontact(int *ire, int *icp, int *lenarr, double *v)
+{
+    int e; Problem *p = activate(*ire, *icp, &e);
+    if (!p) return;
+    const double L = p->scl.len;
+    const double out[6] = { (double) p->mx, (double) p->my, p->xc1 / L, p->yc1 / L, p->dx / L, p->dy / L };   // contact_addon.f90:5144-5187
+    for (int i = 0; i < *lenarr && i < 6; i++) v[i] = out[i];
+}
+
+void cntc_getpenetration(int *ire, int *icp, double *pen)
+{ int e; Problem *p = activate(*ire, *icp, &e); if (p) *pen = p->pen / p->scl.len; }
+
+void cntc_getcreepages(int *ire, int *icp, double *vx, double *vy, double *phi)
+{
+    int e; Problem *p = activate(*ire, *icp, &e);
+    if (!p) return;
+    const bool shift = (p->tang == 1);
+    *vx = p->cksi * p->scl.body / (shift ? p->scl.len : 1.0);
+    *vy = p->ceta * p->scl.body / (shift ? p->scl.len : 1.0);
+    *phi = p->cphi * p->scl.body / (shift ? p->scl.angle : p->scl.angle / p->scl.len);
+}
+
+void cntc_getcontactforces(int *ire, int *icp, double *fn, double *tx, double *ty, double *mz)
+{
+    int e; Problem *p = activate(*ire, *icp, &e);
+    if (!p) return;
+    *fn = p->fcntc[2]; *tx = p->scl.body * p->fcntc[0]; *ty = p->scl.body * p->fcntc[1];
+    *mz = p->scl.body * p->mztrue / p->scl.len;
+}
+
+void cntc_getcontactpatchareas(int *ire, int *icp, double *carea, double *harea, double *sarea)
+{
+    int e; Problem *p = activate(*ire, *icp, &e);
+    if (!p) return;
+    int nadh = 0, nslip = 0, nplast = 0;
+    for (int v : p->el) { if (v == 1) nadh++; else if (v == 2) nslip++; else if (v == 3) nplast++; }
+    const double dxdy = p->dx * p->dy;
+    *carea = (double) (nadh + nslip + nplast) * dxdy / p->scl.area;
+    *harea = (double) nadh * dxdy / p->scl.area;
+    *sarea = (double) nslip * dxdy / p->scl.area;
+}
+
+void cntc_getelementdivision(int *ire, int *icp, int *lenarr, int *eldiv)
+{
+    int e; Problem *p = activate(*ire, *icp, &e);
+    if (!p) return;
+    for (int i = 0; i < *lenarr && i < (int) p->el.size(); i++) eldiv[i] = p->el[i];
+}
+
+void cntc_getmaximumpressure(int *ire, int *icp, double *pnmax)
+{
+    int e; Problem *p = activate(*ire, *icp, &e);
+    if (!p) return;
+    const int npot = p->mx * p->my;
+    double m = 0.0;
+    if ((int) p->ps.size() == 3 * npot) for (int i = 0; i < npot; i++) m = std::max(m, fabs(p->ps[2 * (size_t) npot + i]));
+    *pnmax = m * p->scl.area;
+}
+
+void cntc_getmaximumtraction(int *ire, int *icp, double *ptmax)
+{
+    int e; Problem *p = activate(*ire, *icp, &e);
+    if (!p) return;
+    const int npot = p->mx * p->my;
+    double m = 0.0;
+    if ((int) p->ps.size() == 3 * npot)
+        for (int i = 0; i < npot; i++) m = std::max(m, p->ps[i] * p->ps[i] + p->ps[npot + i] * p->ps[npot + i]);
+    *ptmax = sqrt(m) * p->scl.area;
+}
+
+void cntc_getfielddata(int *ire, int *icp, int *ifld, int *lenarr, double *fld)
+{
+    int e; Problem *p = activate(*ire, *icp, &e);
+    if (!p) return;
+    const int npot = p->mx * p->my;
+    const std::vector<double> *src = nullptr; int col = 0; double scl = 1.0;
+    const Scaling &s = p->scl;
+    switch (*ifld) {
+    case CNTC_fld_h:  src = &p->hs; col = 2; scl = 1.0 / s.len; break;
+    case CNTC_fld_px: src = &p->ps; col = 0; scl = s.area * s.body; break;
+    case CNTC_fld_py: src = &p->ps; col = 1; scl = s.area * s.body; break;
+    case CNTC_fld_pn: src = &p->ps; col = 2; scl = s.area; break;
+    case CNTC_fld_ux: src = &p->us; col = 0; scl = 1.0 / s.len; break;
+    case CNTC_fld_uy: src = &p->us; col = 1; scl = 1.0 / s.len; break;
+    case CNTC_fld_un: src = &p->us; col = 2; scl = 1.0 / s.len; break;
+    default: break;
+    }
+    for (int i = 0; i < *lenarr && i < npot; i++) {
+        if (*ifld == CNTC_fld_mu) fld[i] = p->fstat;
+        else if (src && (int) src->size() == 3 * npot) fld[i] = scl * (*src)[(size_t) col * npot + i];
+        else fld[i] = 0.0;
+    }
+}
+
+void cntc_gettractions(int *ire, int *icp, int *lenarr, double *pn, double *px, double *py)
+{
+    int f;
+    f = CNTC_fld_pn; cntc_getfielddata(ire, icp, &f, lenarr, pn);
+    f = CNTC_fld_px; cntc_getfielddata(ire, icp, &f, lenarr, px);
+    f = CNTC_fld_py; cntc_getfielddata(ire, icp, &f, lenarr, py);
+}
+
+void cntc_getmicroslip(int *ire, int *icp, int *lenarr, double *sx, double *sy)
+{
+    int f;
+    f = CNTC_fld_sx; cntc_getfielddata(ire, icp, &f, lenarr, sx);
+    f = CNTC_fld_sy; cntc_getfielddata(ire, icp, &f, lenarr, sy);
+}
+
+void cntc_getdisplacements(int *ire, int *icp, int *lenarr, double *un, double *ux, double *uy)
+{
+    int f;
+    f = CNTC_fld_un; cntc_getfielddata(ire, icp, &f, lenarr, un);
+    f = CNTC_fld_ux; cntc_getfielddata(ire, icp, &f, lenarr, ux);
+    f = CNTC_fld_uy; cntc_getfielddata(ire, icp, &f, lenarr, uy);
+}
+
+void cntc_getcalculationtime(int *ire, int *icp, double *tcpu, double *twall)
+{ int e; Problem *p = activate(*ire, *icp, &e); if (p) { *tcpu = p->t_cpu; *twall = p->t_wall; } }
+
+void subs_addblock(int *ire, int *icp, int *iblk, int *isubs, int *nx, int *ny, int *nz, double *xparam, double *yparam, double *zparam)
+{
+    int e; Problem *p = activate(*ire, *icp, &e);
+    if (!p) return;
+    // contact_addon.f90:3330-3515: isubs 1/5: all elements x given z ; 9: explicit x, y, z lists ; others: index selections
+    Problem::SubsBlock &b = p->subs[*iblk];
+    b.isubs = *isubs; b.nx = *nx; b.ny = *ny; b.nz = *nz;
+    b.x.clear(); b.y.clear(); b.z.clear(); b.table.clear();
+    const double L = p->scl.len;
+    if (*isubs == 9) {
+        b.x.assign(xparam, xparam + *nx); b.y.assign(yparam, yparam + *ny); b.z.assign(zparam, zparam + *nz);
+        for (double &v : b.x) v *= L; for (double &v : b.y) v *= L; for (double &v : b.z) v *= L;
+    } else if (*isubs == 1 || *isubs == 5) {
+        b.z.assign(zparam, zparam + *nz);
+        for (double &v : b.z) v *= L;
+    } else {
+        b.x.assign(xparam, xparam + (*isubs == 3 || *isubs == 7 ? *nx : 3));
+        b.y.assign(yparam, yparam + (*isubs == 3 || *isubs == 7 ? *ny : 3));
+        b.z.assign(zparam, zparam + *nz);
+        for (double &v : b.z) v *= L;
+    }
+}
+
+void subs_calculate(int *ire, int *icp, int *ierror)
+{
+    Problem *p = activate(*ire, *icp, ierror);
+    if (!p) return;
+    last_error() = "subs_calculate: the subsurface evaluator is not yet served by the B200 path";
+    *ierror = CNTC_err_other;
+}
+
+void subs_getblocksize(int *ire, int *icp, int *iblk, int *nx, int *ny, int *nz)
+{
+    int e; Problem *p = activate(*ire, *icp, &e);
+    if (!p) return;
+    auto it = p->subs.find(*iblk);
+    if (it == p->subs.end()) { *nx = *ny = *nz = 0; return; }
+    *nx = it->second.nx; *ny = it->second.ny; *nz = it->second.nz;
+}
+
+void subs_getresults(int *ire, int *icp, int *iblk, int *lenarr, int *ncol, int *icol, double *values)
+{
+    int e; Problem *p = activate(*ire, *icp, &e);
+    if (!p) return;
+    (void) iblk; (void) icol;
+    for (long i = 0; i < (long) *lenarr * *ncol; i++) values[i] = -999.0;     // contact_addon.f90:6113-6178: invalid -> -999
+}
+
+void cntc_finalize(int *ire)
+{
+    Registry &R = registry();
+    std::lock_guard<std::mutex> lk(R.mu);
+    R.res.erase(*ire);
+}
+
+void cntc_finalizelast(void)
+{
+    Registry &R = registry();
+    std::lock_guard<std::mutex> lk(R.mu);
+    R.res.clear();
+}
+
+}  // extern "C"

@@ -1,0 +1,259 @@
+// api_lowlevel.cuh -- cb200_* entry points: kernel-level C-ABI (plain pointers and sizes).
+#pragma once
+#include "engine.cuh"
+
+namespace cb200 {
+
+inline CoefSet *set_from_handle(int h)
+{
+    Engine &E = engine();
+    std::lock_guard<std::mutex> lk(E.mu);
+    if (h < 0 || h >= (int) E.by_handle.size()) { last_error() = "invalid coefficient-set handle"; return nullptr; }
+    return E.by_handle[h];
+}
+
+inline int handle_of(CoefSet *cs)
+{
+    Engine &E = engine();
+    std::lock_guard<std::mutex> lk(E.mu);
+    for (size_t i = 0; i < E.by_handle.size(); i++) if (E.by_handle[i] == cs) return (int) i;
+    return -1;
+}
+
+inline void dir_range(int arg, int &a0, int &a1)
+{   // m_aijpj.f90:292-336
+    if (arg == -3) { a0 = 1; a1 = 3; } else if (arg == -2) { a0 = 1; a1 = 2; }
+    else if (arg >= 1 && arg <= 3) { a0 = a1 = arg; } else { a0 = 1; a1 = 0; }
+}
+
+__global__ void k_fill_masked(double *u, const int *el, int mask_mode, double val, long n)
+{
+    const long t = blockIdx.x * (long) blockDim.x + threadIdx.x;
+    if (t < n && (mask_mode == 0 || el[t] >= 1)) u[t] = val;
+}
+
+// Strided batched product: case ic reads p + ic*pstride, writes u + ic*ustride, mask el + ic*npot
+__global__ void __launch_bounds__(CB_THREADS, 1)
+k_conv_batch_strided(ConvPlan P, const double *p, long pstride, const cd *chat, double *u, long ustride,
+                     const int *el, int mask_mode, int add, int ncase)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Smem sm = smem_view(P, smem_raw);
+    smem_load_tables(P, sm);
+    for (int ic = blockIdx.x; ic < ncase; ic += gridDim.x)
+        conv_dev(P, sm, p + ic * pstride, chat, u + ic * ustride, el ? el + (size_t) ic * P.npot : nullptr,
+                 el ? mask_mode : 0, add);
+}
+
+// gf3_VecAijPj semantics (m_aijpj.f90:346-395) on device buffers laid out [ncase][3][npot]
+inline int vecaijpj_dev(CoefSet &cs, int set, int ncase, int iigs, int ikarg, int jkarg, const double *d_p,
+                        const int *d_el, double *d_u, cudaStream_t st)
+{
+    Engine &E = engine();
+    const ConvPlan &P = cs.hp.p;
+    if (!cs.hp.fits) { last_error() = "grid too large for the single-CTA product"; return -34; }
+    if (iigs != -9 && iigs != -8) { last_error() = "FFT product allowed only for AllElm or AllInt"; return -99; }
+    if (!cs.d_cf[set]) { last_error() = "coefficient set not available"; return -99; }
+    const int mask_mode = (iigs == -8) ? 1 : 0;
+    if (mask_mode == 1 && !d_el) { last_error() = "AllInt product needs an element division"; return -99; }
+    static bool attr = false;
+    if (!attr) { CB_CUDA(cudaFuncSetAttribute(k_conv_batch_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax)); attr = true; }
+    int ik0, ik1, jk0, jk1;
+    dir_range(ikarg, ik0, ik1); dir_range(jkarg, jk0, jk1);
+    const long cstride = 3L * P.npot;
+    const int nblk = launch_blocks(ncase);
+    for (int ik = ik0; ik <= ik1; ik++) {
+        bool ladd = false;
+        for (int jk = jk0; jk <= jk1; jk++) {
+            if (!cs.nt_cpl && (ik * jk == 3 || ik * jk == 6)) continue;     // :358-369
+            int rc = build_chat(cs, set, ik, jk, st);
+            if (rc) return rc;
+            k_conv_batch_strided<<<nblk, CB_THREADS, P.smem_bytes, st>>>(
+                P, d_p + (size_t) (jk - 1) * P.npot, cstride, cs.d_chat[set][ik - 1][jk - 1],
+                d_u + (size_t) (ik - 1) * P.npot, cstride, d_el, mask_mode, ladd ? 1 : 0, ncase);
+            E.launches++;
+            ladd = true;
+        }
+        if (!ladd) {                                                        // all blocks skipped: u = 0 on the selection
+            for (int ic = 0; ic < ncase; ic++) {
+                k_fill_masked<<<grid1d(P.npot, 256), 256, 0, st>>>(d_u + ic * cstride + (size_t) (ik - 1) * P.npot,
+                                                                  d_el ? d_el + (size_t) ic * P.npot : nullptr,
+                                                                  mask_mode, 0.0, P.npot);
+                E.launches++;
+            }
+        }
+    }
+    CB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+struct NormBatch {            // persistent device workspace of the batched NORM solve
+    int cap = 0;
+    NormCase *d_cases = nullptr;
+    double *d_work = nullptr;
+    std::vector<NormCase> h_cases;
+};
+
+__global__ void k_norm_pack(NormCase *cases, int ncase, int npot, const double *hs, int *el, double *pn, double *un,
+                            const double *scal, double *work, NormCase proto)
+{
+    const int ic = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ic >= ncase) return;
+    NormCase c = proto;
+    c.hs = hs + (size_t) ic * npot;
+    c.el = el + (size_t) ic * npot;
+    c.pn = pn + (size_t) ic * npot;
+    c.work = work + (size_t) ic * 9 * npot;
+    c.pen = scal[ic * 8 + 0];
+    c.fntrue = scal[ic * 8 + 1];
+    c.ptx = nullptr; c.pty = nullptr;
+    (void) un;
+    cases[ic] = c;
+}
+
+__global__ void k_norm_unpack(const NormCase *cases, int ncase, double *scal)
+{
+    const int ic = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ic >= ncase) return;
+    const NormCase &c = cases[ic];
+    double *s = scal + ic * 8;
+    s[0] = c.pen; s[1] = c.fntrue; s[2] = c.itcg; s[3] = c.itnorm; s[4] = c.ncon; s[5] = c.status; s[6] = c.err; s[7] = 0.0;
+}
+
+// u_n = A_zz p_n on the contact area after the solve (soutpt, m_soutpt.f90:378-385), batched
+inline NormBatch &norm_batch() { static NormBatch b; return b; }
+
+inline int snorm_batch_dev(CoefSet &cs, int ncase, int ic_norm, int maxgs, int maxin, double eps, const double *d_hs,
+                           int *d_el, double *d_pn, double *d_un, double *d_scal, cudaStream_t st)
+{
+    Engine &E = engine();
+    const ConvPlan &P = cs.hp.p;
+    if (!cs.hp.fits) { last_error() = "grid too large for the single-CTA solver"; return -34; }
+    int rc;
+    if ((rc = build_prec(cs, st))) return rc;
+    if ((rc = build_chat(cs, SET_CS, 3, 3, st))) return rc;
+    if ((rc = build_chat(cs, SET_MS, 3, 3, st))) return rc;
+    NormBatch &B = norm_batch();
+    static long cap_bytes = 0;
+    const long need = (long) ncase * 9 * P.npot * sizeof(double);
+    if (ncase > B.cap || need > cap_bytes) {
+        if (B.d_cases) cudaFree(B.d_cases);
+        if (B.d_work) cudaFree(B.d_work);
+        CB_CUDA(cudaMalloc(&B.d_cases, sizeof(NormCase) * ncase));
+        CB_CUDA(cudaMalloc(&B.d_work, need));
+        B.cap = ncase; cap_bytes = need;
+    }
+    NormCase proto;
+    memset(&proto, 0, sizeof(proto));
+    proto.chatA = cs.d_chat[SET_CS][2][2];
+    proto.chatM = cs.d_chat[SET_MS][2][2];
+    proto.chatA31 = nullptr; proto.chatA32 = nullptr;
+    proto.cf33 = cs.d_cf[SET_CS] + (size_t) 8 * 4 * cs.mx * cs.my;
+    proto.cmx = cs.mx; proto.cmy = cs.my;
+    proto.ga_inv = cs.ga_inv;
+    proto.ic_norm = ic_norm; proto.maxgs = maxgs; proto.maxin = maxin; proto.eps = eps;
+    proto.dxdy = cs.key.dx * cs.key.dy;
+    k_norm_pack<<<grid1d(ncase, 128), 128, 0, st>>>(B.d_cases, ncase, P.npot, d_hs, d_el, d_pn, d_un, d_scal, B.d_work, proto);
+    k_snorm_batch<<<launch_blocks(ncase), CB_THREADS, P.smem_bytes, st>>>(P, B.d_cases, ncase);
+    k_norm_unpack<<<grid1d(ncase, 128), 128, 0, st>>>(B.d_cases, ncase, d_scal);
+    E.launches += 3;
+    if (d_un) {
+        static bool attr = false;
+        if (!attr) { CB_CUDA(cudaFuncSetAttribute(k_conv_batch_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax)); attr = true; }
+        CB_CUDA(cudaMemsetAsync(d_un, 0, sizeof(double) * (size_t) ncase * P.npot, st));
+        k_conv_batch_strided<<<launch_blocks(ncase), CB_THREADS, P.smem_bytes, st>>>(
+            P, d_pn, P.npot, proto.chatA, d_un, P.npot, d_el, 1, 0, ncase);
+        E.launches++;
+    }
+    CB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace cb200
+
+using namespace cb200;
+
+extern "C" {
+
+const char *cb200_last_error(void) { return last_error().c_str(); }
+long cb200_num_launches(void) { return engine().launches; }
+int cb200_num_sms(void) { int rc = engine_init(); return rc ? rc : engine().num_sms; }
+int cb200_opt_fft_size(int n) { return opt_fft_size(n); }
+
+int cb200_coefset_create(int mx, int my, double dx, double dy, double gg1, double gg2, double poiss1, double poiss2,
+                         int is_roll, double chi, double dq)
+{
+    if (mx < 1 || my < 1 || dx <= 0 || dy <= 0) { last_error() = "invalid grid"; return -34; }
+    Material m = { { gg1, gg2 }, { poiss1, poiss2 }, 0, 0, 0 };
+    CoefSet *cs = nullptr;
+    int rc = get_coefset(mx, my, dx, dy, m, is_roll, chi, dq, 0, &cs);
+    if (rc) return rc;
+    return handle_of(cs);
+}
+
+int cb200_coefset_plan(int handle, int *out)
+{
+    CoefSet *cs = set_from_handle(handle);
+    if (!cs) return -99;
+    const ConvPlan &P = cs->hp.p;
+    out[0] = P.Fx; out[1] = P.Fy; out[2] = P.C; out[3] = P.nchunk; out[4] = P.smem_bytes; out[5] = cs->hp.fits;
+    out[6] = P.nsx; out[7] = P.nsy;
+    return 0;
+}
+
+int cb200_coefset_get_block(int handle, int set, int ik, int jk, double *out)
+{
+    CoefSet *cs = set_from_handle(handle);
+    if (!cs) return -99;
+    if (set < 0 || set > 3 || ik < 1 || ik > 3 || jk < 1 || jk > 3) { last_error() = "invalid block"; return -99; }
+    if (set == SET_MS) { int rc = build_prec(*cs, 0); if (rc) return rc; }
+    if (!cs->d_cf[set]) { last_error() = "coefficient set not available"; return -99; }
+    const size_t nblk = (size_t) 4 * cs->mx * cs->my;
+    CB_CUDA(cudaMemcpy(out, cs->d_cf[set] + ((jk - 1) * 3 + (ik - 1)) * nblk, sizeof(double) * nblk, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int cb200_vecaijpj_dev(int handle, int set, int ncase, int iigs, int ikarg, int jkarg, const double *d_p,
+                       const int *d_el, double *d_u, void *stream)
+{
+    CoefSet *cs = set_from_handle(handle);
+    if (!cs) return -99;
+    if (set == SET_MS) { int rc = build_prec(*cs, (cudaStream_t) stream); if (rc) return rc; }
+    return vecaijpj_dev(*cs, set, ncase, iigs, ikarg, jkarg, d_p, d_el, d_u, (cudaStream_t) stream);
+}
+
+int cb200_vecaijpj(int handle, int set, int ncase, int iigs, int ikarg, int jkarg, const double *p, const int *el,
+                   double *u)
+{
+    CoefSet *cs = set_from_handle(handle);
+    if (!cs) return -99;
+    const size_t n3 = (size_t) ncase * 3 * cs->hp.p.npot, n1 = (size_t) ncase * cs->hp.p.npot;
+    double *d_p = nullptr, *d_u = nullptr; int *d_el = nullptr;
+    CB_CUDA(cudaMalloc(&d_p, sizeof(double) * n3));
+    CB_CUDA(cudaMalloc(&d_u, sizeof(double) * n3));
+    CB_CUDA(cudaMemcpy(d_p, p, sizeof(double) * n3, cudaMemcpyHostToDevice));
+    CB_CUDA(cudaMemcpy(d_u, u, sizeof(double) * n3, cudaMemcpyHostToDevice));   // unselected elements keep their value
+    if (el) { CB_CUDA(cudaMalloc(&d_el, sizeof(int) * n1)); CB_CUDA(cudaMemcpy(d_el, el, sizeof(int) * n1, cudaMemcpyHostToDevice)); }
+    int rc = cb200_vecaijpj_dev(handle, set, ncase, iigs, ikarg, jkarg, d_p, d_el, d_u, nullptr);
+    if (!rc) { cudaError_t e = cudaMemcpy(u, d_u, sizeof(double) * n3, cudaMemcpyDeviceToHost); if (e != cudaSuccess) { last_error() = cudaGetErrorString(e); rc = -99; } }
+    cudaFree(d_p); cudaFree(d_u); if (d_el) cudaFree(d_el);
+    return rc;
+}
+
+int cb200_snorm_batch_dev(int handle, int ncase, int ic_norm, int maxgs, int maxin, double eps, const double *d_hs,
+                          int *d_el, double *d_pn, double *d_un, double *d_scal, void *stream)
+{
+    CoefSet *cs = set_from_handle(handle);
+    if (!cs) return -99;
+    if (ncase < 1) return 0;
+    return snorm_batch_dev(*cs, ncase, ic_norm, maxgs, maxin, eps, d_hs, d_el, d_pn, d_un, d_scal, (cudaStream_t) stream);
+}
+
+long cb200_snorm_workspace_bytes(int handle, int ncase)
+{
+    CoefSet *cs = set_from_handle(handle);
+    if (!cs) return -99;
+    return (long) ncase * (9L * cs->hp.p.npot * sizeof(double) + sizeof(NormCase));
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+// device_core.cuh -- shared-memory view, fused convolution as a device function, deterministic block reductions.
+#pragma once
+#include "fftconv.cuh"
+
+#ifndef CB_THREADS
+#define CB_THREADS 384
+#endif
+
+namespace cb200 {
+
+struct Smem {
+    cd *S, *W, *twx, *twy;
+    unsigned short *posx;
+    double *red;       // 128 doubles of reduction scratch
+};
+
+__device__ __forceinline__ Smem smem_view(const ConvPlan &P, unsigned char *base)
+{
+    Smem s;
+    s.S = reinterpret_cast<cd *>(base + P.off_S);
+    s.W = reinterpret_cast<cd *>(base + P.off_W);
+    s.twx = reinterpret_cast<cd *>(base + P.off_twx);
+    s.twy = reinterpret_cast<cd *>(base + P.off_twy);
+    s.posx = reinterpret_cast<unsigned short *>(base + P.off_posx);
+    s.red = reinterpret_cast<double *>(base + P.off_red);
+    return s;
+}
+
+__device__ __forceinline__ void smem_load_tables(const ConvPlan &P, const Smem &s)
+{
+    for (int k = threadIdx.x; k < 2 * P.Fx; k += blockDim.x) s.twx[k] = P.twx[k];
+    for (int k = threadIdx.x; k < 2 * P.Fy; k += blockDim.x) s.twy[k] = P.twy[k];
+    for (int k = threadIdx.x; k < P.Lx; k += blockDim.x) s.posx[k] = P.posx[k];
+    __syncthreads();
+}
+
+#define CB_PHASE(call) do { call; __syncthreads(); } while (0)
+#include "conv_sequence.inc"
+
+// u (masked) = conv(p) with transformed coefficients chat.  All threads of the CTA must call.
+__device__ __forceinline__ void conv_dev(const ConvPlan &P, const Smem &sm, const double *p, const cd *chat,
+                                         double *u, const int *el, int mask_mode, int add)
+{
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    cd *S = sm.S, *W = sm.W;
+    const cd *twx = sm.twx, *twy = sm.twy;
+    const unsigned short *posx = sm.posx;
+    const int SY = P.SY;
+    RowSrc src;
+    src.base = p; src.kind = 0; src.mx = P.mx; src.my = P.my; src.cmx = 0; src.cmy = 0; src.Fx = P.Fx; src.Fy = P.Fy; src.row0 = 0;
+    CB_CONV_FORWARD_ROWS(P.my, src);
+    CB_CONV_COLUMNS_PRODUCT(P.my, chat);
+    CB_CONV_INVERSE_ROWS(P.my);
+    CB_PHASE(row_store(P, S, SY, u, el, mask_mode, add, tid, nthr));
+}
+
+// ---- deterministic block reductions (fixed shuffle tree; result broadcast to all threads) ----
+template <int N>
+__device__ __forceinline__ void block_sum(double (&v)[N], double *red)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+    __syncthreads();                       // protect red[] from a previous use
+    if (lane == 0)
+#pragma unroll
+        for (int i = 0; i < N; i++) red[wid * N + i] = v[i];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        double s = 0.0;
+        for (int w = 0; w < nw; w++) s += red[w * N + i];
+        v[i] = s;
+    }
+}
+
+__device__ __forceinline__ double block_min(double v, double *red)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    double s = red[0];
+    for (int w = 1; w < nw; w++) s = fmin(s, red[w]);
+    return s;
+}
+
+}  // namespace cb200

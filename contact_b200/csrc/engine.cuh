@@ -1,0 +1,213 @@
+// engine.cuh -- host-side engine: coefficient sets cached per (grid, material, rolling step), their transforms,
+// the FFT preconditioner, launch wrappers.  Everything numeric runs on the device; the host only plans and launches.
+//
+// "coefficients cached per grid and material": the reference recomputes or reuses cs/cv/csv in sgencr
+// (/root/reference/src/m_visc.f90:127-376) and re-transforms them whenever the FFT size changes
+// (m_aijpj.f90:873-920); here one CoefSet owns the spatial blocks and the lazily built C^ per (set, ik, jk).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "kernels.cuh"
+#include "plan.h"
+
+namespace cb200 {
+
+
+
+inline std::string &last_error() { static thread_local std::string e; return e; }
+
+#define CB_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char b_[512];                                                                          \
+            snprintf(b_, sizeof(b_), "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            last_error() = b_;                                                                     \
+            return -99;                                                                            \
+        }                                                                                          \
+    } while (0)
+
+enum { SET_CS = 0, SET_CV = 1, SET_CSV = 2, SET_MS = 3 };
+
+struct Material { double gg[2], poiss[2], ga, nu, ak; };
+
+inline void combine_material(Material &m)
+{   // m_hierarch_data.f90:1543-1553
+    m.ga = 2.0 / (1.0 / m.gg[0] + 1.0 / m.gg[1]);
+    m.nu = m.ga * (m.poiss[0] / m.gg[0] + m.poiss[1] / m.gg[1]) / 2.0;
+    m.ak = (m.ga / 4.0) * ((1.0 - 2.0 * m.poiss[0]) / m.gg[0] - (1.0 - 2.0 * m.poiss[1]) / m.gg[1]);
+}
+
+struct CoefKey {
+    int mx, my; double dx, dy, ga, nu, ak; int is_roll; double chi, dq;
+    bool operator<(const CoefKey &o) const {
+        const double a[] = { (double) mx, (double) my, dx, dy, ga, nu, ak, (double) is_roll, chi, dq };
+        const double b[] = { (double) o.mx, (double) o.my, o.dx, o.dy, o.ga, o.nu, o.ak, (double) o.is_roll, o.chi, o.dq };
+        for (int i = 0; i < 10; i++) { if (a[i] < b[i]) return true; if (a[i] > b[i]) return false; }
+        return false;
+    }
+};
+
+struct CoefSet {
+    CoefKey key;
+    int mx, my;
+    bool nt_cpl;
+    double ga, ga_inv;
+    HostPlan hp;                  // plan for products on the full mx x my grid
+    cd *d_twx = nullptr, *d_twy = nullptr;
+    unsigned short *d_posx = nullptr;
+    double *d_cf[4] = { nullptr, nullptr, nullptr, nullptr };     // spatial coefficients, 9 blocks each
+    cd *d_chat[4][3][3] = {};                                      // transformed blocks (lazy)
+    bool prec_ready = false;
+    long n_chat_built = 0;
+};
+
+struct Engine {
+    std::mutex mu;
+    std::map<CoefKey, CoefSet *> sets;
+    std::vector<CoefSet *> by_handle;
+    int device = -1;
+    int num_sms = 0;
+    bool attr_set = false;
+    long launches = 0;            // kernels launched by this library (for bench "gpu_launches")
+};
+
+inline Engine &engine() { static Engine e; return e; }
+
+inline int engine_init()
+{
+    Engine &E = engine();
+    if (E.device >= 0) return 0;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        last_error() = "contact_addon_b200: no CUDA device available (this library has no CPU fallback)";
+        return -99;
+    }
+    int dev = 0;
+    CB_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CB_CUDA(cudaGetDeviceProperties(&prop, dev));
+    E.device = dev;
+    E.num_sms = prop.multiProcessorCount;
+    CB_CUDA(cudaFuncSetAttribute(k_conv_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    CB_CUDA(cudaFuncSetAttribute(k_snorm_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    CB_CUDA(cudaFuncSetAttribute(k_build_chat, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    return 0;
+}
+
+inline int grid1d(long n, int b) { return (int) ((n + b - 1) / b); }
+
+// ---- coefficient transform of one block ----
+inline int build_chat(CoefSet &cs, int set, int ik, int jk, cudaStream_t st)
+{
+    Engine &E = engine();
+    if (cs.d_chat[set][ik - 1][jk - 1]) return 0;
+    const ConvPlan &P = cs.hp.p;
+    cd *chat = nullptr, *Sg = nullptr, *Wg = nullptr;
+    CB_CUDA(cudaMalloc(&chat, sizeof(cd) * (size_t) P.chat_len));
+    CB_CUDA(cudaMalloc(&Sg, sizeof(cd) * (size_t) (P.Lx + 1) * 2 * P.Fy));
+    CB_CUDA(cudaMalloc(&Wg, sizeof(cd) * (size_t) P.Ly * P.C));
+    const double *blk = cs.d_cf[set] + (size_t) ((jk - 1) * 3 + (ik - 1)) * 4 * cs.mx * cs.my;
+    const double scale = cs.ga_inv / (4.0 * P.Fx * P.Fy);
+    const int smem = (2 * P.Fx + 2 * P.Fy) * 16 + P.Lx * 2 + 64;
+    k_build_chat<<<1, CB_THREADS, smem, st>>>(P, blk, cs.mx, cs.my, scale, Sg, Wg, chat);
+    E.launches++;
+    CB_CUDA(cudaGetLastError());
+    CB_CUDA(cudaStreamSynchronize(st));
+    CB_CUDA(cudaFree(Sg));
+    CB_CUDA(cudaFree(Wg));
+    cs.d_chat[set][ik - 1][jk - 1] = chat;
+    cs.n_chat_built++;
+    return 0;
+}
+
+// ---- FFT preconditioner: ms(3,3) = G^2 IFFT2(1 / FFT2(cs(3,3))) on the un-optimised (2mx x 2my) array ----
+// Follows fft_makePrec (/root/reference/src/m_aijpj.f90:457-708).  The size is not FFT friendly (e.g. 2*7*13), so
+// this one-off transform is done as dense separable DFTs.
+inline int build_prec(CoefSet &cs, cudaStream_t st)
+{
+    Engine &E = engine();
+    if (cs.prec_ready) return 0;
+    const int n1 = 2 * cs.mx, n2 = 2 * cs.my;
+    const long n = (long) n1 * n2;
+    std::vector<cd> t1(n1), t2(n2);
+    const double pi = 3.14159265358979323846;
+    for (int k = 0; k < n1; k++) t1[k] = make_double2(cos(-2.0 * pi * k / n1), sin(-2.0 * pi * k / n1));
+    for (int k = 0; k < n2; k++) t2[k] = make_double2(cos(-2.0 * pi * k / n2), sin(-2.0 * pi * k / n2));
+    cd *d_t1, *d_t2, *a, *b;
+    CB_CUDA(cudaMalloc(&d_t1, sizeof(cd) * n1));
+    CB_CUDA(cudaMalloc(&d_t2, sizeof(cd) * n2));
+    CB_CUDA(cudaMalloc(&a, sizeof(cd) * n));
+    CB_CUDA(cudaMalloc(&b, sizeof(cd) * n));
+    CB_CUDA(cudaMemcpyAsync(d_t1, t1.data(), sizeof(cd) * n1, cudaMemcpyHostToDevice, st));
+    CB_CUDA(cudaMemcpyAsync(d_t2, t2.data(), sizeof(cd) * n2, cudaMemcpyHostToDevice, st));
+    const double *c33 = cs.d_cf[SET_CS] + (size_t) 8 * n;
+    if (!cs.d_cf[SET_MS]) {
+        CB_CUDA(cudaMalloc(&cs.d_cf[SET_MS], sizeof(double) * 9 * n));
+        CB_CUDA(cudaMemsetAsync(cs.d_cf[SET_MS], 0, sizeof(double) * 9 * n, st));
+    }
+    const int B = 256, G = grid1d(n, B);
+    k_real_to_cplx<<<G, B, 0, st>>>(c33, a, n);
+    k_dft_axis<<<G, B, 0, st>>>(a, b, n1, n2, 0, 0, d_t1);
+    k_dft_axis<<<G, B, 0, st>>>(b, a, n1, n2, 1, 0, d_t2);
+    k_cplx_recip<<<G, B, 0, st>>>(a, n);
+    k_dft_axis<<<G, B, 0, st>>>(a, b, n1, n2, 1, 1, d_t2);
+    k_dft_axis<<<G, B, 0, st>>>(b, a, n1, n2, 0, 1, d_t1);
+    k_cplx_real_scaled<<<G, B, 0, st>>>(a, cs.d_cf[SET_MS] + (size_t) 8 * n, n, cs.ga * cs.ga / (double) n);
+    E.launches += 7;
+    CB_CUDA(cudaGetLastError());
+    CB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_t1); cudaFree(d_t2); cudaFree(a); cudaFree(b);
+    cs.prec_ready = true;
+    return 0;
+}
+
+// ---- create / look up a coefficient set ----
+inline int get_coefset(int mx, int my, double dx, double dy, Material mat, int is_roll, double chi, double dq,
+                       cudaStream_t st, CoefSet **out)
+{
+    int rc = engine_init();
+    if (rc) return rc;
+    Engine &E = engine();
+    combine_material(mat);
+    CoefKey key = { mx, my, dx, dy, mat.ga, mat.nu, mat.ak, is_roll, is_roll ? chi : 0.0, is_roll ? dq : 0.0 };
+    std::lock_guard<std::mutex> lk(E.mu);
+    auto it = E.sets.find(key);
+    if (it != E.sets.end()) { *out = it->second; return 0; }
+
+    CoefSet *cs = new CoefSet();
+    cs->key = key; cs->mx = mx; cs->my = my;
+    cs->ga = mat.ga; cs->ga_inv = 1.0 / mat.ga;
+    cs->nt_cpl = !(fabs(mat.ak) < 1e-6);                             // m_visc.f90:239-243
+    if (!make_plan(mx, my, cs->hp)) { last_error() = "unsupported grid size for the FFT product"; delete cs; return -34; }
+    ConvPlan &P = cs->hp.p;
+    CB_CUDA(cudaMalloc(&cs->d_twx, sizeof(cd) * cs->hp.twx.size()));
+    CB_CUDA(cudaMalloc(&cs->d_twy, sizeof(cd) * cs->hp.twy.size()));
+    CB_CUDA(cudaMalloc(&cs->d_posx, sizeof(unsigned short) * cs->hp.posx.size()));
+    CB_CUDA(cudaMemcpyAsync(cs->d_twx, cs->hp.twx.data(), sizeof(cd) * cs->hp.twx.size(), cudaMemcpyHostToDevice, st));
+    CB_CUDA(cudaMemcpyAsync(cs->d_twy, cs->hp.twy.data(), sizeof(cd) * cs->hp.twy.size(), cudaMemcpyHostToDevice, st));
+    CB_CUDA(cudaMemcpyAsync(cs->d_posx, cs->hp.posx.data(), sizeof(unsigned short) * cs->hp.posx.size(), cudaMemcpyHostToDevice, st));
+    P.twx = cs->d_twx; P.twy = cs->d_twy; P.posx = cs->d_posx;
+
+    const long nblk = 4L * mx * my;
+    CB_CUDA(cudaMalloc(&cs->d_cf[SET_CS], sizeof(double) * 9 * nblk));
+    ElascfArgs a = { mat.ak, mat.nu, dx, dy, 0.0, 0.0, mx, my };
+    k_elascf_pcwcns<<<grid1d(nblk, 128), 128, 0, st>>>(a, cs->d_cf[SET_CS]);
+    E.launches++;
+    CB_CUDA(cudaGetLastError());
+    CB_CUDA(cudaStreamSynchronize(st));
+    E.sets[key] = cs;
+    E.by_handle.push_back(cs);
+    *out = cs;
+    return 0;
+}
+
+inline int launch_blocks(int ncase) { Engine &E = engine(); return ncase < E.num_sms ? ncase : E.num_sms; }
+
+}  // namespace cb200

@@ -1,0 +1,130 @@
+// plan.h -- host-side planning for the single-CTA FFT convolution (sizes, radices, tables, shared-memory layout).
+// opt_fft_size restates the reference's size chooser (/root/reference/src/m_aijpj.f90:1022-1119) because the padded
+// size is part of the reference's semantics (it fixes which transform lengths occur); everything else is new.
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include "fftconv.cuh"
+
+namespace cb200 {
+
+static const int kSmemMax = 232448;      // 227 KB opt-in maximum per CTA on sm_100
+
+inline int opt_fft_size(int n)
+{
+    // factor-trading patterns (delta exponents of 2,3,5,7 | numerator, denominator | largest prime used)
+    static const int pat[8][7] = {
+        { -2,  1,  0,  0,   4,  3, 3 }, { -5,  3,  0,  0,  32, 27, 3 }, { -1, -1,  1,  0,   6,  5, 5 },
+        { -4,  1,  1,  0,  16, 15, 5 }, {  0, -3,  2,  0,  27, 25, 5 }, { -3,  0,  0,  1,   8,  7, 7 },
+        {  1, -1, -1,  1,  15, 14, 7 }, { -1,  2, -1,  0,  10,  9, 5 } };
+    int e[4] = { (int) std::ceil(std::log(1.0 * n) / std::log(2.0)), 0, 0, 0 };
+    long prod = 1L << e[0];
+    bool changed = true;
+    while (changed) {
+        changed = false;
+        for (int ip = 0; ip < 8; ip++) {
+            const int *k = pat[ip];
+            for (;;) {
+                bool ok = true;
+                for (int f = 0; f < 4; f++) ok = ok && (e[f] + k[f] >= 0);
+                if (!ok || (long) k[5] * prod < (long) k[4] * n) break;
+                for (int f = 0; f < 4; f++) e[f] += k[f];
+                prod = k[5] * prod / k[4];
+                changed = true;
+            }
+        }
+    }
+    return (int) prod;
+}
+
+// split L = 2^a 3^b 5^c 7^d into register-sized radices; returns false if another prime occurs
+inline bool choose_radices(int L, int *nst, int *rad)
+{
+    int a = 0, b = 0, c = 0, d = 0, n = L;
+    while (n % 2 == 0) { a++; n /= 2; }
+    while (n % 3 == 0) { b++; n /= 3; }
+    while (n % 5 == 0) { c++; n /= 5; }
+    while (n % 7 == 0) { d++; n /= 7; }
+    if (n != 1) return false;
+    int k = 0;
+    while (a >= 7) { rad[k++] = 16; a -= 4; }
+    if (a == 6) { rad[k++] = 8; rad[k++] = 8; }
+    else if (a == 5) { rad[k++] = 8; rad[k++] = 4; }
+    else if (a == 4) { rad[k++] = 16; }
+    else if (a == 3) { rad[k++] = 8; }
+    else if (a == 2) { rad[k++] = 4; }
+    else if (a == 1) { rad[k++] = 2; }
+    while (b >= 2) { rad[k++] = 9; b -= 2; }
+    if (b == 1) rad[k++] = 3;
+    while (d-- > 0) rad[k++] = 7;
+    while (c-- > 0) rad[k++] = 5;
+    if (k > CB_MAXSTAGE) return false;
+    *nst = k;
+    return true;
+}
+
+struct HostPlan {
+    ConvPlan p;
+    std::vector<cd> twx, twy;
+    std::vector<unsigned short> posx;
+    bool fits;           // whole product fits one CTA's shared memory
+};
+
+// position of frequency k after in-place DIF with radices r[0..ns-1]
+inline void dif_positions(int L, int ns, const int *r, std::vector<unsigned short> &pos)
+{
+    pos.resize(L > 0 ? L : 1);
+    for (int k = 0; k < L; k++) {
+        int rem = k, span = L, p = 0;
+        for (int s = 0; s < ns; s++) {
+            const int q = rem % r[s];
+            rem /= r[s];
+            span /= r[s];
+            p += q * span;
+        }
+        pos[k] = (unsigned short) p;
+    }
+}
+
+inline bool make_plan(int mx, int my, HostPlan &hp, int smem_limit = kSmemMax)
+{
+    ConvPlan &P = hp.p;
+    std::memset(&P, 0, sizeof(P));
+    P.mx = mx; P.my = my; P.npot = mx * my;
+    P.Fx = opt_fft_size(mx); P.Fy = opt_fft_size(my);
+    P.Lx = P.Fx; P.Ly = 2 * P.Fy;
+    if (P.Lx == 1) P.nsx = 0;
+    else if (!choose_radices(P.Lx, &P.nsx, P.rx)) return false;
+    if (!choose_radices(P.Ly, &P.nsy, P.ry)) return false;
+    if (P.Lx >= 65535 || P.Ly >= 65535) return false;
+    P.SY = my | 1;
+    hp.twx.resize(2 * P.Fx); hp.twy.resize(2 * P.Fy);
+    const double pi = 3.14159265358979323846;
+    for (int k = 0; k < 2 * P.Fx; k++) hp.twx[k] = make_double2(std::cos(-2.0 * pi * k / (2.0 * P.Fx)), std::sin(-2.0 * pi * k / (2.0 * P.Fx)));
+    for (int k = 0; k < 2 * P.Fy; k++) hp.twy[k] = make_double2(std::cos(-2.0 * pi * k / (2.0 * P.Fy)), std::sin(-2.0 * pi * k / (2.0 * P.Fy)));
+    dif_positions(P.Lx, P.nsx, P.rx, hp.posx);
+
+    // shared-memory layout: S | W | twx | twy | posx | red
+    const long bytesS = (long) (P.Lx + 1) * P.SY * 16;
+    const long bytesT = (long) (2 * P.Fx + 2 * P.Fy) * 16 + ((P.Lx * 2 + 15) / 16) * 16 + 1024;
+    const long avail = (long) smem_limit - bytesS - bytesT;
+    const int ncol = P.Fx + 1;
+    int C = (int) (avail / ((long) P.Ly * 16));
+    hp.fits = C >= 1;
+    if (C < 1) C = 1;
+    if (C > ncol) C = ncol;
+    P.nchunk = (ncol + C - 1) / C;
+    P.C = (ncol + P.nchunk - 1) / P.nchunk;
+    P.chat_len = P.nchunk * P.Ly * P.C;
+    P.off_S = 0;
+    P.off_W = (int) bytesS;
+    P.off_twx = P.off_W + P.Ly * P.C * 16;
+    P.off_twy = P.off_twx + 2 * P.Fx * 16;
+    P.off_posx = P.off_twy + 2 * P.Fy * 16;
+    P.off_red = P.off_posx + ((P.Lx * 2 + 15) / 16) * 16;
+    P.smem_bytes = P.off_red + 1024;
+    return true;
+}
+
+}  // namespace cb200

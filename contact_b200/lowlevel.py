@@ -1,0 +1,90 @@
+"""Kernel-level entry points (cb200_*) for tests and benchmarks: batched influence product and NORM solve.
+
+Device-buffer variants take torch CUDA tensors (PyTorch is used for device memory and streams only).
+"""
+import ctypes as C
+
+import numpy as np
+
+from .lib import load_library, last_error
+
+ALLELM, ALLINT = -9, -8
+SET_CS, SET_CV, SET_CSV, SET_MS = 0, 1, 2, 3
+
+
+class CB200Error(RuntimeError):
+    pass
+
+
+def _check(rc):
+    if rc < 0:
+        raise CB200Error("libcontact_addon_b200 error %d: %s" % (rc, last_error()))
+    return rc
+
+
+def opt_fft_size(n):
+    return load_library().cb200_opt_fft_size(n)
+
+
+def num_launches():
+    return load_library().cb200_num_launches()
+
+
+def num_sms():
+    return _check(load_library().cb200_num_sms())
+
+
+class CoefSet:
+    """Influence coefficients for (grid, material, rolling step), cached inside the library."""
+
+    def __init__(self, mx, my, dx, dy, gg=(82000.0, 82000.0), poiss=(0.28, 0.28), is_roll=False, chi=0.0, dq=1.0):
+        self.mx, self.my, self.npot, self.dx, self.dy = mx, my, mx * my, dx, dy
+        self.h = _check(load_library().cb200_coefset_create(mx, my, dx, dy, gg[0], gg[1], poiss[0], poiss[1],
+                                                            int(is_roll), chi, dq))
+
+    def plan(self):
+        out = (C.c_int * 8)()
+        _check(load_library().cb200_coefset_plan(self.h, out))
+        return dict(zip(("Fx", "Fy", "C", "nchunk", "smem_bytes", "fits", "nsx", "nsy"), list(out)))
+
+    def block(self, set_, ik, jk):
+        """cf(-mx:mx-1, -my:my-1, ik, jk) as array [iy+my, ix+mx]."""
+        out = np.zeros(4 * self.npot)
+        _check(load_library().cb200_coefset_get_block(self.h, set_, ik, jk, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out.reshape(2 * self.my, 2 * self.mx)
+
+    def vecaijpj(self, p, el, iigs=ALLELM, ikarg=3, jkarg=3, set_=SET_CS, u=None):
+        """HOST buffers through the C-ABI. p: (ncase, 3, npot); el: (ncase, npot) or None. Returns u (ncase,3,npot)."""
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        ncase = p.shape[0]
+        u = np.zeros_like(p) if u is None else np.ascontiguousarray(u, dtype=np.float64)
+        elp = None
+        if el is not None:
+            el = np.ascontiguousarray(el, dtype=np.int32)
+            elp = el.ctypes.data_as(C.POINTER(C.c_int))
+        _check(load_library().cb200_vecaijpj(self.h, set_, ncase, iigs, ikarg, jkarg,
+                                             p.ctypes.data_as(C.POINTER(C.c_double)), elp,
+                                             u.ctypes.data_as(C.POINTER(C.c_double))))
+        return u
+
+    def vecaijpj_dev(self, d_p, d_el, d_u, iigs=ALLELM, ikarg=3, jkarg=3, set_=SET_CS, stream=None):
+        """DEVICE buffers (torch CUDA tensors: d_p, d_u float64 (ncase,3,npot); d_el int32 (ncase,npot) or None)."""
+        ncase = d_p.shape[0]
+        _check(load_library().cb200_vecaijpj_dev(self.h, set_, ncase, iigs, ikarg, jkarg, d_p.data_ptr(),
+                                                 0 if d_el is None else d_el.data_ptr(), d_u.data_ptr(),
+                                                 _stream_ptr(stream)))
+
+    def snorm_batch_dev(self, d_hs, d_el, d_pn, d_un, d_scal, ic_norm, maxgs=999, maxin=20, eps=1e-5, stream=None):
+        """Batched NORM solve on DEVICE tensors; d_scal (ncase,8): [pen, fn, itcg, itnorm, ncon, status, err, -]."""
+        ncase = d_hs.shape[0]
+        _check(load_library().cb200_snorm_batch_dev(self.h, ncase, ic_norm, maxgs, maxin, eps, d_hs.data_ptr(),
+                                                    d_el.data_ptr(), d_pn.data_ptr(),
+                                                    0 if d_un is None else d_un.data_ptr(), d_scal.data_ptr(),
+                                                    _stream_ptr(stream)))
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        import torch
+        return torch.cuda.current_stream().cuda_stream
+    return stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)

@@ -1,0 +1,162 @@
+/*
+ * contact_addon_b200.h -- C-ABI of the B200-native CONTACT hot path (libcontact_addon_b200.so).
+ *
+ * Part 1 re-declares, with identical names, argument lists and calling convention (every scalar by pointer, arrays
+ * with explicit lengths, all void), the entry points of the reference library that lie on the hot path and that a
+ * caller needs to drive it.  Canonical prototypes: /root/reference/matlab_intfc/contact_addon.h:7-148; Fortran
+ * implementations: /root/reference/src/contact_addon.f90 (line numbers cited per function).
+ *
+ * Part 2 (cntc_calculate_batch, cb200_*) is new: the batched case scheduler behind cntc_calculate and the
+ * kernel-level entry points (influence product, NORM solve, coefficient access) used by the parity tests and the
+ * benchmark.  They take plain pointers and sizes only.
+ *
+ * There is no CPU fallback: every entry point that computes needs a CUDA device and reports ierror = -99 otherwise.
+ */
+#ifndef CONTACT_ADDON_B200_H
+#define CONTACT_ADDON_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Part 1: the reference's cntc_* / subs_* interface (module 3, contact problems on a given grid)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* contact_addon.f90:235-442 */
+void cntc_initializefirst(int *ifcver, int *ierror, int *ioutput, const char *c_wrkdir, const char *c_outdir,
+                          const char *c_expnam, int *len_wrkdir, int *len_outdir, int *len_expnam);
+/* contact_addon.f90:446-472 */
+void cntc_initializefirst_new(int *ifcver, int *ierror, int *ioutput, const char *c_wrkdir, const char *c_outdir,
+                          const char *c_expnam, int *len_wrkdir, int *len_outdir, int *len_expnam);
+/* contact_addon.f90:476-576 */
+void cntc_initialize(int *ire, int *imodul, int *ifcver, int *ierror, const char *c_outdir, int *len_outdir);
+/* contact_addon.f90:580-725 */
+void cntc_setglobalflags(int *lenflg, int *params, int *values);
+/* contact_addon.f90:780-973 */
+void cntc_setflags(int *ire, int *icp, int *lenflg, int *params, int *values);
+/* contact_addon.f90:1055-1124 */
+void cntc_setmetadata(int *ire, int *icp, int *lenmta, int *params, double *values);
+/* contact_addon.f90:1128-1283 */
+void cntc_setsolverflags(int *ire, int *icp, int *gdigit, int *nints, int *iparam, int *nreals, double *rparam);
+/* contact_addon.f90:1287-1473 (M = 0: [nu1, nu2, g1, g2]) */
+void cntc_setmaterialparameters(int *ire, int *icp, int *mdigit, int *nparam, double *rparam);
+/* contact_addon.f90:1554-1583 */
+void cntc_settimestep(int *ire, int *icp, double *dt);
+/* contact_addon.f90:1587-1615 */
+void cntc_setreferencevelocity(int *ire, int *icp, double *veloc);
+/* contact_addon.f90:1619-1667 */
+void cntc_setrollingstepsize(int *ire, int *icp, double *chi, double *dq);
+/* contact_addon.f90:1671-1968 (L = 0: [fstat, fkin]) */
+void cntc_setfrictionmethod(int *ire, int *icp, int *imeth, int *nparam, double *params);
+/* contact_addon.f90:1972-2093 */
+void cntc_sethertzcontact(int *ire, int *icp, int *ipotcn, int *nparam, double *rparam);
+/* contact_addon.f90:2097-2257 */
+void cntc_setpotcontact(int *ire, int *icp, int *ipotcn, int *nparam, double *rparam);
+/* contact_addon.f90:2294-2323 */
+void cntc_setpenetration(int *ire, int *icp, double *pen);
+/* contact_addon.f90:2327-2357 */
+void cntc_setnormalforce(int *ire, int *icp, double *fn);
+/* contact_addon.f90:2361-2487 */
+void cntc_setundeformeddistc(int *ire, int *icp, int *ibase, int *nparam, double *prmudf);
+/* contact_addon.f90:2491-2530 */
+void cntc_setcreepages(int *ire, int *icp, double *vx, double *vy, double *phi);
+/* contact_addon.f90:2597-2650 */
+void cntc_settangentialforces(int *ire, int *icp, double *fx, double *fy);
+/* contact_addon.f90:3330-3515 */
+void subs_addblock(int *ire, int *icp, int *iblk, int *isubs, int *nx, int *ny, int *nz, double *xparam,
+                   double *yparam, double *zparam);
+/* contact_addon.f90:3519-3552 -> cntc_calculate3 :3754-3900 -> contac (m_scontc.f90:37-216) */
+void cntc_calculate(int *ire, int *icp, int *ierror);
+/* contact_addon.f90:3904-3997 */
+void subs_calculate(int *ire, int *icp, int *ierror);
+/* contact_addon.f90:4001-4160 */
+void cntc_getflags(int *ire, int *icp, int *nparam, int *iparam, int *values);
+/* contact_addon.f90:5070-5099 */
+void cntc_getnumelements(int *ire, int *icp, int *mx, int *my);
+/* contact_addon.f90:5103-5140 */
+void cntc_getgriddiscretization(int *ire, int *icp, double *dx, double *dy);
+/* contact_addon.f90:5144-5187 */
+void cntc_getpotcontact(int *ire, int *icp, int *lenarr, double *values);
+/* contact_addon.f90:5191-5220 */
+void cntc_getpenetration(int *ire, int *icp, double *pen);
+/* contact_addon.f90:5224-5271 */
+void cntc_getcreepages(int *ire, int *icp, double *vx, double *vy, double *phi);
+/* contact_addon.f90:5275-5318 */
+void cntc_getcontactforces(int *ire, int *icp, double *fn, double *tx, double *ty, double *mz);
+/* contact_addon.f90:5460-5497 */
+void cntc_getcontactpatchareas(int *ire, int *icp, double *carea, double *harea, double *sarea);
+/* contact_addon.f90:5501-5552 */
+void cntc_getelementdivision(int *ire, int *icp, int *lenarr, int *eldiv);
+/* contact_addon.f90:5556-5587 */
+void cntc_getmaximumpressure(int *ire, int *icp, double *pnmax);
+/* contact_addon.f90:5591-5626 */
+void cntc_getmaximumtraction(int *ire, int *icp, double *ptmax);
+/* contact_addon.f90:5672-5823 */
+void cntc_getfielddata(int *ire, int *icp, int *ifld, int *lenarr, double *fld);
+/* contact_addon.f90:5827-5855 */
+void cntc_gettractions(int *ire, int *icp, int *lenarr, double *pn, double *px, double *py);
+/* contact_addon.f90:5859-5885 */
+void cntc_getmicroslip(int *ire, int *icp, int *lenarr, double *sx, double *sy);
+/* contact_addon.f90:5889-5915 */
+void cntc_getdisplacements(int *ire, int *icp, int *lenarr, double *un, double *ux, double *uy);
+/* contact_addon.f90:6011-6067 */
+void cntc_getcalculationtime(int *ire, int *icp, double *tcpu, double *twall);
+/* contact_addon.f90:6071-6109 */
+void subs_getblocksize(int *ire, int *icp, int *iblk, int *nx, int *ny, int *nz);
+/* contact_addon.f90:6113-6178 */
+void subs_getresults(int *ire, int *icp, int *iblk, int *lenarr, int *ncol, int *icol, double *values);
+/* contact_addon.f90:6243 */
+void cntc_finalize(int *ire);
+void cntc_finalizelast(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Part 2: B200 extensions
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Batched case scheduler behind cntc_calculate: solve nre result elements (same icp) in ONE launch per grid class.
+ * ierror[k] receives what cntc_calculate(ire[k], icp) would have returned. */
+void cntc_calculate_batch(int *nre, int *ire, int *icp, int *ierror);
+
+/* last error message of the calling thread (NUL-terminated, owned by the library) */
+const char *cb200_last_error(void);
+/* number of kernels launched by the library so far (bench.py: "gpu_launches") */
+long cb200_num_launches(void);
+/* number of SMs of the device in use, or -99 */
+int cb200_num_sms(void);
+
+/* opt_fft_size (m_aijpj.f90:1022-1119) */
+int cb200_opt_fft_size(int n);
+
+/* Coefficient set for (grid, material, rolling step): returns handle >= 0 or a negative error.
+ * gg, poiss: per body; is_roll/chi/dq as in sgencr (m_visc.f90:127-376). */
+int cb200_coefset_create(int mx, int my, double dx, double dy, double gg1, double gg2, double poiss1, double poiss2,
+                         int is_roll, double chi, double dq);
+/* copy the spatial block cf(-mx:mx-1,-my:my-1,ik,jk) of set (0 cs, 1 cv, 2 csv, 3 ms) to the host buffer (4*mx*my) */
+int cb200_coefset_get_block(int handle, int set, int ik, int jk, double *out);
+/* plan information: out[0..7] = Fx, Fy, C, nchunk, smem_bytes, fits, nsx, nsy */
+int cb200_coefset_plan(int handle, int *out);
+
+/* VecAijPj (m_aijpj.f90:258-451) for ncase independent right-hand sides sharing one coefficient set.
+ * p, u: [ncase][3][npot] (direction-major per case, x fastest); el: [ncase][npot] or NULL;
+ * iigs -9 (AllElm) / -8 (AllInt); ikarg, jkarg: 1..3, -2 (tangential), -3 (all).  HOST buffers. */
+int cb200_vecaijpj(int handle, int set, int ncase, int iigs, int ikarg, int jkarg, const double *p, const int *el,
+                   double *u);
+/* same with DEVICE buffers, asynchronous on `stream` (a cudaStream_t passed as void*) */
+int cb200_vecaijpj_dev(int handle, int set, int ncase, int iigs, int ikarg, int jkarg, const double *d_p,
+                       const int *d_el, double *d_u, void *stream);
+
+/* Batched NORM solve (snorm + NormCG, m_snorm.f90:31-378, m_solvpn.f90:24-461) on DEVICE buffers.
+ *   d_hs [ncase][npot] undeformed distance; d_el [ncase][npot] in/out element division;
+ *   d_pn [ncase][npot] in/out pressures; d_un [ncase][npot] out (may be NULL): u_n = A_zz p_n on the contact area;
+ *   d_scal [ncase][8] in/out doubles: pen, fn, (out) itcg, itnorm, ncon, status, err, reserved.
+ * ic_norm: 0 approach prescribed (pen in), 1 force prescribed (fn in). */
+int cb200_snorm_batch_dev(int handle, int ncase, int ic_norm, int maxgs, int maxin, double eps, const double *d_hs,
+                          int *d_el, double *d_pn, double *d_un, double *d_scal, void *stream);
+/* workspace the batched solve keeps per case, bytes (for memory planning) */
+long cb200_snorm_workspace_bytes(int handle, int ncase);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

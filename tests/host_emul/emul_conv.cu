@@ -1,0 +1,76 @@
+// Host emulation of the fused convolution: steps the *product's* phase functions (fftconv.cuh) through all thread
+// ids sequentially on the CPU.  Test infrastructure only -- lets the CPU-only test suite validate the exact device
+// algorithm (indexing, digit-reversed C^ layout, split/merge steps) against the oracle without a GPU.
+#include <vector>
+#include <cstdio>
+#include "../../contact_b200/csrc/plan.h"
+
+using namespace cb200;
+
+#define CB_PHASE(call) do { for (int tid = 0; tid < nthr; tid++) { call; } } while (0)
+#include "../../contact_b200/csrc/conv_sequence.inc"
+
+extern "C" int emul_plan_info(int mx, int my, int *out)
+{
+    HostPlan hp;
+    if (!make_plan(mx, my, hp)) return -1;
+    out[0] = hp.p.Fx; out[1] = hp.p.Fy; out[2] = hp.p.C; out[3] = hp.p.nchunk; out[4] = hp.p.smem_bytes;
+    out[5] = hp.fits; out[6] = hp.p.nsx; out[7] = hp.p.nsy;
+    for (int i = 0; i < CB_MAXSTAGE; i++) { out[8 + i] = hp.p.rx[i]; out[16 + i] = hp.p.ry[i]; }
+    return 0;
+}
+
+// u = mask (.) conv(cf block, p) * scale ; cf block has half sizes (cmx, cmy)
+extern "C" int emul_conv(int mx, int my, const double *p, const double *cfblk, int cmx, int cmy, double scale,
+                         const int *el, int mask_mode, int add, double *u, int nthr)
+{
+    HostPlan hp;
+    if (!make_plan(mx, my, hp)) return -1;
+    const ConvPlan &P = hp.p;
+    const cd *twx = hp.twx.data(), *twy = hp.twy.data();
+    const unsigned short *posx = hp.posx.data();
+
+    // --- build C^ with the coefficient sequence (global-scratch style: S holds all 2Fy rows)
+    std::vector<cd> chat(P.chat_len);
+    {
+        const int SY = 2 * P.Fy;
+        std::vector<cd> Sg((size_t) (P.Lx + 1) * SY), Wg((size_t) P.Ly * P.C);
+        cd *S = Sg.data(), *W = Wg.data();
+        RowSrc src = { cfblk, 1, P.Fx < mx ? P.Fx : mx, P.Fy < my ? P.Fy : my, cmx, cmy, P.Fx, P.Fy, 0 };
+        CB_CONV_FORWARD_ROWS(2 * P.Fy, src);
+        CB_CONV_COLUMNS_DUMP(2 * P.Fy, chat.data(), scale / (4.0 * P.Fx * P.Fy));
+    }
+    // --- the product
+    {
+        const int SY = P.SY;
+        std::vector<cd> Ss((size_t) (P.Lx + 1) * SY), Ws((size_t) P.Ly * P.C);
+        cd *S = Ss.data(), *W = Ws.data();
+        RowSrc src = { p, 0, mx, my, 0, 0, P.Fx, P.Fy, 0 };
+        CB_CONV_FORWARD_ROWS(P.my, src);
+        CB_CONV_COLUMNS_PRODUCT(P.my, chat.data());
+        CB_CONV_INVERSE_ROWS(P.my);
+        CB_PHASE(row_store(P, S, SY, u, el, mask_mode, add, tid, nthr));
+    }
+    return 0;
+}
+
+// radix butterflies against a naive DFT
+extern "C" double emul_radix_error(int R, int inv)
+{
+    cd x[16], y[16];
+    double err = 0.0;
+    for (int q = 0; q < R; q++) { x[q] = make_double2(0.3 + 0.7 * q - 0.05 * q * q, -0.2 + 0.11 * q * q * q / 7.0); y[q] = x[q]; }
+#define RUN(RR) case RR: if (inv) Dft<RR, true>::run(y); else Dft<RR, false>::run(y); break;
+    switch (R) { RUN(2) RUN(3) RUN(4) RUN(5) RUN(7) RUN(8) RUN(9) RUN(16) default: return -1; }
+    const double pi = 3.14159265358979323846, sg = inv ? 1.0 : -1.0;
+    for (int k = 0; k < R; k++) {
+        double re = 0, im = 0;
+        for (int q = 0; q < R; q++) {
+            const double a = sg * 2.0 * pi * q * k / R;
+            re += x[q].x * cos(a) - x[q].y * sin(a);
+            im += x[q].x * sin(a) + x[q].y * cos(a);
+        }
+        err = fmax(err, fmax(fabs(re - y[k].x), fabs(im - y[k].y)));
+    }
+    return err;
+}

@@ -1,0 +1,198 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-9          # north_star: forces, tractions, displacements within 1e-9 relative
+
+
+def _rel(a, b):
+    s = np.abs(b).max()
+    return np.abs(a - b).max() / (s if s > 0 else 1.0)
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import contact_b200
+    contact_b200.load_library()
+    return contact_b200
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+@pytest.mark.parametrize("mx,my,dx,dy,poiss", [(19, 19, 0.13333, 0.13333, (0.42, 0.42)), (91, 91, 0.1, 0.1, (0.28, 0.28)),
+                                               (71, 81, 0.1, 0.1, (0.28, 0.28)), (12, 7, 0.2, 0.3, (0.0, 0.3))])
+def test_coefficients_match_oracle(cb, O, mx, my, dx, dy, poiss):
+    gg = (82000.0, 60000.0) if poiss[0] != poiss[1] else (82000.0, 82000.0)
+    cset = cb.lowlevel.CoefSet(mx, my, dx, dy, gg=gg, poiss=poiss)
+    m = O.mater(gg=gg, poiss=poiss)
+    cs, cv, csv, ms = O.sgencr(m, mx, my, dx, dy)
+    for ik in (1, 2, 3):
+        for jk in (1, 2, 3):
+            ref = cs.block(ik, jk)
+            got = cset.block(0, ik, jk)
+            scale = np.abs(cs.block(3, 3)).max()
+            assert np.abs(got - ref).max() <= 2e-11 * scale, (ik, jk)   # 4-corner cancellation x 1-ulp libm differences
+    O.inflcf_free(cs, cv, csv, ms)
+
+
+@pytest.mark.parametrize("mx,my", [(19, 19), (91, 91), (71, 81), (43, 93), (11, 11), (35, 35), (5, 1), (1, 7), (3, 2)])
+def test_vecaijpj_matches_oracle(cb, O, mx, my):
+    dx, dy = 0.1, 0.13
+    cset = cb.lowlevel.CoefSet(mx, my, dx, dy)
+    assert cset.plan()["fits"] == 1
+    m = O.mater()
+    cs, cv, csv, ms = O.sgencr(m, mx, my, dx, dy)
+    ncase = 5
+    p, el = cases.microbench_p(mx, my, ncase)
+    rng = np.random.default_rng(3)
+    el = (rng.random((ncase, mx * my)) < 0.6).astype(np.int32)
+    p = p * 0 + rng.standard_normal(p.shape) * el[:, None, :]
+    for iigs in (cb.lowlevel.ALLELM, cb.lowlevel.ALLINT):
+        u0 = rng.standard_normal(p.shape)
+        got = cset.vecaijpj(p, el, iigs=iigs, ikarg=3, jkarg=3, u=u0.copy())
+        for ic in range(ncase):
+            igs = O.EldivBuf(mx, my, el[ic])
+            ctx = O.Ctx(fullbox=True)
+            ref = u0[ic].copy()
+            O.vecaijpj(ctx, igs, iigs, ref, 3, np.ascontiguousarray(p[ic]), 3, cs)
+            assert _rel(got[ic, 2], ref[2]) < 2e-11      # includes the 1e-12 coefficient difference (device vs host libm)
+            # rows of other directions and unselected elements are untouched
+            assert np.array_equal(got[ic, :2], u0[ic, :2])
+    O.inflcf_free(cs, cv, csv, ms)
+
+
+def test_vecaijpj_all_blocks_coupled_material(cb, O):
+    mx, my, dx, dy = 33, 27, 0.2, 0.15
+    gg, poiss = (0.5, 1e5), (0.0, 0.0)             # Spence material: AK ~ 0.5 -> n-t coupling (spence71_8281pt.inp:10)
+    cset = cb.lowlevel.CoefSet(mx, my, dx, dy, gg=gg, poiss=poiss)
+    m = O.mater(gg=gg, poiss=poiss)
+    cs, cv, csv, ms = O.sgencr(m, mx, my, dx, dy)
+    rng = np.random.default_rng(11)
+    el = (rng.random((2, mx * my)) < 0.7).astype(np.int32)
+    p = rng.standard_normal((2, 3, mx * my)) * el[:, None, :]
+    got = cset.vecaijpj(p, el, iigs=cb.lowlevel.ALLELM, ikarg=-3, jkarg=-3)
+    for ic in range(2):
+        igs = O.EldivBuf(mx, my, el[ic])
+        ref = np.zeros((3, mx * my))
+        O.vecaijpj(O.Ctx(fullbox=True), igs, -9, ref, -3, np.ascontiguousarray(p[ic]), -3, cs)
+        assert _rel(got[ic], ref) < 2e-11
+    O.inflcf_free(cs, cv, csv, ms)
+
+
+@pytest.mark.parametrize("mx,my", [(19, 19), (91, 91), (12, 7)])
+def test_preconditioner_matches_oracle(cb, O, mx, my):
+    dx, dy = 0.1, 0.1
+    cset = cb.lowlevel.CoefSet(mx, my, dx, dy)
+    m = O.mater()
+    cs, cv, csv, ms = O.sgencr(m, mx, my, dx, dy)
+    ctx = O.Ctx()
+    O.fft_makeprec(ctx, 3, cs, 3, ms)
+    ref = ms.block(3, 3)
+    got = cset.block(cb.lowlevel.SET_MS, 3, 3)
+    assert _rel(got, ref) < 1e-10
+    O.inflcf_free(cs, cv, csv, ms)
+
+
+def _solve_gpu(cb, g, mat, ic_norm, pens, fns, maxgs, maxin, eps, h=None):
+    import torch
+    mx, my = g["mx"], g["my"]
+    npot = mx * my
+    ncase = len(pens)
+    cset = cb.lowlevel.CoefSet(mx, my, g["dx"], g["dy"], **mat)
+    h = cases.quadratic_h(g) if h is None else h
+    # initial element division through the public API's own host logic is tested elsewhere; here: oracle-free guess
+    d_hs = torch.tensor(np.tile(h, (ncase, 1)), dtype=torch.float64, device="cuda")
+    return cset, d_hs
+
+
+def test_cntc_normal_problem_cattaneo(cb, O):
+    """examples/cattaneo.inp case 2, normal part: 197 -> 177 elements, ItCG 6, approach 1.998e-2, pmax 4.393."""
+    c = cases.CATTANEO2
+    ire, icp = 11, 1
+    cb.cntc_initialize(ire, 3)
+    cb.cntc_setflags(ire, icp, [cb.CNTC["if_units"], cb.CNTC["ic_tang"], cb.CNTC["ic_iestim"]], [cb.CNTC["un_cntc"], 0, 0])
+    cb.cntc_setsolverflags(ire, icp, 0, [c["maxgs"], c["maxin"], 30, 1], [c["eps"]])
+    cb.cntc_setmaterialparameters(ire, icp, 0, [c["poiss"][0], c["poiss"][1], c["gg"][0], c["gg"][1]])
+    cb.cntc_setpotcontact(ire, icp, 1, [c["mx"], c["my"], c["xl"], c["yl"], c["dx"], c["dy"]])
+    cb.cntc_setundeformeddistc(ire, icp, 1, c["prmudf"])
+    cb.cntc_setnormalforce(ire, icp, c["fn"])
+    ierr = cb.cntc_calculate(ire, icp)
+    assert ierr == 0, cb.lib.last_error()
+    ref = O.norm_case(c["mx"], c["my"], c["xl"], c["yl"], c["dx"], c["dy"], c["gg"], c["poiss"], 1, c["prmudf"], 1,
+                      fn=c["fn"], maxgs=c["maxgs"], maxin=c["maxin"], eps=c["eps"])
+    el = cb.cntc_getelementdivision(ire, icp)
+    pn, px, py = cb.cntc_gettractions(ire, icp)
+    assert int((el > 0).sum()) == 177
+    assert np.array_equal(el.ravel(), ref["el"])                       # flags bit-exact
+    assert _rel(pn.ravel(), ref["pn"]) < REL
+    assert abs(cb.cntc_getpenetration(ire, icp) - ref["pen"]) < REL * abs(ref["pen"])
+    assert abs(cb.cntc_getpenetration(ire, icp) - 1.998e-2) < 1e-5     # cattaneo.ref_out: APPROACH 1.998E-02
+    assert abs(cb.cntc_getmaximumpressure(ire, icp) - 4.393) < 1e-3    # cattaneo.ref_out: PMAX 4.393
+    fn, tx, ty, mz = cb.cntc_getcontactforces(ire, icp)
+    assert abs(fn - c["fn"]) < 1e-12 * c["fn"] and tx == 0 and ty == 0
+    un, ux, uy = cb.cntc_getdisplacements(ire, icp)
+    # in the contact area: h - pen + un = 0 (to solver accuracy)
+    h = cases.quadratic_h(c)
+    resid = (h - ref["pen"] + un.ravel())[el.ravel() > 0]
+    assert np.abs(resid).max() < 5e-4 * ref["pen"]
+    cb.cntc_finalize(ire)
+
+
+@pytest.mark.parametrize("k,mx,my,dx,ncon,itcg", [(1, 71, 81, 0.1, 3148, 19)])
+def test_cntc_mbench_norm_problem(cb, O, mbench, k, mx, my, dx, ncon, itcg):
+    """perfc_test/norm_problm_1p.inp: ncon 3148, ItCG 19 (perfc_test/get_times.ref_out:7)."""
+    ire, icp = 12, 1
+    cb.cntc_initialize(ire, 3)
+    cb.cntc_setflags(ire, icp, [cb.CNTC["ic_tang"]], [0])
+    cb.cntc_setsolverflags(ire, icp, 0, [1000, 100, 30, 1], [1e-7])
+    cb.cntc_setmaterialparameters(ire, icp, 0, [0.28, 0.28, 82000.0, 82000.0])
+    cb.cntc_setpotcontact(ire, icp, 1, [mx, my, -3.55, -6.15, dx, dx])
+    cb.cntc_setundeformeddistc(ire, icp, 2, mbench["prmudf"])
+    cb.cntc_setpenetration(ire, icp, mbench["pen"])
+    ierr = cb.cntc_calculate(ire, icp)
+    assert ierr >= 0, cb.lib.last_error()
+    ref = O.norm_case(mx, my, -3.55, -6.15, dx, dx, (82000.0, 82000.0), (0.28, 0.28), 2, mbench["prmudf"], 0,
+                      pen=mbench["pen"], maxgs=1000, maxin=100, eps=1e-7, nn=mbench["nn"])
+    el = cb.cntc_getelementdivision(ire, icp)
+    pn, _, _ = cb.cntc_gettractions(ire, icp)
+    assert int((el > 0).sum()) == ncon == int((ref["el"] > 0).sum())
+    assert np.array_equal(el.ravel(), ref["el"])
+    assert _rel(pn.ravel(), ref["pn"]) < 1e-6          # both stop at eps=1e-7 relative updates
+    fn, _, _, _ = cb.cntc_getcontactforces(ire, icp)
+    assert abs(fn - ref["fn"]) < 1e-7 * ref["fn"]
+    cb.cntc_finalize(ire)
+
+
+def test_batch_hertz91_matches_oracle(cb, O):
+    """hertz-91: 91x91 quadratic gap, steel, prescribed force; batch through cntc_calculate_batch."""
+    g = cases.HERTZ91
+    ncase = 6
+    fns, _ = cases.hertz91_fn(ncase)
+    ires = list(range(21, 21 + ncase))
+    for ire, fn in zip(ires, fns):
+        cb.cntc_initialize(ire, 3)
+        cb.cntc_setflags(ire, 1, [cb.CNTC["ic_tang"]], [0])
+        cb.cntc_setsolverflags(ire, 1, 0, [999, 20, 25, 1], [1e-6])
+        cb.cntc_setmaterialparameters(ire, 1, 0, [0.28, 0.28, 82000.0, 82000.0])
+        cb.cntc_setpotcontact(ire, 1, 1, [g["mx"], g["my"], g["xl"], g["yl"], g["dx"], g["dy"]])
+        cb.cntc_setundeformeddistc(ire, 1, 1, g["prmudf"])
+        cb.cntc_setnormalforce(ire, 1, float(fn))
+    ierr = cb.cntc_calculate_batch(ires, 1)
+    assert (ierr >= 0).all(), (ierr, cb.lib.last_error())
+    for ire, fn in zip(ires, fns):
+        ref = O.norm_case(g["mx"], g["my"], g["xl"], g["yl"], g["dx"], g["dy"], (82000.0, 82000.0), (0.28, 0.28), 1,
+                          g["prmudf"], 1, fn=float(fn), maxgs=999, maxin=20, eps=1e-6)
+        el = cb.cntc_getelementdivision(ire, 1)
+        pn, _, _ = cb.cntc_gettractions(ire, 1)
+        assert np.array_equal(el.ravel(), ref["el"])
+        assert _rel(pn.ravel(), ref["pn"]) < 1e-6
+        assert abs(cb.cntc_getpenetration(ire, 1) - ref["pen"]) < 1e-7 * abs(ref["pen"])
+        cb.cntc_finalize(ire)
