@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- contact solves/s on the 8281-element (91x91) grid, with roofline and CPU baseline.
+
+Contract (driver):  python bench.py --gpus N --steps K --warmup W   [--impl reference]
+One "step" = one batch of independent synthetic contact cases ("hertz-91", SURVEY.md 8(d): grid of
+perfc_test/spence71_8281pt.inp:12, quadratic gap, steel, prescribed normal force FN = FN0 (1 + 0.2 u)) solved by the
+device-resident NORM/NormCG path.  Cases are sharded over ranks with no data-path collective (weak scaling: the batch
+per GPU is fixed); the only exchange is the timing reduction.
+
+  value  : whole-job solves/s, inputs resident in HBM when the timed region starts (device buffers, CUDA events)
+  e2e    : the same metric through the C-ABI with HOST buffers (pinned): h2d of gap/element division/pressures and
+           d2h of pressures/displacements/element division inside the timed region
+  roofline : dominant kernel k_snorm_batch; achieved = algorithmic product bytes (npot*(8*(ni+nj)+1) per 1x1
+           product, shared coefficients amortised) / kernel time from CUDA events on its stream
+  cpu_baseline : the CPU oracle (restatement of the reference algorithm, "port") timed on one host core on a bounded
+           sample of the same cases
+  --impl reference : the oracle with all host threads (one case per thread, as test_table.f90 / run_perfc.pl)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from tests import cases  # noqa: E402  (seeded synthetic inputs only; no oracle import here)
+
+FN0 = 50000.0
+EPS, MAXGS, MAXIN = 1e-6, 999, 20
+METRIC, UNIT = "contact_solves_per_s_8281el", "solves/s"
+
+
+def workload_config(ncase_per_gpu, n_gpus):
+    return {"workload": "hertz-91: 91x91 (8281-element) normal contact, NormCG/NORM, quadratic gap of "
+                        "spence71_8281pt.inp, steel, FN=5e4*(1+0.2u) seed 20240229, eps 1e-6",
+            "cases_per_gpu": ncase_per_gpu, "cases_total": ncase_per_gpu * n_gpus,
+            "l2_policy": "inputs larger than L2: per-step state (gap, element division, pressures, 9 work vectors per "
+                         "case) exceeds 126 MB and is rewritten every step",
+            "parallelism": "independent cases sharded over %d GPU(s), no data-path collective" % n_gpus}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+class ClockSampler:
+    """nvidia-smi clocks during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 6:
+                continue
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except ValueError:
+                continue
+            for nme, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def initial_state(g, fns):
+    """Host-side solver inputs of each case: gap h, initial element division and pressure (zero)."""
+    import contact_b200  # noqa: F401
+    h = cases.quadratic_h(g)
+    ncase, npot = len(fns), g["mx"] * g["my"]
+    hs = np.tile(h, (ncase, 1))
+    from contact_b200 import lowlevel as ll
+    el = np.zeros((ncase, npot), dtype=np.int32)
+    pn = np.zeros((ncase, npot))
+    scal = np.zeros((ncase, 8))
+    scal[:, 1] = fns
+    for i, fn in enumerate(fns):        # the reference's own initial estimate (eldiv0), library host logic
+        el[i], scal[i, 0] = ll.eldiv0(g["mx"], g["my"], g["dx"], g["dy"], cases.STEEL["gg"], cases.STEEL["poiss"],
+                                      g["ibase"], g["prmudf"] + [0.0, 0.0], 1, float(fn), 0.0, h)
+    return hs, el, pn, scal
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import contact_b200 as cb
+    ll = cb.lowlevel
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; contact_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cb.load_library()
+
+    g = cases.HERTZ91
+    npot = g["mx"] * g["my"]
+    nsm = ll.num_sms()
+    ncase = args.cases if args.cases > 0 else 8 * nsm           # multiple of the SM count: one CTA per case, 8 waves
+    fns_all, _ = cases.hertz91_fn(ncase * world, fn0=FN0)
+    fns = fns_all[rank * ncase:(rank + 1) * ncase]               # static block sharding of the case index
+    cset = ll.CoefSet(g["mx"], g["my"], g["dx"], g["dy"], **cases.STEEL)
+    hs0, el0, pn0, scal0 = initial_state(g, fns)
+
+    dev = torch.device("cuda", local)
+    d_hs = torch.tensor(hs0, device=dev)
+    d_el0 = torch.tensor(el0, device=dev); d_pn0 = torch.tensor(pn0, device=dev); d_scal0 = torch.tensor(scal0, device=dev)
+    d_el = torch.empty_like(d_el0); d_pn = torch.empty_like(d_pn0); d_scal = torch.empty_like(d_scal0)
+    d_un = torch.empty_like(d_pn0)
+
+    def step_device():
+        d_el.copy_(d_el0); d_pn.copy_(d_pn0); d_scal.copy_(d_scal0)          # fresh initial estimate every step
+        cset.snorm_batch_dev(d_hs, d_el, d_pn, d_un, d_scal, ic_norm=1, maxgs=MAXGS, maxin=MAXIN, eps=EPS)
+
+    # pinned host buffers for the e2e leg
+    p_hs = torch.tensor(hs0).pin_memory(); p_el = torch.tensor(el0).pin_memory(); p_pn = torch.tensor(pn0).pin_memory()
+    p_un = torch.zeros(ncase, npot, dtype=torch.float64).pin_memory(); p_scal = torch.tensor(scal0).pin_memory()
+
+    def step_host():
+        p_el.copy_(torch.from_numpy(el0)); p_pn.zero_(); p_scal.copy_(torch.from_numpy(scal0))
+        cset.snorm_batch(p_hs.numpy(), p_el.numpy(), p_pn.numpy(), p_un.numpy(), p_scal.numpy(), ic_norm=1,
+                         maxgs=MAXGS, maxin=MAXIN, eps=EPS)
+        return float(p_scal[0, 0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg ----
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    launches0 = ll.num_launches()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern_ms = []
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+        kern_ms.append(None)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = ll.num_launches() - launches0
+    # solver-kernel time alone: re-time with the library's own events (one extra step, same stream, same state)
+    kt = []
+    for _ in range(min(3, args.steps)):
+        step_device()
+        kt.append(ll.snorm_kernel_ms())
+    kernel_ms = float(np.mean(kt))
+    scal = d_scal.cpu().numpy()
+    nprod = float(scal[:, 7].sum())
+    itcg_mean = float(scal[:, 2].mean())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end leg (host buffers through the C-ABI) ----
+    for _ in range(max(1, min(args.warmup, 2))):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        step_host()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    t = torch.tensor([ms_total, e2e_s, kernel_ms, nprod], dtype=torch.float64, device=dev)
+    tmax = t.clone()
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        nprod_all = float(tsum[3])
+    else:
+        nprod_all = nprod
+    ms_total, e2e_s, kernel_ms = float(tmax[0]), float(tmax[1]), float(tmax[2])
+
+    if rank == 0:
+        peaks = {}
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            peaks = json.load(open(pk))
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        value = ncase * world * args.steps / (ms_total * 1e-3)
+        alg_bytes_prod = npot * (8 * 2 + 1)                       # B_batched = npot (8 (ni+nj) + 1)
+        plan = cset.plan()
+        N = 4.0 * plan["Fx"] * plan["Fy"]; S = (plan["Fx"] + 1) * 2.0 * plan["Fy"]
+        alg_flops_prod = 2 * 2.5 * N * np.log2(N) + 6 * S
+        achieved = nprod * alg_bytes_prod / (kernel_ms * 1e-3) / 1e9          # per launch = this rank's cases
+        fp64_peak = ll.fp64_peak_tflops(3)
+        fp64_ach = nprod * alg_flops_prod / (kernel_ms * 1e-3) / 1e12
+        h2d = int(p_hs.numel() * 8 + p_el.numel() * 4 + p_pn.numel() * 8 + p_scal.numel() * 8)
+        d2h = int(p_pn.numel() * 8 + p_el.numel() * 4 + p_un.numel() * 8 + p_scal.numel() * 8)
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": workload_config(ncase, world),
+            "e2e": {"value": ncase * world * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_snorm_batch", "achieved": achieved, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "note": "batched 91x91 products are FP64/shared-memory bound, not HBM bound; see roofline_fp64"},
+            "roofline_fp64": {"achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                              "frac": fp64_ach / fp64_peak if fp64_peak > 0 else None,
+                              "peak_source": "measured here with a DFMA chain kernel (cb200_fp64_peak_tflops)"},
+            "kernel_ms": kernel_ms, "products_per_step": nprod_all, "mean_itcg": itcg_mean,
+        }
+        if args.cpu_seconds > 0:
+            out["cpu_baseline"] = cpu_baseline(args.cpu_seconds, threads=1)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(budget_s, threads):
+    """The CPU oracle on a bounded sample of the same cases (imports oracle/: allowed for this leg only)."""
+    from oracle import oracle as O
+    g = cases.HERTZ91
+    n = max(threads, 4)
+    fns, _ = cases.hertz91_fn(4096, fn0=FN0)
+    # size the sample from a first small run
+    t0 = time.perf_counter()
+    O.norm_batch(g, cases.STEEL["gg"], cases.STEEL["poiss"], 1, fns[:n], maxgs=MAXGS, maxin=MAXIN, eps=EPS, nthreads=threads)
+    dt = time.perf_counter() - t0
+    ns = int(max(n, min(4096, n * budget_s / max(dt, 1e-3))))
+    t0 = time.perf_counter()
+    r = O.norm_batch(g, cases.STEEL["gg"], cases.STEEL["poiss"], 1, fns[:ns], maxgs=MAXGS, maxin=MAXIN, eps=EPS, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return {"value": ns / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d hertz-91 cases (first of the seeded sweep), %.1f s wall; CPU restatement of the reference "
+                      "algorithm (oracle/), gcc -O2, own mixed-radix FFT instead of MKL" % (ns, dt),
+            "mean_itcg": float(r["itcg"].mean())}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the Fortran/MKL build is impossible here) on
+    all host threads, one case per thread."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = host_cores()
+    from oracle import oracle as O
+    g = cases.HERTZ91
+    fns, _ = cases.hertz91_fn(4096, fn0=FN0)
+    per_step = max(threads, 2 * threads)
+    def one(k):
+        lo = (k * per_step) % (4096 - per_step)
+        t0 = time.perf_counter()
+        O.norm_batch(g, cases.STEEL["gg"], cases.STEEL["poiss"], 1, fns[lo:lo + per_step], maxgs=MAXGS, maxin=MAXIN,
+                     eps=EPS, nthreads=threads)
+        return time.perf_counter() - t0
+    for k in range(args.warmup):
+        one(k)
+    ts = [one(args.warmup + k) for k in range(args.steps)]
+    total = float(np.sum(ts))
+    value = per_step * args.steps / total
+    nsm = 148
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": workload_config(8 * nsm, args.gpus),
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                            "sample": "%d hertz-91 cases per step, one case per thread (test_table.f90 pattern), CPU "
+                                      "restatement of the reference algorithm (oracle/)" % per_step},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cases", type=int, default=0, help="cases per GPU per step (default 8 x SM count)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg (0 = skip)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -29,7 +29,7 @@ def build(force=False, verbose=False):
         return SO
     os.makedirs(LIBDIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
            "-Xcompiler", "-fPIC", "-shared", "-o", SO, os.path.join(CSRC, "contact_addon_b200.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas")

@@ -510,6 +510,25 @@ void cntc_setcreepages(int *ire, int *icp, double *vx, double *vy, double *phi)
 void cntc_settangentialforces(int *ire, int *icp, double *fx, double *fy)
 { int e; Problem *p = activate(*ire, *icp, &e); if (p) { p->fxrel = *fx * p->scl.body; p->fyrel = *fy * p->scl.body; } }
 
+// initial element division and approach estimate of eldiv0 (m_sdis.f90:818-1007) for kernel-level callers
+int cb200_eldiv0(int mx, int my, double dx, double dy, double gg1, double gg2, double poiss1, double poiss2,
+                 int ibase, const double *prmudf, int ic_norm, double fn, double pen_in, const double *h, int *el,
+                 double *pen_out)
+{
+    Problem p;
+    p.mx = mx; p.my = my; p.dx = dx; p.dy = dy; p.ibase = ibase; p.norm = ic_norm; p.fntrue = fn;
+    p.mat.gg[0] = gg1; p.mat.gg[1] = gg2; p.mat.poiss[0] = poiss1; p.mat.poiss[1] = poiss2;
+    combine_material(p.mat);
+    if (prmudf) p.prmudf.assign(prmudf, prmudf + (ibase == 9 ? mx * my : 8));
+    std::vector<double> hv(h, h + (size_t) mx * my);
+    std::vector<int> e;
+    double pen = pen_in;
+    initial_eldiv(p, hv, e, pen);
+    std::copy(e.begin(), e.end(), el);
+    *pen_out = pen;
+    return 0;
+}
+
 void cntc_calculate(int *ire, int *icp, int *ierror)
 {
     Problem *p = activate(*ire, *icp, ierror);

@@ -91,7 +91,12 @@ struct NormBatch {            // persistent device workspace of the batched NORM
     int cap = 0;
     NormCase *d_cases = nullptr;
     double *d_work = nullptr;
-    std::vector<NormCase> h_cases;
+    int *d_next = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;     // bracket the solver kernel alone (roofline timing)
+    // staging for the host-buffer entry point
+    long stage_cap = 0;
+    double *s_hs = nullptr, *s_pn = nullptr, *s_un = nullptr, *s_scal = nullptr;
+    int *s_el = nullptr;
 };
 
 __global__ void k_norm_pack(NormCase *cases, int ncase, int npot, const double *hs, int *el, double *pn, double *un,
@@ -117,7 +122,7 @@ __global__ void k_norm_unpack(const NormCase *cases, int ncase, double *scal)
     if (ic >= ncase) return;
     const NormCase &c = cases[ic];
     double *s = scal + ic * 8;
-    s[0] = c.pen; s[1] = c.fntrue; s[2] = c.itcg; s[3] = c.itnorm; s[4] = c.ncon; s[5] = c.status; s[6] = c.err; s[7] = 0.0;
+    s[0] = c.pen; s[1] = c.fntrue; s[2] = c.itcg; s[3] = c.itnorm; s[4] = c.ncon; s[5] = c.status; s[6] = c.err; s[7] = c.nprod;
 }
 
 // u_n = A_zz p_n on the contact area after the solve (soutpt, m_soutpt.f90:378-385), batched
@@ -134,6 +139,11 @@ inline int snorm_batch_dev(CoefSet &cs, int ncase, int ic_norm, int maxgs, int m
     if ((rc = build_chat(cs, SET_CS, 3, 3, st))) return rc;
     if ((rc = build_chat(cs, SET_MS, 3, 3, st))) return rc;
     NormBatch &B = norm_batch();
+    if (!B.d_next) {
+        CB_CUDA(cudaMalloc(&B.d_next, sizeof(int)));
+        CB_CUDA(cudaEventCreate(&B.ev0));
+        CB_CUDA(cudaEventCreate(&B.ev1));
+    }
     static long cap_bytes = 0;
     const long need = (long) ncase * 9 * P.npot * sizeof(double);
     if (ncase > B.cap || need > cap_bytes) {
@@ -154,7 +164,10 @@ inline int snorm_batch_dev(CoefSet &cs, int ncase, int ic_norm, int maxgs, int m
     proto.ic_norm = ic_norm; proto.maxgs = maxgs; proto.maxin = maxin; proto.eps = eps;
     proto.dxdy = cs.key.dx * cs.key.dy;
     k_norm_pack<<<grid1d(ncase, 128), 128, 0, st>>>(B.d_cases, ncase, P.npot, d_hs, d_el, d_pn, d_un, d_scal, B.d_work, proto);
-    k_snorm_batch<<<launch_blocks(ncase), CB_THREADS, P.smem_bytes, st>>>(P, B.d_cases, ncase);
+    CB_CUDA(cudaMemsetAsync(B.d_next, 0, sizeof(int), st));
+    CB_CUDA(cudaEventRecord(B.ev0, st));
+    k_snorm_batch<<<launch_blocks(ncase), CB_THREADS, P.smem_bytes, st>>>(P, B.d_cases, ncase, B.d_next);
+    CB_CUDA(cudaEventRecord(B.ev1, st));
     k_norm_unpack<<<grid1d(ncase, 128), 128, 0, st>>>(B.d_cases, ncase, d_scal);
     E.launches += 3;
     if (d_un) {
@@ -247,6 +260,77 @@ int cb200_snorm_batch_dev(int handle, int ncase, int ic_norm, int maxgs, int max
     if (!cs) return -99;
     if (ncase < 1) return 0;
     return snorm_batch_dev(*cs, ncase, ic_norm, maxgs, maxin, eps, d_hs, d_el, d_pn, d_un, d_scal, (cudaStream_t) stream);
+}
+
+// host-buffer variant: copies in, solves, copies out (the e2e path of bench.py and of cntc_calculate_batch)
+int cb200_snorm_batch(int handle, int ncase, int ic_norm, int maxgs, int maxin, double eps, const double *hs,
+                      int *el, double *pn, double *un, double *scal)
+{
+    CoefSet *cs = set_from_handle(handle);
+    if (!cs) return -99;
+    if (ncase < 1) return 0;
+    NormBatch &B = norm_batch();
+    const long n = (long) ncase * cs->hp.p.npot;
+    if (n > B.stage_cap) {
+        cudaFree(B.s_hs); cudaFree(B.s_pn); cudaFree(B.s_un); cudaFree(B.s_scal); cudaFree(B.s_el);
+        B.stage_cap = 0;
+        CB_CUDA(cudaMalloc(&B.s_hs, sizeof(double) * n));
+        CB_CUDA(cudaMalloc(&B.s_pn, sizeof(double) * n));
+        CB_CUDA(cudaMalloc(&B.s_un, sizeof(double) * n));
+        CB_CUDA(cudaMalloc(&B.s_scal, sizeof(double) * 8 * ncase));
+        CB_CUDA(cudaMalloc(&B.s_el, sizeof(int) * n));
+        B.stage_cap = n;
+    }
+    cudaStream_t st = 0;
+    CB_CUDA(cudaMemcpyAsync(B.s_hs, hs, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    CB_CUDA(cudaMemcpyAsync(B.s_pn, pn, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    CB_CUDA(cudaMemcpyAsync(B.s_el, el, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    CB_CUDA(cudaMemcpyAsync(B.s_scal, scal, sizeof(double) * 8 * ncase, cudaMemcpyHostToDevice, st));
+    int rc = snorm_batch_dev(*cs, ncase, ic_norm, maxgs, maxin, eps, B.s_hs, B.s_el, B.s_pn, un ? B.s_un : nullptr, B.s_scal, st);
+    if (rc) return rc;
+    CB_CUDA(cudaMemcpyAsync(pn, B.s_pn, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaMemcpyAsync(el, B.s_el, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    if (un) CB_CUDA(cudaMemcpyAsync(un, B.s_un, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaMemcpyAsync(scal, B.s_scal, sizeof(double) * 8 * ncase, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// device time of the most recent solver kernel (k_snorm_batch) alone, ms; synchronises on its end event
+double cb200_snorm_kernel_ms(void)
+{
+    NormBatch &B = norm_batch();
+    if (!B.ev1) return -1.0;
+    if (cudaEventSynchronize(B.ev1) != cudaSuccess) return -1.0;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, B.ev0, B.ev1) != cudaSuccess) return -1.0;
+    return (double) ms;
+}
+
+// measured FP64 FMA throughput of the device in TFLOP/s (2 flops per FMA), best of `reps`
+double cb200_fp64_peak_tflops(int reps)
+{
+    if (engine_init()) return -1.0;
+    Engine &E = engine();
+    const int blocks = E.num_sms * 8, threads = 256, iters = 1 << 15;
+    double *out = nullptr;
+    if (cudaMalloc(&out, sizeof(double) * blocks * threads) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int r = 0; r < reps + 1; r++) {
+        cudaEventRecord(e0, 0);
+        k_fp64_peak<<<blocks, threads>>>(out, iters);
+        cudaEventRecord(e1, 0);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        E.launches++;
+        const double tf = 2.0 * 8.0 * (double) iters * blocks * threads / (ms * 1e-3) / 1e12;
+        if (r > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    return best;
 }
 
 long cb200_snorm_workspace_bytes(int handle, int ncase)

@@ -12,6 +12,7 @@ struct Smem {
     cd *S, *W, *twx, *twy;
     unsigned short *posx;
     double *red;       // 128 doubles of reduction scratch
+    uint32_t a0;                  // shared-window address of the dynamic shared memory base
 };
 
 __device__ __forceinline__ Smem smem_view(const ConvPlan &P, unsigned char *base)
@@ -23,6 +24,7 @@ __device__ __forceinline__ Smem smem_view(const ConvPlan &P, unsigned char *base
     s.twy = reinterpret_cast<cd *>(base + P.off_twy);
     s.posx = reinterpret_cast<unsigned short *>(base + P.off_posx);
     s.red = reinterpret_cast<double *>(base + P.off_red);
+    s.a0 = (uint32_t) __cvta_generic_to_shared(base);
     return s;
 }
 
@@ -38,20 +40,25 @@ __device__ __forceinline__ void smem_load_tables(const ConvPlan &P, const Smem &
 #include "conv_sequence.inc"
 
 // u (masked) = conv(p) with transformed coefficients chat.  All threads of the CTA must call.
-__device__ __forceinline__ void conv_dev(const ConvPlan &P, const Smem &sm, const double *p, const cd *chat,
+__device__ __noinline__ void conv_dev(const ConvPlan &P, const Smem &sm, const double *p, const cd *chat,
                                          double *u, const int *el, int mask_mode, int add)
 {
     const int tid = threadIdx.x, nthr = blockDim.x;
-    cd *S = sm.S, *W = sm.W;
-    const cd *twx = sm.twx, *twy = sm.twy;
-    const unsigned short *posx = sm.posx;
+    // re-derive the pointers from the shared-window address: the compiler then proves the state space and emits
+    // LDS/STS (the generic pointers in Smem travel through a non-inlined call and would become generic LD/ST)
+    typedef MemBuf<cd> CB_BUF;
+    const CB_BUF BUF = { reinterpret_cast<cd *>(__cvta_shared_to_generic(sm.a0)) };
+    const uint32_t oS = P.off_S / 16, oW = P.off_W / 16;
+    const MemBuf<const cd> twx = { reinterpret_cast<const cd *>(__cvta_shared_to_generic(sm.a0 + P.off_twx)) };
+    const MemBuf<const cd> twy = { reinterpret_cast<const cd *>(__cvta_shared_to_generic(sm.a0 + P.off_twy)) };
+    const MemBuf<const unsigned short> posx = { reinterpret_cast<const unsigned short *>(__cvta_shared_to_generic(sm.a0 + P.off_posx)) };
     const int SY = P.SY;
     RowSrc src;
     src.base = p; src.kind = 0; src.mx = P.mx; src.my = P.my; src.cmx = 0; src.cmy = 0; src.Fx = P.Fx; src.Fy = P.Fy; src.row0 = 0;
     CB_CONV_FORWARD_ROWS(P.my, src);
     CB_CONV_COLUMNS_PRODUCT(P.my, chat);
     CB_CONV_INVERSE_ROWS(P.my);
-    CB_PHASE(row_store(P, S, SY, u, el, mask_mode, add, tid, nthr));
+    CB_PHASE(row_store(P, BUF, oS, SY, u, el, mask_mode, add, tid, nthr));
 }
 
 // ---- deterministic block reductions (fixed shuffle tree; result broadcast to all threads) ----

@@ -95,7 +95,6 @@ inline int engine_init()
     CB_CUDA(cudaGetDeviceProperties(&prop, dev));
     E.device = dev;
     E.num_sms = prop.multiProcessorCount;
-    CB_CUDA(cudaFuncSetAttribute(k_conv_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     CB_CUDA(cudaFuncSetAttribute(k_snorm_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     CB_CUDA(cudaFuncSetAttribute(k_build_chat, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     return 0;
@@ -109,19 +108,17 @@ inline int build_chat(CoefSet &cs, int set, int ik, int jk, cudaStream_t st)
     Engine &E = engine();
     if (cs.d_chat[set][ik - 1][jk - 1]) return 0;
     const ConvPlan &P = cs.hp.p;
-    cd *chat = nullptr, *Sg = nullptr, *Wg = nullptr;
+    cd *chat = nullptr, *SWg = nullptr;
     CB_CUDA(cudaMalloc(&chat, sizeof(cd) * (size_t) P.chat_len));
-    CB_CUDA(cudaMalloc(&Sg, sizeof(cd) * (size_t) (P.Lx + 1) * 2 * P.Fy));
-    CB_CUDA(cudaMalloc(&Wg, sizeof(cd) * (size_t) P.Ly * P.C));
+    CB_CUDA(cudaMalloc(&SWg, sizeof(cd) * ((size_t) (P.Lx + 1) * 2 * P.Fy + (size_t) P.Ly * P.C)));
     const double *blk = cs.d_cf[set] + (size_t) ((jk - 1) * 3 + (ik - 1)) * 4 * cs.mx * cs.my;
     const double scale = cs.ga_inv / (4.0 * P.Fx * P.Fy);
     const int smem = (2 * P.Fx + 2 * P.Fy) * 16 + P.Lx * 2 + 64;
-    k_build_chat<<<1, CB_THREADS, smem, st>>>(P, blk, cs.mx, cs.my, scale, Sg, Wg, chat);
+    k_build_chat<<<1, CB_THREADS, smem, st>>>(P, blk, cs.mx, cs.my, scale, SWg, chat);
     E.launches++;
     CB_CUDA(cudaGetLastError());
     CB_CUDA(cudaStreamSynchronize(st));
-    CB_CUDA(cudaFree(Sg));
-    CB_CUDA(cudaFree(Wg));
+    CB_CUDA(cudaFree(SWg));
     cs.d_chat[set][ik - 1][jk - 1] = chat;
     cs.n_chat_built++;
     return 0;

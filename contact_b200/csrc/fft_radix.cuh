@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #define CB_HD __host__ __device__ __forceinline__
+#define CB_HNI __host__ __device__ __noinline__
 
 namespace cb200 {
 
@@ -123,6 +124,7 @@ template <bool INV> struct Dft<9, INV> {
         Dft<3, INV>::run(a); Dft<3, INV>::run(b); Dft<3, INV>::run(c);
         b[1] = cmul(b[1], w1); b[2] = cmul(b[2], w2);
         c[1] = cmul(c[1], w2); c[2] = cmul(c[2], w4);
+#pragma unroll
         for (int k1 = 0; k1 < 3; k1++) {
             cd t[3] = { a[k1], b[k1], c[k1] };
             Dft<3, INV>::run(t);
@@ -154,6 +156,45 @@ template <bool INV> struct Dft<16, INV> {
             cd t[4] = { y[0][k1], y[1][k1], y[2][k1], y[3][k1] };
             Dft<4, INV>::run(t);
             x[k1] = t[0]; x[k1 + 4] = t[1]; x[k1 + 8] = t[2]; x[k1 + 12] = t[3];
+        }
+    }
+};
+
+template <bool INV> struct Dft<6, INV> {
+    static CB_HD void run(cd *x) {
+        // 6 = 2 x 3 (n = 2 n1 + n2, k = k1 + 3 k2): two radix-3 on even / odd samples, twiddles w6^k1, radix-2 across
+        const double g = INV ? 1.0 : -1.0;
+        cd e[3] = { x[0], x[2], x[4] }, o[3] = { x[1], x[3], x[5] };
+        Dft<3, INV>::run(e); Dft<3, INV>::run(o);
+        const cd w1 = make_double2(0.5, g * 0.86602540378443864676), w2 = make_double2(-0.5, g * 0.86602540378443864676);
+        o[1] = cmul(o[1], w1); o[2] = cmul(o[2], w2);
+        x[0] = cadd(e[0], o[0]); x[3] = csub(e[0], o[0]);
+        x[1] = cadd(e[1], o[1]); x[4] = csub(e[1], o[1]);
+        x[2] = cadd(e[2], o[2]); x[5] = csub(e[2], o[2]);
+    }
+};
+
+template <bool INV> struct Dft<12, INV> {
+    static CB_HD void run(cd *x) {
+        // 12 = 3 x 4: n = 3 n1 + n2 (n1 < 4, n2 < 3), k = k1 + 4 k2 (k1 < 4, k2 < 3)
+        const double g = INV ? 1.0 : -1.0;
+        const double c30 = 0.86602540378443864676;
+        cd y[3][4];
+#pragma unroll
+        for (int n2 = 0; n2 < 3; n2++) {
+            cd t[4] = { x[n2], x[3 + n2], x[6 + n2], x[9 + n2] };
+            Dft<4, INV>::run(t);
+            y[n2][0] = t[0]; y[n2][1] = t[1]; y[n2][2] = t[2]; y[n2][3] = t[3];
+        }
+        // twiddles w12^(n2 k1)
+        const cd w1 = make_double2(c30, g * 0.5), w2 = make_double2(0.5, g * c30), w4 = make_double2(-0.5, g * c30);
+        y[1][1] = cmul(y[1][1], w1); y[1][2] = cmul(y[1][2], w2); y[1][3] = mul_mi<INV>(y[1][3]);          // w12^3 = -+i
+        y[2][1] = cmul(y[2][1], w2); y[2][2] = cmul(y[2][2], w4); y[2][3] = make_double2(-y[2][3].x, -y[2][3].y);  // w12^6 = -1
+#pragma unroll
+        for (int k1 = 0; k1 < 4; k1++) {
+            cd t[3] = { y[0][k1], y[1][k1], y[2][k1] };
+            Dft<3, INV>::run(t);
+            x[k1] = t[0]; x[k1 + 4] = t[1]; x[k1 + 8] = t[2];
         }
     }
 };

@@ -15,9 +15,12 @@
 //   stays in digit-reversed order and C^ is simply stored in that same order (built by the same code) -- no
 //   reordering pass, no second buffer.  1/(4 Fx Fy) and 1/G are folded into C^.
 //
-// Every phase is a plain function of (tid, nthr) so that the identical code can be stepped through on the host
-// (tests/host_emul) for validation without a GPU; on the device phases are separated by __syncthreads().
+// Every phase is a plain function of (tid, nthr) templated on a buffer accessor, so that the identical code runs
+// (a) on shared memory through explicit ld.shared/st.shared (ShBuf), (b) on global scratch for the one-off
+// coefficient transforms (MemBuf) and (c) on the host (tests/host_emul) for validation without a GPU.
+// Index arithmetic uses multiply-high "magic" division (no integer divide in the hot loops).
 #pragma once
+#include <stdint.h>
 #include "fft_radix.cuh"
 
 namespace cb200 {
@@ -42,88 +45,136 @@ struct ConvPlan {
     const unsigned short *posx; // [Lx] position of frequency k after the DIF stages
 };
 
+// ---- exact division of small non-negative integers by a run-time constant: q = (n * magic) >> 32 ----
+// magic = floor(2^32/d) + 1 (32-bit divide only: 0xFFFFFFFF/d equals floor(2^32/d) unless d is a power of two, where the
+// +1 lands exactly on 2^32/d); exact for n*d < 2^32; 0 encodes divide-by-1
+CB_HD uint32_t div_magic(uint32_t d) { return d <= 1u ? 0u : 0xFFFFFFFFu / d + 1u; }
+CB_HD uint32_t fdiv(uint32_t n, uint32_t magic)
+{
+#ifdef __CUDA_ARCH__
+    return magic ? __umulhi(n, magic) : n;
+#else
+    return magic ? (uint32_t) (((uint64_t) n * magic) >> 32) : n;
+#endif
+}
+
+// ---- buffer accessors ----
+template <class T> struct MemBuf {          // any memory through a (restrict-free) pointer: global scratch, host, or
+    T *p;                                   // shared memory when the pointer was derived with __cvta_shared_to_generic
+    CB_HD T ld(uint32_t i) const { return p[i]; }
+    CB_HD void st(uint32_t i, T v) const { p[i] = v; }
+};
+
+// ---- 2-D views used by the FFT stages: element e of transform c ----
+// (templated, inlined views and a compile-time forward/inverse switch measured faster on B200 than one shared
+//  run-time body per radix: 83.6k vs 100.5k cycles per 91x91 product, tools/phase_timer.cu, profiles/)
+template <class B> struct ViewLin {          // buf[off + e*estride + c]
+    B buf; uint32_t off, estride;
+    CB_HD cd ld(uint32_t e, uint32_t c) const { return buf.ld(off + e * estride + c); }
+    CB_HD void st(uint32_t e, uint32_t c, cd v) const { buf.st(off + e * estride + c, v); }
+};
+template <class B> struct ViewPad {          // column chunk read straight from S, zero beyond n_in rows (pruned input)
+    B buf; uint32_t off, SY, n_in;           // off = oS + row0*SY
+    CB_HD cd ld(uint32_t e, uint32_t c) const { return e < n_in ? buf.ld(off + c * SY + e) : make_double2(0.0, 0.0); }
+};
+template <class B> struct ViewCrop {         // column chunk written straight back to S, rows e0..e0+ne-1 only (pruned output)
+    B buf; uint32_t off, SY, e0, ne;
+    CB_HD void st(uint32_t e, uint32_t c, cd v) const { const uint32_t r = e - e0; if (r < ne) buf.st(off + c * SY + r, v); }
+};
+
 // ------------------------------------------------------------------------------------------------------------
-// generic in-place stage over a batch of transforms: element e of transform c lives at buf[e*estride + c]
+// one FFT stage over a batch of transforms (in place when in and out view the same buffer).
+// INV = false: decimation in frequency (butterfly, then twiddle); INV = true: its inverse, decimation in time.
 // ------------------------------------------------------------------------------------------------------------
-template <int R, bool INV>
-CB_HD void fft_stage(cd *buf, int nbatch, int estride, int L, int ns, const cd *tw, int twmul, int tid, int nthr)
+template <int R, bool INV, class VI, class VO, class TW>
+CB_HD void fft_stage(VI in, VO out, int nbatch, int L, int ns, TW tw, int twmul, int tid, int nthr)
 {
     const int m = ns / R;
     const int items = (L / R) * nbatch;
     const int tstep = (L / ns) * twmul;
+    const uint32_t mg_b = div_magic(nbatch), mg_m = div_magic(m);
     for (int w = tid; w < items; w += nthr) {
-        const int c = w % nbatch, g = w / nbatch;
-        const int j = g % m, blk = g / m;
-        cd *p = buf + (size_t) (blk * ns + j) * estride + c;
-        const size_t qs = (size_t) m * estride;
+        const uint32_t g = fdiv(w, mg_b), c = w - g * nbatch;
+        const uint32_t blk = fdiv(g, mg_m), j = g - blk * m;
+        const uint32_t e0 = blk * ns + j;
         cd x[R];
 #pragma unroll
-        for (int q = 0; q < R; q++) x[q] = p[q * qs];
+        for (int q = 0; q < R; q++) x[q] = in.ld(e0 + q * m, c);
         if (INV && m > 1) {
             const int t = tstep * j;
 #pragma unroll
-            for (int q = 1; q < R; q++) x[q] = cmulc(x[q], tw[t * q]);
+            for (int q = 1; q < R; q++) x[q] = cmulc(x[q], tw.ld(t * q));
         }
         Dft<R, INV>::run(x);
         if (!INV && m > 1) {
             const int t = tstep * j;
 #pragma unroll
-            for (int q = 1; q < R; q++) x[q] = cmul(x[q], tw[t * q]);
+            for (int q = 1; q < R; q++) x[q] = cmul(x[q], tw.ld(t * q));
         }
 #pragma unroll
-        for (int q = 0; q < R; q++) p[q * qs] = x[q];
+        for (int q = 0; q < R; q++) out.st(e0 + q * m, c, x[q]);
     }
 }
 
-template <bool INV>
-CB_HD void fft_stage_r(int r, cd *buf, int nbatch, int estride, int L, int ns, const cd *tw, int twmul, int tid, int nthr)
+#define CB_RADIX_SWITCH(r, CALL)          \
+    switch (r) {                           \
+    case 2:  { CALL(2); } break;           \
+    case 3:  { CALL(3); } break;           \
+    case 4:  { CALL(4); } break;           \
+    case 5:  { CALL(5); } break;           \
+    case 6:  { CALL(6); } break;           \
+    case 7:  { CALL(7); } break;           \
+    case 8:  { CALL(8); } break;           \
+    case 9:  { CALL(9); } break;           \
+    case 12: { CALL(12); } break;          \
+    case 16: { CALL(16); } break;          \
+    default: break;                        \
+    }
+
+template <bool INV, class VI, class VO, class TW>
+CB_HD void fft_stage_r(int r, VI in, VO out, int nbatch, int L, int ns, TW tw, int twmul, int tid, int nthr)
 {
-    switch (r) {
-    case 2:  fft_stage<2, INV>(buf, nbatch, estride, L, ns, tw, twmul, tid, nthr); break;
-    case 3:  fft_stage<3, INV>(buf, nbatch, estride, L, ns, tw, twmul, tid, nthr); break;
-    case 4:  fft_stage<4, INV>(buf, nbatch, estride, L, ns, tw, twmul, tid, nthr); break;
-    case 5:  fft_stage<5, INV>(buf, nbatch, estride, L, ns, tw, twmul, tid, nthr); break;
-    case 7:  fft_stage<7, INV>(buf, nbatch, estride, L, ns, tw, twmul, tid, nthr); break;
-    case 8:  fft_stage<8, INV>(buf, nbatch, estride, L, ns, tw, twmul, tid, nthr); break;
-    case 9:  fft_stage<9, INV>(buf, nbatch, estride, L, ns, tw, twmul, tid, nthr); break;
-    case 16: fft_stage<16, INV>(buf, nbatch, estride, L, ns, tw, twmul, tid, nthr); break;
-    default: break;
-    }
+#define CB_CALL_(RR) fft_stage<RR, INV>(in, out, nbatch, L, ns, tw, twmul, tid, nthr)
+    CB_RADIX_SWITCH(r, CB_CALL_)
+#undef CB_CALL_
 }
 
-// last forward stage (m = 1, no twiddles) + pointwise multiply with C^ + first inverse stage, in registers
-template <int R>
-CB_HD void fft_stage_mid(cd *buf, int nbatch, int estride, int L, const cd *chat, int tid, int nthr)
+// last forward stage (m = 1, no twiddles) + pointwise multiply with C^ + first inverse stage, in registers.
+// chat is laid out like W: [e][c] with row stride cstride.
+template <int R, class VI, class VO>
+CB_HD void fft_stage_mid(VI in, VO out, int nbatch, int L, const cd *chat, uint32_t cstride, int tid, int nthr)
 {
     const int items = (L / R) * nbatch;
+    const uint32_t mg_b = div_magic(nbatch);
     for (int w = tid; w < items; w += nthr) {
-        const int c = w % nbatch, g = w / nbatch;
-        const size_t o = (size_t) (g * R) * estride + c;
-        cd x[R];
+        const uint32_t g = fdiv(w, mg_b), c = w - g * nbatch;
+        const uint32_t e0 = g * R;
+        cd x[R], h[R];
 #pragma unroll
-        for (int q = 0; q < R; q++) x[q] = buf[o + (size_t) q * estride];
+        for (int q = 0; q < R; q++) {
+#ifdef __CUDA_ARCH__
+            h[q] = __ldg(reinterpret_cast<const double2 *>(chat + (e0 + q) * cstride + c));
+#else
+            h[q] = chat[(e0 + q) * cstride + c];
+#endif
+        }
+#pragma unroll
+        for (int q = 0; q < R; q++) x[q] = in.ld(e0 + q, c);
         Dft<R, false>::run(x);
 #pragma unroll
-        for (int q = 0; q < R; q++) x[q] = cmul(x[q], chat[o + (size_t) q * estride]);
+        for (int q = 0; q < R; q++) x[q] = cmul(x[q], h[q]);
         Dft<R, true>::run(x);
 #pragma unroll
-        for (int q = 0; q < R; q++) buf[o + (size_t) q * estride] = x[q];
+        for (int q = 0; q < R; q++) out.st(e0 + q, c, x[q]);
     }
 }
 
-CB_HD void fft_stage_mid_r(int r, cd *buf, int nbatch, int estride, int L, const cd *chat, int tid, int nthr)
+template <class VI, class VO>
+CB_HD void fft_stage_mid_r(int r, VI in, VO out, int nbatch, int L, const cd *chat, uint32_t cstride, int tid, int nthr)
 {
-    switch (r) {
-    case 2:  fft_stage_mid<2>(buf, nbatch, estride, L, chat, tid, nthr); break;
-    case 3:  fft_stage_mid<3>(buf, nbatch, estride, L, chat, tid, nthr); break;
-    case 4:  fft_stage_mid<4>(buf, nbatch, estride, L, chat, tid, nthr); break;
-    case 5:  fft_stage_mid<5>(buf, nbatch, estride, L, chat, tid, nthr); break;
-    case 7:  fft_stage_mid<7>(buf, nbatch, estride, L, chat, tid, nthr); break;
-    case 8:  fft_stage_mid<8>(buf, nbatch, estride, L, chat, tid, nthr); break;
-    case 9:  fft_stage_mid<9>(buf, nbatch, estride, L, chat, tid, nthr); break;
-    case 16: fft_stage_mid<16>(buf, nbatch, estride, L, chat, tid, nthr); break;
-    default: break;
-    }
+#define CB_CALL_(RR) fft_stage_mid<RR>(in, out, nbatch, L, chat, cstride, tid, nthr)
+    CB_RADIX_SWITCH(r, CB_CALL_)
+#undef CB_CALL_
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -138,7 +189,7 @@ struct RowSrc {
     int mx, my;          // tractions: grid size ; coefficients: limits min(F, m) used by the reference copy loop
     int cmx, cmy;        // coefficients: allocated half sizes of cf
     int Fx, Fy;
-    int row0;            // first padded row handled in this batch (coefficients are done in slabs of rows)
+    int row0;            // first padded row handled in this batch
 };
 
 CB_HD double rowsrc_get(const RowSrc &s, int row, int col)
@@ -152,114 +203,114 @@ CB_HD double rowsrc_get(const RowSrc &s, int row, int col)
     }
 }
 
-// S[j][b] = x[b][2j] + i x[b][2j+1]  for j < Lx, b < nbatch
-CB_HD void row_load(const ConvPlan &P, cd *S, int SY, int nbatch, const RowSrc &src, int tid, int nthr)
+// S[j][b] = x[b][2j] + i x[b][2j+1]  for j < Lx, b < nbatch      (S = buf + oS)
+template <class B>
+CB_HD void row_load(const ConvPlan &P, B buf, uint32_t oS, int SY, int nbatch, const RowSrc &src, int tid, int nthr)
 {
     const int items = P.Lx * nbatch;
+    const uint32_t mg = div_magic(P.Lx);
     for (int w = tid; w < items; w += nthr) {
-        const int j = w % P.Lx, b = w / P.Lx;
-        S[(size_t) j * SY + b] = make_double2(rowsrc_get(src, b, 2 * j), rowsrc_get(src, b, 2 * j + 1));
+        const uint32_t b = fdiv(w, mg), j = w - b * P.Lx;
+        buf.st(oS + j * SY + b, make_double2(rowsrc_get(src, b, 2 * j), rowsrc_get(src, b, 2 * j + 1)));
     }
 }
 
 // split step of the packed real transform: Z (scrambled) -> X[k], k = 0..Lx, X[k] at row posx[k] (k<Lx), X[Lx] at row Lx
-CB_HD void row_split(const ConvPlan &P, cd *S, int SY, int nbatch, const cd *twx, const unsigned short *posx,
-                     int tid, int nthr)
+template <class B, class TW, class PX>
+CB_HD void row_split(const ConvPlan &P, B buf, uint32_t oS, int SY, int nbatch, TW twx, PX posx, int tid, int nthr)
 {
     const int L = P.Lx, npair = L / 2 + 1;
     const int items = npair * nbatch;
+    const uint32_t mg = div_magic(nbatch);
     for (int w = tid; w < items; w += nthr) {
-        const int b = w % nbatch, k = w / nbatch;
+        const uint32_t k = fdiv(w, mg), b = w - k * nbatch;
         if (k == 0) {
-            cd a = S[b];
-            S[b] = make_double2(a.x + a.y, 0.0);
-            S[(size_t) L * SY + b] = make_double2(a.x - a.y, 0.0);
-        } else if (2 * k == L) {
-            cd *pa = S + (size_t) posx[k] * SY + b;
-            *pa = cconj(*pa);
+            cd a = buf.ld(oS + b);
+            buf.st(oS + b, make_double2(a.x + a.y, 0.0));
+            buf.st(oS + (uint32_t) L * SY + b, make_double2(a.x - a.y, 0.0));
+        } else if (2 * (int) k == L) {
+            const uint32_t ia = oS + (uint32_t) posx.ld(k) * SY + b;
+            buf.st(ia, cconj(buf.ld(ia)));
         } else {
-            cd *pa = S + (size_t) posx[k] * SY + b, *pb = S + (size_t) posx[L - k] * SY + b;
-            cd a = *pa, bb = *pb;
+            const uint32_t ia = oS + (uint32_t) posx.ld(k) * SY + b, ib = oS + (uint32_t) posx.ld(L - k) * SY + b;
+            cd a = buf.ld(ia), bb = buf.ld(ib);
             cd e = make_double2(0.5 * (a.x + bb.x), 0.5 * (a.y - bb.y));          // (a + conj b)/2
             cd d = make_double2(0.5 * (a.x - bb.x), 0.5 * (a.y + bb.y));          // (a - conj b)/2
-            cd t = cmul(twx[k], make_double2(d.y, -d.x));                        // w^k * (-i) d
-            *pa = cadd(e, t);
-            *pb = cconj(csub(e, t));
+            cd t = cmul(twx.ld(k), make_double2(d.y, -d.x));                     // w^k * (-i) d
+            buf.st(ia, cadd(e, t));
+            buf.st(ib, cconj(csub(e, t)));
         }
     }
 }
 
 // merge step of the inverse packed real transform: X -> Z' = 2 Z (scrambled positions)
-CB_HD void row_merge(const ConvPlan &P, cd *S, int SY, int nbatch, const cd *twx, const unsigned short *posx,
-                     int tid, int nthr)
+template <class B, class TW, class PX>
+CB_HD void row_merge(const ConvPlan &P, B buf, uint32_t oS, int SY, int nbatch, TW twx, PX posx, int tid, int nthr)
 {
     const int L = P.Lx, npair = L / 2 + 1;
     const int items = npair * nbatch;
+    const uint32_t mg = div_magic(nbatch);
     for (int w = tid; w < items; w += nthr) {
-        const int b = w % nbatch, k = w / nbatch;
+        const uint32_t k = fdiv(w, mg), b = w - k * nbatch;
         if (k == 0) {
-            cd p = S[b], q = S[(size_t) L * SY + b];
+            cd p = buf.ld(oS + b), q = buf.ld(oS + (uint32_t) L * SY + b);
             cd u = make_double2(p.x + q.x, p.y - q.y), d = make_double2(p.x - q.x, p.y + q.y);
-            S[b] = make_double2(u.x - d.y, u.y + d.x);                           // u + i d
-        } else if (2 * k == L) {
-            cd *pa = S + (size_t) posx[k] * SY + b;
-            *pa = make_double2(2.0 * pa->x, -2.0 * pa->y);
+            buf.st(oS + b, make_double2(u.x - d.y, u.y + d.x));                  // u + i d
+        } else if (2 * (int) k == L) {
+            const uint32_t ia = oS + (uint32_t) posx.ld(k) * SY + b;
+            cd a = buf.ld(ia);
+            buf.st(ia, make_double2(2.0 * a.x, -2.0 * a.y));
         } else {
-            cd *pa = S + (size_t) posx[k] * SY + b, *pb = S + (size_t) posx[L - k] * SY + b;
-            cd p = *pa, q = *pb;
+            const uint32_t ia = oS + (uint32_t) posx.ld(k) * SY + b, ib = oS + (uint32_t) posx.ld(L - k) * SY + b;
+            cd p = buf.ld(ia), q = buf.ld(ib);
             cd u = make_double2(p.x + q.x, p.y - q.y);                           // p + conj q
             cd d = make_double2(p.x - q.x, p.y + q.y);                           // p - conj q
-            cd v = cmulc(make_double2(-d.y, d.x), twx[k]);                       // i d conj(w^k)
-            *pa = cadd(u, v);
-            *pb = cconj(csub(u, v));
+            cd v = cmulc(make_double2(-d.y, d.x), twx.ld(k));                    // i d conj(w^k)
+            buf.st(ia, cadd(u, v));
+            buf.st(ib, cconj(csub(u, v)));
         }
     }
 }
 
 // store the wanted part of the result: u(ix,iy) = x[iy][Fx+ix], ix < mx  (m_aijpj.f90:978-1005)
 // mask_mode 0: all elements (AllElm), 1: el >= Adhes (AllInt).  add: u += result.
-CB_HD void row_store(const ConvPlan &P, const cd *S, int SY, double *u, const int *el, int mask_mode, int add,
+template <class B>
+CB_HD void row_store(const ConvPlan &P, B buf, uint32_t oS, int SY, double *u, const int *el, int mask_mode, int add,
                      int tid, int nthr)
 {
+    const uint32_t mg = div_magic(P.mx);
     for (int ii = tid; ii < P.npot; ii += nthr) {
-        const int ix = ii % P.mx, iy = ii / P.mx;
+        const uint32_t iy = fdiv(ii, mg), ix = ii - iy * P.mx;
         if (mask_mode == 1 && el[ii] < 1) continue;
-        const int xi = P.Fx + ix;
-        const cd z = S[(size_t) (xi >> 1) * SY + iy];
+        const uint32_t xi = P.Fx + ix;
+        const cd z = buf.ld(oS + (xi >> 1) * SY + iy);
         const double v = (xi & 1) ? z.y : z.x;
         u[ii] = add ? u[ii] + v : v;
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// column pass pieces.  Chunk ch holds S rows r = ch*C + c, c < C (rows beyond Fx are treated as zero).
+// coefficient builder pieces.  Chunk ch holds S rows r = ch*C + c, c < C (rows beyond Fx are treated as zero).
 // ------------------------------------------------------------------------------------------------------------
-CB_HD void col_load(const ConvPlan &P, const cd *S, int SY, int n_in, cd *W, int ch, int tid, int nthr)
+template <class B>
+CB_HD void col_load(const ConvPlan &P, B buf, uint32_t oS, int SY, int n_in, uint32_t oW, int ch, int tid, int nthr)
 {
     const int items = P.Ly * P.C;
+    const uint32_t mg = div_magic(P.C);
     for (int w = tid; w < items; w += nthr) {
-        const int c = w % P.C, j = w / P.C;
-        const int r = ch * P.C + c;
-        W[w] = (j < n_in && r <= P.Fx) ? S[(size_t) r * SY + j] : make_double2(0.0, 0.0);
+        const uint32_t j = fdiv(w, mg), c = w - j * P.C;
+        const uint32_t r = ch * P.C + c;
+        buf.st(oW + w, ((int) j < n_in && (int) r <= P.Fx) ? buf.ld(oS + r * SY + j) : make_double2(0.0, 0.0));
     }
 }
 
-CB_HD void col_store(const ConvPlan &P, cd *S, int SY, const cd *W, int ch, int tid, int nthr)
-{
-    const int items = P.my * P.C;
-    for (int w = tid; w < items; w += nthr) {
-        const int c = w % P.C, iy = w / P.C;
-        const int r = ch * P.C + c;
-        if (r <= P.Fx) S[(size_t) r * SY + iy] = W[(size_t) (P.Fy + iy) * P.C + c];
-    }
-}
-
-// coefficient builder: dump the fully forward-transformed chunk, scaled, as C^
-CB_HD void col_dump(const ConvPlan &P, const cd *W, cd *chat, int ch, double scale, int tid, int nthr)
+// dump the fully forward-transformed chunk, scaled, as C^
+template <class B>
+CB_HD void col_dump(const ConvPlan &P, B buf, uint32_t oW, cd *chat, int ch, double scale, int tid, int nthr)
 {
     const int items = P.Ly * P.C;
     for (int w = tid; w < items; w += nthr)
-        chat[(size_t) ch * items + w] = cscale(W[w], scale);
+        chat[(size_t) ch * items + w] = cscale(buf.ld(oW + w), scale);
 }
 
 }  // namespace cb200

@@ -4,35 +4,19 @@
 
 namespace cb200 {
 
-// ---- batched influence product: one CTA per case (grid-stride), shared coefficient transform ----
-__global__ void __launch_bounds__(CB_THREADS, 1)
-k_conv_batch(ConvPlan P, const double *p, const cd *chat, double *u, const int *el, int mask_mode, int add, int ncase)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Smem sm = smem_view(P, smem_raw);
-    smem_load_tables(P, sm);
-    for (int ic = blockIdx.x; ic < ncase; ic += gridDim.x) {
-        const size_t o = (size_t) ic * P.npot;
-        conv_dev(P, sm, p + o, chat, u + o, el ? el + o : nullptr, el ? mask_mode : 0, add);
-    }
-}
-
 // ---- coefficient transform C^ (one CTA, scratch in global memory; runs once per grid/material/block) ----
 __global__ void __launch_bounds__(CB_THREADS, 1)
-k_build_chat(ConvPlan P, const double *cfblk, int cmx, int cmy, double scale, cd *Sg, cd *Wg, cd *chat)
+k_build_chat(ConvPlan P, const double *cfblk, int cmx, int cmy, double scale, cd *SWg, cd *chat)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // only the tables live in shared memory here; reuse the plan's offsets relative to off_twx
-    cd *twx = reinterpret_cast<cd *>(smem_raw);
-    cd *twy = twx + 2 * P.Fx;
-    unsigned short *posx = reinterpret_cast<unsigned short *>(twy + 2 * P.Fy);
-    for (int k = threadIdx.x; k < 2 * P.Fx; k += blockDim.x) twx[k] = P.twx[k];
-    for (int k = threadIdx.x; k < 2 * P.Fy; k += blockDim.x) twy[k] = P.twy[k];
-    for (int k = threadIdx.x; k < P.Lx; k += blockDim.x) posx[k] = P.posx[k];
-    __syncthreads();
+    const MemBuf<const cd> twx = { P.twx }, twy = { P.twy };        // tables straight from global (one-off kernel)
+    const MemBuf<const unsigned short> posx = { P.posx };
     const int tid = threadIdx.x, nthr = blockDim.x;
-    cd *S = Sg, *W = Wg;
+    typedef MemBuf<cd> CB_BUF;
+    const CB_BUF BUF = { SWg };                                   // scratch: S region, then W region
     const int SY = 2 * P.Fy;
+    const uint32_t oS = 0u, oW = (uint32_t) (P.Lx + 1) * SY;
     RowSrc src;
     src.base = cfblk; src.kind = 1;
     src.mx = min(P.Fx, P.mx); src.my = min(P.Fy, P.my);          // m_aijpj.f90:896-898
@@ -146,15 +130,34 @@ __global__ void k_cplx_real_scaled(const cd *in, double *out, long n, double sca
 
 // ---- batched NORM solve: one CTA per contact problem ----
 __global__ void __launch_bounds__(CB_THREADS, 1)
-k_snorm_batch(ConvPlan P, NormCase *cases, int ncase)
+k_snorm_batch(ConvPlan P, NormCase *cases, int ncase, int *next_case)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem sm = smem_view(P, smem_raw);
     smem_load_tables(P, sm);
-    for (int ic = blockIdx.x; ic < ncase; ic += gridDim.x) {
+    volatile int *s_case_p = reinterpret_cast<volatile int *>(sm.red + 127);   // last slot of the reduction scratch
+    // dynamic case queue: iteration counts differ between cases, so CTAs pull the next case when they finish one
+    for (;;) {
+        if (threadIdx.x == 0) *s_case_p = atomicAdd(next_case, 1);
+        __syncthreads();
+        const int ic = *s_case_p;
+        __syncthreads();
+        if (ic >= ncase) break;
         snorm_dev(P, sm, cases[ic]);
         __syncthreads();
     }
+}
+
+// ---- FP64 FMA throughput probe (roofline denominator for the FP64-bound batched small-grid products) ----
+__global__ void k_fp64_peak(double *out, int iters)
+{
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
 }  // namespace cb200

@@ -35,25 +35,57 @@ struct NormCase {
     // outputs
     int itcg, itnorm, ncon, status;     // status bit 0: NormCG diverged at MaxCG (reference: abort_run)
     double err;
+    int nprod;               // number of single-block influence products performed (work accounting)
 };
+
+// Masked vector pass with all loads of a batch in flight before any use: the work vectors live in global memory
+// (L2-resident), so a pass is latency bound unless its loads are issued back to back.  Each thread handles elements
+// tid + k*nt; per batch of CB_VB elements it first loads el[] and the NA input arrays, then calls f(i, el, a[]).
+#define CB_VB 8
+template <int NA, class F>
+__device__ __forceinline__ void vec_pass(int n, const int *el, const double *a0, const double *a1, const double *a2,
+                                         const double *a3, F f)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int base = tid; base < n; base += CB_VB * nt) {
+        int e[CB_VB];
+        double a[CB_VB][NA > 0 ? NA : 1];
+#pragma unroll
+        for (int k = 0; k < CB_VB; k++) {
+            const int i = base + k * nt;
+            const bool ok = i < n;
+            e[k] = ok ? el[i] : 0;
+            if (NA > 0) a[k][0] = ok ? a0[i] : 0.0;
+            if (NA > 1) a[k][1] = ok ? a1[i] : 0.0;
+            if (NA > 2) a[k][2] = ok ? a2[i] : 0.0;
+            if (NA > 3) a[k][3] = ok ? a3[i] : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < CB_VB; k++) {
+            const int i = base + k * nt;
+            if (i < n) f(i, e[k], a[k]);
+        }
+    }
+}
 
 __device__ __forceinline__ void proj_avg_dev(const int *el, double *a, int n, double *red)
 {   // gf3_proj_avg(AllInt): m_gridfunc.f90:1325-1370
     double s[2] = { 0.0, 0.0 };
-    for (int i = threadIdx.x; i < n; i += blockDim.x) if (el[i] >= 1) { s[0] += a[i]; s[1] += 1.0; }
+    vec_pass<1>(n, el, a, nullptr, nullptr, nullptr, [&](int, int e, const double *x) { if (e >= 1) { s[0] += x[0]; s[1] += 1.0; } });
     block_sum<2>(s, red);
     const double avg = s[0] / fmax(1.0, s[1]);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) if (el[i] >= 1) a[i] -= avg;
+    vec_pass<1>(n, el, a, nullptr, nullptr, nullptr, [&](int i, int e, const double *x) { if (e >= 1) a[i] = x[0] - avg; });
     __syncthreads();
 }
 
 // returns 1 when the reference would abort (MaxCG reached while diverging)
 __device__ int normcg_dev(const ConvPlan &P, const Smem &sm, const NormCase &c, const double *hstot, double &pen,
-                          int *el, double *ps, double *wk, int &itcg_out, double &err_out)
+                          int *el, double *ps, double *wk, int &itcg_out, double &err_out, int &nprod)
 {
     const int n = P.npot, tid = threadIdx.x, nt = blockDim.x;
-    double *rhs = wk, *res = wk + n, *r_prv = wk + 2 * n, *dd = wk + 3 * n, *z = wk + 4 * n, *v = wk + 5 * n,
-           *q = wk + 6 * n;
+    double *__restrict__ rhs = wk, *__restrict__ res = wk + n, *__restrict__ r_prv = wk + 2 * n,
+           *__restrict__ dd = wk + 3 * n, *__restrict__ z = wk + 4 * n, *__restrict__ v = wk + 5 * n,
+           *__restrict__ q = wk + 6 * n;
     double *red = sm.red;
     const int ic_norm = c.ic_norm, maxcg = c.maxgs;
     const double eps = c.eps, dxdy = c.dxdy, fntrue = c.fntrue;
@@ -102,8 +134,8 @@ __device__ int normcg_dev(const ConvPlan &P, const Smem &sm, const NormCase &c, 
         __syncthreads();
     }
 
-    conv_dev(P, sm, ps, c.chatA, res, el, 1, 0);                     // :173-175 res = rhs - A ps on C
-    for (int i = tid; i < n; i += nt) if (el[i] >= 1) res[i] = rhs[i] - res[i];
+    conv_dev(P, sm, ps, c.chatA, res, el, 1, 0); nprod++;            // :173-175 res = rhs - A ps on C
+    vec_pass<2>(n, el, rhs, res, nullptr, nullptr, [&](int i, int e, const double *a) { if (e >= 1) res[i] = a[0] - a[1]; });
     __syncthreads();
     if (ic_norm == 1) proj_avg_dev(el, res, n, red);
 
@@ -113,29 +145,32 @@ __device__ int normcg_dev(const ConvPlan &P, const Smem &sm, const NormCase &c, 
 
     while ((lchanged || rms_upd > eps * rms_xk) && itcg < maxcg) {   // :194
         itcg++; itinn++;
-        conv_dev(P, sm, res, c.chatM, z, el, 1, 0);                  // z = M res on C
+        conv_dev(P, sm, res, c.chatM, z, el, 1, 0); nprod++;         // z = M res on C
         if (ic_norm == 1) proj_avg_dev(el, z, n, red);
 
         double d2[2] = { 0.0, 0.0 };
-        for (int i = tid; i < n; i += nt) if (el[i] >= 1) { d2[0] += z[i] * res[i]; d2[1] += z[i] * r_prv[i]; }
+        vec_pass<3>(n, el, z, res, r_prv, nullptr, [&](int, int e, const double *a) {
+            if (e >= 1) { d2[0] += a[0] * a[1]; d2[1] += a[0] * a[2]; }
+        });
         block_sum<2>(d2, red);
         rz1 = rz2; rz2 = d2[0];
 
         if (itcg <= 1 || rz1 < CB_TINY) {                            // :228-241
-            for (int i = tid; i < n; i += nt) if (el[i] >= 1) v[i] = z[i];
+            vec_pass<1>(n, el, z, nullptr, nullptr, nullptr, [&](int i, int e, const double *a) { if (e >= 1) v[i] = a[0]; });
         } else {
             const double beta = fmax(0.0, (rz2 - d2[1]) / fmax(CB_TINY, rz1));
-            for (int i = tid; i < n; i += nt) if (el[i] >= 1) v[i] = beta * v[i] + z[i];
+            vec_pass<2>(n, el, z, v, nullptr, nullptr, [&](int i, int e, const double *a) { if (e >= 1) v[i] = beta * a[1] + a[0]; });
         }
         __syncthreads();
         if (ic_norm == 1) proj_avg_dev(el, v, n, red);
 
-        conv_dev(P, sm, v, c.chatA, q, el, 1, 0);                    // q = A v on C
+        conv_dev(P, sm, v, c.chatA, q, el, 1, 0); nprod++;           // q = A v on C
         if (ic_norm == 1) proj_avg_dev(el, q, n, red);
 
         double d4[4] = { 0.0, 0.0, 0.0, 0.0 };
-        for (int i = tid; i < n; i += nt)
-            if (el[i] >= 1) { const double vi = v[i]; d4[0] += res[i] * vi; d4[1] += q[i] * vi; d4[2] += vi * vi; d4[3] += 1.0; }
+        vec_pass<3>(n, el, v, res, q, nullptr, [&](int, int e, const double *a) {
+            if (e >= 1) { d4[0] += a[1] * a[0]; d4[1] += a[2] * a[0]; d4[2] += a[0] * a[0]; d4[3] += 1.0; }
+        });
         block_sum<4>(d4, red);
         const double rv = d4[0], vav = d4[1];
         double alpha;
@@ -146,20 +181,21 @@ __device__ int normcg_dev(const ConvPlan &P, const Smem &sm, const NormCase &c, 
         const bool need_xk = (itcg <= 3 || itcg % 10 == 0);
 
         double p2[1] = { 0.0 };
-        for (int i = tid; i < n; i += nt) {
-            r_prv[i] = res[i];                                        // :294 (AllElm copy)
-            if (el[i] >= 1) { const double pi = ps[i] + alpha * v[i]; ps[i] = pi; p2[0] += pi * pi; }
-        }
+        vec_pass<3>(n, el, res, ps, v, nullptr, [&](int i, int e, const double *a) {
+            r_prv[i] = a[0];                                          // :294 (AllElm copy)
+            if (e >= 1) { const double pi = a[1] + alpha * a[2]; ps[i] = pi; p2[0] += pi * pi; }
+        });
         if (need_xk) { block_sum<1>(p2, red); rms_xk = sqrt(p2[0] / fmax(1.0, d4[3])); }
         else __syncthreads();
 
         if (itinn < numinn && rms_upd >= eps * rms_xk) {             // :298-303
-            for (int i = tid; i < n; i += nt) if (el[i] >= 1) res[i] = res[i] - alpha * q[i];
+            vec_pass<2>(n, el, res, q, nullptr, nullptr, [&](int i, int e, const double *a) { if (e >= 1) res[i] = a[0] - alpha * a[1]; });
             __syncthreads();
         } else {
             double k2[1] = { 0.0 };
-            for (int i = tid; i < n; i += nt)                         // :310-318
-                if (el[i] >= 1 && ps[i] < 0.0) { el[i] = 0; ps[i] = 0.0; k2[0] += 1.0; }
+            vec_pass<1>(n, el, ps, nullptr, nullptr, nullptr, [&](int i, int e, const double *a) {   // :310-318
+                if (e >= 1 && a[0] < 0.0) { el[i] = 0; ps[i] = 0.0; k2[0] += 1.0; }
+            });
             block_sum<1>(k2, red);
             bool lchg_negpn = k2[0] > 0.0;
             ncon -= (int) k2[0];
@@ -185,13 +221,13 @@ __device__ int normcg_dev(const ConvPlan &P, const Smem &sm, const NormCase &c, 
                 __syncthreads();
             }
 
-            conv_dev(P, sm, ps, c.chatA, dd, el, 0, 0);              // :351-352 dd = A ps - rhs, whole grid
+            conv_dev(P, sm, ps, c.chatA, dd, el, 0, 0); nprod++;     // :351-352 dd = A ps - rhs, whole grid
             double sd[1] = { 0.0 };
-            for (int i = tid; i < n; i += nt) {
-                const double d = dd[i] - rhs[i];
+            vec_pass<2>(n, el, dd, rhs, nullptr, nullptr, [&](int i, int e, const double *a) {
+                const double d = a[0] - a[1];
                 dd[i] = d;
-                if (el[i] >= 1) sd[0] += d;
-            }
+                if (e >= 1) sd[0] += d;
+            });
             if (ic_norm == 1) {                                       // :356-359
                 block_sum<1>(sd, red);
                 davg = sd[0] / (double) ncon;
@@ -200,13 +236,14 @@ __device__ int normcg_dev(const ConvPlan &P, const Smem &sm, const NormCase &c, 
             __syncthreads();
 
             double ke[1] = { 0.0 };
-            for (int i = tid; i < n; i += nt) {                       // :361-384
+            vec_pass<1>(n, el, dd, nullptr, nullptr, nullptr, [&](int i, int e, const double *a) {   // :361-384
+                const double di = a[0];
                 double r = 0.0;
-                if (el[i] >= 1) r = -dd[i];
-                else if (dd[i] - davg < 0.0) { el[i] = 1; r = -(dd[i] - davg); ke[0] += 1.0; }
+                if (e >= 1) r = -di;
+                else if (di - davg < 0.0) { el[i] = 1; r = -(di - davg); ke[0] += 1.0; }
                 else v[i] = 0.0;
                 res[i] = r;
-            }
+            });
             block_sum<1>(ke, red);
             const bool lchg_intpen = ke[0] > 0.0;
             ncon += (int) ke[0];
@@ -255,10 +292,12 @@ __device__ void snorm_dev(const ConvPlan &P, const Smem &sm, NormCase &c)
     int *el = c.el;
     double *ps = c.pn;
     double pen = c.pen;
+    int nprod = 0;
 
     if (c.chatA31 != nullptr && c.ptx != nullptr) {                   // m_snorm.f90:112-119 hstot = hs + A_zt p_t
         conv_dev(P, sm, c.ptx, c.chatA31, tmp, el, 0, 0);
         conv_dev(P, sm, c.pty, c.chatA32, tmp, el, 0, 1);
+        nprod += 2;
         for (int i = tid; i < n; i += nt) hstot[i] = c.hs[i] + tmp[i];
     } else {
         for (int i = tid; i < n; i += nt) hstot[i] = c.hs[i];
@@ -274,7 +313,7 @@ __device__ void snorm_dev(const ConvPlan &P, const Smem &sm, NormCase &c)
         for (int i = tid; i < n; i += nt) if (el[i] < 1) ps[i] = 0.0;
         __syncthreads();
 
-        if (normcg_dev(P, sm, c, hstot, pen, el, ps, wk, it, errpn)) status |= 1;
+        if (normcg_dev(P, sm, c, hstot, pen, el, ps, wk, it, errpn, nprod)) status |= 1;
         itcg += it;
 
         double k[1] = { 0.0 };
@@ -284,7 +323,7 @@ __device__ void snorm_dev(const ConvPlan &P, const Smem &sm, NormCase &c)
         if (k[0] > 0.0) zready = false;
 
         if (zready) {                                                 // :227-292 expand
-            conv_dev(P, sm, ps, c.chatA, unn, el, 0, 0);
+            conv_dev(P, sm, ps, c.chatA, unn, el, 0, 0); nprod++;
             const double tol = fabs(errpn * centre_rowsum_dev(P, c, el, red));
             double kc[1] = { 0.0 };
             for (int i = tid; i < n; i += nt)
@@ -310,7 +349,7 @@ __device__ void snorm_dev(const ConvPlan &P, const Smem &sm, NormCase &c)
     if (tid == 0) {
         c.pen = pen;
         if (c.ic_norm == 0) c.fntrue = c.dxdy * s[0];                 // :352
-        c.itcg = itcg; c.itnorm = itnorm; c.ncon = (int) s[1]; c.status = status; c.err = errpn;
+        c.itcg = itcg; c.itnorm = itnorm; c.ncon = (int) s[1]; c.status = status; c.err = errpn; c.nprod = nprod;
     }
 }
 

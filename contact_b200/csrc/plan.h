@@ -47,18 +47,22 @@ inline bool choose_radices(int L, int *nst, int *rad)
     while (n % 5 == 0) { c++; n /= 5; }
     while (n % 7 == 0) { d++; n /= 7; }
     if (n != 1) return false;
+    // register-sized radices {16, 12, 9, 8, 7, 6, 5, 4, 3, 2}; fewest stages first (every stage is one full pass
+    // over shared memory), largest radix first (the last forward stage is fused with the multiply and the
+    // first inverse stage, so it should be a mid-size radix)
     int k = 0;
-    while (a >= 7) { rad[k++] = 16; a -= 4; }
-    if (a == 6) { rad[k++] = 8; rad[k++] = 8; }
-    else if (a == 5) { rad[k++] = 8; rad[k++] = 4; }
-    else if (a == 4) { rad[k++] = 16; }
-    else if (a == 3) { rad[k++] = 8; }
-    else if (a == 2) { rad[k++] = 4; }
-    else if (a == 1) { rad[k++] = 2; }
+    while (a >= 2 && b >= 1 && (a + b > 3 || c + d > 0 || a == 2)) { rad[k++] = 12; a -= 2; b -= 1; if (a < 2 || b < 1) break; }
+    while (a >= 4) { rad[k++] = 16; a -= 4; }
+    if (a == 3) { rad[k++] = 8; a = 0; }
     while (b >= 2) { rad[k++] = 9; b -= 2; }
-    if (b == 1) rad[k++] = 3;
+    if (a >= 1 && b >= 1) { rad[k++] = 6; a -= 1; b -= 1; }
+    if (a == 2) { rad[k++] = 4; a = 0; }
+    if (a == 1) { rad[k++] = 2; a = 0; }
+    if (b == 1) { rad[k++] = 3; b = 0; }
     while (d-- > 0) rad[k++] = 7;
     while (c-- > 0) rad[k++] = 5;
+    // sort descending
+    for (int i = 0; i < k; i++) for (int j = i + 1; j < k; j++) if (rad[j] > rad[i]) { int t = rad[i]; rad[i] = rad[j]; rad[j] = t; }
     if (k > CB_MAXSTAGE) return false;
     *nst = k;
     return true;

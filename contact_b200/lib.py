@@ -69,6 +69,10 @@ PROTOTYPES = {
     "cb200_vecaijpj": (I, [I, I, I, I, I, I, dp, ip, dp]),
     "cb200_vecaijpj_dev": (I, [I, I, I, I, I, I, V, V, V, V]),
     "cb200_snorm_batch_dev": (I, [I, I, I, I, I, D, V, V, V, V, V, V]),
+    "cb200_eldiv0": (I, [I, I, D, D, D, D, D, D, I, dp, I, D, D, dp, ip, dp]),
+    "cb200_snorm_batch": (I, [I, I, I, I, I, D, dp, ip, dp, dp, dp]),
+    "cb200_snorm_kernel_ms": (D, []),
+    "cb200_fp64_peak_tflops": (D, [I]),
     "cb200_snorm_workspace_bytes": (L, [I, I]),
 }
 

@@ -83,6 +83,37 @@ class CoefSet:
                                                     _stream_ptr(stream)))
 
 
+    def snorm_batch(self, hs, el, pn, un, scal, ic_norm, maxgs=999, maxin=20, eps=1e-5):
+        """HOST buffers (numpy or pinned torch CPU tensors viewed as numpy), modified in place."""
+        ncase = hs.shape[0]
+        dpp, ipp = C.POINTER(C.c_double), C.POINTER(C.c_int)
+        _check(load_library().cb200_snorm_batch(self.h, ncase, ic_norm, maxgs, maxin, eps, hs.ctypes.data_as(dpp),
+                                                el.ctypes.data_as(ipp), pn.ctypes.data_as(dpp),
+                                                None if un is None else un.ctypes.data_as(dpp),
+                                                scal.ctypes.data_as(dpp)))
+
+
+def eldiv0(mx, my, dx, dy, gg, poiss, ibase, prmudf, ic_norm, fn, pen, h):
+    """Initial element division / approach estimate of the library's eldiv0 restatement (host logic)."""
+    h = np.ascontiguousarray(h, dtype=np.float64)
+    prm = np.ascontiguousarray(prmudf, dtype=np.float64)
+    el = np.zeros(mx * my, dtype=np.int32)
+    pen_o = C.c_double(0.0)
+    _check(load_library().cb200_eldiv0(mx, my, dx, dy, gg[0], gg[1], poiss[0], poiss[1], ibase,
+                                       prm.ctypes.data_as(C.POINTER(C.c_double)), ic_norm, fn, pen,
+                                       h.ctypes.data_as(C.POINTER(C.c_double)), el.ctypes.data_as(C.POINTER(C.c_int)),
+                                       C.byref(pen_o)))
+    return el, pen_o.value
+
+
+def snorm_kernel_ms():
+    return load_library().cb200_snorm_kernel_ms()
+
+
+def fp64_peak_tflops(reps=3):
+    return load_library().cb200_fp64_peak_tflops(reps)
+
+
 def _stream_ptr(stream):
     if stream is None:
         import torch

@@ -149,10 +149,21 @@ int cb200_vecaijpj_dev(int handle, int set, int ncase, int iigs, int ikarg, int 
 /* Batched NORM solve (snorm + NormCG, m_snorm.f90:31-378, m_solvpn.f90:24-461) on DEVICE buffers.
  *   d_hs [ncase][npot] undeformed distance; d_el [ncase][npot] in/out element division;
  *   d_pn [ncase][npot] in/out pressures; d_un [ncase][npot] out (may be NULL): u_n = A_zz p_n on the contact area;
- *   d_scal [ncase][8] in/out doubles: pen, fn, (out) itcg, itnorm, ncon, status, err, reserved.
+ *   d_scal [ncase][8] in/out doubles: pen, fn, (out) itcg, itnorm, ncon, status, err, number of products.
  * ic_norm: 0 approach prescribed (pen in), 1 force prescribed (fn in). */
 int cb200_snorm_batch_dev(int handle, int ncase, int ic_norm, int maxgs, int maxin, double eps, const double *d_hs,
                           int *d_el, double *d_pn, double *d_un, double *d_scal, void *stream);
+/* initial element division + approach estimate (eldiv0, m_sdis.f90:818-1007) for a gap h[npot]; host buffers */
+int cb200_eldiv0(int mx, int my, double dx, double dy, double gg1, double gg2, double poiss1, double poiss2,
+                 int ibase, const double *prmudf, int ic_norm, double fn, double pen_in, const double *h, int *el,
+                 double *pen_out);
+/* same with HOST buffers (copies in, solves, copies out, synchronous) */
+int cb200_snorm_batch(int handle, int ncase, int ic_norm, int maxgs, int maxin, double eps, const double *hs,
+                      int *el, double *pn, double *un, double *scal);
+/* device time [ms] of the most recent solver kernel alone (CUDA events on its stream) */
+double cb200_snorm_kernel_ms(void);
+/* measured FP64 FMA throughput [TFLOP/s] (roofline denominator for FP64-bound kernels) */
+double cb200_fp64_peak_tflops(int reps);
 /* workspace the batched solve keeps per case, bytes (for memory planning) */
 long cb200_snorm_workspace_bytes(int handle, int ncase);
 

@@ -8,9 +8,14 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <malloc.h>
 
 co_ctx *co_ctx_new(void)
 {
+    /* keep the per-product work arrays (0.3 - 20 MB) on the heap: with glibc's default mmap threshold every
+     * allocate/deallocate pair of fft_VecAijPj would be an mmap/munmap, which serialises threads on the mm lock */
+    static int once = 0;
+    if (!once) { mallopt(M_MMAP_THRESHOLD, 1 << 30); mallopt(M_TRIM_THRESHOLD, 1 << 30); once = 1; }
     co_ctx *cx = (co_ctx *) calloc(1, sizeof(co_ctx));
     return cx;
 }

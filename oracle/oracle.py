@@ -194,3 +194,22 @@ def norm_case(mx, my, xl, yl, dx, dy, gg, poiss, ibase, prmudf, ic_norm, pen=0.0
                           _i(el), _d(pn), C.byref(pen_o), C.byref(fn_o), C.byref(itcg), C.byref(itnorm), _d(stats))
     return dict(ierror=ierr, el=el, pn=pn, pen=pen_o.value, fn=fn_o.value, itcg=itcg.value, itnorm=itnorm.value,
                 n_prod=int(stats[0]), n_rowsum=int(stats[1]), alg_bytes=stats[2], alg_flops=stats[3])
+
+
+def norm_batch(g, gg, poiss, ic_norm, loads, maxgs=999, maxin=20, eps=1e-5, nthreads=1, fullbox=False, nn=0):
+    """Batch of normal-contact cases on one grid (dict g: mx,my,xl,yl,dx,dy,ibase,prmudf), one case per thread."""
+    loads = np.ascontiguousarray(loads, dtype=np.float64)
+    ncase, npot = len(loads), g["mx"] * g["my"]
+    prm = np.ascontiguousarray(g["prmudf"], dtype=np.float64)
+    el = np.zeros((ncase, npot), dtype=np.int32)
+    pn = np.zeros((ncase, npot))
+    scal = np.zeros((ncase, 4))
+    L = lib()
+    L.co_norm_batch.restype = C.c_int
+    nfail = L.co_norm_batch(C.c_int(ncase), C.c_int(nthreads), C.c_int(g["mx"]), C.c_int(g["my"]), C.c_double(g["xl"]),
+                            C.c_double(g["yl"]), C.c_double(g["dx"]), C.c_double(g["dy"]), C.c_double(gg[0]),
+                            C.c_double(gg[1]), C.c_double(poiss[0]), C.c_double(poiss[1]), C.c_int(g["ibase"]),
+                            C.c_int(nn), _d(prm), C.c_int(ic_norm), _d(loads), C.c_int(maxgs), C.c_int(maxin),
+                            C.c_double(eps), C.c_int(int(fullbox)), _i(el), _d(pn), _d(scal))
+    return dict(nfail=nfail, el=el, pn=pn, pen=scal[:, 0], fn=scal[:, 1], itcg=scal[:, 2].astype(int),
+                n_prod=scal[:, 3].astype(int))

@@ -27,15 +27,17 @@ extern "C" int emul_conv(int mx, int my, const double *p, const double *cfblk, i
     HostPlan hp;
     if (!make_plan(mx, my, hp)) return -1;
     const ConvPlan &P = hp.p;
-    const cd *twx = hp.twx.data(), *twy = hp.twy.data();
-    const unsigned short *posx = hp.posx.data();
+    const MemBuf<const cd> twx = { hp.twx.data() }, twy = { hp.twy.data() };
+    const MemBuf<const unsigned short> posx = { hp.posx.data() };
 
     // --- build C^ with the coefficient sequence (global-scratch style: S holds all 2Fy rows)
     std::vector<cd> chat(P.chat_len);
     {
         const int SY = 2 * P.Fy;
-        std::vector<cd> Sg((size_t) (P.Lx + 1) * SY), Wg((size_t) P.Ly * P.C);
-        cd *S = Sg.data(), *W = Wg.data();
+        std::vector<cd> SW((size_t) (P.Lx + 1) * SY + (size_t) P.Ly * P.C);
+        typedef MemBuf<cd> CB_BUF;
+        const CB_BUF BUF = { SW.data() };
+        const uint32_t oS = 0u, oW = (uint32_t) (P.Lx + 1) * SY;
         RowSrc src = { cfblk, 1, P.Fx < mx ? P.Fx : mx, P.Fy < my ? P.Fy : my, cmx, cmy, P.Fx, P.Fy, 0 };
         CB_CONV_FORWARD_ROWS(2 * P.Fy, src);
         CB_CONV_COLUMNS_DUMP(2 * P.Fy, chat.data(), scale / (4.0 * P.Fx * P.Fy));
@@ -43,13 +45,15 @@ extern "C" int emul_conv(int mx, int my, const double *p, const double *cfblk, i
     // --- the product
     {
         const int SY = P.SY;
-        std::vector<cd> Ss((size_t) (P.Lx + 1) * SY), Ws((size_t) P.Ly * P.C);
-        cd *S = Ss.data(), *W = Ws.data();
+        std::vector<cd> SW((size_t) (P.Lx + 1) * SY + (size_t) P.Ly * P.C);
+        typedef MemBuf<cd> CB_BUF;
+        const CB_BUF BUF = { SW.data() };
+        const uint32_t oS = 0u, oW = (uint32_t) (P.Lx + 1) * SY;
         RowSrc src = { p, 0, mx, my, 0, 0, P.Fx, P.Fy, 0 };
         CB_CONV_FORWARD_ROWS(P.my, src);
         CB_CONV_COLUMNS_PRODUCT(P.my, chat.data());
         CB_CONV_INVERSE_ROWS(P.my);
-        CB_PHASE(row_store(P, S, SY, u, el, mask_mode, add, tid, nthr));
+        CB_PHASE(row_store(P, BUF, oS, SY, u, el, mask_mode, add, tid, nthr));
     }
     return 0;
 }
@@ -61,7 +65,7 @@ extern "C" double emul_radix_error(int R, int inv)
     double err = 0.0;
     for (int q = 0; q < R; q++) { x[q] = make_double2(0.3 + 0.7 * q - 0.05 * q * q, -0.2 + 0.11 * q * q * q / 7.0); y[q] = x[q]; }
 #define RUN(RR) case RR: if (inv) Dft<RR, true>::run(y); else Dft<RR, false>::run(y); break;
-    switch (R) { RUN(2) RUN(3) RUN(4) RUN(5) RUN(7) RUN(8) RUN(9) RUN(16) default: return -1; }
+    switch (R) { RUN(2) RUN(3) RUN(4) RUN(5) RUN(6) RUN(7) RUN(8) RUN(9) RUN(12) RUN(16) default: return -1; }
     const double pi = 3.14159265358979323846, sg = inv ? 1.0 : -1.0;
     for (int k = 0; k < R; k++) {
         double re = 0, im = 0;
