@@ -135,8 +135,10 @@ def run_gpu(args):
     npot = g["mx"] * g["my"]
     nsm = ll.num_sms()
     ncase = args.cases if args.cases > 0 else 8 * nsm           # multiple of the SM count: one CTA per case, 8 waves
+    from contact_b200 import scheduler
     fns_all, _ = cases.hertz91_fn(ncase * world, fn0=FN0)
-    fns = fns_all[rank * ncase:(rank + 1) * ncase]               # static block sharding of the case index
+    lo, hi = scheduler.my_range(ncase * world, rank, world)      # static block sharding of the case index
+    fns = fns_all[lo:hi]
     cset = ll.CoefSet(g["mx"], g["my"], g["dx"], g["dy"], **cases.STEEL)
     hs0, el0, pn0, scal0 = initial_state(g, fns)
 
@@ -189,7 +191,9 @@ def run_gpu(args):
         step_device()
         kt.append(ll.snorm_kernel_ms())
     kernel_ms = float(np.mean(kt))
+    table = scheduler.gather_case_results(d_scal, ncase * world)   # the only collective: final gather of per-case results
     scal = d_scal.cpu().numpy()
+    assert table.shape[0] == ncase * world
     nprod = float(scal[:, 7].sum())
     itcg_mean = float(scal[:, 2].mean())
     clocks = sampler.stop() if rank == 0 else None
