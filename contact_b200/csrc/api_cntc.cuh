@@ -686,31 +686,76 @@ void subs_addblock(int *ire, int *icp, int *iblk, int *isubs, int *nx, int *ny, 
 {
     int e; Problem *p = activate(*ire, *icp, &e);
     if (!p) return;
-    // contact_addon.f90:3330-3515: isubs 1/5: all elements x given z ; 9: explicit x, y, z lists ; others: index selections
+    // contact_addon.f90:3330-3515.  isubs 1,2,3: zparam = [NZ, ZL, DZ]; 5,6,7,9: zparam = z(1:npz);
+    // 2,6: x/yparam = [IL, INC, IH]; 3,7: index lists; 9: coordinate lists.  iblk = 0 clears all blocks.
+    const int is = *isubs;
+    for (auto it = p->subs.lower_bound(*iblk); it != p->subs.end();) it = p->subs.erase(it);
+    if (*iblk <= 0) return;
+    if (is < 1 || is == 4 || is == 8 || is > 9) { last_error() = "subs_addblock: ISUBS does not exist"; return; }
     Problem::SubsBlock &b = p->subs[*iblk];
-    b.isubs = *isubs; b.nx = *nx; b.ny = *ny; b.nz = *nz;
-    b.x.clear(); b.y.clear(); b.z.clear(); b.table.clear();
+    b.isubs = is;
     const double L = p->scl.len;
-    if (*isubs == 9) {
-        b.x.assign(xparam, xparam + *nx); b.y.assign(yparam, yparam + *ny); b.z.assign(zparam, zparam + *nz);
-        for (double &v : b.x) v *= L; for (double &v : b.y) v *= L; for (double &v : b.z) v *= L;
-    } else if (*isubs == 1 || *isubs == 5) {
-        b.z.assign(zparam, zparam + *nz);
-        for (double &v : b.z) v *= L;
-    } else {
-        b.x.assign(xparam, xparam + (*isubs == 3 || *isubs == 7 ? *nx : 3));
-        b.y.assign(yparam, yparam + (*isubs == 3 || *isubs == 7 ? *ny : 3));
-        b.z.assign(zparam, zparam + *nz);
-        for (double &v : b.z) v *= L;
+    b.x.clear(); b.y.clear(); b.z.clear(); b.table.clear();
+    if (is <= 3) { const int n = (int) lround(zparam[0]); for (int k = 0; k < n; k++) b.z.push_back((zparam[1] + k * zparam[2]) * L); }
+    else for (int k = 0; k < *nz; k++) b.z.push_back(zparam[k] * L);
+    if (is == 9) { for (int i = 0; i < *nx; i++) b.x.push_back(xparam[i] * L); for (int j = 0; j < *ny; j++) b.y.push_back(yparam[j] * L); }
+    else if (is == 2 || is == 6) {
+        for (int i = (int) lround(xparam[0]); i <= (int) lround(xparam[2]); i += std::max(1, (int) lround(xparam[1]))) b.x.push_back(i);
+        for (int j = (int) lround(yparam[0]); j <= (int) lround(yparam[2]); j += std::max(1, (int) lround(yparam[1]))) b.y.push_back(j);
+    } else if (is == 3 || is == 7) {
+        for (int i = 0; i < *nx; i++) b.x.push_back(lround(xparam[i]));
+        for (int j = 0; j < *ny; j++) b.y.push_back(lround(yparam[j]));
     }
+    b.nx = b.ny = 0; b.nz = (int) b.z.size();
 }
 
 void subs_calculate(int *ire, int *icp, int *ierror)
 {
-    Problem *p = activate(*ire, *icp, ierror);
-    if (!p) return;
-    last_error() = "subs_calculate: the subsurface evaluator is not yet served by the B200 path";
-    *ierror = CNTC_err_other;
+    Problem *pp = activate(*ire, *icp, ierror);
+    if (!pp) return;
+    Problem &p = *pp;
+    int rc = engine_init();
+    if (rc) { *ierror = rc; return; }
+    const int npot = p.mx * p.my;
+    if ((int) p.ps.size() != 3 * npot) { last_error() = "subs_calculate: no tractions available (run cntc_calculate first)"; *ierror = CNTC_err_other; return; }
+    combine_material(p.mat);
+    for (auto &kv : p.subs) {
+        Problem::SubsBlock &b = kv.second;
+        if (b.isubs == 9) {
+            b.nx = (int) b.x.size(); b.ny = (int) b.y.size();
+            const int np = b.nx * b.ny * b.nz;
+            std::vector<double> xyz((size_t) 3 * np), t18((size_t) 18 * np);
+            int ip = 0;
+            for (int k = 0; k < b.nz; k++) for (int j = 0; j < b.ny; j++) for (int i = 0; i < b.nx; i++, ip++) { xyz[3 * ip] = b.x[i]; xyz[3 * ip + 1] = b.y[j]; xyz[3 * ip + 2] = b.z[k]; }
+            rc = cb200_subsurf_points(p.mx, p.my, p.xc1, p.yc1, p.dx, p.dy, p.mat.gg[0], p.mat.gg[1], p.mat.poiss[0], p.mat.poiss[1],
+                                      p.ps.data(), np, xyz.data(), t18.data());
+            if (rc) { *ierror = rc; return; }
+            b.table.assign((size_t) 21 * np, 0.0);
+            for (int q = 0; q < np; q++) { for (int c = 0; c < 3; c++) b.table[(size_t) q * 21 + c] = xyz[3 * q + c]; for (int c = 0; c < 18; c++) b.table[(size_t) q * 21 + 3 + c] = t18[(size_t) q * 18 + c]; }
+        } else {
+            CoefSet *cs = nullptr;
+            rc = get_coefset(p.mx, p.my, p.dx, p.dy, p.mat, 0, 0.0, 1.0, 0, &cs);
+            if (rc) { *ierror = rc; return; }
+            std::vector<double> tbl((size_t) b.nz * npot * 18);
+            rc = cb200_subsurf_batch(handle_of(cs), 1, b.nz, b.z.data(), p.mat.gg[0], p.mat.gg[1], p.mat.poiss[0], p.mat.poiss[1], p.ps.data(), tbl.data());
+            if (rc) { *ierror = rc; return; }
+            std::vector<int> ixs, iys;
+            if (b.isubs == 1 || b.isubs == 5) { for (int i = 1; i <= p.mx; i++) ixs.push_back(i); for (int j = 1; j <= p.my; j++) iys.push_back(j); }
+            else { for (double v : b.x) if (v >= 1 && v <= p.mx) ixs.push_back((int) v); for (double v : b.y) if (v >= 1 && v <= p.my) iys.push_back((int) v); }
+            b.nx = (int) ixs.size(); b.ny = (int) iys.size();
+            const int np = b.nx * b.ny * b.nz;
+            b.table.assign((size_t) 21 * np, 0.0);
+            int q = 0;
+            for (int k = 0; k < b.nz; k++) for (int j : iys) for (int i : ixs) {
+                const int ii = (i - 1) + (j - 1) * p.mx;
+                double *row = &b.table[(size_t) q * 21];
+                row[0] = p.xc1 + (i - 1) * p.dx; row[1] = p.yc1 + (j - 1) * p.dy; row[2] = b.z[k];
+                for (int c = 0; c < 18; c++) row[3 + c] = tbl[((size_t) k * npot + ii) * 18 + c];
+                q++;
+            }
+        }
+    }
+    *ierror = 0;
 }
 
 void subs_getblocksize(int *ire, int *icp, int *iblk, int *nx, int *ny, int *nz)
@@ -719,15 +764,28 @@ void subs_getblocksize(int *ire, int *icp, int *iblk, int *nx, int *ny, int *nz)
     if (!p) return;
     auto it = p->subs.find(*iblk);
     if (it == p->subs.end()) { *nx = *ny = *nz = 0; return; }
-    *nx = it->second.nx; *ny = it->second.ny; *nz = it->second.nz;
+    Problem::SubsBlock &b = it->second;
+    if (b.nx == 0 && b.ny == 0) {          // before the calculation: sizes implied by the specification
+        if (b.isubs == 1 || b.isubs == 5) { *nx = p->mx; *ny = p->my; } else { *nx = (int) b.x.size(); *ny = (int) b.y.size(); }
+    } else { *nx = b.nx; *ny = b.ny; }
+    *nz = b.nz;
 }
 
 void subs_getresults(int *ire, int *icp, int *iblk, int *lenarr, int *ncol, int *icol, double *values)
 {
     int e; Problem *p = activate(*ire, *icp, &e);
     if (!p) return;
-    (void) iblk; (void) icol;
-    for (long i = 0; i < (long) *lenarr * *ncol; i++) values[i] = -999.0;     // contact_addon.f90:6113-6178: invalid -> -999
+    auto it = p->subs.find(*iblk);
+    if (it == p->subs.end() || it->second.table.empty()) { last_error() = "subs_getresults: no results for this block"; return; }
+    const Problem::SubsBlock &b = it->second;
+    const int np = b.nx * b.ny * b.nz, n = std::min(np, *lenarr);
+    for (int jc = 0; jc < *ncol; jc++) {
+        double *col = values + (size_t) jc * *lenarr;
+        const int c = icol[jc];
+        if (c <= 0 || c > 21) { for (int i = 0; i < *lenarr; i++) col[i] = -999.0; continue; }     // contact_addon.f90:6150-6152
+        const double f = (c <= 6) ? 1.0 / p->scl.len : p->scl.area;
+        for (int i = 0; i < n; i++) col[i] = b.table[(size_t) i * 21 + (c - 1)] * f;
+    }
 }
 
 void cntc_finalize(int *ire)

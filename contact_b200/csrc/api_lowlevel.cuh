@@ -182,6 +182,39 @@ inline int snorm_batch_dev(CoefSet &cs, int ncase, int ic_norm, int maxgs, int m
     return 0;
 }
 
+// ---- batched subsurface evaluation on device buffers ----
+struct SubsBatch { double *d_vr = nullptr; long cap = 0; int *d_next = nullptr; };
+inline SubsBatch &subs_batch() { static SubsBatch b; return b; }
+
+inline int subsurf_batch_dev(CoefSet &cs, int ncase, int nz, const double *z, const double gg[2], const double poiss[2],
+                             const double *d_ps, double *d_table, cudaStream_t st)
+{
+    Engine &E = engine();
+    const ConvPlan &P = cs.hp.p;
+    if (!cs.hp.fits) { last_error() = "grid too large for the single-CTA product"; return -34; }
+    if (nz > 31) { last_error() = "at most 31 depths per subsurface block"; return -99; }
+    std::vector<double> zz(z, z + nz);
+    const cd *chat = nullptr;
+    int rc = build_subsurf_chat(cs, zz, gg, poiss, st, &chat);
+    if (rc) return rc;
+    SubsBatch &B = subs_batch();
+    const int nblk = launch_blocks(ncase * nz);
+    const long need = (long) nblk * 13 * P.npot;
+    if (!B.d_next) CB_CUDA(cudaMalloc(&B.d_next, sizeof(int)));
+    if (need > B.cap) { if (B.d_vr) cudaFree(B.d_vr); CB_CUDA(cudaMalloc(&B.d_vr, sizeof(double) * need)); B.cap = need; }
+    SubsArgs A;
+    A.ncase = ncase; A.nz = nz; A.neg_mask = 0;
+    for (int i = 0; i < nz; i++) if (z[i] < 0.0) A.neg_mask |= (1 << i);
+    A.ps = d_ps; A.chat = chat; A.vr = B.d_vr; A.table = d_table;
+    A.gg[0] = gg[0]; A.gg[1] = gg[1]; A.poiss[0] = poiss[0]; A.poiss[1] = poiss[1];
+    A.next = B.d_next; A.chat_len = P.chat_len;
+    CB_CUDA(cudaMemsetAsync(B.d_next, 0, sizeof(int), st));
+    k_subsurf_batch<<<nblk, CB_THREADS, P.smem_bytes, st>>>(P, A);
+    E.launches++;
+    CB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace cb200
 
 using namespace cb200;
@@ -331,6 +364,57 @@ double cb200_fp64_peak_tflops(int reps)
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
     return best;
+}
+
+// Subsurface block of type ISUBS 1/5: all elements x nz depths, for ncase traction fields (device buffers).
+int cb200_subsurf_batch_dev(int handle, int ncase, int nz, const double *z, double gg1, double gg2, double poiss1,
+                            double poiss2, const double *d_ps, double *d_table, void *stream)
+{
+    CoefSet *cs = set_from_handle(handle);
+    if (!cs) return -99;
+    if (ncase < 1 || nz < 1) return 0;
+    const double gg[2] = { gg1, gg2 }, poiss[2] = { poiss1, poiss2 };
+    return subsurf_batch_dev(*cs, ncase, nz, z, gg, poiss, d_ps, d_table, (cudaStream_t) stream);
+}
+
+// same with HOST buffers: ps [ncase][3][npot] -> table [ncase][nz][npot][18]
+int cb200_subsurf_batch(int handle, int ncase, int nz, const double *z, double gg1, double gg2, double poiss1,
+                        double poiss2, const double *ps, double *table)
+{
+    CoefSet *cs = set_from_handle(handle);
+    if (!cs) return -99;
+    if (ncase < 1 || nz < 1) return 0;
+    const size_t n3 = (size_t) ncase * 3 * cs->hp.p.npot, nt = (size_t) ncase * nz * cs->hp.p.npot * 18;
+    double *d_ps = nullptr, *d_t = nullptr;
+    CB_CUDA(cudaMalloc(&d_ps, sizeof(double) * n3));
+    CB_CUDA(cudaMalloc(&d_t, sizeof(double) * nt));
+    CB_CUDA(cudaMemcpy(d_ps, ps, sizeof(double) * n3, cudaMemcpyHostToDevice));
+    int rc = cb200_subsurf_batch_dev(handle, ncase, nz, z, gg1, gg2, poiss1, poiss2, d_ps, d_t, nullptr);
+    if (!rc) { cudaError_t e = cudaMemcpy(table, d_t, sizeof(double) * nt, cudaMemcpyDeviceToHost); if (e != cudaSuccess) { last_error() = cudaGetErrorString(e); rc = -99; } }
+    cudaFree(d_ps); cudaFree(d_t);
+    return rc;
+}
+
+// ISUBS 9: direct evaluation in npoint arbitrary points xyz[npoint][3] for one traction field (HOST buffers);
+// grid given by first element centre (xc1, yc1) and spacing; table [npoint][18]
+int cb200_subsurf_points(int mx, int my, double xc1, double yc1, double dx, double dy, double gg1, double gg2,
+                         double poiss1, double poiss2, const double *ps, int npoint, const double *xyz, double *table)
+{
+    int rc = engine_init();
+    if (rc) return rc;
+    const size_t n3 = (size_t) 3 * mx * my;
+    double *d_ps = nullptr, *d_x = nullptr, *d_t = nullptr;
+    CB_CUDA(cudaMalloc(&d_ps, sizeof(double) * n3));
+    CB_CUDA(cudaMalloc(&d_x, sizeof(double) * 3 * npoint));
+    CB_CUDA(cudaMalloc(&d_t, sizeof(double) * 18 * npoint));
+    CB_CUDA(cudaMemcpy(d_ps, ps, sizeof(double) * n3, cudaMemcpyHostToDevice));
+    CB_CUDA(cudaMemcpy(d_x, xyz, sizeof(double) * 3 * npoint, cudaMemcpyHostToDevice));
+    k_subsurf_points<<<grid1d(npoint, 64), 64>>>(mx, my, xc1, yc1, dx, dy, gg1, gg2, poiss1, poiss2, d_ps, d_x, npoint, d_t);
+    engine().launches++;
+    CB_CUDA(cudaGetLastError());
+    CB_CUDA(cudaMemcpy(table, d_t, sizeof(double) * 18 * npoint, cudaMemcpyDeviceToHost));
+    cudaFree(d_ps); cudaFree(d_x); cudaFree(d_t);
+    return 0;
 }
 
 long cb200_snorm_workspace_bytes(int handle, int ncase)

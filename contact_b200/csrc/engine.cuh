@@ -65,6 +65,8 @@ struct CoefSet {
     cd *d_chat[4][3][3] = {};                                      // transformed blocks (lazy)
     bool prec_ready = false;
     long n_chat_built = 0;
+    // subsurface: transformed coefficients per depth list / material, [nz][4][9][chat_len]
+    std::map<std::vector<double>, cd *> subs_chat;
 };
 
 struct Engine {
@@ -97,6 +99,7 @@ inline int engine_init()
     E.num_sms = prop.multiProcessorCount;
     CB_CUDA(cudaFuncSetAttribute(k_snorm_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     CB_CUDA(cudaFuncSetAttribute(k_build_chat, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    CB_CUDA(cudaFuncSetAttribute(k_subsurf_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     return 0;
 }
 
@@ -202,6 +205,37 @@ inline int get_coefset(int mx, int my, double dx, double dy, Material mat, int i
     E.sets[key] = cs;
     E.by_handle.push_back(cs);
     *out = cs;
+    return 0;
+}
+
+// ---- subsurface coefficients for a list of depths: built once per (grid, material, z-list), shared by all cases ----
+inline int build_subsurf_chat(CoefSet &cs, const std::vector<double> &z, const double gg[2], const double poiss[2],
+                              cudaStream_t st, const cd **out)
+{
+    Engine &E = engine();
+    std::vector<double> key(z);
+    key.push_back(gg[0]); key.push_back(gg[1]); key.push_back(poiss[0]); key.push_back(poiss[1]);
+    auto it = cs.subs_chat.find(key);
+    if (it != cs.subs_chat.end()) { *out = it->second; return 0; }
+    const ConvPlan &P = cs.hp.p;
+    const int nz = (int) z.size();
+    const long nblk = 4L * cs.mx * cs.my;
+    cd *chat = nullptr, *scr = nullptr; double *cf = nullptr;
+    const size_t nscr = (size_t) (P.Lx + 1) * 2 * P.Fy + (size_t) P.Ly * P.C;
+    CB_CUDA(cudaMalloc(&chat, sizeof(cd) * (size_t) nz * 36 * P.chat_len));
+    CB_CUDA(cudaMalloc(&scr, sizeof(cd) * nscr * 36));
+    CB_CUDA(cudaMalloc(&cf, sizeof(double) * 36 * nblk));
+    for (int iz = 0; iz < nz; iz++) {
+        const int neg = z[iz] >= 0.0 ? 1 : -1, ia = neg > 0 ? 0 : 1;
+        k_subsurf_coef<<<grid1d(nblk, 64), 64, 0, st>>>(cs.mx, cs.my, cs.key.dx, cs.key.dy, gg[ia], poiss[ia], z[iz], neg, cf);
+        k_build_chat<<<36, CB_THREADS, 64, st>>>(P, cf, cs.mx, cs.my, 1.0 / (4.0 * P.Fx * P.Fy), scr, chat + (size_t) iz * 36 * P.chat_len);
+        E.launches += 2;
+    }
+    CB_CUDA(cudaGetLastError());
+    CB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(scr); cudaFree(cf);
+    cs.subs_chat[key] = chat;
+    *out = chat;
     return 0;
 }
 

@@ -1,13 +1,19 @@
 // kernels.cuh -- __global__ entry points of the B200 hot path.
 #pragma once
 #include "norm_solver.cuh"
+#include "subsurf.cuh"
 
 namespace cb200 {
 
 // ---- coefficient transform C^ (one CTA, scratch in global memory; runs once per grid/material/block) ----
 __global__ void __launch_bounds__(CB_THREADS, 1)
-k_build_chat(ConvPlan P, const double *cfblk, int cmx, int cmy, double scale, cd *SWg, cd *chat)
+k_build_chat(ConvPlan P, const double *cfblk0, int cmx, int cmy, double scale, cd *SWg0, cd *chat0)
 {
+    // one CTA per coefficient block: blockIdx.x selects the block, its scratch and its output
+    const size_t nscr = (size_t) (P.Lx + 1) * 2 * P.Fy + (size_t) P.Ly * P.C;
+    const double *cfblk = cfblk0 + (size_t) blockIdx.x * 4 * cmx * cmy;
+    cd *SWg = SWg0 + (size_t) blockIdx.x * nscr;
+    cd *chat = chat0 + (size_t) blockIdx.x * P.chat_len;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // only the tables live in shared memory here; reuse the plan's offsets relative to off_twx
     const MemBuf<const cd> twx = { P.twx }, twy = { P.twy };        // tables straight from global (one-off kernel)

@@ -73,6 +73,9 @@ PROTOTYPES = {
     "cb200_snorm_batch": (I, [I, I, I, I, I, D, dp, ip, dp, dp, dp]),
     "cb200_snorm_kernel_ms": (D, []),
     "cb200_fp64_peak_tflops": (D, [I]),
+    "cb200_subsurf_batch_dev": (I, [I, I, I, dp, D, D, D, D, V, V, V]),
+    "cb200_subsurf_batch": (I, [I, I, I, dp, D, D, D, D, dp, dp]),
+    "cb200_subsurf_points": (I, [I, I, D, D, D, D, D, D, D, D, dp, I, dp, dp]),
     "cb200_snorm_workspace_bytes": (L, [I, I]),
 }
 

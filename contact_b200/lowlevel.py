@@ -83,6 +83,22 @@ class CoefSet:
                                                     _stream_ptr(stream)))
 
 
+    def subsurf_batch(self, ps, zs, gg=(82000.0, 82000.0), poiss=(0.28, 0.28)):
+        """HOST buffers: ps (ncase, 3, npot), depths zs -> table (ncase, nz, npot, 18)."""
+        ps = np.ascontiguousarray(ps, dtype=np.float64)
+        zs = np.ascontiguousarray(zs, dtype=np.float64)
+        tbl = np.zeros((ps.shape[0], len(zs), self.npot, 18))
+        dpp = C.POINTER(C.c_double)
+        _check(load_library().cb200_subsurf_batch(self.h, ps.shape[0], len(zs), zs.ctypes.data_as(dpp), gg[0], gg[1],
+                                                  poiss[0], poiss[1], ps.ctypes.data_as(dpp), tbl.ctypes.data_as(dpp)))
+        return tbl
+
+    def subsurf_batch_dev(self, d_ps, zs, d_table, gg=(82000.0, 82000.0), poiss=(0.28, 0.28), stream=None):
+        zs = np.ascontiguousarray(zs, dtype=np.float64)
+        _check(load_library().cb200_subsurf_batch_dev(self.h, d_ps.shape[0], len(zs), zs.ctypes.data_as(C.POINTER(C.c_double)),
+                                                      gg[0], gg[1], poiss[0], poiss[1], d_ps.data_ptr(), d_table.data_ptr(),
+                                                      _stream_ptr(stream)))
+
     def snorm_batch(self, hs, el, pn, un, scal, ic_norm, maxgs=999, maxin=20, eps=1e-5):
         """HOST buffers (numpy or pinned torch CPU tensors viewed as numpy), modified in place."""
         ncase = hs.shape[0]
@@ -104,6 +120,18 @@ def eldiv0(mx, my, dx, dy, gg, poiss, ibase, prmudf, ic_norm, fn, pen, h):
                                        h.ctypes.data_as(C.POINTER(C.c_double)), el.ctypes.data_as(C.POINTER(C.c_int)),
                                        C.byref(pen_o)))
     return el, pen_o.value
+
+
+def subsurf_points(mx, my, xc1, yc1, dx, dy, gg, poiss, ps, xyz):
+    """ISUBS 9 direct evaluation; ps (3, npot), xyz (npoint, 3). Returns (npoint, 18)."""
+    ps = np.ascontiguousarray(ps, dtype=np.float64)
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    tbl = np.zeros((xyz.shape[0], 18))
+    dpp = C.POINTER(C.c_double)
+    _check(load_library().cb200_subsurf_points(mx, my, xc1, yc1, dx, dy, gg[0], gg[1], poiss[0], poiss[1],
+                                               ps.ctypes.data_as(dpp), xyz.shape[0], xyz.ctypes.data_as(dpp),
+                                               tbl.ctypes.data_as(dpp)))
+    return tbl
 
 
 def snorm_kernel_ms():

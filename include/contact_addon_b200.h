@@ -164,6 +164,16 @@ int cb200_snorm_batch(int handle, int ncase, int ic_norm, int maxgs, int maxin, 
 double cb200_snorm_kernel_ms(void);
 /* measured FP64 FMA throughput [TFLOP/s] (roofline denominator for FP64-bound kernels) */
 double cb200_fp64_peak_tflops(int reps);
+/* Subsurface stresses (sstres_fft, m_subsurf.f90:1097-1257), block type ISUBS 1/5: all npot elements x nz depths z[],
+ * for ncase traction fields ps [ncase][3][npot]; table [ncase][nz][npot][18] = columns 4..21 of the reference's
+ * table (ux,uy,uz, sighyd,sigvm,sigtr, sigma1..3, sigma(3,3) column-major).  DEVICE / HOST buffer variants. */
+int cb200_subsurf_batch_dev(int handle, int ncase, int nz, const double *z, double gg1, double gg2, double poiss1,
+                            double poiss2, const double *d_ps, double *d_table, void *stream);
+int cb200_subsurf_batch(int handle, int ncase, int nz, const double *z, double gg1, double gg2, double poiss1,
+                        double poiss2, const double *ps, double *table);
+/* Subsurface stresses in arbitrary points (ISUBS 9, direct sum sstres, m_subsurf.f90:1412-1515); HOST buffers */
+int cb200_subsurf_points(int mx, int my, double xc1, double yc1, double dx, double dy, double gg1, double gg2,
+                         double poiss1, double poiss2, const double *ps, int npoint, const double *xyz, double *table);
 /* workspace the batched solve keeps per case, bytes (for memory planning) */
 long cb200_snorm_workspace_bytes(int handle, int ncase);
 

@@ -152,6 +152,18 @@ void   co_set_norm_rhs(int ibase, int iplan, int npot, const double *x, const do
 void   co_eldiv0(int ic_norm, int mx, int my, double dx, double dy, int ibase, const double *prmudf,
                  const co_mater *m, double fntrue, double *pen, const double *hs_n, co_eldiv *igs);
 
+/* ---- subsurface stresses (co_subsurf.c) ---- */
+void   co_stres1_pcwcns(double dx, double dy, double gg, double v[3][3][4], double vnu[3][3][4], const double xw[3],
+                        const double xp[2]);
+void   co_sym3_eigenvalues(const double s[3][3], double ev[3]);
+void   co_sstres_derived(double gg, double poiss, int neg, double vr[3][4], double out[18]);
+void   co_sstres_point(int mx, int my, double dx, double dy, const double *x, const double *y, const double gg[2],
+                       const double poiss[2], const double *ps, const double xw[3], double out[18]);
+void   co_sstres_inflcf(int mx, int my, double dx, double dy, const double gg[2], const double poiss[2], double zw,
+                        co_inflcf ck[4]);
+void   co_subsurf_block_fft(co_ctx *cx, int mx, int my, double dx, double dy, const double gg[2], const double poiss[2],
+                            const int *el, const double *ps, int nz, const double *z, int use_fft, double *table);
+
 #ifdef __cplusplus
 }
 #endif

@@ -213,3 +213,38 @@ def norm_batch(g, gg, poiss, ic_norm, loads, maxgs=999, maxin=20, eps=1e-5, nthr
                             C.c_double(eps), C.c_int(int(fullbox)), _i(el), _d(pn), _d(scal))
     return dict(nfail=nfail, el=el, pn=pn, pen=scal[:, 0], fn=scal[:, 1], itcg=scal[:, 2].astype(int),
                 n_prod=scal[:, 3].astype(int))
+
+
+def subsurf_points(mx, my, xl, yl, dx, dy, gg, poiss, ps, xs, ys, zs):
+    """ISUBS=9: direct evaluation (sstres) in the points xs x ys x zs (x fastest). ps: (3, npot).
+    Returns (npoint, 21) table: x, y, z, ux, uy, uz, sighyd, sigvm, sigtr, sigma1..3, sigma(3,3) column-major."""
+    L = lib()
+    npot = mx * my
+    x = np.zeros(npot); y = np.zeros(npot)
+    L.co_grid_coords(C.c_int(mx), C.c_int(my), C.c_double(xl), C.c_double(yl), C.c_double(dx), C.c_double(dy), _d(x), _d(y))
+    ps = np.ascontiguousarray(ps, dtype=np.float64)
+    g2 = (C.c_double * 2)(*gg); p2 = (C.c_double * 2)(*poiss)
+    rows = []
+    out = np.zeros(18)
+    for zz in zs:
+        for yy in ys:
+            for xx in xs:
+                xw = (C.c_double * 3)(xx, yy, zz)
+                L.co_sstres_point(C.c_int(mx), C.c_int(my), C.c_double(dx), C.c_double(dy), _d(x), _d(y), g2, p2, _d(ps), xw, _d(out))
+                rows.append([xx, yy, zz] + list(out))
+    return np.array(rows)
+
+
+def subsurf_block(mx, my, dx, dy, gg, poiss, el, ps, zs, use_fft=True):
+    """ISUBS=1/5 block: all elements x depths zs. Returns (nz, npot, 18): columns 4..21 of the reference's table."""
+    L = lib()
+    npot = mx * my
+    ps = np.ascontiguousarray(ps, dtype=np.float64)
+    el = np.ascontiguousarray(el, dtype=np.int32)
+    zs = np.ascontiguousarray(zs, dtype=np.float64)
+    g2 = (C.c_double * 2)(*gg); p2 = (C.c_double * 2)(*poiss)
+    tbl = np.zeros((len(zs), npot, 18))
+    ctx = Ctx(fullbox=True)
+    L.co_subsurf_block_fft(ctx.p, C.c_int(mx), C.c_int(my), C.c_double(dx), C.c_double(dy), g2, p2, _i(el), _d(ps),
+                           C.c_int(len(zs)), _d(zs), C.c_int(int(use_fft)), _d(tbl))
+    return tbl

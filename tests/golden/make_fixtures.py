@@ -59,7 +59,30 @@ def cattaneo():
     return dict(pictures=pics, source="examples/cattaneo.ref_out")
 
 
+def subsurf():
+    """examples/subsurf.ref_subs (second case: pn = 1, px = 0.999 on the unit square): block 1 fully, block 2 thinned."""
+    blocks, cur = [], None
+    for l in open(os.path.join(REF, "examples/subsurf.ref_subs")):
+        if l.startswith("%"):
+            if "NX" in l:
+                cur = dict(dims=None, rows=[])
+                blocks.append(cur)
+            continue
+        vals = [float(v) for v in l.split()]
+        if cur["dims"] is None:
+            cur["dims"] = [int(v) for v in vals[:3]]
+        else:
+            cur["rows"].append(vals)
+    b2 = blocks[1]["rows"]
+    keep = b2[::7]                                   # every 7th point keeps the fixture small (~950 rows)
+    return dict(source="examples/subsurf.ref_subs, examples/subsurf.inp:21-50",
+                grid=dict(mx=1, my=1, xl=-0.4999, yl=-0.4998, dx=1.0, dy=1.0), gg=[1.0, 1.0], poiss=[0.28, 0.28],
+                pn=1.0, px=0.999, columns="X Y Z UX UY UZ SIGHYD SIGVM SIGXX SIGXY SIGXZ SIGYY SIGYZ SIGZZ",
+                block1=blocks[0]["rows"], block2_every7=keep)
+
+
 if __name__ == "__main__":
+    json.dump(subsurf(), open(os.path.join(HERE, "subsurf_ref_subs.json"), "w"))
     json.dump(mbench_profile(), open(os.path.join(HERE, "mbench_profile.json"), "w"))
     json.dump(get_times(), open(os.path.join(HERE, "get_times.json"), "w"), indent=1)
     json.dump(cattaneo(), open(os.path.join(HERE, "cattaneo_pictures.json"), "w"))

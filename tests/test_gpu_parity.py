@@ -196,3 +196,84 @@ def test_batch_hertz91_matches_oracle(cb, O):
         assert _rel(pn.ravel(), ref["pn"]) < 1e-6
         assert abs(cb.cntc_getpenetration(ire, 1) - ref["pen"]) < 1e-7 * abs(ref["pen"])
         cb.cntc_finalize(ire)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# subsurface stresses
+# ------------------------------------------------------------------------------------------------------------
+def _golden_subsurf():
+    import json, os
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "subsurf_ref_subs.json")))
+
+
+def test_subsurf_points_match_reference_golden(cb, O):
+    """examples/subsurf.ref_subs (unit square with pn = 1, px = 0.999): ISUBS=9 direct path, 5 printed digits."""
+    g = _golden_subsurf()
+    gr = g["grid"]
+    ps = np.zeros((3, 1)); ps[0, 0] = g["px"]; ps[2, 0] = g["pn"]
+    rows = np.array(g["block1"] + g["block2_every7"])
+    xc1, yc1 = gr["xl"] + 0.5 * gr["dx"], gr["yl"] + 0.5 * gr["dy"]
+    t = cb.lowlevel.subsurf_points(1, 1, xc1, yc1, gr["dx"], gr["dy"], g["gg"], g["poiss"], ps, rows[:, :3])
+    # golden columns: UX UY UZ SIGHYD SIGVM SIGXX SIGXY SIGXZ SIGYY SIGYZ SIGZZ ; ours: sigma column-major from index 9
+    mine = np.stack([t[:, 0], t[:, 1], t[:, 2], t[:, 3], t[:, 4], t[:, 9], t[:, 12], t[:, 15], t[:, 13], t[:, 16], t[:, 17]], axis=1)
+    ref = rows[:, 3:14]
+    assert np.all(np.abs(mine - ref) <= 6e-5 * np.abs(ref) + 2e-9)
+    # and against the oracle to 1e-9
+    o = O.subsurf_points(1, 1, gr["xl"], gr["yl"], gr["dx"], gr["dy"], g["gg"], g["poiss"], ps,
+                         [rows[0, 0]], [rows[0, 1]], list(rows[:15, 2]))
+    assert _rel(t[:15], o[:, 3:]) < 1e-9
+
+
+def test_subsurf_block_matches_oracle(cb, O):
+    """ISUBS=5 block (all elements x depths): 36 FFT products per depth + derived stresses, vs the oracle."""
+    mx, my, dx, dy = 33, 27, 0.2, 0.15
+    gg, poiss = (82000.0, 60000.0), (0.28, 0.31)
+    rng = np.random.default_rng(21)
+    el = cases.disk_mask(mx, my, 0.35)
+    ps = np.zeros((2, 3, mx * my))
+    ps[:, 2] = 100.0 * rng.random((2, mx * my)) * el
+    ps[:, 0] = 0.3 * ps[:, 2] * rng.uniform(-1, 1, (2, mx * my))
+    ps[:, 1] = 0.3 * ps[:, 2] * rng.uniform(-1, 1, (2, mx * my))
+    zs = [1e-6, 0.1, 0.5, -0.2]
+    cset = cb.lowlevel.CoefSet(mx, my, dx, dy, gg=gg, poiss=poiss)
+    got = cset.subsurf_batch(ps, zs, gg=gg, poiss=poiss)
+    for ic in range(2):
+        ref = O.subsurf_block(mx, my, dx, dy, gg, poiss, el, ps[ic], zs, use_fft=True)
+        scale = np.abs(ref[..., 3:]).max()
+        assert np.abs(got[ic][..., :3] - ref[..., :3]).max() < 1e-9 * np.abs(ref[..., :3]).max()
+        assert np.abs(got[ic][..., 3:] - ref[..., 3:]).max() < 1e-9 * scale
+
+
+def test_subs_api_after_contact_solve(cb, O):
+    """cntc_calculate then subs_addblock / subs_calculate / subs_getresults (ISUBS 5 and 9) on the cattaneo grid."""
+    c = cases.CATTANEO2
+    ire, icp = 31, 1
+    cb.cntc_initialize(ire, 3)
+    cb.cntc_setflags(ire, icp, [cb.CNTC["ic_tang"]], [0])
+    cb.cntc_setsolverflags(ire, icp, 0, [c["maxgs"], c["maxin"], 30, 1], [c["eps"]])
+    cb.cntc_setmaterialparameters(ire, icp, 0, [c["poiss"][0], c["poiss"][1], c["gg"][0], c["gg"][1]])
+    cb.cntc_setpotcontact(ire, icp, 1, [c["mx"], c["my"], c["xl"], c["yl"], c["dx"], c["dy"]])
+    cb.cntc_setundeformeddistc(ire, icp, 1, c["prmudf"])
+    cb.cntc_setnormalforce(ire, icp, c["fn"])
+    assert cb.cntc_calculate(ire, icp) == 0
+    zs = [0.0, 0.25, 0.5]
+    cb.subs_addblock(ire, icp, 1, 5, [], [], zs)
+    cb.subs_addblock(ire, icp, 2, 9, [0.0, 0.3], [0.0], zs)
+    assert cb.subs_calculate(ire, icp) == 0, cb.lib.last_error()
+    assert cb.subs_getblocksize(ire, icp, 1) == (19, 19, 3) and cb.subs_getblocksize(ire, icp, 2) == (2, 1, 3)
+    pn, px, py = cb.cntc_gettractions(ire, icp)
+    ps = np.stack([px.ravel(), py.ravel(), pn.ravel()])
+    el = cb.cntc_getelementdivision(ire, icp).ravel()
+    t1 = cb.subs_getresults(ire, icp, 1, list(range(1, 22)))
+    ref = O.subsurf_block(c["mx"], c["my"], c["dx"], c["dy"], c["gg"], c["poiss"], el, ps, zs).reshape(-1, 18)
+    # z = 0 exactly sits on the regularised singularity of the closed forms (epsrel, m_subsurf.f90:1655): device and
+    # host libm differ in the last ulp of log/atan there and the cancellation amplifies it to ~2e-9
+    assert _rel(t1[:, 3:], ref) < 2e-8
+    assert _rel(t1[361:, 3:], ref[361:]) < 1e-9
+    t2 = cb.subs_getresults(ire, icp, 2, [1, 2, 3, 8, 21, 25])
+    assert (t2[:, 5] == -999.0).all()
+    o2 = O.subsurf_points(c["mx"], c["my"], c["xl"], c["yl"], c["dx"], c["dy"], c["gg"], c["poiss"], ps, [0.0, 0.3], [0.0], zs)
+    assert _rel(t2[:, 3], o2[:, 7]) < 1e-9 and _rel(t2[:, 4], o2[:, 20]) < 1e-9
+    # Hertz: max von Mises stress below the surface on the axis, sigma_zz(0) = -pmax
+    assert abs(o2[0, 20] + pn.max()) < 2e-2 * pn.max()
+    cb.cntc_finalize(ire)
