@@ -32,6 +32,7 @@ sys.path.insert(0, ROOT)
 from tests import cases  # noqa: E402  (seeded synthetic inputs only; no oracle import here)
 
 FN0 = 50000.0
+SUBS_Z = [1e-6, 0.1, 0.2, 0.3, 0.5, 1.0, 1.5, 2.0, 3.0, 5.0, 9.0]      # perfc_test/spence71_8281pt.inp:17-24
 EPS, MAXGS, MAXIN = 1e-6, 999, 20
 METRIC, UNIT = "contact_solves_per_s_8281el", "solves/s"
 
@@ -196,6 +197,20 @@ def run_gpu(args):
     assert table.shape[0] == ncase * world
     nprod = float(scal[:, 7].sum())
     itcg_mean = float(scal[:, 2].mean())
+    # ---- subsurface leg (ISUBS 5 block of spence71_8281pt.inp: 11 depths x 8281 points, 36 products per depth) ----
+    nsub = min(ncase, nsm)
+    d_ps = torch.zeros(nsub, 3, npot, dtype=torch.float64, device=dev)
+    d_ps[:, 2] = d_pn[:nsub]
+    d_tab = torch.empty(nsub, len(SUBS_Z), npot, 18, dtype=torch.float64, device=dev)
+    cset.subsurf_batch_dev(d_ps, SUBS_Z, d_tab, **cases.STEEL)              # builds + caches the 11 x 36 transforms
+    torch.cuda.synchronize()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(2):
+        cset.subsurf_batch_dev(d_ps, SUBS_Z, d_tab, **cases.STEEL)
+    s1.record()
+    torch.cuda.synchronize()
+    subs_ms = s0.elapsed_time(s1) / 2
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end-to-end leg (host buffers through the C-ABI) ----
@@ -253,6 +268,10 @@ def run_gpu(args):
                               "frac": fp64_ach / fp64_peak if fp64_peak > 0 else None,
                               "peak_source": "measured here with a DFMA chain kernel (cb200_fp64_peak_tflops)"},
             "kernel_ms": kernel_ms, "products_per_step": nprod_all, "mean_itcg": itcg_mean,
+            "subsurf": {"cases": nsub, "depths": len(SUBS_Z), "points_per_case": npot * len(SUBS_Z),
+                        "products": nsub * len(SUBS_Z) * 36, "ms": subs_ms, "cases_per_s": nsub / (subs_ms * 1e-3),
+                        "note": "ISUBS=5 block of spence71_8281pt.inp on the solved pressures of this rank; "
+                                "coefficient transforms cached per (grid, material, z)"},
         }
         if args.cpu_seconds > 0:
             out["cpu_baseline"] = cpu_baseline(args.cpu_seconds, threads=1)
@@ -275,7 +294,12 @@ def cpu_baseline(budget_s, threads):
     t0 = time.perf_counter()
     r = O.norm_batch(g, cases.STEEL["gg"], cases.STEEL["poiss"], 1, fns[:ns], maxgs=MAXGS, maxin=MAXIN, eps=EPS, nthreads=threads)
     dt = time.perf_counter() - t0
-    return {"value": ns / dt, "unit": UNIT, "cores": threads, "kind": "port",
+    t1 = time.perf_counter()
+    el1 = (r["pn"][0] > 0).astype(np.int32)
+    ps1 = np.zeros((3, g["mx"] * g["my"])); ps1[2] = r["pn"][0]
+    O.subsurf_block(g["mx"], g["my"], g["dx"], g["dy"], cases.STEEL["gg"], cases.STEEL["poiss"], el1, ps1, SUBS_Z)
+    dts = time.perf_counter() - t1
+    return {"value": ns / dt, "unit": UNIT, "cores": threads, "kind": "port", "subsurf_cases_per_s": 1.0 / dts,
             "sample": "%d hertz-91 cases (first of the seeded sweep), %.1f s wall; CPU restatement of the reference "
                       "algorithm (oracle/), gcc -O2, own mixed-radix FFT instead of MKL" % (ns, dt),
             "mean_itcg": float(r["itcg"].mean())}

@@ -268,8 +268,10 @@ def test_subs_api_after_contact_solve(cb, O):
     ref = O.subsurf_block(c["mx"], c["my"], c["dx"], c["dy"], c["gg"], c["poiss"], el, ps, zs).reshape(-1, 18)
     # z = 0 exactly sits on the regularised singularity of the closed forms (epsrel, m_subsurf.f90:1655): device and
     # host libm differ in the last ulp of log/atan there and the cancellation amplifies it to ~2e-9
+    # Away from z = 0 the four-corner closed forms still cancel by 1e-4..1e-6 for far elements, so 1-ulp differences
+    # between device and host log/atan show up at a few 1e-9 of the largest stress: 1e-8 is the conditioning limit.
     assert _rel(t1[:, 3:], ref) < 2e-8
-    assert _rel(t1[361:, 3:], ref[361:]) < 1e-9
+    assert _rel(t1[361:, 3:], ref[361:]) < 1e-8
     t2 = cb.subs_getresults(ire, icp, 2, [1, 2, 3, 8, 21, 25])
     assert (t2[:, 5] == -999.0).all()
     o2 = O.subsurf_points(c["mx"], c["my"], c["xl"], c["yl"], c["dx"], c["dy"], c["gg"], c["poiss"], ps, [0.0, 0.3], [0.0], zs)
