@@ -58,7 +58,9 @@ struct Problem {
     // results
     int ncase = 0, itnorm = 0, ittang = 0, itcg = 0, ncon = 0, nadh = 0, nslip = 0, status = 0;
     std::vector<int> el;
-    std::vector<double> ps, us, hs;      // [3][npot]
+    std::vector<double> ps, us, hs, ss;  // [3][npot]
+    int itgs = 0;
+    std::vector<int> nr_itcg;            // TangCG iterations per solver call of the Newton-Raphson process
     double fcntc[3] = { 0, 0, 0 }, mztrue = 0;
     double t_wall = 0, t_cpu = 0;
     bool solved = false;
@@ -192,7 +194,9 @@ inline int count_at_boundary(const Problem &p)
 // check_case / scope check: returns 0 or an error code
 inline int check_scope(const Problem &p)
 {
-    if (p.tang != 0) { last_error() = "T-digit: tangential problems are not yet served by the B200 path"; return CNTC_err_other; }
+    if (p.tang != 0 && p.tang != 1) { last_error() = "T-digit: only T=0 (frictionless) and T=1 (shift) are served by the B200 path yet; rolling (T=2,3) is not"; return CNTC_err_other; }
+    if (p.tang == 1 && p.frclaw != 0) { last_error() = "L-digit: only Coulomb friction (L=0)"; return CNTC_err_other; }
+    if (p.tang == 1 && p.gausei == 2) { last_error() = "G-digit: ConvexGS (G=2) is not served by the B200 path yet"; return CNTC_err_other; }
     if (p.mater != 0) { last_error() = "M-digit: only the elastic half-space (M=0) is in the hot-path scope"; return CNTC_err_other; }
     if (p.gencr != 2 && p.gencr != 1) { last_error() = "C-digit: only piecewise-constant analytical coefficients (C=2)"; return CNTC_err_other; }
     if (p.bound != 0) { last_error() = "B-digit: only the full normal problem (B=0)"; return CNTC_err_other; }
@@ -238,66 +242,133 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
     }
     for (auto &g : groups) {
         CoefSet &cs = *g.first;
-        const std::vector<size_t> &idx = g.second;
-        const int nc = (int) idx.size(), npot = cs.mx * cs.my;
-        // all cases of a launch share ic_norm / solver settings: split further if they differ
-        std::map<std::tuple<int, int, int, double>, std::vector<size_t>> sub;
-        for (size_t k : idx) sub[std::make_tuple(probs[k]->norm, probs[k]->maxgs, probs[k]->maxin, probs[k]->eps)].push_back(k);
-        (void) nc;
-        for (auto &s : sub) {
-            const std::vector<size_t> &ks = s.second;
-            const int n = (int) ks.size();
-            std::vector<double> h_hs((size_t) n * npot), h_pn((size_t) n * npot), h_scal((size_t) n * 8, 0.0);
-            std::vector<int> h_el((size_t) n * npot);
-            for (int i = 0; i < n; i++) {
-                const size_t k = ks[i];
-                std::copy(hs[k].begin(), hs[k].end(), h_hs.begin() + (size_t) i * npot);
-                std::copy(el0[k].begin(), el0[k].end(), h_el.begin() + (size_t) i * npot);
-                std::copy(probs[k]->ps.begin() + 2 * (size_t) npot, probs[k]->ps.begin() + 3 * (size_t) npot, h_pn.begin() + (size_t) i * npot);
-                h_scal[i * 8 + 0] = pen0[k]; h_scal[i * 8 + 1] = probs[k]->fntrue;
-            }
-            double *d_hs = nullptr, *d_pn = nullptr, *d_un = nullptr, *d_scal = nullptr; int *d_el = nullptr;
-            int rc = 0;
-            auto fail = [&](int code) { for (size_t k : ks) ierr[k] = code; };
-            if (cudaMalloc(&d_hs, sizeof(double) * n * npot) != cudaSuccess || cudaMalloc(&d_pn, sizeof(double) * n * npot) != cudaSuccess ||
-                cudaMalloc(&d_un, sizeof(double) * n * npot) != cudaSuccess || cudaMalloc(&d_scal, sizeof(double) * n * 8) != cudaSuccess ||
-                cudaMalloc(&d_el, sizeof(int) * n * npot) != cudaSuccess) { last_error() = "device allocation failed"; fail(CNTC_err_other); rc = -1; }
-            if (!rc) {
-                cudaMemcpy(d_hs, h_hs.data(), sizeof(double) * n * npot, cudaMemcpyHostToDevice);
-                cudaMemcpy(d_pn, h_pn.data(), sizeof(double) * n * npot, cudaMemcpyHostToDevice);
-                cudaMemcpy(d_el, h_el.data(), sizeof(int) * n * npot, cudaMemcpyHostToDevice);
-                cudaMemcpy(d_scal, h_scal.data(), sizeof(double) * n * 8, cudaMemcpyHostToDevice);
-                rc = snorm_batch_dev(cs, n, std::get<0>(s.first), std::get<1>(s.first), std::get<2>(s.first), std::get<3>(s.first),
-                                     d_hs, d_el, d_pn, d_un, d_scal, 0);
-                if (rc) fail(rc);
-            }
-            if (!rc) {
-                std::vector<double> h_un((size_t) n * npot);
-                cudaError_t e = cudaMemcpy(h_pn.data(), d_pn, sizeof(double) * n * npot, cudaMemcpyDeviceToHost);
-                if (e == cudaSuccess) e = cudaMemcpy(h_un.data(), d_un, sizeof(double) * n * npot, cudaMemcpyDeviceToHost);
-                if (e == cudaSuccess) e = cudaMemcpy(h_el.data(), d_el, sizeof(int) * n * npot, cudaMemcpyDeviceToHost);
-                if (e == cudaSuccess) e = cudaMemcpy(h_scal.data(), d_scal, sizeof(double) * n * 8, cudaMemcpyDeviceToHost);
-                if (e != cudaSuccess) { last_error() = cudaGetErrorString(e); fail(CNTC_err_other); }
-                else for (int i = 0; i < n; i++) {
-                    Problem &p = *probs[ks[i]];
-                    p.el.assign(h_el.begin() + (size_t) i * npot, h_el.begin() + (size_t) (i + 1) * npot);
-                    p.ps.assign(3 * (size_t) npot, 0.0);
-                    p.us.assign(3 * (size_t) npot, 0.0);
-                    std::copy(h_pn.begin() + (size_t) i * npot, h_pn.begin() + (size_t) (i + 1) * npot, p.ps.begin() + 2 * (size_t) npot);
-                    std::copy(h_un.begin() + (size_t) i * npot, h_un.begin() + (size_t) (i + 1) * npot, p.us.begin() + 2 * (size_t) npot);
-                    p.hs.assign(3 * (size_t) npot, 0.0);
-                    std::copy(hs[ks[i]].begin(), hs[ks[i]].end(), p.hs.begin() + 2 * (size_t) npot);
-                    const double *sc = &h_scal[i * 8];
-                    p.pen = sc[0]; p.fntrue = sc[1]; p.itcg = (int) sc[2]; p.itnorm = (int) sc[3]; p.ncon = (int) sc[4];
-                    p.status = (int) sc[5]; p.ittang = 0; p.nadh = p.ncon; p.nslip = 0;
-                    p.fcntc[0] = 0.0; p.fcntc[1] = 0.0; p.fcntc[2] = p.fntrue; p.mztrue = 0.0;
-                    p.solved = true;
-                    if (p.itnorm < 0 || (p.status & 1)) ierr[ks[i]] = CNTC_err_norm;
-                    else ierr[ks[i]] = count_at_boundary(p);              // contact_addon.f90:3885-3891
-                }
-            }
-            cudaFree(d_hs); cudaFree(d_pn); cudaFree(d_un); cudaFree(d_scal); cudaFree(d_el);
+        const std::vector<size_t> &ks = g.second;
+        const int n = (int) ks.size(), npot = cs.mx * cs.my;
+        const ConvPlan &P = cs.hp.p;
+        auto fail = [&](int code) { for (size_t k : ks) ierr[k] = code; };
+        bool any_tang = false;
+        for (size_t k : ks) any_tang = any_tang || probs[k]->tang != 0;
+        // coefficient transforms needed by this group
+        int rc = build_prec(cs, 0, 3);
+        if (!rc) rc = build_chat(cs, SET_CS, 3, 3, 0);
+        if (!rc) rc = build_chat(cs, SET_MS, 3, 3, 0);
+        if (!rc && any_tang) {
+            for (int ik = 1; ik <= 2 && !rc; ik++) { rc = build_prec(cs, 0, ik); if (!rc) rc = build_chat(cs, SET_MS, ik, ik, 0); }
+            for (int ik = 1; ik <= 2 && !rc; ik++) for (int jk = 1; jk <= 2 && !rc; jk++) rc = build_chat(cs, SET_CS, ik, jk, 0);
         }
+        if (!rc && cs.nt_cpl) {
+            for (int t = 1; t <= 2 && !rc; t++) { rc = build_chat(cs, SET_CS, 3, t, 0); if (!rc && any_tang) rc = build_chat(cs, SET_CS, t, 3, 0); }
+        }
+        if (rc) { fail(rc); continue; }
+        // device buffers: per case hs_n(1) hst(2) ps(3) ss(2) work(9) twork(24) = 41 n doubles, el n ints
+        const size_t per = (size_t) 41 * npot;
+        double *d_buf = nullptr; int *d_el = nullptr, *d_next = nullptr; ContactCase *d_cases = nullptr;
+        if (cudaMalloc(&d_buf, sizeof(double) * per * n) != cudaSuccess || cudaMalloc(&d_el, sizeof(int) * (size_t) n * npot) != cudaSuccess ||
+            cudaMalloc(&d_cases, sizeof(ContactCase) * n) != cudaSuccess || cudaMalloc(&d_next, sizeof(int)) != cudaSuccess) {
+            last_error() = "device allocation failed"; fail(CNTC_err_other);
+            cudaFree(d_buf); cudaFree(d_el); cudaFree(d_cases); cudaFree(d_next);
+            continue;
+        }
+        std::vector<ContactCase> hc(n);
+        std::vector<double> stage((size_t) 6 * npot);
+        const size_t nblk = (size_t) 4 * cs.mx * cs.my;
+        double c00[2] = { 0, 0 };
+        cudaMemcpy(&c00[0], cs.d_cf[SET_CS] + 0 * nblk + (size_t) cs.my * 2 * cs.mx + cs.mx, sizeof(double), cudaMemcpyDeviceToHost);
+        cudaMemcpy(&c00[1], cs.d_cf[SET_CS] + 4 * nblk + (size_t) cs.my * 2 * cs.mx + cs.mx, sizeof(double), cudaMemcpyDeviceToHost);
+        for (int i = 0; i < n; i++) {
+            Problem &p = *probs[ks[i]];
+            double *base = d_buf + per * i;
+            ContactCase &c = hc[i];
+            memset(&c, 0, sizeof(c));
+            NormCase &nc = c.nrm;
+            nc.hs = base; c.hst = base + npot; c.ps = base + 3 * (size_t) npot; c.ss = base + 6 * (size_t) npot;
+            nc.work = base + 8 * (size_t) npot; c.twork = base + 17 * (size_t) npot;
+            nc.pn = c.ps + 2 * (size_t) npot; nc.el = d_el + (size_t) i * npot;
+            nc.chatA = cs.d_chat[SET_CS][2][2]; nc.chatM = cs.d_chat[SET_MS][2][2];
+            nc.chatA31 = cs.nt_cpl ? cs.d_chat[SET_CS][2][0] : nullptr; nc.chatA32 = cs.nt_cpl ? cs.d_chat[SET_CS][2][1] : nullptr;
+            nc.ptx = cs.nt_cpl ? c.ps : nullptr; nc.pty = cs.nt_cpl ? c.ps + npot : nullptr;
+            nc.cf33 = cs.d_cf[SET_CS] + 8 * nblk; nc.cmx = cs.mx; nc.cmy = cs.my; nc.ga_inv = cs.ga_inv;
+            nc.ic_norm = p.norm; nc.maxgs = p.maxgs; nc.maxin = p.maxin; nc.eps = p.eps; nc.dxdy = p.dx * p.dy;
+            nc.pen = pen0[ks[i]]; nc.fntrue = p.fntrue;
+            c.tang = p.tang; c.force3 = p.force3; c.maxnr = p.maxnr; c.maxout = p.maxout;
+            c.cksi = p.cksi; c.ceta = p.ceta; c.fxrel = p.fxrel; c.fyrel = p.fyrel; c.fstat = p.fstat;
+            if (p.iestim == 0 || p.iestim == 2) { if (p.force3 >= 1) c.cksi = 1e-6; if (p.force3 == 2) c.ceta = 0.0; }   // m_sdis.f90:760-762
+            c.pv = nullptr;
+            for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) { c.chatA[a][b] = cs.d_chat[SET_CS][a][b]; c.chatV[a][b] = cs.d_chat[SET_CS][a][b]; }
+            c.chatM11 = cs.d_chat[SET_MS][0][0]; c.chatM22 = cs.d_chat[SET_MS][1][1];
+            c.cf11 = cs.d_cf[SET_CS] + 0 * nblk; c.cf22 = cs.d_cf[SET_CS] + 4 * nblk;
+            c.c11 = c00[0]; c.c22 = c00[1]; c.ga = cs.ga;
+            // host inputs: hs_n, hst (set_tang_rhs, m_sdis.f90:498-583; shifts: dq = 1), ps
+            std::copy(hs[ks[i]].begin(), hs[ks[i]].end(), stage.begin());
+            const double dq = 1.0;
+            for (int iy = 0; iy < p.my; iy++) for (int ix = 0; ix < p.mx; ix++) {
+                const int ii = iy * p.mx + ix;
+                const double x = p.xc1 + ix * p.dx, y = p.yc1 + iy * p.dy;
+                double wx = -(y) * p.cphi, wy = (x) * p.cphi;
+                if (p.force3 == 0) wx += p.cksi;
+                if (p.force3 <= 1) wy += p.ceta;
+                stage[npot + ii] = -dq * wx; stage[2 * (size_t) npot + ii] = -dq * wy;
+            }
+            std::copy(p.ps.begin(), p.ps.end(), stage.begin() + 3 * (size_t) npot);
+            cudaMemcpy(base, stage.data(), sizeof(double) * 6 * npot, cudaMemcpyHostToDevice);
+            cudaMemcpy(nc.el, el0[ks[i]].data(), sizeof(int) * npot, cudaMemcpyHostToDevice);
+        }
+        cudaMemset(d_buf + 6 * (size_t) npot, 0, 0);
+        cudaMemcpy(d_cases, hc.data(), sizeof(ContactCase) * n, cudaMemcpyHostToDevice);
+        cudaMemset(d_next, 0, sizeof(int));
+        k_contac_batch<<<launch_blocks(n), CB_THREADS, P.smem_bytes>>>(P, d_cases, n, d_next);
+        engine().launches++;
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { last_error() = std::string("k_contac_batch: ") + cudaGetErrorString(e); fail(CNTC_err_other); }
+        else {
+            cudaMemcpy(hc.data(), d_cases, sizeof(ContactCase) * n, cudaMemcpyDeviceToHost);
+            // soutpt (m_soutpt.f90:378-398): us = A ps on the contact area, all directions
+            double *d_us = nullptr, *d_pb = nullptr;
+            cudaMalloc(&d_us, sizeof(double) * 3 * (size_t) npot * n); cudaMalloc(&d_pb, sizeof(double) * 3 * (size_t) npot * n);
+            cudaMemset(d_us, 0, sizeof(double) * 3 * (size_t) npot * n);
+            for (int i = 0; i < n; i++) cudaMemcpy(d_pb + (size_t) i * 3 * npot, hc[i].ps, sizeof(double) * 3 * npot, cudaMemcpyDeviceToDevice);
+            rc = vecaijpj_dev(cs, SET_CS, n, -8, any_tang ? -3 : 3, any_tang ? -3 : 3, d_pb, d_el, d_us, 0);
+            std::vector<double> h_us((size_t) 3 * npot * n);
+            cudaMemcpy(h_us.data(), d_us, sizeof(double) * h_us.size(), cudaMemcpyDeviceToHost);
+            cudaFree(d_us); cudaFree(d_pb);
+            for (int i = 0; i < n; i++) {
+                Problem &p = *probs[ks[i]];
+                const ContactCase &c = hc[i];
+                p.el.resize(npot); p.ps.assign(3 * (size_t) npot, 0.0); p.ss.assign(3 * (size_t) npot, 0.0);
+                cudaMemcpy(p.el.data(), c.nrm.el, sizeof(int) * npot, cudaMemcpyDeviceToHost);
+                cudaMemcpy(p.ps.data(), c.ps, sizeof(double) * 3 * npot, cudaMemcpyDeviceToHost);
+                if (p.tang != 0) cudaMemcpy(p.ss.data(), c.ss, sizeof(double) * 2 * npot, cudaMemcpyDeviceToHost);
+                p.us.assign(h_us.begin() + (size_t) i * 3 * npot, h_us.begin() + (size_t) (i + 1) * 3 * npot);
+                p.hs.assign(3 * (size_t) npot, 0.0);
+                std::copy(hs[ks[i]].begin(), hs[ks[i]].end(), p.hs.begin() + 2 * (size_t) npot);
+                p.pen = c.nrm.pen; p.fntrue = c.nrm.fntrue; p.itcg = c.nrm.itcg; p.itnorm = c.nrm.itnorm; p.ncon = c.nrm.ncon;
+                p.status = c.nrm.status; p.ittang = c.ittang; p.itgs = c.itgs; p.nadh = c.nadh; p.nslip = c.nslip;
+                p.nr_itcg.assign(c.nr_itcg, c.nr_itcg + std::min(c.nr_n, (int) CB_MAXNR_LOG));
+                const double muscal = p.fstat;
+                double sx = 0, sy = 0, mz = 0;
+                for (int iy = 0; iy < p.my; iy++) for (int ix = 0; ix < p.mx; ix++) {
+                    const int ii = iy * p.mx + ix;
+                    const double x = p.xc1 + ix * p.dx, y = p.yc1 + iy * p.dy;
+                    sx += p.ps[ii]; sy += p.ps[npot + ii]; mz += -p.ps[ii] * y + p.ps[npot + ii] * x;
+                }
+                const double dxdy = p.dx * p.dy;
+                if (p.tang != 0) {                                       // m_soutpt.f90:424-450
+                    if (p.force3 == 0) p.fxrel = dxdy * sx / (p.fntrue * muscal + 1e-20);
+                    if (p.force3 <= 1) p.fyrel = dxdy * sy / (p.fntrue * muscal + 1e-20);
+                    if (p.force3 >= 1) p.cksi = c.cksi;
+                    if (p.force3 >= 2) p.ceta = c.ceta;
+                    p.fcntc[0] = p.fxrel * (p.fntrue * muscal + 1e-20); p.fcntc[1] = p.fyrel * (p.fntrue * muscal + 1e-20);
+                    p.mztrue = dxdy * mz;
+                    if (fabs(p.mztrue) < 0.5 * p.eps * (muscal * p.fntrue + 1e-20)) p.mztrue = 0.0;
+                } else { p.fcntc[0] = p.fcntc[1] = 0.0; p.mztrue = 0.0; }
+                p.fcntc[2] = p.fntrue;
+                p.solved = true;
+                if (p.itnorm < 0 || (p.status & 1)) ierr[ks[i]] = CNTC_err_norm;
+                else if (p.ittang < 0) ierr[ks[i]] = CNTC_err_tang;
+                else ierr[ks[i]] = count_at_boundary(p);              // contact_addon.f90:3885-3891
+            }
+        }
+        cudaFree(d_buf); cudaFree(d_el); cudaFree(d_cases); cudaFree(d_next);
     }
     const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     for (size_t k = 0; k < nb; k++) { probs[k]->t_wall += dt / (double) nb; probs[k]->t_cpu += dt / (double) nb; }
@@ -502,13 +573,19 @@ void cntc_setcreepages(int *ire, int *icp, double *vx, double *vy, double *phi)
     if (!p) return;
     // contact_addon.f90:2491-2530: shifts [length] for T=1, creepages [-] for T=2,3; sign by body convention
     const bool shift = (p->tang == 1);
-    p->cksi = *vx * p->scl.body * (shift ? p->scl.len : 1.0);
-    p->ceta = *vy * p->scl.body * (shift ? p->scl.len : 1.0);
-    p->cphi = *phi * p->scl.body * (shift ? p->scl.angle : p->scl.angle / p->scl.len);
+    p->cksi = *vx * (shift ? p->scl.len : 1.0);
+    p->ceta = *vy * (shift ? p->scl.len : 1.0);
+    p->cphi = shift ? *phi : *phi / p->scl.len;
 }
 
 void cntc_settangentialforces(int *ire, int *icp, double *fx, double *fy)
-{ int e; Problem *p = activate(*ire, *icp, &e); if (p) { p->fxrel = *fx * p->scl.body; p->fyrel = *fy * p->scl.body; } }
+{
+    int e; Problem *p = activate(*ire, *icp, &e);
+    if (!p) return;
+    p->fxrel = *fx; p->fyrel = *fy;                       // relative to fstat*fn, contact_addon.f90:2597-2650
+    const double fabs_ = sqrt(p->fxrel * p->fxrel + p->fyrel * p->fyrel);
+    if (fabs_ > 1.0) { p->fxrel /= fabs_; p->fyrel /= fabs_; }
+}
 
 // initial element division and approach estimate of eldiv0 (m_sdis.f90:818-1007) for kernel-level callers
 int cb200_eldiv0(int mx, int my, double dx, double dy, double gg1, double gg2, double poiss1, double poiss2,
@@ -526,6 +603,17 @@ int cb200_eldiv0(int mx, int my, double dx, double dy, double gg1, double gg2, d
     initial_eldiv(p, hv, e, pen);
     std::copy(e.begin(), e.end(), el);
     *pen_out = pen;
+    return 0;
+}
+
+// iteration counters of the last case: out[0..5] = itnorm, itcg (NormCG), ittang, itgs (tangential solver iterations),
+// ncon, number of tangential solver calls nr_n; nr_itcg[0..nr_n) = iterations per solver call (at most lenarr)
+int cb200_get_iterations(int ire, int icp, int *out, int lenarr, int *nr_itcg)
+{
+    int e; Problem *p = activate(ire, icp, &e);
+    if (!p) return e;
+    out[0] = p->itnorm; out[1] = p->itcg; out[2] = p->ittang; out[3] = p->itgs; out[4] = p->ncon; out[5] = (int) p->nr_itcg.size();
+    for (int i = 0; i < lenarr && i < (int) p->nr_itcg.size(); i++) nr_itcg[i] = p->nr_itcg[i];
     return 0;
 }
 
@@ -579,9 +667,9 @@ void cntc_getcreepages(int *ire, int *icp, double *vx, double *vy, double *phi)
     int e; Problem *p = activate(*ire, *icp, &e);
     if (!p) return;
     const bool shift = (p->tang == 1);
-    *vx = p->cksi * p->scl.body / (shift ? p->scl.len : 1.0);
-    *vy = p->ceta * p->scl.body / (shift ? p->scl.len : 1.0);
-    *phi = p->cphi * p->scl.body / (shift ? p->scl.angle : p->scl.angle / p->scl.len);
+    *vx = p->cksi / (shift ? p->scl.len : 1.0);
+    *vy = p->ceta / (shift ? p->scl.len : 1.0);
+    *phi = shift ? p->cphi : p->cphi * p->scl.len;
 }
 
 void cntc_getcontactforces(int *ire, int *icp, double *fn, double *tx, double *ty, double *mz)
@@ -647,6 +735,8 @@ void cntc_getfielddata(int *ire, int *icp, int *ifld, int *lenarr, double *fld)
     case CNTC_fld_ux: src = &p->us; col = 0; scl = 1.0 / s.len; break;
     case CNTC_fld_uy: src = &p->us; col = 1; scl = 1.0 / s.len; break;
     case CNTC_fld_un: src = &p->us; col = 2; scl = 1.0 / s.len; break;
+    case CNTC_fld_sx: src = &p->ss; col = 0; scl = s.body / (p->tang >= 2 ? p->dq : 1.0); break;
+    case CNTC_fld_sy: src = &p->ss; col = 1; scl = s.body / (p->tang >= 2 ? p->dq : 1.0); break;
     default: break;
     }
     for (int i = 0; i < *lenarr && i < npot; i++) {

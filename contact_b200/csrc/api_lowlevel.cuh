@@ -252,7 +252,7 @@ int cb200_coefset_get_block(int handle, int set, int ik, int jk, double *out)
     CoefSet *cs = set_from_handle(handle);
     if (!cs) return -99;
     if (set < 0 || set > 3 || ik < 1 || ik > 3 || jk < 1 || jk > 3) { last_error() = "invalid block"; return -99; }
-    if (set == SET_MS) { int rc = build_prec(*cs, 0); if (rc) return rc; }
+    if (set == SET_MS) { int rc = build_prec(*cs, 0, ik); if (rc) return rc; }
     if (!cs->d_cf[set]) { last_error() = "coefficient set not available"; return -99; }
     const size_t nblk = (size_t) 4 * cs->mx * cs->my;
     CB_CUDA(cudaMemcpy(out, cs->d_cf[set] + ((jk - 1) * 3 + (ik - 1)) * nblk, sizeof(double) * nblk, cudaMemcpyDeviceToHost));

@@ -63,7 +63,7 @@ struct CoefSet {
     unsigned short *d_posx = nullptr;
     double *d_cf[4] = { nullptr, nullptr, nullptr, nullptr };     // spatial coefficients, 9 blocks each
     cd *d_chat[4][3][3] = {};                                      // transformed blocks (lazy)
-    bool prec_ready = false;
+    bool prec_ready[3] = { false, false, false };
     long n_chat_built = 0;
     // subsurface: transformed coefficients per depth list / material, [nz][4][9][chat_len]
     std::map<std::vector<double>, cd *> subs_chat;
@@ -100,6 +100,7 @@ inline int engine_init()
     CB_CUDA(cudaFuncSetAttribute(k_snorm_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     CB_CUDA(cudaFuncSetAttribute(k_build_chat, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     CB_CUDA(cudaFuncSetAttribute(k_subsurf_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    CB_CUDA(cudaFuncSetAttribute(k_contac_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     return 0;
 }
 
@@ -130,10 +131,10 @@ inline int build_chat(CoefSet &cs, int set, int ik, int jk, cudaStream_t st)
 // ---- FFT preconditioner: ms(3,3) = G^2 IFFT2(1 / FFT2(cs(3,3))) on the un-optimised (2mx x 2my) array ----
 // Follows fft_makePrec (/root/reference/src/m_aijpj.f90:457-708).  The size is not FFT friendly (e.g. 2*7*13), so
 // this one-off transform is done as dense separable DFTs.
-inline int build_prec(CoefSet &cs, cudaStream_t st)
+inline int build_prec(CoefSet &cs, cudaStream_t st, int ik = 3)
 {
     Engine &E = engine();
-    if (cs.prec_ready) return 0;
+    if (cs.prec_ready[ik - 1]) return 0;
     const int n1 = 2 * cs.mx, n2 = 2 * cs.my;
     const long n = (long) n1 * n2;
     std::vector<cd> t1(n1), t2(n2);
@@ -147,7 +148,8 @@ inline int build_prec(CoefSet &cs, cudaStream_t st)
     CB_CUDA(cudaMalloc(&b, sizeof(cd) * n));
     CB_CUDA(cudaMemcpyAsync(d_t1, t1.data(), sizeof(cd) * n1, cudaMemcpyHostToDevice, st));
     CB_CUDA(cudaMemcpyAsync(d_t2, t2.data(), sizeof(cd) * n2, cudaMemcpyHostToDevice, st));
-    const double *c33 = cs.d_cf[SET_CS] + (size_t) 8 * n;
+    const size_t blk_ = (size_t) ((ik - 1) * 3 + (ik - 1));
+    const double *c33 = cs.d_cf[SET_CS] + blk_ * n;
     if (!cs.d_cf[SET_MS]) {
         CB_CUDA(cudaMalloc(&cs.d_cf[SET_MS], sizeof(double) * 9 * n));
         CB_CUDA(cudaMemsetAsync(cs.d_cf[SET_MS], 0, sizeof(double) * 9 * n, st));
@@ -159,12 +161,12 @@ inline int build_prec(CoefSet &cs, cudaStream_t st)
     k_cplx_recip<<<G, B, 0, st>>>(a, n);
     k_dft_axis<<<G, B, 0, st>>>(a, b, n1, n2, 1, 1, d_t2);
     k_dft_axis<<<G, B, 0, st>>>(b, a, n1, n2, 0, 1, d_t1);
-    k_cplx_real_scaled<<<G, B, 0, st>>>(a, cs.d_cf[SET_MS] + (size_t) 8 * n, n, cs.ga * cs.ga / (double) n);
+    k_cplx_real_scaled<<<G, B, 0, st>>>(a, cs.d_cf[SET_MS] + blk_ * n, n, cs.ga * cs.ga / (double) n);
     E.launches += 7;
     CB_CUDA(cudaGetLastError());
     CB_CUDA(cudaStreamSynchronize(st));
     cudaFree(d_t1); cudaFree(d_t2); cudaFree(a); cudaFree(b);
-    cs.prec_ready = true;
+    cs.prec_ready[ik - 1] = true;
     return 0;
 }
 

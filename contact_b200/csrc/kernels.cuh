@@ -2,6 +2,7 @@
 #pragma once
 #include "norm_solver.cuh"
 #include "subsurf.cuh"
+#include "tang_solver.cuh"
 
 namespace cb200 {
 
@@ -150,6 +151,25 @@ k_snorm_batch(ConvPlan P, NormCase *cases, int ncase, int *next_case)
         __syncthreads();
         if (ic >= ncase) break;
         snorm_dev(P, sm, cases[ic]);
+        __syncthreads();
+    }
+}
+
+// ---- batched contact cases (NORM + TANG alternation), one CTA per case, dynamic queue ----
+__global__ void __launch_bounds__(CB_THREADS, 1)
+k_contac_batch(ConvPlan P, ContactCase *cases, int ncase, int *next_case)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Smem sm = smem_view(P, smem_raw);
+    smem_load_tables(P, sm);
+    volatile int *s_case_p = reinterpret_cast<volatile int *>(sm.red + 127);
+    for (;;) {
+        if (threadIdx.x == 0) *s_case_p = atomicAdd(next_case, 1);
+        __syncthreads();
+        const int ic = *s_case_p;
+        __syncthreads();
+        if (ic >= ncase) break;
+        panprc_dev(P, sm, cases[ic]);
         __syncthreads();
     }
 }

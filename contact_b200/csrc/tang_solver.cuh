@@ -1,0 +1,452 @@
+// tang_solver.cuh -- device-resident tangential problem for shifts (T=1): TangCG, the Newton-Raphson loop on the
+// creepages for prescribed tangential forces, the TANG adhesion/slip active-set loop and the Panagiotopoulos
+// NORM/TANG alternation -- one CTA owns one contact problem for the whole case.
+//
+// Mirrors the reference's tangcg (/root/reference/src/m_solvpt.f90:1841-2442), solvpt (:51-378), stang / stang_rhs
+// (/root/reference/src/m_stang.f90:28-746, 749-951; Coulomb friction L=0, elastic material) and panprc
+// (/root/reference/src/m_scontc.f90:356-553).  Every influence product is the shared-memory FFT convolution; a 2x2
+// tangential product is four single-block products accumulated in place.
+#pragma once
+#include "norm_solver.cuh"
+
+namespace cb200 {
+
+#define CB_MAXNR_LOG 32
+
+struct ContactCase {
+    NormCase nrm;                   // normal problem (hs normal, el, pn = ps + 2n, work, ...)
+    // tangential inputs
+    int tang, force3, maxnr, maxout;
+    double cksi, ceta, fxrel, fyrel, fstat;
+    const double *hst;              // [2][n] tangential right-hand side -dq*(rigid slip), without unknown creepages
+    const double *pv;               // [3][n] tractions of the previous time instance (null = zero)
+    double *ps;                     // [3][n] tractions (in/out), nrm.pn == ps + 2n
+    double *ss;                     // [2][n] shift / slip distance (out)
+    double *twork;                  // 24 n doubles
+    const cd *chatA[3][3];          // transformed cs blocks (null where not needed / no n-t coupling)
+    const cd *chatV[3][3];          // transformed cv blocks (shifts: same as cs)
+    const cd *chatM11, *chatM22;    // transformed preconditioner blocks
+    const double *cf11, *cf22;      // spatial blocks cs(1,1), cs(2,2)
+    double c11, c22, ga;
+    // outputs
+    int ittang, itgs, itout, nr_n;
+    int nr_itcg[CB_MAXNR_LOG];
+    double nr_cksi[CB_MAXNR_LOG], nr_ceta[CB_MAXNR_LOG], nr_fx[CB_MAXNR_LOG], nr_fy[CB_MAXNR_LOG];
+    double fx, fy, sens[2][2];
+    int nadh, nslip;
+};
+
+// u(ik) = sum_jk A(ik,jk) p(jk) over the given direction ranges, masked (AllInt when el given), blocks with a null
+// transform are skipped (no normal-tangential coupling: m_aijpj.f90:358-369); returns the number of products done
+__device__ int conv_multi(const ConvPlan &P, const Smem &sm, const cd *(&chat)[3][3], const double *p, int jk0, int jk1,
+                          double *u, int ik0, int ik1, const int *el, int mask_mode)
+{
+    const int n = P.npot;
+    int np = 0;
+    for (int ik = ik0; ik <= ik1; ik++) {
+        bool ladd = false;
+        for (int jk = jk0; jk <= jk1; jk++) {
+            if (chat[ik][jk] == nullptr) continue;
+            conv_dev(P, sm, p + (size_t) jk * n, chat[ik][jk], u + (size_t) ik * n, el, mask_mode, ladd ? 1 : 0);
+            ladd = true; np++;
+        }
+        if (!ladd) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) if (mask_mode == 0 || el[i] >= 1) u[(size_t) ik * n + i] = 0.0;
+            __syncthreads();
+        }
+    }
+    return np;
+}
+
+__device__ __forceinline__ void count_el(const int *el, int n, double *red, int &nadh, int &nslip)
+{
+    double c[2] = { 0.0, 0.0 };
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { const int e = el[i]; if (e == 1) c[0] += 1.0; else if (e >= 2) c[1] += 1.0; }
+    block_sum<2>(c, red);
+    nadh = (int) c[0]; nslip = (int) c[1];
+}
+
+// m_solvpt.f90:1841-2442 (elastic material).  ws: [2][n] right-hand side; mu = fstat (uniform).
+__device__ void tangcg_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, const double *ws, int maxcg, double eps,
+                           int &itcg_out, double &err_out, int &nprod)
+{
+    const int n = P.npot, tid = threadIdx.x, nt = blockDim.x;
+    int *el = c.nrm.el;
+    double *ps = c.ps, *psn = c.ps + 2 * (size_t) n, *ss = c.ss, *red = sm.red;
+    double *g = c.twork, *nx = g + n, *ny = nx + n, *r = ny + n, *z = r + 2 * n, *v = z + 2 * n, *q = v + 2 * n,
+           *pold = q + 2 * n;
+    const double small = 1e-6, ga = c.ga, c11 = c.c11, c22 = c.c22, mu = c.fstat;
+    const int num_inn = 4;
+    int nadh, nslip;
+    count_el(el, n, red, nadh, nslip);
+    const double facnel = (double) sqrtf(__fdiv_rn((float) n, (float) (nadh + nslip)));      // REAL(4) arithmetic, :1948
+    bool use_fftprec = true, lchanged = false;
+    int itcg = 0, it_inn = 0;
+    double alpha = 0.0, dif = 2.0, difid = 1.0, difinn = 0.0, trsinn = 0.0;
+
+    // g, n, t; ss = A ps + ws on C; r = -ss projected on the tangent in S
+    for (int i = tid; i < n; i += nt) {
+        g[i] = mu * psn[i];
+        const double a = atan2(ps[n + i], ps[i]);
+        nx[i] = cos(a); ny[i] = sin(a);
+        ss[i] = 0.0; ss[n + i] = 0.0;
+        v[i] = 0.0; v[n + i] = 0.0; q[i] = 0.0; q[n + i] = 0.0; z[i] = 0.0; z[n + i] = 0.0; pold[i] = 0.0; pold[n + i] = 0.0;
+    }
+    __syncthreads();
+    nprod += conv_multi(P, sm, c.chatA, ps, 0, 1, ss, 0, 1, el, 1);
+    for (int i = tid; i < n; i += nt) {
+        const int e = el[i];
+        double sx = ss[i], sy = ss[n + i];
+        if (e >= 1) { sx += ws[i]; sy += ws[n + i]; ss[i] = sx; ss[n + i] = sy; }
+        double rx = -sx, ry = -sy;
+        if (e == 2) { const double tx = -ny[i], ty = nx[i], perp = tx * rx + ty * ry; rx = perp * tx; ry = perp * ty; }
+        r[i] = rx; r[n + i] = ry;
+    }
+    __syncthreads();
+
+    while ((lchanged || dif > difid) && itcg < maxcg) {
+        itcg++; it_inn++;
+        if (use_fftprec) {
+            if (nslip > 3 * nadh && P.my > 1) use_fftprec = false;
+            if (itcg >= maxcg / 2) use_fftprec = false;
+            if (!use_fftprec) lchanged = true;
+        }
+        if (use_fftprec) {
+            conv_dev(P, sm, r, c.chatM11, z, el, 1, 0);
+            conv_dev(P, sm, r + n, c.chatM22, z + n, el, 1, 0);
+            nprod += 2;
+        }
+        double d2[2] = { 0.0, 0.0 };
+        for (int i = tid; i < n; i += nt) {                                   // diagonal scaling + tangent projection
+            const int e = el[i];
+            double zx = use_fftprec ? z[i] : r[i], zy = use_fftprec ? z[n + i] : r[n + i];
+            if (e == 2) {
+                const double snrm = -ss[i] * nx[i] - ss[n + i] * ny[i];
+                zx = zx / (c11 + ga * snrm / g[i]); zy = zy / (c22 + ga * snrm / g[i]);
+                const double tx = -ny[i], ty = nx[i], perp = tx * zx + ty * zy;
+                zx = perp * tx; zy = perp * ty;
+            } else { zx = zx / c11; zy = zy / c22; }
+            z[i] = zx; z[n + i] = zy;
+            d2[0] += zx * q[i] + zy * q[n + i];
+            d2[1] += v[i] * q[i] + v[n + i] * q[n + i];
+        }
+        block_sum<2>(d2, red);
+        double beta = 0.0;
+        const bool restart = (itcg <= 1 || lchanged);
+        if (!restart) {
+            const double zq = d2[0], vq = d2[1];
+            if (fabs(zq) < 1e-60 || fabs(vq) < small * fabs(zq)) beta = 0.0; else beta = -zq / vq;
+        }
+        for (int i = tid; i < n; i += nt) {
+            if (restart) { v[i] = z[i]; v[n + i] = z[n + i]; }
+            else { v[i] = beta * v[i] + z[i]; v[n + i] = beta * v[n + i] + z[n + i]; }
+        }
+        __syncthreads();
+
+        nprod += conv_multi(P, sm, c.chatA, v, 0, 1, q, 0, 1, el, 1);          // q = A_tt v on C
+        double d3[3] = { 0.0, 0.0, 0.0 };
+        for (int i = tid; i < n; i += nt) {
+            double qx = q[i], qy = q[n + i];
+            const double vx = v[i], vy = v[n + i];
+            if (el[i] == 2) {
+                const double tx = -ny[i], ty = nx[i], perp = tx * qx + ty * qy;
+                qx = perp * tx; qy = perp * ty;
+                const double snrm = (nx[i] * ss[i] + ny[i] * ss[n + i]) / g[i];
+                qx = qx - snrm * vx; qy = qy - snrm * vy;
+                q[i] = qx; q[n + i] = qy;
+            }
+            d3[0] += r[i] * vx + r[n + i] * vy;
+            d3[1] += vx * qx + vy * qy;
+            d3[2] += vx * vx + vy * vy;
+        }
+        block_sum<3>(d3, red);
+        const double rv = d3[0], vq = d3[1];
+        if (fabs(rv) < 1e-60) alpha = 0.0; else if (fabs(vq) < small * fabs(rv)) alpha = 1.0; else alpha = rv / vq;
+
+        double p2[1] = { 0.0 };
+        for (int i = tid; i < n; i += nt) {                                   // :2170-2185
+            const int e = el[i];
+            double px = ps[i], py = ps[n + i];
+            pold[i] = px; pold[n + i] = py;
+            if (e >= 1) { px += alpha * v[i]; py += alpha * v[n + i]; }
+            if (e == 2) { const double pa = sqrt(px * px + py * py); px = px * g[i] / pa; py = py * g[i] / pa; }
+            ps[i] = px; ps[n + i] = py;
+            p2[0] += px * px + py * py;
+        }
+        dif = alpha * facnel * sqrt(d3[2] / (2.0 * n));
+        difinn += dif;
+        if (itcg <= 5 || itcg % 5 == 1) {
+            block_sum<1>(p2, red);
+            const double ptang = facnel * sqrt(p2[0] / (2.0 * n));
+            difid = eps * fmax(1e-6, ptang);
+            trsinn = (double) 0.01f * ptang;
+        } else __syncthreads();
+
+        if (it_inn >= num_inn || dif <= difid || difinn > trsinn) {            // :2227 check constraints
+            double ch[1] = { 0.0 };
+            for (int i = tid; i < n; i += nt) if (el[i] == 1) {
+                const double px = ps[i], py = ps[n + i], pa = sqrt(px * px + py * py);
+                if (pa > g[i]) { el[i] = 2; ps[i] = px * g[i] / pa; ps[n + i] = py * g[i] / pa; ch[0] += 1.0; }
+            }
+            __syncthreads();
+            nprod += conv_multi(P, sm, c.chatA, ps, 0, 1, ss, 0, 1, el, 1);
+            double dp[1] = { 0.0 };
+            for (int i = tid; i < n; i += nt) {
+                const int e = el[i];
+                if (e >= 1) { ss[i] += ws[i]; ss[n + i] += ws[n + i]; }
+                if (e == 2 && ss[i] * ps[i] + ss[n + i] * ps[n + i] > 0.0) { el[i] = 1; ch[0] += 1.0; }
+                const double dx = pold[i] - ps[i], dy = pold[n + i] - ps[n + i];
+                pold[i] = dx; pold[n + i] = dy;
+                dp[0] += dx * dx + dy * dy;
+            }
+            double both[2] = { ch[0], dp[0] };
+            block_sum<2>(both, red);
+            lchanged = both[0] > 0.0;
+            dif = facnel * sqrt(both[1] / (2.0 * n));
+            it_inn = 0; difinn = 0.0;
+            if (lchanged) count_el(el, n, red, nadh, nslip);
+        }
+        if ((lchanged || dif > difid) && itcg < maxcg) {                       // :2330-2380
+            if (it_inn <= 0) {
+                for (int i = tid; i < n; i += nt) {
+                    const double a = atan2(ps[n + i], ps[i]);
+                    const double cx = cos(a), sy = sin(a);
+                    nx[i] = cx; ny[i] = sy;
+                    double rx = -ss[i], ry = -ss[n + i];
+                    if (el[i] == 2) { const double tx = -sy, ty = cx, perp = tx * rx + ty * ry; rx = perp * tx; ry = perp * ty; }
+                    r[i] = rx; r[n + i] = ry;
+                }
+            } else {
+                for (int i = tid; i < n; i += nt) if (el[i] >= 1) { r[i] -= alpha * q[i]; r[n + i] -= alpha * q[n + i]; }
+            }
+            __syncthreads();
+        }
+    }
+    itcg_out = itcg; err_out = dif;
+}
+
+// |row sum| of a spatial coefficient block at the central element over the columns AijPj visits (see centre_rowsum_dev)
+__device__ double centre_rowsum_blk(const ConvPlan &P, const double *blk, int cmx, int cmy, const int *el, double *red)
+{
+    const int mx = P.mx, my = P.my;
+    const int ixm = max(1, mx / 2), iym = max(1, my / 2);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double s[1] = { 0.0 };
+    for (int jy = 1 + wid; jy <= my; jy += nw) {
+        int first = mx + 1, last = 0;
+        for (int jx = 1 + lane; jx <= mx; jx += 32)
+            if (el[(jy - 1) * mx + jx - 1] >= 1) { first = min(first, jx); last = max(last, jx); }
+        for (int o = 16; o > 0; o >>= 1) {
+            first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+            last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+        }
+        if (last == 0) first = mx;
+        const int j0 = max(1, first - 1), j1 = min(mx, last + 1);
+        const double *row = blk + (size_t) (iym - jy + cmy) * (2 * cmx) + cmx;
+        for (int jx = j0 + lane; jx <= j1; jx += 32) s[0] += row[ixm - jx];
+    }
+    block_sum<1>(s, red);
+    return s[0];
+}
+
+// one tangential solve + relative forces (+ log of the Newton-Raphson process)
+__device__ void solve_once_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, const double *wstot, double fntrue,
+                               int &it, double &err, double &fx, double &fy, int &nprod)
+{
+    const int n = P.npot;
+    tangcg_dev(P, sm, c, wstot, c.nrm.maxgs, c.nrm.eps, it, err, nprod);
+    double s[2] = { 0.0, 0.0 };
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { s[0] += c.ps[i]; s[1] += c.ps[n + i]; }
+    block_sum<2>(s, sm.red);
+    fx = c.nrm.dxdy * s[0] / (c.fstat * fntrue);
+    fy = c.nrm.dxdy * s[1] / (c.fstat * fntrue);
+    if (threadIdx.x == 0 && c.nr_n < CB_MAXNR_LOG) {
+        const int k = c.nr_n;
+        c.nr_itcg[k] = it; c.nr_cksi[k] = c.cksi; c.nr_ceta[k] = c.ceta; c.nr_fx[k] = fx; c.nr_fy[k] = fy;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) c.nr_n++;
+    __syncthreads();
+}
+
+// solvpt (m_solvpt.f90:51-378): Newton-Raphson on (cksi[, ceta]) for prescribed tangential forces; shifts: dq = 1
+__device__ void solvpt_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, const double *wsfix, double *wstot,
+                           double fntrue, int &itgs, double &err, int &nprod)
+{
+    const int n = P.npot, tid = threadIdx.x, nt = blockDim.x;
+    const int *el = c.nrm.el;
+    const double dq = 1.0, dxdy = c.nrm.dxdy, muscal = c.fstat, eps = c.nrm.eps;
+    double cksi = c.cksi, ceta = c.ceta;                     // block-uniform copies; c.cksi/c.ceta updated by thread 0
+    int it, nadh, nslip;
+    double fxkp1, fykp1;
+    itgs = 0;
+    for (int i = tid; i < n; i += nt) {
+        double wx = wsfix[i], wy = wsfix[n + i];
+        if (el[i] >= 1) { if (c.force3 >= 1) wx += cksi * dq; if (c.force3 >= 2) wy += ceta * dq; }
+        wstot[i] = wx; wstot[n + i] = wy;
+    }
+    __syncthreads();
+    solve_once_dev(P, sm, c, wstot, fntrue, it, err, fxkp1, fykp1, nprod);
+    itgs += it;
+    count_el(el, n, sm.red, nadh, nslip);
+    if (c.force3 >= 1) {
+        int itnr = 0;
+        double df = fabs(c.fxrel - fxkp1);
+        if (c.force3 >= 2) df += fabs(c.fyrel - fykp1);
+        double s00 = c.sens[0][0], s01 = c.sens[0][1], s10 = c.sens[1][0], s11 = c.sens[1][1];
+        while (df > eps && itnr < c.maxnr) {
+            itnr++;
+            const double dfx = c.fxrel - fxkp1, dfy = c.fyrel - fykp1;
+            double dcksi, dceta;
+            if (c.force3 == 1) {
+                dceta = 0.0;
+                dcksi = (fabs(s00) > (double) 1e-6f) ? dfx / s00 : (double) 0.00003f;
+            } else {
+                const double det = s00 * s11 - s10 * s01;
+                if (det > eps) { dcksi = (s11 * dfx - s10 * dfy) / det; dceta = (-s01 * dfx + s00 * dfy) / det; }
+                else { dcksi = 0.000003; dceta = 0.000003; }
+            }
+            for (int ifxy = 1; ifxy <= c.force3; ifxy++) {
+                const double fxk = fxkp1, fyk = fykp1;
+                if (ifxy == 1) { cksi += dcksi; for (int i = tid; i < n; i += nt) if (el[i] >= 1) wstot[i] += dcksi * dq; }
+                else { ceta += dceta; for (int i = tid; i < n; i += nt) if (el[i] >= 1) wstot[n + i] += dceta * dq; }
+                __syncthreads();
+                if (tid == 0) { c.cksi = cksi; c.ceta = ceta; }
+                __syncthreads();
+                solve_once_dev(P, sm, c, wstot, fntrue, it, err, fxkp1, fykp1, nprod);
+                itgs += it;
+                count_el(el, n, sm.red, nadh, nslip);
+                const double dfxk = fxkp1 - fxk, dfyk = fykp1 - fyk, ncon = (double) (nadh + nslip);
+                if (ifxy == 1) {
+                    if (nadh > 0) {
+                        const double dpx = dfxk * muscal * fntrue / (ncon * dxdy), dpy = dfyk * muscal * fntrue / (ncon * dxdy);
+                        if (s00 == 0.0 || fabs(dpx) > 10.0 * err) s00 = dfxk / dcksi;
+                        if (fabs(dpy) > 10.0 * err) s10 = dfyk / dcksi;
+                    } else if (fabs(s00) < (double) 1e-6f) s00 = fxkp1 / cksi;
+                } else {
+                    if (nadh > 0) {
+                        const double dpx = dfxk * muscal * fntrue / (ncon * dxdy), dpy = dfyk * muscal * fntrue / (ncon * dxdy);
+                        if (fabs(dpx) > 10.0 * err) s01 = dfxk / dceta;
+                        if (s11 == 0.0 || fabs(dpy) > 10.0 * err) s11 = dfyk / dceta;
+                    } else if (fabs(s11) < (double) 1e-6f) s11 = fykp1 / ceta;
+                }
+                df = fabs(c.fxrel - fxkp1);
+                if (c.force3 >= 2) df += fabs(c.fyrel - fykp1);
+            }
+        }
+        err = err + 2.0 * df * muscal * fntrue / ((nadh + 2) * dxdy);          // the reference's constant Slip=2, :361
+        if (tid == 0) { c.sens[0][0] = s00; c.sens[0][1] = s01; c.sens[1][0] = s10; c.sens[1][1] = s11; }
+    }
+    if (tid == 0) { c.fx = fxkp1; c.fy = fykp1; }
+    __syncthreads();
+}
+
+// stang (m_stang.f90:28-746) for shifts with uniform Coulomb friction; returns ittang (-1: MaxIn reached)
+__device__ int stang_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, double fntrue, int &itgs_tot, int &nprod)
+{
+    const int n = P.npot, tid = threadIdx.x, nt = blockDim.x;
+    int *el = c.nrm.el;
+    double *ps = c.ps, *ss = c.ss, *red = sm.red;
+    double *wsfix = c.twork + 13 * (size_t) n, *wstot = wsfix + 2 * n, *u1 = wstot + 2 * n, *u2 = u1 + 2 * n;
+    const double mu = c.fstat;
+    // stang_rhs (:749-951), shifts: wsfix = -hs_t + A_tn pn - A'_tn p'n - A'_tt p'_t on C (facdt = 1)
+    nprod += conv_multi(P, sm, c.chatA, ps, 2, 2, u1, 0, 1, el, 1);
+    if (c.pv) {
+        nprod += conv_multi(P, sm, c.chatV, c.pv, 2, 2, u2, 0, 1, el, 1);
+        for (int i = tid; i < n; i += nt) if (el[i] >= 1) { u1[i] -= u2[i]; u1[n + i] -= u2[n + i]; }
+        __syncthreads();
+        nprod += conv_multi(P, sm, c.chatV, c.pv, 0, 1, u2, 0, 1, el, 1);
+        for (int i = tid; i < n; i += nt) if (el[i] >= 1) { u1[i] -= u2[i]; u1[n + i] -= u2[n + i]; }
+        __syncthreads();
+    }
+    for (int i = tid; i < n; i += nt) {
+        const bool in = el[i] >= 1;
+        wsfix[i] = in ? -c.hst[i] + u1[i] : 0.0;
+        wsfix[n + i] = in ? -c.hst[n + i] + u1[n + i] : 0.0;
+    }
+    __syncthreads();
+
+    int ittang = 0, it;
+    bool zready = false;
+    double errpt = 0.0;
+    itgs_tot = 0;
+    while (!zready && ittang < c.nrm.maxin) {
+        ittang++;
+        zready = true;
+        solvpt_dev(P, sm, c, wsfix, wstot, fntrue, it, errpt, nprod);
+        itgs_tot += it;
+        double k[1] = { 0.0 };
+        const double tol = sqrt(2.0) * errpt;
+        for (int i = tid; i < n; i += nt) if (el[i] == 1) {                    // :434-453 adhesion -> slip
+            const double px = ps[i], py = ps[n + i], pn = ps[2 * (size_t) n + i], pabs = sqrt(px * px + py * py);
+            if (pabs >= mu * pn + tol) { el[i] = 2; ps[i] = px * mu * pn / pabs; ps[n + i] = py * mu * pn / pabs; k[0] += 1.0; }
+        }
+        block_sum<1>(k, red);
+        if (k[0] > 0.0) zready = false;
+        if (zready) {                                                          // :463-510 slip -> adhesion
+            const double tol1 = errpt * 2.0 * fabs(centre_rowsum_blk(P, c.cf11, c.nrm.cmx, c.nrm.cmy, el, red) * c.nrm.ga_inv);
+            const double tol2 = errpt * 2.0 * fabs(centre_rowsum_blk(P, c.cf22, c.nrm.cmx, c.nrm.cmy, el, red) * c.nrm.ga_inv);
+            double ka[1] = { 0.0 };
+            for (int i = tid; i < n; i += nt) if (el[i] == 2) {
+                const double ww = ss[i] * ps[i] + ss[n + i] * ps[n + i];
+                const double tl = tol1 * fabs(ps[i]) + tol2 * fabs(ps[n + i]) + errpt * (fabs(ss[i]) + fabs(ss[n + i]));
+                if (ww > tl) { el[i] = 1; ka[0] += 1.0; }
+            }
+            block_sum<1>(ka, red);
+            if (ka[0] > 0.0) zready = false;
+        }
+    }
+    if (!zready) ittang = -1;
+    return ittang;
+}
+
+// contac's computing part: panprc (m_scontc.f90:356-553) = NORM / TANG alternation until the tractions settle
+__device__ void panprc_dev(const ConvPlan &P, const Smem &sm, ContactCase &c)
+{
+    const int n = P.npot, tid = threadIdx.x, nt = blockDim.x;
+    double *ps = c.ps, *po1 = c.twork + 21 * (size_t) n;
+    int *el = c.nrm.el;
+    int itnorm = 0, ittang = 0, itout = 0, itcg = 0, itgs = 0, nprod = 0;
+    double dif = 200.0, difid = 1.0;
+    if (tid == 0) c.nr_n = 0;
+    for (int i = tid; i < 3 * n; i += nt) po1[i] = ps[i];
+    __syncthreads();
+    while (dif > difid && itout < c.maxout && itnorm >= 0 && ittang >= 0) {
+        itout++;
+        snorm_dev(P, sm, c.nrm);
+        __syncthreads();
+        itcg += c.nrm.itcg; nprod += c.nrm.nprod;
+        if (c.nrm.itnorm >= 0) itnorm += c.nrm.itnorm; else itnorm = -1;
+        const int ncon = c.nrm.ncon;
+        for (int i = tid; i < n; i += nt) if (el[i] < 1) { ps[i] = 0.0; ps[n + i] = 0.0; }
+        __syncthreads();
+        if (c.tang == 0 || ncon <= 0) dif = 0.0;
+        else {
+            int it_gs;
+            const int it = stang_dev(P, sm, c, c.nrm.fntrue, it_gs, nprod);
+            itgs += it_gs;
+            if (it >= 0) ittang += it; else ittang = -1;
+            double s[3] = { 0.0, 0.0, 0.0 };
+            for (int i = tid; i < n; i += nt) {
+                const bool in = el[i] >= 1;
+                for (int k = 0; k < 3; k++) {
+                    const double pk = ps[(size_t) k * n + i], d = po1[(size_t) k * n + i] - pk;
+                    if (in) { s[0] += d * d; s[1] += pk * pk; s[2] += 1.0; }
+                    po1[(size_t) k * n + i] = pk;
+                }
+            }
+            block_sum<3>(s, sm.red);
+            dif = sqrt(s[0] / fmax(1.0, s[2]));
+            difid = 5.0 * c.nrm.eps * sqrt(s[1] / fmax(1.0, s[2]));
+        }
+    }
+    int nadh, nslip;
+    count_el(el, n, sm.red, nadh, nslip);
+    if (tid == 0) {
+        c.nrm.itnorm = itnorm; c.nrm.itcg = itcg; c.nrm.nprod = nprod;
+        c.ittang = ittang; c.itgs = itgs; c.itout = itout; c.nadh = nadh; c.nslip = nslip;
+    }
+    __syncthreads();
+}
+
+}  // namespace cb200

@@ -59,6 +59,7 @@ PROTOTYPES = {
     "cntc_finalize": (None, [ip]),
     "cntc_finalizelast": (None, []),
     "cntc_calculate_batch": (None, [ip, ip, ip, ip]),
+    "cb200_get_iterations": (I, [I, I, ip, I, ip]),
     "cb200_last_error": (C.c_char_p, []),
     "cb200_num_launches": (L, []),
     "cb200_num_sms": (I, []),

@@ -152,6 +152,35 @@ void   co_set_norm_rhs(int ibase, int iplan, int npot, const double *x, const do
 void   co_eldiv0(int ic_norm, int mx, int my, double dx, double dy, int ibase, const double *prmudf,
                  const co_mater *m, double fntrue, double *pen, const double *hs_n, co_eldiv *igs);
 
+/* ---- tangential problem and the case driver (co_tang.c) ---- */
+#define CO_MAXNR 64
+typedef struct {
+    /* inputs */
+    int    mx, my;
+    double xl, yl, dx, dy;
+    double gg[2], poiss[2];
+    int    ibase, nn;
+    const double *prmudf;
+    int    tang, norm, force3;          /* T, N, F digits */
+    double pen, fn, cksi, ceta, cphi, fxrel, fyrel, fstat, fkin;
+    int    maxgs, maxin, maxnr, maxout;
+    double eps;
+    int    fullbox;
+    /* outputs */
+    int    *el;                         /* [npot] */
+    double *ps;                         /* [3][npot] */
+    double *ss;                         /* [3][npot] shift/slip (may be NULL) */
+    double pen_out, fn_out, fx_out, fy_out;
+    int    itnorm, ittang, itcg_norm, itgs_tang;
+    int    nr_n, nr_itcg[CO_MAXNR];     /* one entry per tangential solver call of the Newton-Raphson process */
+    double nr_cksi[CO_MAXNR], nr_ceta[CO_MAXNR], nr_fx[CO_MAXNR], nr_fy[CO_MAXNR];
+    long   n_prod;
+} co_case;
+
+void   co_tangcg(co_ctx *cx, int npot, int maxcg, double eps, const double *ws, co_inflcf *cs, co_inflcf *ms,
+                 const double *mu, co_eldiv *igs, double *ps, double *ss, int *itcg, double *err);
+int    co_contac(co_case *c);
+
 /* ---- subsurface stresses (co_subsurf.c) ---- */
 void   co_stres1_pcwcns(double dx, double dy, double gg, double v[3][3][4], double vnu[3][3][4], const double xw[3],
                         const double xp[2]);

@@ -248,3 +248,41 @@ def subsurf_block(mx, my, dx, dy, gg, poiss, el, ps, zs, use_fft=True):
     L.co_subsurf_block_fft(ctx.p, C.c_int(mx), C.c_int(my), C.c_double(dx), C.c_double(dy), g2, p2, _i(el), _d(ps),
                            C.c_int(len(zs)), _d(zs), C.c_int(int(use_fft)), _d(tbl))
     return tbl
+
+
+class Case(C.Structure):
+    _fields_ = [("mx", C.c_int), ("my", C.c_int), ("xl", C.c_double), ("yl", C.c_double), ("dx", C.c_double), ("dy", C.c_double),
+                ("gg", C.c_double * 2), ("poiss", C.c_double * 2), ("ibase", C.c_int), ("nn", C.c_int), ("prmudf", c_dbl_p),
+                ("tang", C.c_int), ("norm", C.c_int), ("force3", C.c_int),
+                ("pen", C.c_double), ("fn", C.c_double), ("cksi", C.c_double), ("ceta", C.c_double), ("cphi", C.c_double),
+                ("fxrel", C.c_double), ("fyrel", C.c_double), ("fstat", C.c_double), ("fkin", C.c_double),
+                ("maxgs", C.c_int), ("maxin", C.c_int), ("maxnr", C.c_int), ("maxout", C.c_int), ("eps", C.c_double),
+                ("fullbox", C.c_int), ("el", c_int_p), ("ps", c_dbl_p), ("ss", c_dbl_p),
+                ("pen_out", C.c_double), ("fn_out", C.c_double), ("fx_out", C.c_double), ("fy_out", C.c_double),
+                ("itnorm", C.c_int), ("ittang", C.c_int), ("itcg_norm", C.c_int), ("itgs_tang", C.c_int),
+                ("nr_n", C.c_int), ("nr_itcg", C.c_int * 64), ("nr_cksi", C.c_double * 64), ("nr_ceta", C.c_double * 64),
+                ("nr_fx", C.c_double * 64), ("nr_fy", C.c_double * 64), ("n_prod", C.c_long)]
+
+
+def contac(g, gg, poiss, tang=0, norm=0, force3=0, pen=0.0, fn=0.0, cksi=0.0, ceta=0.0, cphi=0.0, fxrel=0.0, fyrel=0.0,
+           fstat=0.3, fkin=0.3, maxgs=999, maxin=20, maxnr=25, maxout=1, eps=1e-5, fullbox=False, nn=0):
+    """One module-3 case (T = 0/1) through the oracle's contac/panprc. g: dict mx,my,xl,yl,dx,dy,ibase,prmudf."""
+    npot = g["mx"] * g["my"]
+    prm = np.ascontiguousarray(g["prmudf"], dtype=np.float64)
+    el = np.zeros(npot, dtype=np.int32); ps = np.zeros((3, npot)); ss = np.zeros((3, npot))
+    c = Case()
+    c.mx, c.my, c.xl, c.yl, c.dx, c.dy = g["mx"], g["my"], g["xl"], g["yl"], g["dx"], g["dy"]
+    c.gg[0], c.gg[1], c.poiss[0], c.poiss[1] = gg[0], gg[1], poiss[0], poiss[1]
+    c.ibase, c.nn, c.prmudf = g["ibase"], nn, _d(prm)
+    c.tang, c.norm, c.force3 = tang, norm, force3
+    c.pen, c.fn, c.cksi, c.ceta, c.cphi, c.fxrel, c.fyrel, c.fstat, c.fkin = pen, fn, cksi, ceta, cphi, fxrel, fyrel, fstat, fkin
+    c.maxgs, c.maxin, c.maxnr, c.maxout, c.eps, c.fullbox = maxgs, maxin, maxnr, maxout, eps, int(fullbox)
+    c.el, c.ps, c.ss = _i(el), _d(ps), _d(ss)
+    L = lib()
+    L.co_contac.restype = C.c_int
+    ierr = L.co_contac(C.byref(c))
+    n = c.nr_n
+    return dict(ierror=ierr, el=el, ps=ps, ss=ss, pen=c.pen_out, fn=c.fn_out, fx=c.fx_out, fy=c.fy_out, cksi=c.cksi, ceta=c.ceta,
+                itnorm=c.itnorm, ittang=c.ittang, itcg_norm=c.itcg_norm, itgs_tang=c.itgs_tang,
+                nr_itcg=list(c.nr_itcg[:n]), nr_cksi=list(c.nr_cksi[:n]), nr_ceta=list(c.nr_ceta[:n]), nr_fx=list(c.nr_fx[:n]),
+                nr_fy=list(c.nr_fy[:n]), n_prod=c.n_prod)

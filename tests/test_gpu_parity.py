@@ -279,3 +279,74 @@ def test_subs_api_after_contact_solve(cb, O):
     # Hertz: max von Mises stress below the surface on the axis, sigma_zz(0) = -pmax
     assert abs(o2[0, 20] + pn.max()) < 2e-2 * pn.max()
     cb.cntc_finalize(ire)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# tangential problem (shift, TangCG + Newton-Raphson on the creepages)
+# ------------------------------------------------------------------------------------------------------------
+def _setup_cattaneo2(cb, ire, icp=1, fx=-0.8750, fy=0.0, force=2):
+    c = cases.CATTANEO2
+    cb.cntc_initialize(ire, 3)
+    cb.cntc_setflags(ire, icp, [cb.CNTC["ic_tang"], cb.CNTC["ic_force"], cb.CNTC["ic_iestim"]], [1, force, 0])
+    cb.cntc_setsolverflags(ire, icp, 0, [c["maxgs"], c["maxin"], 30, 1], [c["eps"]])
+    cb.cntc_setmaterialparameters(ire, icp, 0, [c["poiss"][0], c["poiss"][1], c["gg"][0], c["gg"][1]])
+    cb.cntc_setfrictionmethod(ire, icp, 0, [0.4, 0.4])
+    cb.cntc_setpotcontact(ire, icp, 1, [c["mx"], c["my"], c["xl"], c["yl"], c["dx"], c["dy"]])
+    cb.cntc_setundeformeddistc(ire, icp, 1, c["prmudf"])
+    cb.cntc_setnormalforce(ire, icp, c["fn"])
+    if force == 2:
+        cb.cntc_settangentialforces(ire, icp, fx, fy)
+    return c
+
+
+def test_cattaneo_shift_full_case(cb, O):
+    """examples/cattaneo.inp case 2 (T=1, N=1, F=2): examples/cattaneo.ref_out:82-102 -- 7 Newton-Raphson evaluations,
+    final A,S = 45 132, ItCG = 59, Cksi = 8.155E-03, Fx = -0.8750."""
+    ire, icp = 41, 1
+    c = _setup_cattaneo2(cb, ire)
+    ierr = cb.cntc_calculate(ire, icp)
+    assert ierr == 0, (ierr, cb.lib.last_error())
+    ref = O.contac(c, c["gg"], c["poiss"], tang=1, norm=1, force3=2, fn=c["fn"], fxrel=-0.8750, fyrel=0.0, fstat=0.4,
+                   fkin=0.4, maxgs=100, maxin=100, maxnr=30, maxout=1, eps=1e-4)
+    assert ref["itgs_tang"] == 59 and ref["nr_itcg"] == [7, 7, 6, 10, 3, 8, 1, 7, 1, 4, 1, 3, 1]      # golden, per solver call
+    its = cb.lowlevel.get_iterations(ire, icp)
+    assert its["nr_itcg"] == ref["nr_itcg"] and its["itgs"] == 59 and its["itcg"] == 6      # same iteration history as the golden file
+    el = cb.cntc_getelementdivision(ire, icp).ravel()
+    assert int((el == 1).sum()) == 45 and int((el == 2).sum()) == 132
+    assert np.array_equal(el, ref["el"])                               # adhesion / slip flags bit-exact
+    pn, px, py = cb.cntc_gettractions(ire, icp)
+    assert _rel(px.ravel(), ref["ps"][0]) < 1e-7 and _rel(pn.ravel(), ref["ps"][2]) < 1e-9
+    assert np.abs(py.ravel() - ref["ps"][1]).max() < 1e-7 * np.abs(ref["ps"][0]).max()
+    vx, vy, phi = cb.cntc_getcreepages(ire, icp)
+    assert "%.3E" % vx == "8.155E-03" and abs(vx - ref["cksi"]) < 1e-8 * abs(ref["cksi"])
+    fn, tx, ty, mz = cb.cntc_getcontactforces(ire, icp)
+    assert abs(tx / (0.4 * fn) + 0.8750) < 1e-4                         # prescribed Fx reached within eps
+    sx, sy = cb.cntc_getmicroslip(ire, icp)
+    # Cattaneo: adhesion area is a disk of half the contact radius (examples/cattaneo.inp:13-15)
+    X, Y = cases.grid_xy(c["mx"], c["my"], c["xl"], c["yl"], c["dx"], c["dy"])
+    assert np.hypot(X, Y)[el == 1].max() < 0.5 + 0.1 and np.hypot(X, Y)[el == 2].min() > 0.5 - 0.1
+    assert np.abs(sx.ravel()[el == 1]).max() < 1e-5 * np.abs(sx).max() + 1e-12
+    cb.cntc_finalize(ire)
+
+
+def test_shift_with_prescribed_creepage_batch(cb, O):
+    """T=1, F=0: prescribed shifts (with spin), several result elements solved in one batched launch."""
+    c = cases.CATTANEO2
+    shifts = [(4e-3, 0.0, 0.0), (2e-3, -3e-3, 0.0), (1e-3, 1e-3, 4e-3), (0.0, 0.0, 6e-3)]
+    ires = list(range(51, 51 + len(shifts)))
+    for ire, (cx, cy, ph) in zip(ires, shifts):
+        _setup_cattaneo2(cb, ire, force=0)
+        cb.cntc_setcreepages(ire, 1, cx, cy, ph)
+    ierr = cb.cntc_calculate_batch(ires, 1)
+    assert (ierr == 0).all(), (ierr, cb.lib.last_error())
+    for ire, (cx, cy, ph) in zip(ires, shifts):
+        ref = O.contac(c, c["gg"], c["poiss"], tang=1, norm=1, force3=0, fn=c["fn"], cksi=cx, ceta=cy, cphi=ph, fstat=0.4,
+                       fkin=0.4, maxgs=100, maxin=100, maxnr=30, maxout=1, eps=1e-4)
+        el = cb.cntc_getelementdivision(ire, 1).ravel()
+        pn, px, py = cb.cntc_gettractions(ire, 1)
+        assert np.array_equal(el, ref["el"]), (cx, cy, ph)
+        s = np.abs(ref["ps"][:2]).max()
+        assert np.abs(px.ravel() - ref["ps"][0]).max() < 1e-6 * s and np.abs(py.ravel() - ref["ps"][1]).max() < 1e-6 * s
+        fn, tx, ty, mz = cb.cntc_getcontactforces(ire, 1)
+        assert abs(tx / (0.4 * fn) - ref["fx"]) < 1e-7 and abs(ty / (0.4 * fn) - ref["fy"]) < 1e-7
+        cb.cntc_finalize(ire)

@@ -89,3 +89,34 @@ def test_reference_test_fft_stencil():
     O.vecaijpj(O.Ctx(), igs, -9, u, 1, p, 1, cs)
     assert np.allclose(u[0].reshape(2, 3), [[0.0, 2.0, -1.0], [0.0, 1.0, 0.0]], atol=1e-14)
     O.inflcf_free(cs, cv, csv, ms)
+
+
+def test_cattaneo_case2_full_shift_problem():
+    """examples/cattaneo.ref_out:82-102: TANG with Newton-Raphson on (cksi, ceta); every printed NR step is pinned:
+    ItCG 7, 13, 13, 9, 8, 5, 4 (= 7 | 7+6 | 10+3 | 8+1 | 7+1 | 4+1 | 3+1 per solver call), Cksi/Fxk/Ceta/Fyk to the
+    printed digits, final A,S = 45 132, ItCG = 59."""
+    c = cases.CATTANEO2
+    r = O.contac(c, c["gg"], c["poiss"], tang=1, norm=1, force3=2, fn=c["fn"], fxrel=-0.8750, fyrel=0.0, fstat=0.4,
+                 fkin=0.4, maxgs=100, maxin=100, maxnr=30, maxout=1, eps=1e-4)
+    assert r["ierror"] == 0 and r["itcg_norm"] == 6 and r["itgs_tang"] == 59
+    assert r["nr_itcg"] == [7, 7, 6, 10, 3, 8, 1, 7, 1, 4, 1, 3, 1]
+    # (Cksi, Fxk) after the x-step and (Ceta, Fyk) after the y-step of each NR iteration, as printed
+    gold_x = [("1.000E-06", "-1.356E-04"), ("4.000E-06", "-5.424E-04"), ("6.453E-03", "-0.7410"), ("7.620E-03", "-0.8367"),
+              ("8.087E-03", "-0.8704"), ("8.150E-03", "-0.8747"), ("8.155E-03", "-0.8750")]
+    gold_y = [None, ("3.000E-06", "-4.068E-04"), None, ("4.460E-08", "-4.188E-06"), ("8.681E-09", "-2.461E-06"),
+              ("-1.243E-08", "6.659E-07"), ("-6.716E-09", "9.615E-07")]
+
+    def fmt(v, like):
+        return ("%.3E" % v) if "E" in like else ("%.4f" % v)
+    calls_x = [0, 1, 3, 5, 7, 9, 11]
+    for k, (ck, fx) in zip(calls_x, gold_x):
+        assert fmt(r["nr_cksi"][k], ck) == ck and fmt(r["nr_fx"][k], fx) == fx
+    for k, g in zip([None, 2, None, 6, 8, 10, 12], gold_y):
+        if g is not None:
+            assert fmt(r["nr_ceta"][k], g[0]) == g[0] and fmt(r["nr_fy"][k], g[1]) == g[1]
+    el = r["el"]
+    assert int((el == 1).sum()) == 45 and int((el == 2).sum()) == 132
+    pics = json.load(open(os.path.join(HERE, "golden", "cattaneo_pictures.json")))["pictures"]
+    gold = np.array([[{"*": 1, "S": 2, "|": 1}.get(ch, 0) for ch in row] for row in pics[1]], dtype=np.int32)
+    assert np.array_equal((gold.ravel() > 0), el > 0)
+    assert np.array_equal(gold.ravel() == 2, el == 2)
