@@ -165,31 +165,46 @@ void co_tangcg(co_ctx *cx, int npot, int maxcg, double eps, const double *ws, co
 #undef PROJ_T
 }
 
-/* m_stang.f90:749-951 for shifts (T=1): facdt = 1, ii2j = 0, previous tractions pv with cv = cs */
-static void tang_rhs(co_ctx *cx, int npot, const co_eldiv *igs, const double *hs, const double *ps, const double *pv,
-                     co_inflcf *cs, co_inflcf *cv, double *wsfix)
+/* m_stang.f90:749-951: shifts (T=1: facdt = 1, previous tractions pv with cv = cs) and steady rolling (T=3: uvn from the
+ * current pressures with the shifted coefficients cv, uvt left to the solver); no leading-edge correction (ii2j = 0) */
+static void tang_rhs(co_ctx *cx, int npot, int is_ssrol, const double *facdt, const co_eldiv *igs, const double *hs,
+                     const double *ps, const double *pv, co_inflcf *cs, co_inflcf *cv, double *wsfix)
 {
     double *usn = (double *) calloc(3L * npot, sizeof(double)), *uvn = (double *) calloc(3L * npot, sizeof(double));
     double *uvt = (double *) calloc(3L * npot, sizeof(double));
     co_vecaijpj(cx, igs, CO_ALLINT, usn, CO_TANG, ps, igs, CO_Z, cs);
-    co_vecaijpj(cx, igs, CO_ALLINT, uvn, CO_TANG, pv, igs, CO_Z, cv);
-    co_vecaijpj(cx, igs, CO_ALLINT, uvt, CO_TANG, pv, igs, CO_TANG, cv);
+    if (!is_ssrol) {
+        co_vecaijpj(cx, igs, CO_ALLINT, uvn, CO_TANG, pv, igs, CO_Z, cv);
+        co_vecaijpj(cx, igs, CO_ALLINT, uvt, CO_TANG, pv, igs, CO_TANG, cv);
+    } else
+        co_vecaijpj(cx, igs, CO_ALLINT, uvn, CO_TANG, ps, igs, CO_Z, cv);
     for (int k = 0; k < 2; k++)
         for (int i = 0; i < npot; i++)
             if (igs->el[i] >= CO_ADHES) {
                 const long o = (long) k * npot + i;
-                const double wsrig = -1.0 * hs[o];
-                wsfix[o] = wsrig + usn[o] - uvn[o] - uvt[o];
+                const double wsrig = -facdt[i] * hs[o];
+                if (!is_ssrol) wsfix[o] = wsrig + usn[o] - uvn[o] - uvt[o];
+                else wsfix[o] = wsrig + usn[o] - uvn[o];
             }
     free(usn); free(uvn); free(uvt);
 }
 
+/* solver selection and relaxation parameters of stang (m_stang.f90:144-223) */
+typedef struct { int solver; double omegah, omegas, dq; const double *facdt; int info; } tang_opts;
+enum { SOLV_TANGCG = 0, SOLV_STDYGS = 1 };
+
 /* one call of the tangential solver + relative forces */
-static void solve_once(co_ctx *cx, co_case *c, int npot, co_inflcf *cs, co_inflcf *ms, const double *wstot, const double *mus,
-                       co_eldiv *igs, double *ps, double *ss, double dxdy, double muscal, double fntrue, int *it, double *err,
-                       double *fx, double *fy)
+static void solve_once(co_ctx *cx, co_case *c, tang_opts *o, int npot, co_inflcf *cs, co_inflcf *ms, const double *wstot,
+                       const double *mus, co_eldiv *igs, double *ps, double *ss, double dxdy, double muscal, double fntrue,
+                       int *it, double *err, double *fx, double *fy)
 {
-    co_tangcg(cx, npot, c->maxgs, c->eps, wstot, cs, ms, mus, igs, ps, ss, it, err);
+    o->info = 0;
+    if (o->solver == SOLV_TANGCG) co_tangcg(cx, npot, c->maxgs, c->eps, wstot, cs, ms, mus, igs, ps, ss, it, err);
+    else {
+        int k = 0;
+        for (int i = 0; i < npot; i++) if (igs->el[i] >= CO_ADHES) k++;
+        co_stdygs(cx, igs->mx, igs->my, wstot, cs, mus, igs, ps, ss, k, c->eps, c->maxgs, o->omegah, o->omegas, &o->info, it, err);
+    }
     double sx = 0.0, sy = 0.0;
     for (int i = 0; i < npot; i++) sx = sx + ps[i];
     for (int i = 0; i < npot; i++) sy = sy + ps[npot + i];
@@ -200,27 +215,27 @@ static void solve_once(co_ctx *cx, co_case *c, int npot, co_inflcf *cs, co_inflc
 }
 
 /* m_solvpt.f90:51-378 */
-static void solvpt(co_ctx *cx, co_case *c, int npot, co_inflcf *cs, co_inflcf *ms, const double *wsfix, const double *mus,
+static void solvpt(co_ctx *cx, co_case *c, tang_opts *o, int npot, co_inflcf *cs, co_inflcf *ms, const double *wsfix, const double *mus,
                    co_eldiv *igs, double *ps, double *ss, double dxdy, double muscal, double fntrue, double sens[2][2],
                    int *itgs, double *err)
 {
     double *wstot = (double *) calloc(3L * npot, sizeof(double));
     int it, nadh, nslip, nplast, nexter, itnr;
     double fxkp1, fykp1, fxk, fyk, df, dfx, dfy, dcksi = 0.0, dceta = 0.0, det, dfxk, dfyk, dpxavg, dpyavg;
-    const double dq = 1.0;
+    const double dq = o->dq, *facdt = o->facdt;
     *itgs = 0;
     co_areas(igs);
     memcpy(wstot, wsfix, sizeof(double) * 2 * npot);
-    if (c->force3 >= 1) for (int i = 0; i < npot; i++) if (igs->el[i] >= CO_ADHES) wstot[i] = wstot[i] + 1.0 * c->cksi * dq;
-    if (c->force3 >= 2) for (int i = 0; i < npot; i++) if (igs->el[i] >= CO_ADHES) wstot[npot + i] = wstot[npot + i] + 1.0 * c->ceta * dq;
-    solve_once(cx, c, npot, cs, ms, wstot, mus, igs, ps, ss, dxdy, muscal, fntrue, &it, err, &fxkp1, &fykp1);
+    if (c->force3 >= 1) for (int i = 0; i < npot; i++) if (igs->el[i] >= CO_ADHES) wstot[i] = wstot[i] + facdt[i] * c->cksi * dq;
+    if (c->force3 >= 2) for (int i = 0; i < npot; i++) if (igs->el[i] >= CO_ADHES) wstot[npot + i] = wstot[npot + i] + facdt[i] * c->ceta * dq;
+    solve_once(cx, c, o, npot, cs, ms, wstot, mus, igs, ps, ss, dxdy, muscal, fntrue, &it, err, &fxkp1, &fykp1);
     *itgs += it;
     eldiv_count(igs, npot, &nadh, &nslip, &nplast, &nexter);
-    if (c->force3 >= 1) {
+    if (c->force3 >= 1 && o->info <= 1) {
         itnr = 0;
         df = fabs(c->fxrel - fxkp1);
         if (c->force3 >= 2) df = df + fabs(c->fyrel - fykp1);
-        while (df > c->eps && itnr < c->maxnr) {
+        while (df > c->eps && itnr < c->maxnr && o->info <= 1) {
             itnr++;
             dfx = c->fxrel - fxkp1;
             dfy = c->fyrel - fykp1;
@@ -238,12 +253,12 @@ static void solvpt(co_ctx *cx, co_case *c, int npot, co_inflcf *cs, co_inflcf *m
                 fxk = fxkp1; fyk = fykp1;
                 if (ifxy == 1) {
                     c->cksi = c->cksi + dcksi;
-                    for (int i = 0; i < npot; i++) if (igs->el[i] >= CO_ADHES) wstot[i] = wstot[i] + 1.0 * dcksi * dq;
+                    for (int i = 0; i < npot; i++) if (igs->el[i] >= CO_ADHES) wstot[i] = wstot[i] + facdt[i] * dcksi * dq;
                 } else {
                     c->ceta = c->ceta + dceta;
-                    for (int i = 0; i < npot; i++) if (igs->el[i] >= CO_ADHES) wstot[npot + i] = wstot[npot + i] + 1.0 * dceta * dq;
+                    for (int i = 0; i < npot; i++) if (igs->el[i] >= CO_ADHES) wstot[npot + i] = wstot[npot + i] + facdt[i] * dceta * dq;
                 }
-                solve_once(cx, c, npot, cs, ms, wstot, mus, igs, ps, ss, dxdy, muscal, fntrue, &it, err, &fxkp1, &fykp1);
+                solve_once(cx, c, o, npot, cs, ms, wstot, mus, igs, ps, ss, dxdy, muscal, fntrue, &it, err, &fxkp1, &fykp1);
                 *itgs += it;
                 eldiv_count(igs, npot, &nadh, &nslip, &nplast, &nexter);
                 dfxk = fxkp1 - fxk; dfyk = fykp1 - fyk;
@@ -272,23 +287,43 @@ static void solvpt(co_ctx *cx, co_case *c, int npot, co_inflcf *cs, co_inflcf *m
     free(wstot);
 }
 
-/* m_stang.f90:28-746 for L=0, elastic material, shifts */
+/* m_stang.f90:28-746 for L=0, elastic material: shifts with TangCG, steady rolling with SteadyGS */
 static int stang(co_ctx *cx, co_case *c, int npot, co_inflcf *cs, co_inflcf *cv, co_inflcf *ms, const double *hs,
-                 const double *pv, co_eldiv *igs, double *ps, double *ss, double dxdy, double muscal, double fntrue,
-                 double sens[2][2], int *itgs_out)
+                 const double *pv, const double *x, co_eldiv *igs, double *ps, double *ss, double dxdy, double muscal,
+                 double fntrue, double dq, double sens[2][2], int *itgs_out)
 {
-    const int mx = igs->mx, my = igs->my;
+    const int mx = igs->mx, my = igs->my, is_ssrol = (c->tang == 3);
     double *wsfix = (double *) calloc(3L * npot, sizeof(double)), *mus = (double *) malloc(sizeof(double) * npot);
-    double *tmp = (double *) calloc(3L * npot, sizeof(double));
+    double *tmp = (double *) calloc(3L * npot, sizeof(double)), *facdt = (double *) malloc(sizeof(double) * npot);
     int ittang = 0, itgs = 0, zready = 0, it, nadh, nslip, nplast, nexter;
     double errpt = 0.0, tol, tol1, tol2, pabs, ww;
+    tang_opts o = { SOLV_TANGCG, 1.0, 1.0, dq, facdt, 0 };
+    int k = 0;
+    for (int i = 0; i < npot; i++) if (igs->el[i] >= CO_ADHES) k++;
+    if (is_ssrol) {                                                                        /* :136-223 */
+        int icount = 0;
+        for (int iy = 1; iy <= my; iy++) if (igs->el[1 + (iy - 1) * mx - 1] >= CO_ADHES) icount++;
+        o.solver = SOLV_STDYGS;
+        if (icount > 0 || c->gausei == 2 || c->gausei == 5) {     /* ConvexGS / GDsteady are outside this restatement */
+            free(wsfix); free(mus); free(tmp); free(facdt);
+            *itgs_out = 0;
+            return -99;
+        }
+        if (k <= 25) { o.omegah = 1.0; o.omegas = 1.0; }
+        else if (c->dx / c->dy <= 5.0) { o.omegah = 0.9; o.omegas = 1.0; }
+        else if (c->dx / c->dy <= 15.0) { o.omegah = 0.8; o.omegas = 0.8; }
+        else { o.omegah = 0.8; o.omegas = 0.6; }
+        co_sxbnd_facdt(mx, my, igs, x, c->dx, dq, facdt);
+    } else
+        for (int i = 0; i < npot; i++) facdt[i] = 1.0;                                    /* sxbnd, .not.is_roll */
     for (int i = 0; i < npot; i++) mus[i] = c->fstat;
-    tang_rhs(cx, npot, igs, hs, ps, pv, cs, cv, wsfix);
+    tang_rhs(cx, npot, is_ssrol, facdt, igs, hs, ps, pv, cs, cv, wsfix);
     while (!zready && ittang < c->maxin) {                                                /* :376 */
         ittang++;
         zready = 1;
-        solvpt(cx, c, npot, cs, ms, wsfix, mus, igs, ps, ss, dxdy, muscal, fntrue, sens, &it, &errpt);
+        solvpt(cx, c, &o, npot, cs, ms, wsfix, mus, igs, ps, ss, dxdy, muscal, fntrue, sens, &it, &errpt);
         itgs += it;
+        if (o.info >= 3) { zready = 1; ittang = -1; }                                     /* :420-427 */
         int newins = 0;
         tol = sqrt(2.0) * errpt;
         for (int i = 0; i < npot; i++) if (igs->el[i] == CO_ADHES) {                      /* :434-453 */
@@ -314,16 +349,17 @@ static int stang(co_ctx *cx, co_case *c, int npot, co_inflcf *cs, co_inflcf *cv,
                 if (ww > tol) { igs->el[i] = CO_ADHES; newadh++; }
             }
             if (newadh != 0) zready = 0;
+            if (o.info > 0) zready = 1;                                                   /* :510 */
         }
     }
     eldiv_count(igs, npot, &nadh, &nslip, &nplast, &nexter);
     if (!zready) ittang = -1;
     *itgs_out = itgs;
-    free(wsfix); free(mus); free(tmp);
+    free(wsfix); free(mus); free(tmp); free(facdt);
     return ittang;
 }
 
-/* contac (m_scontc.f90:37-216) + panprc (:356-553) for module-3 cases: T = 0 or 1, N = 0/1, F = 0/1/2, I = 0, P = 2 */
+/* contac (m_scontc.f90:37-216) + panprc (:356-553) for module-3 cases: T = 0, 1 or 3 (SteadyGS), N = 0/1, F = 0/1/2, I = 0, P = 2 */
 int co_contac(co_case *c)
 {
     const int mx = c->mx, my = c->my, npot = mx * my;
@@ -333,16 +369,28 @@ int co_contac(co_case *c)
     co_combin_mater(&mat);
     co_inflcf cs, cv, csv, ms;
     memset(&cs, 0, sizeof(cs)); memset(&cv, 0, sizeof(cv)); memset(&csv, 0, sizeof(csv)); memset(&ms, 0, sizeof(ms));
-    co_sgencr(&mat, mx, my, c->dx, c->dy, 0, 0.0, 1.0, &cs, &cv, &csv, &ms);
+    /* check_roll_stepsize (m_sdis.f90:125-204): shifts chi = 0, dq = 1; SteadyGS forces chi = 0 (or pi), dq = dx */
+    const int is_roll = (c->tang == 2 || c->tang == 3), is_ssrol = (c->tang == 3);
+    double chi = 0.0, dq = 1.0;
+    if (is_roll) {
+        chi = c->chi; dq = c->dq;
+        if (is_ssrol && c->gausei != 2) {
+            if (fabs(chi) > 0.01 && fabs(chi - CO_PI) > 0.01) chi = 0.0;
+            dq = c->dx;
+        }
+    }
+    if (c->tang == 2 || (is_ssrol && fabs(chi) > 0.01)) { co_ctx_free(cx); return -99; }     /* not restated */
+    co_sgencr(&mat, mx, my, c->dx, c->dy, is_roll, chi, dq, &cs, &cv, &csv, &ms);
     double *x = (double *) malloc(sizeof(double) * npot), *y = (double *) malloc(sizeof(double) * npot);
     double *hs = (double *) calloc(3L * npot, sizeof(double)), *ps = (double *) calloc(3L * npot, sizeof(double));
     double *pv = (double *) calloc(3L * npot, sizeof(double)), *ss = (double *) calloc(3L * npot, sizeof(double));
     double *po1 = (double *) calloc(3L * npot, sizeof(double));
     co_grid_coords(mx, my, c->xl, c->yl, c->dx, c->dy, x, y);
     co_set_norm_rhs(c->ibase, 1, npot, x, y, c->nn, c->prmudf, NULL, hs + 2L * npot);
-    /* set_tang_rhs (m_sdis.f90:498-583), shifts: dq = 1, no spin offset */
-    const double dq = 1.0;
-    for (int i = 0; i < npot; i++) { hs[i] = 1.0 * -(y[i] + 0.0 - 0.0) * c->cphi + 0.0; hs[npot + i] = 1.0 * (x[i] + 0.0 - 0.0) * c->cphi + 0.0; }
+    /* set_tang_rhs (m_sdis.f90:498-583): spin offset facphi*dq in rolling problems */
+    const double facphi = (c->facphi > 0.0) ? c->facphi : 1.0 / 6.0;
+    const double xofs_dq = is_roll ? cos(chi) * dq * facphi : 0.0, yofs_dq = is_roll ? sin(chi) * dq * facphi : 0.0;
+    for (int i = 0; i < npot; i++) { hs[i] = 1.0 * -(y[i] + yofs_dq - 0.0) * c->cphi + 0.0; hs[npot + i] = 1.0 * (x[i] + xofs_dq - 0.0) * c->cphi + 0.0; }
     if (c->force3 == 0) for (int i = 0; i < npot; i++) hs[i] = hs[i] + c->cksi;
     if (c->force3 <= 1) for (int i = 0; i < npot; i++) hs[npot + i] = hs[npot + i] + c->ceta;
     for (int i = 0; i < 2 * npot; i++) hs[i] = -dq * hs[i];
@@ -364,6 +412,7 @@ int co_contac(co_case *c)
     double dif = 200.0, difid = 1.0;
     const double dxdy = c->dx * c->dy, muscal = c->fstat;
     c->nr_n = 0;
+    int unsupported = 0;
     memcpy(po1, ps, sizeof(double) * 3 * npot);
     while (dif > difid && itout < c->maxout && itnorm >= 0 && ittang >= 0) {
         itout++;
@@ -376,7 +425,8 @@ int co_contac(co_case *c)
         }
         if (c->tang == 0 || ncon <= 0) dif = 0.0;
         else {
-            int it = stang(cx, c, npot, &cs, &cv, &ms, hs, pv, &igs, ps, ss, dxdy, muscal, fntrue, sens, &itgs);
+            int it = stang(cx, c, npot, &cs, &cv, &ms, hs, pv, x, &igs, ps, ss, dxdy, muscal, fntrue, dq, sens, &itgs);
+            if (it == -99) { unsupported = 1; break; }
             if (it >= 0) ittang += it; else ittang = -1;
             for (int i = 0; i < 3 * npot; i++) po1[i] = po1[i] + (-1.0) * ps[i];
             double s1 = 0.0, s2 = 0.0; int cnt = 0;
@@ -401,5 +451,6 @@ int co_contac(co_case *c)
     co_eldiv_free(&igs); co_inflcf_free(&cs); co_inflcf_free(&cv); co_inflcf_free(&csv); co_inflcf_free(&ms);
     free(x); free(y); free(hs); free(ps); free(pv); free(ss); free(po1);
     co_ctx_free(cx);
+    if (unsupported) return -99;
     return itnorm < 0 ? -27 : (ittang < 0 ? -28 : 0);
 }

@@ -166,6 +166,8 @@ typedef struct {
     int    maxgs, maxin, maxnr, maxout;
     double eps;
     int    fullbox;
+    double chi, dq, facphi;             /* rolling direction, step, spin offset factor (<= 0: default 1/6) */
+    int    gausei;                      /* G digit */
     /* outputs */
     int    *el;                         /* [npot] */
     double *ps;                         /* [3][npot] */
@@ -180,6 +182,13 @@ typedef struct {
 void   co_tangcg(co_ctx *cx, int npot, int maxcg, double eps, const double *ws, co_inflcf *cs, co_inflcf *ms,
                  const double *mu, co_eldiv *igs, double *ps, double *ss, int *itcg, double *err);
 int    co_contac(co_case *c);
+
+/* ---- steady rolling (co_steady.c) ---- */
+void   co_plstrc(int *el, const double coef[2][2], double eps, double omegah, double omegas, double pr[3], double mus,
+                 double s[2]);
+void   co_stdygs(co_ctx *cx, int mx, int my, const double *ws, co_inflcf *cs, const double *mus, co_eldiv *igs, double *ps,
+                 double *ss, int k, double eps, int maxgs, double omegah, double omegas, int *info, int *itgs_out, double *err);
+void   co_sxbnd_facdt(int mx, int my, const co_eldiv *igs, const double *x, double dx, double dq, double *facdt);
 
 /* ---- subsurface stresses (co_subsurf.c) ---- */
 void   co_stres1_pcwcns(double dx, double dy, double gg, double v[3][3][4], double vnu[3][3][4], const double xw[3],

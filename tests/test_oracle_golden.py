@@ -120,3 +120,29 @@ def test_cattaneo_case2_full_shift_problem():
     gold = np.array([[{"*": 1, "S": 2, "|": 1}.get(ch, 0) for ch in row] for row in pics[1]], dtype=np.int32)
     assert np.array_equal((gold.ravel() > 0), el > 0)
     assert np.array_equal(gold.ravel() == 2, el == 2)
+
+
+def _mbench_grid(mbench):
+    return dict(mx=71, my=81, xl=-3.55, yl=-6.15, dx=0.1, dy=0.1, ibase=2, prmudf=np.array(mbench["prmudf"]))
+
+
+def test_perfc_tang_problm_1s_shift(mbench):
+    """perfc_test/get_times.ref_out:21 (tang_problm_1s.inp: T=1, F=0, TangCG): nslp = 1730, ItGS(CG) = 51."""
+    gold = json.load(open(os.path.join(HERE, "golden", "get_times.json")))["tang_problm_1s"]
+    r = O.contac(_mbench_grid(mbench), cases.STEEL["gg"], cases.STEEL["poiss"], tang=1, norm=0, force3=0, pen=mbench["pen"],
+                 cksi=0.0005, ceta=-0.001, cphi=0.0008, fstat=0.3, fkin=0.3, maxgs=1000, maxin=100, maxnr=30, maxout=1,
+                 eps=1e-7, nn=mbench["nn"])
+    assert r["ierror"] == 0
+    assert int((r["el"] == 2).sum()) == gold["nslp"] and r["itgs_tang"] == gold["itgs"]
+
+
+def test_perfc_tang_problm_1c_steady_rolling(mbench):
+    """perfc_test/get_times.ref_out:25 (tang_problm_1c.inp run with the default solver, T=3 SteadyGS): nslp = 1872,
+    ItGS = 56.  Pins stdygs + plstrc + the rolling right-hand side (dq forced to dx, spin offset dq/6)."""
+    gold = json.load(open(os.path.join(HERE, "golden", "get_times.json")))["tang_problm_1c"]
+    r = O.contac(_mbench_grid(mbench), cases.STEEL["gg"], cases.STEEL["poiss"], tang=3, norm=0, force3=0, pen=mbench["pen"],
+                 cksi=0.0005, ceta=0.0, cphi=0.0003, fstat=0.3, fkin=0.3, maxgs=1000, maxin=100, maxnr=30, maxout=1,
+                 eps=1e-7, nn=mbench["nn"], chi=0.0, dq=0.1, gausei=0)
+    assert r["ierror"] == 0 and r["ittang"] == 1
+    assert int((r["el"] == 2).sum()) == gold["nslp"] and r["itgs_tang"] == gold["itgs"]
+    assert int((r["el"] == 1).sum()) == 3148 - gold["nslp"]
