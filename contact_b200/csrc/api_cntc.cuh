@@ -54,7 +54,7 @@ struct Problem {
     double fstat = 0.3, fkin = 0.3;
     // solver settings (solv_init, m_hierarch_data.f90:1722-1751)
     int maxgs = 999, maxin = 20, maxnr = 25, maxout = 1;
-    double eps = 1e-5;
+    double eps = 1e-5, omegah = 0.9, omegas = 1.0, dq_eff = 1.0;
     // results
     int ncase = 0, itnorm = 0, ittang = 0, itcg = 0, ncon = 0, nadh = 0, nslip = 0, status = 0;
     std::vector<int> el;
@@ -194,9 +194,11 @@ inline int count_at_boundary(const Problem &p)
 // check_case / scope check: returns 0 or an error code
 inline int check_scope(const Problem &p)
 {
-    if (p.tang != 0 && p.tang != 1) { last_error() = "T-digit: only T=0 (frictionless) and T=1 (shift) are served by the B200 path yet; rolling (T=2,3) is not"; return CNTC_err_other; }
-    if (p.tang == 1 && p.frclaw != 0) { last_error() = "L-digit: only Coulomb friction (L=0)"; return CNTC_err_other; }
-    if (p.tang == 1 && p.gausei == 2) { last_error() = "G-digit: ConvexGS (G=2) is not served by the B200 path yet"; return CNTC_err_other; }
+    if (p.tang == 2) { last_error() = "T-digit: transient rolling (T=2) is not served by the B200 path yet (T=0, 1, 3 are)"; return CNTC_err_other; }
+    if (p.tang != 0 && p.frclaw != 0) { last_error() = "L-digit: only Coulomb friction (L=0)"; return CNTC_err_other; }
+    if (p.tang != 0 && p.gausei == 2) { last_error() = "G-digit: ConvexGS (G=2) is not served by the B200 path yet"; return CNTC_err_other; }
+    if (p.tang == 3 && p.gausei == 5) { last_error() = "G-digit: GDsteady (G=5) is not served by the B200 path yet (SteadyGS, G=0/3/4, is)"; return CNTC_err_other; }
+    if (p.tang == 3 && fabs(p.chi) > 0.01 && fabs(p.chi - 3.14159265358979323846) <= 0.01) { last_error() = "CHI = pi (rolling in -x) is not served by the B200 path yet"; return CNTC_err_other; }
     if (p.mater != 0) { last_error() = "M-digit: only the elastic half-space (M=0) is in the hot-path scope"; return CNTC_err_other; }
     if (p.gencr != 2 && p.gencr != 1) { last_error() = "C-digit: only piecewise-constant analytical coefficients (C=2)"; return CNTC_err_other; }
     if (p.bound != 0) { last_error() = "B-digit: only the full normal problem (B=0)"; return CNTC_err_other; }
@@ -205,6 +207,15 @@ inline int check_scope(const Problem &p)
     if (p.ibase != 1 && p.ibase != 2 && p.ibase != 3 && p.ibase != 9) { last_error() = "invalid IBASE"; return CNTC_err_input; }
     if (p.ibase == 9 && (int) p.prmudf.size() < p.mx * p.my) { last_error() = "IBASE=9 needs npot values"; return CNTC_err_input; }
     return 0;
+}
+
+// check_roll_stepsize (m_sdis.f90:125-204): SteadyGS forces chi = 0 and dq = dx; shifts use chi = 0, dq = 1
+inline void roll_stepsize(const Problem &p, double &chi, double &dq)
+{
+    if (p.tang == 2 || p.tang == 3) {
+        chi = p.chi; dq = p.dq;
+        if (p.tang == 3 && p.gausei != 2) { if (fabs(chi) > 0.01 && fabs(chi - 3.14159265358979323846) > 0.01) chi = 0.0; dq = p.dx; }
+    } else { chi = 0.0; dq = 1.0; }
 }
 
 // contac (m_scontc.f90:37-216) for a batch of problems: host set-up, ONE device launch per coefficient class, gather
@@ -235,7 +246,9 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
         pen0[k] = pen;
         if (p.ret > 1) { ierr[k] = 0; continue; }                        // R=2,3: checks only
         CoefSet *cs = nullptr;
-        int rc = get_coefset(p.mx, p.my, p.dx, p.dy, p.mat, 0, 0.0, 1.0, 0, &cs);
+        double chi_e, dq_e;
+        roll_stepsize(p, chi_e, dq_e);
+        int rc = get_coefset(p.mx, p.my, p.dx, p.dy, p.mat, p.tang == 3 ? 1 : 0, chi_e, dq_e, 0, &cs);
         if (rc) { ierr[k] = rc; continue; }
         if (!cs->hp.fits) { last_error() = "grid too large for the single-CTA solver"; ierr[k] = CNTC_err_discr; continue; }
         groups[cs].push_back(k);
@@ -258,6 +271,7 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
         }
         if (!rc && cs.nt_cpl) {
             for (int t = 1; t <= 2 && !rc; t++) { rc = build_chat(cs, SET_CS, 3, t, 0); if (!rc && any_tang) rc = build_chat(cs, SET_CS, t, 3, 0); }
+            if (cs.key.is_roll) for (int t = 1; t <= 2 && !rc; t++) rc = build_chat(cs, SET_CV, t, 3, 0);
         }
         if (rc) { fail(rc); continue; }
         // device buffers: per case hs_n(1) hst(2) ps(3) ss(2) work(9) twork(24) = 41 n doubles, el n ints
@@ -294,17 +308,23 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
             c.cksi = p.cksi; c.ceta = p.ceta; c.fxrel = p.fxrel; c.fyrel = p.fyrel; c.fstat = p.fstat;
             if (p.iestim == 0 || p.iestim == 2) { if (p.force3 >= 1) c.cksi = 1e-6; if (p.force3 == 2) c.ceta = 0.0; }   // m_sdis.f90:760-762
             c.pv = nullptr;
-            for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) { c.chatA[a][b] = cs.d_chat[SET_CS][a][b]; c.chatV[a][b] = cs.d_chat[SET_CS][a][b]; }
+            double chi_e, dq_e;
+            roll_stepsize(p, chi_e, dq_e);
+            const bool is_roll = cs.key.is_roll != 0;
+            for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) { c.chatA[a][b] = cs.d_chat[SET_CS][a][b]; c.chatV[a][b] = cs.d_chat[is_roll ? SET_CV : SET_CS][a][b]; }
+            c.cf12 = cs.d_cf[SET_CS] + 3 * nblk; c.dq = dq_e; c.dx = p.dx; c.gausei = p.gausei; c.omegah = p.omegah; c.omegas = p.omegas;
             c.chatM11 = cs.d_chat[SET_MS][0][0]; c.chatM22 = cs.d_chat[SET_MS][1][1];
             c.cf11 = cs.d_cf[SET_CS] + 0 * nblk; c.cf22 = cs.d_cf[SET_CS] + 4 * nblk;
             c.c11 = c00[0]; c.c22 = c00[1]; c.ga = cs.ga;
             // host inputs: hs_n, hst (set_tang_rhs, m_sdis.f90:498-583; shifts: dq = 1), ps
             std::copy(hs[ks[i]].begin(), hs[ks[i]].end(), stage.begin());
-            const double dq = 1.0;
+            // rolling: spin pole shifted by facphi*dq along the rolling direction (facphi = 1/6, m_sinput.f90:789-793)
+            const double dq = dq_e, facphi = 1.0 / 6.0;
+            const double xofs = is_roll ? cos(chi_e) * dq * facphi : 0.0, yofs = is_roll ? sin(chi_e) * dq * facphi : 0.0;
             for (int iy = 0; iy < p.my; iy++) for (int ix = 0; ix < p.mx; ix++) {
                 const int ii = iy * p.mx + ix;
                 const double x = p.xc1 + ix * p.dx, y = p.yc1 + iy * p.dy;
-                double wx = -(y) * p.cphi, wy = (x) * p.cphi;
+                double wx = -(y + yofs) * p.cphi, wy = (x + xofs) * p.cphi;
                 if (p.force3 == 0) wx += p.cksi;
                 if (p.force3 <= 1) wy += p.ceta;
                 stage[npot + ii] = -dq * wx; stage[2 * (size_t) npot + ii] = -dq * wy;
@@ -338,6 +358,7 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
                 cudaMemcpy(p.el.data(), c.nrm.el, sizeof(int) * npot, cudaMemcpyDeviceToHost);
                 cudaMemcpy(p.ps.data(), c.ps, sizeof(double) * 3 * npot, cudaMemcpyDeviceToHost);
                 if (p.tang != 0) cudaMemcpy(p.ss.data(), c.ss, sizeof(double) * 2 * npot, cudaMemcpyDeviceToHost);
+                if (p.tang == 3) p.dq_eff = c.dq;
                 p.us.assign(h_us.begin() + (size_t) i * 3 * npot, h_us.begin() + (size_t) (i + 1) * 3 * npot);
                 p.hs.assign(3 * (size_t) npot, 0.0);
                 std::copy(hs[ks[i]].begin(), hs[ks[i]].end(), p.hs.begin() + 2 * (size_t) npot);
@@ -363,7 +384,8 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
                 } else { p.fcntc[0] = p.fcntc[1] = 0.0; p.mztrue = 0.0; }
                 p.fcntc[2] = p.fntrue;
                 p.solved = true;
-                if (p.itnorm < 0 || (p.status & 1)) ierr[ks[i]] = CNTC_err_norm;
+                if (c.tstatus & 1) { last_error() = "TANG: no exterior elements at the trailing edge of the potential contact area: the reference switches to ConvexGS, which the B200 path does not serve yet"; ierr[ks[i]] = CNTC_err_other; }
+                else if (p.itnorm < 0 || (p.status & 1)) ierr[ks[i]] = CNTC_err_norm;
                 else if (p.ittang < 0) ierr[ks[i]] = CNTC_err_tang;
                 else ierr[ks[i]] = count_at_boundary(p);              // contact_addon.f90:3885-3891
             }
@@ -469,6 +491,7 @@ void cntc_setsolverflags(int *ire, int *icp, int *gdigit, int *nints, int *ipara
         p->eps = std::max(1e-20, rparam[0]);
         p->maxgs = std::max(1, iparam[0]); p->maxin = std::max(1, iparam[1]);
         p->maxnr = std::max(1, iparam[2]); p->maxout = std::max(1, iparam[3]);
+        if (g == 2 || g == 3) { p->omegah = std::max(1e-20, rparam[1]); p->omegas = std::max(1e-20, rparam[2]); }   // contact_addon.f90:1203-1208
     }
 }
 
@@ -735,8 +758,8 @@ void cntc_getfielddata(int *ire, int *icp, int *ifld, int *lenarr, double *fld)
     case CNTC_fld_ux: src = &p->us; col = 0; scl = 1.0 / s.len; break;
     case CNTC_fld_uy: src = &p->us; col = 1; scl = 1.0 / s.len; break;
     case CNTC_fld_un: src = &p->us; col = 2; scl = 1.0 / s.len; break;
-    case CNTC_fld_sx: src = &p->ss; col = 0; scl = s.body / (p->tang >= 2 ? p->dq : 1.0); break;
-    case CNTC_fld_sy: src = &p->ss; col = 1; scl = s.body / (p->tang >= 2 ? p->dq : 1.0); break;
+    case CNTC_fld_sx: src = &p->ss; col = 0; scl = s.body / (p->tang >= 2 ? p->dq_eff : 1.0); break;
+    case CNTC_fld_sy: src = &p->ss; col = 1; scl = s.body / (p->tang >= 2 ? p->dq_eff : 1.0); break;
     default: break;
     }
     for (int i = 0; i < *lenarr && i < npot; i++) {

@@ -202,6 +202,17 @@ inline int get_coefset(int mx, int my, double dx, double dy, Material mat, int i
     ElascfArgs a = { mat.ak, mat.nu, dx, dy, 0.0, 0.0, mx, my };
     k_elascf_pcwcns<<<grid1d(nblk, 128), 128, 0, st>>>(a, cs->d_cf[SET_CS]);
     E.launches++;
+    if (is_roll) {
+        // sgencr for rolling (m_visc.f90:310-359): cv = coefficients at the offset dq along the rolling direction for
+        // the tangential displacements, the normal rows are those of cs
+        CB_CUDA(cudaMalloc(&cs->d_cf[SET_CV], sizeof(double) * 9 * nblk));
+        ElascfArgs av = { mat.ak, mat.nu, dx, dy, cos(chi) * dq, sin(chi) * dq, mx, my };
+        k_elascf_pcwcns<<<grid1d(nblk, 128), 128, 0, st>>>(av, cs->d_cf[SET_CV]);
+        E.launches++;
+        for (int jk = 0; jk < 3; jk++)
+            CB_CUDA(cudaMemcpyAsync(cs->d_cf[SET_CV] + (size_t) (jk * 3 + 2) * nblk, cs->d_cf[SET_CS] + (size_t) (jk * 3 + 2) * nblk,
+                                    sizeof(double) * nblk, cudaMemcpyDeviceToDevice, st));
+    }
     CB_CUDA(cudaGetLastError());
     CB_CUDA(cudaStreamSynchronize(st));
     E.sets[key] = cs;

@@ -8,6 +8,7 @@
 // tangential product is four single-block products accumulated in place.
 #pragma once
 #include "norm_solver.cuh"
+#include "steady_solver.cuh"
 
 namespace cb200 {
 
@@ -28,12 +29,17 @@ struct ContactCase {
     const cd *chatM11, *chatM22;    // transformed preconditioner blocks
     const double *cf11, *cf22;      // spatial blocks cs(1,1), cs(2,2)
     double c11, c22, ga;
+    const double *cf12;             // spatial block cs(1,2)
+    double dq, dx;                  // rolling step (shifts: 1), grid step in x
+    int gausei;                     // G-digit
+    double omegah, omegas;          // relaxation factors of the Gauss-Seidel solvers (set by stang)
     // outputs
     int ittang, itgs, itout, nr_n;
     int nr_itcg[CB_MAXNR_LOG];
     double nr_cksi[CB_MAXNR_LOG], nr_ceta[CB_MAXNR_LOG], nr_fx[CB_MAXNR_LOG], nr_fy[CB_MAXNR_LOG];
     double fx, fy, sens[2][2];
     int nadh, nslip;
+    int tstatus;                    // bit 0: the case needs a solver outside this path (ConvexGS / GDsteady)
 };
 
 // u(ik) = sum_jk A(ik,jk) p(jk) over the given direction ranges, masked (AllInt when el given), blocks with a null
@@ -250,11 +256,25 @@ __device__ double centre_rowsum_blk(const ConvPlan &P, const double *blk, int cm
 }
 
 // one tangential solve + relative forces (+ log of the Newton-Raphson process)
-__device__ void solve_once_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, const double *wstot, double fntrue,
-                               int &it, double &err, double &fx, double &fy, int &nprod)
+__device__ int solve_once_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, const double *wstot, double fntrue,
+                              int &it, double &err, double &fx, double &fy, int &nprod)
 {
     const int n = P.npot;
-    tangcg_dev(P, sm, c, wstot, c.nrm.maxgs, c.nrm.eps, it, err, nprod);
+    int info = 0;
+    if (c.tang == 3) {                                                         // SteadyGS (m_stang.f90:166-185)
+        int nadh, nslip;
+        count_el(c.nrm.el, n, sm.red, nadh, nslip);
+        const int ncon = nadh + nslip;
+        SteadyArgs a;
+        a.ws = wstot; a.dp = c.twork + 3 * (size_t) n; a.ug = c.twork + 5 * (size_t) n;
+        a.iel = reinterpret_cast<int *>(c.twork + 7 * (size_t) n);
+        a.chatA = c.chatA; a.cf11 = c.cf11; a.cf12 = c.cf12; a.cf22 = c.cf22; a.cmx = c.nrm.cmx; a.cmy = c.nrm.cmy;
+        a.ga_inv = c.nrm.ga_inv; a.mu = c.fstat; a.eps = c.nrm.eps; a.omegah = c.omegah; a.omegas = c.omegas; a.maxgs = c.nrm.maxgs;
+        if (ncon <= 6 * CB_THREADS) info = stdygs_dev<6>(P, sm, a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
+        else if (ncon <= 12 * CB_THREADS) info = stdygs_dev<12>(P, sm, a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
+        else info = stdygs_dev<22>(P, sm, a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
+    } else
+        tangcg_dev(P, sm, c, wstot, c.nrm.maxgs, c.nrm.eps, it, err, nprod);
     double s[2] = { 0.0, 0.0 };
     for (int i = threadIdx.x; i < n; i += blockDim.x) { s[0] += c.ps[i]; s[1] += c.ps[n + i]; }
     block_sum<2>(s, sm.red);
@@ -267,34 +287,39 @@ __device__ void solve_once_dev(const ConvPlan &P, const Smem &sm, ContactCase &c
     __syncthreads();
     if (threadIdx.x == 0) c.nr_n++;
     __syncthreads();
+    return info;
 }
 
 // solvpt (m_solvpt.f90:51-378): Newton-Raphson on (cksi[, ceta]) for prescribed tangential forces; shifts: dq = 1
-__device__ void solvpt_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, const double *wsfix, double *wstot,
-                           double fntrue, int &itgs, double &err, int &nprod)
+__device__ int solvpt_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, const double *wsfix, double *wstot,
+                          const double *facdt, double fntrue, int &itgs, double &err, int &nprod)
 {
     const int n = P.npot, tid = threadIdx.x, nt = blockDim.x;
     const int *el = c.nrm.el;
-    const double dq = 1.0, dxdy = c.nrm.dxdy, muscal = c.fstat, eps = c.nrm.eps;
+    const double dq = c.dq, dxdy = c.nrm.dxdy, muscal = c.fstat, eps = c.nrm.eps;
     double cksi = c.cksi, ceta = c.ceta;                     // block-uniform copies; c.cksi/c.ceta updated by thread 0
     int it, nadh, nslip;
     double fxkp1, fykp1;
     itgs = 0;
     for (int i = tid; i < n; i += nt) {
         double wx = wsfix[i], wy = wsfix[n + i];
-        if (el[i] >= 1) { if (c.force3 >= 1) wx += cksi * dq; if (c.force3 >= 2) wy += ceta * dq; }
+        if (el[i] >= 1) {
+            const double f = facdt ? facdt[i] : 1.0;
+            if (c.force3 >= 1) wx += f * cksi * dq;
+            if (c.force3 >= 2) wy += f * ceta * dq;
+        }
         wstot[i] = wx; wstot[n + i] = wy;
     }
     __syncthreads();
-    solve_once_dev(P, sm, c, wstot, fntrue, it, err, fxkp1, fykp1, nprod);
+    int info = solve_once_dev(P, sm, c, wstot, fntrue, it, err, fxkp1, fykp1, nprod);
     itgs += it;
     count_el(el, n, sm.red, nadh, nslip);
-    if (c.force3 >= 1) {
+    if (c.force3 >= 1 && info <= 1) {
         int itnr = 0;
         double df = fabs(c.fxrel - fxkp1);
         if (c.force3 >= 2) df += fabs(c.fyrel - fykp1);
         double s00 = c.sens[0][0], s01 = c.sens[0][1], s10 = c.sens[1][0], s11 = c.sens[1][1];
-        while (df > eps && itnr < c.maxnr) {
+        while (df > eps && itnr < c.maxnr && info <= 1) {
             itnr++;
             const double dfx = c.fxrel - fxkp1, dfy = c.fyrel - fykp1;
             double dcksi, dceta;
@@ -308,12 +333,12 @@ __device__ void solvpt_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, co
             }
             for (int ifxy = 1; ifxy <= c.force3; ifxy++) {
                 const double fxk = fxkp1, fyk = fykp1;
-                if (ifxy == 1) { cksi += dcksi; for (int i = tid; i < n; i += nt) if (el[i] >= 1) wstot[i] += dcksi * dq; }
-                else { ceta += dceta; for (int i = tid; i < n; i += nt) if (el[i] >= 1) wstot[n + i] += dceta * dq; }
+                if (ifxy == 1) { cksi += dcksi; for (int i = tid; i < n; i += nt) if (el[i] >= 1) wstot[i] += (facdt ? facdt[i] : 1.0) * dcksi * dq; }
+                else { ceta += dceta; for (int i = tid; i < n; i += nt) if (el[i] >= 1) wstot[n + i] += (facdt ? facdt[i] : 1.0) * dceta * dq; }
                 __syncthreads();
                 if (tid == 0) { c.cksi = cksi; c.ceta = ceta; }
                 __syncthreads();
-                solve_once_dev(P, sm, c, wstot, fntrue, it, err, fxkp1, fykp1, nprod);
+                info = solve_once_dev(P, sm, c, wstot, fntrue, it, err, fxkp1, fykp1, nprod);
                 itgs += it;
                 count_el(el, n, sm.red, nadh, nslip);
                 const double dfxk = fxkp1 - fxk, dfyk = fykp1 - fyk, ncon = (double) (nadh + nslip);
@@ -336,9 +361,10 @@ __device__ void solvpt_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, co
         }
         err = err + 2.0 * df * muscal * fntrue / ((nadh + 2) * dxdy);          // the reference's constant Slip=2, :361
         if (tid == 0) { c.sens[0][0] = s00; c.sens[0][1] = s01; c.sens[1][0] = s10; c.sens[1][1] = s11; }
-    }
+    } else if (tid == 0) { c.sens[0][0] = 0.0; c.sens[0][1] = 0.0; c.sens[1][0] = 0.0; c.sens[1][1] = 0.0; }
     if (tid == 0) { c.fx = fxkp1; c.fy = fykp1; }
     __syncthreads();
+    return info;
 }
 
 // stang (m_stang.f90:28-746) for shifts with uniform Coulomb friction; returns ittang (-1: MaxIn reached)
@@ -349,9 +375,37 @@ __device__ int stang_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, doub
     double *ps = c.ps, *ss = c.ss, *red = sm.red;
     double *wsfix = c.twork + 13 * (size_t) n, *wstot = wsfix + 2 * n, *u1 = wstot + 2 * n, *u2 = u1 + 2 * n;
     const double mu = c.fstat;
-    // stang_rhs (:749-951), shifts: wsfix = -hs_t + A_tn pn - A'_tn p'n - A'_tt p'_t on C (facdt = 1)
+    const bool ssrol = (c.tang == 3);
+    double *facdt = nullptr;
+    if (ssrol) {                                                               // m_stang.f90:129-223
+        double cnt[2] = { 0.0, 0.0 };
+        for (int i = tid; i < n; i += nt) if (el[i] >= 1) { cnt[0] += 1.0; if (i % P.mx == 0) cnt[1] += 1.0; }
+        block_sum<2>(cnt, red);
+        const int k = (int) cnt[0];
+        // no exterior elements at the trailing edge, or G = 2 / 5: ConvexGS / GDsteady, which this path does not serve
+        if (cnt[1] > 0.0 || c.gausei == 2 || c.gausei == 5) { if (tid == 0) c.tstatus |= 1; __syncthreads(); itgs_tot = 0; return -1; }
+        double oh = c.omegah, os = c.omegas;
+        if (c.gausei == 0 || c.gausei == 4) {
+            const double r = c.dx / (c.nrm.dxdy / c.dx);                       // dx / dy
+            if (k <= 25) { oh = 1.0; os = 1.0; }
+            else if (r <= 5.0) { oh = 0.9; os = 1.0; }
+            else if (r <= 15.0) { oh = 0.8; os = 0.8; }
+            else { oh = 0.8; os = 0.6; }
+        }
+        __syncthreads();
+        if (tid == 0) { c.omegah = oh; c.omegas = os; }
+        __syncthreads();
+        facdt = c.twork;
+        sxbnd_facdt_dev(P.mx, P.my, el, c.dx, c.dq, facdt);
+    }
+    // stang_rhs (:749-951): wsfix = -facdt hs_t + A_tn pn - A'_tn p'n - A'_tt p'_t on C; shifts: facdt = 1, previous
+    // tractions p'; steady rolling: p' = p with the shifted coefficients cv, A'_tt p'_t left to the solver
     nprod += conv_multi(P, sm, c.chatA, ps, 2, 2, u1, 0, 1, el, 1);
-    if (c.pv) {
+    if (ssrol) {
+        nprod += conv_multi(P, sm, c.chatV, ps, 2, 2, u2, 0, 1, el, 1);
+        for (int i = tid; i < n; i += nt) if (el[i] >= 1) { u1[i] -= u2[i]; u1[n + i] -= u2[n + i]; }
+        __syncthreads();
+    } else if (c.pv) {
         nprod += conv_multi(P, sm, c.chatV, c.pv, 2, 2, u2, 0, 1, el, 1);
         for (int i = tid; i < n; i += nt) if (el[i] >= 1) { u1[i] -= u2[i]; u1[n + i] -= u2[n + i]; }
         __syncthreads();
@@ -361,8 +415,9 @@ __device__ int stang_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, doub
     }
     for (int i = tid; i < n; i += nt) {
         const bool in = el[i] >= 1;
-        wsfix[i] = in ? -c.hst[i] + u1[i] : 0.0;
-        wsfix[n + i] = in ? -c.hst[n + i] + u1[n + i] : 0.0;
+        const double f = facdt ? facdt[i] : 1.0;
+        wsfix[i] = in ? -f * c.hst[i] + u1[i] : 0.0;
+        wsfix[n + i] = in ? -f * c.hst[n + i] + u1[n + i] : 0.0;
     }
     __syncthreads();
 
@@ -373,8 +428,9 @@ __device__ int stang_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, doub
     while (!zready && ittang < c.nrm.maxin) {
         ittang++;
         zready = true;
-        solvpt_dev(P, sm, c, wsfix, wstot, fntrue, it, errpt, nprod);
+        const int info = solvpt_dev(P, sm, c, wsfix, wstot, facdt, fntrue, it, errpt, nprod);
         itgs_tot += it;
+        if (info >= 3) { ittang = -1; break; }                                 // :420-427 divergence
         double k[1] = { 0.0 };
         const double tol = sqrt(2.0) * errpt;
         for (int i = tid; i < n; i += nt) if (el[i] == 1) {                    // :434-453 adhesion -> slip
@@ -394,6 +450,7 @@ __device__ int stang_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, doub
             }
             block_sum<1>(ka, red);
             if (ka[0] > 0.0) zready = false;
+            if (info > 0) zready = true;                                       // :510
         }
     }
     if (!zready) ittang = -1;
@@ -424,7 +481,7 @@ __device__ void panprc_dev(const ConvPlan &P, const Smem &sm, ContactCase &c)
         else {
             int it_gs;
             const int it = stang_dev(P, sm, c, c.nrm.fntrue, it_gs, nprod);
-            itgs += it_gs;
+            itgs = it_gs;                                                      // solv%itgs is that of the last TANG call (m_stang.f90:274,709)
             if (it >= 0) ittang += it; else ittang = -1;
             double s[3] = { 0.0, 0.0, 0.0 };
             for (int i = tid; i < n; i += nt) {

@@ -350,3 +350,91 @@ def test_shift_with_prescribed_creepage_batch(cb, O):
         fn, tx, ty, mz = cb.cntc_getcontactforces(ire, 1)
         assert abs(tx / (0.4 * fn) - ref["fx"]) < 1e-7 and abs(ty / (0.4 * fn) - ref["fy"]) < 1e-7
         cb.cntc_finalize(ire)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# steady rolling (T=3) with SteadyGS
+# ------------------------------------------------------------------------------------------------------------
+def _setup_rolling(cb, ire, g, gg, poiss, pen=None, fn=None, fstat=0.3, maxgs=1000, maxin=100, maxnr=30, maxout=1, eps=1e-7,
+                   force=0, icp=1):
+    cb.cntc_initialize(ire, 3)
+    cb.cntc_setflags(ire, icp, [cb.CNTC["ic_tang"], cb.CNTC["ic_force"], cb.CNTC["ic_iestim"]], [3, force, 0])
+    cb.cntc_setsolverflags(ire, icp, 0, [maxgs, maxin, maxnr, maxout], [eps])
+    cb.cntc_setmaterialparameters(ire, icp, 0, [poiss[0], poiss[1], gg[0], gg[1]])
+    cb.cntc_setfrictionmethod(ire, icp, 0, [fstat, fstat])
+    cb.cntc_setpotcontact(ire, icp, 1, [g["mx"], g["my"], g["xl"], g["yl"], g["dx"], g["dy"]])
+    cb.cntc_setundeformeddistc(ire, icp, g["ibase"], g["prmudf"])
+    if pen is not None:
+        cb.cntc_setpenetration(ire, icp, pen)
+    else:
+        cb.cntc_setnormalforce(ire, icp, fn)
+
+
+def test_steady_rolling_mbench_1c(cb, O, mbench):
+    """perfc_test/tang_problm_1c.inp with the default solver (T=3, SteadyGS) on the 71x81 'right wheel at 6.2 mm' grid:
+    perfc_test/get_times.ref_out:25 gives nslp = 1872, ItGS = 56 -- the device SteadyGS must reproduce both, the
+    element division bit-exactly and the tractions of the oracle."""
+    g = dict(mx=71, my=81, xl=-3.55, yl=-6.15, dx=0.1, dy=0.1, ibase=2, prmudf=np.array(mbench["prmudf"]))
+    ire, icp = 61, 1
+    _setup_rolling(cb, ire, g, cases.STEEL["gg"], cases.STEEL["poiss"], pen=mbench["pen"])
+    cb.cntc_setrollingstepsize(ire, icp, 0.0, 0.1)
+    cb.cntc_setcreepages(ire, icp, 0.0005, 0.0, 0.0003)
+    ierr = cb.cntc_calculate(ire, icp)
+    assert ierr == 0, (ierr, cb.lib.last_error())
+    ref = O.contac(g, cases.STEEL["gg"], cases.STEEL["poiss"], tang=3, norm=0, force3=0, pen=mbench["pen"], cksi=0.0005,
+                   ceta=0.0, cphi=0.0003, fstat=0.3, fkin=0.3, maxgs=1000, maxin=100, maxnr=30, maxout=1, eps=1e-7,
+                   nn=mbench["nn"], chi=0.0, dq=0.1, gausei=0)
+    assert ref["ierror"] == 0 and ref["itgs_tang"] == 56
+    its = cb.lowlevel.get_iterations(ire, icp)
+    el = cb.cntc_getelementdivision(ire, icp).ravel()
+    assert its["itgs"] == 56 and int((el == 2).sum()) == 1872 and int((el >= 1).sum()) == 3148      # golden counts
+    assert np.array_equal(el, ref["el"])
+    pn, px, py = cb.cntc_gettractions(ire, icp)
+    s = np.abs(ref["ps"][:2]).max()
+    assert np.abs(px.ravel() - ref["ps"][0]).max() < 1e-8 * s and np.abs(py.ravel() - ref["ps"][1]).max() < 1e-8 * s
+    fn, tx, ty, mz = cb.cntc_getcontactforces(ire, icp)
+    assert abs(tx / (0.3 * fn) - ref["fx"]) < 1e-9 and abs(ty / (0.3 * fn) - ref["fy"]) < 1e-9
+    sx, sy = cb.cntc_getmicroslip(ire, icp)
+    ssx = ref["ss"][0] / 0.1                                           # relative slip = shift / dq
+    assert np.abs(sx.ravel() - ssx)[el == 2].max() < 1e-7 * np.abs(ssx).max()
+    cb.cntc_finalize(ire)
+
+
+def test_steady_rolling_dissimilar_materials_prescribed_force(cb, O):
+    """T=3, N=1, F=1 on a quadratic gap with dissimilar materials (normal-tangential coupling: the shifted coefficients cv
+    enter the right-hand side, Panagiotopoulos alternation with MAXOUT > 1, Newton-Raphson on CKSI around SteadyGS)."""
+    g = dict(mx=34, my=27, xl=-3.4, yl=-2.7, dx=0.2, dy=0.2, ibase=1, prmudf=[0.004, 0.0, 0.006, 0.0, 0.0, 0.0])
+    gg, poiss = (82000.0, 40000.0), (0.28, 0.35)
+    ire, icp = 62, 1
+    _setup_rolling(cb, ire, g, gg, poiss, fn=9.0e3, fstat=0.25, maxgs=500, maxin=50, maxnr=30, maxout=10, eps=1e-6, force=1)
+    cb.cntc_setrollingstepsize(ire, icp, 0.0, 0.2)
+    cb.cntc_setcreepages(ire, icp, 0.0, 0.0004, 0.0002)
+    cb.cntc_settangentialforces(ire, icp, -0.6, 0.0)
+    ierr = cb.cntc_calculate(ire, icp)
+    assert ierr == 0, (ierr, cb.lib.last_error())
+    ref = O.contac(g, gg, poiss, tang=3, norm=1, force3=1, fn=9.0e3, fxrel=-0.6, ceta=0.0004, cphi=0.0002, fstat=0.25,
+                   fkin=0.25, maxgs=500, maxin=50, maxnr=30, maxout=10, eps=1e-6, chi=0.0, dq=0.2, gausei=0)
+    assert ref["ierror"] == 0
+    its = cb.lowlevel.get_iterations(ire, icp)
+    el = cb.cntc_getelementdivision(ire, icp).ravel()
+    assert its["nr_itcg"] == ref["nr_itcg"][:len(its["nr_itcg"])] and its["itgs"] == ref["itgs_tang"]
+    assert np.array_equal(el, ref["el"])
+    pn, px, py = cb.cntc_gettractions(ire, icp)
+    assert _rel(pn.ravel(), ref["ps"][2]) < 1e-8
+    s = np.abs(ref["ps"][:2]).max()
+    assert np.abs(px.ravel() - ref["ps"][0]).max() < 1e-7 * s and np.abs(py.ravel() - ref["ps"][1]).max() < 1e-7 * s
+    vx, vy, phi = cb.cntc_getcreepages(ire, icp)
+    assert abs(vx - ref["cksi"]) < 1e-7 * abs(ref["cksi"])
+    cb.cntc_finalize(ire)
+
+
+def test_steady_rolling_without_guard_band_is_refused(cb):
+    """Contact reaching the trailing edge of the potential contact area: the reference switches to ConvexGS
+    (m_stang.f90:184-191); this path refuses the case loudly instead of answering with another solver."""
+    g = dict(mx=12, my=9, xl=-0.6, yl=-0.45, dx=0.1, dy=0.1, ibase=1, prmudf=[0.001, 0.0, 0.001, 0.0, 0.0, 0.0])
+    ire, icp = 63, 1
+    _setup_rolling(cb, ire, g, cases.STEEL["gg"], cases.STEEL["poiss"], pen=0.01, eps=1e-5)
+    cb.cntc_setrollingstepsize(ire, icp, 0.0, 0.1)
+    cb.cntc_setcreepages(ire, icp, 0.001, 0.0, 0.0)
+    assert cb.cntc_calculate(ire, icp) == -99 and "ConvexGS" in cb.lib.last_error()
+    cb.cntc_finalize(ire)
