@@ -45,13 +45,30 @@ k_conv_batch_strided(ConvPlan P, const double *p, long pstride, const cd *chat, 
                  el ? mask_mode : 0, add);
 }
 
+// one single-block product on a grid beyond one CTA: three grid-wide phases (rows, columns x C^, inverse rows)
+inline int conv_large_launch(CoefSet &cs, const double *d_p, const cd *chat, double *d_u, const int *d_el, int mask_mode,
+                             int add, cudaStream_t st)
+{
+    Engine &E = engine();
+    const LargePlan &L = cs.lp;
+    RowSrc src;
+    src.base = d_p; src.kind = 0; src.mx = L.P.mx; src.my = L.P.my; src.cmx = 0; src.cmy = 0; src.Fx = L.P.Fx; src.Fy = L.P.Fy; src.row0 = 0;
+    if (!cs.ev_l0) { CB_CUDA(cudaEventCreate(&cs.ev_l0)); CB_CUDA(cudaEventCreate(&cs.ev_l1)); }
+    CB_CUDA(cudaEventRecord(cs.ev_l0, st));
+    k_lg_rows_fwd<<<L.ntr, CB_THREADS, L.smem_bytes, st>>>(L, src, L.P.my, L.RB, cs.d_T, L.ldT);
+    k_lg_cols<<<L.ntc, CB_THREADS, L.smem_bytes, st>>>(L, L.P.my, L.P.my, cs.d_T, L.ldT, chat, nullptr, 1.0);
+    k_lg_rows_inv<<<L.ntr, CB_THREADS, L.smem_bytes, st>>>(L, cs.d_T, d_u, d_el, mask_mode, add);
+    CB_CUDA(cudaEventRecord(cs.ev_l1, st));
+    E.launches += 3;
+    return 0;
+}
+
 // gf3_VecAijPj semantics (m_aijpj.f90:346-395) on device buffers laid out [ncase][3][npot]
 inline int vecaijpj_dev(CoefSet &cs, int set, int ncase, int iigs, int ikarg, int jkarg, const double *d_p,
                         const int *d_el, double *d_u, cudaStream_t st)
 {
     Engine &E = engine();
     const ConvPlan &P = cs.hp.p;
-    if (!cs.hp.fits) { last_error() = "grid too large for the single-CTA product"; return -34; }
     if (iigs != -9 && iigs != -8) { last_error() = "FFT product allowed only for AllElm or AllInt"; return -99; }
     if (!cs.d_cf[set]) { last_error() = "coefficient set not available"; return -99; }
     const int mask_mode = (iigs == -8) ? 1 : 0;
@@ -68,6 +85,15 @@ inline int vecaijpj_dev(CoefSet &cs, int set, int ncase, int iigs, int ikarg, in
             if (!cs.nt_cpl && (ik * jk == 3 || ik * jk == 6)) continue;     // :358-369
             int rc = build_chat(cs, set, ik, jk, st);
             if (rc) return rc;
+            if (!cs.hp.fits) {
+                for (int ic = 0; ic < ncase && !rc; ic++)
+                    rc = conv_large_launch(cs, d_p + ic * cstride + (size_t) (jk - 1) * P.npot, cs.d_chat[set][ik - 1][jk - 1],
+                                           d_u + ic * cstride + (size_t) (ik - 1) * P.npot,
+                                           d_el ? d_el + (size_t) ic * P.npot : nullptr, mask_mode, ladd ? 1 : 0, st);
+                if (rc) return rc;
+                ladd = true;
+                continue;
+            }
             k_conv_batch_strided<<<nblk, CB_THREADS, P.smem_bytes, st>>>(
                 P, d_p + (size_t) (jk - 1) * P.npot, cstride, cs.d_chat[set][ik - 1][jk - 1],
                 d_u + (size_t) (ik - 1) * P.npot, cstride, d_el, mask_mode, ladd ? 1 : 0, ncase);
@@ -128,12 +154,39 @@ __global__ void k_norm_unpack(const NormCase *cases, int ncase, double *scal)
 // u_n = A_zz p_n on the contact area after the solve (soutpt, m_soutpt.f90:378-385), batched
 inline NormBatch &norm_batch() { static NormBatch b; return b; }
 
+// grids beyond one CTA: one cooperative whole-GPU launch per case (cases run one after the other)
+inline int snorm_large_dev(CoefSet &cs, int ncase, NormCase proto, const double *d_hs, int *d_el, double *d_pn,
+                           double *d_un, double *d_scal, cudaStream_t st)
+{
+    Engine &E = engine();
+    NormBatch &B = norm_batch();
+    const LargePlan &L = cs.lp;
+    const int npot = L.P.npot;
+    LargeCtx X;
+    X.L = L; X.T = cs.d_T; X.gpart = cs.d_gpart; X.prof = nullptr;
+    k_norm_pack<<<grid1d(ncase, 128), 128, 0, st>>>(B.d_cases, ncase, npot, d_hs, d_el, d_pn, d_un, d_scal, B.d_work, proto);
+    E.launches++;
+    CB_CUDA(cudaEventRecord(B.ev0, st));
+    for (int ic = 0; ic < ncase; ic++) {
+        NormCase *cp = B.d_cases + ic;
+        double *un = d_un ? d_un + (size_t) ic * npot : nullptr;
+        if (un) CB_CUDA(cudaMemsetAsync(un, 0, sizeof(double) * npot, st));
+        void *args[] = { (void *) &X, (void *) &cp, (void *) &un };
+        CB_CUDA(cudaLaunchCooperativeKernel((void *) k_lg_snorm, dim3(E.num_sms), dim3(CB_THREADS), args, (size_t) L.smem_bytes, st));
+        E.launches++;
+    }
+    CB_CUDA(cudaEventRecord(B.ev1, st));
+    k_norm_unpack<<<grid1d(ncase, 128), 128, 0, st>>>(B.d_cases, ncase, d_scal);
+    E.launches++;
+    CB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 inline int snorm_batch_dev(CoefSet &cs, int ncase, int ic_norm, int maxgs, int maxin, double eps, const double *d_hs,
                            int *d_el, double *d_pn, double *d_un, double *d_scal, cudaStream_t st)
 {
     Engine &E = engine();
     const ConvPlan &P = cs.hp.p;
-    if (!cs.hp.fits) { last_error() = "grid too large for the single-CTA solver"; return -34; }
     int rc;
     if ((rc = build_prec(cs, st))) return rc;
     if ((rc = build_chat(cs, SET_CS, 3, 3, st))) return rc;
@@ -163,6 +216,7 @@ inline int snorm_batch_dev(CoefSet &cs, int ncase, int ic_norm, int maxgs, int m
     proto.ga_inv = cs.ga_inv;
     proto.ic_norm = ic_norm; proto.maxgs = maxgs; proto.maxin = maxin; proto.eps = eps;
     proto.dxdy = cs.key.dx * cs.key.dy;
+    if (!cs.hp.fits) return snorm_large_dev(cs, ncase, proto, d_hs, d_el, d_pn, d_un, d_scal, st);
     k_norm_pack<<<grid1d(ncase, 128), 128, 0, st>>>(B.d_cases, ncase, P.npot, d_hs, d_el, d_pn, d_un, d_scal, B.d_work, proto);
     CB_CUDA(cudaMemsetAsync(B.d_next, 0, sizeof(int), st));
     CB_CUDA(cudaEventRecord(B.ev0, st));
@@ -223,6 +277,14 @@ extern "C" {
 
 const char *cb200_last_error(void) { return last_error().c_str(); }
 long cb200_num_launches(void) { return engine().launches; }
+int cb200_steady_prof(unsigned long long *out, int reset)
+{   // cycle counters of the SteadyGS step, summed over all CTAs since the last reset (see steady_solver.cuh)
+    int rc = engine_init();
+    if (rc) return rc;
+    CB_CUDA(cudaMemcpyFromSymbol(out, g_steady_prof, sizeof(unsigned long long) * 8));
+    if (reset) { unsigned long long z[8] = { 0 }; CB_CUDA(cudaMemcpyToSymbol(g_steady_prof, z, sizeof(z))); }
+    return 0;
+}
 int cb200_num_sms(void) { int rc = engine_init(); return rc ? rc : engine().num_sms; }
 int cb200_opt_fft_size(int n) { return opt_fft_size(n); }
 

@@ -67,6 +67,12 @@ struct CoefSet {
     long n_chat_built = 0;
     // subsurface: transformed coefficients per depth list / material, [nz][4][9][chat_len]
     std::map<std::vector<double>, cd *> subs_chat;
+    // grids beyond one CTA's shared memory (hp.fits == false): whole-GPU plan, spectrum workspace, reduction scratch;
+    // d_chat then holds the transforms in the column-task layout [ntc][Ly][CB]
+    LargePlan lp;
+    cd *d_T = nullptr;
+    double *d_gpart = nullptr;
+    cudaEvent_t ev_l0 = nullptr, ev_l1 = nullptr;   // bracket the three phase kernels of the last stand-alone product
 };
 
 struct Engine {
@@ -101,16 +107,67 @@ inline int engine_init()
     CB_CUDA(cudaFuncSetAttribute(k_build_chat, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     CB_CUDA(cudaFuncSetAttribute(k_subsurf_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     CB_CUDA(cudaFuncSetAttribute(k_contac_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    CB_CUDA(cudaFuncSetAttribute(k_lg_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    CB_CUDA(cudaFuncSetAttribute(k_lg_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    CB_CUDA(cudaFuncSetAttribute(k_lg_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    CB_CUDA(cudaFuncSetAttribute(k_lg_snorm, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     return 0;
 }
 
 inline int grid1d(long n, int b) { return (int) ((n + b - 1) / b); }
+
+// ---- whole-GPU plan for grids that do not fit one CTA ----
+inline bool make_large_plan(const ConvPlan &P, int nsm, LargePlan &L)
+{
+    L.P = P;
+    const int ncol = P.Fx + 1;
+    const long budget = kSmemMax - 1024;
+    L.RB = (P.my + nsm - 1) / nsm;
+    while (L.RB > 1 && (long) (P.Lx + 1) * (L.RB | 1) * 16 > budget) L.RB--;
+    L.CB = (ncol + nsm - 1) / nsm;
+    while (L.CB > 1 && (long) P.Ly * L.CB * 16 > budget) L.CB--;
+    if ((long) (P.Lx + 1) * (L.RB | 1) * 16 > budget || (long) P.Ly * L.CB * 16 > budget) return false;
+    L.ntr = (P.my + L.RB - 1) / L.RB;
+    L.ntc = (ncol + L.CB - 1) / L.CB;
+    L.ldT = P.my;
+    // the coefficient transform runs the row pass over 2Fy rows with the same RB
+    const long sr = (long) (P.Lx + 1) * (L.RB | 1) * 16, sc = (long) P.Ly * L.CB * 16;
+    L.smem_bytes = (int) (sr > sc ? sr : sc) + 1024;
+    L.P.chat_len = L.ntc * P.Ly * L.CB;
+    return true;
+}
+
+inline int build_chat_large(CoefSet &cs, int set, int ik, int jk, cudaStream_t st)
+{
+    Engine &E = engine();
+    const LargePlan &L = cs.lp;
+    const ConvPlan &P = L.P;
+    cd *chat = nullptr, *T2 = nullptr;
+    CB_CUDA(cudaMalloc(&chat, sizeof(cd) * (size_t) P.chat_len));
+    CB_CUDA(cudaMalloc(&T2, sizeof(cd) * (size_t) (P.Lx + 1) * 2 * P.Fy));
+    RowSrc src;
+    src.base = cs.d_cf[set] + (size_t) ((jk - 1) * 3 + (ik - 1)) * 4 * cs.mx * cs.my;
+    src.kind = 1; src.mx = std::min(P.Fx, P.mx); src.my = std::min(P.Fy, P.my); src.cmx = cs.mx; src.cmy = cs.my;
+    src.Fx = P.Fx; src.Fy = P.Fy; src.row0 = 0;
+    const double scale = cs.ga_inv / (4.0 * P.Fx * P.Fy);
+    const int nrows = 2 * P.Fy, ntask = (nrows + L.RB - 1) / L.RB;
+    k_lg_rows_fwd<<<std::min(ntask, 4 * E.num_sms), CB_THREADS, L.smem_bytes, st>>>(L, src, nrows, L.RB, T2, nrows);
+    k_lg_cols<<<L.ntc, CB_THREADS, L.smem_bytes, st>>>(L, nrows, 0, T2, nrows, nullptr, chat, scale);
+    E.launches += 2;
+    CB_CUDA(cudaGetLastError());
+    CB_CUDA(cudaStreamSynchronize(st));
+    CB_CUDA(cudaFree(T2));
+    cs.d_chat[set][ik - 1][jk - 1] = chat;
+    cs.n_chat_built++;
+    return 0;
+}
 
 // ---- coefficient transform of one block ----
 inline int build_chat(CoefSet &cs, int set, int ik, int jk, cudaStream_t st)
 {
     Engine &E = engine();
     if (cs.d_chat[set][ik - 1][jk - 1]) return 0;
+    if (!cs.hp.fits) return build_chat_large(cs, set, ik, jk, st);
     const ConvPlan &P = cs.hp.p;
     cd *chat = nullptr, *SWg = nullptr;
     CB_CUDA(cudaMalloc(&chat, sizeof(cd) * (size_t) P.chat_len));
@@ -196,6 +253,11 @@ inline int get_coefset(int mx, int my, double dx, double dy, Material mat, int i
     CB_CUDA(cudaMemcpyAsync(cs->d_twy, cs->hp.twy.data(), sizeof(cd) * cs->hp.twy.size(), cudaMemcpyHostToDevice, st));
     CB_CUDA(cudaMemcpyAsync(cs->d_posx, cs->hp.posx.data(), sizeof(unsigned short) * cs->hp.posx.size(), cudaMemcpyHostToDevice, st));
     P.twx = cs->d_twx; P.twy = cs->d_twy; P.posx = cs->d_posx;
+    if (!cs->hp.fits) {
+        if (!make_large_plan(P, E.num_sms, cs->lp)) { last_error() = "grid too large for the whole-GPU FFT product"; delete cs; return -34; }
+        CB_CUDA(cudaMalloc(&cs->d_T, sizeof(cd) * (size_t) (P.Lx + 1) * cs->lp.ldT));
+        CB_CUDA(cudaMalloc(&cs->d_gpart, sizeof(double) * 2 * 8 * (size_t) E.num_sms));
+    }
 
     const long nblk = 4L * mx * my;
     CB_CUDA(cudaMalloc(&cs->d_cf[SET_CS], sizeof(double) * 9 * nblk));

@@ -3,6 +3,7 @@
 #include "norm_solver.cuh"
 #include "subsurf.cuh"
 #include "tang_solver.cuh"
+#include "large_solver.cuh"
 
 namespace cb200 {
 

@@ -19,6 +19,10 @@ namespace cb200 {
 
 enum { EL_EXTER = 0, EL_ADHES = 1, EL_SLIP = 2, EL_PLAST = 3 };
 
+// cycle counters of the SteadyGS step (thread 0 of every CTA adds its totals at the end of a solver call):
+// [0] element steps, [1] plstrc, [2] re-integration, [3] waiting + rank-1 updates + hand-over, [4] solver calls
+__device__ unsigned long long g_steady_prof[8];
+
 // plstrc (m_solvpt.f90:3278-3807) without plasticity (tau_c = 1e20, k_tau = 0): el, (px,py), (sx,sy) in/out.
 // c00..c11: 2x2 influence matrix of the element, bound = mus * pn.
 __device__ void plstrc_dev(int &el, double c00, double c01, double c10, double c11, double eps, double omegah,
@@ -34,18 +38,20 @@ __device__ void plstrc_dev(int &el, double c00, double c01, double c10, double c
             const double dinv = 1.0 / (c00 * c11 - c01 * c10);
             const double dx = (-c11 * sx + c01 * sy) * dinv, dy = (c10 * sx - c00 * sy) * dinv;
             px = pox + omegah * dx; py = poy + omegah * dy;
-            const double pa2 = sqrt(px * px + py * py);
-            if (pa2 <= bound) violated = false;
+            const double q2 = px * px + py * py, b2 = bound * bound;           // compare squares: no square root on the
+            if (q2 <= b2) violated = false;                                    // common path
             else {
-                const double fx = pox + dx, fy = poy + dy, pa1 = sqrt(fx * fx + fy * fy);
-                if (pa1 <= bound) { px = px * bound / pa2; py = py * bound / pa2; violated = false; }
+                const double fx = pox + dx, fy = poy + dy;
+                if (fx * fx + fy * fy <= b2) { const double t = bound / sqrt(q2); px *= t; py *= t; violated = false; }
                 else violated = true;
             }
             six = s0x + c00 * px + c01 * py; siy = s0y + c10 * px + c11 * py;
         } else if (el == EL_SLIP) {                                            // |P| = bound, S anti-parallel to P
             violated = false;
-            const double sabs = sqrt(s0x * s0x + s0y * s0y);
-            px = -bound * s0x / sabs; py = -bound * s0y / sabs;
+            // (one reciprocal instead of two divisions here and in the Newton step: a device division costs ~20
+            //  dependent instructions and this code runs on a single thread)
+            const double t0 = -bound / sqrt(s0x * s0x + s0y * s0y);
+            px = t0 * s0x; py = t0 * s0y;
             six = s0x + c00 * px + c01 * py; siy = s0y + c10 * px + c11 * py;
             double f0 = py * six - px * siy, f1 = px * px + py * py - bound * bound;
             int itnr = 0;
@@ -56,18 +62,26 @@ __device__ void plstrc_dev(int &el, double c00, double c01, double c10, double c
                 const double det = g00 * g11 - g01 * g10;
                 if (det == 0.0) itnr = 10;
                 else {
-                    px += -(g11 * f0 - g01 * f1) / det;
-                    py += -(-g10 * f0 + g00 * f1) / det;
+                    const double rdet = 1.0 / det;
+                    px -= (g11 * f0 - g01 * f1) * rdet;
+                    py -= (-g10 * f0 + g00 * f1) * rdet;
                 }
                 six = s0x + c00 * px + c01 * py; siy = s0y + c10 * px + c11 * py;
                 f0 = py * six - px * siy; f1 = px * px + py * py - bound * bound;
             }
-            const double a0 = atan2(poy, pox);                                 // relaxation of the direction, :3612-3619
-            double da = atan2(py, px) - a0;
-            if (da < -pi) da += 2.0 * pi;
-            if (da > pi) da -= 2.0 * pi;
-            const double a1 = a0 + omegas * da;
-            px = bound * cos(a1); py = bound * sin(a1);
+            if (omegas == 1.0) {
+                // relaxation of the direction with omega = 1 (:3612-3619): bound * (cos, sin)(atan2(py, px)) is the
+                // traction scaled back onto the bound -- no trigonometry needed
+                const double t1 = bound / sqrt(px * px + py * py);
+                px *= t1; py *= t1;
+            } else {
+                const double a0 = atan2(poy, pox);
+                double da = atan2(py, px) - a0;
+                if (da < -pi) da += 2.0 * pi;
+                if (da > pi) da -= 2.0 * pi;
+                const double a1 = a0 + omegas * da;
+                px = bound * cos(a1); py = bound * sin(a1);
+            }
             if (fabs(px) > fabs(py)) { if (px * six > 0.0) violated = true; }
             else { if (py * siy > 0.0) violated = true; }
         } else {                                                               // plasticity with an infinite yield limit
@@ -202,6 +216,7 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
 
     int itgs = 0;
     double dif = 2.0, difid = 1.0, dif1 = 0.0;
+    unsigned long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0, tlast = clock64();
     while (dif >= difid && itgs < a.maxgs) {
         itgs++;
         double dsum = 0.0;                                     // thread 0 only
@@ -219,6 +234,8 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
             int ixc = -1;                                      // thread 0: position of the current element
             for (int k = k0; k < k1; k++) {
                 if (tid == 0) {
+                    const unsigned long long ta = clock64();
+                    tp3 += ta - tlast; tp0++;
                     do ixc++; while (s.el[ixc] < 1);
                     const int ix = ixc;
                     int jx = ix - 1;
@@ -236,6 +253,8 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
                     double px = pox, py = poy;
                     int e = s.el[ix];
                     plstrc_dev(e, c00, c01, c01, c11, a.eps, a.omegah, a.omegas, px, py, s.bnd[ix], sx, sy);
+                    const unsigned long long tb = clock64();
+                    tp1 += tb - ta;
                     const double ex = px - pox, ey = py - poy;
                     dsum += ex * ex + ey * ey;
                     int nch = 0;
@@ -248,9 +267,10 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
                         const int ej = s.el[jj];
                         if (ej == EL_ADHES) {
                             double nx = rx + s.dpx[jj], ny = ry + s.dpy[jj];
-                            const double pa = sqrt(nx * nx + ny * ny), pb = fmin(s.bnd[jj], 1e20);
-                            if (pa > pb) {
-                                nx = nx * pb / pa; ny = ny * pb / pa;
+                            const double pa2 = nx * nx + ny * ny, pb = fmin(s.bnd[jj], 1e20);
+                            if (pa2 > pb * pb) {
+                                const double t = pb / sqrt(pa2);
+                                nx *= t; ny *= t;
                                 const double ndx = nx - rx, ndy = ny - ry;
                                 s.chj[nch] = jj; s.chx[nch] = ndx - s.dpx[jj]; s.chy[nch] = ndy - s.dpy[jj]; nch++;
                                 s.dpx[jj] = ndx; s.dpy[jj] = ndy;
@@ -271,6 +291,8 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
                         }
                     }
                     s.ictl[0] = nch;
+                    tlast = clock64();
+                    tp2 += tlast - tb;
                 }
                 __syncthreads();
                 // rank-1 updates of U for every changed dp, all elements
@@ -328,6 +350,10 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
     if (itgs >= a.maxgs && conv > 0.997) info = 2;
     if (itgs >= a.maxgs && conv > 1.0) info = 3;
     itgs_out = itgs; err_out = dif;
+    if (tid == 0) {
+        atomicAdd(&g_steady_prof[0], tp0); atomicAdd(&g_steady_prof[1], tp1); atomicAdd(&g_steady_prof[2], tp2);
+        atomicAdd(&g_steady_prof[3], tp3); atomicAdd(&g_steady_prof[4], 1ull);
+    }
     __syncthreads();
     return info;
 }

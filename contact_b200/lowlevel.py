@@ -30,6 +30,14 @@ def num_launches():
     return load_library().cb200_num_launches()
 
 
+def steady_prof(reset=True):
+    """Cycle counters of the SteadyGS element step: dict(steps, plstrc, reintegrate, update, calls)."""
+    import ctypes as C
+    out = (C.c_ulonglong * 8)()
+    _check(load_library().cb200_steady_prof(out, 1 if reset else 0))
+    return dict(steps=out[0], plstrc=out[1], reintegrate=out[2], update=out[3], calls=out[4])
+
+
 def num_sms():
     return _check(load_library().cb200_num_sms())
 

@@ -126,6 +126,9 @@ int cb200_get_iterations(int ire, int icp, int *out, int lenarr, int *nr_itcg);
 const char *cb200_last_error(void);
 /* number of kernels launched by the library so far (bench.py: "gpu_launches") */
 long cb200_num_launches(void);
+/* cycle counters of the SteadyGS element step summed over all CTAs since the last reset: out[0] element steps,
+ * [1] cycles in the per-element solve (plstrc), [2] re-integration, [3] rank-1 updates + barriers, [4] solver calls */
+int cb200_steady_prof(unsigned long long *out, int reset);
 /* number of SMs of the device in use, or -99 */
 int cb200_num_sms(void);
 

@@ -438,3 +438,82 @@ def test_steady_rolling_without_guard_band_is_refused(cb):
     cb.cntc_setcreepages(ire, icp, 0.001, 0.0, 0.0)
     assert cb.cntc_calculate(ire, icp) == -99 and "ConvexGS" in cb.lib.last_error()
     cb.cntc_finalize(ire)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# grids beyond one CTA's shared memory: whole-GPU product and NORM (perfc_test/norm_problm_{2,4,8}p.inp)
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mx,my", [(143, 163), (120, 135), (48, 650)])
+def test_large_grid_product_matches_oracle(cb, O, mx, my):
+    """The three-phase whole-GPU product (rows -> columns x C^ -> inverse rows over the L2-resident spectrum) against
+    the oracle's FFT product, AllElm and AllInt, single blocks and the 2x2 tangential call."""
+    dx, dy = 0.05, 0.06
+    cset = cb.lowlevel.CoefSet(mx, my, dx, dy)
+    assert cset.plan()["fits"] == 0
+    m = O.mater()
+    cs, cv, csv, ms = O.sgencr(m, mx, my, dx, dy)
+    rng = np.random.default_rng(5)
+    ncase = 2
+    el = (rng.random((ncase, mx * my)) < 0.6).astype(np.int32)
+    p = rng.standard_normal((ncase, 3, mx * my)) * el[:, None, :]
+    for iigs, ikarg, jkarg in ((cb.lowlevel.ALLELM, 3, 3), (cb.lowlevel.ALLINT, 3, 3), (cb.lowlevel.ALLINT, -2, -2)):
+        u0 = rng.standard_normal(p.shape)
+        got = cset.vecaijpj(p, el, iigs=iigs, ikarg=ikarg, jkarg=jkarg, u=u0.copy())
+        for ic in range(ncase):
+            igs = O.EldivBuf(mx, my, el[ic])
+            ref = u0[ic].copy()
+            O.vecaijpj(O.Ctx(fullbox=True), igs, iigs, ref, ikarg, np.ascontiguousarray(p[ic]), jkarg, cs)
+            rows = [2] if ikarg == 3 else [0, 1]
+            assert _rel(got[ic][rows], ref[rows]) < 2e-11, (iigs, ikarg, ic)
+            other = [r for r in range(3) if r not in rows]
+            assert np.array_equal(got[ic][other], u0[ic][other])
+    O.inflcf_free(cs, cv, csv, ms)
+
+
+def _large_norm_case(cb, ire, mbench, mx, my, dx):
+    cb.cntc_initialize(ire, 3)
+    cb.cntc_setflags(ire, 1, [cb.CNTC["ic_tang"], cb.CNTC["ic_iestim"]], [0, 0])
+    cb.cntc_setsolverflags(ire, 1, 0, [1000, 100, 30, 1], [1e-7])
+    cb.cntc_setmaterialparameters(ire, 1, 0, [0.28, 0.28, 82000.0, 82000.0])
+    cb.cntc_setpotcontact(ire, 1, 1, [mx, my, -3.55, -6.15, dx, dx])
+    cb.cntc_setundeformeddistc(ire, 1, 2, np.array(mbench["prmudf"]))
+    cb.cntc_setpenetration(ire, 1, mbench["pen"])
+    ierr = cb.cntc_calculate(ire, 1)
+    assert ierr == 0, (ierr, cb.lib.last_error())
+    its = cb.lowlevel.get_iterations(ire, 1)
+    el = cb.cntc_getelementdivision(ire, 1).ravel()
+    pn, _, _ = cb.cntc_gettractions(ire, 1)
+    un, _, _ = cb.cntc_getdisplacements(ire, 1)
+    h = cb.cntc_getfielddata(ire, 1, cb.CNTC["fld_h"]).ravel()
+    pen = cb.cntc_getpenetration(ire, 1)
+    fn = cb.cntc_getcontactforces(ire, 1)[0]
+    cb.cntc_finalize(ire)
+    return its, el, pn.ravel(), un.ravel(), h, pen, fn
+
+
+@pytest.mark.parametrize("name,mx,my,dx", [("norm_problm_2p", 143, 163, 0.05), ("norm_problm_4p", 287, 323, 0.025)])
+def test_large_grid_norm_matches_oracle_and_golden(cb, O, mbench, name, mx, my, dx):
+    """perfc_test/norm_problm_{2,4}p.inp through cntc_calculate: ncon and ItCG of perfc_test/get_times.ref_out:8-9,
+    element division bit-exact and pressures against the oracle."""
+    import json, os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "get_times.json")))[name]
+    its, el, pn, un, h, pen, fn = _large_norm_case(cb, 71, mbench, mx, my, dx)
+    assert int((el > 0).sum()) == gold["ncon"] and its["itcg"] == gold["itcg"]
+    r = O.norm_case(mx, my, -3.55, -6.15, dx, dx, (82000.0, 82000.0), (0.28, 0.28), 2, mbench["prmudf"], 0,
+                    pen=mbench["pen"], maxgs=1000, maxin=100, eps=1e-7, nn=mbench["nn"])
+    assert np.array_equal(el, r["el"])
+    assert _rel(pn, r["pn"]) < 1e-8
+    # complementarity: zero deformed distance inside the contact area
+    c = el > 0
+    assert np.abs(h[c] + un[c] - pen).max() < 1e-5 * pen
+
+
+def test_large_grid_norm_8p_golden(cb, mbench):
+    """perfc_test/norm_problm_8p.inp (575x647 = 372 025 elements, the grid of tang_problm_8c): ncon = 200980,
+    ItCG = 31 (perfc_test/get_times.ref_out:10); size-independent checks instead of the (slow) oracle."""
+    its, el, pn, un, h, pen, fn = _large_norm_case(cb, 72, mbench, 575, 647, 0.0125)
+    assert int((el > 0).sum()) == 200980 and its["itcg"] == 31
+    c = el > 0
+    assert pn[~c].max() == 0.0 and pn[c].min() >= 0.0
+    assert np.abs(h[c] + un[c] - pen).max() < 1e-5 * pen
+    assert abs(fn - pn.sum() * 0.0125 * 0.0125) < 1e-9 * fn
