@@ -99,6 +99,90 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def mbench_grid(mx=71, my=81, dx=0.1):
+    """The module-3 'right wheel at 6.2 mm' section of the perf suite (perfc_test/norm_problm_*p.inp, tang_problm_*c.inp)."""
+    mb = json.load(open(os.path.join(ROOT, "tests", "golden", "mbench_profile.json")))
+    prm = np.array([mb["nn"], mb["xm"], mb["rm"], mb["y1"], mb["dy1"]] + mb["heights"])
+    return dict(mx=mx, my=my, xl=-3.55, yl=-6.15, dx=dx, dy=dx, ibase=2, prmudf=prm, pen=mb["pen"], nn=mb["nn"])
+
+
+def rolling_sweep_leg(cb, n, rank_offset):
+    """sweep-4096 class: mbench 71x81 grid, steady rolling T=3 (default solver SteadyGS), penetration
+    PEN (1 + 0.1 u) and creepages (2e-3 u, 2e-3 u, 3e-4 u), seed 20240229 -- n cases through cntc_calculate_batch."""
+    g = mbench_grid()
+    u = np.random.default_rng(20240229).uniform(-1.0, 1.0, size=(4096, 4))[rank_offset:rank_offset + n]
+    ires = list(range(1, n + 1))
+    for i, ire in enumerate(ires):
+        cb.cntc_initialize(ire, 3)
+        cb.cntc_setflags(ire, 1, [cb.CNTC["ic_tang"], cb.CNTC["ic_force"], cb.CNTC["ic_iestim"]], [3, 0, 0])
+        cb.cntc_setsolverflags(ire, 1, 0, [999, 100, 30, 1], [1e-5])
+        cb.cntc_setmaterialparameters(ire, 1, 0, [0.28, 0.28, 82000.0, 82000.0])
+        cb.cntc_setfrictionmethod(ire, 1, 0, [0.3, 0.3])
+        cb.cntc_setpotcontact(ire, 1, 1, [g["mx"], g["my"], g["xl"], g["yl"], g["dx"], g["dy"]])
+        cb.cntc_setundeformeddistc(ire, 1, 2, g["prmudf"])
+        cb.cntc_setpenetration(ire, 1, g["pen"] * (1.0 + 0.1 * u[i, 0]))
+        cb.cntc_setrollingstepsize(ire, 1, 0.0, g["dx"])
+        cb.cntc_setcreepages(ire, 1, 2e-3 * u[i, 1], 2e-3 * u[i, 2], 3e-4 * u[i, 3])
+    t0 = time.perf_counter()
+    ierr = cb.cntc_calculate_batch(ires, 1)
+    dt = time.perf_counter() - t0
+    its = [cb.lowlevel.get_iterations(ire, 1)["itgs"] for ire in ires]
+    for ire in ires:
+        cb.cntc_finalize(ire)
+    return {"cases": n, "s": dt, "cases_per_s": n / dt, "mean_itgs": float(np.mean(its)), "errors": int((ierr < 0).sum()),
+            "note": "mbench 71x81, T=3 SteadyGS, eps 1e-5, host buffers through cntc_calculate_batch (one launch)"}
+
+
+def large_grid_leg(cb, torch):
+    """575x647 grid of perfc_test/norm_problm_8p.inp / tang_problm_8c.inp: stand-alone 1x1 products (three grid-wide
+    phases over the L2-resident spectrum) and the whole NORM solve in one cooperative launch."""
+    ll = cb.lowlevel
+    g = mbench_grid(575, 647, 0.0125)
+    npot = g["mx"] * g["my"]
+    cset = ll.CoefSet(g["mx"], g["my"], g["dx"], g["dy"], **cases.STEEL)
+    pl = cset.plan()
+    rng = np.random.default_rng(7)
+    d_p = torch.tensor(rng.standard_normal((1, 3, npot)), device="cuda")
+    d_el = torch.ones((1, npot), dtype=torch.int32, device="cuda")
+    d_u = torch.zeros_like(d_p)
+    for _ in range(3):
+        cset.vecaijpj_dev(d_p, d_el, d_u, iigs=ll.ALLINT, ikarg=3, jkarg=3)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nrep = 40
+    e0.record()
+    for _ in range(nrep):
+        cset.vecaijpj_dev(d_p, d_el, d_u, iigs=ll.ALLINT, ikarg=3, jkarg=3)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / nrep
+    S = (pl["Fx"] + 1) * 2 * pl["Fy"]
+    B = npot * 17 + 16 * S                                   # SURVEY 8(d): 8 npot (nj + ni) + npot + 16 S nb
+    N = 4.0 * pl["Fx"] * pl["Fy"]
+    F = 2 * 2.5 * N * np.log2(N) + 6 * S
+    ire = 900
+    kms = []
+    for _ in range(3):
+        cb.cntc_initialize(ire, 3)
+        cb.cntc_setflags(ire, 1, [cb.CNTC["ic_tang"], cb.CNTC["ic_iestim"]], [0, 0])
+        cb.cntc_setsolverflags(ire, 1, 0, [1000, 100, 30, 1], [1e-7])
+        cb.cntc_setmaterialparameters(ire, 1, 0, [0.28, 0.28, 82000.0, 82000.0])
+        cb.cntc_setpotcontact(ire, 1, 1, [g["mx"], g["my"], g["xl"], g["yl"], g["dx"], g["dy"]])
+        cb.cntc_setundeformeddistc(ire, 1, 2, g["prmudf"])
+        cb.cntc_setpenetration(ire, 1, g["pen"])
+        t0 = time.perf_counter()
+        ierr = cb.cntc_calculate(ire, 1)
+        wall = time.perf_counter() - t0
+        its = ll.get_iterations(ire, 1)
+        kms.append(ll.snorm_kernel_ms())
+        cb.cntc_finalize(ire)
+    return {"grid": "575x647", "product_us": us, "alg_bytes_per_product": B, "alg_GBps": B / us * 1e-3,
+            "nominal_flops_per_product": F, "nominal_TFLOPs": F / us * 1e-6,
+            "norm_8p": {"ierror": int(ierr), "ncon": its["ncon"], "itcg": its["itcg"], "solver_kernel_ms": float(np.min(kms)),
+                        "cntc_calculate_wall_ms": wall * 1e3,
+                        "golden": "perfc_test/get_times.ref_out:10 ncon 200980, ItCG 31, 17.6 s (2016 host)"}}
+
+
 def initial_state(g, fns):
     """Host-side solver inputs of each case: gap h, initial element division and pressure (zero)."""
     import contact_b200  # noqa: F401
@@ -192,6 +276,7 @@ def run_gpu(args):
         step_device()
         kt.append(ll.snorm_kernel_ms())
     kernel_ms = float(np.mean(kt))
+    cprof = ll.conv_prof()
     table = scheduler.gather_case_results(d_scal, ncase * world)   # the only collective: final gather of per-case results
     scal = d_scal.cpu().numpy()
     assert table.shape[0] == ncase * world
@@ -212,6 +297,10 @@ def run_gpu(args):
     torch.cuda.synchronize()
     subs_ms = s0.elapsed_time(s1) / 2
     clocks = sampler.stop() if rank == 0 else None
+    # ---- secondary legs: rolling sweep (every rank its own shard) and the 575x647 grid (rank 0) ----
+    nroll = nsm if args.cases <= 0 else min(args.cases, nsm)
+    roll = rolling_sweep_leg(cb, nroll, (rank * nroll) % (4096 - nroll)) if not args.skip_extra else None
+    large = large_grid_leg(cb, torch) if (rank == 0 and not args.skip_extra) else None
 
     # ---- end-to-end leg (host buffers through the C-ABI) ----
     for _ in range(max(1, min(args.warmup, 2))):
@@ -224,7 +313,8 @@ def run_gpu(args):
     barrier()
     e2e_s = time.perf_counter() - t0
 
-    t = torch.tensor([ms_total, e2e_s, kernel_ms, nprod], dtype=torch.float64, device=dev)
+    roll_s = roll["s"] if roll else 0.0
+    t = torch.tensor([ms_total, e2e_s, kernel_ms, nprod, roll_s], dtype=torch.float64, device=dev)
     tmax = t.clone()
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -234,6 +324,8 @@ def run_gpu(args):
     else:
         nprod_all = nprod
     ms_total, e2e_s, kernel_ms = float(tmax[0]), float(tmax[1]), float(tmax[2])
+    if roll:
+        roll["cases_per_s"] = roll["cases"] * world / float(tmax[4]); roll["cases_total"] = roll["cases"] * world
 
     if rank == 0:
         peaks = {}
@@ -268,11 +360,20 @@ def run_gpu(args):
                               "frac": fp64_ach / fp64_peak if fp64_peak > 0 else None,
                               "peak_source": "measured here with a DFMA chain kernel (cb200_fp64_peak_tflops)"},
             "kernel_ms": kernel_ms, "products_per_step": nprod_all, "mean_itcg": itcg_mean,
+            "cta0_cycles": {"per_product": cprof["conv_cycles"] / max(1, cprof["products"]),
+                            "conv_share_of_kernel": cprof["conv_cycles"] / max(1, cprof["kernel_cycles"]),
+                            "note": "clock64 counters of CTA 0 over the whole run"},
             "subsurf": {"cases": nsub, "depths": len(SUBS_Z), "points_per_case": npot * len(SUBS_Z),
                         "products": nsub * len(SUBS_Z) * 36, "ms": subs_ms, "cases_per_s": nsub / (subs_ms * 1e-3),
                         "note": "ISUBS=5 block of spence71_8281pt.inp on the solved pressures of this rank; "
                                 "coefficient transforms cached per (grid, material, z)"},
         }
+        if roll:
+            out["rolling_sweep"] = roll
+        if large:
+            large["frac_hbm"] = large["alg_GBps"] / hbm_peak
+            large["frac_fp64"] = large["nominal_TFLOPs"] / fp64_peak if fp64_peak > 0 else None
+            out["large_grid"] = large
         if args.cpu_seconds > 0:
             out["cpu_baseline"] = cpu_baseline(args.cpu_seconds, threads=1)
         print(json.dumps(out))
@@ -299,7 +400,15 @@ def cpu_baseline(budget_s, threads):
     ps1 = np.zeros((3, g["mx"] * g["my"])); ps1[2] = r["pn"][0]
     O.subsurf_block(g["mx"], g["my"], g["dx"], g["dy"], cases.STEEL["gg"], cases.STEEL["poiss"], el1, ps1, SUBS_Z)
     dts = time.perf_counter() - t1
+    gm = mbench_grid()
+    t2 = time.perf_counter()
+    rr = O.contac(gm, cases.STEEL["gg"], cases.STEEL["poiss"], tang=3, norm=0, force3=0, pen=gm["pen"], cksi=0.0005, ceta=0.0,
+                  cphi=0.0003, fstat=0.3, fkin=0.3, maxgs=999, maxin=100, maxnr=30, maxout=1, eps=1e-5, nn=gm["nn"], chi=0.0,
+                  dq=0.1, gausei=0)
+    dtr = time.perf_counter() - t2
     return {"value": ns / dt, "unit": UNIT, "cores": threads, "kind": "port", "subsurf_cases_per_s": 1.0 / dts,
+            "rolling_cases_per_s": 1.0 / dtr, "rolling_sample": "tang_problm_1c creepages on mbench 71x81, T=3 SteadyGS, eps 1e-5, "
+                                                              "%d sweeps, %.2f s" % (rr["itgs_tang"], dtr),
             "sample": "%d hertz-91 cases (first of the seeded sweep), %.1f s wall; CPU restatement of the reference "
                       "algorithm (oracle/), gcc -O2, own mixed-radix FFT instead of MKL" % (ns, dt),
             "mean_itcg": float(r["itcg"].mean())}
@@ -347,6 +456,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cases", type=int, default=0, help="cases per GPU per step (default 8 x SM count)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg (0 = skip)")
+    ap.add_argument("--skip-extra", action="store_true", help="skip the rolling-sweep and 575x647 legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

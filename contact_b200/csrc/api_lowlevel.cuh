@@ -277,6 +277,14 @@ extern "C" {
 
 const char *cb200_last_error(void) { return last_error().c_str(); }
 long cb200_num_launches(void) { return engine().launches; }
+int cb200_conv_prof(unsigned long long *out, int reset)
+{   // cycle counters of CTA 0: out[0] products, [1] cycles inside the fused product, [2] cycles of k_snorm_batch
+    int rc = engine_init();
+    if (rc) return rc;
+    CB_CUDA(cudaMemcpyFromSymbol(out, g_conv_prof, sizeof(unsigned long long) * 4));
+    if (reset) { unsigned long long z[4] = { 0 }; CB_CUDA(cudaMemcpyToSymbol(g_conv_prof, z, sizeof(z))); }
+    return 0;
+}
 int cb200_steady_prof(unsigned long long *out, int reset)
 {   // cycle counters of the SteadyGS step, summed over all CTAs since the last reset (see steady_solver.cuh)
     int rc = engine_init();

@@ -36,6 +36,10 @@ __device__ __forceinline__ void smem_load_tables(const ConvPlan &P, const Smem &
     __syncthreads();
 }
 
+// cycle counters of CTA 0 (development aid, read with cb200_conv_prof): [0] products, [1] cycles inside conv_dev,
+// [2] cycles of the whole solver kernels
+__device__ unsigned long long g_conv_prof[4];
+
 #define CB_PHASE(call) do { call; __syncthreads(); } while (0)
 #include "conv_sequence.inc"
 
@@ -44,6 +48,7 @@ __device__ __noinline__ void conv_dev(const ConvPlan &P, const Smem &sm, const d
                                          double *u, const int *el, int mask_mode, int add)
 {
     const int tid = threadIdx.x, nthr = blockDim.x;
+    const long long t_in = (tid == 0 && blockIdx.x == 0) ? clock64() : 0;
     // re-derive the pointers from the shared-window address: the compiler then proves the state space and emits
     // LDS/STS (the generic pointers in Smem travel through a non-inlined call and would become generic LD/ST)
     typedef MemBuf<cd> CB_BUF;
@@ -59,6 +64,7 @@ __device__ __noinline__ void conv_dev(const ConvPlan &P, const Smem &sm, const d
     CB_CONV_COLUMNS_PRODUCT(P.my, chat);
     CB_CONV_INVERSE_ROWS(P.my);
     CB_PHASE(row_store(P, BUF, oS, SY, u, el, mask_mode, add, tid, nthr));
+    if (tid == 0 && blockIdx.x == 0) { g_conv_prof[0] += 1; g_conv_prof[1] += (unsigned long long) (clock64() - t_in); }
 }
 
 // ---- deterministic block reductions (fixed shuffle tree; result broadcast to all threads) ----

@@ -144,6 +144,7 @@ k_snorm_batch(ConvPlan P, NormCase *cases, int ncase, int *next_case)
     const Smem sm = smem_view(P, smem_raw);
     smem_load_tables(P, sm);
     volatile int *s_case_p = reinterpret_cast<volatile int *>(sm.red + 127);   // last slot of the reduction scratch
+    const long long t_in = clock64();
     // dynamic case queue: iteration counts differ between cases, so CTAs pull the next case when they finish one
     for (;;) {
         if (threadIdx.x == 0) *s_case_p = atomicAdd(next_case, 1);
@@ -154,6 +155,7 @@ k_snorm_batch(ConvPlan P, NormCase *cases, int ncase, int *next_case)
         snorm_dev(P, sm, cases[ic]);
         __syncthreads();
     }
+    if (threadIdx.x == 0 && blockIdx.x == 0) g_conv_prof[2] += (unsigned long long) (clock64() - t_in);
 }
 
 // ---- batched contact cases (NORM + TANG alternation), one CTA per case, dynamic queue ----

@@ -30,6 +30,14 @@ def num_launches():
     return load_library().cb200_num_launches()
 
 
+def conv_prof(reset=True):
+    """Cycle counters of CTA 0: dict(products, conv_cycles, kernel_cycles)."""
+    import ctypes as C
+    out = (C.c_ulonglong * 4)()
+    _check(load_library().cb200_conv_prof(out, 1 if reset else 0))
+    return dict(products=out[0], conv_cycles=out[1], kernel_cycles=out[2])
+
+
 def steady_prof(reset=True):
     """Cycle counters of the SteadyGS element step: dict(steps, plstrc, reintegrate, update, calls)."""
     import ctypes as C
