@@ -219,39 +219,6 @@ inline void roll_stepsize(const Problem &p, double &chi, double &dq)
 }
 
 
-// frictionless case on a grid that needs the whole GPU: NORM + u_n in one cooperative launch
-inline int calculate_large_norm(Problem &p, CoefSet &cs, const std::vector<double> &hs, const std::vector<int> &el0, double pen0)
-{
-    const int npot = p.mx * p.my;
-    double *d_hs = nullptr, *d_pn = nullptr, *d_un = nullptr, *d_scal = nullptr; int *d_el = nullptr;
-    auto cleanup = [&]() { cudaFree(d_hs); cudaFree(d_pn); cudaFree(d_un); cudaFree(d_scal); cudaFree(d_el); };
-    if (cudaMalloc(&d_hs, sizeof(double) * npot) != cudaSuccess || cudaMalloc(&d_pn, sizeof(double) * npot) != cudaSuccess ||
-        cudaMalloc(&d_un, sizeof(double) * npot) != cudaSuccess || cudaMalloc(&d_scal, sizeof(double) * 8) != cudaSuccess ||
-        cudaMalloc(&d_el, sizeof(int) * npot) != cudaSuccess) { cleanup(); last_error() = "device allocation failed"; return CNTC_err_other; }
-    double scal[8] = { pen0, p.fntrue, 0, 0, 0, 0, 0, 0 };
-    cudaMemcpy(d_hs, hs.data(), sizeof(double) * npot, cudaMemcpyHostToDevice);
-    cudaMemcpy(d_el, el0.data(), sizeof(int) * npot, cudaMemcpyHostToDevice);
-    cudaMemcpy(d_pn, p.ps.data() + 2 * (size_t) npot, sizeof(double) * npot, cudaMemcpyHostToDevice);
-    cudaMemcpy(d_scal, scal, sizeof(scal), cudaMemcpyHostToDevice);
-    int rc = snorm_batch_dev(cs, 1, p.norm, p.maxgs, p.maxin, p.eps, d_hs, d_el, d_pn, d_un, d_scal, 0);
-    if (!rc && cudaDeviceSynchronize() != cudaSuccess) { last_error() = std::string("k_lg_snorm: ") + cudaGetErrorString(cudaGetLastError()); rc = CNTC_err_other; }
-    if (rc) { cleanup(); return rc; }
-    p.el.resize(npot); p.ps.assign(3 * (size_t) npot, 0.0); p.us.assign(3 * (size_t) npot, 0.0); p.ss.assign(3 * (size_t) npot, 0.0);
-    p.hs.assign(3 * (size_t) npot, 0.0);
-    std::copy(hs.begin(), hs.end(), p.hs.begin() + 2 * (size_t) npot);
-    cudaMemcpy(p.el.data(), d_el, sizeof(int) * npot, cudaMemcpyDeviceToHost);
-    cudaMemcpy(p.ps.data() + 2 * (size_t) npot, d_pn, sizeof(double) * npot, cudaMemcpyDeviceToHost);
-    cudaMemcpy(p.us.data() + 2 * (size_t) npot, d_un, sizeof(double) * npot, cudaMemcpyDeviceToHost);
-    cudaMemcpy(scal, d_scal, sizeof(scal), cudaMemcpyDeviceToHost);
-    cleanup();
-    p.pen = scal[0]; p.fntrue = scal[1]; p.itcg = (int) scal[2]; p.itnorm = (int) scal[3]; p.ncon = (int) scal[4]; p.status = (int) scal[5];
-    p.ittang = 0; p.itgs = 0; p.nadh = p.ncon; p.nslip = 0; p.nr_itcg.clear();
-    p.fcntc[0] = p.fcntc[1] = 0.0; p.fcntc[2] = p.fntrue; p.mztrue = 0.0;
-    p.solved = true;
-    if (p.itnorm < 0 || (p.status & 1)) return CNTC_err_norm;
-    return count_at_boundary(p);
-}
-
 // contac (m_scontc.f90:37-216) for a batch of problems: host set-up, ONE device launch per coefficient class, gather
 inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int> &ierr)
 {
@@ -284,12 +251,8 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
         roll_stepsize(p, chi_e, dq_e);
         int rc = get_coefset(p.mx, p.my, p.dx, p.dy, p.mat, p.tang == 3 ? 1 : 0, chi_e, dq_e, 0, &cs);
         if (rc) { ierr[k] = rc; continue; }
-        if (!cs->hp.fits) {
-            // grid beyond one CTA's shared memory: the whole-GPU path serves the normal problem
-            if (p.tang != 0) { last_error() = "grid too large for the single-CTA tangential solvers (the whole-GPU path serves T=0)"; ierr[k] = CNTC_err_discr; continue; }
-            ierr[k] = calculate_large_norm(p, *cs, hs[k], el0[k], pen);
-            continue;
-        }
+        // grids beyond one CTA's shared memory go to the whole-GPU path, which serves T = 0 and T = 1 (TangCG)
+        if (!cs->hp.fits && p.tang == 3) { last_error() = "grid too large for the single-CTA SteadyGS solver (the whole-GPU path serves T=0 and T=1)"; ierr[k] = CNTC_err_discr; continue; }
         groups[cs].push_back(k);
     }
     for (auto &g : groups) {
@@ -375,8 +338,19 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
         cudaMemset(d_buf + 6 * (size_t) npot, 0, 0);
         cudaMemcpy(d_cases, hc.data(), sizeof(ContactCase) * n, cudaMemcpyHostToDevice);
         cudaMemset(d_next, 0, sizeof(int));
-        k_contac_batch<<<launch_blocks(n), CB_THREADS, P.smem_bytes>>>(P, d_cases, n, d_next);
-        engine().launches++;
+        if (cs.hp.fits) {
+            k_contac_batch<<<launch_blocks(n), CB_THREADS, P.smem_bytes>>>(P, d_cases, n, d_next);
+            engine().launches++;
+        } else {
+            LargeCtx X;
+            X.L = cs.lp; X.T = cs.d_T; X.gpart = cs.d_gpart; X.prof = nullptr;
+            for (int i = 0; i < n; i++) {                              // one cooperative whole-GPU launch per case
+                ContactCase *cp = d_cases + i;
+                void *args[] = { (void *) &X, (void *) &cp };
+                cudaLaunchCooperativeKernel((void *) k_lg_contac, dim3(engine().num_sms), dim3(CB_THREADS), args, (size_t) cs.lp.smem_bytes, 0);
+                engine().launches++;
+            }
+        }
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { last_error() = std::string("k_contac_batch: ") + cudaGetErrorString(e); fail(CNTC_err_other); }
         else {

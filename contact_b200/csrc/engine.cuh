@@ -111,6 +111,7 @@ inline int engine_init()
     CB_CUDA(cudaFuncSetAttribute(k_lg_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     CB_CUDA(cudaFuncSetAttribute(k_lg_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     CB_CUDA(cudaFuncSetAttribute(k_lg_snorm, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    CB_CUDA(cudaFuncSetAttribute(k_lg_contac, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     return 0;
 }
 

@@ -172,7 +172,7 @@ k_contac_batch(ConvPlan P, ContactCase *cases, int ncase, int *next_case)
         const int ic = *s_case_p;
         __syncthreads();
         if (ic >= ncase) break;
-        panprc_dev(P, sm, cases[ic]);
+        panprc_dev(BlockCtx{ P, sm }, cases[ic]);
         __syncthreads();
     }
 }

@@ -15,7 +15,7 @@
 // reductions), so there is no host round trip per iteration.
 #pragma once
 #include <cooperative_groups.h>
-#include "norm_solver.cuh"
+#include "tang_solver.cuh"
 
 namespace cb200 {
 namespace cg = cooperative_groups;
@@ -415,7 +415,7 @@ __device__ int lg_normcg(const LargeCtx &X, uint32_t a0, double *red, const Norm
 }
 
 // snorm (m_snorm.f90:31-378) on the whole GPU
-__device__ void lg_snorm(const LargeCtx &X, uint32_t a0, double *red, NormCase &c, cg::grid_group &grid)
+__device__ void lg_snorm(const LargeCtx &X, uint32_t a0, double *red, NormCase &c, int &phase, cg::grid_group &grid)
 {
     const ConvPlan &P = X.L.P;
     const int n = P.npot;
@@ -424,7 +424,7 @@ __device__ void lg_snorm(const LargeCtx &X, uint32_t a0, double *red, NormCase &
     int *el = c.el;
     double *ps = c.pn;
     double pen = c.pen;
-    int nprod = 0, phase = 0;
+    int nprod = 0;
 
     if (c.chatA31 != nullptr && c.ptx != nullptr) {                   // :112-119 hstot = hs + A_zt p_t
         lg_conv(X, a0, c.ptx, c.chatA31, tmp, el, 0, 0, grid);
@@ -490,10 +490,45 @@ k_lg_snorm(LargeCtx X, NormCase *cp, double *un)
     const uint32_t a0 = (uint32_t) __cvta_generic_to_shared(smem_raw);
     double *red = reinterpret_cast<double *>(smem_raw + X.L.smem_bytes - 1024);
     NormCase c = *cp;
+    int phase = 0;
     grid.sync();                                                      // everybody has read the case before it is updated
-    lg_snorm(X, a0, red, c, grid);
+    lg_snorm(X, a0, red, c, phase, grid);
     if (blockIdx.x == 0 && threadIdx.x == 0) *cp = c;
     if (un) lg_conv(X, a0, c.pn, c.chatA, un, c.el, 1, 0, grid);      // soutpt: u_n = A_zz p_n on the contact area
+}
+
+// execution context "whole GPU per problem" for the solver text of tang_solver.cuh (see BlockCtx there)
+struct GridCtx {
+    const LargeCtx &X;
+    uint32_t a0;
+    double *redp;
+    cg::grid_group &grid;
+    int &phase;
+    static constexpr bool kBlock = false;
+    __device__ __forceinline__ int n() const { return X.L.P.npot; }
+    __device__ __forceinline__ const ConvPlan &plan() const { return X.L.P; }
+    __device__ __forceinline__ double *red() const { return redp; }
+    __device__ __forceinline__ size_t first() const { return (size_t) blockIdx.x * blockDim.x + threadIdx.x; }
+    __device__ __forceinline__ size_t stride() const { return (size_t) gridDim.x * blockDim.x; }
+    __device__ __forceinline__ bool leader() const { return blockIdx.x == 0 && threadIdx.x == 0; }
+    __device__ __forceinline__ void sync() const { grid.sync(); }
+    template <int N> __device__ __forceinline__ void sum(double (&v)[N]) const { grid_sum<N>(v, redp, X.gpart, phase, grid); }
+    __device__ __forceinline__ void conv(const double *p, const cd *chat, double *u, const int *el, int mask_mode, int add) const
+    { lg_conv(X, a0, p, chat, u, el, mask_mode, add, grid); }
+    __device__ __forceinline__ void snorm(NormCase &c) const { lg_snorm(X, a0, redp, c, phase, grid); grid.sync(); }
+};
+
+// one contact case (NORM / TANG alternation: T = 0 or shifts T = 1 with TangCG) on the whole GPU
+__global__ void __launch_bounds__(CB_THREADS, 1)
+k_lg_contac(LargeCtx X, ContactCase *cp)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cg::grid_group grid = cg::this_grid();
+    const uint32_t a0 = (uint32_t) __cvta_generic_to_shared(smem_raw);
+    double *red = reinterpret_cast<double *>(smem_raw + X.L.smem_bytes - 1024);
+    int phase = 0;
+    const GridCtx x = { X, a0, red, grid, phase };
+    panprc_dev(x, *cp);
 }
 
 }  // namespace cb200

@@ -42,65 +42,90 @@ struct ContactCase {
     int tstatus;                    // bit 0: the case needs a solver outside this path (ConvexGS / GDsteady)
 };
 
+// Execution context of the solver code below: one CTA per problem (BlockCtx, the batched path) or the whole GPU per
+// problem (GridCtx in large_solver.cuh).  The solver text is written once against this interface: element loops run
+// from first() with stride(), sum<N>() is a fixed-order reduction whose result every thread receives, sync() orders
+// element passes against products, conv() is the influence product.
+struct BlockCtx {
+    const ConvPlan &P;
+    const Smem &sm;
+    static constexpr bool kBlock = true;
+    __device__ __forceinline__ int n() const { return P.npot; }
+    __device__ __forceinline__ const ConvPlan &plan() const { return P; }
+    __device__ __forceinline__ const Smem &smem() const { return sm; }
+    __device__ __forceinline__ double *red() const { return sm.red; }
+    __device__ __forceinline__ size_t first() const { return threadIdx.x; }
+    __device__ __forceinline__ size_t stride() const { return blockDim.x; }
+    __device__ __forceinline__ bool leader() const { return threadIdx.x == 0; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+    template <int N> __device__ __forceinline__ void sum(double (&v)[N]) const { block_sum<N>(v, sm.red); }
+    __device__ __forceinline__ void conv(const double *p, const cd *chat, double *u, const int *el, int mask_mode, int add) const
+    { conv_dev(P, sm, p, chat, u, el, mask_mode, add); }
+    __device__ __forceinline__ void snorm(NormCase &c) const { snorm_dev(P, sm, c); __syncthreads(); }
+};
+
 // u(ik) = sum_jk A(ik,jk) p(jk) over the given direction ranges, masked (AllInt when el given), blocks with a null
 // transform are skipped (no normal-tangential coupling: m_aijpj.f90:358-369); returns the number of products done
-__device__ int conv_multi(const ConvPlan &P, const Smem &sm, const cd *(&chat)[3][3], const double *p, int jk0, int jk1,
+template <class X>
+__device__ int conv_multi(const X &x, const cd *(&chat)[3][3], const double *p, int jk0, int jk1,
                           double *u, int ik0, int ik1, const int *el, int mask_mode)
 {
-    const int n = P.npot;
+    const int n = x.n();
     int np = 0;
     for (int ik = ik0; ik <= ik1; ik++) {
         bool ladd = false;
         for (int jk = jk0; jk <= jk1; jk++) {
             if (chat[ik][jk] == nullptr) continue;
-            conv_dev(P, sm, p + (size_t) jk * n, chat[ik][jk], u + (size_t) ik * n, el, mask_mode, ladd ? 1 : 0);
+            x.conv(p + (size_t) jk * n, chat[ik][jk], u + (size_t) ik * n, el, mask_mode, ladd ? 1 : 0);
             ladd = true; np++;
         }
         if (!ladd) {
-            for (int i = threadIdx.x; i < n; i += blockDim.x) if (mask_mode == 0 || el[i] >= 1) u[(size_t) ik * n + i] = 0.0;
-            __syncthreads();
+            for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) if (mask_mode == 0 || el[i] >= 1) u[(size_t) ik * n + i] = 0.0;
+            x.sync();
         }
     }
     return np;
 }
 
-__device__ __forceinline__ void count_el(const int *el, int n, double *red, int &nadh, int &nslip)
+template <class X>
+__device__ __forceinline__ void count_el(const X &x, const int *el, int n, int &nadh, int &nslip)
 {
     double c[2] = { 0.0, 0.0 };
-    for (int i = threadIdx.x; i < n; i += blockDim.x) { const int e = el[i]; if (e == 1) c[0] += 1.0; else if (e >= 2) c[1] += 1.0; }
-    block_sum<2>(c, red);
+    for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) { const int e = el[i]; if (e == 1) c[0] += 1.0; else if (e >= 2) c[1] += 1.0; }
+    x.template sum<2>(c);
     nadh = (int) c[0]; nslip = (int) c[1];
 }
 
 // m_solvpt.f90:1841-2442 (elastic material).  ws: [2][n] right-hand side; mu = fstat (uniform).
-__device__ void tangcg_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, const double *ws, int maxcg, double eps,
+template <class X>
+__device__ void tangcg_dev(const X &x, ContactCase &c, const double *ws, int maxcg, double eps,
                            int &itcg_out, double &err_out, int &nprod)
 {
-    const int n = P.npot, tid = threadIdx.x, nt = blockDim.x;
+    const int n = x.n();
     int *el = c.nrm.el;
-    double *ps = c.ps, *psn = c.ps + 2 * (size_t) n, *ss = c.ss, *red = sm.red;
+    double *ps = c.ps, *psn = c.ps + 2 * (size_t) n, *ss = c.ss;
     double *g = c.twork, *nx = g + n, *ny = nx + n, *r = ny + n, *z = r + 2 * n, *v = z + 2 * n, *q = v + 2 * n,
            *pold = q + 2 * n;
     const double small = 1e-6, ga = c.ga, c11 = c.c11, c22 = c.c22, mu = c.fstat;
     const int num_inn = 4;
     int nadh, nslip;
-    count_el(el, n, red, nadh, nslip);
+    count_el(x, el, n, nadh, nslip);
     const double facnel = (double) sqrtf(__fdiv_rn((float) n, (float) (nadh + nslip)));      // REAL(4) arithmetic, :1948
     bool use_fftprec = true, lchanged = false;
     int itcg = 0, it_inn = 0;
     double alpha = 0.0, dif = 2.0, difid = 1.0, difinn = 0.0, trsinn = 0.0;
 
     // g, n, t; ss = A ps + ws on C; r = -ss projected on the tangent in S
-    for (int i = tid; i < n; i += nt) {
+    for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) {
         g[i] = mu * psn[i];
         const double a = atan2(ps[n + i], ps[i]);
         nx[i] = cos(a); ny[i] = sin(a);
         ss[i] = 0.0; ss[n + i] = 0.0;
         v[i] = 0.0; v[n + i] = 0.0; q[i] = 0.0; q[n + i] = 0.0; z[i] = 0.0; z[n + i] = 0.0; pold[i] = 0.0; pold[n + i] = 0.0;
     }
-    __syncthreads();
-    nprod += conv_multi(P, sm, c.chatA, ps, 0, 1, ss, 0, 1, el, 1);
-    for (int i = tid; i < n; i += nt) {
+    x.sync();
+    nprod += conv_multi(x, c.chatA, ps, 0, 1, ss, 0, 1, el, 1);
+    for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) {
         const int e = el[i];
         double sx = ss[i], sy = ss[n + i];
         if (e >= 1) { sx += ws[i]; sy += ws[n + i]; ss[i] = sx; ss[n + i] = sy; }
@@ -108,22 +133,22 @@ __device__ void tangcg_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, co
         if (e == 2) { const double tx = -ny[i], ty = nx[i], perp = tx * rx + ty * ry; rx = perp * tx; ry = perp * ty; }
         r[i] = rx; r[n + i] = ry;
     }
-    __syncthreads();
+    x.sync();
 
     while ((lchanged || dif > difid) && itcg < maxcg) {
         itcg++; it_inn++;
         if (use_fftprec) {
-            if (nslip > 3 * nadh && P.my > 1) use_fftprec = false;
+            if (nslip > 3 * nadh && x.plan().my > 1) use_fftprec = false;
             if (itcg >= maxcg / 2) use_fftprec = false;
             if (!use_fftprec) lchanged = true;
         }
         if (use_fftprec) {
-            conv_dev(P, sm, r, c.chatM11, z, el, 1, 0);
-            conv_dev(P, sm, r + n, c.chatM22, z + n, el, 1, 0);
+            x.conv(r, c.chatM11, z, el, 1, 0);
+            x.conv(r + n, c.chatM22, z + n, el, 1, 0);
             nprod += 2;
         }
         double d2[2] = { 0.0, 0.0 };
-        for (int i = tid; i < n; i += nt) {                                   // diagonal scaling + tangent projection
+        for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) {                                   // diagonal scaling + tangent projection
             const int e = el[i];
             double zx = use_fftprec ? z[i] : r[i], zy = use_fftprec ? z[n + i] : r[n + i];
             if (e == 2) {
@@ -136,22 +161,22 @@ __device__ void tangcg_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, co
             d2[0] += zx * q[i] + zy * q[n + i];
             d2[1] += v[i] * q[i] + v[n + i] * q[n + i];
         }
-        block_sum<2>(d2, red);
+        x.template sum<2>(d2);
         double beta = 0.0;
         const bool restart = (itcg <= 1 || lchanged);
         if (!restart) {
             const double zq = d2[0], vq = d2[1];
             if (fabs(zq) < 1e-60 || fabs(vq) < small * fabs(zq)) beta = 0.0; else beta = -zq / vq;
         }
-        for (int i = tid; i < n; i += nt) {
+        for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) {
             if (restart) { v[i] = z[i]; v[n + i] = z[n + i]; }
             else { v[i] = beta * v[i] + z[i]; v[n + i] = beta * v[n + i] + z[n + i]; }
         }
-        __syncthreads();
+        x.sync();
 
-        nprod += conv_multi(P, sm, c.chatA, v, 0, 1, q, 0, 1, el, 1);          // q = A_tt v on C
+        nprod += conv_multi(x, c.chatA, v, 0, 1, q, 0, 1, el, 1);          // q = A_tt v on C
         double d3[3] = { 0.0, 0.0, 0.0 };
-        for (int i = tid; i < n; i += nt) {
+        for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) {
             double qx = q[i], qy = q[n + i];
             const double vx = v[i], vy = v[n + i];
             if (el[i] == 2) {
@@ -165,12 +190,12 @@ __device__ void tangcg_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, co
             d3[1] += vx * qx + vy * qy;
             d3[2] += vx * vx + vy * vy;
         }
-        block_sum<3>(d3, red);
+        x.template sum<3>(d3);
         const double rv = d3[0], vq = d3[1];
         if (fabs(rv) < 1e-60) alpha = 0.0; else if (fabs(vq) < small * fabs(rv)) alpha = 1.0; else alpha = rv / vq;
 
         double p2[1] = { 0.0 };
-        for (int i = tid; i < n; i += nt) {                                   // :2170-2185
+        for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) {                                   // :2170-2185
             const int e = el[i];
             double px = ps[i], py = ps[n + i];
             pold[i] = px; pold[n + i] = py;
@@ -182,22 +207,22 @@ __device__ void tangcg_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, co
         dif = alpha * facnel * sqrt(d3[2] / (2.0 * n));
         difinn += dif;
         if (itcg <= 5 || itcg % 5 == 1) {
-            block_sum<1>(p2, red);
+            x.template sum<1>(p2);
             const double ptang = facnel * sqrt(p2[0] / (2.0 * n));
             difid = eps * fmax(1e-6, ptang);
             trsinn = (double) 0.01f * ptang;
-        } else __syncthreads();
+        } else x.sync();
 
         if (it_inn >= num_inn || dif <= difid || difinn > trsinn) {            // :2227 check constraints
             double ch[1] = { 0.0 };
-            for (int i = tid; i < n; i += nt) if (el[i] == 1) {
+            for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) if (el[i] == 1) {
                 const double px = ps[i], py = ps[n + i], pa = sqrt(px * px + py * py);
                 if (pa > g[i]) { el[i] = 2; ps[i] = px * g[i] / pa; ps[n + i] = py * g[i] / pa; ch[0] += 1.0; }
             }
-            __syncthreads();
-            nprod += conv_multi(P, sm, c.chatA, ps, 0, 1, ss, 0, 1, el, 1);
+            x.sync();
+            nprod += conv_multi(x, c.chatA, ps, 0, 1, ss, 0, 1, el, 1);
             double dp[1] = { 0.0 };
-            for (int i = tid; i < n; i += nt) {
+            for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) {
                 const int e = el[i];
                 if (e >= 1) { ss[i] += ws[i]; ss[n + i] += ws[n + i]; }
                 if (e == 2 && ss[i] * ps[i] + ss[n + i] * ps[n + i] > 0.0) { el[i] = 1; ch[0] += 1.0; }
@@ -206,15 +231,15 @@ __device__ void tangcg_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, co
                 dp[0] += dx * dx + dy * dy;
             }
             double both[2] = { ch[0], dp[0] };
-            block_sum<2>(both, red);
+            x.template sum<2>(both);
             lchanged = both[0] > 0.0;
             dif = facnel * sqrt(both[1] / (2.0 * n));
             it_inn = 0; difinn = 0.0;
-            if (lchanged) count_el(el, n, red, nadh, nslip);
+            if (lchanged) count_el(x, el, n, nadh, nslip);
         }
         if ((lchanged || dif > difid) && itcg < maxcg) {                       // :2330-2380
             if (it_inn <= 0) {
-                for (int i = tid; i < n; i += nt) {
+                for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) {
                     const double a = atan2(ps[n + i], ps[i]);
                     const double cx = cos(a), sy = sin(a);
                     nx[i] = cx; ny[i] = sy;
@@ -223,9 +248,9 @@ __device__ void tangcg_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, co
                     r[i] = rx; r[n + i] = ry;
                 }
             } else {
-                for (int i = tid; i < n; i += nt) if (el[i] >= 1) { r[i] -= alpha * q[i]; r[n + i] -= alpha * q[n + i]; }
+                for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) if (el[i] >= 1) { r[i] -= alpha * q[i]; r[n + i] -= alpha * q[n + i]; }
             }
-            __syncthreads();
+            x.sync();
         }
     }
     itcg_out = itcg; err_out = dif;
@@ -256,52 +281,56 @@ __device__ double centre_rowsum_blk(const ConvPlan &P, const double *blk, int cm
 }
 
 // one tangential solve + relative forces (+ log of the Newton-Raphson process)
-__device__ int solve_once_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, const double *wstot, double fntrue,
+template <class X>
+__device__ int solve_once_dev(const X &x, ContactCase &c, const double *wstot, double fntrue,
                               int &it, double &err, double &fx, double &fy, int &nprod)
 {
-    const int n = P.npot;
+    const int n = x.n();
     int info = 0;
     if (c.tang == 3) {                                                         // SteadyGS (m_stang.f90:166-185)
+        if constexpr (X::kBlock) {
         int nadh, nslip;
-        count_el(c.nrm.el, n, sm.red, nadh, nslip);
+        count_el(x, c.nrm.el, n, nadh, nslip);
         const int ncon = nadh + nslip;
         SteadyArgs a;
         a.ws = wstot; a.dp = c.twork + 3 * (size_t) n; a.ug = c.twork + 5 * (size_t) n;
         a.iel = reinterpret_cast<int *>(c.twork + 7 * (size_t) n);
         a.chatA = c.chatA; a.cf11 = c.cf11; a.cf12 = c.cf12; a.cf22 = c.cf22; a.cmx = c.nrm.cmx; a.cmy = c.nrm.cmy;
         a.ga_inv = c.nrm.ga_inv; a.mu = c.fstat; a.eps = c.nrm.eps; a.omegah = c.omegah; a.omegas = c.omegas; a.maxgs = c.nrm.maxgs;
-        if (ncon <= 6 * CB_THREADS) info = stdygs_dev<6>(P, sm, a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
-        else if (ncon <= 12 * CB_THREADS) info = stdygs_dev<12>(P, sm, a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
-        else info = stdygs_dev<22>(P, sm, a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
+        if (ncon <= 6 * CB_THREADS) info = stdygs_dev<6>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
+        else if (ncon <= 12 * CB_THREADS) info = stdygs_dev<12>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
+        else info = stdygs_dev<22>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
+        }
     } else
-        tangcg_dev(P, sm, c, wstot, c.nrm.maxgs, c.nrm.eps, it, err, nprod);
+        tangcg_dev(x, c, wstot, c.nrm.maxgs, c.nrm.eps, it, err, nprod);
     double s[2] = { 0.0, 0.0 };
-    for (int i = threadIdx.x; i < n; i += blockDim.x) { s[0] += c.ps[i]; s[1] += c.ps[n + i]; }
-    block_sum<2>(s, sm.red);
+    for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) { s[0] += c.ps[i]; s[1] += c.ps[n + i]; }
+    x.template sum<2>(s);
     fx = c.nrm.dxdy * s[0] / (c.fstat * fntrue);
     fy = c.nrm.dxdy * s[1] / (c.fstat * fntrue);
-    if (threadIdx.x == 0 && c.nr_n < CB_MAXNR_LOG) {
+    if (x.leader() && c.nr_n < CB_MAXNR_LOG) {
         const int k = c.nr_n;
         c.nr_itcg[k] = it; c.nr_cksi[k] = c.cksi; c.nr_ceta[k] = c.ceta; c.nr_fx[k] = fx; c.nr_fy[k] = fy;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) c.nr_n++;
-    __syncthreads();
+    x.sync();
+    if (x.leader()) c.nr_n++;
+    x.sync();
     return info;
 }
 
 // solvpt (m_solvpt.f90:51-378): Newton-Raphson on (cksi[, ceta]) for prescribed tangential forces; shifts: dq = 1
-__device__ int solvpt_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, const double *wsfix, double *wstot,
+template <class X>
+__device__ int solvpt_dev(const X &x, ContactCase &c, const double *wsfix, double *wstot,
                           const double *facdt, double fntrue, int &itgs, double &err, int &nprod)
 {
-    const int n = P.npot, tid = threadIdx.x, nt = blockDim.x;
+    const int n = x.n();
     const int *el = c.nrm.el;
     const double dq = c.dq, dxdy = c.nrm.dxdy, muscal = c.fstat, eps = c.nrm.eps;
     double cksi = c.cksi, ceta = c.ceta;                     // block-uniform copies; c.cksi/c.ceta updated by thread 0
     int it, nadh, nslip;
     double fxkp1, fykp1;
     itgs = 0;
-    for (int i = tid; i < n; i += nt) {
+    for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) {
         double wx = wsfix[i], wy = wsfix[n + i];
         if (el[i] >= 1) {
             const double f = facdt ? facdt[i] : 1.0;
@@ -310,10 +339,10 @@ __device__ int solvpt_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, con
         }
         wstot[i] = wx; wstot[n + i] = wy;
     }
-    __syncthreads();
-    int info = solve_once_dev(P, sm, c, wstot, fntrue, it, err, fxkp1, fykp1, nprod);
+    x.sync();
+    int info = solve_once_dev(x, c, wstot, fntrue, it, err, fxkp1, fykp1, nprod);
     itgs += it;
-    count_el(el, n, sm.red, nadh, nslip);
+    count_el(x, el, n, nadh, nslip);
     if (c.force3 >= 1 && info <= 1) {
         int itnr = 0;
         double df = fabs(c.fxrel - fxkp1);
@@ -333,14 +362,14 @@ __device__ int solvpt_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, con
             }
             for (int ifxy = 1; ifxy <= c.force3; ifxy++) {
                 const double fxk = fxkp1, fyk = fykp1;
-                if (ifxy == 1) { cksi += dcksi; for (int i = tid; i < n; i += nt) if (el[i] >= 1) wstot[i] += (facdt ? facdt[i] : 1.0) * dcksi * dq; }
-                else { ceta += dceta; for (int i = tid; i < n; i += nt) if (el[i] >= 1) wstot[n + i] += (facdt ? facdt[i] : 1.0) * dceta * dq; }
-                __syncthreads();
-                if (tid == 0) { c.cksi = cksi; c.ceta = ceta; }
-                __syncthreads();
-                info = solve_once_dev(P, sm, c, wstot, fntrue, it, err, fxkp1, fykp1, nprod);
+                if (ifxy == 1) { cksi += dcksi; for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) if (el[i] >= 1) wstot[i] += (facdt ? facdt[i] : 1.0) * dcksi * dq; }
+                else { ceta += dceta; for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) if (el[i] >= 1) wstot[n + i] += (facdt ? facdt[i] : 1.0) * dceta * dq; }
+                x.sync();
+                if (x.leader()) { c.cksi = cksi; c.ceta = ceta; }
+                x.sync();
+                info = solve_once_dev(x, c, wstot, fntrue, it, err, fxkp1, fykp1, nprod);
                 itgs += it;
-                count_el(el, n, sm.red, nadh, nslip);
+                count_el(x, el, n, nadh, nslip);
                 const double dfxk = fxkp1 - fxk, dfyk = fykp1 - fyk, ncon = (double) (nadh + nslip);
                 if (ifxy == 1) {
                     if (nadh > 0) {
@@ -360,30 +389,31 @@ __device__ int solvpt_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, con
             }
         }
         err = err + 2.0 * df * muscal * fntrue / ((nadh + 2) * dxdy);          // the reference's constant Slip=2, :361
-        if (tid == 0) { c.sens[0][0] = s00; c.sens[0][1] = s01; c.sens[1][0] = s10; c.sens[1][1] = s11; }
-    } else if (tid == 0) { c.sens[0][0] = 0.0; c.sens[0][1] = 0.0; c.sens[1][0] = 0.0; c.sens[1][1] = 0.0; }
-    if (tid == 0) { c.fx = fxkp1; c.fy = fykp1; }
-    __syncthreads();
+        if (x.leader()) { c.sens[0][0] = s00; c.sens[0][1] = s01; c.sens[1][0] = s10; c.sens[1][1] = s11; }
+    } else if (x.leader()) { c.sens[0][0] = 0.0; c.sens[0][1] = 0.0; c.sens[1][0] = 0.0; c.sens[1][1] = 0.0; }
+    if (x.leader()) { c.fx = fxkp1; c.fy = fykp1; }
+    x.sync();
     return info;
 }
 
 // stang (m_stang.f90:28-746) for shifts with uniform Coulomb friction; returns ittang (-1: MaxIn reached)
-__device__ int stang_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, double fntrue, int &itgs_tot, int &nprod)
+template <class X>
+__device__ int stang_dev(const X &x, ContactCase &c, double fntrue, int &itgs_tot, int &nprod)
 {
-    const int n = P.npot, tid = threadIdx.x, nt = blockDim.x;
+    const int n = x.n();
     int *el = c.nrm.el;
-    double *ps = c.ps, *ss = c.ss, *red = sm.red;
+    double *ps = c.ps, *ss = c.ss;
     double *wsfix = c.twork + 13 * (size_t) n, *wstot = wsfix + 2 * n, *u1 = wstot + 2 * n, *u2 = u1 + 2 * n;
     const double mu = c.fstat;
     const bool ssrol = (c.tang == 3);
     double *facdt = nullptr;
-    if (ssrol) {                                                               // m_stang.f90:129-223
+    if constexpr (X::kBlock) if (ssrol) {                                      // m_stang.f90:129-223
         double cnt[2] = { 0.0, 0.0 };
-        for (int i = tid; i < n; i += nt) if (el[i] >= 1) { cnt[0] += 1.0; if (i % P.mx == 0) cnt[1] += 1.0; }
-        block_sum<2>(cnt, red);
+        for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) if (el[i] >= 1) { cnt[0] += 1.0; if (i % x.plan().mx == 0) cnt[1] += 1.0; }
+        x.template sum<2>(cnt);
         const int k = (int) cnt[0];
         // no exterior elements at the trailing edge, or G = 2 / 5: ConvexGS / GDsteady, which this path does not serve
-        if (cnt[1] > 0.0 || c.gausei == 2 || c.gausei == 5) { if (tid == 0) c.tstatus |= 1; __syncthreads(); itgs_tot = 0; return -1; }
+        if (cnt[1] > 0.0 || c.gausei == 2 || c.gausei == 5) { if (x.leader()) c.tstatus |= 1; x.sync(); itgs_tot = 0; return -1; }
         double oh = c.omegah, os = c.omegas;
         if (c.gausei == 0 || c.gausei == 4) {
             const double r = c.dx / (c.nrm.dxdy / c.dx);                       // dx / dy
@@ -392,34 +422,34 @@ __device__ int stang_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, doub
             else if (r <= 15.0) { oh = 0.8; os = 0.8; }
             else { oh = 0.8; os = 0.6; }
         }
-        __syncthreads();
-        if (tid == 0) { c.omegah = oh; c.omegas = os; }
-        __syncthreads();
+        x.sync();
+        if (x.leader()) { c.omegah = oh; c.omegas = os; }
+        x.sync();
         facdt = c.twork;
-        sxbnd_facdt_dev(P.mx, P.my, el, c.dx, c.dq, facdt);
+        sxbnd_facdt_dev(x.plan().mx, x.plan().my, el, c.dx, c.dq, facdt);
     }
     // stang_rhs (:749-951): wsfix = -facdt hs_t + A_tn pn - A'_tn p'n - A'_tt p'_t on C; shifts: facdt = 1, previous
     // tractions p'; steady rolling: p' = p with the shifted coefficients cv, A'_tt p'_t left to the solver
-    nprod += conv_multi(P, sm, c.chatA, ps, 2, 2, u1, 0, 1, el, 1);
+    nprod += conv_multi(x, c.chatA, ps, 2, 2, u1, 0, 1, el, 1);
     if (ssrol) {
-        nprod += conv_multi(P, sm, c.chatV, ps, 2, 2, u2, 0, 1, el, 1);
-        for (int i = tid; i < n; i += nt) if (el[i] >= 1) { u1[i] -= u2[i]; u1[n + i] -= u2[n + i]; }
-        __syncthreads();
+        nprod += conv_multi(x, c.chatV, ps, 2, 2, u2, 0, 1, el, 1);
+        for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) if (el[i] >= 1) { u1[i] -= u2[i]; u1[n + i] -= u2[n + i]; }
+        x.sync();
     } else if (c.pv) {
-        nprod += conv_multi(P, sm, c.chatV, c.pv, 2, 2, u2, 0, 1, el, 1);
-        for (int i = tid; i < n; i += nt) if (el[i] >= 1) { u1[i] -= u2[i]; u1[n + i] -= u2[n + i]; }
-        __syncthreads();
-        nprod += conv_multi(P, sm, c.chatV, c.pv, 0, 1, u2, 0, 1, el, 1);
-        for (int i = tid; i < n; i += nt) if (el[i] >= 1) { u1[i] -= u2[i]; u1[n + i] -= u2[n + i]; }
-        __syncthreads();
+        nprod += conv_multi(x, c.chatV, c.pv, 2, 2, u2, 0, 1, el, 1);
+        for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) if (el[i] >= 1) { u1[i] -= u2[i]; u1[n + i] -= u2[n + i]; }
+        x.sync();
+        nprod += conv_multi(x, c.chatV, c.pv, 0, 1, u2, 0, 1, el, 1);
+        for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) if (el[i] >= 1) { u1[i] -= u2[i]; u1[n + i] -= u2[n + i]; }
+        x.sync();
     }
-    for (int i = tid; i < n; i += nt) {
+    for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) {
         const bool in = el[i] >= 1;
         const double f = facdt ? facdt[i] : 1.0;
         wsfix[i] = in ? -f * c.hst[i] + u1[i] : 0.0;
         wsfix[n + i] = in ? -f * c.hst[n + i] + u1[n + i] : 0.0;
     }
-    __syncthreads();
+    x.sync();
 
     int ittang = 0, it;
     bool zready = false;
@@ -428,27 +458,27 @@ __device__ int stang_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, doub
     while (!zready && ittang < c.nrm.maxin) {
         ittang++;
         zready = true;
-        const int info = solvpt_dev(P, sm, c, wsfix, wstot, facdt, fntrue, it, errpt, nprod);
+        const int info = solvpt_dev(x, c, wsfix, wstot, facdt, fntrue, it, errpt, nprod);
         itgs_tot += it;
         if (info >= 3) { ittang = -1; break; }                                 // :420-427 divergence
         double k[1] = { 0.0 };
         const double tol = sqrt(2.0) * errpt;
-        for (int i = tid; i < n; i += nt) if (el[i] == 1) {                    // :434-453 adhesion -> slip
+        for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) if (el[i] == 1) {                    // :434-453 adhesion -> slip
             const double px = ps[i], py = ps[n + i], pn = ps[2 * (size_t) n + i], pabs = sqrt(px * px + py * py);
             if (pabs >= mu * pn + tol) { el[i] = 2; ps[i] = px * mu * pn / pabs; ps[n + i] = py * mu * pn / pabs; k[0] += 1.0; }
         }
-        block_sum<1>(k, red);
+        x.template sum<1>(k);
         if (k[0] > 0.0) zready = false;
         if (zready) {                                                          // :463-510 slip -> adhesion
-            const double tol1 = errpt * 2.0 * fabs(centre_rowsum_blk(P, c.cf11, c.nrm.cmx, c.nrm.cmy, el, red) * c.nrm.ga_inv);
-            const double tol2 = errpt * 2.0 * fabs(centre_rowsum_blk(P, c.cf22, c.nrm.cmx, c.nrm.cmy, el, red) * c.nrm.ga_inv);
+            const double tol1 = errpt * 2.0 * fabs(centre_rowsum_blk(x.plan(), c.cf11, c.nrm.cmx, c.nrm.cmy, el, x.red()) * c.nrm.ga_inv);
+            const double tol2 = errpt * 2.0 * fabs(centre_rowsum_blk(x.plan(), c.cf22, c.nrm.cmx, c.nrm.cmy, el, x.red()) * c.nrm.ga_inv);
             double ka[1] = { 0.0 };
-            for (int i = tid; i < n; i += nt) if (el[i] == 2) {
+            for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) if (el[i] == 2) {
                 const double ww = ss[i] * ps[i] + ss[n + i] * ps[n + i];
                 const double tl = tol1 * fabs(ps[i]) + tol2 * fabs(ps[n + i]) + errpt * (fabs(ss[i]) + fabs(ss[n + i]));
                 if (ww > tl) { el[i] = 1; ka[0] += 1.0; }
             }
-            block_sum<1>(ka, red);
+            x.template sum<1>(ka);
             if (ka[0] > 0.0) zready = false;
             if (info > 0) zready = true;                                       // :510
         }
@@ -458,33 +488,33 @@ __device__ int stang_dev(const ConvPlan &P, const Smem &sm, ContactCase &c, doub
 }
 
 // contac's computing part: panprc (m_scontc.f90:356-553) = NORM / TANG alternation until the tractions settle
-__device__ void panprc_dev(const ConvPlan &P, const Smem &sm, ContactCase &c)
+template <class X>
+__device__ void panprc_dev(const X &x, ContactCase &c)
 {
-    const int n = P.npot, tid = threadIdx.x, nt = blockDim.x;
+    const int n = x.n();
     double *ps = c.ps, *po1 = c.twork + 21 * (size_t) n;
     int *el = c.nrm.el;
     int itnorm = 0, ittang = 0, itout = 0, itcg = 0, itgs = 0, nprod = 0;
     double dif = 200.0, difid = 1.0;
-    if (tid == 0) c.nr_n = 0;
-    for (int i = tid; i < 3 * n; i += nt) po1[i] = ps[i];
-    __syncthreads();
+    if (x.leader()) c.nr_n = 0;
+    for (size_t i = x.first(); i < (size_t) (3 * n); i += x.stride()) po1[i] = ps[i];
+    x.sync();
     while (dif > difid && itout < c.maxout && itnorm >= 0 && ittang >= 0) {
         itout++;
-        snorm_dev(P, sm, c.nrm);
-        __syncthreads();
+        x.snorm(c.nrm);
         itcg += c.nrm.itcg; nprod += c.nrm.nprod;
         if (c.nrm.itnorm >= 0) itnorm += c.nrm.itnorm; else itnorm = -1;
         const int ncon = c.nrm.ncon;
-        for (int i = tid; i < n; i += nt) if (el[i] < 1) { ps[i] = 0.0; ps[n + i] = 0.0; }
-        __syncthreads();
+        for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) if (el[i] < 1) { ps[i] = 0.0; ps[n + i] = 0.0; }
+        x.sync();
         if (c.tang == 0 || ncon <= 0) dif = 0.0;
         else {
             int it_gs;
-            const int it = stang_dev(P, sm, c, c.nrm.fntrue, it_gs, nprod);
+            const int it = stang_dev(x, c, c.nrm.fntrue, it_gs, nprod);
             itgs = it_gs;                                                      // solv%itgs is that of the last TANG call (m_stang.f90:274,709)
             if (it >= 0) ittang += it; else ittang = -1;
             double s[3] = { 0.0, 0.0, 0.0 };
-            for (int i = tid; i < n; i += nt) {
+            for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) {
                 const bool in = el[i] >= 1;
                 for (int k = 0; k < 3; k++) {
                     const double pk = ps[(size_t) k * n + i], d = po1[(size_t) k * n + i] - pk;
@@ -492,18 +522,18 @@ __device__ void panprc_dev(const ConvPlan &P, const Smem &sm, ContactCase &c)
                     po1[(size_t) k * n + i] = pk;
                 }
             }
-            block_sum<3>(s, sm.red);
+            x.template sum<3>(s);
             dif = sqrt(s[0] / fmax(1.0, s[2]));
             difid = 5.0 * c.nrm.eps * sqrt(s[1] / fmax(1.0, s[2]));
         }
     }
     int nadh, nslip;
-    count_el(el, n, sm.red, nadh, nslip);
-    if (tid == 0) {
+    count_el(x, el, n, nadh, nslip);
+    if (x.leader()) {
         c.nrm.itnorm = itnorm; c.nrm.itcg = itcg; c.nrm.nprod = nprod;
         c.ittang = ittang; c.itgs = itgs; c.itout = itout; c.nadh = nadh; c.nslip = nslip;
     }
-    __syncthreads();
+    x.sync();
 }
 
 }  // namespace cb200

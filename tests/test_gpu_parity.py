@@ -517,3 +517,58 @@ def test_large_grid_norm_8p_golden(cb, mbench):
     assert pn[~c].max() == 0.0 and pn[c].min() >= 0.0
     assert np.abs(h[c] + un[c] - pen).max() < 1e-5 * pen
     assert abs(fn - pn.sum() * 0.0125 * 0.0125) < 1e-9 * fn
+
+
+def _large_shift_case(cb, ire, mbench, mx, my, dx):
+    cb.cntc_initialize(ire, 3)
+    cb.cntc_setflags(ire, 1, [cb.CNTC["ic_tang"], cb.CNTC["ic_force"], cb.CNTC["ic_iestim"]], [1, 0, 0])
+    cb.cntc_setsolverflags(ire, 1, 0, [1000, 100, 30, 1], [1e-7])
+    cb.cntc_setmaterialparameters(ire, 1, 0, [0.28, 0.28, 82000.0, 82000.0])
+    cb.cntc_setfrictionmethod(ire, 1, 0, [0.3, 0.3])
+    cb.cntc_setpotcontact(ire, 1, 1, [mx, my, -3.55, -6.15, dx, dx])
+    cb.cntc_setundeformeddistc(ire, 1, 2, np.array(mbench["prmudf"]))
+    cb.cntc_setpenetration(ire, 1, mbench["pen"])
+    cb.cntc_setcreepages(ire, 1, 0.0005, -0.0010, 0.0008)
+    ierr = cb.cntc_calculate(ire, 1)
+    assert ierr == 0, (ierr, cb.lib.last_error())
+    its = cb.lowlevel.get_iterations(ire, 1)
+    el = cb.cntc_getelementdivision(ire, 1).ravel()
+    pn, px, py = cb.cntc_gettractions(ire, 1)
+    forces = cb.cntc_getcontactforces(ire, 1)
+    cb.cntc_finalize(ire)
+    return its, el, pn.ravel(), px.ravel(), py.ravel(), forces
+
+
+def test_large_grid_shift_2s_matches_oracle_and_golden(cb, O, mbench):
+    """perfc_test/tang_problm_2s.inp (143x163, T=1 shift, TangCG) on the whole-GPU path: nslp = 7243, ItGS(CG) = 71
+    (perfc_test/get_times.ref_out:22); flags bit-exact and tractions against the oracle."""
+    mx, my, dx = 143, 163, 0.05
+    its, el, pn, px, py, (fn, tx, ty, mz) = _large_shift_case(cb, 73, mbench, mx, my, dx)
+    assert int((el == 2).sum()) == 7243 and its["itgs"] == 71
+    g = dict(mx=mx, my=my, xl=-3.55, yl=-6.15, dx=dx, dy=dx, ibase=2, prmudf=np.array(mbench["prmudf"]))
+    ref = O.contac(g, cases.STEEL["gg"], cases.STEEL["poiss"], tang=1, norm=0, force3=0, pen=mbench["pen"], cksi=0.0005,
+                   ceta=-0.001, cphi=0.0008, fstat=0.3, fkin=0.3, maxgs=1000, maxin=100, maxnr=30, maxout=1, eps=1e-7,
+                   nn=mbench["nn"])
+    assert ref["itgs_tang"] == 71 and np.array_equal(el, ref["el"])
+    s = np.abs(ref["ps"][:2]).max()
+    assert np.abs(px - ref["ps"][0]).max() < 1e-7 * s and np.abs(py - ref["ps"][1]).max() < 1e-7 * s
+    assert abs(tx / (0.3 * fn) - ref["fx"]) < 1e-8 and abs(ty / (0.3 * fn) - ref["fy"]) < 1e-8
+
+
+def test_large_grid_shift_4s_golden(cb, mbench):
+    """perfc_test/tang_problm_4s.inp (287x323): nslp = 28260, ItGS(CG) = 154 (perfc_test/get_times.ref_out:23); traction
+    bound respected everywhere, slip elements on the bound."""
+    its, el, pn, px, py, forces = _large_shift_case(cb, 74, mbench, 287, 323, 0.025)
+    assert int((el == 2).sum()) == 28260 and its["itgs"] == 154
+    pt = np.hypot(px, py)
+    assert (pt <= 0.3 * pn * (1 + 1e-9) + 1e-12).all()
+    assert np.abs(pt[el == 2] - 0.3 * pn[el == 2]).max() < 1e-9 * pn.max()
+
+
+def test_large_grid_shift_8s_golden(cb, mbench):
+    """perfc_test/tang_problm_8s.inp (575x647 = 372 025 elements): nslp = 111191, ItGS(CG) = 190
+    (perfc_test/get_times.ref_out:24, 167 s on the 2016 host)."""
+    its, el, pn, px, py, forces = _large_shift_case(cb, 75, mbench, 575, 647, 0.0125)
+    assert int((el == 2).sum()) == 111191 and its["itgs"] == 190
+    pt = np.hypot(px, py)
+    assert (pt <= 0.3 * pn * (1 + 1e-9) + 1e-12).all()
