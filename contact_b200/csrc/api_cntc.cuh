@@ -196,7 +196,7 @@ inline int check_scope(const Problem &p)
 {
     if (p.tang == 2) { last_error() = "T-digit: transient rolling (T=2) is not served by the B200 path yet (T=0, 1, 3 are)"; return CNTC_err_other; }
     if (p.tang != 0 && p.frclaw != 0) { last_error() = "L-digit: only Coulomb friction (L=0)"; return CNTC_err_other; }
-    if (p.tang != 0 && p.gausei == 2) { last_error() = "G-digit: ConvexGS (G=2) is not served by the B200 path yet"; return CNTC_err_other; }
+    if (p.tang == 3 && p.gausei == 2 && fabs(p.chi) > 0.01) { last_error() = "ConvexGS in steady rolling: only CHI = 0 is served by the B200 path"; return CNTC_err_other; }
     if (p.tang == 3 && p.gausei == 5) { last_error() = "G-digit: GDsteady (G=5) is not served by the B200 path yet (SteadyGS, G=0/3/4, is)"; return CNTC_err_other; }
     if (p.tang == 3 && fabs(p.chi) > 0.01 && fabs(p.chi - 3.14159265358979323846) <= 0.01) { last_error() = "CHI = pi (rolling in -x) is not served by the B200 path yet"; return CNTC_err_other; }
     if (p.mater != 0) { last_error() = "M-digit: only the elastic half-space (M=0) is in the hot-path scope"; return CNTC_err_other; }
@@ -275,6 +275,8 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
             for (int t = 1; t <= 2 && !rc; t++) { rc = build_chat(cs, SET_CS, 3, t, 0); if (!rc && any_tang) rc = build_chat(cs, SET_CS, t, 3, 0); }
             if (cs.key.is_roll) for (int t = 1; t <= 2 && !rc; t++) rc = build_chat(cs, SET_CV, t, 3, 0);
         }
+        if (!rc && cs.key.is_roll)                                  // ConvexGS in steady rolling works with csv = cs - cv
+            for (int ik = 1; ik <= 2 && !rc; ik++) for (int jk = 1; jk <= 2 && !rc; jk++) rc = build_chat(cs, SET_CSV, ik, jk, 0);
         if (rc) { fail(rc); continue; }
         // device buffers: per case hs_n(1) hst(2) ps(3) ss(2) work(9) twork(24) = 41 n doubles, el n ints
         const size_t per = (size_t) 41 * npot;
@@ -314,6 +316,8 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
             roll_stepsize(p, chi_e, dq_e);
             const bool is_roll = cs.key.is_roll != 0;
             for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) { c.chatA[a][b] = cs.d_chat[SET_CS][a][b]; c.chatV[a][b] = cs.d_chat[is_roll ? SET_CV : SET_CS][a][b]; }
+            for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) c.chatSV[a][b] = is_roll ? cs.d_chat[SET_CSV][a][b] : nullptr;
+            if (is_roll) { c.cfv11 = cs.d_cf[SET_CSV] + 0 * nblk; c.cfv12 = cs.d_cf[SET_CSV] + 3 * nblk; c.cfv22 = cs.d_cf[SET_CSV] + 4 * nblk; }
             c.cf12 = cs.d_cf[SET_CS] + 3 * nblk; c.dq = dq_e; c.dx = p.dx; c.gausei = p.gausei; c.omegah = p.omegah; c.omegas = p.omegas;
             c.chatM11 = cs.d_chat[SET_MS][0][0]; c.chatM22 = cs.d_chat[SET_MS][1][1];
             c.cf11 = cs.d_cf[SET_CS] + 0 * nblk; c.cf22 = cs.d_cf[SET_CS] + 4 * nblk;
@@ -397,7 +401,7 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
                 } else { p.fcntc[0] = p.fcntc[1] = 0.0; p.mztrue = 0.0; }
                 p.fcntc[2] = p.fntrue;
                 p.solved = true;
-                if (c.tstatus & 1) { last_error() = "TANG: no exterior elements at the trailing edge of the potential contact area: the reference switches to ConvexGS, which the B200 path does not serve yet"; ierr[ks[i]] = CNTC_err_other; }
+                if (c.tstatus & 1) { last_error() = "TANG: the case needs a solver that the B200 path does not serve (GDsteady, ConvexGS with DQ > DX, or a Gauss-Seidel solver on a grid beyond one CTA)"; ierr[ks[i]] = CNTC_err_other; }
                 else if (p.itnorm < 0 || (p.status & 1)) ierr[ks[i]] = CNTC_err_norm;
                 else if (p.ittang < 0) ierr[ks[i]] = CNTC_err_tang;
                 else ierr[ks[i]] = count_at_boundary(p);              // contact_addon.f90:3885-3891

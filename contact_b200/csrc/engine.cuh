@@ -275,6 +275,9 @@ inline int get_coefset(int mx, int my, double dx, double dy, Material mat, int i
         for (int jk = 0; jk < 3; jk++)
             CB_CUDA(cudaMemcpyAsync(cs->d_cf[SET_CV] + (size_t) (jk * 3 + 2) * nblk, cs->d_cf[SET_CS] + (size_t) (jk * 3 + 2) * nblk,
                                     sizeof(double) * nblk, cudaMemcpyDeviceToDevice, st));
+        CB_CUDA(cudaMalloc(&cs->d_cf[SET_CSV], sizeof(double) * 9 * nblk));
+        k_csv_blocks<<<grid1d(9 * nblk, 256), 256, 0, st>>>(cs->d_cf[SET_CS], cs->d_cf[SET_CV], cs->d_cf[SET_CSV], nblk);
+        E.launches++;
     }
     CB_CUDA(cudaGetLastError());
     CB_CUDA(cudaStreamSynchronize(st));

@@ -95,6 +95,15 @@ __global__ void k_elascf_pcwcns(ElascfArgs a, double *cf)
     cf[8 * nblk + t] = c33;      // (3,3)
 }
 
+// csv = cs - cv for the tangential displacement rows, csv(3,:) = cs(3,:) (sgencr, m_visc.f90:310-359); n = 4 mx my
+__global__ void k_csv_blocks(const double *cs, const double *cv, double *csv, long n)
+{
+    const long t = blockIdx.x * (long) blockDim.x + threadIdx.x;
+    if (t >= 9 * n) return;
+    const int blk = (int) (t / n), ik = blk % 3;                 // block index = (jk-1)*3 + (ik-1)
+    csv[t] = (ik == 2) ? cs[t] : cs[t] - cv[t];
+}
+
 // ---- dense DFT along one axis of a complex (n2 x n1) array (used by the preconditioner builder only) ----
 // out[k] = sum_n in[n] tw[(n k) mod N] (sign +1: conj table).  axis 0: along x (fastest), axis 1: along y.
 __global__ void k_dft_axis(const cd *in, cd *out, int n1, int n2, int axis, int inverse, const cd *tw)

@@ -20,7 +20,8 @@ namespace cb200 {
 enum { EL_EXTER = 0, EL_ADHES = 1, EL_SLIP = 2, EL_PLAST = 3 };
 
 // cycle counters of the SteadyGS step (thread 0 of every CTA adds its totals at the end of a solver call):
-// [0] element steps, [1] plstrc, [2] re-integration, [3] waiting + rank-1 updates + hand-over, [4] solver calls
+// [0] element steps, [1] per-element solve (plstrc), [2] re-integration of the row, [3] in-row rank-1 updates,
+// [4] solver calls, [5] per-row updates of all other rows (whole CTA)
 __device__ unsigned long long g_steady_prof[8];
 
 // plstrc (m_solvpt.f90:3278-3807) without plasticity (tau_c = 1e20, k_tau = 0): el, (px,py), (sx,sy) in/out.
@@ -93,9 +94,10 @@ __device__ void plstrc_dev(int &el, double c00, double c01, double c10, double c
     sx = six; sy = siy;
 }
 
-// leading-edge factor facdt (m_leadedge.f90:92-332, chi = 0, no leading-edge correction): 0 in the exterior, 1 near
-// the end of the grid, min(1, (xbnd - x)/dq) otherwise with xbnd two elements beyond the next C->E transition
-__device__ void sxbnd_facdt_dev(int mx, int my, const int *el, double dx, double dq, double *facdt)
+// leading-edge factor facdt (m_leadedge.f90:92-332, chi = 0): 0 in the exterior, 1 near the end of the grid,
+// min(1, (xbnd - x)/dq) otherwise with xbnd fxdfac elements beyond the next C->E transition (2 without the leading-edge
+// correction -- SteadyGS --, 1 with it -- ConvexGS)
+__device__ void sxbnd_facdt_dev(int mx, int my, const int *el, double dx, double dq, double fxdfac, double *facdt)
 {
     for (int iy = threadIdx.x; iy < my; iy += blockDim.x) {
         const int *e = el + (size_t) iy * mx;
@@ -105,7 +107,7 @@ __device__ void sxbnd_facdt_dev(int mx, int my, const int *el, double dx, double
             if (e[ix] < 1) { f[ix] = 0.0; continue; }
             if (ixb < ix) { ixb = ix; while (ixb < mx - 1 && e[ixb + 1] >= 1) ixb++; }
             if (ix + 3 > mx) f[ix] = 1.0;
-            else f[ix] = fmin(1.0, ((double) (ixb - ix + 2) * dx) / dq);
+            else f[ix] = fmin(1.0, (((double) (ixb - ix) + fxdfac) * dx) / dq);
         }
     }
     __syncthreads();
@@ -121,75 +123,159 @@ struct SteadyArgs {
     int cmx, cmy;
     double ga_inv, mu, eps, omegah, omegas;
     int maxgs;
+    int convex;             // 0: SteadyGS on the traction differences; 1: ConvexGS on the tractions (cnvxgs)
+    int sym;                // coefficient blocks have the quadrant symmetry of cs (false for csv = cs - cv)
 };
 
-// shared-memory carve-up for the sweep (bytes); tab = 0: coefficient table does not fit, read cf from global memory
-struct SteadySmem { double *q, *psx, *psy, *dpx, *dpy, *bnd, *wsx, *wsy, *ssx, *ssy, *chx, *chy, *scal; int *el, *chj, *rowk, *ictl; };
+// shared-memory carve-up for the sweep.  q: coefficient table (quadrant [3][my][mx] for the symmetric cs, half plane
+// [3][my][2mx] for csv, null when it does not fit: blocks are then read from global memory); r0: the dy = 0 rows of the
+// three blocks for dx in [-mx, mx) (in-row updates and the element's own 2x2 matrix)
+struct SteadySmem {
+    double *q, *r0, *row;      // table (or null), dy = 0 rows [3][2mx], per-row arrays [15][mx] + 8 scalars
+    int *irow;                 // int arrays [3][mx], then rowk[my+2], ictl[8]
+    int mx;
+    // accessors: one base pointer + multiples of mx (keeps the register footprint small)
+    __device__ __forceinline__ double &psx(int j) const { return row[j]; }
+    __device__ __forceinline__ double &psy(int j) const { return row[mx + j]; }
+    __device__ __forceinline__ double &dpx(int j) const { return row[2 * mx + j]; }
+    __device__ __forceinline__ double &dpy(int j) const { return row[3 * mx + j]; }
+    __device__ __forceinline__ double &bnd(int j) const { return row[4 * mx + j]; }
+    __device__ __forceinline__ double &wsx(int j) const { return row[5 * mx + j]; }
+    __device__ __forceinline__ double &wsy(int j) const { return row[6 * mx + j]; }
+    __device__ __forceinline__ double &ssx(int j) const { return row[7 * mx + j]; }
+    __device__ __forceinline__ double &ssy(int j) const { return row[8 * mx + j]; }
+    __device__ __forceinline__ double &urx(int j) const { return row[9 * mx + j]; }
+    __device__ __forceinline__ double &ury(int j) const { return row[10 * mx + j]; }
+    __device__ __forceinline__ double &ddx(int j) const { return row[11 * mx + j]; }
+    __device__ __forceinline__ double &ddy(int j) const { return row[12 * mx + j]; }
+    __device__ __forceinline__ double &chx(int j) const { return row[13 * mx + j]; }
+    __device__ __forceinline__ double &chy(int j) const { return row[14 * mx + j]; }
+    __device__ __forceinline__ double &scal(int j) const { return row[15 * mx + j]; }
+    __device__ __forceinline__ int &el(int j) const { return irow[j]; }
+    __device__ __forceinline__ int &chj(int j) const { return irow[mx + j]; }
+    __device__ __forceinline__ int &cix(int j) const { return irow[2 * mx + j]; }
+    __device__ __forceinline__ int &rowk(int j) const { return irow[3 * mx + j]; }
+    __device__ __forceinline__ int &ictl(int j, int my) const { return irow[3 * mx + my + 2 + j]; }
+};
 
-__device__ __forceinline__ bool steady_carve(const ConvPlan &P, unsigned char *base, SteadySmem &s)
+__device__ __forceinline__ void steady_carve(const ConvPlan &P, unsigned char *base, int sym, SteadySmem &s)
 {
     const size_t n = P.npot, mx = P.mx, my = P.my;
-    const size_t fixed = (11 * mx + 8) * 8 + (2 * mx + my + 8) * 4 + 64;
-    const bool tab = 3 * n * 8 + fixed <= (size_t) P.off_twx;
+    const size_t fixed = (6 * mx + 15 * mx + 8) * 8 + (3 * mx + my + 10) * 4 + 64;
+    const size_t tabsz = (sym ? 3 : 6) * n * 8;
+    const bool tab = tabsz + fixed <= (size_t) P.off_twx;
     double *d = reinterpret_cast<double *>(base);
     s.q = tab ? d : nullptr;
-    if (tab) d += 3 * n;
-    s.psx = d; s.psy = d + mx; s.dpx = d + 2 * mx; s.dpy = d + 3 * mx; s.bnd = d + 4 * mx; s.wsx = d + 5 * mx; s.wsy = d + 6 * mx;
-    s.ssx = d + 7 * mx; s.ssy = d + 8 * mx; s.chx = d + 9 * mx; s.chy = d + 10 * mx; s.scal = d + 11 * mx;
-    int *i = reinterpret_cast<int *>(d + 11 * mx + 8);
-    s.el = i; s.chj = i + mx; s.rowk = i + 2 * mx; s.ictl = i + 2 * mx + my + 2;
-    return fixed <= (size_t) P.off_twx;
+    if (tab) d += (sym ? 3 : 6) * n;
+    s.r0 = d; d += 6 * mx;
+    s.row = d;
+    s.irow = reinterpret_cast<int *>(d + 15 * mx + 8);
+    s.mx = (int) mx;
 }
 
-// stdygs: returns info (0 ok, 1 maxgs reached, 2 stagnation, 3 divergence).  All threads of the CTA must call.
+// coefficient lookup A_tt(dx, dy): c11, c12 (= c21), c22, already times 1/G
+struct SteadyTab {
+    const double *q, *r0;
+    const double *cf11, *cf12, *cf22;
+    int n, mx, cmx, cmy, sym;
+    double ga_inv;
+    __device__ __forceinline__ void get(int dx, int dy, double &c11, double &c12, double &c22) const
+    {
+        if (q) {
+            if (sym) {                                      // even (c11, c22) / odd (c12) in x and in y
+                const int o = abs(dy) * mx + abs(dx);
+                c11 = q[o]; c12 = q[n + o]; c22 = q[2 * n + o];
+                if ((dx < 0) != (dy < 0)) c12 = -c12;
+            } else {                                        // csv: symmetric in y only
+                const int o = abs(dy) * 2 * mx + dx + mx;
+                c11 = q[o]; c12 = q[2 * n + o]; c22 = q[4 * n + o];
+                if (dy < 0) c12 = -c12;
+            }
+        } else {
+            const size_t o = (size_t) (dy + cmy) * (2 * cmx) + dx + cmx;
+            c11 = cf11[o] * ga_inv; c12 = cf12[o] * ga_inv; c22 = cf22[o] * ga_inv;
+        }
+    }
+    __device__ __forceinline__ void row0(int dx, double &c11, double &c12, double &c22) const
+    { const int o = dx + mx; c11 = r0[o]; c12 = r0[2 * mx + o]; c22 = r0[4 * mx + o]; }
+};
+
+// Gauss-Seidel sweeps of stdygs (convex = 0) or cnvxgs (convex = 1): returns info (0 ok, 1 maxgs reached,
+// 2 stagnation, 3 divergence).  All threads of the CTA must call.
+//
+// Row-blocked organisation: the elements of one grid row are processed by warp 0 alone -- lane 0 runs the scalar
+// per-element solve, all 32 lanes keep the row's own displacement differences up to date and re-integrate the row
+// with a warp scan -- while the net change of the row is applied to the register-resident U of all other rows once
+// per row by the whole CTA.
 template <int KMAX>
 __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const SteadyArgs &a, int *el, double *ps, double *ss,
                           int ncon, int &itgs_out, double &err_out, int &nprod)
 {
-    const int n = P.npot, mx = P.mx, my = P.my, tid = threadIdx.x, nt = blockDim.x;
+    const int n = P.npot, mx = P.mx, my = P.my, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    const unsigned full = 0xffffffffu;
     double *psx = ps, *psy = ps + n, *psn = ps + 2 * (size_t) n;
     double *red = sm.red;
 
-    // traction differences along the rolling direction (x ascending = towards the leading edge), :2900-2915
-    for (int i = tid; i < n; i += nt) {
-        const int ix = i % mx;
-        a.dp[i] = (ix != mx - 1) ? psx[i] - psx[i + 1] : psx[i];
-        a.dp[n + i] = (ix != mx - 1) ? psy[i] - psy[i + 1] : psy[i];
+    // SteadyGS: traction differences along the rolling direction (x ascending = towards the leading edge), :2900-2915;
+    // ConvexGS works on the tractions themselves
+    const bool convex = a.convex != 0;
+    const double *xp = convex ? ps : a.dp;
+    if (!convex) {
+        for (int i = tid; i < n; i += nt) {
+            const int ix = i % mx;
+            a.dp[i] = (ix != mx - 1) ? psx[i] - psx[i + 1] : psx[i];
+            a.dp[n + i] = (ix != mx - 1) ? psy[i] - psy[i + 1] : psy[i];
+        }
     }
     __syncthreads();
     const double facnel = (double) sqrtf(__fdiv_rn((float) n, (float) ncon));
 
-    // U = A_tt dp on the contact area by four FFT products (fresh at every solver call)
+    // U = A_tt xp on the contact area by four FFT products (fresh at every solver call)
     for (int ik = 0; ik < 2; ik++) {
         bool ladd = false;
         for (int jk = 0; jk < 2; jk++) {
             if (a.chatA[ik][jk] == nullptr) continue;
-            conv_dev(P, sm, a.dp + (size_t) jk * n, a.chatA[ik][jk], a.ug + (size_t) ik * n, el, 1, ladd ? 1 : 0);
+            conv_dev(P, sm, xp + (size_t) jk * n, a.chatA[ik][jk], a.ug + (size_t) ik * n, el, 1, ladd ? 1 : 0);
             ladd = true; nprod++;
         }
     }
 
     // shared memory is ours now (S and W regions of the FFT layout)
     SteadySmem s;
-    steady_carve(P, reinterpret_cast<unsigned char *>(sm.S), s);
+    steady_carve(P, reinterpret_cast<unsigned char *>(sm.S), a.sym, s);
     if (s.q) {
-        for (int i = tid; i < n; i += nt) {
-            const int ay = i / mx, ax = i - ay * mx;
-            const size_t o = (size_t) (ay + a.cmy) * (2 * a.cmx) + ax + a.cmx;
-            s.q[i] = a.cf11[o] * a.ga_inv; s.q[n + i] = a.cf12[o] * a.ga_inv; s.q[2 * n + i] = a.cf22[o] * a.ga_inv;
+        if (a.sym) {
+            for (int i = tid; i < n; i += nt) {
+                const int ay = i / mx, ax = i - ay * mx;
+                const size_t o = (size_t) (ay + a.cmy) * (2 * a.cmx) + ax + a.cmx;
+                s.q[i] = a.cf11[o] * a.ga_inv; s.q[n + i] = a.cf12[o] * a.ga_inv; s.q[2 * n + i] = a.cf22[o] * a.ga_inv;
+            }
+        } else {
+            for (int i = tid; i < 2 * n; i += nt) {
+                const int ay = i / (2 * mx), dx = i - ay * 2 * mx - mx;
+                const size_t o = (size_t) (ay + a.cmy) * (2 * a.cmx) + dx + a.cmx;
+                s.q[i] = a.cf11[o] * a.ga_inv; s.q[2 * n + i] = a.cf12[o] * a.ga_inv; s.q[4 * n + i] = a.cf22[o] * a.ga_inv;
+            }
         }
     }
+    for (int i = tid; i < 2 * mx; i += nt) {
+        const size_t o = (size_t) a.cmy * (2 * a.cmx) + (i - mx) + a.cmx;
+        s.r0[i] = a.cf11[o] * a.ga_inv; s.r0[2 * mx + i] = a.cf12[o] * a.ga_inv; s.r0[4 * mx + i] = a.cf22[o] * a.ga_inv;
+    }
+    SteadyTab T;
+    T.q = s.q; T.r0 = s.r0; T.cf11 = a.cf11; T.cf12 = a.cf12; T.cf22 = a.cf22; T.n = n; T.mx = mx; T.cmx = a.cmx; T.cmy = a.cmy;
+    T.sym = a.sym; T.ga_inv = a.ga_inv;
     // compact list of contact elements in sweep order + row offsets
     for (int iy = tid; iy < my; iy += nt) {
         int cnt = 0;
         for (int ix = 0; ix < mx; ix++) cnt += (el[iy * mx + ix] >= 1);
-        s.rowk[iy + 1] = cnt;
+        s.rowk(iy + 1) = cnt;
     }
     __syncthreads();
-    if (tid == 0) { s.rowk[0] = 0; for (int iy = 0; iy < my; iy++) s.rowk[iy + 1] += s.rowk[iy]; }
+    if (tid == 0) { s.rowk(0) = 0; for (int iy = 0; iy < my; iy++) s.rowk(iy + 1) += s.rowk(iy); }
     __syncthreads();
     for (int iy = tid; iy < my; iy += nt) {
-        int k = s.rowk[iy];
+        int k = s.rowk(iy);
         for (int ix = 0; ix < mx; ix++) if (el[iy * mx + ix] >= 1) a.iel[k++] = iy * mx + ix;
     }
     __syncthreads();
@@ -200,145 +286,263 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
 #pragma unroll
     for (int m = 0; m < KMAX; m++) {
         const int k = tid + m * nt;
-        Ux[m] = 0.0; Uy[m] = 0.0; ixy[m] = 0;
+        Ux[m] = 0.0; Uy[m] = 0.0; ixy[m] = -1;
         if (k < ncon) {
             const int ii = a.iel[k], iy = ii / mx;
             ixy[m] = (ii - iy * mx) | (iy << 16);
             Ux[m] = a.ug[ii]; Uy[m] = a.ug[n + ii];
         }
     }
-    if (tid == 0) { s.scal[0] = Ux[0]; s.scal[1] = Uy[0]; }
-    __syncthreads();
-
-    const double q00 = s.q ? s.q[0] : a.cf11[(size_t) a.cmy * 2 * a.cmx + a.cmx] * a.ga_inv;
-    const double q11 = s.q ? s.q[2 * n] : a.cf22[(size_t) a.cmy * 2 * a.cmx + a.cmx] * a.ga_inv;
-    const double q01 = s.q ? s.q[n] : a.cf12[(size_t) a.cmy * 2 * a.cmx + a.cmx] * a.ga_inv;
+    double q00, q01, q11;
+    T.row0(0, q00, q01, q11);
 
     int itgs = 0;
     double dif = 2.0, difid = 1.0, dif1 = 0.0;
-    unsigned long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0, tlast = clock64();
+    unsigned long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0, tp4 = 0, tp5 = 0, tp6 = 0;
     while (dif >= difid && itgs < a.maxgs) {
         itgs++;
-        double dsum = 0.0;                                     // thread 0 only
-        int own_t = 0, own_m = 0;                              // owner (thread, slot) of the NEXT element k+1
+        double dsum = 0.0;                                     // lane 0 of warp 0 only
         for (int iy = 0; iy < my; iy++) {
-            const int k0 = s.rowk[iy], k1 = s.rowk[iy + 1];
+            const int k0 = s.rowk(iy), k1 = s.rowk(iy + 1);
             if (k1 == k0) continue;
             for (int jx = tid; jx < mx; jx += nt) {            // stage the row in shared memory
                 const int ii = iy * mx + jx;
-                s.psx[jx] = psx[ii]; s.psy[jx] = psy[ii]; s.dpx[jx] = a.dp[ii]; s.dpy[jx] = a.dp[n + ii];
-                s.bnd[jx] = a.mu * psn[ii]; s.wsx[jx] = a.ws[ii]; s.wsy[jx] = a.ws[n + ii];
-                s.ssx[jx] = ss[ii]; s.ssy[jx] = ss[n + ii]; s.el[jx] = el[ii];
+                s.psx(jx) = psx[ii]; s.psy(jx) = psy[ii];
+                if (!convex) { s.dpx(jx) = a.dp[ii]; s.dpy(jx) = a.dp[n + ii]; }
+                s.bnd(jx) = a.mu * psn[ii]; s.wsx(jx) = a.ws[ii]; s.wsy(jx) = a.ws[n + ii];
+                s.ssx(jx) = ss[ii]; s.ssy(jx) = ss[n + ii]; s.el(jx) = el[ii];
+                s.ddx(jx) = 0.0; s.ddy(jx) = 0.0;
+            }
+            for (int k = k0 + tid; k < k1; k += nt) s.cix(k - k0) = a.iel[k] - iy * mx;
+#pragma unroll
+            for (int m = 0; m < KMAX; m++)
+                if (ixy[m] >= 0 && (ixy[m] >> 16) == iy) { s.urx(ixy[m] & 0xffff) = Ux[m]; s.ury(ixy[m] & 0xffff) = Uy[m]; }
+            __syncthreads();
+
+            if (tid < 32) {                                    // ---- warp 0: the Gauss-Seidel steps of this row ----
+                for (int k = k0; k < k1; k++) {
+                    const unsigned long long ta = clock64();
+                    const int ix = s.cix(k - k0);
+                    int e = s.el(ix);
+                    // cnvxgs :2626: after 1000 iterations the slip elements are skipped every other iteration
+                    const bool active = (!convex || itgs <= 1000 || (itgs & 1) == 0 || e == EL_ADHES);
+                    // run of adhesion elements directly to the left of ix (lanes look at ix-1, ix-2, ...): gives the
+                    // element jx of the 2x2 matrix (stdygs :3010-3040) and the first window of the re-integration
+                    int ej0 = -1, L0 = 0, jxs = ix - 1;
+                    if (!convex) {
+                        const int jj = ix - 1 - lane;
+                        ej0 = (jj >= 0) ? s.el(jj) : -1;
+                        const unsigned na = __ballot_sync(full, ej0 != EL_ADHES);
+                        L0 = na ? __ffs(na) - 1 : 32;
+                        jxs = ix - 1 - L0;
+                        if (L0 == 32) { while (jxs > 0 && s.el(jxs) == EL_ADHES) jxs--; }
+                        if (jxs < 0) jxs = 0;
+                    }
+                    double px = 0.0, py = 0.0;
+                    if (lane == 0) {
+                        s.ictl(0, my) = 0;
+                        if (active) {
+                            double c00, c01, c11;
+                            if (convex) { c00 = q00; c01 = q01; c11 = q11; }   // cnvxgs: coefs / coefsv, :2519-2541
+                            else {                                              // stdygs: c(0) - c(jx - ix), :3010-3040
+                                double t00, t01, t11;
+                                T.row0(jxs - ix, t00, t01, t11);
+                                c00 = q00 - t00; c01 = q01 - t01; c11 = q11 - t11;
+                            }
+                            double sx = s.wsx(ix) + s.urx(ix), sy = s.wsy(ix) + s.ury(ix);
+                            const double pox = s.psx(ix), poy = s.psy(ix);
+                            px = pox; py = poy;
+                            plstrc_dev(e, c00, c01, c01, c11, a.eps, a.omegah, a.omegas, px, py, s.bnd(ix), sx, sy);
+                            const double ex = px - pox, ey = py - poy;
+                            dsum += ex * ex + ey * ey;
+                            if (ex != 0.0 || ey != 0.0) { s.chj(0) = ix; s.chx(0) = ex; s.chy(0) = ey; s.ictl(0, my) = 1; }
+                            s.psx(ix) = px; s.psy(ix) = py; s.ssx(ix) = sx; s.ssy(ix) = sy; s.el(ix) = e;
+                            if (!convex) { s.dpx(ix) += ex; s.dpy(ix) += ey; }
+                        }
+                    }
+                    const unsigned long long tb = clock64();
+                    __syncwarp();
+                    if (!convex && active) {
+                        // re-integrate dp -> ps to the left (:3089-3126) with a warp scan: lanes 0.. take the elements
+                        // ix-1, ix-2, ...; the chain of adhesion elements follows the new traction, it ends at the
+                        // first element that does not change, at a clamped element or at the first non-adhesion element
+                        double rx = __shfl_sync(full, px, 0), ry = __shfl_sync(full, py, 0);
+                        int jj0 = ix - 1;
+                        bool done = false, first = true;
+                        while (!done && jj0 >= 0) {
+                            const int jj = jj0 - lane;
+                            int ej, L;
+                            if (first) { ej = ej0; L = L0; first = false; }
+                            else {
+                                ej = (jj >= 0) ? s.el(jj) : -1;
+                                const unsigned notadh = __ballot_sync(full, ej != EL_ADHES);
+                                L = notadh ? __ffs(notadh) - 1 : 32;
+                            }
+                            double ax = (lane < L) ? s.dpx(jj) : 0.0, ay = (lane < L) ? s.dpy(jj) : 0.0;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const double tx = __shfl_up_sync(full, ax, o), ty = __shfl_up_sync(full, ay, o);
+                                if (lane >= o) { ax += tx; ay += ty; }
+                            }
+                            double nx = rx + ax, ny = ry + ay;
+                            const double pb = (lane < L) ? fmin(s.bnd(jj), 1e20) : 0.0;
+                            const bool clamp = lane < L && (nx * nx + ny * ny > pb * pb);
+                            const unsigned cm = __ballot_sync(full, clamp);
+                            const int Lc = cm ? __ffs(cm) - 1 : L;              // lanes < Lc keep the scanned values
+                            const bool same = lane < Lc && nx == s.psx(jj) && ny == s.psy(jj);
+                            const unsigned smk = __ballot_sync(full, same);
+                            const int Ls = smk ? __ffs(smk) - 1 : 32;
+                            if (lane < Lc && lane <= Ls) { s.psx(jj) = nx; s.psy(jj) = ny; }
+                            if (Ls < Lc) { done = true; break; }
+                            // traction of the element to the right of lane Lc
+                            const int src = Lc > 0 ? Lc - 1 : 0;
+                            const double qx = __shfl_sync(full, nx, src), qy = __shfl_sync(full, ny, src);
+                            const double prx = Lc > 0 ? qx : rx, pry = Lc > 0 ? qy : ry;
+                            if (Lc < L) {                                       // lane Lc: adhesion element beyond its bound
+                                double cxn = 0.0, cyn = 0.0;
+                                int stop = 0;
+                                if (lane == Lc) {
+                                    double mx_ = prx + s.dpx(jj), my_ = pry + s.dpy(jj);
+                                    const double t = pb / sqrt(mx_ * mx_ + my_ * my_);
+                                    mx_ *= t; my_ *= t;
+                                    const double ndx = mx_ - prx, ndy = my_ - pry;
+                                    const int c = s.ictl(0, my);
+                                    s.chj(c) = jj; s.chx(c) = ndx - s.dpx(jj); s.chy(c) = ndy - s.dpy(jj); s.ictl(0, my) = c + 1;
+                                    s.dpx(jj) = ndx; s.dpy(jj) = ndy;
+                                    stop = (mx_ == s.psx(jj) && my_ == s.psy(jj));
+                                    s.psx(jj) = mx_; s.psy(jj) = my_;
+                                    cxn = mx_; cyn = my_;
+                                }
+                                rx = __shfl_sync(full, cxn, Lc); ry = __shfl_sync(full, cyn, Lc);
+                                done = __shfl_sync(full, stop, Lc) != 0;
+                                jj0 -= Lc + 1;
+                                __syncwarp();
+                            } else if (L < 32) {                                // lane L: the chain's terminator
+                                if (lane == L && jj >= 0) {
+                                    double ndx, ndy;
+                                    bool upd = true;
+                                    if (ej >= EL_SLIP) { ndx = s.psx(jj) - prx; ndy = s.psy(jj) - pry; }
+                                    else if (s.el(jj + 1) >= EL_ADHES) { ndx = -prx; ndy = -pry; }
+                                    else { upd = false; ndx = 0.0; ndy = 0.0; }
+                                    if (upd) {
+                                        const double cx = ndx - s.dpx(jj), cy = ndy - s.dpy(jj);
+                                        if (cx != 0.0 || cy != 0.0) { const int c = s.ictl(0, my); s.chj(c) = jj; s.chx(c) = cx; s.chy(c) = cy; s.ictl(0, my) = c + 1; }
+                                        s.dpx(jj) = ndx; s.dpy(jj) = ndy;
+                                    }
+                                }
+                                done = true;
+                            } else {                                            // 32 adhesion elements done, next window
+                                rx = __shfl_sync(full, nx, 31); ry = __shfl_sync(full, ny, 31);
+                                jj0 -= 32;
+                                __syncwarp();
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    const unsigned long long tc = clock64();
+                    // in-row rank-1 updates: keep the displacement differences of this row current, accumulate the net
+                    // change of the row for the other rows
+                    const int nch = s.ictl(0, my);
+                    for (int c = 0; c < nch; c++) {
+                        const int jx = s.chj(c);
+                        const double ex = s.chx(c), ey = s.chy(c);
+                        if (lane == 0) { s.ddx(jx) += ex; s.ddy(jx) += ey; }
+                        for (int base = 0; base < mx; base += 96) {             // 3 elements per lane, loads first; the
+                            double c11[3], c12[3], c22[3], u0[3], u1[3];        // exterior elements are updated too (unused)
+#pragma unroll
+                            for (int r = 0; r < 3; r++) {
+                                const int ixp = min(base + lane + 32 * r, mx - 1);
+                                T.row0(ixp - jx, c11[r], c12[r], c22[r]); u0[r] = s.urx(ixp); u1[r] = s.ury(ixp);
+                            }
+#pragma unroll
+                            for (int r = 0; r < 3; r++) {
+                                const int ixp = base + lane + 32 * r;
+                                if (ixp < mx) { s.urx(ixp) = u0[r] + (c11[r] * ex + c12[r] * ey); s.ury(ixp) = u1[r] + (c12[r] * ex + c22[r] * ey); }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) { const unsigned long long td = clock64(); tp0++; tp1 += tb - ta; tp2 += tc - tb; tp3 += td - tc; tp5 += nch; }
+                }
+                // compact the net changes of this row for the update of the other rows
+                int cnt = 0;
+                for (int base = 0; base < mx; base += 32) {
+                    const int jx = base + lane;
+                    const double ex = jx < mx ? s.ddx(jx) : 0.0, ey = jx < mx ? s.ddy(jx) : 0.0;
+                    const bool nz = (ex != 0.0 || ey != 0.0);
+                    const unsigned mk = __ballot_sync(full, nz);
+                    if (nz) { const int pos = cnt + __popc(mk & ((1u << lane) - 1u)); s.chj(pos) = jx; s.chx(pos) = ex; s.chy(pos) = ey; }
+                    cnt += __popc(mk);
+                }
+                if (lane == 0) { s.ictl(1, my) = cnt; tp6 += cnt; }
             }
             __syncthreads();
-            int ixc = -1;                                      // thread 0: position of the current element
-            for (int k = k0; k < k1; k++) {
-                if (tid == 0) {
-                    const unsigned long long ta = clock64();
-                    tp3 += ta - tlast; tp0++;
-                    do ixc++; while (s.el[ixc] < 1);
-                    const int ix = ixc;
-                    int jx = ix - 1;
-                    while (jx > 0 && s.el[jx] == EL_ADHES) jx--;
-                    const int off = ix - jx;
-                    double t00, t01, t11;
-                    if (s.q) { t00 = s.q[off]; t01 = -s.q[n + off]; t11 = s.q[2 * n + off]; }
-                    else {
-                        const size_t o = (size_t) a.cmy * 2 * a.cmx + a.cmx - off;
-                        t00 = a.cf11[o] * a.ga_inv; t01 = a.cf12[o] * a.ga_inv; t11 = a.cf22[o] * a.ga_inv;
-                    }
-                    const double c00 = q00 - t00, c01 = q01 - t01, c11 = q11 - t11;
-                    double sx = s.wsx[ix] + s.scal[0], sy = s.wsy[ix] + s.scal[1];
-                    const double pox = s.psx[ix], poy = s.psy[ix];
-                    double px = pox, py = poy;
-                    int e = s.el[ix];
-                    plstrc_dev(e, c00, c01, c01, c11, a.eps, a.omegah, a.omegas, px, py, s.bnd[ix], sx, sy);
-                    const unsigned long long tb = clock64();
-                    tp1 += tb - ta;
-                    const double ex = px - pox, ey = py - poy;
-                    dsum += ex * ex + ey * ey;
-                    int nch = 0;
-                    if (ex != 0.0 || ey != 0.0) { s.chj[nch] = ix; s.chx[nch] = ex; s.chy[nch] = ey; nch++; }
-                    s.dpx[ix] += ex; s.dpy[ix] += ey;
-                    s.psx[ix] = px; s.psy[ix] = py; s.ssx[ix] = sx; s.ssy[ix] = sy; s.el[ix] = e;
-                    // re-integrate dp -> ps to the left (:3089-3126); stops where nothing can change any more
-                    double rx = px, ry = py;                   // tractions of element jj+1
-                    for (int jj = ix - 1; jj >= 0; jj--) {
-                        const int ej = s.el[jj];
-                        if (ej == EL_ADHES) {
-                            double nx = rx + s.dpx[jj], ny = ry + s.dpy[jj];
-                            const double pa2 = nx * nx + ny * ny, pb = fmin(s.bnd[jj], 1e20);
-                            if (pa2 > pb * pb) {
-                                const double t = pb / sqrt(pa2);
-                                nx *= t; ny *= t;
-                                const double ndx = nx - rx, ndy = ny - ry;
-                                s.chj[nch] = jj; s.chx[nch] = ndx - s.dpx[jj]; s.chy[nch] = ndy - s.dpy[jj]; nch++;
-                                s.dpx[jj] = ndx; s.dpy[jj] = ndy;
-                            }
-                            const bool same = (nx == s.psx[jj] && ny == s.psy[jj]);
-                            s.psx[jj] = nx; s.psy[jj] = ny;
-                            rx = nx; ry = ny;
-                            if (same) break;
-                        } else {
-                            double ndx, ndy;
-                            if (ej >= EL_SLIP) { ndx = s.psx[jj] - rx; ndy = s.psy[jj] - ry; }
-                            else if (s.el[jj + 1] >= EL_ADHES) { ndx = -rx; ndy = -ry; }
-                            else break;
-                            const double cx = ndx - s.dpx[jj], cy = ndy - s.dpy[jj];
-                            if (cx != 0.0 || cy != 0.0) { s.chj[nch] = jj; s.chx[nch] = cx; s.chy[nch] = cy; nch++; }
-                            s.dpx[jj] = ndx; s.dpy[jj] = ndy;
-                            break;
-                        }
-                    }
-                    s.ictl[0] = nch;
-                    tlast = clock64();
-                    tp2 += tlast - tb;
-                }
-                __syncthreads();
-                // rank-1 updates of U for every changed dp, all elements
-                const int nch = s.ictl[0];
-                for (int c = 0; c < nch; c++) {
-                    const int jx = s.chj[c];
-                    const double ex = s.chx[c], ey = s.chy[c];
+
+            // ---- whole CTA: apply the net change of row iy to the elements of all other rows ----
+            const unsigned long long te = clock64();
+            const int ncl = s.ictl(1, my);
+            if (s.q && a.sym) {                                // quadrant table in shared memory: the fast path
 #pragma unroll
-                    for (int m = 0; m < KMAX; m++) {
-                        if (tid + m * nt < ncon) {
-                            const int dx = (ixy[m] & 0xffff) - jx, dy = (ixy[m] >> 16) - iy;
+                for (int m = 0; m < KMAX; m++) {
+                    const int iym = ixy[m] >> 16, ixm = ixy[m] & 0xffff;
+                    if (ixy[m] >= 0 && iym != iy) {
+                        const int dy = iym - iy;
+                        const double *r11 = s.q + abs(dy) * mx, *r12 = r11 + n, *r22 = r12 + n;
+                        const bool ny = dy < 0;
+                        double ux0 = 0.0, uy0 = 0.0, ux1 = 0.0, uy1 = 0.0;
+                        int c = 0;
+                        for (; c + 1 < ncl; c += 2) {
+                            const int d0 = ixm - s.chj(c), d1 = ixm - s.chj(c + 1);
+                            const int a0 = abs(d0), a1 = abs(d1);
+                            const double e0x = s.chx(c), e0y = s.chy(c), e1x = s.chx(c + 1), e1y = s.chy(c + 1);
+                            const double g0 = r11[a0], h0 = ((d0 < 0) != ny) ? -r12[a0] : r12[a0], k0_ = r22[a0];
+                            const double g1 = r11[a1], h1 = ((d1 < 0) != ny) ? -r12[a1] : r12[a1], k1_ = r22[a1];
+                            ux0 += g0 * e0x + h0 * e0y; uy0 += h0 * e0x + k0_ * e0y;
+                            ux1 += g1 * e1x + h1 * e1y; uy1 += h1 * e1x + k1_ * e1y;
+                        }
+                        if (c < ncl) {
+                            const int d0 = ixm - s.chj(c), a0 = abs(d0);
+                            const double e0x = s.chx(c), e0y = s.chy(c);
+                            const double g0 = r11[a0], h0 = ((d0 < 0) != ny) ? -r12[a0] : r12[a0], k0_ = r22[a0];
+                            ux0 += g0 * e0x + h0 * e0y; uy0 += h0 * e0x + k0_ * e0y;
+                        }
+                        Ux[m] += ux0 + ux1; Uy[m] += uy0 + uy1;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < KMAX; m++) {
+                    const int iym = ixy[m] >> 16, ixm = ixy[m] & 0xffff;
+                    if (ixy[m] >= 0 && iym != iy) {
+                        double ux = 0.0, uy = 0.0;
+                        for (int c = 0; c < ncl; c++) {
                             double c11, c12, c22;
-                            if (s.q) {
-                                const int o = abs(dy) * mx + abs(dx);
-                                c11 = s.q[o]; c12 = s.q[n + o]; c22 = s.q[2 * n + o];
-                                if ((dx < 0) != (dy < 0)) c12 = -c12;
-                            } else {
-                                const size_t o = (size_t) (dy + a.cmy) * (2 * a.cmx) + dx + a.cmx;
-                                c11 = a.cf11[o] * a.ga_inv; c12 = a.cf12[o] * a.ga_inv; c22 = a.cf22[o] * a.ga_inv;
-                            }
-                            Ux[m] += c11 * ex + c12 * ey;
-                            Uy[m] += c12 * ex + c22 * ey;
+                            T.get(ixm - s.chj(c), iym - iy, c11, c12, c22);
+                            const double ex = s.chx(c), ey = s.chy(c);
+                            ux += c11 * ex + c12 * ey;
+                            uy += c12 * ex + c22 * ey;
                         }
+                        Ux[m] += ux; Uy[m] += uy;
                     }
                 }
-                // hand U of the next element to thread 0
-                own_t++; if (own_t == nt) { own_t = 0; own_m++; }
-                if (k + 1 == ncon) { own_t = 0; own_m = 0; }
-                if (tid == own_t) {
-#pragma unroll
-                    for (int m = 0; m < KMAX; m++) if (m == own_m) { s.scal[0] = Ux[m]; s.scal[1] = Uy[m]; }
-                }
-                __syncthreads();
             }
+#pragma unroll
+            for (int m = 0; m < KMAX; m++)
+                if (ixy[m] >= 0 && (ixy[m] >> 16) == iy) { Ux[m] = s.urx(ixy[m] & 0xffff); Uy[m] = s.ury(ixy[m] & 0xffff); }
             for (int jx = tid; jx < mx; jx += nt) {            // write the row back
                 const int ii = iy * mx + jx;
-                psx[ii] = s.psx[jx]; psy[ii] = s.psy[jx]; a.dp[ii] = s.dpx[jx]; a.dp[n + ii] = s.dpy[jx];
-                ss[ii] = s.ssx[jx]; ss[n + ii] = s.ssy[jx]; el[ii] = s.el[jx];
+                psx[ii] = s.psx(jx); psy[ii] = s.psy(jx);
+                if (!convex) { a.dp[ii] = s.dpx(jx); a.dp[n + ii] = s.dpy(jx); }
+                ss[ii] = s.ssx(jx); ss[n + ii] = s.ssy(jx); el[ii] = s.el(jx);
             }
+            if (tid == 0) tp4 += clock64() - te;
             __syncthreads();
         }
-        if (tid == 0) s.scal[2] = dsum;
+        if (tid == 0) s.scal(2) = dsum;
         double p2[1] = { 0.0 };
         for (int i = tid; i < n; i += nt) p2[0] += psx[i] * psx[i] + psy[i] * psy[i];
         block_sum<1>(p2, red);
-        dif = sqrt(s.scal[2] / (2.0 * ncon));
+        dif = sqrt(s.scal(2) / (2.0 * ncon));
         difid = a.eps * fmax(1e-6, facnel * sqrt(p2[0] / (2.0 * n)));
         if (itgs == 1) dif1 = dif;
         __syncthreads();
@@ -352,7 +556,8 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
     itgs_out = itgs; err_out = dif;
     if (tid == 0) {
         atomicAdd(&g_steady_prof[0], tp0); atomicAdd(&g_steady_prof[1], tp1); atomicAdd(&g_steady_prof[2], tp2);
-        atomicAdd(&g_steady_prof[3], tp3); atomicAdd(&g_steady_prof[4], 1ull);
+        atomicAdd(&g_steady_prof[3], tp3); atomicAdd(&g_steady_prof[4], 1ull); atomicAdd(&g_steady_prof[5], tp4);
+        atomicAdd(&g_steady_prof[6], tp5); atomicAdd(&g_steady_prof[7], tp6);
     }
     __syncthreads();
     return info;

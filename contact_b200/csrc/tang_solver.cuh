@@ -33,6 +33,9 @@ struct ContactCase {
     double dq, dx;                  // rolling step (shifts: 1), grid step in x
     int gausei;                     // G-digit
     double omegah, omegas;          // relaxation factors of the Gauss-Seidel solvers (set by stang)
+    const cd *chatSV[2][2];         // transformed csv = cs - cv blocks (steady rolling with ConvexGS)
+    const double *cfv11, *cfv12, *cfv22;   // spatial blocks of csv
+    int solver_eff;                 // 0 TangCG, 1 SteadyGS, 2 ConvexGS (set by stang, m_stang.f90:144-191)
     // outputs
     int ittang, itgs, itout, nr_n;
     int nr_itcg[CB_MAXNR_LOG];
@@ -287,16 +290,22 @@ __device__ int solve_once_dev(const X &x, ContactCase &c, const double *wstot, d
 {
     const int n = x.n();
     int info = 0;
-    if (c.tang == 3) {                                                         // SteadyGS (m_stang.f90:166-185)
+    if (c.solver_eff != 0) {                                                   // SteadyGS / ConvexGS
         if constexpr (X::kBlock) {
         int nadh, nslip;
         count_el(x, c.nrm.el, n, nadh, nslip);
         const int ncon = nadh + nslip;
+        const bool convex = c.solver_eff == 2, sv = convex && c.tang == 3;     // csv in steady rolling, cs otherwise
+        const cd *chat_sv[3][3] = { { c.chatSV[0][0], c.chatSV[0][1], nullptr }, { c.chatSV[1][0], c.chatSV[1][1], nullptr },
+                                    { nullptr, nullptr, nullptr } };
         SteadyArgs a;
         a.ws = wstot; a.dp = c.twork + 3 * (size_t) n; a.ug = c.twork + 5 * (size_t) n;
         a.iel = reinterpret_cast<int *>(c.twork + 7 * (size_t) n);
-        a.chatA = c.chatA; a.cf11 = c.cf11; a.cf12 = c.cf12; a.cf22 = c.cf22; a.cmx = c.nrm.cmx; a.cmy = c.nrm.cmy;
+        a.chatA = sv ? chat_sv : c.chatA;
+        a.cf11 = sv ? c.cfv11 : c.cf11; a.cf12 = sv ? c.cfv12 : c.cf12; a.cf22 = sv ? c.cfv22 : c.cf22;
+        a.cmx = c.nrm.cmx; a.cmy = c.nrm.cmy;
         a.ga_inv = c.nrm.ga_inv; a.mu = c.fstat; a.eps = c.nrm.eps; a.omegah = c.omegah; a.omegas = c.omegas; a.maxgs = c.nrm.maxgs;
+        a.convex = convex ? 1 : 0; a.sym = sv ? 0 : 1;
         if (ncon <= 6 * CB_THREADS) info = stdygs_dev<6>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
         else if (ncon <= 12 * CB_THREADS) info = stdygs_dev<12>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
         else info = stdygs_dev<22>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
@@ -407,26 +416,36 @@ __device__ int stang_dev(const X &x, ContactCase &c, double fntrue, int &itgs_to
     const double mu = c.fstat;
     const bool ssrol = (c.tang == 3);
     double *facdt = nullptr;
-    if constexpr (X::kBlock) if (ssrol) {                                      // m_stang.f90:129-223
+    {                                                                          // m_stang.f90:129-223
         double cnt[2] = { 0.0, 0.0 };
         for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) if (el[i] >= 1) { cnt[0] += 1.0; if (i % x.plan().mx == 0) cnt[1] += 1.0; }
         x.template sum<2>(cnt);
         const int k = (int) cnt[0];
-        // no exterior elements at the trailing edge, or G = 2 / 5: ConvexGS / GDsteady, which this path does not serve
-        if (cnt[1] > 0.0 || c.gausei == 2 || c.gausei == 5) { if (x.leader()) c.tstatus |= 1; x.sync(); itgs_tot = 0; return -1; }
+        int solver = ssrol ? (c.gausei != 2 ? 1 : 2) : (c.gausei != 2 ? 0 : 2);
+        if (cnt[1] > 0.0 && solver == 1) solver = 2;                           // no exterior elements at the trailing edge
+        // GDsteady (G = 5) is not served; ConvexGS with dq > dx needs the leading-edge equations (ii2j > 0), not served
+        bool refuse = (ssrol && c.gausei == 5) || (solver == 2 && ssrol && c.dq > c.dx * (1.0 + 1e-4)) || (solver != 0 && !X::kBlock);
+        if (refuse) { if (x.leader()) c.tstatus |= 1; x.sync(); itgs_tot = 0; return -1; }
         double oh = c.omegah, os = c.omegas;
-        if (c.gausei == 0 || c.gausei == 4) {
+        if (c.gausei == 0 || c.gausei == 4 || c.gausei == 5) {
             const double r = c.dx / (c.nrm.dxdy / c.dx);                       // dx / dy
             if (k <= 25) { oh = 1.0; os = 1.0; }
-            else if (r <= 5.0) { oh = 0.9; os = 1.0; }
-            else if (r <= 15.0) { oh = 0.8; os = 0.8; }
-            else { oh = 0.8; os = 0.6; }
+            else if (ssrol && solver == 2) { oh = 0.5; os = 0.5; }
+            else if (ssrol) {
+                if (r <= 5.0) { oh = 0.9; os = 1.0; }
+                else if (r <= 15.0) { oh = 0.8; os = 0.8; }
+                else { oh = 0.8; os = 0.6; }
+            } else { oh = 0.5; os = 0.5; }
         }
         x.sync();
-        if (x.leader()) { c.omegah = oh; c.omegas = os; }
+        if (x.leader()) { c.omegah = oh; c.omegas = os; c.solver_eff = solver; }
         x.sync();
-        facdt = c.twork;
-        sxbnd_facdt_dev(x.plan().mx, x.plan().my, el, c.dx, c.dq, facdt);
+        if constexpr (X::kBlock) if (ssrol) {
+            facdt = c.twork;
+            // sxbnd (m_leadedge.f90:92-332): the leading edge sits 2 dx (SteadyGS) or 1 dx (ConvexGS) beyond the last
+            // interior element
+            sxbnd_facdt_dev(x.plan().mx, x.plan().my, el, c.dx, c.dq, solver == 1 ? 2.0 : 1.0, facdt);
+        }
     }
     // stang_rhs (:749-951): wsfix = -facdt hs_t + A_tn pn - A'_tn p'n - A'_tt p'_t on C; shifts: facdt = 1, previous
     // tractions p'; steady rolling: p' = p with the shifted coefficients cv, A'_tt p'_t left to the solver

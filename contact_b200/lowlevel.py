@@ -43,7 +43,7 @@ def steady_prof(reset=True):
     import ctypes as C
     out = (C.c_ulonglong * 8)()
     _check(load_library().cb200_steady_prof(out, 1 if reset else 0))
-    return dict(steps=out[0], plstrc=out[1], reintegrate=out[2], update=out[3], calls=out[4])
+    return dict(steps=out[0], plstrc=out[1], reintegrate=out[2], update=out[3], calls=out[4], rowupdate=out[5], changes=out[6], rowchanges=out[7])
 
 
 def num_sms():

@@ -3,7 +3,8 @@
  * Steady rolling (T=3) with the SteadyGS solver: per-element constrained 2x2 solve (plstrc, elastic branches),
  * Gauss-Seidel sweep on the traction differences dp with re-integration along the rows, leading-edge factors.
  * Follows /root/reference/src/m_solvpt.f90:2825-3254 (stdygs), :3278-3807 (plstrc; the plastic branch is reached with
- * taucs = 1e20 and only cycles the state, see SURVEY.md 7 "quirks"), /root/reference/src/m_leadedge.f90:92-332 (sxbnd).
+ * taucs = 1e20 and only cycles the state, see SURVEY.md 7 "quirks"), /root/reference/src/m_leadedge.f90:92-332 (sxbnd),
+ * :336-394 (subnd), and the ConvexGS solver /root/reference/src/m_solvpt.f90:2446-2821 (cnvxgs).
  */
 #include "contact_oracle.h"
 #include <stdlib.h>
@@ -203,4 +204,143 @@ void co_sxbnd_facdt(int mx, int my, const co_eldiv *igs, const double *x, double
         }
         free(ixb);
     }
+}
+
+/* m_leadedge.f90:92-332 for chi = 0: leading-edge positions per row (jbnd, ixbnd), facdx = fxdfac (2 without, 1 with the
+ * leading-edge correction), xbnd, facdt and ii2j (0: interior equation, j > 0: leading-edge equation at position j) */
+void co_sxbnd(int mx, int my, int is_roll, int use_ledg, const co_eldiv *igs, const double *x, double dx, double dq,
+              co_leadedge *lg)
+{
+    const int npot = mx * my;
+    lg->jbnd = (int *) realloc(lg->jbnd, sizeof(int) * (my + 2));
+    lg->jbnd[1] = 1;
+    for (int iy = 1; iy <= my; iy++) {
+        int np = 0;
+        for (int ix = 1; ix <= mx - 1; ix++) {
+            const int ii = ix + (iy - 1) * mx - 1;
+            if (igs->el[ii] >= CO_ADHES && igs->el[ii + 1] <= CO_EXTER) np++;
+        }
+        if (igs->el[mx + (iy - 1) * mx - 1] >= CO_ADHES) np++;
+        lg->jbnd[iy + 1] = lg->jbnd[iy] + np;
+    }
+    lg->npos = lg->jbnd[my + 1];
+    lg->ixbnd = (int *) realloc(lg->ixbnd, sizeof(int) * (lg->npos + 1));
+    lg->xbnd = (double *) realloc(lg->xbnd, sizeof(double) * (lg->npos + 1));
+    lg->facdx = (double *) realloc(lg->facdx, sizeof(double) * (lg->npos + 1));
+    lg->ubnd = (double *) realloc(lg->ubnd, sizeof(double) * 2 * (lg->npos + 1));
+    lg->ii2j = (int *) realloc(lg->ii2j, sizeof(int) * npot);
+    lg->facdt = (double *) realloc(lg->facdt, sizeof(double) * npot);
+    for (int iy = 1; iy <= my; iy++) {
+        int j = lg->jbnd[iy];
+        for (int ix = 1; ix <= mx - 1; ix++) {
+            const int ii = ix + (iy - 1) * mx - 1;
+            if (igs->el[ii] >= CO_ADHES && igs->el[ii + 1] <= CO_EXTER) lg->ixbnd[j++] = ix;
+        }
+        if (igs->el[mx + (iy - 1) * mx - 1] >= CO_ADHES) lg->ixbnd[j++] = mx;
+    }
+    const double fxdfac = use_ledg ? 1.0 : 2.0;
+    for (int iy = 1; iy <= my; iy++)
+        for (int j = lg->jbnd[iy]; j < lg->jbnd[iy + 1]; j++) {
+            lg->facdx[j] = fxdfac;
+            lg->xbnd[j] = x[lg->ixbnd[j] + (iy - 1) * mx - 1] + 1 * lg->facdx[j] * dx;
+        }
+    for (int iy = 1; iy <= my; iy++) {
+        int j = lg->jbnd[iy];
+        for (int ix = 1; ix <= mx; ix++) {
+            while (j < lg->jbnd[iy + 1] && ix > lg->ixbnd[j]) j++;
+            const int ii = ix + (iy - 1) * mx - 1;
+            if (!is_roll) { lg->ii2j[ii] = 0; lg->facdt[ii] = 1.0; }
+            else if (igs->el[ii] <= CO_EXTER) { lg->ii2j[ii] = 0; lg->facdt[ii] = 0.0; }
+            else if (ix + 2 > mx) { lg->ii2j[ii] = 0; lg->facdt[ii] = 1.0; }
+            else {
+                lg->facdt[ii] = fmin(1.0, 1 * (lg->xbnd[j] - x[ii]) / dq);
+                lg->ii2j[ii] = (lg->facdt[ii] < 0.9999) ? j : 0;
+            }
+        }
+    }
+}
+
+void co_leadedge_free(co_leadedge *lg)
+{
+    free(lg->jbnd); free(lg->ixbnd); free(lg->xbnd); free(lg->facdx); free(lg->ubnd); free(lg->ii2j); free(lg->facdt);
+    memset(lg, 0, sizeof(*lg));
+}
+
+/* m_leadedge.f90:336-394: displacement difference at the leading-edge positions, interpolated between the last interior
+ * element and its exterior neighbour (all three traction directions) */
+void co_subnd(co_ctx *cx, int mx, int my, const double *p, const co_eldiv *pel, const co_inflcf *c, co_leadedge *lg)
+{
+    for (int iy = 1; iy <= my; iy++)
+        for (int j = lg->jbnd[iy]; j < lg->jbnd[iy + 1]; j++) {
+            const int ix0 = lg->ixbnd[j];
+            if (ix0 + 2 > mx) { lg->ubnd[2 * j] = 0.0; lg->ubnd[2 * j + 1] = 0.0; continue; }
+            const int ii = ix0 + (iy - 1) * mx;
+            for (int ik = 1; ik <= 2; ik++) {
+                const double u0 = co_aijpj(ii, ik, p, pel, CO_ALL, c), u1 = co_aijpj(ii + 1, ik, p, pel, CO_ALL, c);
+                cx->st.n_rowsum += 2;
+                lg->ubnd[2 * j + ik - 1] = (1.0 - lg->facdx[j]) * u0 + lg->facdx[j] * u1;
+            }
+        }
+}
+
+/* m_solvpt.f90:2446-2821, chi = 0, elastic: block Gauss-Seidel with the per-element constrained solve; shifts use cs,
+ * steady rolling csv (= cs - cv) in the interior and cs - ubnd at the leading-edge elements (ii2j > 0) */
+void co_cnvxgs(co_ctx *cx, int mx, int my, int is_ssrol, const double *ws, co_inflcf *cs, co_inflcf *csv, co_leadedge *lg,
+               const double *mus, co_eldiv *igs, double *ps, double *ss, int k, const int *iel, double eps, int maxgs,
+               double omegah, double omegas, int *info, int *itgs_out, double *err)
+{
+    const int npot = mx * my;
+    double coefs[2][2], coefsv[2][2];
+    for (int a = 0; a < 2; a++)
+        for (int b = 0; b < 2; b++) {
+            coefs[a][b] = cs->ga_inv * CO_CF(cs, co_cf_ptr(cs, a + 1, b + 1), 0, 0);
+            coefsv[a][b] = csv->ga_inv * CO_CF(csv, co_cf_ptr(csv, a + 1, b + 1), 0, 0);
+        }
+    int nadh = 0, nslip = 0, nplst = 0;
+    for (int i = 0; i < npot; i++) { if (igs->el[i] == CO_ADHES) nadh++; else if (igs->el[i] == CO_SLIP) nslip++; else if (igs->el[i] == CO_PLAST) nplst++; }
+    const double facnel = (double) sqrtf((float) npot / (float) (nadh + nslip + nplst));
+    int itgs = 0;
+    double dif = 2.0, difid = 1.0, dif1 = 0.0;
+    while (dif >= difid && itgs < maxgs) {
+        itgs++;
+        dif = 0.0;
+        if (is_ssrol) co_subnd(cx, mx, my, ps, igs, cs, lg);
+        for (int i = 0; i < k; i++) {
+            const int ii = iel[i];                         /* 0-based element number */
+            if (itgs <= 1000 || itgs % 2 == 0 || igs->el[ii] == CO_ADHES) {
+                double pr[3] = { ps[ii], ps[npot + ii], ps[2L * npot + ii] }, s[2];
+                const int zledge = is_ssrol && lg->ii2j[ii] > 0;
+                if (!is_ssrol) {
+                    s[0] = ws[ii] + co_aijpj(ii + 1, CO_X, ps, igs, CO_TANG, cs);
+                    s[1] = ws[npot + ii] + co_aijpj(ii + 1, CO_Y, ps, igs, CO_TANG, cs);
+                } else if (!zledge) {
+                    s[0] = ws[ii] + co_aijpj(ii + 1, CO_X, ps, igs, CO_TANG, csv);
+                    s[1] = ws[npot + ii] + co_aijpj(ii + 1, CO_Y, ps, igs, CO_TANG, csv);
+                } else {
+                    s[0] = ws[ii] + co_aijpj(ii + 1, CO_X, ps, igs, CO_TANG, cs) - lg->ubnd[2 * lg->ii2j[ii]];
+                    s[1] = ws[npot + ii] + co_aijpj(ii + 1, CO_Y, ps, igs, CO_TANG, cs) - lg->ubnd[2 * lg->ii2j[ii] + 1];
+                }
+                cx->st.n_rowsum += 2;
+                co_plstrc(&igs->el[ii], (!is_ssrol || zledge) ? coefs : coefsv, eps, omegah, omegas, pr, mus[ii], s);
+                dif = dif + (ps[ii] - pr[0]) * (ps[ii] - pr[0]) + (ps[npot + ii] - pr[1]) * (ps[npot + ii] - pr[1]);
+                ps[ii] = pr[0]; ps[npot + ii] = pr[1];
+                ss[ii] = s[0]; ss[npot + ii] = s[1];
+            }
+        }
+        dif = sqrt(dif / (2.0 * k));
+        {
+            double sq = 0.0;
+            for (int i = 0; i < 2 * npot; i++) sq += ps[i] * ps[i];
+            difid = eps * fmax(1e-6, facnel * sqrt(sq / (2.0 * npot)));
+        }
+        if (itgs == 1) dif1 = dif;
+    }
+    double conv = 1.0;
+    if (dif * dif1 != 0.0 && itgs > 1) conv = exp(log(dif / dif1) / (itgs - 1));
+    *err = dif;
+    *info = 0;
+    if (itgs >= maxgs) *info = 1;
+    if (itgs >= maxgs && conv > 0.997) *info = 2;
+    if (itgs >= maxgs && conv > 1.0) *info = 3;
+    *itgs_out = itgs;
 }

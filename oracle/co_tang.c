@@ -190,8 +190,9 @@ static void tang_rhs(co_ctx *cx, int npot, int is_ssrol, const double *facdt, co
 }
 
 /* solver selection and relaxation parameters of stang (m_stang.f90:144-223) */
-typedef struct { int solver; double omegah, omegas, dq; const double *facdt; int info; } tang_opts;
-enum { SOLV_TANGCG = 0, SOLV_STDYGS = 1 };
+typedef struct { int solver; double omegah, omegas, dq; const double *facdt; int info;
+                 co_inflcf *csv; co_leadedge *lg; const int *iel; int is_ssrol; } tang_opts;
+enum { SOLV_TANGCG = 0, SOLV_STDYGS = 1, SOLV_CNVXGS = 2 };
 
 /* one call of the tangential solver + relative forces */
 static void solve_once(co_ctx *cx, co_case *c, tang_opts *o, int npot, co_inflcf *cs, co_inflcf *ms, const double *wstot,
@@ -203,7 +204,11 @@ static void solve_once(co_ctx *cx, co_case *c, tang_opts *o, int npot, co_inflcf
     else {
         int k = 0;
         for (int i = 0; i < npot; i++) if (igs->el[i] >= CO_ADHES) k++;
-        co_stdygs(cx, igs->mx, igs->my, wstot, cs, mus, igs, ps, ss, k, c->eps, c->maxgs, o->omegah, o->omegas, &o->info, it, err);
+        if (o->solver == SOLV_STDYGS)
+            co_stdygs(cx, igs->mx, igs->my, wstot, cs, mus, igs, ps, ss, k, c->eps, c->maxgs, o->omegah, o->omegas, &o->info, it, err);
+        else
+            co_cnvxgs(cx, igs->mx, igs->my, o->is_ssrol, wstot, cs, o->csv, o->lg, mus, igs, ps, ss, k, o->iel, c->eps, c->maxgs,
+                      o->omegah, o->omegas, &o->info, it, err);
     }
     double sx = 0.0, sy = 0.0;
     for (int i = 0; i < npot; i++) sx = sx + ps[i];
@@ -288,7 +293,7 @@ static void solvpt(co_ctx *cx, co_case *c, tang_opts *o, int npot, co_inflcf *cs
 }
 
 /* m_stang.f90:28-746 for L=0, elastic material: shifts with TangCG, steady rolling with SteadyGS */
-static int stang(co_ctx *cx, co_case *c, int npot, co_inflcf *cs, co_inflcf *cv, co_inflcf *ms, const double *hs,
+static int stang(co_ctx *cx, co_case *c, int npot, co_inflcf *cs, co_inflcf *cv, co_inflcf *csv, co_inflcf *ms, const double *hs,
                  const double *pv, const double *x, co_eldiv *igs, double *ps, double *ss, double dxdy, double muscal,
                  double fntrue, double dq, double sens[2][2], int *itgs_out)
 {
@@ -297,25 +302,35 @@ static int stang(co_ctx *cx, co_case *c, int npot, co_inflcf *cs, co_inflcf *cv,
     double *tmp = (double *) calloc(3L * npot, sizeof(double)), *facdt = (double *) malloc(sizeof(double) * npot);
     int ittang = 0, itgs = 0, zready = 0, it, nadh, nslip, nplast, nexter;
     double errpt = 0.0, tol, tol1, tol2, pabs, ww;
-    tang_opts o = { SOLV_TANGCG, 1.0, 1.0, dq, facdt, 0 };
+    co_leadedge lg;
+    memset(&lg, 0, sizeof(lg));
+    int *iel = (int *) malloc(sizeof(int) * npot);
+    tang_opts o = { SOLV_TANGCG, 1.0, 1.0, dq, facdt, 0, csv, &lg, iel, is_ssrol };
     int k = 0;
-    for (int i = 0; i < npot; i++) if (igs->el[i] >= CO_ADHES) k++;
-    if (is_ssrol) {                                                                        /* :136-223 */
+    for (int i = 0; i < npot; i++) if (igs->el[i] >= CO_ADHES) iel[k++] = i;
+    {                                                                                      /* :129-223 */
         int icount = 0;
         for (int iy = 1; iy <= my; iy++) if (igs->el[1 + (iy - 1) * mx - 1] >= CO_ADHES) icount++;
-        o.solver = SOLV_STDYGS;
-        if (icount > 0 || c->gausei == 2 || c->gausei == 5) {     /* ConvexGS / GDsteady are outside this restatement */
-            free(wsfix); free(mus); free(tmp); free(facdt);
+        if (is_ssrol) o.solver = (c->gausei == 5) ? -1 : (c->gausei != 2 ? SOLV_STDYGS : SOLV_CNVXGS);
+        else o.solver = (c->gausei != 2) ? SOLV_TANGCG : SOLV_CNVXGS;
+        if (icount > 0 && (o.solver == SOLV_STDYGS || o.solver == -1)) o.solver = SOLV_CNVXGS;
+        if (o.solver == -1) {                              /* GDsteady is outside this restatement */
+            free(wsfix); free(mus); free(tmp); free(facdt); free(iel);
             *itgs_out = 0;
             return -99;
         }
-        if (k <= 25) { o.omegah = 1.0; o.omegas = 1.0; }
-        else if (c->dx / c->dy <= 5.0) { o.omegah = 0.9; o.omegas = 1.0; }
-        else if (c->dx / c->dy <= 15.0) { o.omegah = 0.8; o.omegas = 0.8; }
-        else { o.omegah = 0.8; o.omegas = 0.6; }
-        co_sxbnd_facdt(mx, my, igs, x, c->dx, dq, facdt);
-    } else
-        for (int i = 0; i < npot; i++) facdt[i] = 1.0;                                    /* sxbnd, .not.is_roll */
+        if (c->gausei == 0 || c->gausei == 4 || c->gausei == 5) {
+            if (k <= 25) { o.omegah = 1.0; o.omegas = 1.0; }
+            else if (is_ssrol && o.solver == SOLV_CNVXGS) { o.omegah = 0.5; o.omegas = 0.5; }
+            else if (is_ssrol) {
+                if (c->dx / c->dy <= 5.0) { o.omegah = 0.9; o.omegas = 1.0; }
+                else if (c->dx / c->dy <= 15.0) { o.omegah = 0.8; o.omegas = 0.8; }
+                else { o.omegah = 0.8; o.omegas = 0.6; }
+            } else { o.omegah = 0.5; o.omegas = 0.5; }
+        } else { o.omegah = c->omegah; o.omegas = c->omegas; }
+        co_sxbnd(mx, my, c->tang == 2 || c->tang == 3, o.solver != SOLV_STDYGS, igs, x, c->dx, dq, &lg);
+        memcpy(facdt, lg.facdt, sizeof(double) * npot);
+    }
     for (int i = 0; i < npot; i++) mus[i] = c->fstat;
     tang_rhs(cx, npot, is_ssrol, facdt, igs, hs, ps, pv, cs, cv, wsfix);
     while (!zready && ittang < c->maxin) {                                                /* :376 */
@@ -355,7 +370,8 @@ static int stang(co_ctx *cx, co_case *c, int npot, co_inflcf *cs, co_inflcf *cv,
     eldiv_count(igs, npot, &nadh, &nslip, &nplast, &nexter);
     if (!zready) ittang = -1;
     *itgs_out = itgs;
-    free(wsfix); free(mus); free(tmp); free(facdt);
+    free(wsfix); free(mus); free(tmp); free(facdt); free(iel);
+    co_leadedge_free(&lg);
     return ittang;
 }
 
@@ -425,7 +441,7 @@ int co_contac(co_case *c)
         }
         if (c->tang == 0 || ncon <= 0) dif = 0.0;
         else {
-            int it = stang(cx, c, npot, &cs, &cv, &ms, hs, pv, x, &igs, ps, ss, dxdy, muscal, fntrue, dq, sens, &itgs);
+            int it = stang(cx, c, npot, &cs, &cv, &csv, &ms, hs, pv, x, &igs, ps, ss, dxdy, muscal, fntrue, dq, sens, &itgs);
             if (it == -99) { unsupported = 1; break; }
             if (it >= 0) ittang += it; else ittang = -1;
             for (int i = 0; i < 3 * npot; i++) po1[i] = po1[i] + (-1.0) * ps[i];

@@ -168,6 +168,7 @@ typedef struct {
     int    fullbox;
     double chi, dq, facphi;             /* rolling direction, step, spin offset factor (<= 0: default 1/6) */
     int    gausei;                      /* G digit */
+    double omegah, omegas;              /* relaxation factors for G = 2, 3 (G = 0, 4: defaults of stang) */
     /* outputs */
     int    *el;                         /* [npot] */
     double *ps;                         /* [3][npot] */
@@ -189,6 +190,15 @@ void   co_plstrc(int *el, const double coef[2][2], double eps, double omegah, do
 void   co_stdygs(co_ctx *cx, int mx, int my, const double *ws, co_inflcf *cs, const double *mus, co_eldiv *igs, double *ps,
                  double *ss, int k, double eps, int maxgs, double omegah, double omegas, int *info, int *itgs_out, double *err);
 void   co_sxbnd_facdt(int mx, int my, const co_eldiv *igs, const double *x, double dx, double dq, double *facdt);
+/* leading-edge administration: t_leadedge, m_leadedge.f90:30-70 (1-based position index j) */
+typedef struct { int npos, *jbnd, *ixbnd, *ii2j; double *xbnd, *facdx, *ubnd, *facdt; } co_leadedge;
+void   co_sxbnd(int mx, int my, int is_roll, int use_ledg, const co_eldiv *igs, const double *x, double dx, double dq,
+                co_leadedge *lg);
+void   co_leadedge_free(co_leadedge *lg);
+void   co_subnd(co_ctx *cx, int mx, int my, const double *p, const co_eldiv *pel, const co_inflcf *c, co_leadedge *lg);
+void   co_cnvxgs(co_ctx *cx, int mx, int my, int is_ssrol, const double *ws, co_inflcf *cs, co_inflcf *csv, co_leadedge *lg,
+                 const double *mus, co_eldiv *igs, double *ps, double *ss, int k, const int *iel, double eps, int maxgs,
+                 double omegah, double omegas, int *info, int *itgs_out, double *err);
 
 /* ---- subsurface stresses (co_subsurf.c) ---- */
 void   co_stres1_pcwcns(double dx, double dy, double gg, double v[3][3][4], double vnu[3][3][4], const double xw[3],

@@ -258,6 +258,7 @@ class Case(C.Structure):
                 ("fxrel", C.c_double), ("fyrel", C.c_double), ("fstat", C.c_double), ("fkin", C.c_double),
                 ("maxgs", C.c_int), ("maxin", C.c_int), ("maxnr", C.c_int), ("maxout", C.c_int), ("eps", C.c_double),
                 ("fullbox", C.c_int), ("chi", C.c_double), ("dq", C.c_double), ("facphi", C.c_double), ("gausei", C.c_int),
+                ("omegah", C.c_double), ("omegas", C.c_double),
                 ("el", c_int_p), ("ps", c_dbl_p), ("ss", c_dbl_p),
                 ("pen_out", C.c_double), ("fn_out", C.c_double), ("fx_out", C.c_double), ("fy_out", C.c_double),
                 ("itnorm", C.c_int), ("ittang", C.c_int), ("itcg_norm", C.c_int), ("itgs_tang", C.c_int),
@@ -267,7 +268,7 @@ class Case(C.Structure):
 
 def contac(g, gg, poiss, tang=0, norm=0, force3=0, pen=0.0, fn=0.0, cksi=0.0, ceta=0.0, cphi=0.0, fxrel=0.0, fyrel=0.0,
            fstat=0.3, fkin=0.3, maxgs=999, maxin=20, maxnr=25, maxout=1, eps=1e-5, fullbox=False, nn=0, chi=0.0, dq=1.0,
-           facphi=0.0, gausei=0):
+           facphi=0.0, gausei=0, omegah=0.9, omegas=0.9):
     """One module-3 case (T = 0/1/3) through the oracle's contac/panprc. g: dict mx,my,xl,yl,dx,dy,ibase,prmudf."""
     npot = g["mx"] * g["my"]
     prm = np.ascontiguousarray(g["prmudf"], dtype=np.float64)
@@ -280,6 +281,7 @@ def contac(g, gg, poiss, tang=0, norm=0, force3=0, pen=0.0, fn=0.0, cksi=0.0, ce
     c.pen, c.fn, c.cksi, c.ceta, c.cphi, c.fxrel, c.fyrel, c.fstat, c.fkin = pen, fn, cksi, ceta, cphi, fxrel, fyrel, fstat, fkin
     c.maxgs, c.maxin, c.maxnr, c.maxout, c.eps, c.fullbox = maxgs, maxin, maxnr, maxout, eps, int(fullbox)
     c.chi, c.dq, c.facphi, c.gausei = chi, dq, facphi, gausei
+    c.omegah, c.omegas = omegah, omegas
     c.el, c.ps, c.ss = _i(el), _d(ps), _d(ss)
     L = lib()
     L.co_contac.restype = C.c_int

@@ -36,8 +36,9 @@ def main():
             its = [cb.lowlevel.get_iterations(ire, 1) for ire in ires]
             pr = cb.lowlevel.steady_prof()
             if pr["steps"]:
-                print("   cycles per element step: plstrc %.0f, re-integration %.0f, update+barriers %.0f (%d steps, %d calls)" % (
-                    pr["plstrc"] / pr["steps"], pr["reintegrate"] / pr["steps"], pr["update"] / pr["steps"], pr["steps"], pr["calls"]))
+                print("   cycles per element step: plstrc %.0f, re-integration %.0f, in-row update %.0f, other rows %.0f (%d steps, %d calls)" % (
+                    pr["plstrc"] / pr["steps"], pr["reintegrate"] / pr["steps"], pr["update"] / pr["steps"], pr["rowupdate"] / pr["steps"], pr["steps"], pr["calls"]))
+                print("   changes per step %.2f, net changes per row-block total %d" % (pr["changes"] / pr["steps"], pr["rowchanges"]))
             print("T=%d rep %d: %d cases in %.3f s = %.1f cases/s; ierr %s; mean itgs %.1f max %d, ncon %.0f" % (
                 tang, rep, n, dt, n / dt, sorted(set(ierr.tolist())), np.mean([t["itgs"] for t in its]),
                 max(t["itgs"] for t in its), np.mean([t["ncon"] for t in its])))
