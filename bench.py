@@ -342,6 +342,13 @@ def run_gpu(args):
         achieved = nprod * alg_bytes_prod / (kernel_ms * 1e-3) / 1e9          # per launch = this rank's cases
         fp64_peak = ll.fp64_peak_tflops(3)
         fp64_ach = nprod * alg_flops_prod / (kernel_ms * 1e-3) / 1e12
+        traffic = None
+        try:                                    # dram bytes per case of the dominant kernel from the committed ncu capture
+            import glob
+            tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_r*.json")))[-1]
+            traffic = json.load(open(tf))["k_snorm_batch"]["dram_bytes_per_case"] * ncase
+        except Exception:
+            pass
         h2d = int(p_hs.numel() * 8 + p_el.numel() * 4 + p_pn.numel() * 8 + p_scal.numel() * 8)
         d2h = int(p_pn.numel() * 8 + p_el.numel() * 4 + p_un.numel() * 8 + p_scal.numel() * 8)
         out = {
@@ -354,7 +361,7 @@ def run_gpu(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_snorm_batch", "achieved": achieved, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                          "note": "batched 91x91 products are FP64/shared-memory bound, not HBM bound; see roofline_fp64"},
             "roofline_fp64": {"achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s",
                               "frac": fp64_ach / fp64_peak if fp64_peak > 0 else None,

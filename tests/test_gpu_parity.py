@@ -637,7 +637,7 @@ def test_large_grid_shift_4s_golden(cb, mbench):
 def test_large_grid_shift_8s_golden(cb, mbench):
     """perfc_test/tang_problm_8s.inp (575x647 = 372 025 elements): nslp = 111191 (perfc_test/get_times.ref_out:24, 167 s
     on the 2016 host).  The TangCG iteration count is rounding-sensitive at this size (active-set changes close to the
-    tolerance): the 2016 ifort/MKL build needed 190, the CPU oracle needs 226 with the reference's bounding-box products,
+    tolerance): the 2016 ifort/MKL build needed 190, the CPU oracle needs 226 (with bounding-box and with full-grid products),
     this path 207 -- so the count is only bounded here, the slip area is exact."""
     its, el, pn, px, py, forces = _large_shift_case(cb, 75, mbench, 575, 647, 0.0125)
     assert int((el == 2).sum()) == 111191 and 150 <= its["itgs"] <= 260

@@ -64,5 +64,50 @@ json.dump({"k_snorm_batch": {"dram_bytes_per_case": traffic / ncase, "cases_in_c
                              "source": "profiles/ncu_%s.txt" % tag}}, open("profiles/traffic_%s.json" % tag, "w"))
 out.append("")
 out.append("dram traffic per launch (148 cases): %.1f MB = %.2f MB per case" % (traffic / 1e6, traffic / 1e6 / ncase))
+
+# 3. the three phase kernels of the whole-GPU product (575x647), one launch each
+import os
+if os.path.exists("gpurun_out/prof_large_%s.ncu-rep" % tag):
+    raw = subprocess.run(["ncu", "-i", "gpurun_out/prof_large_%s.ncu-rep" % tag, "--page", "raw", "--csv"],
+                         capture_output=True, text=True).stdout
+    rr = list(csv.reader(raw.splitlines()))
+    hh, units = rr[0], rr[1]
+    out.append("")
+    out.append("# ncu --set full --clock-control none -k regex:k_lg_ : python tools/large_product_only.py (575x647, 1x1 product)")
+    ki = hh.index("Kernel Name")
+    for vals in rr[2:]:
+        out.append("## " + vals[ki][:60])
+        for i, nme in enumerate(hh):
+            if nme in want:
+                out.append("%-90s %-12s %s" % (nme, units[i], vals[i]))
+
+# 4. where the warp-stall samples of the dominant kernel sit, by SASS opcode (source page, SASS view)
+src = subprocess.run(["ncu", "-i", "gpurun_out/prof_snorm_%s.ncu-rep" % tag, "--page", "source", "--csv"],
+                     capture_output=True, text=True).stdout
+rs = list(csv.reader(src.splitlines()))
+hi = next((i for i, r in enumerate(rs) if r and r[0] == "Address"), None)
+if hi is not None:
+    hdr = rs[hi]
+    si, ci, ei = hdr.index("Source"), hdr.index("Warp Stall Sampling (All Samples)"), hdr.index("Instructions Executed")
+    byop = collections.defaultdict(lambda: [0.0, 0.0])
+    tot = 0.0
+    for r in rs[hi + 1:]:
+        if len(r) <= max(ci, ei):
+            continue
+        try:
+            smp, exe = float(r[ci]), float(r[ei])
+        except ValueError:
+            continue
+        toks = r[si].split()
+        op = toks[1] if toks and toks[0].startswith("@") and len(toks) > 1 else (toks[0] if toks else "?")
+        op = op.split(".")[0] + ("." + op.split(".")[1] if op.startswith(("LD", "ST", "BAR")) and "." in op else "")
+        byop[op][0] += smp; byop[op][1] += exe
+        tot += smp
+    out.append("")
+    out.append("# k_snorm_batch: warp-stall samples by SASS opcode (ncu source page; total %.0f samples)" % tot)
+    for op, (smp, exe) in sorted(byop.items(), key=lambda kv: -kv[1][0])[:18]:
+        out.append("%-12s %6.2f%% of samples   %12.0f warp-instructions executed" % (op, 100 * smp / max(tot, 1), exe))
+else:
+    out.append("# (source page not available)")
 open("profiles/ncu_%s.txt" % tag, "w").write("\n".join(out) + "\n")
 print("\n".join(out))
