@@ -59,6 +59,8 @@ struct Problem {
     int ncase = 0, itnorm = 0, ittang = 0, itcg = 0, ncon = 0, nadh = 0, nslip = 0, status = 0;
     std::vector<int> el;
     std::vector<double> ps, us, hs, ss;  // [3][npot]
+    std::vector<double> pv;              // [3][npot] tractions of the previous time instance (set_prev_data)
+    double hz_cp = 0, hz_rho = 0;
     int itgs = 0;
     std::vector<int> nr_itcg;            // TangCG iterations per solver call of the Newton-Raphson process
     double fcntc[3] = { 0, 0, 0 }, mztrue = 0;
@@ -202,12 +204,86 @@ inline int check_scope(const Problem &p)
     if (p.mater != 0) { last_error() = "M-digit: only the elastic half-space (M=0) is in the hot-path scope"; return CNTC_err_other; }
     if (p.gencr != 2 && p.gencr != 1) { last_error() = "C-digit: only piecewise-constant analytical coefficients (C=2)"; return CNTC_err_other; }
     if (p.bound != 0) { last_error() = "B-digit: only the full normal problem (B=0)"; return CNTC_err_other; }
-    if (p.ipotcn < 1 || p.ipotcn > 4) { last_error() = "IPOTCN: Hertzian input is not yet served by the B200 path"; return CNTC_err_other; }
+    if (!((p.ipotcn >= 1 && p.ipotcn <= 4) || p.ipotcn == -1 || p.ipotcn == -3)) { last_error() = "IPOTCN: only 1..4 and the 3D Hertzian options -1, -3 are served by the B200 path"; return CNTC_err_other; }
     if (p.iplan != 1) { last_error() = "IPLAN: only the unrestricted planform"; return CNTC_err_other; }
     if (p.ibase != 1 && p.ibase != 2 && p.ibase != 3 && p.ibase != 9) { last_error() = "invalid IBASE"; return CNTC_err_input; }
     if (p.ibase == 9 && (int) p.prmudf.size() < p.mx * p.my) { last_error() = "IBASE=9 needs npot values"; return CNTC_err_input; }
     return 0;
 }
+
+// complete elliptic integrals K, E and the associate integrals B = (E - mc K)/m, D = (K - E)/m by the arithmetic-
+// geometric mean (the reference uses Fukushima's series, m_hertz.f90:509-...; same functions, own evaluation).
+// D stays finite for m -> 0: (K - E)/K = (1/2) sum 2^n c_n^2 with c_0^2 = m, evaluated divided by m term by term.
+inline void ellip_kebd(double mc, double &K, double &E, double &B, double &D)
+{
+    const double pi = 3.14159265358979323846, m = 1.0 - mc;
+    double a = 1.0, b = sqrt(mc);
+    double t = (1.0 - b) / (4.0 * (1.0 + b));        // c_1^2 / m
+    double sum = 1.0 + 2.0 * t, pw = 2.0;
+    double an = 0.5 * (a + b), bn = sqrt(a * b);
+    double c2 = t * m;                                  // c_1^2
+    a = an; b = bn;
+    for (int it = 0; it < 40 && fabs(a - b) > 1e-17 * a; it++) {
+        an = 0.5 * (a + b); bn = sqrt(a * b);
+        const double cn = 0.5 * (a - b);               // c_{n+1} = (a_n - b_n)/2
+        pw *= 2.0;
+        t = (m > 0.0) ? cn * cn / m : 0.0;
+        if (m <= 1e-300) t = 0.0;
+        sum += pw * t;
+        c2 = cn * cn;
+        a = an; b = bn;
+    }
+    (void) c2;
+    K = pi / (2.0 * a);
+    D = 0.5 * K * sum;
+    B = K - D;
+    E = B + mc * D;
+}
+
+// hzcalc3d (m_hertz.f90:267-385): 3D Hertzian point contact.  ipotcn -1: curvatures given, -3: semi-axes given;
+// ic_norm 0: approach given, 1: normal force given
+inline void hertz3d(double e_star, int ipotcn, double &a1, double &b1, double &aa, double &bb, int ic_norm, double &pen,
+                    double &fn, double &cp, double &rho)
+{
+    const double pi = 3.14159265358979323846;
+    double K, E, B, D;
+    auto eli = [&](double k) { ellip_kebd(1.0 - k * k, K, E, B, D); return (E - B) / B; };
+    if (ipotcn == -1) {
+        const bool zbla = b1 <= a1;
+        const double y = zbla ? b1 / a1 : a1 / b1;
+        double xl = 0.0, xr = 1.0, elr = eli(xr), ell = eli(xl), x = 0.5;      // bisection on the modulus, :386-440
+        while (fabs(xr - xl) > 1e-9) {
+            x = 0.5 * (xl + xr);
+            const double elx = eli(x);
+            if ((y - elr) * (y - elx) <= 0.0) { xl = x; ell = elx; } else { xr = x; elr = elx; }
+        }
+        (void) ell;
+        eli(x);
+        const double g = sqrt(std::max(1e-40, 1.0 - x * x)), sg = sqrt(g);
+        rho = 2.0 / (a1 + b1);
+        if (ic_norm == 1) { cp = pow(3.0 * std::max(0.0, fn) * rho * E / (4.0 * pi * e_star * sg), 1.0 / 3.0); pen = 2.0 * (cp * sg) * (cp * sg) * K / (rho * E); }
+        else { cp = sqrt(std::max(0.0, pen) * rho * E / (2.0 * K * sg * sg)); fn = 4.0 * pi * cp * cp * cp * e_star * sg / (3.0 * rho * E); }
+        if (zbla) { aa = cp * sg; bb = cp / sg; } else { aa = cp / sg; bb = cp * sg; }
+    } else {
+        const bool zbla = bb <= aa;
+        const double g = zbla ? bb / aa : aa / bb, sg = sqrt(g), k = sqrt(1.0 - g * g);
+        const double y = eli(k);
+        cp = sqrt(aa * bb);
+        if (ic_norm == 1) { rho = 4.0 * pi * cp * cp * cp * e_star * sg / (3.0 * fn * E); pen = 2.0 * (cp * sg) * (cp * sg) * K / (rho * E); }
+        else {
+            pen = std::max(pen, 1e-9);
+            rho = 2.0 * (cp * sg) * (cp * sg) * K / (pen * E);
+            fn = 4.0 * pi * cp * cp * cp * e_star * sg / (3.0 * rho * E);
+        }
+        const double apb = 2.0 / rho, ama = apb / (y + 1.0), ami = y * ama;
+        if (zbla) { a1 = ami; b1 = ama; } else { a1 = ama; b1 = ami; }
+    }
+}
+
+struct Problem;
+// hzsol + potcon_hertz (m_hertz.f90:29-91, m_hierarch_data.f90:1889-1959) for IPOTCN = -1, -3: quadratic geometry from
+// the Hertz solution, potential contact = scale * contact ellipse
+inline int hertz_setup(Problem &p);
 
 // check_roll_stepsize (m_sdis.f90:125-204): SteadyGS forces chi = 0 and dq = dx; shifts use chi = 0, dq = 1
 inline void roll_stepsize(const Problem &p, double &chi, double &dq)
@@ -218,6 +294,22 @@ inline void roll_stepsize(const Problem &p, double &chi, double &dq)
     } else { chi = 0.0; dq = 1.0; }
 }
 
+
+inline int hertz_setup(Problem &p)
+{
+    if (p.ipotcn != -1 && p.ipotcn != -3) { last_error() = "IPOTCN: only the 3D Hertzian options -1 (curvatures) and -3 (semi-axes) are served by the B200 path"; return CNTC_err_other; }
+    const double e_star = p.mat.ga / (1.0 - p.mat.nu);
+    hertz3d(e_star, p.ipotcn, p.hz_a1, p.hz_b1, p.hz_aa, p.hz_bb, p.norm, p.pen, p.fntrue, p.hz_cp, p.hz_rho);
+    p.ibase = 1; p.iplan = 1;
+    p.prmudf.assign(10, 0.0);
+    p.prmudf[0] = p.hz_a1; p.prmudf[2] = p.hz_b1;
+    p.xl = -p.hz_scale * std::max(1e-9, p.hz_aa); p.yl = -p.hz_scale * std::max(1e-9, p.hz_bb);
+    p.xh = -p.xl; p.yh = -p.yl;
+    p.dx = (p.xh - p.xl) / p.mx; p.dy = (p.yh - p.yl) / p.my;           // potcon_fill with ipotcn = 2
+    p.xc1 = p.xl + 0.5 * p.dx; p.yc1 = p.yl + 0.5 * p.dy;
+    p.xcm = p.xc1 + (p.mx - 1) * p.dx; p.ycm = p.yc1 + (p.my - 1) * p.dy;
+    return 0;
+}
 
 // contac (m_scontc.f90:37-216) for a batch of problems: host set-up, ONE device launch per coefficient class, gather
 inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int> &ierr)
@@ -235,14 +327,43 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
         if ((ierr[k] = check_scope(p))) continue;
         combine_material(p.mat);
         if (p.ncase <= 1) p.pvtime = 2;                                   // check_case, m_scontc.f90:268-274
+        if (p.ipotcn < 0 && (ierr[k] = hertz_setup(p))) continue;         // contac, m_scontc.f90:81-91
         undeformed_distance(p, hs[k]);
         const int npot = p.mx * p.my;
+        const bool have_prev = p.solved && (int) p.el.size() == npot && (int) p.ps.size() == 3 * npot;
+        // set_prev_data (m_sdis.f90:208-317): P = 0 full sequence, 1 sequence for the normal part, 2 initiation of contact
+        if (p.pvtime == 0 && have_prev) p.pv = p.ps;
+        else if (p.pvtime == 1 && have_prev) { p.pv.assign(3 * (size_t) npot, 0.0); std::copy(p.ps.begin() + 2 * (size_t) npot, p.ps.end(), p.pv.begin() + 2 * (size_t) npot); }
+        else if (p.pvtime != 3 || (int) p.pv.size() != 3 * npot) p.pv.assign(3 * (size_t) npot, 0.0);
+        // init_curr_data (m_sdis.f90:587-768)
         double pen = p.pen;
-        if (p.iestim == 0 || (int) p.el.size() != npot) {
-            initial_eldiv(p, hs[k], el0[k], pen);
+        const int iestim = have_prev ? p.iestim : 0;
+        if (iestim == 0) {
             p.ps.assign(3 * (size_t) npot, 0.0);
+            if (p.ipotcn < 0 && p.bound == 0) {                           // Hertzian solution as initial estimate, :640-700
+                const double pi = 3.14159265358979323846, pnmax = 3.0 * p.fntrue / (2.0 * pi * p.hz_aa * p.hz_bb);
+                el0[k].assign(npot, 0);
+                for (int iy = 0; iy < p.my; iy++) for (int ix = 0; ix < p.mx; ix++) {
+                    const double x = p.xc1 + ix * p.dx, y = p.yc1 + iy * p.dy;
+                    const double f = 1.0 - (x / p.hz_aa) * (x / p.hz_aa) - (y / p.hz_bb) * (y / p.hz_bb);
+                    const double v = pnmax * sqrt(std::max(0.0, f));
+                    p.ps[2 * (size_t) npot + iy * p.mx + ix] = v;
+                    el0[k][iy * p.mx + ix] = v > 1e-20 ? 1 : 0;
+                }
+            } else
+                initial_eldiv(p, hs[k], el0[k], pen);
         } else {
-            el0[k] = p.el;                                                // I>=1: keep element division and tractions
+            el0[k] = p.el;                                                // I >= 1: keep the element division
+            if (iestim == 2 || p.tang == 0) std::fill(p.ps.begin(), p.ps.begin() + 2 * (size_t) npot, 0.0);
+            if (iestim == 1) {                                            // regularise the tractions, :722-735
+                for (int i = 0; i < npot; i++) {
+                    double &px = p.ps[i], &py = p.ps[npot + i], &pn = p.ps[2 * (size_t) npot + i];
+                    if (el0[k][i] <= 0) { px = py = pn = 0.0; }
+                    else if (el0[k][i] == 2) { const double pa = std::max(1e-10, sqrt(px * px + py * py)); px = p.fstat * pn * px / pa; py = p.fstat * pn * py / pa; }
+                }
+            }
+            if (iestim == 2) for (int i = 0; i < npot; i++) if (el0[k][i] >= 1) el0[k][i] = 1;
+            for (int i = 0; i < npot; i++) if (hs[k][i] > (double) 1e29f) el0[k][i] = 0;
         }
         pen0[k] = pen;
         if (p.ret > 1) { ierr[k] = 0; continue; }                        // R=2,3: checks only
@@ -278,8 +399,8 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
         if (!rc && cs.key.is_roll)                                  // ConvexGS in steady rolling works with csv = cs - cv
             for (int ik = 1; ik <= 2 && !rc; ik++) for (int jk = 1; jk <= 2 && !rc; jk++) rc = build_chat(cs, SET_CSV, ik, jk, 0);
         if (rc) { fail(rc); continue; }
-        // device buffers: per case hs_n(1) hst(2) ps(3) ss(2) work(9) twork(24) = 41 n doubles, el n ints
-        const size_t per = (size_t) 41 * npot;
+        // device buffers: per case hs_n(1) hst(2) ps(3) ss(2) work(9) twork(24) pv(3) = 44 n doubles, el n ints
+        const size_t per = (size_t) 44 * npot;
         double *d_buf = nullptr; int *d_el = nullptr, *d_next = nullptr; ContactCase *d_cases = nullptr;
         if (cudaMalloc(&d_buf, sizeof(double) * per * n) != cudaSuccess || cudaMalloc(&d_el, sizeof(int) * (size_t) n * npot) != cudaSuccess ||
             cudaMalloc(&d_cases, sizeof(ContactCase) * n) != cudaSuccess || cudaMalloc(&d_next, sizeof(int)) != cudaSuccess) {
@@ -310,8 +431,11 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
             nc.pen = pen0[ks[i]]; nc.fntrue = p.fntrue;
             c.tang = p.tang; c.force3 = p.force3; c.maxnr = p.maxnr; c.maxout = p.maxout;
             c.cksi = p.cksi; c.ceta = p.ceta; c.fxrel = p.fxrel; c.fyrel = p.fyrel; c.fstat = p.fstat;
-            if (p.iestim == 0 || p.iestim == 2) { if (p.force3 >= 1) c.cksi = 1e-6; if (p.force3 == 2) c.ceta = 0.0; }   // m_sdis.f90:760-762
-            c.pv = nullptr;
+            if (!p.solved || p.iestim == 0 || p.iestim == 2) { if (p.force3 >= 1) c.cksi = 1e-6; if (p.force3 == 2) c.ceta = 0.0; }   // m_sdis.f90:760-762
+            bool pv_nonzero = false;
+            for (double v : p.pv) if (v != 0.0) { pv_nonzero = true; break; }
+            c.pv = (pv_nonzero && p.tang == 1) ? base + 41 * (size_t) npot : nullptr;
+            if (c.pv) cudaMemcpy(base + 41 * (size_t) npot, p.pv.data(), sizeof(double) * 3 * npot, cudaMemcpyHostToDevice);
             double chi_e, dq_e;
             roll_stepsize(p, chi_e, dq_e);
             const bool is_roll = cs.key.is_roll != 0;

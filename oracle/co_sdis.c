@@ -107,3 +107,70 @@ void co_eldiv0(int ic_norm, int mx, int my, double dx, double dy, int ibase, con
     for (int i = 0; i < npot; i++)                                          /* :999-1005 */
         igs->el[i] = (hs[i] - hsmin < facpen * pentru) ? CO_ADHES : CO_EXTER;
 }
+
+/* complete elliptic integrals by the AGM: K, E, B = (E - mc K)/m, D = (K - E)/m (finite for m -> 0).  The reference
+ * evaluates the same functions with Fukushima's series (m_hertz.f90:446-520, ellip_bd). */
+void co_ellip_kebd(double mc, double *K, double *E, double *B, double *D)
+{
+    const double m = 1.0 - mc;
+    double a = 1.0, b = sqrt(mc);
+    double t = (1.0 - b) / (4.0 * (1.0 + b));
+    double sum = 1.0 + 2.0 * t, pw = 2.0;
+    double an = 0.5 * (a + b), bn = sqrt(a * b);
+    a = an; b = bn;
+    for (int it = 0; it < 40 && fabs(a - b) > 1e-17 * a; it++) {
+        an = 0.5 * (a + b); bn = sqrt(a * b);
+        const double cn = 0.5 * (a - b);
+        pw *= 2.0;
+        t = (m > 1e-300) ? cn * cn / m : 0.0;
+        sum += pw * t;
+        a = an; b = bn;
+    }
+    *K = CO_PI / (2.0 * a);
+    *D = 0.5 * *K * sum;
+    *B = *K - *D;
+    *E = *B + mc * *D;
+}
+
+static double eli_(double k, double *K, double *E)
+{
+    double B, D;
+    co_ellip_kebd(1.0 - k * k, K, E, &B, &D);
+    return (*E - B) / B;
+}
+
+/* m_hertz.f90:267-385 (hzcalc3d) with bisec (:386-440) */
+void co_hertz3d(double e_star, int ipotcn, double *a1, double *b1, double *aa, double *bb, int ic_norm, double *pen,
+                double *fn, double *cp, double *rho)
+{
+    double K, E;
+    if (ipotcn == -1) {
+        const int zbla = *b1 <= *a1;
+        const double y = zbla ? *b1 / *a1 : *a1 / *b1;
+        double xl = 0.0, xr = 1.0, elr = eli_(xr, &K, &E), x = 0.5;
+        while (fabs(xr - xl) > 1e-9) {
+            x = 0.5 * (xl + xr);
+            const double elx = eli_(x, &K, &E);
+            if ((y - elr) * (y - elx) <= 0.0) xl = x; else { xr = x; elr = elx; }
+        }
+        eli_(x, &K, &E);
+        const double g = sqrt(fmax(1e-40, 1.0 - x * x)), sg = sqrt(g);
+        *rho = 2.0 / (*a1 + *b1);
+        if (ic_norm == 1) { *cp = pow(3.0 * fmax(0.0, *fn) * *rho * E / (4.0 * CO_PI * e_star * sg), 1.0 / 3.0); *pen = 2.0 * (*cp * sg) * (*cp * sg) * K / (*rho * E); }
+        else { *cp = sqrt(fmax(0.0, *pen) * *rho * E / (2.0 * K * sg * sg)); *fn = 4.0 * CO_PI * *cp * *cp * *cp * e_star * sg / (3.0 * *rho * E); }
+        if (zbla) { *aa = *cp * sg; *bb = *cp / sg; } else { *aa = *cp / sg; *bb = *cp * sg; }
+    } else {
+        const int zbla = *bb <= *aa;
+        const double g = zbla ? *bb / *aa : *aa / *bb, sg = sqrt(g), k = sqrt(1.0 - g * g);
+        const double y = eli_(k, &K, &E);
+        *cp = sqrt(*aa * *bb);
+        if (ic_norm == 1) { *rho = 4.0 * CO_PI * *cp * *cp * *cp * e_star * sg / (3.0 * *fn * E); *pen = 2.0 * (*cp * sg) * (*cp * sg) * K / (*rho * E); }
+        else {
+            *pen = fmax(*pen, 1e-9);
+            *rho = 2.0 * (*cp * sg) * (*cp * sg) * K / (*pen * E);
+            *fn = 4.0 * CO_PI * *cp * *cp * *cp * e_star * sg / (3.0 * *rho * E);
+        }
+        const double apb = 2.0 / *rho, ama = apb / (y + 1.0), ami = y * ama;
+        if (zbla) { *a1 = ami; *b1 = ama; } else { *a1 = ama; *b1 = ami; }
+    }
+}

@@ -378,6 +378,18 @@ static int stang(co_ctx *cx, co_case *c, int npot, co_inflcf *cs, co_inflcf *cv,
 /* contac (m_scontc.f90:37-216) + panprc (:356-553) for module-3 cases: T = 0, 1 or 3 (SteadyGS), N = 0/1, F = 0/1/2, I = 0, P = 2 */
 int co_contac(co_case *c)
 {
+    /* Hertzian input (hzsol + potcon_hertz, m_hertz.f90:29-91, m_hierarch_data.f90:1889-1959) */
+    double hz_prm[6] = { 0, 0, 0, 0, 0, 0 };
+    if (c->ipotcn == -1 || c->ipotcn == -3) {
+        co_mater hm = { { c->gg[0], c->gg[1] }, { c->poiss[0], c->poiss[1] }, 0, 0, 0 };
+        co_combin_mater(&hm);
+        double cp, rho;
+        co_hertz3d(hm.ga / (1.0 - hm.nu), c->ipotcn, &c->hz_a1, &c->hz_b1, &c->hz_aa, &c->hz_bb, c->norm, &c->pen, &c->fn, &cp, &rho);
+        hz_prm[0] = c->hz_a1; hz_prm[2] = c->hz_b1;
+        c->ibase = 1; c->prmudf = hz_prm;
+        c->xl = -c->hz_scale * fmax(1e-9, c->hz_aa); c->yl = -c->hz_scale * fmax(1e-9, c->hz_bb);
+        c->dx = (-c->xl - c->xl) / c->mx; c->dy = (-c->yl - c->yl) / c->my;
+    }
     const int mx = c->mx, my = c->my, npot = mx * my;
     co_ctx *cx = co_ctx_new();
     cx->fullbox = c->fullbox;
@@ -414,11 +426,38 @@ int co_contac(co_case *c)
     co_eldiv igs;
     co_eldiv_init(&igs, mx, my);
     double pen = c->pen, fntrue = c->fn;
-    co_eldiv0(c->norm, mx, my, c->dx, c->dy, c->ibase, c->prmudf, &mat, fntrue, &pen, hs + 2L * npot, &igs);
+    if (c->pv_in) memcpy(pv, c->pv_in, sizeof(double) * 3 * npot);                            /* set_prev_data */
+    const int iestim = (c->el_in && c->ps_in) ? c->iestim : 0;
+    if (iestim == 0) {                                                                       /* init_curr_data, m_sdis.f90:587-768 */
+        if (c->ipotcn == -1 || c->ipotcn == -3) {
+            const double pnmax = 3.0 * fntrue / (2.0 * CO_PI * c->hz_aa * c->hz_bb);
+            for (int i = 0; i < npot; i++) {
+                const double f = 1.0 - (x[i] / c->hz_aa) * (x[i] / c->hz_aa) - (y[i] / c->hz_bb) * (y[i] / c->hz_bb);
+                ps[2L * npot + i] = pnmax * sqrt(fmax(0.0, f));
+                igs.el[i] = ps[2L * npot + i] > 1e-20 ? CO_ADHES : CO_EXTER;
+            }
+        } else
+            co_eldiv0(c->norm, mx, my, c->dx, c->dy, c->ibase, c->prmudf, &mat, fntrue, &pen, hs + 2L * npot, &igs);
+    } else {
+        memcpy(igs.el, c->el_in, sizeof(int) * npot);
+        memcpy(ps, c->ps_in, sizeof(double) * 3 * npot);
+        if (iestim == 2 || c->tang == 0) memset(ps, 0, sizeof(double) * 2 * npot);
+        if (iestim == 1)
+            for (int i = 0; i < npot; i++) {
+                if (igs.el[i] <= CO_EXTER) { ps[i] = 0.0; ps[npot + i] = 0.0; ps[2L * npot + i] = 0.0; }
+                else if (igs.el[i] == CO_SLIP) {
+                    const double pa = fmax(1e-10, sqrt(ps[i] * ps[i] + ps[npot + i] * ps[npot + i]));
+                    ps[i] = c->fstat * ps[2L * npot + i] * ps[i] / pa; ps[npot + i] = c->fstat * ps[2L * npot + i] * ps[npot + i] / pa;
+                }
+            }
+        if (iestim == 2) for (int i = 0; i < npot; i++) if (igs.el[i] >= CO_ADHES) igs.el[i] = CO_ADHES;
+    }
     for (int i = 0; i < npot; i++) if (hs[2L * npot + i] > (double) 1e29f) igs.el[i] = CO_EXTER;
     co_areas(&igs);
-    if (c->force3 >= 1) c->cksi = 1e-6;
-    if (c->force3 == 2) c->ceta = 0.0;
+    if (iestim == 0 || iestim == 2) {
+        if (c->force3 >= 1) c->cksi = 1e-6;
+        if (c->force3 == 2) c->ceta = 0.0;
+    }
     double sens[2][2] = { { 0, 0 }, { 0, 0 } };
 
     /* panprc */

@@ -178,7 +178,17 @@ typedef struct {
     int    nr_n, nr_itcg[CO_MAXNR];     /* one entry per tangential solver call of the Newton-Raphson process */
     double nr_cksi[CO_MAXNR], nr_ceta[CO_MAXNR], nr_fx[CO_MAXNR], nr_fy[CO_MAXNR];
     long   n_prod;
+    /* sequences of cases and Hertzian input (appended; zero = not used) */
+    int    iestim;                      /* I digit: 0 new initial estimate, 1 regularised previous solution, 2, 3 */
+    const int    *el_in;                /* [npot] previous element division (I >= 1) */
+    const double *ps_in;                /* [3][npot] previous tractions (I >= 1) */
+    const double *pv_in;                /* [3][npot] tractions of the previous time instance (P = 0/1), NULL = zero */
+    int    ipotcn;                      /* -1 / -3: 3D Hertzian geometry (curvatures / semi-axes given); else grid as given */
+    double hz_a1, hz_b1, hz_aa, hz_bb, hz_scale;
 } co_case;
+void   co_ellip_kebd(double mc, double *K, double *E, double *B, double *D);
+void   co_hertz3d(double e_star, int ipotcn, double *a1, double *b1, double *aa, double *bb, int ic_norm, double *pen,
+                  double *fn, double *cp, double *rho);
 
 void   co_tangcg(co_ctx *cx, int npot, int maxcg, double eps, const double *ws, co_inflcf *cs, co_inflcf *ms,
                  const double *mu, co_eldiv *igs, double *ps, double *ss, int *itcg, double *err);

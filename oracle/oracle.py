@@ -263,12 +263,15 @@ class Case(C.Structure):
                 ("pen_out", C.c_double), ("fn_out", C.c_double), ("fx_out", C.c_double), ("fy_out", C.c_double),
                 ("itnorm", C.c_int), ("ittang", C.c_int), ("itcg_norm", C.c_int), ("itgs_tang", C.c_int),
                 ("nr_n", C.c_int), ("nr_itcg", C.c_int * 64), ("nr_cksi", C.c_double * 64), ("nr_ceta", C.c_double * 64),
-                ("nr_fx", C.c_double * 64), ("nr_fy", C.c_double * 64), ("n_prod", C.c_long)]
+                ("nr_fx", C.c_double * 64), ("nr_fy", C.c_double * 64), ("n_prod", C.c_long),
+                ("iestim", C.c_int), ("el_in", c_int_p), ("ps_in", c_dbl_p), ("pv_in", c_dbl_p),
+                ("ipotcn", C.c_int), ("hz_a1", C.c_double), ("hz_b1", C.c_double), ("hz_aa", C.c_double),
+                ("hz_bb", C.c_double), ("hz_scale", C.c_double)]
 
 
 def contac(g, gg, poiss, tang=0, norm=0, force3=0, pen=0.0, fn=0.0, cksi=0.0, ceta=0.0, cphi=0.0, fxrel=0.0, fyrel=0.0,
            fstat=0.3, fkin=0.3, maxgs=999, maxin=20, maxnr=25, maxout=1, eps=1e-5, fullbox=False, nn=0, chi=0.0, dq=1.0,
-           facphi=0.0, gausei=0, omegah=0.9, omegas=0.9):
+           facphi=0.0, gausei=0, omegah=0.9, omegas=0.9, iestim=0, el_in=None, ps_in=None, pv_in=None, hertz=None):
     """One module-3 case (T = 0/1/3) through the oracle's contac/panprc. g: dict mx,my,xl,yl,dx,dy,ibase,prmudf."""
     npot = g["mx"] * g["my"]
     prm = np.ascontiguousarray(g["prmudf"], dtype=np.float64)
@@ -282,12 +285,26 @@ def contac(g, gg, poiss, tang=0, norm=0, force3=0, pen=0.0, fn=0.0, cksi=0.0, ce
     c.maxgs, c.maxin, c.maxnr, c.maxout, c.eps, c.fullbox = maxgs, maxin, maxnr, maxout, eps, int(fullbox)
     c.chi, c.dq, c.facphi, c.gausei = chi, dq, facphi, gausei
     c.omegah, c.omegas = omegah, omegas
+    keep = []
+    if el_in is not None and ps_in is not None:
+        e_ = np.ascontiguousarray(el_in, dtype=np.int32); p_ = np.ascontiguousarray(ps_in, dtype=np.float64)
+        keep += [e_, p_]
+        c.iestim, c.el_in, c.ps_in = iestim, _i(e_), _d(p_)
+    if pv_in is not None:
+        v_ = np.ascontiguousarray(pv_in, dtype=np.float64)
+        keep.append(v_)
+        c.pv_in = _d(v_)
+    if hertz is not None:          # dict(ipotcn, a1, b1, aa, bb, scale): grid and geometry from the Hertz solution
+        c.ipotcn = hertz["ipotcn"]
+        c.hz_a1, c.hz_b1, c.hz_aa, c.hz_bb = hertz.get("a1", 0.0), hertz.get("b1", 0.0), hertz.get("aa", 0.0), hertz.get("bb", 0.0)
+        c.hz_scale = hertz.get("scale", 1.0)
     c.el, c.ps, c.ss = _i(el), _d(ps), _d(ss)
     L = lib()
     L.co_contac.restype = C.c_int
     ierr = L.co_contac(C.byref(c))
     n = c.nr_n
     return dict(ierror=ierr, el=el, ps=ps, ss=ss, pen=c.pen_out, fn=c.fn_out, fx=c.fx_out, fy=c.fy_out, cksi=c.cksi, ceta=c.ceta,
+                grid=dict(mx=c.mx, my=c.my, xl=c.xl, yl=c.yl, dx=c.dx, dy=c.dy), hz=dict(a1=c.hz_a1, b1=c.hz_b1, aa=c.hz_aa, bb=c.hz_bb),
                 itnorm=c.itnorm, ittang=c.ittang, itcg_norm=c.itcg_norm, itgs_tang=c.itgs_tang,
                 nr_itcg=list(c.nr_itcg[:n]), nr_cksi=list(c.nr_cksi[:n]), nr_ceta=list(c.nr_ceta[:n]), nr_fx=list(c.nr_fx[:n]),
                 nr_fy=list(c.nr_fy[:n]), n_prod=c.n_prod)

@@ -43,6 +43,29 @@ def get_times():
     return out
 
 
+def ref_out_stats(path):
+    """Per case of a .ref_out file: the statistics row NPOT NCON NADH NSLIP INORM ITANG and the row
+    FN/G FX/FSTAT/FN FY/FSTAT/FN APPROACH PMAX as printed."""
+    lines = open(os.path.join(REF, path)).read().splitlines()
+    cases = []
+    for i, l in enumerate(lines):
+        m = re.match(r"\s*FN/G\s+(FX/FSTAT/FN|SHIFT X|CREEP X)\s+(FY/FSTAT/FN|SHIFT Y|CREEP Y)\s+APPROACH", l)
+        if m:       # columns 2, 3 are the relative forces (F = 0) or the resulting shifts / creepages (F = 1, 2)
+            cases.append(dict(forces=lines[i + 1].split(), col2=m.group(1), col3=m.group(2)))
+        if re.match(r"\s*NPOT\s+NCON\s+NADH\s+NSLIP\s+INORM\s+ITANG", l):
+            cases[-1]["stats"] = [int(v) for v in lines[i + 1].split()]
+    return cases
+
+
+def inp_cases(path):
+    """The module-3 cases of a reference .inp file as parsed by contact_b200.inp (derived data: lets the GPU box, which
+    has no /root/reference, run the same sequence)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from contact_b200 import inp as INP
+    return INP.parse_inp(open(os.path.join(REF, path)).read())
+
+
 def cattaneo():
     txt = open(os.path.join(REF, "examples/cattaneo.ref_out")).read().splitlines()
     pics = []
@@ -81,7 +104,15 @@ def subsurf():
                 block1=blocks[0]["rows"], block2_every7=keep)
 
 
+def write_sequences():
+    for name in ("spence35", "cattaneo"):
+        json.dump(dict(source="examples/%s.inp, examples/%s.ref_out" % (name, name), cases=inp_cases("examples/%s.inp" % name),
+                       ref_out=ref_out_stats("examples/%s.ref_out" % name)),
+                  open(os.path.join(HERE, "%s_sequence.json" % name), "w"), indent=0)
+
+
 if __name__ == "__main__":
+    write_sequences()
     json.dump(subsurf(), open(os.path.join(HERE, "subsurf_ref_subs.json"), "w"))
     json.dump(mbench_profile(), open(os.path.join(HERE, "mbench_profile.json"), "w"))
     json.dump(get_times(), open(os.path.join(HERE, "get_times.json"), "w"), indent=1)

@@ -643,3 +643,92 @@ def test_large_grid_shift_8s_golden(cb, mbench):
     assert int((el == 2).sum()) == 111191 and 150 <= its["itgs"] <= 260
     pt = np.hypot(px, py)
     assert (pt <= 0.3 * pn * (1 + 1e-9) + 1e-12).all()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the reference's example inputs as case sequences through the .inp reader and the cntc_* interface
+# ------------------------------------------------------------------------------------------------------------
+def _sequence(name):
+    import json, os
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "%s_sequence.json" % name)))
+
+
+def _inp_text_from_cases(name):
+    """The GPU box has no /root/reference: rebuild an equivalent .inp text from the committed parsed cases."""
+    d = _sequence(name)
+    out = []
+    for c in d["cases"]:
+        out.append(" 3 MODULE")
+        out.append(" %d%d%d%d%d%d" % (c["P"], c["B"], c["T"], c["N"], c["F"], c["S"]))
+        out.append(" %d%d%d%d%d%d%d" % (c["V"], c["L"], c["D"], c["C"], c["M"], c["Z"], c["E"]))
+        out.append(" %d%d%d%d%d%d%d%d" % (c["X"], c["H"], c["G"], c["I"], c["A"], c["O"], c["W"], c["R"]))
+        if "solver" in c:
+            s = c["solver"]
+            out.append(" %d %d %d %d %r" % (s["maxgs"], s["maxin"], s["maxnr"], s["maxout"], s["eps"]))
+        out.append(" " + " ".join(repr(v) for v in c["kin"]))
+        if "fric" in c:
+            out.append(" %r %r" % tuple(c["fric"]))
+        if "mater" in c:
+            out.append(" %r %r %r %r" % (c["mater"]["poiss"][0], c["mater"]["poiss"][1], c["mater"]["gg"][0], c["mater"]["gg"][1]))
+        if "potcon" in c:
+            p = c["potcon"]
+            out.append(" %d" % p["ipotcn"])
+            if p["ipotcn"] < 0:
+                out.append(" %d %d %r %r %r" % (p["mx"], p["my"], p["p1"], p["p2"], p["scale"]))
+            else:
+                out.append(" %d %d " % (p["mx"], p["my"]) + " ".join(repr(v) for v in p["prm"]))
+        if "geom" in c:
+            out.append(" %d %d" % (c["geom"]["ibase"], c["geom"]["iplan"]))
+            out.append(" " + " ".join(repr(v) for v in c["geom"]["prm"]))
+        if c["S"] >= 2:
+            out.append(" 0 0")
+        if c["S"] >= 3:
+            for b in c["subs"]:
+                out.append(" %d" % b["isubs"])
+                if b["isubs"] in (2, 6):
+                    out.append(" %d %d %d" % tuple(b["ix"])); out.append(" %d %d %d" % tuple(b["iy"]))
+                if b["isubs"] <= 3:
+                    out.append(" %d %r %r" % tuple(b["zparam"]))
+                else:
+                    out.append(" %d" % len(b["z"])); out.append(" " + " ".join(repr(v) for v in b["z"]))
+            out.append(" 0")
+    out.append(" 0 MODULE")
+    return "\n".join(out) + "\n", d
+
+
+def test_inp_sequence_spence35(cb, O):
+    """examples/spence35.inp (35-stage Spence compression: dissimilar materials, T=1 with zero shift, P=0 / I=1 sequence,
+    MAXOUT=10) through the .inp reader and cntc_calculate: every stage against the printed rows of
+    examples/spence35.ref_out and the element division / tractions of the oracle."""
+    from contact_b200 import inp as INP
+    from tests import inp_oracle
+    from tests.test_inp_sequences import check_against_ref_out
+    text, d = _inp_text_from_cases("spence35")
+    res = INP.run_inp(text, ire=81)
+    ref = inp_oracle.run_cases(d["cases"])
+    assert len(res) == 35 and all(r["ierror"] == 0 for r in res), [(r["case"], r["ierror"], r.get("message")) for r in res if r["ierror"] != 0]
+    mine = [dict(pen=r["pen"], pmax=r["pmax"], fx=r["fx"] / (0.2986 * r["fn"]), fy=r["fy"] / (0.2986 * r["fn"]), ncon=r["ncon"],
+                 nadh=r["nadh"], nslip=r["nslip"], itnorm=r["its"]["itnorm"], ittang=r["its"]["ittang"]) for r in res]
+    check_against_ref_out(mine, d["ref_out"])
+    for k, (r, o) in enumerate(zip(res, ref), 1):
+        assert np.array_equal(r["el"].ravel(), o["el"]), k
+        assert _rel(r["pn"].ravel(), o["ps"][2]) < 1e-6, k
+        s = max(np.abs(o["ps"][:2]).max(), 1e-30)
+        assert np.abs(r["px"].ravel() - o["ps"][0]).max() < 1e-5 * s + 1e-12 * np.abs(o["ps"][2]).max(), k
+    # the subsurface block of the input (ISUBS=2: the centre row, just below the surface) was evaluated in every stage
+    assert all(r.get("subs_ierror", 0) == 0 for r in res) and res[-1]["subs"][0].shape == (45, 21)
+
+
+def test_inp_sequence_cattaneo(cb, O):
+    """examples/cattaneo.inp: Hertzian input (IPOTCN=-3) and the Cattaneo shift with prescribed forces, against
+    examples/cattaneo.ref_out."""
+    from contact_b200 import inp as INP
+    from tests.test_inp_sequences import check_against_ref_out
+    text, d = _inp_text_from_cases("cattaneo")
+    res = INP.run_inp(text, ire=82)
+    assert [r["ierror"] for r in res] == [0, 0], [r.get("message") for r in res]
+    mine = [dict(pen=r["pen"], pmax=r["pmax"], fx=r["fx"] / (0.4 * r["fn"]), fy=r["fy"] / (0.4 * r["fn"]), cksi=r["creep"][0],
+                 ceta=r["creep"][1], ncon=r["ncon"], nadh=r["nadh"], nslip=r["nslip"], itnorm=r["its"]["itnorm"],
+                 ittang=r["its"]["ittang"]) for r in res]
+    check_against_ref_out(mine, d["ref_out"])
+    assert res[0]["its"]["itcg"] == 4 and res[1]["its"]["itgs"] == 59          # cattaneo.ref_out:10, :84-100
