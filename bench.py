@@ -133,6 +133,23 @@ def rolling_sweep_leg(cb, n, rank_offset):
             "note": "mbench 71x81, T=3 SteadyGS, eps 1e-5, host buffers through cntc_calculate_batch (one launch)"}
 
 
+def spence71_leg(cb):
+    """perfc_test/spence71_8281pt.inp itself (BASELINE config: 69 cases in sequence on the 91x91 grid, dissimilar
+    materials, Panagiotopoulos process, 11-depth subsurface block per case) through the .inp reader and cntc_calculate /
+    subs_calculate.  A sequence runs one case at a time (one CTA), so this is a latency figure, not a throughput one."""
+    from contact_b200 import inp as INP
+    from tests.test_gpu_parity import _inp_text_from_cases
+    text, d = _inp_text_from_cases("spence71")
+    t0 = time.perf_counter()
+    res = INP.run_inp(text, ire=950, with_fields=False)
+    dt = time.perf_counter() - t0
+    return {"cases": len(res), "errors": sum(1 for r in res if r["ierror"] != 0), "wall_s": dt,
+            "contact_s": float(sum(r["wall_s"] for r in res)), "subsurf_s": float(sum(r.get("subs_wall_s", 0.0) for r in res)),
+            "first12_contact_s": float(sum(r["wall_s"] for r in res[:12])),
+            "ncon_final": res[-1].get("ncon"), "nout": int(sum(r["its"]["itout"] for r in res if "its" in r)),
+            "golden": "perfc_test/get_times.ref_out:76-79: ncon 3657, nout 511, 30.7 s + 22.0 s subsurface (2016 host)"}
+
+
 def large_grid_leg(cb, torch):
     """575x647 grid of perfc_test/norm_problm_8p.inp / tang_problm_8c.inp: stand-alone 1x1 products (three grid-wide
     phases over the L2-resident spectrum) and the whole NORM solve in one cooperative launch."""
@@ -301,6 +318,7 @@ def run_gpu(args):
     nroll = nsm if args.cases <= 0 else min(args.cases, nsm)
     roll = rolling_sweep_leg(cb, nroll, (rank * nroll) % (4096 - nroll)) if not args.skip_extra else None
     large = large_grid_leg(cb, torch) if (rank == 0 and not args.skip_extra) else None
+    sp71 = spence71_leg(cb) if (rank == 0 and not args.skip_extra) else None
 
     # ---- end-to-end leg (host buffers through the C-ABI) ----
     for _ in range(max(1, min(args.warmup, 2))):
@@ -381,6 +399,8 @@ def run_gpu(args):
             large["frac_hbm"] = large["alg_GBps"] / hbm_peak
             large["frac_fp64"] = large["nominal_TFLOPs"] / fp64_peak if fp64_peak > 0 else None
             out["large_grid"] = large
+        if sp71:
+            out["spence71_inp"] = sp71
         if args.cpu_seconds > 0:
             out["cpu_baseline"] = cpu_baseline(args.cpu_seconds, threads=1)
         print(json.dumps(out))
@@ -413,7 +433,13 @@ def cpu_baseline(budget_s, threads):
                   cphi=0.0003, fstat=0.3, fkin=0.3, maxgs=999, maxin=100, maxnr=30, maxout=1, eps=1e-5, nn=gm["nn"], chi=0.0,
                   dq=0.1, gausei=0)
     dtr = time.perf_counter() - t2
+    from tests import inp_oracle
+    from tests.test_gpu_parity import _sequence
+    t3 = time.perf_counter()
+    inp_oracle.run_cases(_sequence("spence71")["cases"][:12])
+    dt71 = time.perf_counter() - t3
     return {"value": ns / dt, "unit": UNIT, "cores": threads, "kind": "port", "subsurf_cases_per_s": 1.0 / dts,
+            "spence71_first12_contact_s": dt71,
             "rolling_cases_per_s": 1.0 / dtr, "rolling_sample": "tang_problm_1c creepages on mbench 71x81, T=3 SteadyGS, eps 1e-5, "
                                                               "%d sweeps, %.2f s" % (rr["itgs_tang"], dtr),
             "sample": "%d hertz-91 cases (first of the seeded sweep), %.1f s wall; CPU restatement of the reference "

@@ -56,7 +56,7 @@ struct Problem {
     int maxgs = 999, maxin = 20, maxnr = 25, maxout = 1;
     double eps = 1e-5, omegah = 0.9, omegas = 1.0, dq_eff = 1.0;
     // results
-    int ncase = 0, itnorm = 0, ittang = 0, itcg = 0, ncon = 0, nadh = 0, nslip = 0, status = 0;
+    int ncase = 0, itnorm = 0, ittang = 0, itcg = 0, ncon = 0, nadh = 0, nslip = 0, status = 0, itout = 0;
     std::vector<int> el;
     std::vector<double> ps, us, hs, ss;  // [3][npot]
     std::vector<double> pv;              // [3][npot] tractions of the previous time instance (set_prev_data)
@@ -504,7 +504,7 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
                 p.hs.assign(3 * (size_t) npot, 0.0);
                 std::copy(hs[ks[i]].begin(), hs[ks[i]].end(), p.hs.begin() + 2 * (size_t) npot);
                 p.pen = c.nrm.pen; p.fntrue = c.nrm.fntrue; p.itcg = c.nrm.itcg; p.itnorm = c.nrm.itnorm; p.ncon = c.nrm.ncon;
-                p.status = c.nrm.status; p.ittang = c.ittang; p.itgs = c.itgs; p.nadh = c.nadh; p.nslip = c.nslip;
+                p.status = c.nrm.status; p.ittang = c.ittang; p.itgs = c.itgs; p.itout = c.itout; p.nadh = c.nadh; p.nslip = c.nslip;
                 p.nr_itcg.assign(c.nr_itcg, c.nr_itcg + std::min(c.nr_n, (int) CB_MAXNR_LOG));
                 const double muscal = p.fstat;
                 double sx = 0, sy = 0, mz = 0;
@@ -770,13 +770,13 @@ int cb200_eldiv0(int mx, int my, double dx, double dy, double gg1, double gg2, d
     return 0;
 }
 
-// iteration counters of the last case: out[0..5] = itnorm, itcg (NormCG), ittang, itgs (tangential solver iterations),
-// ncon, number of tangential solver calls nr_n; nr_itcg[0..nr_n) = iterations per solver call (at most lenarr)
+// iteration counters of the last case: out[0..6] = itnorm, itcg (NormCG), ittang, itgs (tangential solver iterations),
+// ncon, number of tangential solver calls nr_n, outer iterations; nr_itcg[0..nr_n) = iterations per solver call (at most lenarr)
 int cb200_get_iterations(int ire, int icp, int *out, int lenarr, int *nr_itcg)
 {
     int e; Problem *p = activate(ire, icp, &e);
     if (!p) return e;
-    out[0] = p->itnorm; out[1] = p->itcg; out[2] = p->ittang; out[3] = p->itgs; out[4] = p->ncon; out[5] = (int) p->nr_itcg.size();
+    out[0] = p->itnorm; out[1] = p->itcg; out[2] = p->ittang; out[3] = p->itgs; out[4] = p->ncon; out[5] = (int) p->nr_itcg.size(); out[6] = p->itout;
     for (int i = 0; i < lenarr && i < (int) p->nr_itcg.size(); i++) nr_itcg[i] = p->nr_itcg[i];
     return 0;
 }

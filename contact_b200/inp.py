@@ -8,6 +8,7 @@ based, '%' starts a comment, Fortran 'd' exponents are accepted.  Inputs outside
 laws L > 1, materials M > 0, planforms, temperature ...) raise NotImplementedError instead of being guessed.
 """
 import re
+import time
 
 import numpy as np
 
@@ -264,8 +265,9 @@ def run_inp(text, ire=1, icp=1, api=None, with_fields=True):
         else:
             cb.cntc_setcreepages(ire, icp, 0.0, 0.0, k[3])
             cb.cntc_settangentialforces(ire, icp, k[1], k[2])
+        t0 = time.perf_counter()
         ierr = cb.cntc_calculate(ire, icp)
-        res = dict(case=n, ierror=ierr)
+        res = dict(case=n, ierror=ierr, wall_s=time.perf_counter() - t0)
         if ierr >= 0:
             its = cb.lowlevel.get_iterations(ire, icp)
             el = cb.cntc_getelementdivision(ire, icp)
@@ -287,7 +289,9 @@ def run_inp(text, ire=1, icp=1, api=None, with_fields=True):
                         cb.subs_addblock(ire, icp, ib, b["isubs"], b["ixs"], b["iys"], z)
                     else:
                         cb.subs_addblock(ire, icp, ib, b["isubs"], [], [], z)
+                t0 = time.perf_counter()
                 res["subs_ierror"] = cb.subs_calculate(ire, icp)
+                res["subs_wall_s"] = time.perf_counter() - t0
                 if with_fields and res["subs_ierror"] == 0:
                     res["subs"] = [cb.subs_getresults(ire, icp, ib, list(range(1, 22))) for ib in range(1, len(c["subs"]) + 1)]
         else:

@@ -151,9 +151,9 @@ def subsurf_points(mx, my, xc1, yc1, dx, dy, gg, poiss, ps, xyz):
 
 
 def get_iterations(ire, icp=1):
-    out = (C.c_int * 6)(); log = (C.c_int * 64)()
+    out = (C.c_int * 8)(); log = (C.c_int * 64)()
     _check(load_library().cb200_get_iterations(ire, icp, out, 64, log))
-    return dict(itnorm=out[0], itcg=out[1], ittang=out[2], itgs=out[3], ncon=out[4], nr_itcg=list(log[:out[5]]))
+    return dict(itnorm=out[0], itcg=out[1], ittang=out[2], itgs=out[3], ncon=out[4], nr_itcg=list(log[:out[5]]), itout=out[6])
 
 
 def snorm_kernel_ms():

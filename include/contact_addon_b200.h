@@ -118,8 +118,9 @@ void cntc_finalizelast(void);
  * ierror[k] receives what cntc_calculate(ire[k], icp) would have returned. */
 void cntc_calculate_batch(int *nre, int *ire, int *icp, int *ierror);
 
-/* iteration counters of the last case of (ire, icp): out[0..5] = itnorm, ItCG of NormCG, ittang, iterations of the
- * tangential solver, ncon, number of tangential solver calls; nr_itcg = iterations per call (Newton-Raphson log) */
+/* iteration counters of the last case of (ire, icp): out[0..6] = itnorm, ItCG of NormCG, ittang, iterations of the
+ * tangential solver, ncon, number of tangential solver calls, outer (Panagiotopoulos) iterations; nr_itcg = iterations
+ * per solver call (Newton-Raphson log) */
 int cb200_get_iterations(int ire, int icp, int *out, int lenarr, int *nr_itcg);
 
 /* last error message of the calling thread (NUL-terminated, owned by the library) */

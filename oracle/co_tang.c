@@ -498,6 +498,7 @@ int co_contac(co_case *c)
     for (int i = 0; i < npot; i++) sy = sy + ps[npot + i];
     c->fx_out = (c->force3 == 0) ? dxdy * sx / (fntrue * muscal + CO_TINY) : c->fxrel;
     c->fy_out = (c->force3 <= 1) ? dxdy * sy / (fntrue * muscal + CO_TINY) : c->fyrel;
+    c->itout = itout;
     c->pen_out = pen; c->fn_out = fntrue; c->itnorm = itnorm; c->ittang = ittang; c->itcg_norm = itcg_norm; c->itgs_tang = itgs;
     memcpy(c->el, igs.el, sizeof(int) * npot);
     memcpy(c->ps, ps, sizeof(double) * 3 * npot);

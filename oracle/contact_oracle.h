@@ -185,6 +185,7 @@ typedef struct {
     const double *pv_in;                /* [3][npot] tractions of the previous time instance (P = 0/1), NULL = zero */
     int    ipotcn;                      /* -1 / -3: 3D Hertzian geometry (curvatures / semi-axes given); else grid as given */
     double hz_a1, hz_b1, hz_aa, hz_bb, hz_scale;
+    int    itout;                       /* out: outer (Panagiotopoulos) iterations */
 } co_case;
 void   co_ellip_kebd(double mc, double *K, double *E, double *B, double *D);
 void   co_hertz3d(double e_star, int ipotcn, double *a1, double *b1, double *aa, double *bb, int ic_norm, double *pen,

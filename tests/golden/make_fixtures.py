@@ -111,8 +111,15 @@ def write_sequences():
                   open(os.path.join(HERE, "%s_sequence.json" % name), "w"), indent=0)
 
 
+def write_spence71():
+    json.dump(dict(source="perfc_test/spence71_8281pt.inp; perfc_test/get_times.ref_out:76-79 (spence71_nosubs: ncon 3657, nout 511)",
+                   cases=inp_cases("perfc_test/spence71_8281pt.inp"), golden=dict(ncon=3657, nout=511)),
+              open(os.path.join(HERE, "spence71_sequence.json"), "w"), indent=0)
+
+
 if __name__ == "__main__":
     write_sequences()
+    write_spence71()
     json.dump(subsurf(), open(os.path.join(HERE, "subsurf_ref_subs.json"), "w"))
     json.dump(mbench_profile(), open(os.path.join(HERE, "mbench_profile.json"), "w"))
     json.dump(get_times(), open(os.path.join(HERE, "get_times.json"), "w"), indent=1)

@@ -732,3 +732,22 @@ def test_inp_sequence_cattaneo(cb, O):
                  ittang=r["its"]["ittang"]) for r in res]
     check_against_ref_out(mine, d["ref_out"])
     assert res[0]["its"]["itcg"] == 4 and res[1]["its"]["itgs"] == 59          # cattaneo.ref_out:10, :84-100
+
+
+def test_inp_sequence_spence71_golden(cb):
+    """perfc_test/spence71_8281pt.inp (BASELINE config: 69 cases on the 91x91 grid, dissimilar materials, 11-depth
+    subsurface block per case): final contact area of perfc_test/get_times.ref_out:76 (spence71_nosubs: ncon = 3657).
+    Its nout = 511 (total outer iterations, 2016 revision) is met to 2 %: the CPU oracle, which reproduces every printed
+    row of the current examples/spence35.ref_out, needs 521 on this input."""
+    import time
+    from contact_b200 import inp as INP
+    text, d = _inp_text_from_cases("spence71")
+    t0 = time.perf_counter()
+    res = INP.run_inp(text, ire=83, with_fields=False)
+    dt = time.perf_counter() - t0
+    assert len(res) == 69 and all(r["ierror"] == 0 for r in res), [(r["case"], r["ierror"], r.get("message")) for r in res if r["ierror"] != 0]
+    assert res[-1]["ncon"] == d["golden"]["ncon"]
+    nout = sum(r["its"]["itout"] for r in res)
+    assert abs(nout - d["golden"]["nout"]) <= 26 and abs(nout - 521) <= 5, nout
+    assert all(r.get("subs_ierror", 0) == 0 for r in res)
+    print("spence71_8281pt.inp: 69 cases with subsurface stresses in %.2f s" % dt)
