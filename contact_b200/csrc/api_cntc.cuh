@@ -466,6 +466,9 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
         cudaMemset(d_buf + 6 * (size_t) npot, 0, 0);
         cudaMemcpy(d_cases, hc.data(), sizeof(ContactCase) * n, cudaMemcpyHostToDevice);
         cudaMemset(d_next, 0, sizeof(int));
+        NormBatch &NB = norm_batch();                               // events around the solver kernel(s): cb200_snorm_kernel_ms
+        if (!NB.ev0) { cudaEventCreate(&NB.ev0); cudaEventCreate(&NB.ev1); }
+        cudaEventRecord(NB.ev0, 0);
         if (cs.hp.fits) {
             k_contac_batch<<<launch_blocks(n), CB_THREADS, P.smem_bytes>>>(P, d_cases, n, d_next);
             engine().launches++;
@@ -479,6 +482,7 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
                 engine().launches++;
             }
         }
+        cudaEventRecord(NB.ev1, 0);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { last_error() = std::string("k_contac_batch: ") + cudaGetErrorString(e); fail(CNTC_err_other); }
         else {

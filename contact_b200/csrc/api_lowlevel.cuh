@@ -192,11 +192,8 @@ inline int snorm_batch_dev(CoefSet &cs, int ncase, int ic_norm, int maxgs, int m
     if ((rc = build_chat(cs, SET_CS, 3, 3, st))) return rc;
     if ((rc = build_chat(cs, SET_MS, 3, 3, st))) return rc;
     NormBatch &B = norm_batch();
-    if (!B.d_next) {
-        CB_CUDA(cudaMalloc(&B.d_next, sizeof(int)));
-        CB_CUDA(cudaEventCreate(&B.ev0));
-        CB_CUDA(cudaEventCreate(&B.ev1));
-    }
+    if (!B.d_next) CB_CUDA(cudaMalloc(&B.d_next, sizeof(int)));
+    if (!B.ev0) { CB_CUDA(cudaEventCreate(&B.ev0)); CB_CUDA(cudaEventCreate(&B.ev1)); }
     static long cap_bytes = 0;
     const long need = (long) ncase * 9 * P.npot * sizeof(double);
     if (ncase > B.cap || need > cap_bytes) {
@@ -399,7 +396,8 @@ int cb200_snorm_batch(int handle, int ncase, int ic_norm, int maxgs, int maxin, 
     return 0;
 }
 
-// device time of the most recent solver kernel (k_snorm_batch) alone, ms; synchronises on its end event
+// device time of the most recent solver kernel(s) alone (k_snorm_batch, k_contac_batch, k_lg_*), ms; synchronises on
+// the end event
 double cb200_snorm_kernel_ms(void)
 {
     NormBatch &B = norm_batch();
