@@ -398,6 +398,7 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
         }
         if (!rc && cs.key.is_roll)                                  // ConvexGS in steady rolling works with csv = cs - cv
             for (int ik = 1; ik <= 2 && !rc; ik++) for (int jk = 1; jk <= 2 && !rc; jk++) rc = build_chat(cs, SET_CSV, ik, jk, 0);
+        if (!rc) rc = build_levels(cs, 0, any_tang);            // after the full-size transforms and preconditioners exist
         if (rc) { fail(rc); continue; }
         // device buffers: per case hs_n(1) hst(2) ps(3) ss(2) work(9) twork(24) pv(3) = 44 n doubles, el n ints
         const size_t per = (size_t) 44 * npot;
@@ -429,6 +430,7 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
             nc.cf33 = cs.d_cf[SET_CS] + 8 * nblk; nc.cmx = cs.mx; nc.cmy = cs.my; nc.ga_inv = cs.ga_inv;
             nc.ic_norm = p.norm; nc.maxgs = p.maxgs; nc.maxin = p.maxin; nc.eps = p.eps; nc.dxdy = p.dx * p.dy;
             nc.pen = pen0[ks[i]]; nc.fntrue = p.fntrue;
+            nc.lev = cs.d_lev; nc.nlx = cs.nlx; nc.nly = cs.nly;
             c.tang = p.tang; c.force3 = p.force3; c.maxnr = p.maxnr; c.maxout = p.maxout;
             c.cksi = p.cksi; c.ceta = p.ceta; c.fxrel = p.fxrel; c.fyrel = p.fyrel; c.fstat = p.fstat;
             if (!p.solved || p.iestim == 0 || p.iestim == 2) { if (p.force3 >= 1) c.cksi = 1e-6; if (p.force3 == 2) c.ceta = 0.0; }   // m_sdis.f90:760-762

@@ -52,7 +52,7 @@ inline int conv_large_launch(CoefSet &cs, const double *d_p, const cd *chat, dou
     Engine &E = engine();
     const LargePlan &L = cs.lp;
     RowSrc src;
-    src.base = d_p; src.kind = 0; src.mx = L.P.mx; src.my = L.P.my; src.cmx = 0; src.cmy = 0; src.Fx = L.P.Fx; src.Fy = L.P.Fy; src.row0 = 0;
+    src.base = d_p; src.kind = 0; src.mx = L.P.mx; src.my = L.P.my; src.cmx = 0; src.cmy = 0; src.Fx = L.P.Fx; src.Fy = L.P.Fy; src.row0 = 0; src.stride = 0;
     if (!cs.ev_l0) { CB_CUDA(cudaEventCreate(&cs.ev_l0)); CB_CUDA(cudaEventCreate(&cs.ev_l1)); }
     CB_CUDA(cudaEventRecord(cs.ev_l0, st));
     k_lg_rows_fwd<<<L.ntr, CB_THREADS, L.smem_bytes, st>>>(L, src, L.P.my, L.RB, cs.d_T, L.ldT);
@@ -191,6 +191,7 @@ inline int snorm_batch_dev(CoefSet &cs, int ncase, int ic_norm, int maxgs, int m
     if ((rc = build_prec(cs, st))) return rc;
     if ((rc = build_chat(cs, SET_CS, 3, 3, st))) return rc;
     if ((rc = build_chat(cs, SET_MS, 3, 3, st))) return rc;
+    if ((rc = build_levels(cs, st))) return rc;
     NormBatch &B = norm_batch();
     if (!B.d_next) CB_CUDA(cudaMalloc(&B.d_next, sizeof(int)));
     if (!B.ev0) { CB_CUDA(cudaEventCreate(&B.ev0)); CB_CUDA(cudaEventCreate(&B.ev1)); }
@@ -213,6 +214,7 @@ inline int snorm_batch_dev(CoefSet &cs, int ncase, int ic_norm, int maxgs, int m
     proto.ga_inv = cs.ga_inv;
     proto.ic_norm = ic_norm; proto.maxgs = maxgs; proto.maxin = maxin; proto.eps = eps;
     proto.dxdy = cs.key.dx * cs.key.dy;
+    proto.lev = cs.d_lev; proto.nlx = cs.nlx; proto.nly = cs.nly;
     if (!cs.hp.fits) return snorm_large_dev(cs, ncase, proto, d_hs, d_el, d_pn, d_un, d_scal, st);
     k_norm_pack<<<grid1d(ncase, 128), 128, 0, st>>>(B.d_cases, ncase, P.npot, d_hs, d_el, d_pn, d_un, d_scal, B.d_work, proto);
     CB_CUDA(cudaMemsetAsync(B.d_next, 0, sizeof(int), st));

@@ -43,28 +43,46 @@ __device__ unsigned long long g_conv_prof[4];
 #define CB_PHASE(call) do { call; __syncthreads(); } while (0)
 #include "conv_sequence.inc"
 
-// u (masked) = conv(p) with transformed coefficients chat.  All threads of the CTA must call.
-__device__ __noinline__ void conv_dev(const ConvPlan &P, const Smem &sm, const double *p, const cd *chat,
-                                         double *u, const int *el, int mask_mode, int add)
+// The same product restricted to the box (x0, y0, bw x bh) of a grid with row stride `stride`, with the plan P of a
+// (smaller) transform size Fx >= bw, Fy >= bh and ITS transformed coefficients: what the reference does for AllInt
+// products (bounding box of the contact area, m_aijpj.f90:774-793).  p must vanish outside the box; u is written inside
+// the box only.  The plan's tables are (re)loaded into shared memory first -- plans of different sizes share the buffer.
+__device__ __noinline__ void conv_box_dev(const ConvPlan &P, const Smem &sm, const double *p, const cd *chat, double *u,
+                                          const int *el, int mask_mode, int add, int x0, int y0, int bw, int bh, int stride)
 {
     const int tid = threadIdx.x, nthr = blockDim.x;
     const long long t_in = (tid == 0 && blockIdx.x == 0) ? clock64() : 0;
-    // re-derive the pointers from the shared-window address: the compiler then proves the state space and emits
-    // LDS/STS (the generic pointers in Smem travel through a non-inlined call and would become generic LD/ST)
     typedef MemBuf<cd> CB_BUF;
     const CB_BUF BUF = { reinterpret_cast<cd *>(__cvta_shared_to_generic(sm.a0)) };
     const uint32_t oS = P.off_S / 16, oW = P.off_W / 16;
+    {
+        cd *tx = reinterpret_cast<cd *>(__cvta_shared_to_generic(sm.a0 + P.off_twx));
+        cd *ty = reinterpret_cast<cd *>(__cvta_shared_to_generic(sm.a0 + P.off_twy));
+        unsigned short *px = reinterpret_cast<unsigned short *>(__cvta_shared_to_generic(sm.a0 + P.off_posx));
+        for (int k = tid; k < 2 * P.Fx; k += nthr) tx[k] = P.twx[k];
+        for (int k = tid; k < 2 * P.Fy; k += nthr) ty[k] = P.twy[k];
+        for (int k = tid; k < P.Lx; k += nthr) px[k] = P.posx[k];
+        __syncthreads();
+    }
     const MemBuf<const cd> twx = { reinterpret_cast<const cd *>(__cvta_shared_to_generic(sm.a0 + P.off_twx)) };
     const MemBuf<const cd> twy = { reinterpret_cast<const cd *>(__cvta_shared_to_generic(sm.a0 + P.off_twy)) };
     const MemBuf<const unsigned short> posx = { reinterpret_cast<const unsigned short *>(__cvta_shared_to_generic(sm.a0 + P.off_posx)) };
     const int SY = P.SY;
     RowSrc src;
-    src.base = p; src.kind = 0; src.mx = P.mx; src.my = P.my; src.cmx = 0; src.cmy = 0; src.Fx = P.Fx; src.Fy = P.Fy; src.row0 = 0;
-    CB_CONV_FORWARD_ROWS(P.my, src);
-    CB_CONV_COLUMNS_PRODUCT(P.my, chat);
-    CB_CONV_INVERSE_ROWS(P.my);
-    CB_PHASE(row_store(P, BUF, oS, SY, u, el, mask_mode, add, tid, nthr));
+    src.base = p + (size_t) y0 * stride + x0; src.kind = 0; src.mx = bw; src.my = bh; src.cmx = 0; src.cmy = 0; src.Fx = P.Fx; src.Fy = P.Fy;
+    src.row0 = 0; src.stride = stride;
+    CB_CONV_FORWARD_ROWS(bh, src);
+    CB_CONV_COLUMNS_PRODUCT2(bh, bh, chat);
+    CB_CONV_INVERSE_ROWS(bh);
+    CB_PHASE(row_store_box(P, BUF, oS, SY, u, el, mask_mode, add, x0, y0, bw, bh, stride, tid, nthr));
     if (tid == 0 && blockIdx.x == 0) { g_conv_prof[0] += 1; g_conv_prof[1] += (unsigned long long) (clock64() - t_in); }
+}
+
+// u (masked) = conv(p) with transformed coefficients chat on the full grid of plan P.  All threads of the CTA must call.
+__device__ __forceinline__ void conv_dev(const ConvPlan &P, const Smem &sm, const double *p, const cd *chat,
+                                         double *u, const int *el, int mask_mode, int add)
+{
+    conv_box_dev(P, sm, p, chat, u, el, mask_mode, add, 0, 0, P.mx, P.my, P.mx);
 }
 
 // ---- deterministic block reductions (fixed shuffle tree; result broadcast to all threads) ----

@@ -73,6 +73,11 @@ struct CoefSet {
     cd *d_T = nullptr;
     double *d_gpart = nullptr;
     cudaEvent_t ev_l0 = nullptr, ev_l1 = nullptr;   // bracket the three phase kernels of the last stand-alone product
+    // ladder of smaller transform sizes for products on the bounding box of the contact area (single-CTA path)
+    std::vector<HostPlan> lev_hp;
+    ConvLevel *d_lev = nullptr;
+    int nlx = 0, nly = 0;
+    bool lev_tang = false;
 };
 
 struct Engine {
@@ -149,7 +154,7 @@ inline int build_chat_large(CoefSet &cs, int set, int ik, int jk, cudaStream_t s
     RowSrc src;
     src.base = cs.d_cf[set] + (size_t) ((jk - 1) * 3 + (ik - 1)) * 4 * cs.mx * cs.my;
     src.kind = 1; src.mx = std::min(P.Fx, P.mx); src.my = std::min(P.Fy, P.my); src.cmx = cs.mx; src.cmy = cs.my;
-    src.Fx = P.Fx; src.Fy = P.Fy; src.row0 = 0;
+    src.Fx = P.Fx; src.Fy = P.Fy; src.row0 = 0; src.stride = 0;
     const double scale = cs.ga_inv / (4.0 * P.Fx * P.Fy);
     const int nrows = 2 * P.Fy, ntask = (nrows + L.RB - 1) / L.RB;
     k_lg_rows_fwd<<<std::min(ntask, 4 * E.num_sms), CB_THREADS, L.smem_bytes, st>>>(L, src, nrows, L.RB, T2, nrows);
@@ -183,6 +188,95 @@ inline int build_chat(CoefSet &cs, int set, int ik, int jk, cudaStream_t st)
     CB_CUDA(cudaFree(SWg));
     cs.d_chat[set][ik - 1][jk - 1] = chat;
     cs.n_chat_built++;
+    return 0;
+}
+
+// ---- ladder of transform sizes for the contact-box products (m_aijpj.f90:774-793): sizes ~ 1, .8, .64, .5, .4, .3 of
+//      the grid in each direction, every combination with its own plan, tables and transformed cs(3,3), ms(3,3) ----
+inline int build_levels(CoefSet &cs, cudaStream_t st, bool tang = false)
+{
+    Engine &E = engine();
+    if (!cs.hp.fits) return 0;
+    if (cs.d_lev && (!tang || cs.lev_tang)) return 0;
+    // blocks wanted per level: normal problem cs(3,3), ms(3,3); tangential problem also cs(1:2,1:2), ms(1,1), ms(2,2) and,
+    // with normal-tangential coupling, cs(1:2,3)
+    struct Want { int set, ik, jk; };
+    std::vector<Want> want = { { 0, 3, 3 }, { 1, 3, 3 } };
+    if (tang) {
+        for (int ik = 1; ik <= 2; ik++) for (int jk = 1; jk <= 2; jk++) want.push_back({ 0, ik, jk });
+        want.push_back({ 1, 1, 1 }); want.push_back({ 1, 2, 2 });
+        if (cs.nt_cpl) { want.push_back({ 0, 1, 3 }); want.push_back({ 0, 2, 3 }); }
+    }
+    if (cs.d_lev) {                                            // second call: add the tangential blocks
+        std::vector<ConvLevel> h((size_t) cs.nlx * cs.nly);
+        CB_CUDA(cudaMemcpy(h.data(), cs.d_lev, sizeof(ConvLevel) * h.size(), cudaMemcpyDeviceToHost));
+        for (size_t l = 1; l < h.size(); l++)
+            for (const Want &w : want) {
+                if (h[l].chat[w.set][w.ik - 1][w.jk - 1]) continue;
+                const ConvPlan &P = h[l].P;
+                cd *chat = nullptr, *SWg = nullptr;
+                CB_CUDA(cudaMalloc(&chat, sizeof(cd) * (size_t) P.chat_len));
+                CB_CUDA(cudaMalloc(&SWg, sizeof(cd) * ((size_t) (P.Lx + 1) * 2 * P.Fy + (size_t) P.Ly * P.C)));
+                const double *blk = cs.d_cf[w.set ? SET_MS : SET_CS] + (size_t) ((w.jk - 1) * 3 + (w.ik - 1)) * 4 * cs.mx * cs.my;
+                k_build_chat<<<1, CB_THREADS, 64, st>>>(P, blk, cs.mx, cs.my, cs.ga_inv / (4.0 * P.Fx * P.Fy), SWg, chat);
+                E.launches++;
+                CB_CUDA(cudaGetLastError());
+                CB_CUDA(cudaStreamSynchronize(st));
+                CB_CUDA(cudaFree(SWg));
+                h[l].chat[w.set][w.ik - 1][w.jk - 1] = chat;
+            }
+        for (const Want &w : want) h[0].chat[w.set][w.ik - 1][w.jk - 1] = cs.d_chat[w.set ? SET_MS : SET_CS][w.ik - 1][w.jk - 1];
+        CB_CUDA(cudaMemcpy(cs.d_lev, h.data(), sizeof(ConvLevel) * h.size(), cudaMemcpyHostToDevice));
+        cs.lev_tang = true;
+        return 0;
+    }
+    auto ladder = [](int n) {
+        std::vector<int> v(1, n);
+        for (double r : { 0.8, 0.64, 0.5, 0.4, 0.3 }) {
+            const int f = opt_fft_size(std::max(4, (int) ceil(n * r)));
+            if (f < v.back() && f >= 4) v.push_back(f);
+        }
+        return v;
+    };
+    const std::vector<int> fx = ladder(cs.mx), fy = ladder(cs.my);
+    cs.nlx = (int) fx.size(); cs.nly = (int) fy.size();
+    if (cs.nlx * cs.nly <= 1) return 0;
+    cs.lev_hp.resize((size_t) cs.nlx * cs.nly);
+    std::vector<ConvLevel> h((size_t) cs.nlx * cs.nly);
+    const double scale = cs.ga_inv;
+    for (int ly = 0; ly < cs.nly; ly++)
+        for (int lx = 0; lx < cs.nlx; lx++) {
+            HostPlan &hp = cs.lev_hp[(size_t) ly * cs.nlx + lx];
+            ConvLevel &L = h[(size_t) ly * cs.nlx + lx];
+            memset(&L, 0, sizeof(L));
+            if (lx == 0 && ly == 0) { L.P = cs.hp.p; L.chat[0][2][2] = cs.d_chat[SET_CS][2][2]; L.chat[1][2][2] = cs.d_chat[SET_MS][2][2]; continue; }
+            if (!make_plan(fx[lx], fy[ly], hp) || !hp.fits) { last_error() = "internal: level plan does not fit"; return -99; }
+            ConvPlan &P = hp.p;
+            cd *twx, *twy; unsigned short *posx;
+            CB_CUDA(cudaMalloc(&twx, sizeof(cd) * hp.twx.size()));
+            CB_CUDA(cudaMalloc(&twy, sizeof(cd) * hp.twy.size()));
+            CB_CUDA(cudaMalloc(&posx, sizeof(unsigned short) * hp.posx.size()));
+            CB_CUDA(cudaMemcpyAsync(twx, hp.twx.data(), sizeof(cd) * hp.twx.size(), cudaMemcpyHostToDevice, st));
+            CB_CUDA(cudaMemcpyAsync(twy, hp.twy.data(), sizeof(cd) * hp.twy.size(), cudaMemcpyHostToDevice, st));
+            CB_CUDA(cudaMemcpyAsync(posx, hp.posx.data(), sizeof(unsigned short) * hp.posx.size(), cudaMemcpyHostToDevice, st));
+            P.twx = twx; P.twy = twy; P.posx = posx;
+            L.P = P;
+            for (int which = 0; which < 2; which++) {
+                cd *chat = nullptr, *SWg = nullptr;
+                CB_CUDA(cudaMalloc(&chat, sizeof(cd) * (size_t) P.chat_len));
+                CB_CUDA(cudaMalloc(&SWg, sizeof(cd) * ((size_t) (P.Lx + 1) * 2 * P.Fy + (size_t) P.Ly * P.C)));
+                const double *blk = cs.d_cf[which ? SET_MS : SET_CS] + (size_t) 8 * 4 * cs.mx * cs.my;
+                k_build_chat<<<1, CB_THREADS, 64, st>>>(P, blk, cs.mx, cs.my, scale / (4.0 * P.Fx * P.Fy), SWg, chat);
+                E.launches++;
+                CB_CUDA(cudaGetLastError());
+                CB_CUDA(cudaStreamSynchronize(st));
+                CB_CUDA(cudaFree(SWg));
+                L.chat[which][2][2] = chat;
+            }
+        }
+    CB_CUDA(cudaMalloc(&cs.d_lev, sizeof(ConvLevel) * h.size()));
+    CB_CUDA(cudaMemcpy(cs.d_lev, h.data(), sizeof(ConvLevel) * h.size(), cudaMemcpyHostToDevice));
+    if (tang) return build_levels(cs, st, true);
     return 0;
 }
 

@@ -190,12 +190,13 @@ struct RowSrc {
     int cmx, cmy;        // coefficients: allocated half sizes of cf
     int Fx, Fy;
     int row0;            // first padded row handled in this batch
+    int stride;          // tractions: row stride of the source array (0: = mx); lets a sub-box of a larger grid be the input
 };
 
 CB_HD double rowsrc_get(const RowSrc &s, int row, int col)
 {
     if (s.kind == 0) {
-        return (row < s.my && col < s.mx) ? s.base[(size_t) row * s.mx + col] : 0.0;
+        return (row < s.my && col < s.mx) ? s.base[(size_t) row * (s.stride ? s.stride : s.mx) + col] : 0.0;
     } else {
         const int iy = row + s.row0 - s.Fy, ix = col - s.Fx;
         if (iy < -s.my || iy >= s.my || ix < -s.mx || ix >= s.mx) return 0.0;
@@ -281,6 +282,26 @@ CB_HD void row_store(const ConvPlan &P, B buf, uint32_t oS, int SY, double *u, c
     const uint32_t mg = div_magic(P.mx);
     for (int ii = tid; ii < P.npot; ii += nthr) {
         const uint32_t iy = fdiv(ii, mg), ix = ii - iy * P.mx;
+        if (mask_mode == 1 && el[ii] < 1) continue;
+        const uint32_t xi = P.Fx + ix;
+        const cd z = buf.ld(oS + (xi >> 1) * SY + iy);
+        const double v = (xi & 1) ? z.y : z.x;
+        u[ii] = add ? u[ii] + v : v;
+    }
+}
+
+// the same for a sub-box (x0, y0, bw x bh) of a grid with row stride `stride`: element (ix, iy) of the box is element
+// (x0+ix, y0+iy) of u / el.  Used when the product is restricted to the bounding box of the contact area
+// (m_aijpj.f90:774-793).
+template <class B>
+CB_HD void row_store_box(const ConvPlan &P, B buf, uint32_t oS, int SY, double *u, const int *el, int mask_mode, int add,
+                         int x0, int y0, int bw, int bh, int stride, int tid, int nthr)
+{
+    const uint32_t mg = div_magic(bw);
+    const int nbox = bw * bh;
+    for (int w = tid; w < nbox; w += nthr) {
+        const uint32_t iy = fdiv(w, mg), ix = w - iy * bw;
+        const size_t ii = (size_t) (y0 + iy) * stride + x0 + ix;
         if (mask_mode == 1 && el[ii] < 1) continue;
         const uint32_t xi = P.Fx + ix;
         const cd z = buf.ld(oS + (xi >> 1) * SY + iy);

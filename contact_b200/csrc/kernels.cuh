@@ -28,7 +28,7 @@ k_build_chat(ConvPlan P, const double *cfblk0, int cmx, int cmy, double scale, c
     RowSrc src;
     src.base = cfblk; src.kind = 1;
     src.mx = min(P.Fx, P.mx); src.my = min(P.Fy, P.my);          // m_aijpj.f90:896-898
-    src.cmx = cmx; src.cmy = cmy; src.Fx = P.Fx; src.Fy = P.Fy; src.row0 = 0;
+    src.cmx = cmx; src.cmy = cmy; src.Fx = P.Fx; src.Fy = P.Fy; src.row0 = 0; src.stride = 0;
     CB_CONV_FORWARD_ROWS(2 * P.Fy, src);
     CB_CONV_COLUMNS_DUMP(2 * P.Fy, chat, scale);
 }

@@ -189,7 +189,7 @@ __device__ void lg_conv(const LargeCtx &X, uint32_t a0, const double *p, const c
     const LargePlan &L = X.L;
     const ConvPlan &P = L.P;
     RowSrc src;
-    src.base = p; src.kind = 0; src.mx = P.mx; src.my = P.my; src.cmx = 0; src.cmy = 0; src.Fx = P.Fx; src.Fy = P.Fy; src.row0 = 0;
+    src.base = p; src.kind = 0; src.mx = P.mx; src.my = P.my; src.cmx = 0; src.cmy = 0; src.Fx = P.Fx; src.Fy = P.Fy; src.row0 = 0; src.stride = 0;
     for (int t = blockIdx.x; t < L.ntr; t += gridDim.x)
         lg_rows_fwd_task(P, a0, t * L.RB, min(L.RB, P.my - t * L.RB), src, X.T, L.ldT);
     grid.sync();
@@ -516,6 +516,9 @@ struct GridCtx {
     __device__ __forceinline__ void conv(const double *p, const cd *chat, double *u, const int *el, int mask_mode, int add) const
     { lg_conv(X, a0, p, chat, u, el, mask_mode, add, grid); }
     __device__ __forceinline__ void snorm(NormCase &c) const { lg_snorm(X, a0, redp, c, phase, grid); grid.sync(); }
+    __device__ __forceinline__ void update_box(const NormCase &, const int *) const {}
+    __device__ __forceinline__ void conv_int(int, int, int, const double *p, const cd *chat_full, double *u, const int *el, int add) const
+    { lg_conv(X, a0, p, chat_full, u, el, 1, add, grid); }
 };
 
 // one contact case (NORM / TANG alternation: T = 0 or shifts T = 1 with TangCG) on the whole GPU

@@ -5,15 +5,23 @@
 // pressures with contact/exterior active set, prescribed approach (N=0) or prescribed force (N=1, mean deflation).
 // B200-first: every influence product is the shared-memory FFT convolution (conv_dev), the masked BLAS-1 steps of
 // m_gridfunc.f90:936-1591 are fused into a handful of block-wide passes with fixed-tree reductions, and the
-// iteration control (active-set flips, convergence test) never leaves the SM.  Products always use the full
-// potential-contact grid (the reference crops to the contact bounding box, m_aijpj.f90:774-793; p is zero outside
-// it, so the result is the same up to rounding).
+// iteration control (active-set flips, convergence test) never leaves the SM.  Like the reference
+// (m_aijpj.f90:774-793), products on the contact area use the bounding box of the contact area with a smaller
+// transform when that pays (a ladder of sizes per coefficient set); products on all elements use the full grid.
 #pragma once
 #include "device_core.cuh"
 
 namespace cb200 {
 
 #define CB_TINY 1e-20
+
+// Products on the contact area (AllInt) are restricted to the bounding box of the contact area, as in the reference
+// (m_aijpj.f90:774-793): a ladder of smaller transform sizes with their own transformed coefficients is prepared per
+// coefficient set; lev[ly * nlx + lx], sizes descending, lev[0] = the full grid.
+struct ConvLevel {
+    ConvPlan P;
+    const cd *chat[2][3][3];   // [0: cs, 1: ms (preconditioner)][ik][jk]; null = not prepared (the full grid is used then)
+};
 
 struct NormCase {
     // inputs
@@ -36,7 +44,51 @@ struct NormCase {
     int itcg, itnorm, ncon, status;     // status bit 0: NormCG diverged at MaxCG (reference: abort_run)
     double err;
     int nprod;               // number of single-block influence products performed (work accounting)
+    const ConvLevel *lev;    // ladder of transform sizes (null: always the full grid)
+    int nlx, nly;
 };
+
+struct ContactBox { int x0, y0, bw, bh; const ConvLevel *lv; };
+
+// bounding box of the contact area (+1 column on either side, m_aijpj.f90:774-777) and the smallest level that holds it
+__device__ ContactBox contact_box_dev(const ConvPlan &P, const NormCase &c, const int *el, double *red)
+{
+    const int mx = P.mx, n = P.npot;
+    int x0 = mx, x1 = -1, y0 = P.my, y1 = -1;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        if (el[i] >= 1) { const int iy = i / mx, ix = i - iy * mx; x0 = min(x0, ix); x1 = max(x1, ix); y0 = min(y0, iy); y1 = max(y1, iy); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+        y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+    }
+    int *ired = reinterpret_cast<int *>(red);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) { ired[4 * wid] = x0; ired[4 * wid + 1] = x1; ired[4 * wid + 2] = y0; ired[4 * wid + 3] = y1; }
+    __syncthreads();
+    for (int w = 0; w < nw; w++) { x0 = min(x0, ired[4 * w]); x1 = max(x1, ired[4 * w + 1]); y0 = min(y0, ired[4 * w + 2]); y1 = max(y1, ired[4 * w + 3]); }
+    __syncthreads();
+    ContactBox b = { 0, 0, mx, P.my, nullptr };
+    if (c.lev == nullptr || x1 < x0) return b;
+    x0 = max(0, x0 - 1); x1 = min(mx - 1, x1 + 1);
+    const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
+    if (1.1 * (double) bw * bh > (double) mx * P.my) return b;              // not much smaller: full grid (:783-789)
+    int lx = 0, ly = 0;
+    while (lx + 1 < c.nlx && c.lev[lx + 1].P.mx >= bw) lx++;
+    while (ly + 1 < c.nly && c.lev[(ly + 1) * c.nlx].P.my >= bh) ly++;
+    if (lx == 0 && ly == 0) return b;
+    b.x0 = x0; b.y0 = y0; b.bw = bw; b.bh = bh; b.lv = &c.lev[ly * c.nlx + lx];
+    return b;
+}
+
+// AllInt product with A_zz (which = 0) or the preconditioner M_zz (which = 1), on the contact box when a smaller level fits
+__device__ __forceinline__ void conv_int_dev(const ConvPlan &P, const Smem &sm, const NormCase &c, const ContactBox &b, int which,
+                                             const double *p, double *u, const int *el)
+{
+    if (b.lv && b.lv->chat[which][2][2]) conv_box_dev(b.lv->P, sm, p, b.lv->chat[which][2][2], u, el, 1, 0, b.x0, b.y0, b.bw, b.bh, P.mx);
+    else conv_dev(P, sm, p, which ? c.chatM : c.chatA, u, el, 1, 0);
+}
 
 // Masked vector pass with all loads of a batch in flight before any use: the work vectors live in global memory
 // (L2-resident), so a pass is latency bound unless its loads are issued back to back.  Each thread handles elements
@@ -134,7 +186,8 @@ __device__ int normcg_dev(const ConvPlan &P, const Smem &sm, const NormCase &c, 
         __syncthreads();
     }
 
-    conv_dev(P, sm, ps, c.chatA, res, el, 1, 0); nprod++;            // :173-175 res = rhs - A ps on C
+    ContactBox box = contact_box_dev(P, c, el, red);
+    conv_int_dev(P, sm, c, box, 0, ps, res, el); nprod++;             // :173-175 res = rhs - A ps on C
     vec_pass<2>(n, el, rhs, res, nullptr, nullptr, [&](int i, int e, const double *a) { if (e >= 1) res[i] = a[0] - a[1]; });
     __syncthreads();
     if (ic_norm == 1) proj_avg_dev(el, res, n, red);
@@ -145,7 +198,7 @@ __device__ int normcg_dev(const ConvPlan &P, const Smem &sm, const NormCase &c, 
 
     while ((lchanged || rms_upd > eps * rms_xk) && itcg < maxcg) {   // :194
         itcg++; itinn++;
-        conv_dev(P, sm, res, c.chatM, z, el, 1, 0); nprod++;         // z = M res on C
+        conv_int_dev(P, sm, c, box, 1, res, z, el); nprod++;          // z = M res on C
         if (ic_norm == 1) proj_avg_dev(el, z, n, red);
 
         double d2[2] = { 0.0, 0.0 };
@@ -164,7 +217,7 @@ __device__ int normcg_dev(const ConvPlan &P, const Smem &sm, const NormCase &c, 
         __syncthreads();
         if (ic_norm == 1) proj_avg_dev(el, v, n, red);
 
-        conv_dev(P, sm, v, c.chatA, q, el, 1, 0); nprod++;           // q = A v on C
+        conv_int_dev(P, sm, c, box, 0, v, q, el); nprod++;            // q = A v on C
         if (ic_norm == 1) proj_avg_dev(el, q, n, red);
 
         double d4[4] = { 0.0, 0.0, 0.0, 0.0 };
@@ -249,6 +302,7 @@ __device__ int normcg_dev(const ConvPlan &P, const Smem &sm, const NormCase &c, 
             ncon += (int) ke[0];
             itinn = 0;
             lchanged = lchg_intpen || lchg_negpn;
+            if (lchanged) box = contact_box_dev(P, c, el, red);
         }
     }
 

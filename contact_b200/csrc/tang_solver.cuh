@@ -52,8 +52,18 @@ struct ContactCase {
 struct BlockCtx {
     const ConvPlan &P;
     const Smem &sm;
+    mutable ContactBox box = { 0, 0, 0, 0, nullptr };   // bounding box of the contact area + its transform level (null: full grid)
     static constexpr bool kBlock = true;
     __device__ __forceinline__ int n() const { return P.npot; }
+    __device__ __forceinline__ void update_box(const NormCase &c, const int *el) const { box = contact_box_dev(P, c, el, sm.red); }
+    // AllInt product with block (ik, jk) of cs (lset 0) or of the preconditioner (lset 1): on the contact box when a smaller
+    // level with that block is prepared; lset < 0: inputs that may be non-zero outside the contact area -> full grid
+    __device__ __forceinline__ void conv_int(int lset, int ik, int jk, const double *p, const cd *chat_full, double *u, const int *el, int add) const
+    {
+        const cd *ch = (lset >= 0 && box.lv) ? box.lv->chat[lset][ik][jk] : nullptr;
+        if (ch) conv_box_dev(box.lv->P, sm, p, ch, u, el, 1, add, box.x0, box.y0, box.bw, box.bh, P.mx);
+        else conv_dev(P, sm, p, chat_full, u, el, 1, add);
+    }
     __device__ __forceinline__ const ConvPlan &plan() const { return P; }
     __device__ __forceinline__ const Smem &smem() const { return sm; }
     __device__ __forceinline__ double *red() const { return sm.red; }
@@ -71,7 +81,7 @@ struct BlockCtx {
 // transform are skipped (no normal-tangential coupling: m_aijpj.f90:358-369); returns the number of products done
 template <class X>
 __device__ int conv_multi(const X &x, const cd *(&chat)[3][3], const double *p, int jk0, int jk1,
-                          double *u, int ik0, int ik1, const int *el, int mask_mode)
+                          double *u, int ik0, int ik1, const int *el, int mask_mode, int lset = -1)
 {
     const int n = x.n();
     int np = 0;
@@ -79,7 +89,8 @@ __device__ int conv_multi(const X &x, const cd *(&chat)[3][3], const double *p, 
         bool ladd = false;
         for (int jk = jk0; jk <= jk1; jk++) {
             if (chat[ik][jk] == nullptr) continue;
-            x.conv(p + (size_t) jk * n, chat[ik][jk], u + (size_t) ik * n, el, mask_mode, ladd ? 1 : 0);
+            if (mask_mode == 1) x.conv_int(lset, ik, jk, p + (size_t) jk * n, chat[ik][jk], u + (size_t) ik * n, el, ladd ? 1 : 0);
+            else x.conv(p + (size_t) jk * n, chat[ik][jk], u + (size_t) ik * n, el, mask_mode, ladd ? 1 : 0);
             ladd = true; np++;
         }
         if (!ladd) {
@@ -127,7 +138,7 @@ __device__ void tangcg_dev(const X &x, ContactCase &c, const double *ws, int max
         v[i] = 0.0; v[n + i] = 0.0; q[i] = 0.0; q[n + i] = 0.0; z[i] = 0.0; z[n + i] = 0.0; pold[i] = 0.0; pold[n + i] = 0.0;
     }
     x.sync();
-    nprod += conv_multi(x, c.chatA, ps, 0, 1, ss, 0, 1, el, 1);
+    nprod += conv_multi(x, c.chatA, ps, 0, 1, ss, 0, 1, el, 1, 0);
     for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) {
         const int e = el[i];
         double sx = ss[i], sy = ss[n + i];
@@ -146,8 +157,8 @@ __device__ void tangcg_dev(const X &x, ContactCase &c, const double *ws, int max
             if (!use_fftprec) lchanged = true;
         }
         if (use_fftprec) {
-            x.conv(r, c.chatM11, z, el, 1, 0);
-            x.conv(r + n, c.chatM22, z + n, el, 1, 0);
+            x.conv_int(1, 0, 0, r, c.chatM11, z, el, 0);
+            x.conv_int(1, 1, 1, r + n, c.chatM22, z + n, el, 0);
             nprod += 2;
         }
         double d2[2] = { 0.0, 0.0 };
@@ -177,7 +188,7 @@ __device__ void tangcg_dev(const X &x, ContactCase &c, const double *ws, int max
         }
         x.sync();
 
-        nprod += conv_multi(x, c.chatA, v, 0, 1, q, 0, 1, el, 1);          // q = A_tt v on C
+        nprod += conv_multi(x, c.chatA, v, 0, 1, q, 0, 1, el, 1, 0);       // q = A_tt v on C
         double d3[3] = { 0.0, 0.0, 0.0 };
         for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) {
             double qx = q[i], qy = q[n + i];
@@ -223,7 +234,7 @@ __device__ void tangcg_dev(const X &x, ContactCase &c, const double *ws, int max
                 if (pa > g[i]) { el[i] = 2; ps[i] = px * g[i] / pa; ps[n + i] = py * g[i] / pa; ch[0] += 1.0; }
             }
             x.sync();
-            nprod += conv_multi(x, c.chatA, ps, 0, 1, ss, 0, 1, el, 1);
+            nprod += conv_multi(x, c.chatA, ps, 0, 1, ss, 0, 1, el, 1, 0);
             double dp[1] = { 0.0 };
             for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) {
                 const int e = el[i];
@@ -449,7 +460,7 @@ __device__ int stang_dev(const X &x, ContactCase &c, double fntrue, int &itgs_to
     }
     // stang_rhs (:749-951): wsfix = -facdt hs_t + A_tn pn - A'_tn p'n - A'_tt p'_t on C; shifts: facdt = 1, previous
     // tractions p'; steady rolling: p' = p with the shifted coefficients cv, A'_tt p'_t left to the solver
-    nprod += conv_multi(x, c.chatA, ps, 2, 2, u1, 0, 1, el, 1);
+    nprod += conv_multi(x, c.chatA, ps, 2, 2, u1, 0, 1, el, 1, 0);
     if (ssrol) {
         nprod += conv_multi(x, c.chatV, ps, 2, 2, u2, 0, 1, el, 1);
         for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) if (el[i] >= 1) { u1[i] -= u2[i]; u1[n + i] -= u2[n + i]; }
@@ -521,6 +532,7 @@ __device__ void panprc_dev(const X &x, ContactCase &c)
     while (dif > difid && itout < c.maxout && itnorm >= 0 && ittang >= 0) {
         itout++;
         x.snorm(c.nrm);
+        x.update_box(c.nrm, el);
         itcg += c.nrm.itcg; nprod += c.nrm.nprod;
         if (c.nrm.itnorm >= 0) itnorm += c.nrm.itnorm; else itnorm = -1;
         const int ncon = c.nrm.ncon;

@@ -36,7 +36,7 @@ k_prof(ConvPlan P, const double *p, const cd *chat, double *u, int ncase)
     for (int ic = blockIdx.x; ic < ncase; ic += gridDim.x) {
         np_ = 0;
         if (tid == 0 && blockIdx.x == 0) tt_[np_++] = clock64();
-        RowSrc src; src.base = p + (size_t) ic * P.npot; src.kind = 0; src.mx = P.mx; src.my = P.my; src.cmx = 0; src.cmy = 0; src.Fx = P.Fx; src.Fy = P.Fy; src.row0 = 0;
+        RowSrc src; src.base = p + (size_t) ic * P.npot; src.kind = 0; src.mx = P.mx; src.my = P.my; src.cmx = 0; src.cmy = 0; src.Fx = P.Fx; src.Fy = P.Fy; src.row0 = 0; src.stride = 0;
         CB_CONV_FORWARD_ROWS(P.my, src);
         CB_CONV_COLUMNS_PRODUCT(P.my, chat);
         CB_CONV_INVERSE_ROWS(P.my);
