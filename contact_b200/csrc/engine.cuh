@@ -198,85 +198,72 @@ inline int build_levels(CoefSet &cs, cudaStream_t st, bool tang = false)
     Engine &E = engine();
     if (!cs.hp.fits) return 0;
     if (cs.d_lev && (!tang || cs.lev_tang)) return 0;
-    // blocks wanted per level: normal problem cs(3,3), ms(3,3); tangential problem also cs(1:2,1:2), ms(1,1), ms(2,2) and,
-    // with normal-tangential coupling, cs(1:2,3)
-    struct Want { int set, ik, jk; };
-    std::vector<Want> want = { { 0, 3, 3 }, { 1, 3, 3 } };
-    if (tang) {
-        for (int ik = 1; ik <= 2; ik++) for (int jk = 1; jk <= 2; jk++) want.push_back({ 0, ik, jk });
-        want.push_back({ 1, 1, 1 }); want.push_back({ 1, 2, 2 });
-        if (cs.nt_cpl) { want.push_back({ 0, 1, 3 }); want.push_back({ 0, 2, 3 }); }
-    }
-    if (cs.d_lev) {                                            // second call: add the tangential blocks
+    const size_t nblk = (size_t) 4 * cs.mx * cs.my;
+    if (!cs.d_lev) {
+        // sizes with two large radix stages per direction (48, 64, 72, 96 ...) are preferred over the tightest fit
+        auto ladder = [](int n) {
+            static const int nice[] = { 192, 144, 128, 96, 80, 72, 64, 48, 32, 24, 16, 12, 8 };
+            std::vector<int> v(1, n);
+            for (int c : nice) if (c < n && (int) v.size() < 8) v.push_back(c);
+            return v;
+        };
+        const std::vector<int> fx = ladder(cs.mx), fy = ladder(cs.my);
+        cs.nlx = (int) fx.size(); cs.nly = (int) fy.size();
+        if (cs.nlx * cs.nly <= 1) return 0;
+        cs.lev_hp.resize((size_t) cs.nlx * cs.nly);
         std::vector<ConvLevel> h((size_t) cs.nlx * cs.nly);
-        CB_CUDA(cudaMemcpy(h.data(), cs.d_lev, sizeof(ConvLevel) * h.size(), cudaMemcpyDeviceToHost));
-        for (size_t l = 1; l < h.size(); l++)
-            for (const Want &w : want) {
-                if (h[l].chat[w.set][w.ik - 1][w.jk - 1]) continue;
-                const ConvPlan &P = h[l].P;
-                cd *chat = nullptr, *SWg = nullptr;
-                CB_CUDA(cudaMalloc(&chat, sizeof(cd) * (size_t) P.chat_len));
-                CB_CUDA(cudaMalloc(&SWg, sizeof(cd) * ((size_t) (P.Lx + 1) * 2 * P.Fy + (size_t) P.Ly * P.C)));
-                const double *blk = cs.d_cf[w.set ? SET_MS : SET_CS] + (size_t) ((w.jk - 1) * 3 + (w.ik - 1)) * 4 * cs.mx * cs.my;
-                k_build_chat<<<1, CB_THREADS, 64, st>>>(P, blk, cs.mx, cs.my, cs.ga_inv / (4.0 * P.Fx * P.Fy), SWg, chat);
-                E.launches++;
-                CB_CUDA(cudaGetLastError());
-                CB_CUDA(cudaStreamSynchronize(st));
-                CB_CUDA(cudaFree(SWg));
-                h[l].chat[w.set][w.ik - 1][w.jk - 1] = chat;
+        for (int ly = 0; ly < cs.nly; ly++)
+            for (int lx = 0; lx < cs.nlx; lx++) {
+                HostPlan &hp = cs.lev_hp[(size_t) ly * cs.nlx + lx];
+                ConvLevel &L = h[(size_t) ly * cs.nlx + lx];
+                memset(&L, 0, sizeof(L));
+                if (lx == 0 && ly == 0) { L.P = cs.hp.p; continue; }
+                // the level plans live in the dynamic shared memory that the kernels are launched with for the full-size plan
+                if (!make_plan(fx[lx], fy[ly], hp, cs.hp.p.smem_bytes) || !hp.fits) { last_error() = "internal: level plan does not fit"; return -99; }
+                ConvPlan &P = hp.p;
+                cd *twx, *twy; unsigned short *posx;
+                CB_CUDA(cudaMalloc(&twx, sizeof(cd) * hp.twx.size()));
+                CB_CUDA(cudaMalloc(&twy, sizeof(cd) * hp.twy.size()));
+                CB_CUDA(cudaMalloc(&posx, sizeof(unsigned short) * hp.posx.size()));
+                CB_CUDA(cudaMemcpyAsync(twx, hp.twx.data(), sizeof(cd) * hp.twx.size(), cudaMemcpyHostToDevice, st));
+                CB_CUDA(cudaMemcpyAsync(twy, hp.twy.data(), sizeof(cd) * hp.twy.size(), cudaMemcpyHostToDevice, st));
+                CB_CUDA(cudaMemcpyAsync(posx, hp.posx.data(), sizeof(unsigned short) * hp.posx.size(), cudaMemcpyHostToDevice, st));
+                P.twx = twx; P.twy = twy; P.posx = posx;
+                L.P = P;
             }
-        for (const Want &w : want) h[0].chat[w.set][w.ik - 1][w.jk - 1] = cs.d_chat[w.set ? SET_MS : SET_CS][w.ik - 1][w.jk - 1];
+        CB_CUDA(cudaMalloc(&cs.d_lev, sizeof(ConvLevel) * h.size()));
         CB_CUDA(cudaMemcpy(cs.d_lev, h.data(), sizeof(ConvLevel) * h.size(), cudaMemcpyHostToDevice));
-        cs.lev_tang = true;
-        return 0;
     }
-    auto ladder = [](int n) {
-        std::vector<int> v(1, n);
-        for (double r : { 0.8, 0.64, 0.5, 0.4, 0.3 }) {
-            const int f = opt_fft_size(std::max(4, (int) ceil(n * r)));
-            if (f < v.back() && f >= 4) v.push_back(f);
-        }
-        return v;
-    };
-    const std::vector<int> fx = ladder(cs.mx), fy = ladder(cs.my);
-    cs.nlx = (int) fx.size(); cs.nly = (int) fy.size();
-    if (cs.nlx * cs.nly <= 1) return 0;
-    cs.lev_hp.resize((size_t) cs.nlx * cs.nly);
+    // transformed blocks per level: all nine blocks of cs (and the diagonal of ms) in one launch per (level, set); the
+    // normal problem needs cs(3,3), ms(3,3), the tangential problem cs(1:2,1:3), ms(1,1), ms(2,2)
     std::vector<ConvLevel> h((size_t) cs.nlx * cs.nly);
-    const double scale = cs.ga_inv;
-    for (int ly = 0; ly < cs.nly; ly++)
-        for (int lx = 0; lx < cs.nlx; lx++) {
-            HostPlan &hp = cs.lev_hp[(size_t) ly * cs.nlx + lx];
-            ConvLevel &L = h[(size_t) ly * cs.nlx + lx];
-            memset(&L, 0, sizeof(L));
-            if (lx == 0 && ly == 0) { L.P = cs.hp.p; L.chat[0][2][2] = cs.d_chat[SET_CS][2][2]; L.chat[1][2][2] = cs.d_chat[SET_MS][2][2]; continue; }
-            if (!make_plan(fx[lx], fy[ly], hp) || !hp.fits) { last_error() = "internal: level plan does not fit"; return -99; }
-            ConvPlan &P = hp.p;
-            cd *twx, *twy; unsigned short *posx;
-            CB_CUDA(cudaMalloc(&twx, sizeof(cd) * hp.twx.size()));
-            CB_CUDA(cudaMalloc(&twy, sizeof(cd) * hp.twy.size()));
-            CB_CUDA(cudaMalloc(&posx, sizeof(unsigned short) * hp.posx.size()));
-            CB_CUDA(cudaMemcpyAsync(twx, hp.twx.data(), sizeof(cd) * hp.twx.size(), cudaMemcpyHostToDevice, st));
-            CB_CUDA(cudaMemcpyAsync(twy, hp.twy.data(), sizeof(cd) * hp.twy.size(), cudaMemcpyHostToDevice, st));
-            CB_CUDA(cudaMemcpyAsync(posx, hp.posx.data(), sizeof(unsigned short) * hp.posx.size(), cudaMemcpyHostToDevice, st));
-            P.twx = twx; P.twy = twy; P.posx = posx;
-            L.P = P;
-            for (int which = 0; which < 2; which++) {
-                cd *chat = nullptr, *SWg = nullptr;
-                CB_CUDA(cudaMalloc(&chat, sizeof(cd) * (size_t) P.chat_len));
-                CB_CUDA(cudaMalloc(&SWg, sizeof(cd) * ((size_t) (P.Lx + 1) * 2 * P.Fy + (size_t) P.Ly * P.C)));
-                const double *blk = cs.d_cf[which ? SET_MS : SET_CS] + (size_t) 8 * 4 * cs.mx * cs.my;
-                k_build_chat<<<1, CB_THREADS, 64, st>>>(P, blk, cs.mx, cs.my, scale / (4.0 * P.Fx * P.Fy), SWg, chat);
-                E.launches++;
-                CB_CUDA(cudaGetLastError());
-                CB_CUDA(cudaStreamSynchronize(st));
-                CB_CUDA(cudaFree(SWg));
-                L.chat[which][2][2] = chat;
+    CB_CUDA(cudaMemcpy(h.data(), cs.d_lev, sizeof(ConvLevel) * h.size(), cudaMemcpyDeviceToHost));
+    for (size_t l = 1; l < h.size(); l++) {
+        const ConvPlan &P = h[l].P;
+        const size_t nscr = (size_t) (P.Lx + 1) * 2 * P.Fy + (size_t) P.Ly * P.C;
+        for (int set = 0; set < 2; set++) {
+            const bool have33 = h[l].chat[set][2][2] != nullptr, have11 = h[l].chat[set][0][0] != nullptr;
+            if (have33 && (!tang || have11)) continue;
+            cd *chat = nullptr, *scr = nullptr;
+            CB_CUDA(cudaMalloc(&chat, sizeof(cd) * 9 * (size_t) P.chat_len));
+            CB_CUDA(cudaMalloc(&scr, sizeof(cd) * 9 * nscr));
+            k_build_chat<<<9, CB_THREADS, 64, st>>>(P, cs.d_cf[set ? SET_MS : SET_CS], cs.mx, cs.my, cs.ga_inv / (4.0 * P.Fx * P.Fy), scr, chat);
+            E.launches++;
+            CB_CUDA(cudaGetLastError());
+            CB_CUDA(cudaStreamSynchronize(st));
+            CB_CUDA(cudaFree(scr));
+            for (int jk = 0; jk < 3; jk++) for (int ik = 0; ik < 3; ik++) {
+                const bool diag = ik == jk, nt = (ik == 2) != (jk == 2);
+                if (set == 1 && !diag) continue;                       // the preconditioner has diagonal blocks only
+                if (nt && !cs.nt_cpl) continue;
+                if (set == 1 && !cs.prec_ready[ik]) continue;          // ms(ik,ik) not built: leave null -> full grid
+                h[l].chat[set][ik][jk] = chat + (size_t) (jk * 3 + ik) * P.chat_len;
             }
         }
-    CB_CUDA(cudaMalloc(&cs.d_lev, sizeof(ConvLevel) * h.size()));
+    }
     CB_CUDA(cudaMemcpy(cs.d_lev, h.data(), sizeof(ConvLevel) * h.size(), cudaMemcpyHostToDevice));
-    if (tang) return build_levels(cs, st, true);
+    if (tang) cs.lev_tang = true;
+    (void) nblk;
     return 0;
 }
 
