@@ -370,7 +370,10 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
         CoefSet *cs = nullptr;
         double chi_e, dq_e;
         roll_stepsize(p, chi_e, dq_e);
-        int rc = get_coefset(p.mx, p.my, p.dx, p.dy, p.mat, p.tang == 3 ? 1 : 0, chi_e, dq_e, 0, &cs);
+        // latency mode: a single case (the usual call pattern of a multibody code, and of case sequences) would occupy one
+        // of 148 SMs on the batched path; with a grid of some size it runs faster spread over the whole GPU
+        const int whole = (nb == 1 && p.tang != 3 && p.mx * p.my >= 1024 && p.mx >= 16 && p.my >= 16) ? 1 : 0;
+        int rc = get_coefset(p.mx, p.my, p.dx, p.dy, p.mat, p.tang == 3 ? 1 : 0, chi_e, dq_e, 0, &cs, whole);
         if (rc) { ierr[k] = rc; continue; }
         // grids beyond one CTA's shared memory go to the whole-GPU path, which serves T = 0 and T = 1 (TangCG)
         if (!cs->hp.fits && p.tang == 3) { last_error() = "grid too large for the single-CTA SteadyGS solver (the whole-GPU path serves T=0 and T=1)"; ierr[k] = CNTC_err_discr; continue; }

@@ -45,10 +45,11 @@ inline void combine_material(Material &m)
 
 struct CoefKey {
     int mx, my; double dx, dy, ga, nu, ak; int is_roll; double chi, dq;
+    int whole_gpu;     // 1: plan and transforms for the whole-GPU path even though the grid fits one CTA (latency mode)
     bool operator<(const CoefKey &o) const {
-        const double a[] = { (double) mx, (double) my, dx, dy, ga, nu, ak, (double) is_roll, chi, dq };
-        const double b[] = { (double) o.mx, (double) o.my, o.dx, o.dy, o.ga, o.nu, o.ak, (double) o.is_roll, o.chi, o.dq };
-        for (int i = 0; i < 10; i++) { if (a[i] < b[i]) return true; if (a[i] > b[i]) return false; }
+        const double a[] = { (double) mx, (double) my, dx, dy, ga, nu, ak, (double) is_roll, chi, dq, (double) whole_gpu };
+        const double b[] = { (double) o.mx, (double) o.my, o.dx, o.dy, o.ga, o.nu, o.ak, (double) o.is_roll, o.chi, o.dq, (double) o.whole_gpu };
+        for (int i = 0; i < 11; i++) { if (a[i] < b[i]) return true; if (a[i] > b[i]) return false; }
         return false;
     }
 };
@@ -311,13 +312,13 @@ inline int build_prec(CoefSet &cs, cudaStream_t st, int ik = 3)
 
 // ---- create / look up a coefficient set ----
 inline int get_coefset(int mx, int my, double dx, double dy, Material mat, int is_roll, double chi, double dq,
-                       cudaStream_t st, CoefSet **out)
+                       cudaStream_t st, CoefSet **out, int whole_gpu = 0)
 {
     int rc = engine_init();
     if (rc) return rc;
     Engine &E = engine();
     combine_material(mat);
-    CoefKey key = { mx, my, dx, dy, mat.ga, mat.nu, mat.ak, is_roll, is_roll ? chi : 0.0, is_roll ? dq : 0.0 };
+    CoefKey key = { mx, my, dx, dy, mat.ga, mat.nu, mat.ak, is_roll, is_roll ? chi : 0.0, is_roll ? dq : 0.0, whole_gpu };
     std::lock_guard<std::mutex> lk(E.mu);
     auto it = E.sets.find(key);
     if (it != E.sets.end()) { *out = it->second; return 0; }
@@ -327,6 +328,7 @@ inline int get_coefset(int mx, int my, double dx, double dy, Material mat, int i
     cs->ga = mat.ga; cs->ga_inv = 1.0 / mat.ga;
     cs->nt_cpl = !(fabs(mat.ak) < 1e-6);                             // m_visc.f90:239-243
     if (!make_plan(mx, my, cs->hp)) { last_error() = "unsupported grid size for the FFT product"; delete cs; return -34; }
+    if (whole_gpu) cs->hp.fits = false;
     ConvPlan &P = cs->hp.p;
     CB_CUDA(cudaMalloc(&cs->d_twx, sizeof(cd) * cs->hp.twx.size()));
     CB_CUDA(cudaMalloc(&cs->d_twy, sizeof(cd) * cs->hp.twy.size()));
