@@ -196,7 +196,8 @@ inline int count_at_boundary(const Problem &p)
 // check_case / scope check: returns 0 or an error code
 inline int check_scope(const Problem &p)
 {
-    if (p.tang == 2) { last_error() = "T-digit: transient rolling (T=2) is not served by the B200 path yet (T=0, 1, 3 are)"; return CNTC_err_other; }
+    if (p.tang == 2 && fabs(p.chi) > 0.01) { last_error() = "transient rolling (T=2): only CHI = 0 is served by the B200 path"; return CNTC_err_other; }
+    if (p.tang == 2 && p.dq > p.dx * (1.0 + 1e-4)) { last_error() = "transient rolling (T=2) with DQ > DX needs the leading-edge equations, which the B200 path does not serve"; return CNTC_err_other; }
     if (p.tang != 0 && p.frclaw != 0) { last_error() = "L-digit: only Coulomb friction (L=0)"; return CNTC_err_other; }
     if (p.tang == 3 && p.gausei == 2 && fabs(p.chi) > 0.01) { last_error() = "ConvexGS in steady rolling: only CHI = 0 is served by the B200 path"; return CNTC_err_other; }
     if (p.tang == 3 && p.gausei == 5) { last_error() = "G-digit: GDsteady (G=5) is not served by the B200 path yet (SteadyGS, G=0/3/4, is)"; return CNTC_err_other; }
@@ -373,7 +374,7 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
         // latency mode: a single case (the usual call pattern of a multibody code, and of case sequences) would occupy one
         // of 148 SMs on the batched path; with a grid of some size it runs faster spread over the whole GPU
         const int whole = (nb == 1 && p.tang != 3 && p.mx * p.my >= 1024 && p.mx >= 16 && p.my >= 16) ? 1 : 0;
-        int rc = get_coefset(p.mx, p.my, p.dx, p.dy, p.mat, p.tang == 3 ? 1 : 0, chi_e, dq_e, 0, &cs, whole);
+        int rc = get_coefset(p.mx, p.my, p.dx, p.dy, p.mat, p.tang >= 2 ? 1 : 0, chi_e, dq_e, 0, &cs, whole);
         if (rc) { ierr[k] = rc; continue; }
         // grids beyond one CTA's shared memory go to the whole-GPU path, which serves T = 0 and T = 1 (TangCG)
         if (!cs->hp.fits && p.tang == 3) { last_error() = "grid too large for the single-CTA SteadyGS solver (the whole-GPU path serves T=0 and T=1)"; ierr[k] = CNTC_err_discr; continue; }
@@ -399,6 +400,9 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
             for (int t = 1; t <= 2 && !rc; t++) { rc = build_chat(cs, SET_CS, 3, t, 0); if (!rc && any_tang) rc = build_chat(cs, SET_CS, t, 3, 0); }
             if (cs.key.is_roll) for (int t = 1; t <= 2 && !rc; t++) rc = build_chat(cs, SET_CV, t, 3, 0);
         }
+        bool any_trans = false;                                   // transient rolling: A'_tt p'_t with the shifted coefficients
+        for (size_t k : ks) any_trans = any_trans || probs[k]->tang == 2;
+        if (!rc && any_trans) for (int ik = 1; ik <= 2 && !rc; ik++) for (int jk = 1; jk <= 2 && !rc; jk++) rc = build_chat(cs, SET_CV, ik, jk, 0);
         if (!rc && cs.key.is_roll)                                  // ConvexGS in steady rolling works with csv = cs - cv
             for (int ik = 1; ik <= 2 && !rc; ik++) for (int jk = 1; jk <= 2 && !rc; jk++) rc = build_chat(cs, SET_CSV, ik, jk, 0);
         if (!rc) rc = build_levels(cs, 0, any_tang);            // after the full-size transforms and preconditioners exist
@@ -439,7 +443,7 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
             if (!p.solved || p.iestim == 0 || p.iestim == 2) { if (p.force3 >= 1) c.cksi = 1e-6; if (p.force3 == 2) c.ceta = 0.0; }   // m_sdis.f90:760-762
             bool pv_nonzero = false;
             for (double v : p.pv) if (v != 0.0) { pv_nonzero = true; break; }
-            c.pv = (pv_nonzero && p.tang == 1) ? base + 41 * (size_t) npot : nullptr;
+            c.pv = (pv_nonzero && (p.tang == 1 || p.tang == 2)) ? base + 41 * (size_t) npot : nullptr;
             if (c.pv) cudaMemcpy(base + 41 * (size_t) npot, p.pv.data(), sizeof(double) * 3 * npot, cudaMemcpyHostToDevice);
             double chi_e, dq_e;
             roll_stepsize(p, chi_e, dq_e);
@@ -508,7 +512,7 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
                 cudaMemcpy(p.el.data(), c.nrm.el, sizeof(int) * npot, cudaMemcpyDeviceToHost);
                 cudaMemcpy(p.ps.data(), c.ps, sizeof(double) * 3 * npot, cudaMemcpyDeviceToHost);
                 if (p.tang != 0) cudaMemcpy(p.ss.data(), c.ss, sizeof(double) * 2 * npot, cudaMemcpyDeviceToHost);
-                if (p.tang == 3) p.dq_eff = c.dq;
+                if (p.tang >= 2) p.dq_eff = c.dq;
                 p.us.assign(h_us.begin() + (size_t) i * 3 * npot, h_us.begin() + (size_t) (i + 1) * 3 * npot);
                 p.hs.assign(3 * (size_t) npot, 0.0);
                 std::copy(hs[ks[i]].begin(), hs[ks[i]].end(), p.hs.begin() + 2 * (size_t) npot);

@@ -407,7 +407,8 @@ int co_contac(co_case *c)
             dq = c->dx;
         }
     }
-    if (c->tang == 2 || (is_ssrol && fabs(chi) > 0.01)) { co_ctx_free(cx); return -99; }     /* not restated */
+    /* not restated: rolling directions other than +x; transient rolling with the leading-edge equations (dq > dx) */
+    if ((is_roll && fabs(chi) > 0.01) || (c->tang == 2 && dq > c->dx * (1.0 + 1e-4))) { co_ctx_free(cx); return -99; }
     co_sgencr(&mat, mx, my, c->dx, c->dy, is_roll, chi, dq, &cs, &cv, &csv, &ms);
     double *x = (double *) malloc(sizeof(double) * npot), *y = (double *) malloc(sizeof(double) * npot);
     double *hs = (double *) calloc(3L * npot, sizeof(double)), *ps = (double *) calloc(3L * npot, sizeof(double));

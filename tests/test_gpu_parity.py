@@ -751,3 +751,37 @@ def test_inp_sequence_spence71_golden(cb):
     assert abs(nout - d["golden"]["nout"]) <= 26 and abs(nout - 521) <= 5, nout
     assert all(r.get("subs_ierror", 0) == 0 for r in res)
     print("spence71_8281pt.inp: 69 cases with subsurface stresses in %.2f s" % dt)
+
+
+def test_transient_rolling_sequence(cb, O):
+    """T=2 (transient rolling, TangCG with the shifted coefficients cv acting on the previous tractions): a sequence of
+    steps from rest (P=0, I=1) against the oracle step by step.  No golden file of the reference covers T=2 on a
+    module-3 grid; the oracle itself is checked by the property that the sequence converges to the T=3 steady state."""
+    g = dict(mx=34, my=27, xl=-3.4, yl=-2.7, dx=0.2, dy=0.2, ibase=1, prmudf=[0.004, 0.0, 0.006, 0.0, 0.0, 0.0])
+    gg, poiss = (82000.0, 82000.0), (0.28, 0.28)
+    kw = dict(norm=1, force3=0, fn=9.0e3, cksi=0.0012, ceta=0.0004, cphi=0.0002, fstat=0.25, fkin=0.25, maxgs=500, maxin=50,
+              maxnr=30, maxout=1, eps=1e-6, chi=0.0, dq=0.2)
+    ire, icp = 91, 1
+    _setup_rolling(cb, ire, g, gg, poiss, fn=9.0e3, fstat=0.25, maxgs=500, maxin=50, maxnr=30, maxout=1, eps=1e-6, force=0)
+    cb.cntc_setrollingstepsize(ire, icp, 0.0, 0.2)
+    cb.cntc_setcreepages(ire, icp, 0.0012, 0.0004, 0.0002)
+    el = ps = None
+    fx_hist = []
+    for k in range(8):
+        cb.cntc_setflags(ire, icp, [cb.CNTC["ic_tang"], cb.CNTC["ic_pvtime"], cb.CNTC["ic_iestim"]], [2, 0 if k else 2, 1 if k else 0])
+        ierr = cb.cntc_calculate(ire, icp)
+        assert ierr == 0, (k, ierr, cb.lib.last_error())
+        extra = {} if el is None else dict(iestim=1, el_in=el, ps_in=ps, pv_in=ps)
+        ref = O.contac(g, gg, poiss, tang=2, gausei=0, **kw, **extra)
+        assert ref["ierror"] == 0
+        el, ps = ref["el"].copy(), ref["ps"].copy()
+        mine_el = cb.cntc_getelementdivision(ire, icp).ravel()
+        pn, px, py = cb.cntc_gettractions(ire, icp)
+        assert np.array_equal(mine_el, el), k
+        s = np.abs(ps[:2]).max()
+        assert np.abs(px.ravel() - ps[0]).max() < 1e-6 * s and np.abs(py.ravel() - ps[1]).max() < 1e-6 * s, k
+        fn, tx, ty, mz = cb.cntc_getcontactforces(ire, icp)
+        fx_hist.append(tx / (0.25 * fn))
+        assert abs(fx_hist[-1] - ref["fx"]) < 1e-7
+    assert all(fx_hist[i + 1] < fx_hist[i] for i in range(7))          # the traction builds up monotonically from rest
+    cb.cntc_finalize(ire)
