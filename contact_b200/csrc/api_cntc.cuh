@@ -479,7 +479,7 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
         if (!NB.ev0) { cudaEventCreate(&NB.ev0); cudaEventCreate(&NB.ev1); }
         cudaEventRecord(NB.ev0, 0);
         if (cs.hp.fits) {
-            k_contac_batch<<<launch_blocks(n), CB_THREADS, P.smem_bytes>>>(P, d_cases, n, d_next);
+            k_contac_batch<<<launch_blocks(n), CB_THREADS, P.smem_bytes + steady_extra_smem(P)>>>(P, d_cases, n, d_next);
             engine().launches++;
         } else {
             LargeCtx X;

@@ -158,12 +158,27 @@ struct SteadySmem {
     __device__ __forceinline__ int &ictl(int j, int my) const { return irow[3 * mx + my + 2 + j]; }
 };
 
+// bytes of the row arrays etc. (without the coefficient table)
+__host__ __device__ __forceinline__ size_t steady_fixed_bytes(int mx, int my)
+{
+    return ((size_t) (6 * mx + 15 * mx + 8)) * 8 + ((size_t) (3 * mx + my + 10)) * 4 + 64;
+}
+
+// extra dynamic shared memory that a launch must provide beyond the FFT plan's: for small grids the S/W regions of the
+// plan are too small for the sweep arrays, which then live behind the plan's own layout
+__host__ __device__ __forceinline__ size_t steady_extra_smem(const ConvPlan &P)
+{
+    const size_t fixed = steady_fixed_bytes(P.mx, P.my);
+    return fixed <= (size_t) P.off_twx ? 0 : fixed;
+}
+
 __device__ __forceinline__ void steady_carve(const ConvPlan &P, unsigned char *base, int sym, SteadySmem &s)
 {
     const size_t n = P.npot, mx = P.mx, my = P.my;
-    const size_t fixed = (6 * mx + 15 * mx + 8) * 8 + (3 * mx + my + 10) * 4 + 64;
+    const size_t fixed = steady_fixed_bytes(P.mx, P.my);
     const size_t tabsz = (sym ? 3 : 6) * n * 8;
     const bool tab = tabsz + fixed <= (size_t) P.off_twx;
+    if (fixed > (size_t) P.off_twx) base += P.smem_bytes;      // behind the plan's layout (see steady_extra_smem)
     double *d = reinterpret_cast<double *>(base);
     s.q = tab ? d : nullptr;
     if (tab) d += (sym ? 3 : 6) * n;

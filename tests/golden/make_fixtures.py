@@ -105,7 +105,7 @@ def subsurf():
 
 
 def write_sequences():
-    for name in ("spence35", "cattaneo"):
+    for name in ("spence35", "cattaneo", "carter2d"):
         json.dump(dict(source="examples/%s.inp, examples/%s.ref_out" % (name, name), cases=inp_cases("examples/%s.inp" % name),
                        ref_out=ref_out_stats("examples/%s.ref_out" % name)),
                   open(os.path.join(HERE, "%s_sequence.json" % name), "w"), indent=0)

@@ -19,8 +19,11 @@ def run_cases(cases):
             g = dict(mx=pc["mx"], my=pc["my"], xl=0.0, yl=0.0, dx=1.0, dy=1.0, ibase=1, prmudf=[0.0] * 6)
             nn = 0
         else:
-            assert pc["ipotcn"] == 1, "tests use IPOTCN = 1 or Hertzian input"
-            g = dict(mx=pc["mx"], my=pc["my"], xl=pc["prm"][0], yl=pc["prm"][1], dx=pc["prm"][2], dy=pc["prm"][3],
+            assert pc["ipotcn"] in (1, 3), "tests use IPOTCN = 1, 3 or Hertzian input"
+            xl, yl = pc["prm"][0], pc["prm"][1]
+            if pc["ipotcn"] == 3:                          # centre of the first element given (potcon_fill)
+                xl, yl = xl - 0.5 * pc["prm"][2], yl - 0.5 * pc["prm"][3]
+            g = dict(mx=pc["mx"], my=pc["my"], xl=xl, yl=yl, dx=pc["prm"][2], dy=pc["prm"][3],
                      ibase=c["geom"]["ibase"], prmudf=np.array(c["geom"]["prm"], dtype=float))
             nn = int(c["geom"]["prm"][0]) if c["geom"]["ibase"] == 2 else 0
         have_prev = el is not None and grid == (pc["mx"], pc["my"])

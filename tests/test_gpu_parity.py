@@ -661,13 +661,15 @@ def _inp_text_from_cases(name):
         out.append(" 3 MODULE")
         out.append(" %d%d%d%d%d%d" % (c["P"], c["B"], c["T"], c["N"], c["F"], c["S"]))
         out.append(" %d%d%d%d%d%d%d" % (c["V"], c["L"], c["D"], c["C"], c["M"], c["Z"], c["E"]))
-        out.append(" %d%d%d%d%d%d%d%d" % (c["X"], c["H"], c["G"], c["I"], c["A"], c["O"], c["W"], c["R"]))
+        out.append(" %d%d%d%d%d%d%d%d" % (0, c["H"], c["G"], c["I"], c["A"], c["O"], c["W"], c["R"]))      # X = 0: no debug record
         if "solver" in c:
             s = c["solver"]
             out.append(" %d %d %d %d %r" % (s["maxgs"], s["maxin"], s["maxnr"], s["maxout"], s["eps"]))
         out.append(" " + " ".join(repr(v) for v in c["kin"]))
         if "fric" in c:
             out.append(" %r %r" % tuple(c["fric"]))
+        if "roll" in c:
+            out.append(" %r %r %r" % (c["roll"]["chi"], c["roll"]["dq"], c["roll"]["veloc"]))
         if "mater" in c:
             out.append(" %r %r %r %r" % (c["mater"]["poiss"][0], c["mater"]["poiss"][1], c["mater"]["gg"][0], c["mater"]["gg"][1]))
         if "potcon" in c:
@@ -785,3 +787,18 @@ def test_transient_rolling_sequence(cb, O):
         assert abs(fx_hist[-1] - ref["fx"]) < 1e-7
     assert all(fx_hist[i + 1] < fx_hist[i] for i in range(7))          # the traction builds up monotonically from rest
     cb.cntc_finalize(ire)
+
+
+def test_inp_carter2d(cb, O):
+    """examples/carter2d.inp (2-D Carter problem: 55 x 1 strip, T=3 SteadyGS, N=1) through the .inp reader: the rows of
+    examples/carter2d.ref_out (ItCG 11, ItGS 19, C/A/S = 50/30/20, Fx = 0.6480, approach 6.492E-03, pmax 113.9)."""
+    from contact_b200 import inp as INP
+    from tests.test_inp_sequences import check_against_ref_out
+    text, d = _inp_text_from_cases("carter2d")
+    res = INP.run_inp(text, ire=84)
+    assert [r["ierror"] for r in res] == [0], [r.get("message") for r in res]
+    r = res[0]
+    mine = [dict(pen=r["pen"], pmax=r["pmax"], fx=r["fx"] / (0.3 * r["fn"]), fy=r["fy"] / (0.3 * r["fn"]), ncon=r["ncon"],
+                 nadh=r["nadh"], nslip=r["nslip"], itnorm=r["its"]["itnorm"], ittang=r["its"]["ittang"])]
+    check_against_ref_out(mine, d["ref_out"])
+    assert r["its"]["itcg"] == 11 and r["its"]["itgs"] == 19

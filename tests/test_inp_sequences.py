@@ -53,9 +53,19 @@ def test_oracle_reproduces_cattaneo_ref_out():
     assert r[1]["itgs_tang"] == 59 and (r[1]["nadh"], r[1]["nslip"]) == (45, 132)
 
 
+def test_oracle_reproduces_carter2d_ref_out():
+    """examples/carter2d.inp: the 2-D Carter problem (55 x 1 strip, steady rolling T=3 with SteadyGS, N=1, IPOTCN=3, DQ
+    overruled to DX): examples/carter2d.ref_out:70, :519, :561 -- ItCG 11, ItGS 19, C/A/S = 50/30/20, Fx = 0.6480,
+    approach 6.492E-03, pmax 113.9."""
+    d = _load("carter2d")
+    r = inp_oracle.run_cases(d["cases"])
+    check_against_ref_out(r, d["ref_out"])
+    assert r[0]["itcg_norm"] == 11 and r[0]["itgs_tang"] == 19
+
+
 @pytest.mark.skipif(not os.path.exists("/root/reference/examples/spence35.inp"), reason="reference tree not present")
 def test_reader_on_reference_files_matches_fixtures():
-    for name in ("spence35", "cattaneo"):
+    for name in ("spence35", "cattaneo", "carter2d"):
         cases = INP.parse_inp(open("/root/reference/examples/%s.inp" % name).read())
         assert json.loads(json.dumps(cases)) == _load(name)["cases"]
     # the perf-suite inputs parse too (BASELINE configs): 69-case Spence sequence with the 11-depth subsurface block
