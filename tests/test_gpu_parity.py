@@ -802,3 +802,60 @@ def test_inp_carter2d(cb, O):
                  nadh=r["nadh"], nslip=r["nslip"], itnorm=r["its"]["itnorm"], ittang=r["its"]["ittang"])]
     check_against_ref_out(mine, d["ref_out"])
     assert r["its"]["itcg"] == 11 and r["its"]["itgs"] == 19
+
+
+# ------------------------------------------------------------------------------------------------------------
+# edge cases of the interface
+# ------------------------------------------------------------------------------------------------------------
+def test_no_contact_and_tiny_grids(cb, O):
+    """Empty contact (bodies apart), a single-element grid and 1-D strips."""
+    ire = 95
+    for (mx, my, pen, expect_ncon) in ((9, 7, -0.01, 0), (1, 1, 0.01, 1), (1, 9, 0.005, None), (13, 1, 0.005, None)):
+        g = dict(mx=mx, my=my, xl=-0.5 * mx * 0.1, yl=-0.5 * my * 0.1, dx=0.1, dy=0.1, ibase=1, prmudf=[0.02, 0.0, 0.02, 0.0, 0.0, 0.0])
+        cb.cntc_initialize(ire, 3)
+        cb.cntc_setflags(ire, 1, [cb.CNTC["ic_tang"], cb.CNTC["ic_iestim"]], [0, 0])
+        cb.cntc_setsolverflags(ire, 1, 0, [200, 20, 30, 1], [1e-6])
+        cb.cntc_setmaterialparameters(ire, 1, 0, [0.28, 0.28, 82000.0, 82000.0])
+        cb.cntc_setpotcontact(ire, 1, 1, [mx, my, g["xl"], g["yl"], g["dx"], g["dy"]])
+        cb.cntc_setundeformeddistc(ire, 1, 1, g["prmudf"])
+        cb.cntc_setpenetration(ire, 1, pen)
+        ierr = cb.cntc_calculate(ire, 1)
+        assert ierr >= 0, (mx, my, ierr, cb.lib.last_error())
+        el = cb.cntc_getelementdivision(ire, 1).ravel()
+        pn, px, py = cb.cntc_gettractions(ire, 1)
+        ref = O.norm_case(mx, my, g["xl"], g["yl"], 0.1, 0.1, (82000.0, 82000.0), (0.28, 0.28), 1, g["prmudf"], 0, pen=pen,
+                          maxgs=200, maxin=20, eps=1e-6)
+        assert np.array_equal(el, ref["el"]), (mx, my)
+        if expect_ncon is not None:
+            assert int((el > 0).sum()) == expect_ncon
+        if (el > 0).any():
+            assert _rel(pn.ravel(), ref["pn"]) < 1e-9
+        else:
+            assert not pn.any() and cb.cntc_getcontactforces(ire, 1)[0] == 0.0
+        cb.cntc_finalize(ire)
+
+
+def test_interface_errors_and_short_buffers(cb):
+    """Error codes instead of aborts; getters honour the caller's array length (contact_addon.f90:5547, 5817)."""
+    import ctypes as C
+    L = cb.load_library()
+    ierr = C.c_int(0)
+    L.cntc_calculate(C.c_int(0), C.c_int(1), ierr)                      # invalid result element
+    assert ierr.value == -101
+    L.cntc_calculate(C.c_int(5), C.c_int(12), ierr)                     # invalid contact problem
+    assert ierr.value == cb.CNTC["err_icp"]
+    ire = 96
+    cb.cntc_initialize(ire, 3)
+    cb.cntc_setflags(ire, 1, [cb.CNTC["ic_tang"]], [0])
+    cb.cntc_setmaterialparameters(ire, 1, 1, [0.28, 0.28, 82000.0, 82000.0, 1.0, 1.0, 0.0, 0.0])     # visco-elastic: out of scope
+    cb.cntc_setpotcontact(ire, 1, 1, [5, 5, -0.25, -0.25, 0.1, 0.1])
+    cb.cntc_setundeformeddistc(ire, 1, 1, [0.02, 0.0, 0.02, 0.0, 0.0, 0.0])
+    cb.cntc_setpenetration(ire, 1, 0.001)
+    assert cb.cntc_calculate(ire, 1) == -99 and "M-digit" in cb.lib.last_error()
+    cb.cntc_setmaterialparameters(ire, 1, 0, [0.28, 0.28, 82000.0, 82000.0])
+    assert cb.cntc_calculate(ire, 1) >= 0
+    short = np.full(10, -7.0)
+    n = C.c_int(4)
+    L.cntc_getfielddata(C.c_int(ire), C.c_int(1), C.c_int(cb.CNTC["fld_pn"]), n, short.ctypes.data_as(C.POINTER(C.c_double)))
+    assert (short[4:] == -7.0).all() and (short[:4] >= 0.0).all()       # only lenarr entries written
+    cb.cntc_finalize(ire)
