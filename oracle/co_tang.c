@@ -192,7 +192,7 @@ static void tang_rhs(co_ctx *cx, int npot, int is_ssrol, const double *facdt, co
 /* solver selection and relaxation parameters of stang (m_stang.f90:144-223) */
 typedef struct { int solver; double omegah, omegas, dq; const double *facdt; int info;
                  co_inflcf *csv; co_leadedge *lg; const int *iel; int is_ssrol; } tang_opts;
-enum { SOLV_TANGCG = 0, SOLV_STDYGS = 1, SOLV_CNVXGS = 2 };
+enum { SOLV_TANGCG = 0, SOLV_STDYGS = 1, SOLV_CNVXGS = 2, SOLV_GDSTDY = 3 };
 
 /* one call of the tangential solver + relative forces */
 static void solve_once(co_ctx *cx, co_case *c, tang_opts *o, int npot, co_inflcf *cs, co_inflcf *ms, const double *wstot,
@@ -204,7 +204,16 @@ static void solve_once(co_ctx *cx, co_case *c, tang_opts *o, int npot, co_inflcf
     else {
         int k = 0;
         for (int i = 0; i < npot; i++) if (igs->el[i] >= CO_ADHES) k++;
-        if (o->solver == SOLV_STDYGS)
+        if (o->solver == SOLV_GDSTDY) {                    /* tang_solver, m_solvpt.f90:459-484 */
+            co_gdparams sp;
+            int lstagn = 0;
+            co_gdparams_set(c->gd, &sp);
+            *it = co_gdsteady(cx, igs->mx, igs->my, c->maxgs, c->eps, wstot, cs, mus, igs, ps, ss, &sp, err, &lstagn);
+            if (lstagn) {
+                c->gd_fallback++;
+                co_stdygs(cx, igs->mx, igs->my, wstot, cs, mus, igs, ps, ss, k, c->eps, c->maxgs, o->omegah, o->omegas, &o->info, it, err);
+            }
+        } else if (o->solver == SOLV_STDYGS)
             co_stdygs(cx, igs->mx, igs->my, wstot, cs, mus, igs, ps, ss, k, c->eps, c->maxgs, o->omegah, o->omegas, &o->info, it, err);
         else
             co_cnvxgs(cx, igs->mx, igs->my, o->is_ssrol, wstot, cs, o->csv, o->lg, mus, igs, ps, ss, k, o->iel, c->eps, c->maxgs,
@@ -311,14 +320,9 @@ static int stang(co_ctx *cx, co_case *c, int npot, co_inflcf *cs, co_inflcf *cv,
     {                                                                                      /* :129-223 */
         int icount = 0;
         for (int iy = 1; iy <= my; iy++) if (igs->el[1 + (iy - 1) * mx - 1] >= CO_ADHES) icount++;
-        if (is_ssrol) o.solver = (c->gausei == 5) ? -1 : (c->gausei != 2 ? SOLV_STDYGS : SOLV_CNVXGS);
+        if (is_ssrol) o.solver = (c->gausei == 5) ? SOLV_GDSTDY : (c->gausei != 2 ? SOLV_STDYGS : SOLV_CNVXGS);
         else o.solver = (c->gausei != 2) ? SOLV_TANGCG : SOLV_CNVXGS;
-        if (icount > 0 && (o.solver == SOLV_STDYGS || o.solver == -1)) o.solver = SOLV_CNVXGS;
-        if (o.solver == -1) {                              /* GDsteady is outside this restatement */
-            free(wsfix); free(mus); free(tmp); free(facdt); free(iel);
-            *itgs_out = 0;
-            return -99;
-        }
+        if (icount > 0 && (o.solver == SOLV_STDYGS || o.solver == SOLV_GDSTDY)) o.solver = SOLV_CNVXGS;
         if (c->gausei == 0 || c->gausei == 4 || c->gausei == 5) {
             if (k <= 25) { o.omegah = 1.0; o.omegas = 1.0; }
             else if (is_ssrol && o.solver == SOLV_CNVXGS) { o.omegah = 0.5; o.omegas = 0.5; }

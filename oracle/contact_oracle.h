@@ -186,7 +186,14 @@ typedef struct {
     int    ipotcn;                      /* -1 / -3: 3D Hertzian geometry (curvatures / semi-axes given); else grid as given */
     double hz_a1, hz_b1, hz_aa, hz_bb, hz_scale;
     int    itout;                       /* out: outer (Panagiotopoulos) iterations */
+    double gd[8];                       /* G = 5: fdecay, betath, kdowfb, d_ifc, d_lin, d_cns, d_slp, pow_s (as in the .inp record) */
+    int    gd_fallback;                 /* out: GDsteady stagnated, SteadyGS was used (m_solvpt.f90:474-484) */
 } co_case;
+/* parameters of GDsteady after solv_input (m_sinput.f90:649-680) */
+typedef struct { int gd_meth, kdown, kdowfb; double fdecay, betath, d_ifc, d_lin, d_cns, d_slp, pow_s; } co_gdparams;
+void   co_gdparams_set(const double gd[8], co_gdparams *sp);
+int    co_gdsteady(co_ctx *cx, int mx, int my, int maxgd, double eps, const double *ws, co_inflcf *cs, const double *mus,
+                   co_eldiv *igs, double *ps, double *ss, const co_gdparams *sp, double *err, int *lstagn);
 void   co_ellip_kebd(double mc, double *K, double *E, double *B, double *D);
 void   co_hertz3d(double e_star, int ipotcn, double *a1, double *b1, double *aa, double *bb, int ic_norm, double *pen,
                   double *fn, double *cp, double *rho);

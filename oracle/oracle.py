@@ -266,12 +266,14 @@ class Case(C.Structure):
                 ("nr_fx", C.c_double * 64), ("nr_fy", C.c_double * 64), ("n_prod", C.c_long),
                 ("iestim", C.c_int), ("el_in", c_int_p), ("ps_in", c_dbl_p), ("pv_in", c_dbl_p),
                 ("ipotcn", C.c_int), ("hz_a1", C.c_double), ("hz_b1", C.c_double), ("hz_aa", C.c_double),
-                ("hz_bb", C.c_double), ("hz_scale", C.c_double), ("itout", C.c_int)]
+                ("hz_bb", C.c_double), ("hz_scale", C.c_double), ("itout", C.c_int),
+                ("gd", C.c_double * 8), ("gd_fallback", C.c_int)]
 
 
 def contac(g, gg, poiss, tang=0, norm=0, force3=0, pen=0.0, fn=0.0, cksi=0.0, ceta=0.0, cphi=0.0, fxrel=0.0, fyrel=0.0,
            fstat=0.3, fkin=0.3, maxgs=999, maxin=20, maxnr=25, maxout=1, eps=1e-5, fullbox=False, nn=0, chi=0.0, dq=1.0,
-           facphi=0.0, gausei=0, omegah=0.9, omegas=0.9, iestim=0, el_in=None, ps_in=None, pv_in=None, hertz=None):
+           facphi=0.0, gausei=0, omegah=0.9, omegas=0.9, iestim=0, el_in=None, ps_in=None, pv_in=None, hertz=None,
+           gd=(1.0, 0.05, 1, 2.0, -1.0, 1.0, 2.6, 1.0)):
     """One module-3 case (T = 0/1/3) through the oracle's contac/panprc. g: dict mx,my,xl,yl,dx,dy,ibase,prmudf."""
     npot = g["mx"] * g["my"]
     prm = np.ascontiguousarray(g["prmudf"], dtype=np.float64)
@@ -285,6 +287,8 @@ def contac(g, gg, poiss, tang=0, norm=0, force3=0, pen=0.0, fn=0.0, cksi=0.0, ce
     c.maxgs, c.maxin, c.maxnr, c.maxout, c.eps, c.fullbox = maxgs, maxin, maxnr, maxout, eps, int(fullbox)
     c.chi, c.dq, c.facphi, c.gausei = chi, dq, facphi, gausei
     c.omegah, c.omegas = omegah, omegas
+    for i in range(8):
+        c.gd[i] = float(gd[i])
     keep = []
     if el_in is not None and ps_in is not None:
         e_ = np.ascontiguousarray(el_in, dtype=np.int32); p_ = np.ascontiguousarray(ps_in, dtype=np.float64)
@@ -307,4 +311,4 @@ def contac(g, gg, poiss, tang=0, norm=0, force3=0, pen=0.0, fn=0.0, cksi=0.0, ce
                 grid=dict(mx=c.mx, my=c.my, xl=c.xl, yl=c.yl, dx=c.dx, dy=c.dy), hz=dict(a1=c.hz_a1, b1=c.hz_b1, aa=c.hz_aa, bb=c.hz_bb),
                 itnorm=c.itnorm, ittang=c.ittang, itout=c.itout, itcg_norm=c.itcg_norm, itgs_tang=c.itgs_tang,
                 nr_itcg=list(c.nr_itcg[:n]), nr_cksi=list(c.nr_cksi[:n]), nr_ceta=list(c.nr_ceta[:n]), nr_fx=list(c.nr_fx[:n]),
-                nr_fy=list(c.nr_fy[:n]), n_prod=c.n_prod)
+                nr_fy=list(c.nr_fy[:n]), n_prod=c.n_prod, gd_fallback=c.gd_fallback)

@@ -183,3 +183,26 @@ def test_transient_rolling_converges_to_steady_state():
     assert abs(r["fx"] - rs["fx"]) < 2e-3 and abs(r["fy"] - rs["fy"]) < 2e-3
     assert abs(int((el == 2).sum()) - int((rs["el"] == 2).sum())) <= 2
     assert np.abs(ps[:2] - rs["ps"][:2]).max() < 0.03 * np.abs(rs["ps"][:2]).max()
+
+
+def test_gdsteady_converges_to_steadygs(mbench):
+    """perfc_test/tang_problm_1c.inp with the solver record of tang_problm_8c.inp:9 (G=5, GDsteady, gdsteady.f90).  No golden
+    file of the reference runs GDsteady ("parity unpinned" for its iteration count): the restatement is pinned by reaching
+    the SteadyGS solution of the same problem (golden nslp 1872) without the stagnation fall-back."""
+    kw = dict(tang=3, norm=0, force3=0, pen=mbench["pen"], cksi=0.0005, ceta=0.0, cphi=0.0003, fstat=0.3, fkin=0.3, maxgs=5000,
+              maxin=100, maxnr=30, maxout=1, eps=1e-7, nn=mbench["nn"], chi=0.0, dq=0.1)
+    r0 = O.contac(_mbench_grid(mbench), cases.STEEL["gg"], cases.STEEL["poiss"], gausei=0, **kw)
+    r5 = O.contac(_mbench_grid(mbench), cases.STEEL["gg"], cases.STEEL["poiss"], gausei=5,
+                  gd=(1.0, 0.05, 1, 2.0, -1.0, 1.0, 2.6, 1.0), **kw)
+    assert r5["ierror"] == 0 and r5["gd_fallback"] == 0 and r5["ittang"] == 1
+    assert int((r5["el"] == 2).sum()) == 1872 and (r5["el"] == r0["el"]).all()
+    assert 0 < r5["itgs_tang"] < 400
+    scale = np.abs(r0["ps"][:2]).max()
+    assert np.abs(r5["ps"][:2] - r0["ps"][:2]).max() < 1e-5 * scale
+    assert abs(r5["fx"] - r0["fx"]) < 1e-7 and abs(r5["fy"] - r0["fy"]) < 1e-7
+    # the other two search-direction variants (E_down(k), E_keep(f)) reach the same solution
+    for fdecay in (-2.0, 0.5):
+        rv = O.contac(_mbench_grid(mbench), cases.STEEL["gg"], cases.STEEL["poiss"], gausei=5,
+                      gd=(fdecay, 0.05, 1, 2.0, -1.0, 1.0, 2.6, 1.0), **kw)
+        assert rv["ierror"] == 0 and int((rv["el"] == 2).sum()) == 1872, fdecay
+        assert np.abs(rv["ps"][:2] - r0["ps"][:2]).max() < 1e-4 * scale, fdecay
