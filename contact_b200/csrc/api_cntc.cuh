@@ -55,6 +55,9 @@ struct Problem {
     // solver settings (solv_init, m_hierarch_data.f90:1722-1751)
     int maxgs = 999, maxin = 20, maxnr = 25, maxout = 1;
     double eps = 1e-5, omegah = 0.9, omegas = 1.0, dq_eff = 1.0;
+    // GDsteady (G=5), defaults of solv_init (m_hierarch_data.f90:1722-1751): fdecay, betath, d_ifc, d_lin, d_cns, d_slp, pow_s
+    double gd_fdecay = (double) 0.90f, gd_betath = (double) 0.10f, gd_difc = 1.0, gd_dlin = 1.0, gd_dcns = 1.0, gd_dslp = 1.0, gd_pows = (double) 0.90f;
+    int gd_meth = 1, gd_kdown = 3, gd_kdowfb = 1, gd_fallback = 0, gd_ntrial = 0;
     // results
     int ncase = 0, itnorm = 0, ittang = 0, itcg = 0, ncon = 0, nadh = 0, nslip = 0, status = 0, itout = 0;
     std::vector<int> el;
@@ -200,7 +203,7 @@ inline int check_scope(const Problem &p)
     if (p.tang == 2 && p.dq > p.dx * (1.0 + 1e-4)) { last_error() = "transient rolling (T=2) with DQ > DX needs the leading-edge equations, which the B200 path does not serve"; return CNTC_err_other; }
     if (p.tang != 0 && p.frclaw != 0) { last_error() = "L-digit: only Coulomb friction (L=0)"; return CNTC_err_other; }
     if (p.tang == 3 && p.gausei == 2 && fabs(p.chi) > 0.01) { last_error() = "ConvexGS in steady rolling: only CHI = 0 is served by the B200 path"; return CNTC_err_other; }
-    if (p.tang == 3 && p.gausei == 5) { last_error() = "G-digit: GDsteady (G=5) is not served by the B200 path yet (SteadyGS, G=0/3/4, is)"; return CNTC_err_other; }
+    if (p.tang == 3 && p.gausei == 5 && fabs(p.chi) > 0.01) { last_error() = "GDsteady: only CHI = 0 is served by the B200 path"; return CNTC_err_other; }
     if (p.tang == 3 && fabs(p.chi) > 0.01 && fabs(p.chi - 3.14159265358979323846) <= 0.01) { last_error() = "CHI = pi (rolling in -x) is not served by the B200 path yet"; return CNTC_err_other; }
     if (p.mater != 0) { last_error() = "M-digit: only the elastic half-space (M=0) is in the hot-path scope"; return CNTC_err_other; }
     if (p.gencr != 2 && p.gencr != 1) { last_error() = "C-digit: only piecewise-constant analytical coefficients (C=2)"; return CNTC_err_other; }
@@ -377,7 +380,7 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
         int rc = get_coefset(p.mx, p.my, p.dx, p.dy, p.mat, p.tang >= 2 ? 1 : 0, chi_e, dq_e, 0, &cs, whole);
         if (rc) { ierr[k] = rc; continue; }
         // grids beyond one CTA's shared memory go to the whole-GPU path, which serves T = 0 and T = 1 (TangCG)
-        if (!cs->hp.fits && p.tang == 3) { last_error() = "grid too large for the single-CTA SteadyGS solver (the whole-GPU path serves T=0 and T=1)"; ierr[k] = CNTC_err_discr; continue; }
+        if (!cs->hp.fits && p.tang == 3 && p.gausei != 5) { last_error() = "grid too large for the single-CTA SteadyGS solver (the whole-GPU path serves T=0 and T=1)"; ierr[k] = CNTC_err_discr; continue; }
         groups[cs].push_back(k);
     }
     for (auto &g : groups) {
@@ -408,7 +411,10 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
         if (!rc) rc = build_levels(cs, 0, any_tang);            // after the full-size transforms and preconditioners exist
         if (rc) { fail(rc); continue; }
         // device buffers: per case hs_n(1) hst(2) ps(3) ss(2) work(9) twork(24) pv(3) = 44 n doubles, el n ints
-        const size_t per = (size_t) 44 * npot;
+        // (+ 16 n of GDsteady work space when a case of the group asks for G = 5)
+        bool any_gd = false;
+        for (size_t k : ks) any_gd = any_gd || (probs[k]->tang == 3 && probs[k]->gausei == 5);
+        const size_t per = (size_t) (any_gd ? 60 : 44) * npot;
         double *d_buf = nullptr; int *d_el = nullptr, *d_next = nullptr; ContactCase *d_cases = nullptr;
         if (cudaMalloc(&d_buf, sizeof(double) * per * n) != cudaSuccess || cudaMalloc(&d_el, sizeof(int) * (size_t) n * npot) != cudaSuccess ||
             cudaMalloc(&d_cases, sizeof(ContactCase) * n) != cudaSuccess || cudaMalloc(&d_next, sizeof(int)) != cudaSuccess) {
@@ -453,6 +459,15 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
             if (is_roll) { c.cfv11 = cs.d_cf[SET_CSV] + 0 * nblk; c.cfv12 = cs.d_cf[SET_CSV] + 3 * nblk; c.cfv22 = cs.d_cf[SET_CSV] + 4 * nblk; }
             c.cf12 = cs.d_cf[SET_CS] + 3 * nblk; c.dq = dq_e; c.dx = p.dx; c.gausei = p.gausei; c.omegah = p.omegah; c.omegas = p.omegas;
             c.chatM11 = cs.d_chat[SET_MS][0][0]; c.chatM22 = cs.d_chat[SET_MS][1][1];
+            if (p.tang == 3 && p.gausei == 5) {                          // cntc_setsolverflags, contact_addon.f90:1220-1250
+                c.gwork = base + 44 * (size_t) npot;
+                GdParams &sp = c.gd;
+                sp.fdecay = p.gd_fdecay; sp.betath = p.gd_betath; sp.kdowfb = p.gd_kdowfb;
+                sp.d_ifc = std::max(0.01, p.gd_difc); sp.d_lin = p.gd_dlin; sp.d_cns = std::max(0.01, p.gd_dcns);
+                sp.d_slp = std::max(0.01, p.gd_dslp); sp.pow_s = std::max(0.01, std::min(10.0, p.gd_pows));
+                if (sp.d_lin * (sp.d_cns - sp.d_ifc) < 0.0) { sp.d_lin = 0.0; sp.d_cns = sp.d_ifc; }
+                sp.gd_meth = p.gd_meth; sp.kdown = p.gd_kdown;
+            }
             c.cf11 = cs.d_cf[SET_CS] + 0 * nblk; c.cf22 = cs.d_cf[SET_CS] + 4 * nblk;
             c.c11 = c00[0]; c.c22 = c00[1]; c.ga = cs.ga;
             // host inputs: hs_n, hst (set_tang_rhs, m_sdis.f90:498-583; shifts: dq = 1), ps
@@ -519,6 +534,7 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
                 p.pen = c.nrm.pen; p.fntrue = c.nrm.fntrue; p.itcg = c.nrm.itcg; p.itnorm = c.nrm.itnorm; p.ncon = c.nrm.ncon;
                 p.status = c.nrm.status; p.ittang = c.ittang; p.itgs = c.itgs; p.itout = c.itout; p.nadh = c.nadh; p.nslip = c.nslip;
                 p.nr_itcg.assign(c.nr_itcg, c.nr_itcg + std::min(c.nr_n, (int) CB_MAXNR_LOG));
+                p.gd_fallback = c.gd_fallback; p.gd_ntrial = c.gd_ntrial;
                 const double muscal = p.fstat;
                 double sx = 0, sy = 0, mz = 0;
                 for (int iy = 0; iy < p.my; iy++) for (int ix = 0; ix < p.mx; ix++) {
@@ -538,7 +554,7 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
                 } else { p.fcntc[0] = p.fcntc[1] = 0.0; p.mztrue = 0.0; }
                 p.fcntc[2] = p.fntrue;
                 p.solved = true;
-                if (c.tstatus & 1) { last_error() = "TANG: the case needs a solver that the B200 path does not serve (GDsteady, ConvexGS with DQ > DX, or a Gauss-Seidel solver on a grid beyond one CTA)"; ierr[ks[i]] = CNTC_err_other; }
+                if (c.tstatus & 1) { last_error() = "TANG: the case needs a solver that the B200 path does not serve (ConvexGS with DQ > DX, or a Gauss-Seidel solver -- also as the fall-back of a stagnating GDsteady -- on a grid beyond one CTA)"; ierr[ks[i]] = CNTC_err_other; }
                 else if (p.itnorm < 0 || (p.status & 1)) ierr[ks[i]] = CNTC_err_norm;
                 else if (p.ittang < 0) ierr[ks[i]] = CNTC_err_tang;
                 else ierr[ks[i]] = count_at_boundary(p);              // contact_addon.f90:3885-3891
@@ -646,6 +662,13 @@ void cntc_setsolverflags(int *ire, int *icp, int *gdigit, int *nints, int *ipara
         p->maxgs = std::max(1, iparam[0]); p->maxin = std::max(1, iparam[1]);
         p->maxnr = std::max(1, iparam[2]); p->maxout = std::max(1, iparam[3]);
         if (g == 2 || g == 3) { p->omegah = std::max(1e-20, rparam[1]); p->omegas = std::max(1e-20, rparam[2]); }   // contact_addon.f90:1203-1208
+        if (g == 5) {                                                                                                // :1220-1250
+            p->gd_fdecay = rparam[1]; p->gd_betath = rparam[2]; p->gd_kdowfb = iparam[4];
+            p->gd_difc = rparam[3]; p->gd_dlin = rparam[4]; p->gd_dcns = rparam[5]; p->gd_dslp = rparam[6]; p->gd_pows = rparam[7];
+            if (p->gd_fdecay >= 0.999) p->gd_meth = 1;                                   // E_trl
+            else if (p->gd_fdecay <= 0.001) { p->gd_meth = 2; p->gd_kdown = std::max(1, (int) nearbyint(-p->gd_fdecay)); }   // E_down(k)
+            else p->gd_meth = 3;                                                         // E_keep(f)
+        }
     }
 }
 

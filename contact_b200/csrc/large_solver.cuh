@@ -511,6 +511,11 @@ struct GridCtx {
     __device__ __forceinline__ size_t first() const { return (size_t) blockIdx.x * blockDim.x + threadIdx.x; }
     __device__ __forceinline__ size_t stride() const { return (size_t) gridDim.x * blockDim.x; }
     __device__ __forceinline__ bool leader() const { return blockIdx.x == 0 && threadIdx.x == 0; }
+    // rows interleaved over the CTAs so that a few hundred rows spread over all SMs
+    __device__ __forceinline__ size_t row_first() const { return (size_t) threadIdx.x * gridDim.x + blockIdx.x; }
+    __device__ __forceinline__ size_t row_stride() const { return (size_t) gridDim.x * blockDim.x; }
+    __device__ __forceinline__ size_t warp_first() const { return (size_t) (threadIdx.x >> 5) * gridDim.x + blockIdx.x; }
+    __device__ __forceinline__ size_t warp_stride() const { return (size_t) gridDim.x * (blockDim.x >> 5); }
     __device__ __forceinline__ void sync() const { grid.sync(); }
     template <int N> __device__ __forceinline__ void sum(double (&v)[N]) const { grid_sum<N>(v, redp, X.gpart, phase, grid); }
     __device__ __forceinline__ void conv(const double *p, const cd *chat, double *u, const int *el, int mask_mode, int add) const

@@ -14,6 +14,9 @@ namespace cb200 {
 
 #define CB_MAXNR_LOG 32
 
+// parameters of GDsteady (solv_input, m_sinput.f90:649-680; cntc_setsolverflags G=5, contact_addon.f90:1220-1250)
+struct GdParams { int gd_meth, kdown, kdowfb; double fdecay, betath, d_ifc, d_lin, d_cns, d_slp, pow_s; };
+
 struct ContactCase {
     NormCase nrm;                   // normal problem (hs normal, el, pn = ps + 2n, work, ...)
     // tangential inputs
@@ -35,7 +38,10 @@ struct ContactCase {
     double omegah, omegas;          // relaxation factors of the Gauss-Seidel solvers (set by stang)
     const cd *chatSV[2][2];         // transformed csv = cs - cv blocks (steady rolling with ConvexGS)
     const double *cfv11, *cfv12, *cfv22;   // spatial blocks of csv
-    int solver_eff;                 // 0 TangCG, 1 SteadyGS, 2 ConvexGS (set by stang, m_stang.f90:144-191)
+    int solver_eff;                 // 0 TangCG, 1 SteadyGS, 2 ConvexGS, 3 GDsteady (set by stang, m_stang.f90:144-191)
+    GdParams gd;                    // G = 5
+    double *gwork;                  // 16 n doubles of GDsteady work space (null unless G = 5)
+    int gd_fallback, gd_ntrial;     // out: GDsteady stagnated -> SteadyGS used (m_solvpt.f90:474-484); line-search trials
     // outputs
     int ittang, itgs, itout, nr_n;
     int nr_itcg[CB_MAXNR_LOG];
@@ -70,6 +76,11 @@ struct BlockCtx {
     __device__ __forceinline__ size_t first() const { return threadIdx.x; }
     __device__ __forceinline__ size_t stride() const { return blockDim.x; }
     __device__ __forceinline__ bool leader() const { return threadIdx.x == 0; }
+    // loops over grid rows: one thread per row / one warp per row
+    __device__ __forceinline__ size_t row_first() const { return threadIdx.x; }
+    __device__ __forceinline__ size_t row_stride() const { return blockDim.x; }
+    __device__ __forceinline__ size_t warp_first() const { return threadIdx.x >> 5; }
+    __device__ __forceinline__ size_t warp_stride() const { return blockDim.x >> 5; }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
     template <int N> __device__ __forceinline__ void sum(double (&v)[N]) const { block_sum<N>(v, sm.red); }
     __device__ __forceinline__ void conv(const double *p, const cd *chat, double *u, const int *el, int mask_mode, int add) const
@@ -109,6 +120,10 @@ __device__ __forceinline__ void count_el(const X &x, const int *el, int n, int &
     x.template sum<2>(c);
     nadh = (int) c[0]; nslip = (int) c[1];
 }
+
+}  // namespace cb200
+#include "gdsteady_solver.cuh"
+namespace cb200 {
 
 // m_solvpt.f90:1841-2442 (elastic material).  ws: [2][n] right-hand side; mu = fstat (uniform).
 template <class X>
@@ -301,7 +316,17 @@ __device__ int solve_once_dev(const X &x, ContactCase &c, const double *wstot, d
 {
     const int n = x.n();
     int info = 0;
-    if (c.solver_eff != 0) {                                                   // SteadyGS / ConvexGS
+    bool use_gs = (c.solver_eff == 1 || c.solver_eff == 2);
+    if (c.solver_eff == 3) {                                                   // GDsteady, tang_solver m_solvpt.f90:459-484
+        int lstagn = 0;
+        it = gdsteady_dev(x, c, wstot, c.nrm.maxgs, c.nrm.eps, err, lstagn, nprod);
+        if (lstagn) {                                                          // stagnation: SteadyGS takes over
+            if (x.leader()) { c.gd_fallback++; if (!X::kBlock) c.tstatus |= 1; }
+            x.sync();
+            if (X::kBlock) use_gs = true; else info = 3;
+        }
+    }
+    if (use_gs) {                                                              // SteadyGS / ConvexGS
         if constexpr (X::kBlock) {
         int nadh, nslip;
         count_el(x, c.nrm.el, n, nadh, nslip);
@@ -321,7 +346,7 @@ __device__ int solve_once_dev(const X &x, ContactCase &c, const double *wstot, d
         else if (ncon <= 12 * CB_THREADS) info = stdygs_dev<12>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
         else info = stdygs_dev<22>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
         }
-    } else
+    } else if (c.solver_eff == 0)
         tangcg_dev(x, c, wstot, c.nrm.maxgs, c.nrm.eps, it, err, nprod);
     double s[2] = { 0.0, 0.0 };
     for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) { s[0] += c.ps[i]; s[1] += c.ps[n + i]; }
@@ -432,10 +457,12 @@ __device__ int stang_dev(const X &x, ContactCase &c, double fntrue, int &itgs_to
         for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) if (el[i] >= 1) { cnt[0] += 1.0; if (i % x.plan().mx == 0) cnt[1] += 1.0; }
         x.template sum<2>(cnt);
         const int k = (int) cnt[0];
-        int solver = ssrol ? (c.gausei != 2 ? 1 : 2) : (c.gausei != 2 ? 0 : 2);
-        if (cnt[1] > 0.0 && solver == 1) solver = 2;                           // no exterior elements at the trailing edge
-        // GDsteady (G = 5) is not served; ConvexGS with dq > dx needs the leading-edge equations (ii2j > 0), not served
-        bool refuse = (ssrol && c.gausei == 5) || (solver == 2 && ssrol && c.dq > c.dx * (1.0 + 1e-4)) || (solver != 0 && !X::kBlock);
+        int solver = ssrol ? (c.gausei == 5 ? 3 : (c.gausei != 2 ? 1 : 2)) : (c.gausei != 2 ? 0 : 2);
+        if (cnt[1] > 0.0 && (solver == 1 || solver == 3)) solver = 2;          // no exterior elements at the trailing edge
+        // ConvexGS with dq > dx needs the leading-edge equations (ii2j > 0), not served; the Gauss-Seidel solvers exist on
+        // the one-CTA-per-case path only
+        bool refuse = (solver == 2 && ssrol && c.dq > c.dx * (1.0 + 1e-4)) || ((solver == 1 || solver == 2) && !X::kBlock) ||
+                      (solver == 3 && c.gwork == nullptr);
         if (refuse) { if (x.leader()) c.tstatus |= 1; x.sync(); itgs_tot = 0; return -1; }
         double oh = c.omegah, os = c.omegas;
         if (c.gausei == 0 || c.gausei == 4 || c.gausei == 5) {
@@ -451,11 +478,11 @@ __device__ int stang_dev(const X &x, ContactCase &c, double fntrue, int &itgs_to
         x.sync();
         if (x.leader()) { c.omegah = oh; c.omegas = os; c.solver_eff = solver; }
         x.sync();
-        if constexpr (X::kBlock) if (ssrol) {
+        if (ssrol) {
             facdt = c.twork;
-            // sxbnd (m_leadedge.f90:92-332): the leading edge sits 2 dx (SteadyGS) or 1 dx (ConvexGS) beyond the last
-            // interior element
-            sxbnd_facdt_dev(x.plan().mx, x.plan().my, el, c.dx, c.dq, solver == 1 ? 2.0 : 1.0, facdt);
+            // sxbnd (m_leadedge.f90:92-332): the leading edge sits 2 dx (SteadyGS) or 1 dx (ConvexGS, GDsteady) beyond the
+            // last interior element
+            sxbnd_facdt_x(x, x.plan().mx, x.plan().my, el, c.dx, c.dq, solver == 1 ? 2.0 : 1.0, facdt);
         }
     }
     // stang_rhs (:749-951): wsfix = -facdt hs_t + A_tn pn - A'_tn p'n - A'_tt p'_t on C; shifts: facdt = 1, previous

@@ -498,14 +498,96 @@ def test_convexgs_shift(cb, O):
     cb.cntc_finalize(ire)
 
 
-def test_gdsteady_is_refused(cb):
-    """G=5 (GDsteady) is outside what this path serves: refused loudly, never answered by another solver."""
-    g = dict(mx=12, my=9, xl=-0.6, yl=-0.45, dx=0.1, dy=0.1, ibase=1, prmudf=[0.004, 0.0, 0.004, 0.0, 0.0, 0.0])
-    ire = 66
-    _setup_rolling(cb, ire, g, cases.STEEL["gg"], cases.STEEL["poiss"], pen=0.005, eps=1e-5)
-    cb.cntc_setsolverflags(ire, 1, 5, [1000, 100, 30, 1, 1], [1e-5, 1.0, 0.05, 2.0, -1.0, 1.0, 2.6, 1.0])
-    cb.cntc_setcreepages(ire, 1, 0.001, 0.0, 0.0)
-    assert cb.cntc_calculate(ire, 1) == -99 and "GDsteady" in cb.lib.last_error()
+GD_8C = (1.0, 0.05, 1, 2.0, -1.0, 1.0, 2.6, 1.0)        # perfc_test/tang_problm_8c.inp:9: fdecay betath kdowfb d_ifc d_lin d_cns d_slp pow_s
+
+
+def _gd_flags(cb, ire, icp, gd, maxgs=5000, eps=1e-7):
+    cb.cntc_setsolverflags(ire, icp, 5, [maxgs, 100, 30, 1, int(gd[2])], [eps, gd[0], gd[1], gd[3], gd[4], gd[5], gd[6], gd[7]])
+
+
+@pytest.mark.parametrize("fdecay", [1.0, -2.0, 0.5])
+def test_gdsteady_mbench_1c(cb, O, mbench, fdecay):
+    """perfc_test/tang_problm_1c.inp with the solver record of tang_problm_8c.inp:9 (T=3, G=5: GDsteady, gdsteady.f90) and
+    its two other search-direction variants (E_down(2), E_keep(0.5)) on the one-CTA-per-case path: element division
+    bit-exact against the oracle (golden nslp 1872 of the SteadyGS run), tractions to the solver's accuracy, the same
+    number of iterations up to the rounding sensitivity of the line search."""
+    g = dict(mx=71, my=81, xl=-3.55, yl=-6.15, dx=0.1, dy=0.1, ibase=2, prmudf=np.array(mbench["prmudf"]))
+    gd = (fdecay,) + GD_8C[1:]
+    ire, icp = 66, 1
+    _setup_rolling(cb, ire, g, cases.STEEL["gg"], cases.STEEL["poiss"], pen=mbench["pen"])
+    _gd_flags(cb, ire, icp, gd)
+    cb.cntc_setrollingstepsize(ire, icp, 0.0, 0.1)
+    cb.cntc_setcreepages(ire, icp, 0.0005, 0.0, 0.0003)
+    ierr = cb.cntc_calculate(ire, icp)
+    assert ierr == 0, (ierr, cb.lib.last_error())
+    ref = O.contac(g, cases.STEEL["gg"], cases.STEEL["poiss"], tang=3, norm=0, force3=0, pen=mbench["pen"], cksi=0.0005,
+                   ceta=0.0, cphi=0.0003, fstat=0.3, fkin=0.3, maxgs=5000, maxin=100, maxnr=30, maxout=1, eps=1e-7,
+                   nn=mbench["nn"], chi=0.0, dq=0.1, gausei=5, gd=gd)
+    assert ref["ierror"] == 0 and ref["gd_fallback"] == 0
+    its = cb.lowlevel.get_iterations(ire, icp)
+    el = cb.cntc_getelementdivision(ire, icp).ravel()
+    assert int((el == 2).sum()) == 1872 and int((el >= 1).sum()) == 3148
+    assert np.array_equal(el, ref["el"])
+    assert abs(its["itgs"] - ref["itgs_tang"]) <= max(3, ref["itgs_tang"] // 20), (its, ref["itgs_tang"])
+    pn, px, py = cb.cntc_gettractions(ire, icp)
+    s = np.abs(ref["ps"][:2]).max()
+    assert np.abs(px.ravel() - ref["ps"][0]).max() < 2e-6 * s and np.abs(py.ravel() - ref["ps"][1]).max() < 2e-6 * s
+    fn, tx, ty, mz = cb.cntc_getcontactforces(ire, icp)
+    assert abs(tx / (0.3 * fn) - ref["fx"]) < 1e-7 and abs(ty / (0.3 * fn) - ref["fy"]) < 1e-7
+    cb.cntc_finalize(ire)
+
+
+def test_gdsteady_large_grid_2c(cb, O, mbench):
+    """perfc_test/tang_problm_2c.inp (143x161, T=3, G=5) does not fit one CTA: the same GDsteady text runs on the whole-GPU
+    path (three-phase products, grid-wide reductions, one warp per grid row for the integration along the rolling
+    direction).  Element division against the oracle, tractions to the solver's accuracy."""
+    g = dict(mx=143, my=161, xl=-3.55, yl=-6.15, dx=0.05, dy=0.05, ibase=2, prmudf=np.array(mbench["prmudf"]))
+    ire, icp = 67, 1
+    _setup_rolling(cb, ire, g, cases.STEEL["gg"], cases.STEEL["poiss"], pen=mbench["pen"])
+    _gd_flags(cb, ire, icp, GD_8C)
+    cb.cntc_setrollingstepsize(ire, icp, 0.0, 0.05)
+    cb.cntc_setcreepages(ire, icp, 0.0005, 0.0, 0.0003)
+    ierr = cb.cntc_calculate(ire, icp)
+    assert ierr == 0, (ierr, cb.lib.last_error())
+    ref = O.contac(g, cases.STEEL["gg"], cases.STEEL["poiss"], tang=3, norm=0, force3=0, pen=mbench["pen"], cksi=0.0005,
+                   ceta=0.0, cphi=0.0003, fstat=0.3, fkin=0.3, maxgs=5000, maxin=100, maxnr=30, maxout=1, eps=1e-7,
+                   nn=mbench["nn"], chi=0.0, dq=0.05, gausei=5, gd=GD_8C)
+    assert ref["ierror"] == 0 and ref["gd_fallback"] == 0
+    its = cb.lowlevel.get_iterations(ire, icp)
+    el = cb.cntc_getelementdivision(ire, icp).ravel()
+    assert int((el >= 1).sum()) == 12902                                  # perfc_test/get_times.ref_out:8
+    ndiff = int((el != ref["el"]).sum())
+    assert ndiff == 0, (ndiff, its, ref["itgs_tang"])
+    assert abs(its["itgs"] - ref["itgs_tang"]) <= max(3, ref["itgs_tang"] // 20), (its, ref["itgs_tang"])
+    pn, px, py = cb.cntc_gettractions(ire, icp)
+    s = np.abs(ref["ps"][:2]).max()
+    assert np.abs(px.ravel() - ref["ps"][0]).max() < 2e-6 * s and np.abs(py.ravel() - ref["ps"][1]).max() < 2e-6 * s
+    cb.cntc_finalize(ire)
+
+
+def test_gdsteady_prescribed_force_small(cb, O):
+    """GDsteady inside the Newton-Raphson loop on CKSI (F=1) on a small quadratic gap, default iteration constants of
+    cntc_setsolverflags G=5; against the oracle."""
+    g = dict(mx=34, my=27, xl=-3.4, yl=-2.7, dx=0.2, dy=0.2, ibase=1, prmudf=[0.004, 0.0, 0.006, 0.0, 0.0, 0.0])
+    gg, poiss = cases.STEEL["gg"], cases.STEEL["poiss"]
+    ire, icp = 68, 1
+    _setup_rolling(cb, ire, g, gg, poiss, fn=9.0e3, fstat=0.25, maxgs=500, maxin=50, maxnr=30, maxout=1, eps=1e-6, force=1)
+    cb.cntc_setsolverflags(ire, icp, 5, [500, 50, 30, 1, 1], [1e-6] + [GD_8C[0], GD_8C[1]] + list(GD_8C[3:]))
+    cb.cntc_setrollingstepsize(ire, icp, 0.0, 0.2)
+    cb.cntc_setcreepages(ire, icp, 0.0, 0.0004, 0.0002)
+    cb.cntc_settangentialforces(ire, icp, -0.6, 0.0)
+    ierr = cb.cntc_calculate(ire, icp)
+    assert ierr == 0, (ierr, cb.lib.last_error())
+    ref = O.contac(g, gg, poiss, tang=3, norm=1, force3=1, fn=9.0e3, fxrel=-0.6, ceta=0.0004, cphi=0.0002, fstat=0.25,
+                   fkin=0.25, maxgs=500, maxin=50, maxnr=30, maxout=1, eps=1e-6, chi=0.0, dq=0.2, gausei=5, gd=GD_8C)
+    assert ref["ierror"] == 0
+    el = cb.cntc_getelementdivision(ire, icp).ravel()
+    assert np.array_equal(el, ref["el"])
+    pn, px, py = cb.cntc_gettractions(ire, icp)
+    s = np.abs(ref["ps"][:2]).max()
+    assert np.abs(px.ravel() - ref["ps"][0]).max() < 1e-4 * s and np.abs(py.ravel() - ref["ps"][1]).max() < 1e-4 * s
+    cksi = cb.cntc_getcreepages(ire, icp)[0]
+    assert abs(cksi - ref["cksi"]) < 1e-4 * abs(ref["cksi"])
     cb.cntc_finalize(ire)
 
 
