@@ -150,6 +150,50 @@ def spence71_leg(cb):
             "golden": "perfc_test/get_times.ref_out:76-79: ncon 3657, nout 511, 30.7 s + 22.0 s subsurface (2016 host)"}
 
 
+def gdsteady_leg(cb):
+    """BASELINE config 3, perfc_test/tang_problm_8c.inp: 575x647 = 372 025 elements, PEN prescribed, T=3, G=5 (GDsteady with
+    the solver record of line 9: E_trl, betath 0.05, kdowfb 1, d_ifc 2, d_lin -1, d_cns 1, d_slp 2.6, pow_s 1), MAXGS 5000,
+    EPS 1e-7, through the cntc_* C-ABI on the whole-GPU path; the 287x323 case (4c) beside it.  Oracle results from
+    tests/golden/gdsteady_mbench.json (the oracle needs minutes on these grids)."""
+    import hashlib
+    fx_path = os.path.join(ROOT, "tests", "golden", "gdsteady_mbench.json")
+    fx = json.load(open(fx_path)) if os.path.exists(fx_path) else {}
+    out = {}
+    for name, (mx, my, dx) in (("tang_problm_4c", (287, 323, 0.025)), ("tang_problm_8c", (575, 647, 0.0125))):
+        g = mbench_grid(mx, my, dx)
+        ire = 901
+        best = None
+        for rep in range(2):
+            cb.cntc_initialize(ire, 3)
+            cb.cntc_setflags(ire, 1, [cb.CNTC["ic_tang"], cb.CNTC["ic_force"], cb.CNTC["ic_iestim"]], [3, 0, 0])
+            cb.cntc_setsolverflags(ire, 1, 5, [5000, 100, 30, 1, 1], [1e-7, 1.0, 0.05, 2.0, -1.0, 1.0, 2.6, 1.0])
+            cb.cntc_setmaterialparameters(ire, 1, 0, [0.28, 0.28, 82000.0, 82000.0])
+            cb.cntc_setfrictionmethod(ire, 1, 0, [0.3, 0.3])
+            cb.cntc_setpotcontact(ire, 1, 1, [g["mx"], g["my"], g["xl"], g["yl"], g["dx"], g["dy"]])
+            cb.cntc_setundeformeddistc(ire, 1, 2, g["prmudf"])
+            cb.cntc_setpenetration(ire, 1, g["pen"])
+            cb.cntc_setrollingstepsize(ire, 1, 0.0, dx)
+            cb.cntc_setcreepages(ire, 1, 0.0005, 0.0, 0.0003)
+            t0 = time.perf_counter()
+            ierr = cb.cntc_calculate(ire, 1)
+            wall = time.perf_counter() - t0
+            its = cb.lowlevel.get_iterations(ire, 1)
+            el = cb.cntc_getelementdivision(ire, 1).ravel().astype(np.int8)
+            r = {"ierror": int(ierr), "wall_s": wall, "solver_kernel_ms": cb.lowlevel.snorm_kernel_ms(), "itgd": its["itgs"],
+                 "linesearch_trials": its["gd_trials"], "fallback_to_steadygs": its["gd_fallback"], "ncon": int((el >= 1).sum()),
+                 "nadh": int((el == 1).sum()), "nslip": int((el == 2).sum())}
+            ref = fx.get(name[-2:])
+            if ref:
+                r["oracle"] = {"itgd": ref["itgs"], "nslip": ref["nslip"], "seconds_1core_here": ref["oracle_seconds"],
+                               "element_division_identical": hashlib.sha1(el.tobytes()).hexdigest() == ref["el_sha1"]}
+            cb.cntc_finalize(ire)
+            if best is None or r["wall_s"] < best["wall_s"]:
+                best = r
+        out[name] = best
+    out["note"] = "T=3, G=5 (GDsteady), one case on the whole GPU: FFT products in three grid-wide phases, one warp per grid row for the integration along the rolling direction, line search on device"
+    return out
+
+
 def large_grid_leg(cb, torch):
     """575x647 grid of perfc_test/norm_problm_8p.inp / tang_problm_8c.inp: stand-alone 1x1 products (three grid-wide
     phases over the L2-resident spectrum) and the whole NORM solve in one cooperative launch."""
@@ -319,6 +363,7 @@ def run_gpu(args):
     roll = rolling_sweep_leg(cb, nroll, (rank * nroll) % (4096 - nroll)) if not args.skip_extra else None
     large = large_grid_leg(cb, torch) if (rank == 0 and not args.skip_extra) else None
     sp71 = spence71_leg(cb) if (rank == 0 and not args.skip_extra) else None
+    gdl = gdsteady_leg(cb) if (rank == 0 and not args.skip_extra) else None
 
     # ---- end-to-end leg (host buffers through the C-ABI) ----
     for _ in range(max(1, min(args.warmup, 2))):
@@ -401,6 +446,8 @@ def run_gpu(args):
             out["large_grid"] = large
         if sp71:
             out["spence71_inp"] = sp71
+        if gdl:
+            out["gdsteady_large"] = gdl
         if args.cpu_seconds > 0:
             out["cpu_baseline"] = cpu_baseline(args.cpu_seconds, threads=1)
         print(json.dumps(out))

@@ -813,6 +813,7 @@ int cb200_get_iterations(int ire, int icp, int *out, int lenarr, int *nr_itcg)
     int e; Problem *p = activate(ire, icp, &e);
     if (!p) return e;
     out[0] = p->itnorm; out[1] = p->itcg; out[2] = p->ittang; out[3] = p->itgs; out[4] = p->ncon; out[5] = (int) p->nr_itcg.size(); out[6] = p->itout;
+    out[7] = p->gd_fallback > 0 ? -p->gd_ntrial - 1 : p->gd_ntrial;
     for (int i = 0; i < lenarr && i < (int) p->nr_itcg.size(); i++) nr_itcg[i] = p->nr_itcg[i];
     return 0;
 }

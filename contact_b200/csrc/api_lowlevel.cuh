@@ -292,6 +292,14 @@ int cb200_steady_prof(unsigned long long *out, int reset)
     if (reset) { unsigned long long z[8] = { 0 }; CB_CUDA(cudaMemcpyToSymbol(g_steady_prof, z, sizeof(z))); }
     return 0;
 }
+int cb200_gd_prof(unsigned long long *out, int reset)
+{   // cycle counters of GDsteady (leader thread of every solver call) since the last reset (see gdsteady_solver.cuh)
+    int rc = engine_init();
+    if (rc) return rc;
+    CB_CUDA(cudaMemcpyFromSymbol(out, g_gd_prof, sizeof(unsigned long long) * 8));
+    if (reset) { unsigned long long z[8] = { 0 }; CB_CUDA(cudaMemcpyToSymbol(g_gd_prof, z, sizeof(z))); }
+    return 0;
+}
 int cb200_num_sms(void) { int rc = engine_init(); return rc ? rc : engine().num_sms; }
 int cb200_opt_fft_size(int n) { return opt_fft_size(n); }
 

@@ -17,6 +17,13 @@
 
 namespace cb200 {
 
+// cycle counters of GDsteady, added by the leader thread of every solver call (development aid, cb200_gd_prof):
+// [0] iterations, [1] cycles in the products A dv / A dp, [2] search direction, [3] line search: integration along the
+// rows, [4] line search: element pass + reduction + bracketing, [5] step, active set, diagonal scaling, residual,
+// [6] line-search trials, [7] total cycles of the solver calls
+__device__ unsigned long long g_gd_prof[8];
+#define GD_TICK(slot) do { if (x.leader()) { const long long t_ = clock64(); prof[slot] += (unsigned long long) (t_ - tprev); tprev = t_; } } while (0)
+
 __device__ __forceinline__ double gd_wrap_pi(double e)
 {
     const double pi = 3.14159265358979323846;
@@ -92,17 +99,61 @@ __device__ void gd_apply_trcbnd(const X &x, int mx, int my, const int *el, const
     x.sync();
 }
 
-// project_searchdir (:639-803): dv in/out, v out.  imeth 1: E_trl, 2: E_down(kdown) (needs the scratch copy of dv),
-// 3: E_keep(fdecay).  One thread per row (once per iteration).
+// project_searchdir (:639-803): dv in/out, v out.  imeth 1: E_trl, 3: E_keep(fdecay): one warp per row, like
+// gd_apply_trcbnd; imeth 2: E_down(kdown), the fall-back direction after a small step, looks kdown elements ahead in a
+// scratch copy of dv that it modifies on the way: one thread per row.
 template <class X>
 __device__ void gd_project_searchdir(const X &x, int mx, int my, const int *el, const double *g, int imeth, int kdown, double fdecay,
                                      const double *nn, double *dv, double *v, double *scr, double fac_v)
 {
     const int n = mx * my;
-    if (imeth == 2) {
-        for (size_t i = x.first(); i < (size_t) (2 * n); i += x.stride()) scr[i] = dv[i];
+    if (imeth != 2) {
+        const int lane = threadIdx.x & 31;
+        for (int iy = (int) x.warp_first(); iy < my; iy += (int) x.warp_stride()) {
+            const int i0 = iy * mx;
+            double vrx = 0.0, vry = 0.0;                      // v of the element to the right (uniform over the warp)
+            for (int base = ((mx - 1) >> 5) << 5; base >= 0; base -= 32) {
+                const int ix = base + lane, ii = i0 + ix;
+                const bool have = ix < mx;
+                int e = 0; double dx_ = 0.0, dy_ = 0.0, tx = 0.0, ty = 0.0, lim = 0.0;
+                if (have) {
+                    e = el[ii]; dx_ = dv[ii]; dy_ = dv[n + ii];
+                    if (e == EL_SLIP) { tx = -nn[n + ii]; ty = nn[ii]; lim = fac_v * g[ii]; }
+                }
+                double myvx = 0.0, myvy = 0.0, mydx = dx_, mydy = dy_;
+                const int kmax = min(31, mx - 1 - base);
+                for (int k = kmax; k >= 0; k--) {
+                    const int ek = __shfl_sync(0xffffffffu, e, k);
+                    const double dkx = shfl_d(dx_, k), dky = shfl_d(dy_, k);
+                    double vx, vy;
+                    if (base + k == mx - 1) { vx = 0.0; vy = 0.0; }
+                    else if (ek == EL_ADHES) {
+                        if (imeth == 1) { vx = vrx + dkx; vy = vry + dky; }
+                        else {
+                            vx = fdecay * vrx + dkx; vy = fdecay * vry + dky;
+                            if (lane == k) { mydx = vx - vrx; mydy = vy - vry; }
+                        }
+                    } else if (ek == EL_SLIP) {
+                        const double tkx = shfl_d(tx, k), tky = shfl_d(ty, k), lk = shfl_d(lim, k);
+                        double vt = tkx * dkx + tky * dky;
+                        vt = copysign(1.0, vt) * fmin(fabs(vt), lk);
+                        vx = tkx * vt; vy = tky * vt;
+                        if (lane == k) { mydx = vx - vrx; mydy = vy - vry; }
+                    } else {
+                        vx = 0.0; vy = 0.0;
+                        if (lane == k) { mydx = -vrx; mydy = -vry; }
+                    }
+                    if (lane == k) { myvx = vx; myvy = vy; }
+                    vrx = vx; vry = vy;
+                }
+                if (have) { v[ii] = myvx; v[n + ii] = myvy; dv[ii] = mydx; dv[n + ii] = mydy; }
+            }
+        }
         x.sync();
+        return;
     }
+    for (size_t i = x.first(); i < (size_t) (2 * n); i += x.stride()) scr[i] = dv[i];
+    x.sync();
     for (int iy = (int) x.row_first(); iy < my; iy += (int) x.row_stride()) {
         const int i0 = iy * mx;
         double *dxin = scr + i0, *dyin = scr + n + i0;
@@ -114,27 +165,19 @@ __device__ void gd_project_searchdir(const X &x, int mx, int my, const int *el, 
             const int e = el[ii];
             double vx, vy;
             if (e == EL_ADHES) {
-                if (imeth == 1) { vx = vrx + dv[ii]; vy = vry + dv[n + ii]; }
-                else if (imeth == 2) {
-                    if (ix + kdown <= mx - 1) { vx = vrx + dxin[ix] - dxin[ix + kdown]; vy = vry + dyin[ix] - dyin[ix + kdown]; }
-                    else { vx = vrx + dxin[ix]; vy = vry + dyin[ix]; }
-                    dv[ii] = vx - vrx; dv[n + ii] = vy - vry;
-                } else {
-                    vx = fdecay * vrx + dv[ii]; vy = fdecay * vry + dv[n + ii];
-                    dv[ii] = vx - vrx; dv[n + ii] = vy - vry;
-                }
+                if (ix + kdown <= mx - 1) { vx = vrx + dxin[ix] - dxin[ix + kdown]; vy = vry + dyin[ix] - dyin[ix + kdown]; }
+                else { vx = vrx + dxin[ix]; vy = vry + dyin[ix]; }
             } else if (e == EL_SLIP) {
                 const double tx = -nn[n + ii], ty = nn[ii];
-                double vt = (imeth == 2) ? tx * dxin[ix] + ty * dyin[ix] : tx * dv[ii] + ty * dv[n + ii];
+                double vt = tx * dxin[ix] + ty * dyin[ix];
                 vt = copysign(1.0, vt) * fmin(fabs(vt), fac_v * g[ii]);
                 vx = tx * vt; vy = ty * vt;
-                dv[ii] = vx - vrx; dv[n + ii] = vy - vry;
-                if (imeth == 2) for (int k = 1; k <= kdown; k++) if (ix + k <= mx - 1) { dxin[ix + k] = 0.0; dyin[ix + k] = 0.0; }
+                for (int k = 1; k <= kdown; k++) if (ix + k <= mx - 1) { dxin[ix + k] = 0.0; dyin[ix + k] = 0.0; }
             } else {
                 vx = 0.0; vy = 0.0;
-                dv[ii] = -vrx; dv[n + ii] = -vry;
-                if (imeth == 2) for (int k = 1; k <= kdown; k++) if (ix + k <= mx - 1) { dxin[ix + k] = 0.0; dyin[ix + k] = 0.0; }
+                for (int k = 1; k <= kdown; k++) if (ix + k <= mx - 1) { dxin[ix + k] = 0.0; dyin[ix + k] = 0.0; }
             }
+            dv[ii] = vx - vrx; dv[n + ii] = vy - vry;
             v[ii] = vx; v[n + ii] = vy;
             vrx = vx; vry = vy;
         }
@@ -229,6 +272,9 @@ __device__ __noinline__ int gdsteady_dev(const X &x, ContactCase &c, const doubl
     const double facnel = (double) sqrtf(__fdiv_rn((float) n, (float) (nadh + nslip)));
     int itgd = 0, it_fb = -99;
     bool lchanged = false;
+    unsigned long long prof[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    long long tprev = clock64();
+    const long long tstart = tprev;
     double dif = 2.0, difid = 1.0, dif1 = 0.0, beta = 1.0, alpha = 0.0, alpha0 = 0.0;
     lstagn = 0;
 
@@ -258,8 +304,11 @@ __device__ __noinline__ int gdsteady_dev(const X &x, ContactCase &c, const doubl
         int imeth, kdown;
         if (beta > sp.betath || itgd - it_fb <= 1) { imeth = sp.gd_meth; kdown = sp.kdown; }
         else { imeth = 2; kdown = sp.kdowfb; it_fb = itgd; }
+        GD_TICK(5);
         gd_project_searchdir(x, mx, my, el, g, imeth, kdown, sp.fdecay, nn, dv, v, scr, fac_v);
+        GD_TICK(2);
         nprod += conv_multi(x, c.chatA, dv, 0, 1, q, 0, 1, el, 1, 0);
+        GD_TICK(1);
         double sm4[4] = { 0.0, 0.0, 0.0, 0.0 };                                  // r.r, (r.q) d over all; d^2 q.q, r.r over C
         for (size_t i = x.first(); i < (size_t) n; i += x.stride()) {
             const bool in = el[i] >= EL_ADHES;
@@ -281,7 +330,9 @@ __device__ __noinline__ int gdsteady_dev(const X &x, ContactCase &c, const doubl
             bool stop_j = false, has_bracket = false;
             double alpha_j = 0.0, dst_cur = 0.0, dst_prv1 = 0.0, dst_prv2 = 0.0;
             while (!stop_j) {
+                GD_TICK(4);
                 gd_apply_trcbnd(x, mx, my, el, g, dp, alpha_j, dv, (double *) nullptr, scr, (double *) nullptr);
+                GD_TICK(3);
                 double s6[6] = { 0.0, 0.0, 0.0, 0.0, 0.0, 0.0 };               // rho, c0adh, c1adh, c0slp, c1slp, c2slp
                 for (size_t i = x.first(); i < (size_t) n; i += x.stride()) {
                     const int e0 = el[i];
@@ -399,7 +450,8 @@ __device__ __noinline__ int gdsteady_dev(const X &x, ContactCase &c, const doubl
                 alpha_j = tbl_alpha[im];
             }
             alpha = alpha_j;
-            if (x.leader()) c.gd_ntrial += j;
+            if (x.leader()) { c.gd_ntrial += j; prof[6] += j; }
+            GD_TICK(4);
         }
 
         beta = alpha * sqrt(sm4[2]) / sqrt(sm4[3]);
@@ -410,7 +462,9 @@ __device__ __noinline__ int gdsteady_dev(const X &x, ContactCase &c, const doubl
             nn[i] = cos(th); nn[n + i] = sin(th);
         }
         x.sync();
+        GD_TICK(5);
         gd_slip(x, c, dp, ws, ss, nprod);
+        GD_TICK(1);
         double ch[1] = { 0.0 };
         for (size_t i = x.first(); i < (size_t) n; i += x.stride()) {
             const int e0 = el[i];
@@ -454,6 +508,11 @@ __device__ __noinline__ int gdsteady_dev(const X &x, ContactCase &c, const doubl
     if (lchanged && itgd >= maxgd) lstagn = 1;
     else if (dif > difid && conv > 1.0 && itgd >= maxgd) lstagn = 1;
     else if (conv < 1.0 - tiny && res_dp > 5.0 * difid / (1.0 - conv)) { itgd = -itgd; lstagn = 1; }
+    GD_TICK(5);
+    if (x.leader()) {
+        prof[0] = (unsigned long long) abs(itgd); prof[7] = (unsigned long long) (clock64() - tstart);
+        for (int k = 0; k < 8; k++) atomicAdd(&g_gd_prof[k], prof[k]);
+    }
     return itgd;
 }
 

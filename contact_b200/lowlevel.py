@@ -46,6 +46,14 @@ def steady_prof(reset=True):
     return dict(steps=out[0], plstrc=out[1], reintegrate=out[2], update=out[3], calls=out[4], rowupdate=out[5], changes=out[6], rowchanges=out[7])
 
 
+def gd_prof(reset=True):
+    """Cycle counters of GDsteady (leader thread): dict(iterations, products, searchdir, ls_rows, ls_elements, step, trials, total)."""
+    import ctypes as C
+    out = (C.c_ulonglong * 8)()
+    _check(load_library().cb200_gd_prof(out, 1 if reset else 0))
+    return dict(iterations=out[0], products=out[1], searchdir=out[2], ls_rows=out[3], ls_elements=out[4], step=out[5], trials=out[6], total=out[7])
+
+
 def num_sms():
     return _check(load_library().cb200_num_sms())
 
@@ -153,7 +161,8 @@ def subsurf_points(mx, my, xc1, yc1, dx, dy, gg, poiss, ps, xyz):
 def get_iterations(ire, icp=1):
     out = (C.c_int * 8)(); log = (C.c_int * 64)()
     _check(load_library().cb200_get_iterations(ire, icp, out, 64, log))
-    return dict(itnorm=out[0], itcg=out[1], ittang=out[2], itgs=out[3], ncon=out[4], nr_itcg=list(log[:out[5]]), itout=out[6])
+    return dict(itnorm=out[0], itcg=out[1], ittang=out[2], itgs=out[3], ncon=out[4], nr_itcg=list(log[:out[5]]), itout=out[6],
+                gd_trials=(out[7] if out[7] >= 0 else -out[7] - 1), gd_fallback=int(out[7] < 0))
 
 
 def snorm_kernel_ms():

@@ -118,9 +118,10 @@ void cntc_finalizelast(void);
  * ierror[k] receives what cntc_calculate(ire[k], icp) would have returned. */
 void cntc_calculate_batch(int *nre, int *ire, int *icp, int *ierror);
 
-/* iteration counters of the last case of (ire, icp): out[0..6] = itnorm, ItCG of NormCG, ittang, iterations of the
- * tangential solver, ncon, number of tangential solver calls, outer (Panagiotopoulos) iterations; nr_itcg = iterations
- * per solver call (Newton-Raphson log) */
+/* iteration counters of the last case of (ire, icp): out[0..7] = itnorm, ItCG of NormCG, ittang, iterations of the
+ * tangential solver, ncon, number of tangential solver calls, outer (Panagiotopoulos) iterations, GDsteady: number of
+ * line-search trials (negated - 1 when a stagnating GDsteady fell back to SteadyGS, m_solvpt.f90:474-484); nr_itcg =
+ * iterations per solver call (Newton-Raphson log) */
 int cb200_get_iterations(int ire, int icp, int *out, int lenarr, int *nr_itcg);
 
 /* last error message of the calling thread (NUL-terminated, owned by the library) */
@@ -133,6 +134,10 @@ int cb200_conv_prof(unsigned long long *out, int reset);
 /* cycle counters of the SteadyGS element step summed over all CTAs since the last reset: out[0] element steps,
  * [1] cycles in the per-element solve (plstrc), [2] re-integration, [3] rank-1 updates + barriers, [4] solver calls */
 int cb200_steady_prof(unsigned long long *out, int reset);
+/* cycle counters of GDsteady (leader thread of every solver call) since the last reset: out[0] iterations, [1] cycles in
+ * the FFT products, [2] search direction, [3] line search: integration along the rows, [4] line search: element pass,
+ * reduction, bracketing, [5] step + active set + diagonal scaling + residual, [6] line-search trials, [7] total cycles */
+int cb200_gd_prof(unsigned long long *out, int reset);
 /* number of SMs of the device in use, or -99 */
 int cb200_num_sms(void);
 

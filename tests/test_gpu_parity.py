@@ -1,4 +1,6 @@
 """GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs."""
+import os
+
 import numpy as np
 import pytest
 
@@ -562,6 +564,44 @@ def test_gdsteady_large_grid_2c(cb, O, mbench):
     pn, px, py = cb.cntc_gettractions(ire, icp)
     s = np.abs(ref["ps"][:2]).max()
     assert np.abs(px.ravel() - ref["ps"][0]).max() < 2e-6 * s and np.abs(py.ravel() - ref["ps"][1]).max() < 2e-6 * s
+    cb.cntc_finalize(ire)
+
+
+@pytest.mark.parametrize("name", ["4c", "8c"])
+def test_gdsteady_perfc_large_grids_against_oracle_fixture(cb, name):
+    """perfc_test/tang_problm_4c.inp (287x323) and tang_problm_8c.inp (575x647, BASELINE config 3: T=3, G=5, solver record
+    :9) on the whole-GPU path.  The oracle needs minutes for these, so its results are committed as fixtures
+    (tests/golden/gdsteady_mbench.json, made by tests/golden/make_gdsteady_fixtures.py): contact area of the golden
+    norm_problm runs (get_times.ref_out:9-10), element division by checksum, iteration count, forces."""
+    import hashlib
+    import json
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "gdsteady_mbench.json")))
+    if name not in fx:
+        pytest.skip("no oracle fixture for " + name)
+    ref = fx[name]
+    mb = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "mbench_profile.json")))
+    prm = np.array([mb["nn"], mb["xm"], mb["rm"], mb["y1"], mb["dy1"]] + mb["heights"])
+    mx, my, dx = ref["grid"]
+    g = dict(mx=mx, my=my, xl=-3.55, yl=-6.15, dx=dx, dy=dx, ibase=2, prmudf=prm)
+    ire, icp = 69, 1
+    _setup_rolling(cb, ire, g, cases.STEEL["gg"], cases.STEEL["poiss"], pen=mb["pen"])
+    _gd_flags(cb, ire, icp, GD_8C)
+    cb.cntc_setrollingstepsize(ire, icp, 0.0, dx)
+    cb.cntc_setcreepages(ire, icp, 0.0005, 0.0, 0.0003)
+    ierr = cb.cntc_calculate(ire, icp)
+    assert ierr == 0, (ierr, cb.lib.last_error())
+    its = cb.lowlevel.get_iterations(ire, icp)
+    el = cb.cntc_getelementdivision(ire, icp).ravel().astype(np.int8)
+    assert int((el >= 1).sum()) == ref["ncon"] == {"4c": 50796, "8c": 200980}[name]
+    assert its["gd_fallback"] == 0 and ref["gd_fallback"] == 0
+    assert abs(int((el == 2).sum()) - ref["nslip"]) <= (0 if name == "4c" else 4), (int((el == 2).sum()), ref["nslip"])
+    if name == "4c":
+        assert hashlib.sha1(el.tobytes()).hexdigest() == ref["el_sha1"]
+    assert abs(its["itgs"] - ref["itgs"]) <= max(3, ref["itgs"] // 20), (its, ref["itgs"])
+    fn, tx, ty, mz = cb.cntc_getcontactforces(ire, icp)
+    assert abs(tx / (0.3 * fn) - ref["fx"]) < 1e-7 and abs(ty / (0.3 * fn) - ref["fy"]) < 1e-7
+    pn, px, py = cb.cntc_gettractions(ire, icp)
+    assert abs(px.sum() - ref["ps_sum"][0]) < 1e-7 * abs(ref["ps_sum"][0]) and abs(py.sum() - ref["ps_sum"][1]) < 1e-7 * abs(ref["ps_sum"][1])
     cb.cntc_finalize(ire)
 
 

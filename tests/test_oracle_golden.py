@@ -206,3 +206,17 @@ def test_gdsteady_converges_to_steadygs(mbench):
                       gd=(fdecay, 0.05, 1, 2.0, -1.0, 1.0, 2.6, 1.0), **kw)
         assert rv["ierror"] == 0 and int((rv["el"] == 2).sum()) == 1872, fdecay
         assert np.abs(rv["ps"][:2] - r0["ps"][:2]).max() < 1e-4 * scale, fdecay
+
+
+def test_gdsteady_fixture_file_matches_oracle(mbench):
+    """tests/golden/gdsteady_mbench.json (oracle runs of tang_problm_{1,2,4,8}c with G=5, used by the GPU tests for the
+    grids the oracle needs minutes for) is reproduced by the oracle on the 71x81 grid: same element division, iteration
+    count and forces."""
+    import hashlib
+    import json
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "gdsteady_mbench.json")))["1c"]
+    kw = dict(tang=3, norm=0, force3=0, pen=mbench["pen"], cksi=0.0005, ceta=0.0, cphi=0.0003, fstat=0.3, fkin=0.3, maxgs=5000,
+              maxin=100, maxnr=30, maxout=1, eps=1e-7, nn=mbench["nn"], chi=0.0, dq=0.1)
+    r = O.contac(_mbench_grid(mbench), cases.STEEL["gg"], cases.STEEL["poiss"], gausei=5, gd=(1.0, 0.05, 1, 2.0, -1.0, 1.0, 2.6, 1.0), **kw)
+    assert hashlib.sha1(r["el"].astype(np.int8).tobytes()).hexdigest() == fx["el_sha1"]
+    assert r["itgs_tang"] == fx["itgs"] and abs(r["fx"] - fx["fx"]) < 1e-12 and abs(r["fy"] - fx["fy"]) < 1e-12
