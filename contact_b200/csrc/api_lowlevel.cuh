@@ -123,7 +123,9 @@ struct NormBatch {            // persistent device workspace of the batched NORM
     long stage_cap = 0;
     double *s_hs = nullptr, *s_pn = nullptr, *s_un = nullptr, *s_scal = nullptr;
     int *s_el = nullptr;
+    cudaStream_t pipe[3] = { nullptr, nullptr, nullptr };   // host-buffer entry point: chunks of the batch alternate over these
 };
+#define CB_NEXT_SLOTS 64
 
 __global__ void k_norm_pack(NormCase *cases, int ncase, int npot, const double *hs, int *el, double *pn, double *un,
                             const double *scal, double *work, NormCase proto)
@@ -182,8 +184,11 @@ inline int snorm_large_dev(CoefSet &cs, int ncase, NormCase proto, const double 
     return 0;
 }
 
+// c0 / total / slot: this call handles cases c0 .. c0+ncase-1 of a batch of `total` cases whose chunks are in flight on
+// different streams (host-buffer entry point); the workspace is sized for the whole batch, `slot` selects the work queue
 inline int snorm_batch_dev(CoefSet &cs, int ncase, int ic_norm, int maxgs, int maxin, double eps, const double *d_hs,
-                           int *d_el, double *d_pn, double *d_un, double *d_scal, cudaStream_t st)
+                           int *d_el, double *d_pn, double *d_un, double *d_scal, cudaStream_t st, int c0 = 0, int total = 0,
+                           int slot = 0)
 {
     Engine &E = engine();
     const ConvPlan &P = cs.hp.p;
@@ -193,17 +198,23 @@ inline int snorm_batch_dev(CoefSet &cs, int ncase, int ic_norm, int maxgs, int m
     if ((rc = build_chat(cs, SET_MS, 3, 3, st))) return rc;
     if ((rc = build_levels(cs, st))) return rc;
     NormBatch &B = norm_batch();
-    if (!B.d_next) CB_CUDA(cudaMalloc(&B.d_next, sizeof(int)));
+    if (!B.d_next) CB_CUDA(cudaMalloc(&B.d_next, sizeof(int) * CB_NEXT_SLOTS));
     if (!B.ev0) { CB_CUDA(cudaEventCreate(&B.ev0)); CB_CUDA(cudaEventCreate(&B.ev1)); }
     static long cap_bytes = 0;
-    const long need = (long) ncase * 9 * P.npot * sizeof(double);
-    if (ncase > B.cap || need > cap_bytes) {
+    const int ntot = total > ncase ? total : ncase;
+    const long need = (long) ntot * 9 * P.npot * sizeof(double);
+    if (ntot > B.cap || need > cap_bytes) {
+        if (c0 > 0) { last_error() = "snorm_batch_dev: workspace must be reserved by the first chunk"; return -99; }
+        CB_CUDA(cudaDeviceSynchronize());
         if (B.d_cases) cudaFree(B.d_cases);
         if (B.d_work) cudaFree(B.d_work);
-        CB_CUDA(cudaMalloc(&B.d_cases, sizeof(NormCase) * ncase));
+        CB_CUDA(cudaMalloc(&B.d_cases, sizeof(NormCase) * ntot));
         CB_CUDA(cudaMalloc(&B.d_work, need));
-        B.cap = ncase; cap_bytes = need;
+        B.cap = ntot; cap_bytes = need;
     }
+    NormCase *d_cases = B.d_cases + c0;
+    double *d_work = B.d_work + (size_t) c0 * 9 * P.npot;
+    int *d_next = B.d_next + (slot % CB_NEXT_SLOTS);
     NormCase proto;
     memset(&proto, 0, sizeof(proto));
     proto.chatA = cs.d_chat[SET_CS][2][2];
@@ -216,12 +227,12 @@ inline int snorm_batch_dev(CoefSet &cs, int ncase, int ic_norm, int maxgs, int m
     proto.dxdy = cs.key.dx * cs.key.dy;
     proto.lev = cs.d_lev; proto.nlx = cs.nlx; proto.nly = cs.nly;
     if (!cs.hp.fits) return snorm_large_dev(cs, ncase, proto, d_hs, d_el, d_pn, d_un, d_scal, st);
-    k_norm_pack<<<grid1d(ncase, 128), 128, 0, st>>>(B.d_cases, ncase, P.npot, d_hs, d_el, d_pn, d_un, d_scal, B.d_work, proto);
-    CB_CUDA(cudaMemsetAsync(B.d_next, 0, sizeof(int), st));
-    CB_CUDA(cudaEventRecord(B.ev0, st));
-    k_snorm_batch<<<launch_blocks(ncase), CB_THREADS, P.smem_bytes, st>>>(P, B.d_cases, ncase, B.d_next);
-    CB_CUDA(cudaEventRecord(B.ev1, st));
-    k_norm_unpack<<<grid1d(ncase, 128), 128, 0, st>>>(B.d_cases, ncase, d_scal);
+    k_norm_pack<<<grid1d(ncase, 128), 128, 0, st>>>(d_cases, ncase, P.npot, d_hs, d_el, d_pn, d_un, d_scal, d_work, proto);
+    CB_CUDA(cudaMemsetAsync(d_next, 0, sizeof(int), st));
+    if (c0 == 0) CB_CUDA(cudaEventRecord(B.ev0, st));
+    k_snorm_batch<<<launch_blocks(ncase), CB_THREADS, P.smem_bytes, st>>>(P, d_cases, ncase, d_next);
+    if (total <= ncase || c0 + ncase >= total) CB_CUDA(cudaEventRecord(B.ev1, st));
+    k_norm_unpack<<<grid1d(ncase, 128), 128, 0, st>>>(d_cases, ncase, d_scal);
     E.launches += 3;
     if (d_un) {
         static bool attr = false;
@@ -296,8 +307,8 @@ int cb200_gd_prof(unsigned long long *out, int reset)
 {   // cycle counters of GDsteady (leader thread of every solver call) since the last reset (see gdsteady_solver.cuh)
     int rc = engine_init();
     if (rc) return rc;
-    CB_CUDA(cudaMemcpyFromSymbol(out, g_gd_prof, sizeof(unsigned long long) * 8));
-    if (reset) { unsigned long long z[8] = { 0 }; CB_CUDA(cudaMemcpyToSymbol(g_gd_prof, z, sizeof(z))); }
+    CB_CUDA(cudaMemcpyFromSymbol(out, g_gd_prof, sizeof(unsigned long long) * 12));
+    if (reset) { unsigned long long z[12] = { 0 }; CB_CUDA(cudaMemcpyToSymbol(g_gd_prof, z, sizeof(z))); }
     return 0;
 }
 int cb200_num_sms(void) { int rc = engine_init(); return rc ? rc : engine().num_sms; }
@@ -391,18 +402,42 @@ int cb200_snorm_batch(int handle, int ncase, int ic_norm, int maxgs, int maxin, 
         CB_CUDA(cudaMalloc(&B.s_el, sizeof(int) * n));
         B.stage_cap = n;
     }
-    cudaStream_t st = 0;
-    CB_CUDA(cudaMemcpyAsync(B.s_hs, hs, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-    CB_CUDA(cudaMemcpyAsync(B.s_pn, pn, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-    CB_CUDA(cudaMemcpyAsync(B.s_el, el, sizeof(int) * n, cudaMemcpyHostToDevice, st));
-    CB_CUDA(cudaMemcpyAsync(B.s_scal, scal, sizeof(double) * 8 * ncase, cudaMemcpyHostToDevice, st));
-    int rc = snorm_batch_dev(*cs, ncase, ic_norm, maxgs, maxin, eps, B.s_hs, B.s_el, B.s_pn, un ? B.s_un : nullptr, B.s_scal, st);
-    if (rc) return rc;
-    CB_CUDA(cudaMemcpyAsync(pn, B.s_pn, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-    CB_CUDA(cudaMemcpyAsync(el, B.s_el, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
-    if (un) CB_CUDA(cudaMemcpyAsync(un, B.s_un, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-    CB_CUDA(cudaMemcpyAsync(scal, B.s_scal, sizeof(double) * 8 * ncase, cudaMemcpyDeviceToHost, st));
-    CB_CUDA(cudaStreamSynchronize(st));
+    // The batch is cut into chunks (multiples of the SM count: one CTA per case) that alternate over three streams, so
+    // that the host->device copy of chunk k+1 and the device->host copy of chunk k-1 run on the copy engines while the
+    // solver kernel of chunk k occupies the SMs.  Pageable host buffers still work (the copies then serialise).
+    Engine &E = engine();
+    const int npot = cs->hp.p.npot, nsm = E.num_sms > 0 ? E.num_sms : 1;
+    int csz = ncase;
+    if (cs->hp.fits && ncase >= 4 * nsm) csz = ((ncase / 4 + nsm - 1) / nsm) * nsm;        // about four chunks
+    const int nchunk = (ncase + csz - 1) / csz;
+    if (nchunk > 1) {
+        for (int k = 0; k < 3; k++) if (!B.pipe[k]) CB_CUDA(cudaStreamCreateWithFlags(&B.pipe[k], cudaStreamNonBlocking));
+        // coefficient transforms (cached per grid and material) are built once, before the chunks fan out over the streams
+        int rc0 = build_prec(*cs, 0);
+        if (!rc0) rc0 = build_chat(*cs, SET_CS, 3, 3, 0);
+        if (!rc0) rc0 = build_chat(*cs, SET_MS, 3, 3, 0);
+        if (!rc0) rc0 = build_levels(*cs, 0);
+        if (rc0) return rc0;
+        CB_CUDA(cudaStreamSynchronize(0));
+    }
+    for (int ch = 0; ch < nchunk; ch++) {
+        const int c0 = ch * csz, nc = (ncase - c0 < csz) ? ncase - c0 : csz;
+        const size_t o = (size_t) c0 * npot, m = (size_t) nc * npot;
+        cudaStream_t st = nchunk > 1 ? B.pipe[ch % 3] : (cudaStream_t) 0;
+        CB_CUDA(cudaMemcpyAsync(B.s_hs + o, hs + o, sizeof(double) * m, cudaMemcpyHostToDevice, st));
+        CB_CUDA(cudaMemcpyAsync(B.s_pn + o, pn + o, sizeof(double) * m, cudaMemcpyHostToDevice, st));
+        CB_CUDA(cudaMemcpyAsync(B.s_el + o, el + o, sizeof(int) * m, cudaMemcpyHostToDevice, st));
+        CB_CUDA(cudaMemcpyAsync(B.s_scal + (size_t) c0 * 8, scal + (size_t) c0 * 8, sizeof(double) * 8 * nc, cudaMemcpyHostToDevice, st));
+        int rc = snorm_batch_dev(*cs, nc, ic_norm, maxgs, maxin, eps, B.s_hs + o, B.s_el + o, B.s_pn + o, un ? B.s_un + o : nullptr,
+                                 B.s_scal + (size_t) c0 * 8, st, c0, ncase, ch);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        CB_CUDA(cudaMemcpyAsync(pn + o, B.s_pn + o, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+        CB_CUDA(cudaMemcpyAsync(el + o, B.s_el + o, sizeof(int) * m, cudaMemcpyDeviceToHost, st));
+        if (un) CB_CUDA(cudaMemcpyAsync(un + o, B.s_un + o, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+        CB_CUDA(cudaMemcpyAsync(scal + (size_t) c0 * 8, B.s_scal + (size_t) c0 * 8, sizeof(double) * 8 * nc, cudaMemcpyDeviceToHost, st));
+    }
+    if (nchunk > 1) { for (int k = 0; k < 3; k++) CB_CUDA(cudaStreamSynchronize(B.pipe[k])); }
+    else CB_CUDA(cudaStreamSynchronize(0));
     return 0;
 }
 

@@ -90,6 +90,7 @@ template <int N>
 __device__ __forceinline__ void block_sum(double (&v)[N], double *red)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncwarp();                          // shuffles of a warp that is still split after a ragged loop take a slow path
 #pragma unroll
     for (int i = 0; i < N; i++)
 #pragma unroll

@@ -21,7 +21,7 @@ namespace cb200 {
 // [0] iterations, [1] cycles in the products A dv / A dp, [2] search direction, [3] line search: integration along the
 // rows, [4] line search: element pass + reduction + bracketing, [5] step, active set, diagonal scaling, residual,
 // [6] line-search trials, [7] total cycles of the solver calls
-__device__ unsigned long long g_gd_prof[8];
+__device__ unsigned long long g_gd_prof[12];
 #define GD_TICK(slot) do { if (x.leader()) { const long long t_ = clock64(); prof[slot] += (unsigned long long) (t_ - tprev); tprev = t_; } } while (0)
 
 __device__ __forceinline__ double gd_wrap_pi(double e)
@@ -63,6 +63,7 @@ __device__ void gd_apply_trcbnd(const X &x, int mx, int my, const int *el, const
         const int i0 = iy * mx;
         double prx = 0.0, pry = 0.0;                          // ps of the element to the right (uniform over the warp)
         for (int base = ((mx - 1) >> 5) << 5; base >= 0; base -= 32) {
+            __syncwarp();
             const int ix = base + lane, ii = i0 + ix;
             const bool have = ix < mx;
             int e = 0; double gg = 0.0, dx_ = 0.0, dy_ = 0.0;
@@ -73,6 +74,12 @@ __device__ void gd_apply_trcbnd(const X &x, int mx, int my, const int *el, const
             }
             double mypx = 0.0, mypy = 0.0, mydx = dx_, mydy = dy_;
             const int kmax = min(31, mx - 1 - base);
+            if (__all_sync(0xffffffffu, e <= EL_EXTER)) {
+                // 32 exterior elements: no walk; zero tractions, and only the element next to the chunk on the right
+                // sees a non-zero neighbour (about half of a potential contact area is exterior)
+                if (ix != mx - 1) { mydx = (lane == kmax) ? 0.0 - prx : 0.0; mydy = (lane == kmax) ? 0.0 - pry : 0.0; }
+                prx = 0.0; pry = 0.0;
+            } else
             for (int k = kmax; k >= 0; k--) {
                 const int ek = __shfl_sync(0xffffffffu, e, k);
                 const double gk = shfl_d(gg, k), dkx = shfl_d(dx_, k), dky = shfl_d(dy_, k);
@@ -82,8 +89,13 @@ __device__ void gd_apply_trcbnd(const X &x, int mx, int my, const int *el, const
                     if (ek <= EL_EXTER) { px = 0.0; py = 0.0; }
                     else {
                         px = prx + dkx; py = pry + dky;
-                        const double pa = sqrt(px * px + py * py);
-                        if (ek == EL_SLIP || pa >= gk) { px = px * gk / pa; py = py * gk / pa; }
+                        const double p2 = px * px + py * py;
+                        // (square root and divisions only where the bound can be active: the filter is conservative
+                        //  by more than the rounding of the square root, the decision itself is the reference's)
+                        if (ek == EL_SLIP || p2 >= gk * gk * (1.0 - 1e-15)) {
+                            const double pa = sqrt(p2);
+                            if (ek == EL_SLIP || pa >= gk) { px = px * gk / pa; py = py * gk / pa; }
+                        }
                     }
                     if (lane == k) { mydx = px - prx; mydy = py - pry; }
                 }
@@ -99,90 +111,77 @@ __device__ void gd_apply_trcbnd(const X &x, int mx, int my, const int *el, const
     x.sync();
 }
 
-// project_searchdir (:639-803): dv in/out, v out.  imeth 1: E_trl, 3: E_keep(fdecay): one warp per row, like
-// gd_apply_trcbnd; imeth 2: E_down(kdown), the fall-back direction after a small step, looks kdown elements ahead in a
-// scratch copy of dv that it modifies on the way: one thread per row.
+// project_searchdir (:639-803): dv in/out, v out.  imeth 1: E_trl, 2: E_down(kdown), 3: E_keep(fdecay).  One warp per
+// row, like gd_apply_trcbnd.  E_down looks kdown elements ahead in a copy of dv in which every non-adhesion element
+// zeroes the kdown entries to its right as the row is walked (:700-790); seen from the adhesion element at ix the entry
+// ix + kdown is still intact exactly when the elements ix+1 .. ix+kdown-1 are all in adhesion, so the walk only carries
+// the length of the adhesion run to the right (`clean`) and reads the look-ahead from the unmodified copy scr.
 template <class X>
 __device__ void gd_project_searchdir(const X &x, int mx, int my, const int *el, const double *g, int imeth, int kdown, double fdecay,
-                                     const double *nn, double *dv, double *v, double *scr, double fac_v)
+                                     const double *nn, double *dv, double *v, double *scr, double fac_v,
+                                     unsigned long long *prof = nullptr)
 {
     const int n = mx * my;
-    if (imeth != 2) {
-        const int lane = threadIdx.x & 31;
-        for (int iy = (int) x.warp_first(); iy < my; iy += (int) x.warp_stride()) {
-            const int i0 = iy * mx;
-            double vrx = 0.0, vry = 0.0;                      // v of the element to the right (uniform over the warp)
-            for (int base = ((mx - 1) >> 5) << 5; base >= 0; base -= 32) {
-                const int ix = base + lane, ii = i0 + ix;
-                const bool have = ix < mx;
-                int e = 0; double dx_ = 0.0, dy_ = 0.0, tx = 0.0, ty = 0.0, lim = 0.0;
-                if (have) {
-                    e = el[ii]; dx_ = dv[ii]; dy_ = dv[n + ii];
-                    if (e == EL_SLIP) { tx = -nn[n + ii]; ty = nn[ii]; lim = fac_v * g[ii]; }
-                }
-                double myvx = 0.0, myvy = 0.0, mydx = dx_, mydy = dy_;
-                const int kmax = min(31, mx - 1 - base);
-                for (int k = kmax; k >= 0; k--) {
-                    const int ek = __shfl_sync(0xffffffffu, e, k);
-                    const double dkx = shfl_d(dx_, k), dky = shfl_d(dy_, k);
-                    double vx, vy;
-                    if (base + k == mx - 1) { vx = 0.0; vy = 0.0; }
-                    else if (ek == EL_ADHES) {
-                        if (imeth == 1) { vx = vrx + dkx; vy = vry + dky; }
-                        else {
-                            vx = fdecay * vrx + dkx; vy = fdecay * vry + dky;
-                            if (lane == k) { mydx = vx - vrx; mydy = vy - vry; }
-                        }
-                    } else if (ek == EL_SLIP) {
-                        const double tkx = shfl_d(tx, k), tky = shfl_d(ty, k), lk = shfl_d(lim, k);
-                        double vt = tkx * dkx + tky * dky;
-                        vt = copysign(1.0, vt) * fmin(fabs(vt), lk);
-                        vx = tkx * vt; vy = tky * vt;
-                        if (lane == k) { mydx = vx - vrx; mydy = vy - vry; }
-                    } else {
-                        vx = 0.0; vy = 0.0;
-                        if (lane == k) { mydx = -vrx; mydy = -vry; }
-                    }
-                    if (lane == k) { myvx = vx; myvy = vy; }
-                    vrx = vx; vry = vy;
-                }
-                if (have) { v[ii] = myvx; v[n + ii] = myvy; dv[ii] = mydx; dv[n + ii] = mydy; }
-            }
-        }
+    long long tq0 = clock64();
+    if (imeth == 2) {
+        for (size_t i = x.first(); i < (size_t) (2 * n); i += x.stride()) scr[i] = dv[i];
         x.sync();
-        return;
+        if (prof) { prof[11] += 1; }
     }
-    for (size_t i = x.first(); i < (size_t) (2 * n); i += x.stride()) scr[i] = dv[i];
-    x.sync();
-    for (int iy = (int) x.row_first(); iy < my; iy += (int) x.row_stride()) {
+    long long tq1 = clock64();
+    const int lane = threadIdx.x & 31;
+    for (int iy = (int) x.warp_first(); iy < my; iy += (int) x.warp_stride()) {
         const int i0 = iy * mx;
-        double *dxin = scr + i0, *dyin = scr + n + i0;
-        int ii = i0 + mx - 1;
-        v[ii] = 0.0; v[n + ii] = 0.0;
-        double vrx = 0.0, vry = 0.0;                          // v of the element to the right
-        for (int ix = mx - 2; ix >= 0; ix--) {
-            ii = i0 + ix;
-            const int e = el[ii];
-            double vx, vy;
-            if (e == EL_ADHES) {
-                if (ix + kdown <= mx - 1) { vx = vrx + dxin[ix] - dxin[ix + kdown]; vy = vry + dyin[ix] - dyin[ix + kdown]; }
-                else { vx = vrx + dxin[ix]; vy = vry + dyin[ix]; }
-            } else if (e == EL_SLIP) {
-                const double tx = -nn[n + ii], ty = nn[ii];
-                double vt = tx * dxin[ix] + ty * dyin[ix];
-                vt = copysign(1.0, vt) * fmin(fabs(vt), fac_v * g[ii]);
-                vx = tx * vt; vy = ty * vt;
-                for (int k = 1; k <= kdown; k++) if (ix + k <= mx - 1) { dxin[ix + k] = 0.0; dyin[ix + k] = 0.0; }
-            } else {
-                vx = 0.0; vy = 0.0;
-                for (int k = 1; k <= kdown; k++) if (ix + k <= mx - 1) { dxin[ix + k] = 0.0; dyin[ix + k] = 0.0; }
+        double vrx = 0.0, vry = 0.0;                          // v of the element to the right (uniform over the warp)
+        int clean = 0;                                        // adhesion run to the right of the current element
+        for (int base = ((mx - 1) >> 5) << 5; base >= 0; base -= 32) {
+            __syncwarp();
+            const int ix = base + lane, ii = i0 + ix;
+            const bool have = ix < mx;
+            int e = 0; double dx_ = 0.0, dy_ = 0.0, tx = 0.0, ty = 0.0, lim = 0.0, lx_ = 0.0, ly_ = 0.0;
+            if (have) {
+                e = el[ii]; dx_ = dv[ii]; dy_ = dv[n + ii];
+                if (e == EL_SLIP) { tx = -nn[n + ii]; ty = nn[ii]; lim = fac_v * g[ii]; }
+                if (imeth == 2 && e == EL_ADHES && ix + kdown <= mx - 1) { lx_ = scr[ii + kdown]; ly_ = scr[n + ii + kdown]; }
             }
-            dv[ii] = vx - vrx; dv[n + ii] = vy - vry;
-            v[ii] = vx; v[n + ii] = vy;
-            vrx = vx; vry = vy;
+            double myvx = 0.0, myvy = 0.0, mydx = dx_, mydy = dy_;
+            const int kmax = min(31, mx - 1 - base);
+            // the walk: all broadcasts of a step are issued unconditionally at its top and the three element kinds are
+            // evaluated by selection, so that the loop body is straight-line code (a nested branch per element kind with
+            // shuffles inside cost ~2000 cycles per step on the whole-GPU path, tools/gd_timing.py)
+            if (__all_sync(0xffffffffu, e <= EL_EXTER)) {                 // 32 exterior elements: no walk (see gd_apply_trcbnd)
+                if (ix != mx - 1) { mydx = (lane == kmax) ? 0.0 - vrx : 0.0; mydy = (lane == kmax) ? 0.0 - vry : 0.0; }
+                vrx = 0.0; vry = 0.0;
+                clean = (kmax == 0 && base == mx - 1) ? 1 : 0;
+            } else
+            for (int k = kmax; k >= 0; k--) {
+                const int ek = __shfl_sync(0xffffffffu, e, k);
+                const double dkx = shfl_d(dx_, k), dky = shfl_d(dy_, k);
+                const double tkx = shfl_d(tx, k), tky = shfl_d(ty, k), lk = shfl_d(lim, k);
+                double lkx = 0.0, lky = 0.0;
+                if (imeth == 2) { lkx = shfl_d(lx_, k); lky = shfl_d(ly_, k); if (clean < kdown - 1) { lkx = 0.0; lky = 0.0; } }
+                const bool last = (base + k == mx - 1), adh = (ek == EL_ADHES) && !last, slp = (ek == EL_SLIP) && !last;
+                // adhesion: accumulate (E_keep damps the running sum, E_down subtracts the look-ahead entry)
+                const double fr = (imeth == 3) ? fdecay : 1.0;
+                const double ax = (fr * vrx + dkx) - lkx, ay = (fr * vry + dky) - lky;
+                // slip: component along the tangent, limited
+                double vt = tkx * dkx + tky * dky;
+                vt = copysign(1.0, vt) * fmin(fabs(vt), lk);
+                const double sx = tkx * vt, sy = tky * vt;
+                const double vx = adh ? ax : (slp ? sx : 0.0), vy = adh ? ay : (slp ? sy : 0.0);
+                if (lane == k) {
+                    myvx = vx; myvy = vy;
+                    if (!last && !(adh && imeth == 1)) { mydx = vx - vrx; mydy = vy - vry; }
+                }
+                clean = last ? 1 : (adh ? clean + 1 : 0);
+                vrx = vx; vry = vy;
+            }
+            if (have) { v[ii] = myvx; v[n + ii] = myvy; dv[ii] = mydx; dv[n + ii] = mydy; }
         }
     }
+    long long tq2 = clock64();
     x.sync();
+    if (prof) { prof[8] += (unsigned long long) (tq1 - tq0); prof[9] += (unsigned long long) (tq2 - tq1); prof[10] += (unsigned long long) (clock64() - tq2); }
 }
 
 // compute_diagscaling (:901-1042) + residual r = -D s (adhesion) / -D (s.t) t (slip), per element
@@ -272,7 +271,7 @@ __device__ __noinline__ int gdsteady_dev(const X &x, ContactCase &c, const doubl
     const double facnel = (double) sqrtf(__fdiv_rn((float) n, (float) (nadh + nslip)));
     int itgd = 0, it_fb = -99;
     bool lchanged = false;
-    unsigned long long prof[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    unsigned long long prof[12] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
     long long tprev = clock64();
     const long long tstart = tprev;
     double dif = 2.0, difid = 1.0, dif1 = 0.0, beta = 1.0, alpha = 0.0, alpha0 = 0.0;
@@ -305,7 +304,7 @@ __device__ __noinline__ int gdsteady_dev(const X &x, ContactCase &c, const doubl
         if (beta > sp.betath || itgd - it_fb <= 1) { imeth = sp.gd_meth; kdown = sp.kdown; }
         else { imeth = 2; kdown = sp.kdowfb; it_fb = itgd; }
         GD_TICK(5);
-        gd_project_searchdir(x, mx, my, el, g, imeth, kdown, sp.fdecay, nn, dv, v, scr, fac_v);
+        gd_project_searchdir(x, mx, my, el, g, imeth, kdown, sp.fdecay, nn, dv, v, scr, fac_v, x.leader() ? prof : nullptr);
         GD_TICK(2);
         nprod += conv_multi(x, c.chatA, dv, 0, 1, q, 0, 1, el, 1, 0);
         GD_TICK(1);
@@ -511,7 +510,7 @@ __device__ __noinline__ int gdsteady_dev(const X &x, ContactCase &c, const doubl
     GD_TICK(5);
     if (x.leader()) {
         prof[0] = (unsigned long long) abs(itgd); prof[7] = (unsigned long long) (clock64() - tstart);
-        for (int k = 0; k < 8; k++) atomicAdd(&g_gd_prof[k], prof[k]);
+        for (int k = 0; k < 12; k++) atomicAdd(&g_gd_prof[k], prof[k]);
     }
     return itgd;
 }

@@ -49,9 +49,10 @@ def steady_prof(reset=True):
 def gd_prof(reset=True):
     """Cycle counters of GDsteady (leader thread): dict(iterations, products, searchdir, ls_rows, ls_elements, step, trials, total)."""
     import ctypes as C
-    out = (C.c_ulonglong * 8)()
+    out = (C.c_ulonglong * 12)()
     _check(load_library().cb200_gd_prof(out, 1 if reset else 0))
-    return dict(iterations=out[0], products=out[1], searchdir=out[2], ls_rows=out[3], ls_elements=out[4], step=out[5], trials=out[6], total=out[7])
+    return dict(iterations=out[0], products=out[1], searchdir=out[2], ls_rows=out[3], ls_elements=out[4], step=out[5], trials=out[6], total=out[7],
+                sd_copy=out[8], sd_leader_rows=out[9], sd_wait=out[10], sd_fallbacks=out[11])
 
 
 def num_sms():

@@ -136,7 +136,8 @@ int cb200_conv_prof(unsigned long long *out, int reset);
 int cb200_steady_prof(unsigned long long *out, int reset);
 /* cycle counters of GDsteady (leader thread of every solver call) since the last reset: out[0] iterations, [1] cycles in
  * the FFT products, [2] search direction, [3] line search: integration along the rows, [4] line search: element pass,
- * reduction, bracketing, [5] step + active set + diagonal scaling + residual, [6] line-search trials, [7] total cycles */
+ * reduction, bracketing, [5] step + active set + diagonal scaling + residual, [6] line-search trials, [7] total cycles,
+ * [8..10] search direction: copy for E_down, the leader's own rows, wait for the other rows, [11] E_down fall-backs (out: 12 values) */
 int cb200_gd_prof(unsigned long long *out, int reset);
 /* number of SMs of the device in use, or -99 */
 int cb200_num_sms(void);

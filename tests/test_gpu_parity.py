@@ -200,6 +200,50 @@ def test_batch_hertz91_matches_oracle(cb, O):
         cb.cntc_finalize(ire)
 
 
+def test_host_buffer_batch_pipeline_matches_device_path_and_oracle(cb, O):
+    """cb200_snorm_batch (HOST buffers; the end-to-end entry point of bench.py) cuts a large batch into chunks that alternate
+    over three streams so that copies overlap the solver kernel.  A batch large enough to be cut (4 x SM count + a ragged
+    rest) on the 19x19 cattaneo grid must give bit-identical results to ONE launch on device buffers, and spot-checked cases
+    must match the oracle."""
+    import torch
+    ll = cb.lowlevel
+    c = cases.CATTANEO2
+    g = dict(mx=c["mx"], my=c["my"], xl=c["xl"], yl=c["yl"], dx=c["dx"], dy=c["dy"], ibase=1, prmudf=c["prmudf"])
+    npot = g["mx"] * g["my"]
+    ncase = 4 * ll.num_sms() + 37
+    u = np.random.default_rng(11).uniform(-1.0, 1.0, size=ncase)
+    fns = c["fn"] * (1.0 + 0.3 * u)
+    h = cases.quadratic_h(g)
+    hs = np.tile(h, (ncase, 1))
+    el0 = np.zeros((ncase, npot), dtype=np.int32)
+    scal0 = np.zeros((ncase, 8)); scal0[:, 1] = fns
+    for i in range(ncase):
+        el0[i], scal0[i, 0] = ll.eldiv0(g["mx"], g["my"], g["dx"], g["dy"], c["gg"], c["poiss"], 1, list(c["prmudf"]) + [0.0, 0.0],
+                                        1, float(fns[i]), 0.0, h)
+    cset = ll.CoefSet(g["mx"], g["my"], g["dx"], g["dy"], gg=c["gg"], poiss=c["poiss"])
+    # host buffers (pinned), pipelined chunks
+    p_hs = torch.tensor(hs).pin_memory(); p_el = torch.tensor(el0).pin_memory(); p_pn = torch.zeros(ncase, npot, dtype=torch.float64).pin_memory()
+    p_un = torch.zeros(ncase, npot, dtype=torch.float64).pin_memory(); p_scal = torch.tensor(scal0).pin_memory()
+    for rep in range(2):                                           # second pass reuses the staging buffers and streams
+        p_el.copy_(torch.from_numpy(el0)); p_pn.zero_(); p_scal.copy_(torch.from_numpy(scal0))
+        cset.snorm_batch(p_hs.numpy(), p_el.numpy(), p_pn.numpy(), p_un.numpy(), p_scal.numpy(), ic_norm=1, maxgs=c["maxgs"],
+                         maxin=c["maxin"], eps=c["eps"])
+    # device buffers, one launch
+    d_hs = torch.tensor(hs, device="cuda"); d_el = torch.tensor(el0, device="cuda"); d_pn = torch.zeros(ncase, npot, dtype=torch.float64, device="cuda")
+    d_un = torch.zeros_like(d_pn); d_scal = torch.tensor(scal0, device="cuda")
+    cset.snorm_batch_dev(d_hs, d_el, d_pn, d_un, d_scal, ic_norm=1, maxgs=c["maxgs"], maxin=c["maxin"], eps=c["eps"])
+    torch.cuda.synchronize()
+    assert np.array_equal(p_el.numpy(), d_el.cpu().numpy())
+    assert np.array_equal(p_pn.numpy(), d_pn.cpu().numpy()) and np.array_equal(p_un.numpy(), d_un.cpu().numpy())
+    assert np.array_equal(p_scal.numpy()[:, :7], d_scal.cpu().numpy()[:, :7])
+    for i in (0, ll.num_sms(), ncase - 1):                         # first chunk, a middle chunk, the ragged last chunk
+        ref = O.norm_case(g["mx"], g["my"], g["xl"], g["yl"], g["dx"], g["dy"], c["gg"], c["poiss"], 1, c["prmudf"], 1,
+                          fn=float(fns[i]), maxgs=c["maxgs"], maxin=c["maxin"], eps=c["eps"])
+        assert np.array_equal(p_el.numpy()[i], ref["el"])
+        assert _rel(p_pn.numpy()[i], ref["pn"]) < 1e-9
+        assert abs(p_scal.numpy()[i, 0] - ref["pen"]) < 1e-9 * abs(ref["pen"])
+
+
 # ------------------------------------------------------------------------------------------------------------
 # subsurface stresses
 # ------------------------------------------------------------------------------------------------------------

@@ -47,6 +47,8 @@ def run(name, gausei=5, reps=2):
             out["cycle_share"] = {k: round(pr[k] / pr["total"], 3) for k in ("products", "searchdir", "ls_rows", "ls_elements", "step")}
             out["kcycles_per_trial"] = {k: round(pr[k] / max(1, pr["trials"]) / 1e3, 1) for k in ("ls_rows", "ls_elements")}
             out["kcycles_per_iteration"] = round(pr["total"] / max(1, pr["iterations"]) / 1e3, 1)
+            out["searchdir_kcycles_per_iteration"] = {k: round(pr[k] / max(1, pr["iterations"]) / 1e3, 1) for k in ("searchdir", "sd_copy", "sd_leader_rows", "sd_wait")}
+            out["sd_fallbacks"] = pr["sd_fallbacks"]
         if ierr < 0:
             out["error"] = cb.lib.last_error()
         cb.cntc_finalize(ire)
