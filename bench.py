@@ -106,16 +106,20 @@ def mbench_grid(mx=71, my=81, dx=0.1):
     return dict(mx=mx, my=my, xl=-3.55, yl=-6.15, dx=dx, dy=dx, ibase=2, prmudf=prm, pen=mb["pen"], nn=mb["nn"])
 
 
-def rolling_sweep_leg(cb, n, rank_offset):
-    """sweep-4096 class: mbench 71x81 grid, steady rolling T=3 (default solver SteadyGS), penetration
-    PEN (1 + 0.1 u) and creepages (2e-3 u, 2e-3 u, 3e-4 u), seed 20240229 -- n cases through cntc_calculate_batch."""
+def rolling_sweep_leg(cb, n, rank_offset, gausei=0):
+    """sweep-4096 class: mbench 71x81 grid, steady rolling T=3, penetration PEN (1 + 0.1 u) and creepages
+    (2e-3 u, 2e-3 u, 3e-4 u), seed 20240229 -- n cases through cntc_calculate_batch.  gausei 0: the default solver
+    (SteadyGS); 5: GDsteady with the solver record of perfc_test/tang_problm_8c.inp:9."""
     g = mbench_grid()
     u = np.random.default_rng(20240229).uniform(-1.0, 1.0, size=(4096, 4))[rank_offset:rank_offset + n]
     ires = list(range(1, n + 1))
     for i, ire in enumerate(ires):
         cb.cntc_initialize(ire, 3)
         cb.cntc_setflags(ire, 1, [cb.CNTC["ic_tang"], cb.CNTC["ic_force"], cb.CNTC["ic_iestim"]], [3, 0, 0])
-        cb.cntc_setsolverflags(ire, 1, 0, [999, 100, 30, 1], [1e-5])
+        if gausei == 5:
+            cb.cntc_setsolverflags(ire, 1, 5, [999, 100, 30, 1, 1], [1e-5, 1.0, 0.05, 2.0, -1.0, 1.0, 2.6, 1.0])
+        else:
+            cb.cntc_setsolverflags(ire, 1, 0, [999, 100, 30, 1], [1e-5])
         cb.cntc_setmaterialparameters(ire, 1, 0, [0.28, 0.28, 82000.0, 82000.0])
         cb.cntc_setfrictionmethod(ire, 1, 0, [0.3, 0.3])
         cb.cntc_setpotcontact(ire, 1, 1, [g["mx"], g["my"], g["xl"], g["yl"], g["dx"], g["dy"]])
@@ -126,11 +130,20 @@ def rolling_sweep_leg(cb, n, rank_offset):
     t0 = time.perf_counter()
     ierr = cb.cntc_calculate_batch(ires, 1)
     dt = time.perf_counter() - t0
-    its = [cb.lowlevel.get_iterations(ire, 1)["itgs"] for ire in ires]
+    kms = cb.lowlevel.snorm_kernel_ms()
+    split = cb.lowlevel.batch_timing()
+    its = [cb.lowlevel.get_iterations(ire, 1) for ire in ires]
+    fxy = np.array([cb.cntc_getcontactforces(ire, 1)[:3] for ire in ires])
     for ire in ires:
         cb.cntc_finalize(ire)
-    return {"cases": n, "s": dt, "cases_per_s": n / dt, "mean_itgs": float(np.mean(its)), "errors": int((ierr < 0).sum()),
-            "note": "mbench 71x81, T=3 SteadyGS, eps 1e-5, host buffers through cntc_calculate_batch (one launch)"}
+    out = {"cases": n, "s": dt, "cases_per_s": n / dt, "solver_kernel_ms": kms, "mean_itgs": float(np.mean([t["itgs"] for t in its])),
+           "errors": int((ierr < 0).sum()), "wall_split_s": split,
+           "note": "mbench 71x81, T=3 %s, eps 1e-5, host buffers through cntc_calculate_batch (one launch)" % ("GDsteady (G=5)" if gausei == 5 else "SteadyGS")}
+    if gausei == 5:
+        out["fallbacks_to_steadygs"] = int(sum(t["gd_fallback"] for t in its))
+        out["mean_linesearch_trials"] = float(np.mean([t["gd_trials"] for t in its]))
+    out["_forces"] = fxy
+    return out
 
 
 def spence71_leg(cb):
@@ -369,6 +382,10 @@ def run_gpu(args):
     # ---- secondary legs: rolling sweep (every rank its own shard) and the 575x647 grid (rank 0) ----
     nroll = nsm if args.cases <= 0 else min(args.cases, nsm)
     roll = rolling_sweep_leg(cb, nroll, (rank * nroll) % (4096 - nroll)) if not args.skip_extra else None
+    roll_gd = rolling_sweep_leg(cb, nroll, (rank * nroll) % (4096 - nroll), gausei=5) if not args.skip_extra else None
+    if roll and roll_gd:                     # the two solvers on the same cases: largest difference of the total forces
+        f0, f5 = roll.pop("_forces"), roll_gd.pop("_forces")
+        roll_gd["max_rel_force_diff_vs_steadygs"] = float(np.abs(f5 - f0).max() / np.abs(f0).max())
     large = large_grid_leg(cb, torch) if (rank == 0 and not args.skip_extra) else None
     sp71 = spence71_leg(cb) if (rank == 0 and not args.skip_extra) else None
     gdl = gdsteady_leg(cb) if (rank == 0 and not args.skip_extra) else None
@@ -385,7 +402,8 @@ def run_gpu(args):
     e2e_s = time.perf_counter() - t0
 
     roll_s = roll["s"] if roll else 0.0
-    t = torch.tensor([ms_total, e2e_s, kernel_ms, nprod, roll_s], dtype=torch.float64, device=dev)
+    rollgd_s = roll_gd["s"] if roll_gd else 0.0
+    t = torch.tensor([ms_total, e2e_s, kernel_ms, nprod, roll_s, rollgd_s], dtype=torch.float64, device=dev)
     tmax = t.clone()
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -397,6 +415,8 @@ def run_gpu(args):
     ms_total, e2e_s, kernel_ms = float(tmax[0]), float(tmax[1]), float(tmax[2])
     if roll:
         roll["cases_per_s"] = roll["cases"] * world / float(tmax[4]); roll["cases_total"] = roll["cases"] * world
+    if roll_gd:
+        roll_gd["cases_per_s"] = roll_gd["cases"] * world / float(tmax[5]); roll_gd["cases_total"] = roll_gd["cases"] * world
 
     if rank == 0:
         peaks = {}
@@ -448,6 +468,8 @@ def run_gpu(args):
         }
         if roll:
             out["rolling_sweep"] = roll
+        if roll_gd:
+            out["rolling_sweep_gdsteady"] = roll_gd
         if large:
             large["frac_hbm"] = large["alg_GBps"] / hbm_peak
             large["frac_fp64"] = large["nominal_TFLOPs"] / fp64_peak if fp64_peak > 0 else None
@@ -488,6 +510,11 @@ def cpu_baseline(budget_s, threads):
                   cphi=0.0003, fstat=0.3, fkin=0.3, maxgs=999, maxin=100, maxnr=30, maxout=1, eps=1e-5, nn=gm["nn"], chi=0.0,
                   dq=0.1, gausei=0)
     dtr = time.perf_counter() - t2
+    t2 = time.perf_counter()
+    rg = O.contac(gm, cases.STEEL["gg"], cases.STEEL["poiss"], tang=3, norm=0, force3=0, pen=gm["pen"], cksi=0.0005, ceta=0.0,
+                  cphi=0.0003, fstat=0.3, fkin=0.3, maxgs=999, maxin=100, maxnr=30, maxout=1, eps=1e-5, nn=gm["nn"], chi=0.0,
+                  dq=0.1, gausei=5, gd=(1.0, 0.05, 1, 2.0, -1.0, 1.0, 2.6, 1.0))
+    dtg = time.perf_counter() - t2
     from tests import inp_oracle
     from tests.test_gpu_parity import _sequence
     t3 = time.perf_counter()
@@ -497,6 +524,8 @@ def cpu_baseline(budget_s, threads):
             "spence71_first12_contact_s": dt71,
             "rolling_cases_per_s": 1.0 / dtr, "rolling_sample": "tang_problm_1c creepages on mbench 71x81, T=3 SteadyGS, eps 1e-5, "
                                                               "%d sweeps, %.2f s" % (rr["itgs_tang"], dtr),
+            "rolling_gdsteady_cases_per_s": 1.0 / dtg,
+            "rolling_gdsteady_sample": "same case, G=5 GDsteady, eps 1e-5, %d iterations, %.2f s" % (rg["itgs_tang"], dtg),
             "sample": "%d hertz-91 cases (first of the seeded sweep), %.1f s wall; CPU restatement of the reference "
                       "algorithm (oracle/), gcc -O2, own mixed-radix FFT instead of MKL" % (ns, dt),
             "mean_itcg": float(r["itcg"].mean())}
@@ -512,7 +541,7 @@ def run_reference(args):
     from oracle import oracle as O
     g = cases.HERTZ91
     fns, _ = cases.hertz91_fn(4096, fn0=FN0)
-    per_step = max(threads, 2 * threads)
+    per_step = 16 * threads            # enough cases per thread that the uneven iteration counts of the cases average out
     def one(k):
         lo = (k * per_step) % (4096 - per_step)
         t0 = time.perf_counter()

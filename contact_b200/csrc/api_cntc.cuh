@@ -316,8 +316,16 @@ inline int hertz_setup(Problem &p)
 }
 
 // contac (m_scontc.f90:37-216) for a batch of problems: host set-up, ONE device launch per coefficient class, gather
+// wall-clock split of the last calculate_batch call (s): [0] host set-up of the cases, [1] coefficient transforms (cached),
+// [2] device allocation + uploads, [3] solver kernel(s), [4] output products + downloads, [5] total
+inline double *batch_timing() { static double t[6] = { 0, 0, 0, 0, 0, 0 }; return t; }
+
 inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int> &ierr)
 {
+    double *bt = batch_timing();
+    for (int k = 0; k < 6; k++) bt[k] = 0.0;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
     const size_t nb = probs.size();
     ierr.assign(nb, 0);
     std::map<CoefSet *, std::vector<size_t>> groups;
@@ -383,7 +391,9 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
         if (!cs->hp.fits && p.tang == 3 && p.gausei != 5) { last_error() = "grid too large for the single-CTA SteadyGS solver (the whole-GPU path serves T=0 and T=1)"; ierr[k] = CNTC_err_discr; continue; }
         groups[cs].push_back(k);
     }
+    bt[0] = secs(t0, now());
     for (auto &g : groups) {
+        auto tg0 = now();
         CoefSet &cs = *g.first;
         const std::vector<size_t> &ks = g.second;
         const int n = (int) ks.size(), npot = cs.mx * cs.my;
@@ -410,6 +420,9 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
             for (int ik = 1; ik <= 2 && !rc; ik++) for (int jk = 1; jk <= 2 && !rc; jk++) rc = build_chat(cs, SET_CSV, ik, jk, 0);
         if (!rc) rc = build_levels(cs, 0, any_tang);            // after the full-size transforms and preconditioners exist
         if (rc) { fail(rc); continue; }
+        cudaDeviceSynchronize();
+        auto tg1 = now();
+        bt[1] += secs(tg0, tg1);
         // device buffers: per case hs_n(1) hst(2) ps(3) ss(2) work(9) twork(24) pv(3) = 44 n doubles, el n ints
         // (+ 16 n of GDsteady work space when a case of the group asks for G = 5)
         bool any_gd = false;
@@ -490,6 +503,8 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
         cudaMemset(d_buf + 6 * (size_t) npot, 0, 0);
         cudaMemcpy(d_cases, hc.data(), sizeof(ContactCase) * n, cudaMemcpyHostToDevice);
         cudaMemset(d_next, 0, sizeof(int));
+        auto tg2 = now();
+        bt[2] += secs(tg1, tg2);
         NormBatch &NB = norm_batch();                               // events around the solver kernel(s): cb200_snorm_kernel_ms
         if (!NB.ev0) { cudaEventCreate(&NB.ev0); cudaEventCreate(&NB.ev1); }
         cudaEventRecord(NB.ev0, 0);
@@ -508,6 +523,8 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
         }
         cudaEventRecord(NB.ev1, 0);
         cudaError_t e = cudaDeviceSynchronize();
+        auto tg3 = now();
+        bt[3] += secs(tg2, tg3);
         if (e != cudaSuccess) { last_error() = std::string("k_contac_batch: ") + cudaGetErrorString(e); fail(CNTC_err_other); }
         else {
             cudaMemcpy(hc.data(), d_cases, sizeof(ContactCase) * n, cudaMemcpyDeviceToHost);
@@ -561,8 +578,10 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
             }
         }
         cudaFree(d_buf); cudaFree(d_el); cudaFree(d_cases); cudaFree(d_next);
+        bt[4] += secs(tg3, now());
     }
     const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    bt[5] = dt;
     for (size_t k = 0; k < nb; k++) { probs[k]->t_wall += dt / (double) nb; probs[k]->t_cpu += dt / (double) nb; }
 }
 
@@ -808,6 +827,8 @@ int cb200_eldiv0(int mx, int my, double dx, double dy, double gg1, double gg2, d
 
 // iteration counters of the last case: out[0..6] = itnorm, itcg (NormCG), ittang, itgs (tangential solver iterations),
 // ncon, number of tangential solver calls nr_n, outer iterations; nr_itcg[0..nr_n) = iterations per solver call (at most lenarr)
+int cb200_batch_timing(double *out) { for (int k = 0; k < 6; k++) out[k] = batch_timing()[k]; return 0; }
+
 int cb200_get_iterations(int ire, int icp, int *out, int lenarr, int *nr_itcg)
 {
     int e; Problem *p = activate(ire, icp, &e);

@@ -46,6 +46,14 @@ def steady_prof(reset=True):
     return dict(steps=out[0], plstrc=out[1], reintegrate=out[2], update=out[3], calls=out[4], rowupdate=out[5], changes=out[6], rowchanges=out[7])
 
 
+def batch_timing():
+    """Wall-clock split (s) of the last cntc_calculate[_batch] call: dict(setup, coefficients, upload, kernel, output, total)."""
+    import ctypes as C
+    out = (C.c_double * 6)()
+    _check(load_library().cb200_batch_timing(out))
+    return dict(zip(("setup", "coefficients", "upload", "kernel", "output", "total"), [round(v, 5) for v in out]))
+
+
 def gd_prof(reset=True):
     """Cycle counters of GDsteady (leader thread): dict(iterations, products, searchdir, ls_rows, ls_elements, step, trials, total)."""
     import ctypes as C

@@ -124,6 +124,11 @@ void cntc_calculate_batch(int *nre, int *ire, int *icp, int *ierror);
  * iterations per solver call (Newton-Raphson log) */
 int cb200_get_iterations(int ire, int icp, int *out, int lenarr, int *nr_itcg);
 
+/* wall-clock split (s) of the last cntc_calculate / cntc_calculate_batch call: out[0] host set-up of the cases, [1] coefficient
+ * transforms (cached per grid and material), [2] device allocation + uploads, [3] solver kernel(s), [4] output products +
+ * downloads, [5] total */
+int cb200_batch_timing(double *out);
+
 /* last error message of the calling thread (NUL-terminated, owned by the library) */
 const char *cb200_last_error(void);
 /* number of kernels launched by the library so far (bench.py: "gpu_launches") */

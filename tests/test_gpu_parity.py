@@ -649,6 +649,35 @@ def test_gdsteady_perfc_large_grids_against_oracle_fixture(cb, name):
     cb.cntc_finalize(ire)
 
 
+def test_gdsteady_batch_sweep_agrees_with_steadygs(cb, mbench):
+    """sweep-4096 class: a batch of mbench 71x81 rolling cases with seeded penetrations and creepages through
+    cntc_calculate_batch, once with the default solver (SteadyGS) and once with G=5 (GDsteady): no stagnation fall-back,
+    same contact area, element divisions equal up to a few borderline elements, total forces within the solvers' eps."""
+    n = 12
+    g = dict(mx=71, my=81, xl=-3.55, yl=-6.15, dx=0.1, dy=0.1, ibase=2, prmudf=np.array(mbench["prmudf"]))
+    u = np.random.default_rng(20240229).uniform(-1.0, 1.0, size=(4096, 4))[:n]
+    res = {}
+    for gausei in (0, 5):
+        ires = list(range(70, 70 + n))
+        for i, ire in enumerate(ires):
+            _setup_rolling(cb, ire, g, cases.STEEL["gg"], cases.STEEL["poiss"], pen=mbench["pen"] * (1.0 + 0.1 * u[i, 0]), eps=1e-6)
+            if gausei == 5:
+                _gd_flags(cb, ire, 1, GD_8C, maxgs=999, eps=1e-6)
+            cb.cntc_setrollingstepsize(ire, 1, 0.0, 0.1)
+            cb.cntc_setcreepages(ire, 1, 2e-3 * u[i, 1], 2e-3 * u[i, 2], 3e-4 * u[i, 3])
+        ierr = cb.cntc_calculate_batch(ires, 1)
+        assert (ierr == 0).all(), (ierr, cb.lib.last_error())
+        res[gausei] = [(cb.cntc_getelementdivision(ire, 1).ravel().copy(), np.array(cb.cntc_getcontactforces(ire, 1)),
+                        cb.lowlevel.get_iterations(ire, 1)) for ire in ires]
+        for ire in ires:
+            cb.cntc_finalize(ire)
+    for (el0, f0, it0), (el5, f5, it5) in zip(res[0], res[5]):
+        assert it5["gd_fallback"] == 0 and it5["itgs"] > 0
+        assert np.array_equal(el0 >= 1, el5 >= 1)
+        assert int((el0 != el5).sum()) <= 6, int((el0 != el5).sum())
+        assert np.abs(f5[:3] - f0[:3]).max() < 2e-5 * np.abs(f0[:3]).max()
+
+
 def test_gdsteady_prescribed_force_small(cb, O):
     """GDsteady inside the Newton-Raphson loop on CKSI (F=1) on a small quadratic gap, default iteration constants of
     cntc_setsolverflags G=5; against the oracle."""

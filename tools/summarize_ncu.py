@@ -1,9 +1,21 @@
 """Summarise ncu outputs under gpurun_out/ into tracked text files under profiles/ (round tag as argument)."""
 import collections
 import csv
+import gzip
 import json
+import os
 import subprocess
 import sys
+
+
+def page(name, tag, which):
+    """CSV of an ncu page: the export made on the GPU box (tools/profile_round.sh) or, failing that, ncu -i on the report."""
+    for f in ("gpurun_out/%s_%s.%s.csv" % (name, tag, which), "gpurun_out/%s_%s.%s.csv.gz" % (name, tag, which)):
+        if os.path.exists(f) and os.path.getsize(f) > 100:
+            return (gzip.open(f, "rt") if f.endswith(".gz") else open(f)).read()
+    return subprocess.run(["ncu", "-i", "gpurun_out/%s_%s.ncu-rep" % (name, tag), "--page", which, "--csv"],
+                          capture_output=True, text=True).stdout
+
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 out = []
@@ -26,8 +38,7 @@ for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append("%-72s n=%4d total=%10.3f ms share=%6.2f%%" % (k, v[0], v[1] / 1e6, 100 * v[1] / tot))
 
 # 2. key metrics of the dominant kernel from the --set full capture (148 cases, one per SM)
-raw = subprocess.run(["ncu", "-i", "gpurun_out/prof_snorm_%s.ncu-rep" % tag, "--page", "raw", "--csv"],
-                     capture_output=True, text=True).stdout
+raw = page("prof_snorm", tag, "raw")
 rr = list(csv.reader(raw.splitlines()))
 hh, units, vals = rr[0], rr[1], rr[2]
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread",
@@ -66,14 +77,15 @@ out.append("")
 out.append("dram traffic per launch (148 cases): %.1f MB = %.2f MB per case" % (traffic / 1e6, traffic / 1e6 / ncase))
 
 # 3. the three phase kernels of the whole-GPU product (575x647), one launch each
-import os
-if os.path.exists("gpurun_out/prof_large_%s.ncu-rep" % tag):
-    raw = subprocess.run(["ncu", "-i", "gpurun_out/prof_large_%s.ncu-rep" % tag, "--page", "raw", "--csv"],
-                         capture_output=True, text=True).stdout
+for name, title in (("prof_large", "# ncu --set full --clock-control none -k regex:k_lg_ : python tools/large_product_only.py (575x647, 1x1 product)"),
+                    ("prof_gd", "# ncu --set full --clock-control none -k regex:k_lg_contac -c 1 : python tools/gd_timing.py 2c (143x161, T=3, G=5 GDsteady on the whole GPU)")):
+    raw = page(name, tag, "raw")
     rr = list(csv.reader(raw.splitlines()))
+    if len(rr) < 3:
+        continue
     hh, units = rr[0], rr[1]
     out.append("")
-    out.append("# ncu --set full --clock-control none -k regex:k_lg_ : python tools/large_product_only.py (575x647, 1x1 product)")
+    out.append(title)
     ki = hh.index("Kernel Name")
     for vals in rr[2:]:
         out.append("## " + vals[ki][:60])
@@ -82,8 +94,7 @@ if os.path.exists("gpurun_out/prof_large_%s.ncu-rep" % tag):
                 out.append("%-90s %-12s %s" % (nme, units[i], vals[i]))
 
 # 4. where the warp-stall samples of the dominant kernel sit, by SASS opcode (source page, SASS view)
-src = subprocess.run(["ncu", "-i", "gpurun_out/prof_snorm_%s.ncu-rep" % tag, "--page", "source", "--csv"],
-                     capture_output=True, text=True).stdout
+src = page("prof_snorm", tag, "source")
 rs = list(csv.reader(src.splitlines()))
 hi = next((i for i, r in enumerate(rs) if r and r[0] == "Address"), None)
 if hi is not None:
