@@ -117,7 +117,17 @@ def write_spence71():
               open(os.path.join(HERE, "spence71_sequence.json"), "w"), indent=0)
 
 
+def write_tang_problm_c():
+    """perfc_test/tang_problm_{1,2}c.inp (T=3, G=5 GDsteady with its 8-parameter record) as parsed cases."""
+    cs = []
+    for k in (1, 2):
+        cs += inp_cases("perfc_test/tang_problm_%dc.inp" % k)
+    json.dump(dict(source="perfc_test/tang_problm_1c.inp, tang_problm_2c.inp", cases=cs),
+              open(os.path.join(HERE, "tang_problm_c_sequence.json"), "w"), indent=0)
+
+
 if __name__ == "__main__":
+    write_tang_problm_c()
     write_sequences()
     write_spence71()
     json.dump(subsurf(), open(os.path.join(HERE, "subsurf_ref_subs.json"), "w"))

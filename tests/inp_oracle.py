@@ -30,6 +30,8 @@ def run_cases(cases):
         kw = dict(tang=c["T"], norm=c["N"], force3=c["F"], fstat=c["fric"][0], fkin=c["fric"][1], maxgs=so["maxgs"], maxin=so["maxin"],
                   maxnr=so["maxnr"], maxout=so["maxout"], eps=so["eps"], nn=nn, gausei=c["G_eff"], omegah=so.get("omegah", 0.9),
                   omegas=so.get("omegas", 0.9), chi=c["roll"]["chi"], dq=c["roll"]["dq"], hertz=hertz, cphi=k[3])
+        if "gdsteady" in so:
+            kw["gd"] = tuple(so["gdsteady"])
         kw["pen" if c["N"] == 0 else "fn"] = k[0]
         if c["F"] == 0:
             kw.update(cksi=k[1], ceta=k[2])

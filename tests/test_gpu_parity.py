@@ -678,6 +678,39 @@ def test_gdsteady_batch_sweep_agrees_with_steadygs(cb, mbench):
         assert np.abs(f5[:3] - f0[:3]).max() < 2e-5 * np.abs(f0[:3]).max()
 
 
+def test_gdsteady_stagnation_falls_back_to_steadygs(cb, O, mbench):
+    """tang_solver (m_solvpt.f90:459-484): when GDsteady reports stagnation -- here forced by MAXGS = 40 on tang_problm_1c --
+    SteadyGS takes over from GDsteady's tractions.  One-CTA path: same switch, same sweeps and element division as the
+    oracle.  Whole-GPU path (143x163): the Gauss-Seidel solvers do not exist there, the case is refused with a message."""
+    g = dict(mx=71, my=81, xl=-3.55, yl=-6.15, dx=0.1, dy=0.1, ibase=2, prmudf=np.array(mbench["prmudf"]))
+    ire, icp = 66, 1
+    _setup_rolling(cb, ire, g, cases.STEEL["gg"], cases.STEEL["poiss"], pen=mbench["pen"])
+    _gd_flags(cb, ire, icp, GD_8C, maxgs=40)
+    cb.cntc_setrollingstepsize(ire, icp, 0.0, 0.1)
+    cb.cntc_setcreepages(ire, icp, 0.0005, 0.0, 0.0003)
+    ierr = cb.cntc_calculate(ire, icp)
+    assert ierr == 0, (ierr, cb.lib.last_error())
+    ref = O.contac(g, cases.STEEL["gg"], cases.STEEL["poiss"], tang=3, norm=0, force3=0, pen=mbench["pen"], cksi=0.0005,
+                   ceta=0.0, cphi=0.0003, fstat=0.3, fkin=0.3, maxgs=40, maxin=100, maxnr=30, maxout=1, eps=1e-7,
+                   nn=mbench["nn"], chi=0.0, dq=0.1, gausei=5, gd=GD_8C)
+    assert ref["ierror"] == 0 and ref["gd_fallback"] == 1
+    its = cb.lowlevel.get_iterations(ire, icp)
+    el = cb.cntc_getelementdivision(ire, icp).ravel()
+    assert its["gd_fallback"] == 1 and its["itgs"] == ref["itgs_tang"], (its, ref["itgs_tang"])
+    assert np.array_equal(el, ref["el"]) and int((el == 2).sum()) == 1872
+    pn, px, py = cb.cntc_gettractions(ire, icp)
+    s = np.abs(ref["ps"][:2]).max()
+    assert np.abs(px.ravel() - ref["ps"][0]).max() < 1e-7 * s and np.abs(py.ravel() - ref["ps"][1]).max() < 1e-7 * s
+    cb.cntc_finalize(ire)
+    g2 = dict(mx=143, my=163, xl=-3.55, yl=-6.15, dx=0.05, dy=0.05, ibase=2, prmudf=np.array(mbench["prmudf"]))
+    _setup_rolling(cb, ire, g2, cases.STEEL["gg"], cases.STEEL["poiss"], pen=mbench["pen"])
+    _gd_flags(cb, ire, icp, GD_8C, maxgs=10)
+    cb.cntc_setrollingstepsize(ire, icp, 0.0, 0.05)
+    cb.cntc_setcreepages(ire, icp, 0.0005, 0.0, 0.0003)
+    assert cb.cntc_calculate(ire, icp) == -99 and "Gauss-Seidel" in cb.lib.last_error()
+    cb.cntc_finalize(ire)
+
+
 def test_gdsteady_prescribed_force_small(cb, O):
     """GDsteady inside the Newton-Raphson loop on CKSI (F=1) on a small quadratic gap, default iteration constants of
     cntc_setsolverflags G=5; against the oracle."""
@@ -860,6 +893,13 @@ def _inp_text_from_cases(name):
         if "solver" in c:
             s = c["solver"]
             out.append(" %d %d %d %d %r" % (s["maxgs"], s["maxin"], s["maxnr"], s["maxout"], s["eps"]))
+            if c["G"] in (2, 3):
+                out.append(" %r %r %d %r" % (s["omegah"], s["omegas"], s["inislp"], s["omgslp"]))
+            elif c["G"] == 4:
+                out.append(" %d %r" % (s["inislp"], s["omgslp"]))
+            elif c["G"] == 5:                                   # FDECAY BETATH KDOWFB D_IFC D_LIN D_CNS D_SLP POW_S
+                gd = s["gdsteady"]
+                out.append(" %r %r %d %r %r %r %r %r" % (gd[0], gd[1], int(gd[2]), gd[3], gd[4], gd[5], gd[6], gd[7]))
         out.append(" " + " ".join(repr(v) for v in c["kin"]))
         if "fric" in c:
             out.append(" %r %r" % tuple(c["fric"]))
@@ -876,7 +916,11 @@ def _inp_text_from_cases(name):
                 out.append(" %d %d " % (p["mx"], p["my"]) + " ".join(repr(v) for v in p["prm"]))
         if "geom" in c:
             out.append(" %d %d" % (c["geom"]["ibase"], c["geom"]["iplan"]))
-            out.append(" " + " ".join(repr(v) for v in c["geom"]["prm"]))
+            prm = c["geom"]["prm"]
+            if c["geom"]["ibase"] == 2:                         # NN XM RM Y1 DY1, then the NN profile heights
+                out.append(" %d %r %r %r %r" % (int(prm[0]), prm[1], prm[2], prm[3], prm[4]))
+                prm = prm[5:]
+            out.append(" " + " ".join(repr(v) for v in prm))
         if c["S"] >= 2:
             out.append(" 0 0")
         if c["S"] >= 3:
@@ -914,6 +958,26 @@ def test_inp_sequence_spence35(cb, O):
         assert np.abs(r["px"].ravel() - o["ps"][0]).max() < 1e-5 * s + 1e-12 * np.abs(o["ps"][2]).max(), k
     # the subsurface block of the input (ISUBS=2: the centre row, just below the surface) was evaluated in every stage
     assert all(r.get("subs_ierror", 0) == 0 for r in res) and res[-1]["subs"][0].shape == (45, 21)
+
+
+def test_inp_tang_problm_c_gdsteady(cb, O):
+    """perfc_test/tang_problm_1c.inp and tang_problm_2c.inp as .inp text (G=5 with the 8-parameter GDsteady record,
+    m_sinput.f90:649-680; DQ is forced to DX, m_sdis.f90:125-204) through the reader and cntc_calculate: 71x81 on the
+    one-CTA path, 143x163 on the whole-GPU path, against the oracle run from the same parsed cases."""
+    from contact_b200 import inp as INP
+    from tests import inp_oracle
+    text, d = _inp_text_from_cases("tang_problm_c")
+    assert [c["G"] for c in d["cases"]] == [5, 5] and d["cases"][0]["solver"]["gdsteady"][0] == 1.0
+    res = INP.run_inp(text, ire=84)
+    ref = inp_oracle.run_cases(d["cases"])
+    assert [r["ierror"] for r in res] == [0, 0], [r.get("message") for r in res]
+    for r, o in zip(res, ref):
+        assert o["ierror"] == 0 and o["gd_fallback"] == 0
+        assert np.array_equal(r["el"].ravel(), o["el"])
+        assert r["its"]["itgs"] == o["itgs_tang"] and r["its"]["gd_fallback"] == 0
+        s = np.abs(o["ps"][:2]).max()
+        assert np.abs(r["px"].ravel() - o["ps"][0]).max() < 2e-6 * s and np.abs(r["py"].ravel() - o["ps"][1]).max() < 2e-6 * s
+    assert res[0]["nslip"] == 1872 and res[0]["ncon"] == 3148          # perfc_test/get_times.ref_out:7, :25
 
 
 def test_inp_sequence_cattaneo(cb, O):
