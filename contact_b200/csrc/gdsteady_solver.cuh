@@ -49,23 +49,32 @@ __device__ void sxbnd_facdt_x(const X &x, int mx, int my, const int *el, double 
     x.sync();
 }
 
-__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+// broadcast within a group of `gw` lanes (gw = 32: the whole warp)
+__device__ __forceinline__ double shfl_d(double v, int src, int gw) { return __shfl_sync(0xffffffffu, v, src, gw); }
+
+// The walks below give one grid row to a group of gw lanes (gw = 32, 16, 8 or 4: the largest width with which all rows are in
+// flight at once, X::row_group_width).  A group loads gw consecutive elements of its row, then its lanes walk them from the
+// leading edge; the 32/gw groups of a warp execute the same instruction stream on different rows, so on the one-CTA path
+// (12 warps, 81 rows of tang_problm_1c) the rows take 1 round of walks instead of 7.
 
 // apply_trcbnd (:807-847) on dpnew = dp + alpha dv (on C): integrate the increments from the leading edge (high x) and
-// clip at the traction bound g.  One warp per row, 32 elements per chunk.  ps_out receives the tractions, dp_out (may be
-// null: trial step of the line search) the consistent increments, pold (may be null) the previous content of ps_out.
+// clip at the traction bound g.  ps_out receives the tractions, dp_out (may be null: trial step of the line search) the
+// consistent increments, pold (may be null) the previous content of ps_out.
 template <class X>
 __device__ void gd_apply_trcbnd(const X &x, int mx, int my, const int *el, const double *g, const double *dp, double alpha,
                                 const double *dv, double *dp_out, double *ps_out, double *pold)
 {
     const int n = mx * my, lane = threadIdx.x & 31;
-    for (int iy = (int) x.warp_first(); iy < my; iy += (int) x.warp_stride()) {
+    const int gw = x.row_group_width(my), lig = lane & (gw - 1), grp = lane / gw, ngrp = 32 / gw;
+    for (int r0 = (int) x.warp_first() * ngrp; r0 < my; r0 += (int) x.warp_stride() * ngrp) {
+        const int iy = r0 + grp;
+        const bool row_ok = iy < my;
         const int i0 = iy * mx;
-        double prx = 0.0, pry = 0.0;                          // ps of the element to the right (uniform over the warp)
-        for (int base = ((mx - 1) >> 5) << 5; base >= 0; base -= 32) {
+        double prx = 0.0, pry = 0.0;                          // ps of the element to the right (uniform over the group)
+        for (int base = ((mx - 1) / gw) * gw; base >= 0; base -= gw) {
             __syncwarp();
-            const int ix = base + lane, ii = i0 + ix;
-            const bool have = ix < mx;
+            const int ix = base + lig, ii = i0 + ix;
+            const bool have = row_ok && ix < mx;
             int e = 0; double gg = 0.0, dx_ = 0.0, dy_ = 0.0;
             if (have) {
                 e = el[ii]; gg = g[ii]; dx_ = dp[ii]; dy_ = dp[n + ii];
@@ -73,34 +82,31 @@ __device__ void gd_apply_trcbnd(const X &x, int mx, int my, const int *el, const
                 if (pold) { pold[ii] = ps_out[ii]; pold[n + ii] = ps_out[n + ii]; }
             }
             double mypx = 0.0, mypy = 0.0, mydx = dx_, mydy = dy_;
-            const int kmax = min(31, mx - 1 - base);
+            const int kmax = min(gw - 1, mx - 1 - base);
             if (__all_sync(0xffffffffu, e <= EL_EXTER)) {
-                // 32 exterior elements: no walk; zero tractions, and only the element next to the chunk on the right
+                // exterior elements only: no walk; zero tractions, and only the element next to the chunk on the right
                 // sees a non-zero neighbour (about half of a potential contact area is exterior)
-                if (ix != mx - 1) { mydx = (lane == kmax) ? 0.0 - prx : 0.0; mydy = (lane == kmax) ? 0.0 - pry : 0.0; }
+                if (ix != mx - 1) { mydx = (lig == kmax) ? 0.0 - prx : 0.0; mydy = (lig == kmax) ? 0.0 - pry : 0.0; }
                 prx = 0.0; pry = 0.0;
             } else
             for (int k = kmax; k >= 0; k--) {
-                const int ek = __shfl_sync(0xffffffffu, e, k);
-                const double gk = shfl_d(gg, k), dkx = shfl_d(dx_, k), dky = shfl_d(dy_, k);
-                double px, py;
-                if (base + k == mx - 1) { px = 0.0; py = 0.0; }
-                else {
-                    if (ek <= EL_EXTER) { px = 0.0; py = 0.0; }
-                    else {
-                        px = prx + dkx; py = pry + dky;
-                        const double p2 = px * px + py * py;
-                        // (square root and divisions only where the bound can be active: the filter is conservative
-                        //  by more than the rounding of the square root, the decision itself is the reference's)
-                        if (ek == EL_SLIP || p2 >= gk * gk * (1.0 - 1e-15)) {
-                            const double pa = sqrt(p2);
-                            if (ek == EL_SLIP || pa >= gk) { px = px * gk / pa; py = py * gk / pa; }
-                        }
+                const int ek = __shfl_sync(0xffffffffu, e, k, gw);
+                const double gk = shfl_d(gg, k, gw), dkx = shfl_d(dx_, k, gw), dky = shfl_d(dy_, k, gw);
+                double px = 0.0, py = 0.0;
+                const bool last = (base + k == mx - 1);
+                if (!last && ek > EL_EXTER) {
+                    px = prx + dkx; py = pry + dky;
+                    const double p2 = px * px + py * py;
+                    // (square root and divisions only where the bound can be active: the filter is conservative
+                    //  by more than the rounding of the square root, the decision itself is the reference's)
+                    if (ek == EL_SLIP || p2 >= gk * gk * (1.0 - 1e-15)) {
+                        const double pa = sqrt(p2);
+                        if (ek == EL_SLIP || pa >= gk) { px = px * gk / pa; py = py * gk / pa; }
                     }
-                    if (lane == k) { mydx = px - prx; mydy = py - pry; }
                 }
-                if (lane == k) { mypx = px; mypy = py; }
+                if (lig == k) { mypx = px; mypy = py; if (!last) { mydx = px - prx; mydy = py - pry; } }
                 prx = px; pry = py;
+                __syncwarp();
             }
             if (have) {
                 ps_out[ii] = mypx; ps_out[n + ii] = mypy;
@@ -111,8 +117,8 @@ __device__ void gd_apply_trcbnd(const X &x, int mx, int my, const int *el, const
     x.sync();
 }
 
-// project_searchdir (:639-803): dv in/out, v out.  imeth 1: E_trl, 2: E_down(kdown), 3: E_keep(fdecay).  One warp per
-// row, like gd_apply_trcbnd.  E_down looks kdown elements ahead in a copy of dv in which every non-adhesion element
+// project_searchdir (:639-803): dv in/out, v out.  imeth 1: E_trl, 2: E_down(kdown), 3: E_keep(fdecay).  One group of lanes
+// per row, like gd_apply_trcbnd.  E_down looks kdown elements ahead in a copy of dv in which every non-adhesion element
 // zeroes the kdown entries to its right as the row is walked (:700-790); seen from the adhesion element at ix the entry
 // ix + kdown is still intact exactly when the elements ix+1 .. ix+kdown-1 are all in adhesion, so the walk only carries
 // the length of the adhesion run to the right (`clean`) and reads the look-ahead from the unmodified copy scr.
@@ -130,14 +136,17 @@ __device__ void gd_project_searchdir(const X &x, int mx, int my, const int *el, 
     }
     long long tq1 = clock64();
     const int lane = threadIdx.x & 31;
-    for (int iy = (int) x.warp_first(); iy < my; iy += (int) x.warp_stride()) {
+    const int gw = x.row_group_width(my), lig = lane & (gw - 1), grp = lane / gw, ngrp = 32 / gw;
+    for (int r0 = (int) x.warp_first() * ngrp; r0 < my; r0 += (int) x.warp_stride() * ngrp) {
+        const int iy = r0 + grp;
+        const bool row_ok = iy < my;
         const int i0 = iy * mx;
-        double vrx = 0.0, vry = 0.0;                          // v of the element to the right (uniform over the warp)
+        double vrx = 0.0, vry = 0.0;                          // v of the element to the right (uniform over the group)
         int clean = 0;                                        // adhesion run to the right of the current element
-        for (int base = ((mx - 1) >> 5) << 5; base >= 0; base -= 32) {
+        for (int base = ((mx - 1) / gw) * gw; base >= 0; base -= gw) {
             __syncwarp();
-            const int ix = base + lane, ii = i0 + ix;
-            const bool have = ix < mx;
+            const int ix = base + lig, ii = i0 + ix;
+            const bool have = row_ok && ix < mx;
             int e = 0; double dx_ = 0.0, dy_ = 0.0, tx = 0.0, ty = 0.0, lim = 0.0, lx_ = 0.0, ly_ = 0.0;
             if (have) {
                 e = el[ii]; dx_ = dv[ii]; dy_ = dv[n + ii];
@@ -145,21 +154,20 @@ __device__ void gd_project_searchdir(const X &x, int mx, int my, const int *el, 
                 if (imeth == 2 && e == EL_ADHES && ix + kdown <= mx - 1) { lx_ = scr[ii + kdown]; ly_ = scr[n + ii + kdown]; }
             }
             double myvx = 0.0, myvy = 0.0, mydx = dx_, mydy = dy_;
-            const int kmax = min(31, mx - 1 - base);
-            // the walk: all broadcasts of a step are issued unconditionally at its top and the three element kinds are
-            // evaluated by selection, so that the loop body is straight-line code (a nested branch per element kind with
-            // shuffles inside cost ~2000 cycles per step on the whole-GPU path, tools/gd_timing.py)
-            if (__all_sync(0xffffffffu, e <= EL_EXTER)) {                 // 32 exterior elements: no walk (see gd_apply_trcbnd)
-                if (ix != mx - 1) { mydx = (lane == kmax) ? 0.0 - vrx : 0.0; mydy = (lane == kmax) ? 0.0 - vry : 0.0; }
+            const int kmax = min(gw - 1, mx - 1 - base);
+            if (__all_sync(0xffffffffu, e <= EL_EXTER)) {                 // exterior elements only: no walk (see gd_apply_trcbnd)
+                if (ix != mx - 1) { mydx = (lig == kmax) ? 0.0 - vrx : 0.0; mydy = (lig == kmax) ? 0.0 - vry : 0.0; }
                 vrx = 0.0; vry = 0.0;
                 clean = (kmax == 0 && base == mx - 1) ? 1 : 0;
             } else
+            // the walk: all broadcasts of a step are issued unconditionally at its top and the three element kinds are
+            // evaluated by selection, so that the loop body is straight-line code for every group of the warp
             for (int k = kmax; k >= 0; k--) {
-                const int ek = __shfl_sync(0xffffffffu, e, k);
-                const double dkx = shfl_d(dx_, k), dky = shfl_d(dy_, k);
-                const double tkx = shfl_d(tx, k), tky = shfl_d(ty, k), lk = shfl_d(lim, k);
+                const int ek = __shfl_sync(0xffffffffu, e, k, gw);
+                const double dkx = shfl_d(dx_, k, gw), dky = shfl_d(dy_, k, gw);
+                const double tkx = shfl_d(tx, k, gw), tky = shfl_d(ty, k, gw), lk = shfl_d(lim, k, gw);
                 double lkx = 0.0, lky = 0.0;
-                if (imeth == 2) { lkx = shfl_d(lx_, k); lky = shfl_d(ly_, k); if (clean < kdown - 1) { lkx = 0.0; lky = 0.0; } }
+                if (imeth == 2) { lkx = shfl_d(lx_, k, gw); lky = shfl_d(ly_, k, gw); if (clean < kdown - 1) { lkx = 0.0; lky = 0.0; } }
                 const bool last = (base + k == mx - 1), adh = (ek == EL_ADHES) && !last, slp = (ek == EL_SLIP) && !last;
                 // adhesion: accumulate (E_keep damps the running sum, E_down subtracts the look-ahead entry)
                 const double fr = (imeth == 3) ? fdecay : 1.0;
@@ -169,7 +177,7 @@ __device__ void gd_project_searchdir(const X &x, int mx, int my, const int *el, 
                 vt = copysign(1.0, vt) * fmin(fabs(vt), lk);
                 const double sx = tkx * vt, sy = tky * vt;
                 const double vx = adh ? ax : (slp ? sx : 0.0), vy = adh ? ay : (slp ? sy : 0.0);
-                if (lane == k) {
+                if (lig == k) {
                     myvx = vx; myvy = vy;
                     if (!last && !(adh && imeth == 1)) { mydx = vx - vrx; mydy = vy - vry; }
                 }
@@ -339,8 +347,13 @@ __device__ __noinline__ int gdsteady_dev(const X &x, ContactCase &c, const doubl
                     const double gi = g[i], sx = ss[i], sy = ss[n + i], qx = q[i], qy = q[n + i];
                     const double vt = v[i] * (-nn[n + i]) + v[n + i] * nn[i];
                     const double dth_da = (gi * vt) / (fmax(tiny, gi * gi) + alpha_j * alpha_j * vt * vt);
-                    const double th = atan2(scr[n + i], scr[i]);
-                    const double nx = cos(th), ny = sin(th), tx = -ny, ty = nx;
+                    // direction of the trial traction: (cos, sin)(atan2(py, px)) of the reference is the normalised
+                    // vector ((1, 0) for the zero vector), evaluated here without the three transcendentals -- this pass
+                    // runs once per line-search trial
+                    const double qx_ = scr[i], qy_ = scr[n + i], q2_ = qx_ * qx_ + qy_ * qy_;
+                    double nx = 1.0, ny = 0.0;
+                    if (q2_ > 0.0) { const double qi = 1.0 / sqrt(q2_); nx = qx_ * qi; ny = qy_ * qi; }
+                    const double tx = -ny, ty = nx;
                     const double sn = sx * nx + sy * ny;
                     int elnew = e0;
                     if (elnew == EL_SLIP && sn > 0.0) elnew = EL_ADHES;

@@ -516,6 +516,8 @@ struct GridCtx {
     __device__ __forceinline__ size_t row_stride() const { return (size_t) gridDim.x * blockDim.x; }
     __device__ __forceinline__ size_t warp_first() const { return (size_t) (threadIdx.x >> 5) * gridDim.x + blockIdx.x; }
     __device__ __forceinline__ size_t warp_stride() const { return (size_t) gridDim.x * (blockDim.x >> 5); }
+    __device__ __forceinline__ int row_group_width(int nrows) const
+    { const int nw = (int) (gridDim.x * (blockDim.x >> 5)); return nrows <= nw ? 32 : (nrows <= 2 * nw ? 16 : (nrows <= 4 * nw ? 8 : 4)); }
     __device__ __forceinline__ void sync() const { grid.sync(); }
     template <int N> __device__ __forceinline__ void sum(double (&v)[N]) const { grid_sum<N>(v, redp, X.gpart, phase, grid); }
     __device__ __forceinline__ void conv(const double *p, const cd *chat, double *u, const int *el, int mask_mode, int add) const

@@ -81,6 +81,9 @@ struct BlockCtx {
     __device__ __forceinline__ size_t row_stride() const { return blockDim.x; }
     __device__ __forceinline__ size_t warp_first() const { return threadIdx.x >> 5; }
     __device__ __forceinline__ size_t warp_stride() const { return blockDim.x >> 5; }
+    // lanes per grid row in the row walks of GDsteady: the largest of 32, 16, 8, 4 with which all rows are in flight at once
+    __device__ __forceinline__ int row_group_width(int nrows) const
+    { const int nw = blockDim.x >> 5; return nrows <= nw ? 32 : (nrows <= 2 * nw ? 16 : (nrows <= 4 * nw ? 8 : 4)); }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
     template <int N> __device__ __forceinline__ void sum(double (&v)[N]) const { block_sum<N>(v, sm.red); }
     __device__ __forceinline__ void conv(const double *p, const cd *chat, double *u, const int *el, int mask_mode, int add) const
