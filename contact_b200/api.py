@@ -18,7 +18,9 @@ __all__ = [
     "cntc_getnumelements", "cntc_getgriddiscretization", "cntc_getpotcontact", "cntc_getpenetration",
     "cntc_getcreepages", "cntc_getcontactforces", "cntc_getcontactpatchareas", "cntc_getelementdivision",
     "cntc_getmaximumpressure", "cntc_getmaximumtraction", "cntc_getfielddata", "cntc_gettractions",
-    "cntc_getmicroslip", "cntc_getdisplacements", "cntc_getcalculationtime", "subs_addblock", "subs_calculate",
+    "cntc_getmicroslip", "cntc_getdisplacements", "cntc_getcalculationtime", "cntc_getparameters",
+    "cntc_getreferencevelocity", "cntc_gethertzcontact", "cntc_getsensitivities", "cntc_resetcalculationtime",
+    "subs_addblock", "subs_calculate",
     "subs_getblocksize", "subs_getresults", "cntc_finalize", "cntc_finalizelast",
 ]
 
@@ -265,6 +267,37 @@ def cntc_getcalculationtime(ire=1, icp=1):
     a, b = cd(0), cd(0)
     load_library().cntc_getcalculationtime(ci(ire), ci(icp), a, b)
     return a.value, b.value
+
+
+def cntc_getparameters(ire, icp, itask, lenarr=22):
+    """python_intfc/cntc_getparameters.py: itask 1 kinematic constants, 2 material, 3 friction."""
+    v = np.zeros(lenarr)
+    load_library().cntc_getparameters(ci(ire), ci(icp), ci(itask), ci(lenarr), _dp(v))
+    return v
+
+
+def cntc_getreferencevelocity(ire=1, icp=1):
+    v = cd(0)
+    load_library().cntc_getreferencevelocity(ci(ire), ci(icp), v)
+    return v.value
+
+
+def cntc_gethertzcontact(ire=1, icp=1):
+    """python_intfc/cntc_gethertzcontact.py: [a1, b1, aa, bb, rho, cp, scale, bneg, bpos, aob]."""
+    v = np.zeros(10)
+    load_library().cntc_gethertzcontact(ci(ire), ci(icp), ci(10), _dp(v))
+    return v
+
+
+def cntc_getsensitivities(ire=1, icp=1, lenout=4, lenin=4):
+    """python_intfc/cntc_getsensitivities.py: sens[iout, iin], outputs fn, fx, fy, mz; inputs pen, cksi, ceta, cphi."""
+    s = np.zeros(lenout * lenin)
+    load_library().cntc_getsensitivities(ci(ire), ci(icp), ci(lenout), ci(lenin), _dp(s))
+    return s.reshape(lenin, lenout).T
+
+
+def cntc_resetcalculationtime(ire=1, icp=1):
+    load_library().cntc_resetcalculationtime(ci(ire), ci(icp))
 
 
 def subs_addblock(ire, icp, iblk, isubs, xparam, yparam, zparam):

@@ -67,6 +67,8 @@ struct Problem {
     int itgs = 0;
     std::vector<int> nr_itcg;            // TangCG iterations per solver call of the Newton-Raphson process
     double fcntc[3] = { 0, 0, 0 }, mztrue = 0;
+    double sens_nr[2][2] = { { 0, 0 }, { 0, 0 } };   // d(fx, fy)/d(cksi, ceta) of the Newton-Raphson process (m_solvpt.f90:51-378)
+    int exrhs_len = 0, heat_meth = 0;                 // cntc_setextrarigidslip / cntc_settemperaturedata were called (stored, not served)
     double t_wall = 0, t_cpu = 0;
     bool solved = false;
     // subsurface blocks
@@ -552,6 +554,7 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
                 p.status = c.nrm.status; p.ittang = c.ittang; p.itgs = c.itgs; p.itout = c.itout; p.nadh = c.nadh; p.nslip = c.nslip;
                 p.nr_itcg.assign(c.nr_itcg, c.nr_itcg + std::min(c.nr_n, (int) CB_MAXNR_LOG));
                 p.gd_fallback = c.gd_fallback; p.gd_ntrial = c.gd_ntrial;
+                for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) p.sens_nr[a][b] = c.sens[a][b];
                 const double muscal = p.fstat;
                 double sx = 0, sy = 0, mz = 0;
                 for (int iy = 0; iy < p.my; iy++) for (int ix = 0; ix < p.mx; ix++) {
@@ -990,6 +993,97 @@ void cntc_getdisplacements(int *ire, int *icp, int *lenarr, double *un, double *
     f = CNTC_fld_ux; cntc_getfielddata(ire, icp, &f, lenarr, ux);
     f = CNTC_fld_uy; cntc_getfielddata(ire, icp, &f, lenarr, uy);
 }
+
+// ---- the remaining entry points of matlab_intfc/contact_addon.h:7-148, so that a caller linked against the reference's
+//      library resolves every symbol.  Module-3 getters are served from the problem's data; the entry points of the
+//      wheel/rail module (category "m=1 only" in contact_addon.f90) log an error and return, which is what the reference
+//      does when they are called on a module-3 result element (cntc_activate with the wrong module) ----
+static void module1_only(const char *name)
+{ last_error() = std::string(name) + ": available for module 1 (wheel/rail contact) only, which is outside the hot-path scope of this library"; }
+
+void cntc_getparameters(int *ire, int *icp, int *itask, int *lenarr, double *values)
+{   // contact_addon.f90:4164-4251: 1 kinematic constants used by plot3d, 2 material, 3 friction
+    int e; Problem *p = activate(*ire, *icp, &e);
+    if (!p) return;
+    const int n = *lenarr;
+    auto put = [&](int k, double v) { if (n >= k) values[k - 1] = v; };
+    if (*itask == 1) {
+        double chi, dq; roll_stepsize(*p, chi, dq);
+        put(1, p->veloc / p->scl.veloc); put(2, chi / p->scl.angle); put(3, (p->solved && p->tang >= 2 ? p->dq_eff : dq) / p->scl.len);
+        put(4, 0.0); put(5, 0.0); put(6, 0.0);                       // spin centre offsets, tau_c0: not used on this path
+    } else if (*itask == 2) {
+        Material m = p->mat; combine_material(m);
+        put(1, m.gg[0] * p->scl.area); put(2, m.gg[1] * p->scl.area); put(3, m.ga * p->scl.area);
+        put(4, m.poiss[0]); put(5, m.poiss[1]); put(6, m.nu); put(7, m.ak);
+        for (int k = 8; k <= 22; k++) put(k, 0.0);                    // flexibilities, interfacial layer, damping: M = 0 only
+    } else if (*itask == 3) {
+        put(1, 0.0); put(2, 1.0); put(3, 0.0); put(4, 0.0); put(5, 0.0); put(6, p->fstat); put(7, p->fkin);   // L = 0: one set (fstat, fkin)
+    }
+}
+
+void cntc_getreferencevelocity(int *ire, int *icp, double *veloc)
+{ int e; Problem *p = activate(*ire, *icp, &e); if (p) *veloc = p->veloc / p->scl.veloc; }
+
+void cntc_gethertzcontact(int *ire, int *icp, int *lenarr, double *values)
+{   // contact_addon.f90:5021-5063
+    int e; Problem *p = activate(*ire, *icp, &e);
+    if (!p) return;
+    const int n = *lenarr;
+    const double L = p->scl.len;
+    const double v[10] = { p->hz_a1 * L, p->hz_b1 * L, p->hz_aa / L, p->hz_bb / L, p->hz_rho / L, p->hz_cp / L, p->hz_scale,
+                           p->hz_bb / L, p->hz_bb / L, p->hz_bb > 0.0 ? p->hz_aa / p->hz_bb : 0.0 };
+    for (int k = 0; k < 10 && k < n; k++) values[k] = v[k];
+}
+
+void cntc_getmaximumtemperature(int *ire, int *icp, double *t1max, double *t2max)
+{ int e; Problem *p = activate(*ire, *icp, &e); if (p) { *t1max = 0.0; *t2max = 0.0; } }      // H = 0: no temperature calculation
+
+void cntc_getsensitivities(int *ire, int *icp, int *lenout, int *lenin, double *sens)
+{   // contact_addon.f90:5919-6040: sens(lenout, lenin), outputs fn, fx, fy, mz; inputs pen, cksi, ceta, cphi; zeros where not
+    // computed.  Filled here: d(fx, fy)/d(cksi, ceta) from the Newton-Raphson process on the creepages (F = 1, 2).
+    int e; Problem *p = activate(*ire, *icp, &e);
+    if (!p) return;
+    const int no = *lenout, ni = *lenin;
+    for (int k = 0; k < no * ni; k++) sens[k] = 0.0;
+    const double fin = (p->tang == 1) ? p->scl.len : 1.0;             // shifts: cksi, ceta are distances
+    for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++)
+        if (a + 1 < no && b + 1 < ni) sens[(a + 1) + (b + 1) * no] = p->sens_nr[a][b] * fin;
+}
+
+void cntc_resetcalculationtime(int *ire, int *icp)
+{ int e; Problem *p = activate(*ire, *icp, &e); if (p) { p->t_cpu = 0.0; p->t_wall = 0.0; } }
+
+void cntc_setextrarigidslip(int *ire, int *icp, int *lenarr, double *, double *)
+{   // E = 9 (m_sinput.f90, extra term of the rigid slip per element): accepted, refused at cntc_calculate when E-digit is set
+    int e; Problem *p = activate(*ire, *icp, &e); if (p) p->exrhs_len = *lenarr;
+}
+
+void cntc_settemperaturedata(int *ire, int *icp, int *imeth, int *, double *)
+{ int e; Problem *p = activate(*ire, *icp, &e); if (p) p->heat_meth = *imeth; }                 // H-digit: stored, H >= 1 is refused
+
+void cntc_readinpfile(int *ire, int *, const char *, int *, int *ierror)
+{   // contact_addon.f90:729-...: the .inp reader of this library is contact_b200/inp.py (parse_inp / run_inp), which drives
+    // these same entry points; there is no second reader in C++
+    (void) ire;
+    if (ierror) *ierror = CNTC_err_other;
+    last_error() = "cntc_readinpfile: use contact_b200.inp.run_inp (the .inp reader of this library drives the cntc_* entry points from Python)";
+}
+
+void cntc_setverticalforce(int *, double *) { module1_only("cntc_setverticalforce"); }
+void cntc_setprofileinputfname(int *, const char *, int *, int *, int *, int *, double *) { module1_only("cntc_setprofileinputfname"); }
+void cntc_setprofileinputvalues(int *, int *, double *, int *, int *, int *, double *) { module1_only("cntc_setprofileinputvalues"); }
+void cntc_settrackdimensions(int *, int *, int *, double *) { module1_only("cntc_settrackdimensions"); }
+void cntc_setwheelsetdimensions(int *, int *, int *, double *) { module1_only("cntc_setwheelsetdimensions"); }
+void cntc_setwheelsetposition(int *, int *, int *, double *) { module1_only("cntc_setwheelsetposition"); }
+void cntc_setwheelsetvelocity(int *, int *, int *, double *) { module1_only("cntc_setwheelsetvelocity"); }
+void cntc_setwheelsetflexibility(int *, int *, int *, double *) { module1_only("cntc_setwheelsetflexibility"); }
+void cntc_getprofilevalues(int *, int *, int *, int *, int *, double *, int *, double *) { module1_only("cntc_getprofilevalues"); }
+void cntc_getprofilevalues_new(int *, int *, int *, int *, int *, double *, int *, double *) { module1_only("cntc_getprofilevalues_new"); }
+void cntc_getwheelsetposition(int *, int *, double *) { module1_only("cntc_getwheelsetposition"); }
+void cntc_getwheelsetvelocity(int *, int *, double *) { module1_only("cntc_getwheelsetvelocity"); }
+void cntc_getnumcontactpatches(int *, int *npatch) { if (npatch) *npatch = 0; module1_only("cntc_getnumcontactpatches"); }
+void cntc_getcontactlocation(int *, int *, int *, double *) { module1_only("cntc_getcontactlocation"); }
+void cntc_getglobalforces(int *, int *, int *, double *) { module1_only("cntc_getglobalforces"); }
 
 void cntc_getcalculationtime(int *ire, int *icp, double *tcpu, double *twall)
 { int e; Problem *p = activate(*ire, *icp, &e); if (p) { *tcpu = p->t_cpu; *twall = p->t_wall; } }

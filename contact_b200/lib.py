@@ -56,6 +56,30 @@ PROTOTYPES = {
     "cntc_getcalculationtime": (None, [ip, ip, dp, dp]),
     "subs_getblocksize": (None, [ip, ip, ip, ip, ip, ip]),
     "subs_getresults": (None, [ip, ip, ip, ip, ip, ip, dp]),
+    "cntc_getparameters": (None, [ip, ip, ip, ip, dp]),
+    "cntc_getreferencevelocity": (None, [ip, ip, dp]),
+    "cntc_gethertzcontact": (None, [ip, ip, ip, dp]),
+    "cntc_getmaximumtemperature": (None, [ip, ip, dp, dp]),
+    "cntc_getsensitivities": (None, [ip, ip, ip, ip, dp]),
+    "cntc_resetcalculationtime": (None, [ip, ip]),
+    "cntc_setextrarigidslip": (None, [ip, ip, ip, dp, dp]),
+    "cntc_settemperaturedata": (None, [ip, ip, ip, ip, dp]),
+    "cntc_readinpfile": (None, [ip, ip, cp, ip, ip]),
+    "cntc_setverticalforce": (None, [ip, dp]),
+    "cntc_setprofileinputfname": (None, [ip, cp, ip, ip, ip, ip, dp]),
+    "cntc_setprofileinputvalues": (None, [ip, ip, dp, ip, ip, ip, dp]),
+    "cntc_settrackdimensions": (None, [ip, ip, ip, dp]),
+    "cntc_setwheelsetdimensions": (None, [ip, ip, ip, dp]),
+    "cntc_setwheelsetposition": (None, [ip, ip, ip, dp]),
+    "cntc_setwheelsetvelocity": (None, [ip, ip, ip, dp]),
+    "cntc_setwheelsetflexibility": (None, [ip, ip, ip, dp]),
+    "cntc_getprofilevalues": (None, [ip, ip, ip, ip, ip, dp, ip, dp]),
+    "cntc_getprofilevalues_new": (None, [ip, ip, ip, ip, ip, dp, ip, dp]),
+    "cntc_getwheelsetposition": (None, [ip, ip, dp]),
+    "cntc_getwheelsetvelocity": (None, [ip, ip, dp]),
+    "cntc_getnumcontactpatches": (None, [ip, ip]),
+    "cntc_getcontactlocation": (None, [ip, ip, ip, dp]),
+    "cntc_getglobalforces": (None, [ip, ip, ip, dp]),
     "cntc_finalize": (None, [ip]),
     "cntc_finalizelast": (None, []),
     "cntc_calculate_batch": (None, [ip, ip, ip, ip]),

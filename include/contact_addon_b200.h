@@ -106,6 +106,46 @@ void cntc_getcalculationtime(int *ire, int *icp, double *tcpu, double *twall);
 void subs_getblocksize(int *ire, int *icp, int *iblk, int *nx, int *ny, int *nz);
 /* contact_addon.f90:6113-6178 */
 void subs_getresults(int *ire, int *icp, int *iblk, int *lenarr, int *ncol, int *icol, double *values);
+/* ---- the remaining prototypes of matlab_intfc/contact_addon.h:7-148, so that a caller built against the reference's
+ *      header links unchanged.  Module-3 getters are served; the wheel/rail (module 1) entry points are outside the
+ *      hot-path scope: they record an error (cb200_last_error) and return. ---- */
+/* contact_addon.f90:4164-4251: itask 1 kinematic constants, 2 material, 3 friction */
+void cntc_getparameters(int *ire, int *icp, int *itask, int *lenarr, double *values);
+/* contact_addon.h:100 */
+void cntc_getreferencevelocity(int *ire, int *icp, double *veloc);
+/* contact_addon.f90:5021-5066: a1, b1, aa, bb, rho, cp, scale, bneg, bpos, aob */
+void cntc_gethertzcontact(int *ire, int *icp, int *lenarr, double *values);
+/* contact_addon.h:126 (H = 0 on this path: both zero) */
+void cntc_getmaximumtemperature(int *ire, int *icp, double *t1max, double *t2max);
+/* contact_addon.f90:5919-6007: sens(lenout, lenin); filled: d(fx, fy)/d(cksi, ceta) of the Newton-Raphson process */
+void cntc_getsensitivities(int *ire, int *icp, int *lenout, int *lenin, double *sens);
+/* contact_addon.h:140 */
+void cntc_resetcalculationtime(int *ire, int *icp);
+/* contact_addon.h:55 (E = 9), :31 (H-digit): stored, the digits themselves are refused at cntc_calculate */
+void cntc_setextrarigidslip(int *ire, int *icp, int *lenarr, double *wx, double *wy);
+void cntc_settemperaturedata(int *ire, int *icp, int *imeth, int *nparam, double *rparam);
+/* contact_addon.h:20: the .inp reader of this library is contact_b200/inp.py; returns CNTC_err_other */
+void cntc_readinpfile(int *ire, int *inp_type, const char *c_fname, int *len_fname, int *ierror);
+/* contact_addon.h:45-73, 86-98, 116: module 1 only */
+void cntc_setverticalforce(int *ire, double *fz);
+void cntc_setprofileinputfname(int *ire, const char *c_fname, int *len_fname, int *nints, int *iparam, int *nreals,
+                               double *rparam);
+void cntc_setprofileinputvalues(int *ire, int *npoint, double *values, int *nints, int *iparam, int *nreals,
+                                double *rparam);
+void cntc_settrackdimensions(int *ire, int *ztrack, int *nparam, double *rparam);
+void cntc_setwheelsetdimensions(int *ire, int *ewheel, int *nparam, double *rparam);
+void cntc_setwheelsetposition(int *ire, int *ewheel, int *nparam, double *rparam);
+void cntc_setwheelsetvelocity(int *ire, int *ewheel, int *nparam, double *rparam);
+void cntc_setwheelsetflexibility(int *ire, int *ewheel, int *nparam, double *rparam);
+void cntc_getprofilevalues(int *ire, int *itask, int *nints, int *iparam, int *nreals, double *rparam, int *lenarr,
+                           double *values);
+void cntc_getprofilevalues_new(int *ire, int *itask, int *nints, int *iparam, int *nreals, double *rparam, int *lenarr,
+                               double *values);
+void cntc_getwheelsetposition(int *ire, int *lenarr, double *values);
+void cntc_getwheelsetvelocity(int *ire, int *lenarr, double *values);
+void cntc_getnumcontactpatches(int *ire, int *npatch);
+void cntc_getcontactlocation(int *ire, int *icp, int *lenarr, double *values);
+void cntc_getglobalforces(int *ire, int *icp, int *lenarr, double *values);
 /* contact_addon.f90:6243 */
 void cntc_finalize(int *ire);
 void cntc_finalizelast(void);

@@ -372,6 +372,14 @@ def test_cattaneo_shift_full_case(cb, O):
     X, Y = cases.grid_xy(c["mx"], c["my"], c["xl"], c["yl"], c["dx"], c["dy"])
     assert np.hypot(X, Y)[el == 1].max() < 0.5 + 0.1 and np.hypot(X, Y)[el == 2].min() > 0.5 - 0.1
     assert np.abs(sx.ravel()[el == 1]).max() < 1e-5 * np.abs(sx).max() + 1e-12
+    # cntc_getsensitivities (contact_addon.f90:5919-6007): d fx / d cksi of the Newton-Raphson process sits at (2, 2);
+    # the tangent of the Cattaneo curve at Fx = -7/8 is flatter than its secant Fx / cksi = -107
+    sens = cb.cntc_getsensitivities(ire, icp)
+    assert sens.shape == (4, 4) and -107.0 < sens[1, 1] < -5.0 and sens[0, 0] == 0.0
+    mat = cb.cntc_getparameters(ire, icp, 2, 7)           # gg1, gg2, ga, poiss1, poiss2, nu, ak
+    assert mat[0] == c["gg"][0] and abs(mat[2] - 2.0 / (1.0 / c["gg"][0] + 1.0 / c["gg"][1])) < 1e-12 * mat[2]
+    fr = cb.cntc_getparameters(ire, icp, 3, 7)
+    assert fr[1] == 1.0 and fr[5] == 0.4 and fr[6] == 0.4
     cb.cntc_finalize(ire)
 
 
