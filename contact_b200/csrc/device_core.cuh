@@ -1,6 +1,6 @@
 // device_core.cuh -- shared-memory view, fused convolution as a device function, deterministic block reductions.
 #pragma once
-#include "fftconv.cuh"
+#include "fftconv_warp.cuh"
 
 #ifndef CB_THREADS
 #define CB_THREADS 384
@@ -68,6 +68,8 @@ __device__ __noinline__ void conv_box_dev(const ConvPlan &P, const Smem &sm, con
     const MemBuf<const cd> twy = { reinterpret_cast<const cd *>(__cvta_shared_to_generic(sm.a0 + P.off_twy)) };
     const MemBuf<const unsigned short> posx = { reinterpret_cast<const unsigned short *>(__cvta_shared_to_generic(sm.a0 + P.off_posx)) };
     const int SY = P.SY;
+#ifndef CB_WARP_CONV
+    // block-wide phase sequence (default: measured faster inside the solvers)
     RowSrc src;
     src.base = p + (size_t) y0 * stride + x0; src.kind = 0; src.mx = bw; src.my = bh; src.cmx = 0; src.cmy = 0; src.Fx = P.Fx; src.Fy = P.Fy;
     src.row0 = 0; src.stride = stride;
@@ -75,6 +77,17 @@ __device__ __noinline__ void conv_box_dev(const ConvPlan &P, const Smem &sm, con
     CB_CONV_COLUMNS_PRODUCT2(bh, bh, chat);
     CB_CONV_INVERSE_ROWS(bh);
     CB_PHASE(row_store_box(P, BUF, oS, SY, u, el, mask_mode, add, x0, y0, bw, bh, stride, tid, nthr));
+#else
+    // warp-scheduled variant (fftconv_warp.cuh, -DCB_WARP_CONV): a transform never leaves its warp, three block barriers
+    // per product; bit-identical results
+    const int warp = tid >> 5, nwarps = nthr >> 5;
+    warp_rows_fwd(P, BUF, oS, SY, p + (size_t) y0 * stride + x0, bw, bh, stride, twx, posx, warp, nwarps);
+    __syncthreads();
+    warp_cols(P, BUF, oS, oW, SY, bh, bh, chat, twy, warp, nwarps);
+    __syncthreads();
+    warp_rows_inv(P, BUF, oS, SY, u, el, mask_mode, add, x0, y0, bw, bh, stride, twx, posx, warp, nwarps);
+    __syncthreads();
+#endif
     if (tid == 0 && blockIdx.x == 0) { g_conv_prof[0] += 1; g_conv_prof[1] += (unsigned long long) (clock64() - t_in); }
 }
 

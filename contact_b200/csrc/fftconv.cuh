@@ -27,6 +27,15 @@ namespace cb200 {
 
 #define CB_MAXSTAGE 8
 
+// per-stage constants of a transform of length L at sub-length ns with radix R (host-computed: no integer divisions
+// in the device loops)
+struct StageK {
+    int m;                      // ns / R
+    int cnt;                    // L / R   (butterflies per transform)
+    int tstep;                  // (L / ns) * twmul   (twiddle index step)
+    uint32_t mg_m;              // div_magic(m)
+};
+
 struct ConvPlan {
     int mx, my, npot;
     int Fx, Fy;                 // half sizes of the padded array (opt_fft_size)
@@ -43,6 +52,13 @@ struct ConvPlan {
     const cd *twx;              // [2Fx] exp(-2 pi i k / 2Fx)
     const cd *twy;              // [2Fy] exp(-2 pi i k / 2Fy)
     const unsigned short *posx; // [Lx] position of frequency k after the DIF stages
+    // warp-scheduled product (fftconv_warp.cuh): per-stage constants and the column grouping, all from make_plan
+    StageK kx[CB_MAXSTAGE], ky[CB_MAXSTAGE];
+    int G;                      // columns per warp group (<= C)
+    int gpc;                    // groups per chunk = ceil(C / G)
+    int wslots;                 // warps that own a W slot
+    int wslot_len;              // cd elements per W slot (padded layout, ViewSk)
+    uint32_t mg_G, mg_gpc;      // division magics
 };
 
 // ---- exact division of small non-negative integers by a run-time constant: q = (n * magic) >> 32 ----
@@ -86,13 +102,12 @@ template <class B> struct ViewCrop {         // column chunk written straight ba
 // one FFT stage over a batch of transforms (in place when in and out view the same buffer).
 // INV = false: decimation in frequency (butterfly, then twiddle); INV = true: its inverse, decimation in time.
 // ------------------------------------------------------------------------------------------------------------
+// core loop with all constants supplied: items = cnt * nbatch butterflies, m = ns / R, twiddle step tstep
 template <int R, bool INV, class VI, class VO, class TW>
-CB_HD void fft_stage(VI in, VO out, int nbatch, int L, int ns, TW tw, int twmul, int tid, int nthr)
+CB_HD void fft_stage_core(VI in, VO out, int nbatch, int items, int m, int tstep, uint32_t mg_b, uint32_t mg_m, TW tw,
+                          int tid, int nthr)
 {
-    const int m = ns / R;
-    const int items = (L / R) * nbatch;
-    const int tstep = (L / ns) * twmul;
-    const uint32_t mg_b = div_magic(nbatch), mg_m = div_magic(m);
+    const int ns = m * R;
     for (int w = tid; w < items; w += nthr) {
         const uint32_t g = fdiv(w, mg_b), c = w - g * nbatch;
         const uint32_t blk = fdiv(g, mg_m), j = g - blk * m;
@@ -116,6 +131,19 @@ CB_HD void fft_stage(VI in, VO out, int nbatch, int L, int ns, TW tw, int twmul,
     }
 }
 
+template <int R, bool INV, class VI, class VO, class TW>
+CB_HD void fft_stage(VI in, VO out, int nbatch, int L, int ns, TW tw, int twmul, int tid, int nthr)
+{
+    const int m = ns / R;
+    fft_stage_core<R, INV>(in, out, nbatch, (L / R) * nbatch, m, (L / ns) * twmul, div_magic(nbatch), div_magic(m), tw,
+                           tid, nthr);
+}
+
+#ifdef CB_MAXRADIX8
+#define CB_RADIX_BIG(CALL)
+#else
+#define CB_RADIX_BIG(CALL) case 12: { CALL(12); } break; case 16: { CALL(16); } break;
+#endif
 #define CB_RADIX_SWITCH(r, CALL)          \
     switch (r) {                           \
     case 2:  { CALL(2); } break;           \
@@ -126,8 +154,7 @@ CB_HD void fft_stage(VI in, VO out, int nbatch, int L, int ns, TW tw, int twmul,
     case 7:  { CALL(7); } break;           \
     case 8:  { CALL(8); } break;           \
     case 9:  { CALL(9); } break;           \
-    case 12: { CALL(12); } break;          \
-    case 16: { CALL(16); } break;          \
+    CB_RADIX_BIG(CALL)                     \
     default: break;                        \
     }
 
@@ -142,10 +169,9 @@ CB_HD void fft_stage_r(int r, VI in, VO out, int nbatch, int L, int ns, TW tw, i
 // last forward stage (m = 1, no twiddles) + pointwise multiply with C^ + first inverse stage, in registers.
 // chat is laid out like W: [e][c] with row stride cstride.
 template <int R, class VI, class VO>
-CB_HD void fft_stage_mid(VI in, VO out, int nbatch, int L, const cd *chat, uint32_t cstride, int tid, int nthr)
+CB_HD void fft_stage_mid_core(VI in, VO out, int nbatch, int items, uint32_t mg_b, const cd *chat, uint32_t cstride,
+                              int tid, int nthr)
 {
-    const int items = (L / R) * nbatch;
-    const uint32_t mg_b = div_magic(nbatch);
     for (int w = tid; w < items; w += nthr) {
         const uint32_t g = fdiv(w, mg_b), c = w - g * nbatch;
         const uint32_t e0 = g * R;
@@ -169,10 +195,34 @@ CB_HD void fft_stage_mid(VI in, VO out, int nbatch, int L, const cd *chat, uint3
     }
 }
 
+template <int R, class VI, class VO>
+CB_HD void fft_stage_mid(VI in, VO out, int nbatch, int L, const cd *chat, uint32_t cstride, int tid, int nthr)
+{
+    fft_stage_mid_core<R>(in, out, nbatch, (L / R) * nbatch, div_magic(nbatch), chat, cstride, tid, nthr);
+}
+
 template <class VI, class VO>
 CB_HD void fft_stage_mid_r(int r, VI in, VO out, int nbatch, int L, const cd *chat, uint32_t cstride, int tid, int nthr)
 {
 #define CB_CALL_(RR) fft_stage_mid<RR>(in, out, nbatch, L, chat, cstride, tid, nthr)
+    CB_RADIX_SWITCH(r, CB_CALL_)
+#undef CB_CALL_
+}
+
+// the same stages with the per-stage constants of the plan (StageK) and a ready-made magic for nbatch
+template <bool INV, class VI, class VO, class TW>
+CB_HD void fft_stage_k(int r, VI in, VO out, int nbatch, uint32_t mg_b, const StageK &k, TW tw, int tid, int nthr)
+{
+#define CB_CALL_(RR) fft_stage_core<RR, INV>(in, out, nbatch, k.cnt * nbatch, k.m, k.tstep, mg_b, k.mg_m, tw, tid, nthr)
+    CB_RADIX_SWITCH(r, CB_CALL_)
+#undef CB_CALL_
+}
+
+template <class VI, class VO>
+CB_HD void fft_stage_mid_k(int r, VI in, VO out, int nbatch, uint32_t mg_b, const StageK &k, const cd *chat,
+                           uint32_t cstride, int tid, int nthr)
+{
+#define CB_CALL_(RR) fft_stage_mid_core<RR>(in, out, nbatch, k.cnt * nbatch, mg_b, chat, cstride, tid, nthr)
     CB_RADIX_SWITCH(r, CB_CALL_)
 #undef CB_CALL_
 }

@@ -10,6 +10,7 @@
 namespace cb200 {
 
 static const int kSmemMax = 232448;      // 227 KB opt-in maximum per CTA on sm_100
+static const int kPlanWarps = 12;        // warps per CTA the plans are laid out for (CB_THREADS / 32)
 
 inline int opt_fft_size(int n)
 {
@@ -51,6 +52,10 @@ inline bool choose_radices(int L, int *nst, int *rad)
     // over shared memory), largest radix first (the last forward stage is fused with the multiply and the
     // first inverse stage, so it should be a mid-size radix)
     int k = 0;
+#ifdef CB_MAXRADIX8
+    // experiment: radices <= 9 only (smaller register footprint per butterfly => more warps per SM)
+    while (a >= 3) { rad[k++] = 8; a -= 3; }
+#endif
     while (a >= 2 && b >= 1 && (a + b > 3 || c + d > 0 || a == 2)) { rad[k++] = 12; a -= 2; b -= 1; if (a < 2 || b < 1) break; }
     while (a >= 4) { rad[k++] = 16; a -= 4; }
     if (a == 3) { rad[k++] = 8; a = 0; }
@@ -121,9 +126,29 @@ inline bool make_plan(int mx, int my, HostPlan &hp, int smem_limit = kSmemMax)
     P.nchunk = (ncol + C - 1) / C;
     P.C = (ncol + P.nchunk - 1) / P.nchunk;
     P.chat_len = P.nchunk * P.Ly * P.C;
+    // per-stage constants (twiddle tables: twx has 2Fx entries for transforms of length Fx => index step x2)
+    for (int s = 0, ns = P.Lx; s < P.nsx; ns /= P.rx[s], s++) {
+        StageK &k = P.kx[s];
+        k.m = ns / P.rx[s]; k.cnt = P.Lx / P.rx[s]; k.tstep = (P.Lx / ns) * 2; k.mg_m = div_magic((uint32_t) k.m);
+    }
+    for (int s = 0, ns = P.Ly; s < P.nsy; ns /= P.ry[s], s++) {
+        StageK &k = P.ky[s];
+        k.m = ns / P.ry[s]; k.cnt = P.Ly / P.ry[s]; k.tstep = P.Ly / ns; k.mg_m = div_magic((uint32_t) k.m);
+    }
+    // warp-scheduled column pass: every warp owns a W slot for G columns (padded layout: one spare element per 8);
+    // the W region is the larger of the block-wide chunk and the warp slots
+    const int nwarp = kPlanWarps;
+    int G = P.C / nwarp; if (G > 4) G = 4; if (G < 1) G = 1;
+    int slot = P.Ly * G + (P.Ly * G) / 8 + 1;
+    int wslots = (int) ((avail / 16) / slot); if (wslots > nwarp) wslots = nwarp; if (wslots > (P.C + G - 1) / G * P.nchunk) wslots = (P.C + G - 1) / G * P.nchunk;
+    if (wslots < 1) { wslots = 1; if (hp.fits && (long) slot * 16 > avail) hp.fits = false; }
+    P.G = G; P.gpc = (P.C + G - 1) / G; P.wslots = wslots; P.wslot_len = slot;
+    P.mg_G = div_magic((uint32_t) G); P.mg_gpc = div_magic((uint32_t) P.gpc);
+    long bytesW = (long) P.Ly * P.C * 16;
+    if ((long) wslots * slot * 16 > bytesW) bytesW = (long) wslots * slot * 16;
     P.off_S = 0;
     P.off_W = (int) bytesS;
-    P.off_twx = P.off_W + P.Ly * P.C * 16;
+    P.off_twx = P.off_W + (int) bytesW;
     P.off_twy = P.off_twx + 2 * P.Fx * 16;
     P.off_posx = P.off_twy + 2 * P.Fy * 16;
     P.off_red = P.off_posx + ((P.Lx * 2 + 15) / 16) * 16;

@@ -4,6 +4,7 @@
 #include <vector>
 #include <cstdio>
 #include "../../contact_b200/csrc/plan.h"
+#include "../../contact_b200/csrc/fftconv_warp.cuh"
 
 using namespace cb200;
 
@@ -21,8 +22,8 @@ extern "C" int emul_plan_info(int mx, int my, int *out)
 }
 
 // u = mask (.) conv(cf block, p) * scale ; cf block has half sizes (cmx, cmy)
-extern "C" int emul_conv(int mx, int my, const double *p, const double *cfblk, int cmx, int cmy, double scale,
-                         const int *el, int mask_mode, int add, double *u, int nthr)
+static int emul_conv_impl(int mx, int my, const double *p, const double *cfblk, int cmx, int cmy, double scale,
+                          const int *el, int mask_mode, int add, double *u, int nthr, int warp_sched)
 {
     HostPlan hp;
     if (!make_plan(mx, my, hp)) return -1;
@@ -45,10 +46,18 @@ extern "C" int emul_conv(int mx, int my, const double *p, const double *cfblk, i
     // --- the product
     {
         const int SY = P.SY;
-        std::vector<cd> SW((size_t) (P.Lx + 1) * SY + (size_t) P.Ly * P.C);
+        std::vector<cd> SW((size_t) (P.off_twx / 16) + 16);        // S | W exactly as laid out in shared memory
         typedef MemBuf<cd> CB_BUF;
         const CB_BUF BUF = { SW.data() };
-        const uint32_t oS = 0u, oW = (uint32_t) (P.Lx + 1) * SY;
+        const uint32_t oS = 0u, oW = (uint32_t) (P.off_W / 16);
+        if (warp_sched) {
+            // the warp-scheduled product (fftconv_warp.cuh): one call per warp and pass, lanes looped inside
+            const int nwarps = nthr / 32 > 0 ? nthr / 32 : 1;
+            for (int w = 0; w < nwarps; w++) warp_rows_fwd(P, BUF, oS, SY, p, mx, my, mx, twx, posx, w, nwarps);
+            for (int w = 0; w < nwarps; w++) warp_cols(P, BUF, oS, oW, SY, my, my, chat.data(), twy, w, nwarps);
+            for (int w = 0; w < nwarps; w++) warp_rows_inv(P, BUF, oS, SY, u, el, mask_mode, add, 0, 0, mx, my, mx, twx, posx, w, nwarps);
+            return 0;
+        }
         RowSrc src = { p, 0, mx, my, 0, 0, P.Fx, P.Fy, 0 };
         CB_CONV_FORWARD_ROWS(P.my, src);
         CB_CONV_COLUMNS_PRODUCT(P.my, chat.data());
@@ -57,6 +66,15 @@ extern "C" int emul_conv(int mx, int my, const double *p, const double *cfblk, i
     }
     return 0;
 }
+
+extern "C" int emul_conv(int mx, int my, const double *p, const double *cfblk, int cmx, int cmy, double scale,
+                         const int *el, int mask_mode, int add, double *u, int nthr)
+{ return emul_conv_impl(mx, my, p, cfblk, cmx, cmy, scale, el, mask_mode, add, u, nthr, 0); }
+
+// the same product through the warp-scheduled passes with nthr/32 warps
+extern "C" int emul_conv_warp(int mx, int my, const double *p, const double *cfblk, int cmx, int cmy, double scale,
+                              const int *el, int mask_mode, int add, double *u, int nthr)
+{ return emul_conv_impl(mx, my, p, cfblk, cmx, cmy, scale, el, mask_mode, add, u, nthr, 1); }
 
 // radix butterflies against a naive DFT
 extern "C" double emul_radix_error(int R, int inv)

@@ -24,7 +24,7 @@ def emul():
     if not os.path.exists(nvcc):
         pytest.skip("nvcc not available")
     os.makedirs(os.path.dirname(SO), exist_ok=True)
-    deps = [SRC] + [os.path.join(ROOT, "contact_b200", "csrc", f) for f in ("fftconv.cuh", "fft_radix.cuh", "plan.h", "conv_sequence.inc")]
+    deps = [SRC] + [os.path.join(ROOT, "contact_b200", "csrc", f) for f in ("fftconv.cuh", "fftconv_warp.cuh", "fft_radix.cuh", "plan.h", "conv_sequence.inc")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call([nvcc, "-O1", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-Wno-deprecated-gpu-targets",
                                "-o", SO, SRC])
@@ -63,6 +63,13 @@ def test_emulated_product_matches_direct_sum(emul, mx, my):
         sel = np.ones(npot, bool) if mask_mode == 0 else el > 0
         exp[sel] = ud[2][sel] + (7.0 if add else 0.0)
         assert np.abs(ue - exp).max() < 1e-13 * max(1.0, np.abs(ud[2]).max()) + 1e-12
+        # the warp-scheduled passes (fftconv_warp.cuh, what the device runs) regroup the same butterflies: bit-identical
+        for nthr in (384, 64):
+            uw = np.full(npot, 7.0)
+            rc = emul.emul_conv_warp(mx, my, pz.ctypes.data_as(dp), blk.ctypes.data_as(dp), mx, my, C.c_double(cs.ga_inv),
+                                     el.ctypes.data_as(ip), mask_mode, add, uw.ctypes.data_as(dp), nthr)
+            assert rc == 0
+            assert np.array_equal(uw, ue)
     O.inflcf_free(cs, cv, csv, ms)
 
 

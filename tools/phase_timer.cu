@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <vector>
 #include "../contact_b200/csrc/plan.h"
+#include "../contact_b200/csrc/fftconv_warp.cuh"
 using namespace cb200;
 
 #ifndef CB_THREADS
@@ -37,10 +38,18 @@ k_prof(ConvPlan P, const double *p, const cd *chat, double *u, int ncase)
         np_ = 0;
         if (tid == 0 && blockIdx.x == 0) tt_[np_++] = clock64();
         RowSrc src; src.base = p + (size_t) ic * P.npot; src.kind = 0; src.mx = P.mx; src.my = P.my; src.cmx = 0; src.cmy = 0; src.Fx = P.Fx; src.Fy = P.Fy; src.row0 = 0; src.stride = 0;
+#ifdef PT_WARP
+        // warp-scheduled product (fftconv_warp.cuh): three passes, one barrier after each
+        const int warp = tid >> 5, nwarps = nthr >> 5;
+        CB_PHASE(warp_rows_fwd(P, BUF, oS, SY, src.base, P.mx, P.my, P.mx, twx, posx, warp, nwarps));
+        CB_PHASE(warp_cols(P, BUF, oS, oW, SY, P.my, P.my, chat, twy, warp, nwarps));
+        CB_PHASE(warp_rows_inv(P, BUF, oS, SY, u + (size_t) ic * P.npot, (const int *) nullptr, 0, 0, 0, 0, P.mx, P.my, P.mx, twx, posx, warp, nwarps));
+#else
         CB_CONV_FORWARD_ROWS(P.my, src);
         CB_CONV_COLUMNS_PRODUCT(P.my, chat);
         CB_CONV_INVERSE_ROWS(P.my);
         CB_PHASE(row_store(P, BUF, oS, SY, u + (size_t) ic * P.npot, (const int *) nullptr, 0, 0, tid, nthr));
+#endif
     }
     if (tid == 0 && blockIdx.x == 0) { for (int i = 0; i < np_; i++) g_t[i] = tt_[i]; g_n = np_; }
 }
@@ -61,6 +70,17 @@ int main(int argc, char **argv)
     cudaFuncSetAttribute(k_prof, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
     for (int rep = 0; rep < 2; rep++) k_prof<<<ncase < 148 ? ncase : 148, CB_THREADS, P.smem_bytes>>>(P, p, chat, u, ncase);
     cudaError_t e = cudaDeviceSynchronize();
+    {   // whole-kernel time per product (all CTAs busy), CUDA events
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        const int big = 148 * 8;
+        double *pb, *ub; cudaMalloc(&pb, 8L * big * P.npot); cudaMalloc(&ub, 8L * big * P.npot); cudaMemset(pb, 0, 8L * big * P.npot);
+        k_prof<<<148, CB_THREADS, P.smem_bytes>>>(P, pb, chat, ub, big);
+        cudaEventRecord(e0);
+        k_prof<<<148, CB_THREADS, P.smem_bytes>>>(P, pb, chat, ub, big);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        printf("kernel: %d products in %.3f ms = %.2f us per product per SM\n", big, ms, 1e3 * ms / 8);
+    }
     printf("status %s; plan Fx %d Fy %d C %d nchunk %d rx", cudaGetErrorString(e), P.Fx, P.Fy, P.C, P.nchunk);
     for (int i = 0; i < P.nsx; i++) printf(" %d", P.rx[i]);
     printf(" ry");
