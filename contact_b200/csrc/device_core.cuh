@@ -75,8 +75,7 @@ __device__ __noinline__ void conv_box_dev(const ConvPlan &P, const Smem &sm, con
     src.row0 = 0; src.stride = stride;
     CB_CONV_FORWARD_ROWS(bh, src);
     CB_CONV_COLUMNS_PRODUCT2(bh, bh, chat);
-    CB_CONV_INVERSE_ROWS(bh);
-    CB_PHASE(row_store_box(P, BUF, oS, SY, u, el, mask_mode, add, x0, y0, bw, bh, stride, tid, nthr));
+    CB_CONV_INVERSE_ROWS_STORE(bh, u, el, mask_mode, add, x0, y0, bw, stride);
 #else
     // warp-scheduled variant (fftconv_warp.cuh, -DCB_WARP_CONV): a transform never leaves its warp, three block barriers
     // per product; bit-identical results

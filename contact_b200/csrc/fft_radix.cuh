@@ -199,4 +199,80 @@ template <bool INV> struct Dft<12, INV> {
     }
 };
 
+// ---- input-pruned butterflies: the upper half of the inputs x[R/2 .. R-1] is known to be zero (first stage of a
+// zero-padded transform: the tractions fill at most half of the padded array, m_aijpj.f90:932-939).  Same operations as
+// Dft<R> on the non-zero terms, the additions of zeros left out => identical results (up to the sign of a zero).
+template <bool INV> CB_HD void dft4_ab00(cd a, cd b, cd *t)
+{
+    const cd s3 = mul_mi<INV>(b);
+    t[0] = cadd(a, b); t[2] = csub(a, b); t[1] = cadd(a, s3); t[3] = csub(a, s3);
+}
+
+template <int R, bool INV> struct DftHalfIn { static const bool ok = false; static CB_HD void run(cd *x) { Dft<R, INV>::run(x); } };
+
+template <bool INV> struct DftHalfIn<4, INV> {
+    static const bool ok = true;
+    static CB_HD void run(cd *x) { cd t[4]; dft4_ab00<INV>(x[0], x[1], t); x[0] = t[0]; x[1] = t[1]; x[2] = t[2]; x[3] = t[3]; }
+};
+
+template <bool INV> struct DftHalfIn<8, INV> {
+    static const bool ok = true;
+    static CB_HD void run(cd *x) {
+        const double h = 0.70710678118654752440;
+        cd e[4], o[4];
+        dft4_ab00<INV>(x[0], x[2], e); dft4_ab00<INV>(x[1], x[3], o);
+        cd o1 = INV ? make_double2(h * (o[1].x - o[1].y), h * (o[1].x + o[1].y))
+                    : make_double2(h * (o[1].x + o[1].y), h * (o[1].y - o[1].x));
+        cd o2 = mul_mi<INV>(o[2]);
+        cd o3 = INV ? make_double2(-h * (o[3].x + o[3].y), h * (o[3].x - o[3].y))
+                    : make_double2(h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y));
+        x[0] = cadd(e[0], o[0]); x[4] = csub(e[0], o[0]);
+        x[1] = cadd(e[1], o1);   x[5] = csub(e[1], o1);
+        x[2] = cadd(e[2], o2);   x[6] = csub(e[2], o2);
+        x[3] = cadd(e[3], o3);   x[7] = csub(e[3], o3);
+    }
+};
+
+template <bool INV> struct DftHalfIn<12, INV> {
+    static const bool ok = true;
+    static CB_HD void run(cd *x) {
+        const double g = INV ? 1.0 : -1.0;
+        const double c30 = 0.86602540378443864676;
+        cd y[3][4];
+#pragma unroll
+        for (int n2 = 0; n2 < 3; n2++) dft4_ab00<INV>(x[n2], x[3 + n2], y[n2]);
+        const cd w1 = make_double2(c30, g * 0.5), w2 = make_double2(0.5, g * c30), w4 = make_double2(-0.5, g * c30);
+        y[1][1] = cmul(y[1][1], w1); y[1][2] = cmul(y[1][2], w2); y[1][3] = mul_mi<INV>(y[1][3]);
+        y[2][1] = cmul(y[2][1], w2); y[2][2] = cmul(y[2][2], w4); y[2][3] = make_double2(-y[2][3].x, -y[2][3].y);
+#pragma unroll
+        for (int k1 = 0; k1 < 4; k1++) {
+            cd t[3] = { y[0][k1], y[1][k1], y[2][k1] };
+            Dft<3, INV>::run(t);
+            x[k1] = t[0]; x[k1 + 4] = t[1]; x[k1 + 8] = t[2];
+        }
+    }
+};
+
+template <bool INV> struct DftHalfIn<16, INV> {
+    static const bool ok = true;
+    static CB_HD void run(cd *x) {
+        const double g = INV ? 1.0 : -1.0;
+        const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173, h = 0.70710678118654752440;
+        cd y[4][4];
+#pragma unroll
+        for (int n2 = 0; n2 < 4; n2++) dft4_ab00<INV>(x[n2], x[4 + n2], y[n2]);
+        const cd w1 = make_double2(c1, g * s1), w2 = make_double2(h, g * h), w3 = make_double2(s1, g * c1);
+        const cd w6 = make_double2(-h, g * h), w9 = make_double2(-c1, -g * s1);
+        y[1][1] = cmul(y[1][1], w1); y[1][2] = cmul(y[1][2], w2); y[1][3] = cmul(y[1][3], w3);
+        y[2][1] = cmul(y[2][1], w2); y[2][2] = mul_mi<INV>(y[2][2]); y[2][3] = cmul(y[2][3], w6);
+        y[3][1] = cmul(y[3][1], w3); y[3][2] = cmul(y[3][2], w6); y[3][3] = cmul(y[3][3], w9);
+#pragma unroll
+        for (int k1 = 0; k1 < 4; k1++) {
+            cd t[4] = { y[0][k1], y[1][k1], y[2][k1], y[3][k1] };
+            Dft<4, INV>::run(t);
+            x[k1] = t[0]; x[k1 + 4] = t[1]; x[k1 + 8] = t[2]; x[k1 + 12] = t[3];
+        }
+    }
+};
+
 }  // namespace cb200

@@ -258,7 +258,9 @@ CB_HD double rowsrc_get(const RowSrc &s, int row, int col)
 // The source lives in global memory: the loads of CB_RLB items are issued back to back before the first store, so a
 // thread has CB_RLB loads in flight instead of one (the loop was bound by the L2/HBM latency: 9.6k of the 88k cycles of
 // a 91x91 product, tools/phase_timer.cu).
+#ifndef CB_RLB
 #define CB_RLB 8
+#endif
 template <class B>
 CB_HD void row_load(const ConvPlan &P, B buf, uint32_t oS, int SY, int nbatch, const RowSrc &src, int tid, int nthr)
 {
@@ -286,30 +288,153 @@ CB_HD void row_load(const ConvPlan &P, B buf, uint32_t oS, int SY, int nbatch, c
     }
 }
 
+// ---- fused row passes ----
+// The tractions fill at most the lower half of a padded row (mx <= Fx), so in the first DIF stage of the packed row
+// transform the inputs x[R/2..R-1] of every butterfly are zero, and of the last DIT stage of the inverse only the outputs
+// x[R/2..R-1] (columns Fx..2Fx-1) are read.  For an even first radix the staging pass through S (row_load) and the separate
+// store pass (row_store_box) therefore merge with those stages: the butterfly reads its R/2 non-zero inputs straight from
+// the traction row and writes its R/2 wanted outputs straight to u.  Items run with the column index j fastest, so global
+// accesses are contiguous per row.  Same operations on the non-zero terms => same results as the unfused passes.
+CB_HD bool rows_fusable(const ConvPlan &P)
+{
+    const int r = P.nsx > 0 ? P.rx[0] : 0;
+    return r == 4 || r == 8 || r == 12 || r == 16;
+}
+
+template <int R, class B, class TW>
+CB_HD void row_first_stage(const ConvPlan &P, B buf, uint32_t oS, int SY, int nbatch, const RowSrc &src, TW tw,
+                           int tid, int nthr)
+{
+    const StageK &k = P.kx[0];
+    const int m = k.m, items = m * nbatch;
+    const int rs = src.stride ? src.stride : src.mx;
+    for (int w = tid; w < items; w += nthr) {
+        const uint32_t b = fdiv(w, k.mg_m), j = w - b * m;
+        const double *row = src.base + (size_t) b * rs;
+        cd x[R];
+#pragma unroll
+        for (int q = 0; q < R / 2; q++) {
+            const int col = 2 * (int) (j + q * m);
+            x[q] = make_double2(col < src.mx ? row[col] : 0.0, col + 1 < src.mx ? row[col + 1] : 0.0);
+        }
+        DftHalfIn<R, false>::run(x);
+        if (m > 1) {
+            const int t = k.tstep * j;
+#pragma unroll
+            for (int q = 1; q < R; q++) x[q] = cmul(x[q], tw.ld(t * q));
+        }
+#pragma unroll
+        for (int q = 0; q < R; q++) buf.st(oS + (j + q * m) * SY + b, x[q]);
+    }
+}
+
+template <class B, class TW>
+CB_HD void row_first_stage_r(const ConvPlan &P, B buf, uint32_t oS, int SY, int nbatch, const RowSrc &src, TW tw,
+                             int tid, int nthr)
+{
+    switch (P.rx[0]) {
+    case 4:  row_first_stage<4>(P, buf, oS, SY, nbatch, src, tw, tid, nthr); break;
+    case 8:  row_first_stage<8>(P, buf, oS, SY, nbatch, src, tw, tid, nthr); break;
+#ifndef CB_MAXRADIX8
+    case 12: row_first_stage<12>(P, buf, oS, SY, nbatch, src, tw, tid, nthr); break;
+    case 16: row_first_stage<16>(P, buf, oS, SY, nbatch, src, tw, tid, nthr); break;
+#endif
+    default: break;
+    }
+}
+
+// last DIT stage of the inverse row transforms + masked store of the box (x0, y0, bw x nbatch) of u (row stride `stride`);
+// semantics of row_store_box
+template <int R, class B, class TW>
+CB_HD void row_last_stage_store(const ConvPlan &P, B buf, uint32_t oS, int SY, int nbatch, TW tw, double *u, const int *el,
+                                int mask_mode, int add, int x0, int y0, int bw, int stride, int tid, int nthr)
+{
+    const StageK &k = P.kx[0];
+    const int m = k.m, items = m * nbatch;
+    for (int w = tid; w < items; w += nthr) {
+        const uint32_t b = fdiv(w, k.mg_m), j = w - b * m;
+        cd x[R];
+#pragma unroll
+        for (int q = 0; q < R; q++) x[q] = buf.ld(oS + (j + q * m) * SY + b);
+        if (m > 1) {
+            const int t = k.tstep * j;
+#pragma unroll
+            for (int q = 1; q < R; q++) x[q] = cmulc(x[q], tw.ld(t * q));
+        }
+        Dft<R, true>::run(x);
+        const size_t r0 = (size_t) (y0 + b) * stride + x0;
+#pragma unroll
+        for (int q = R / 2; q < R; q++) {
+            const int ix = 2 * (int) (j + q * m) - P.Fx;           // real column 2e -> grid column ix (Fx is even here)
+            if (ix < bw && !(mask_mode == 1 && el[r0 + ix] < 1)) u[r0 + ix] = add ? u[r0 + ix] + x[q].x : x[q].x;
+            if (ix + 1 < bw && !(mask_mode == 1 && el[r0 + ix + 1] < 1)) u[r0 + ix + 1] = add ? u[r0 + ix + 1] + x[q].y : x[q].y;
+        }
+    }
+}
+
+template <class B, class TW>
+CB_HD void row_last_stage_store_r(const ConvPlan &P, B buf, uint32_t oS, int SY, int nbatch, TW tw, double *u, const int *el,
+                                  int mask_mode, int add, int x0, int y0, int bw, int stride, int tid, int nthr)
+{
+    switch (P.rx[0]) {
+    case 4:  row_last_stage_store<4>(P, buf, oS, SY, nbatch, tw, u, el, mask_mode, add, x0, y0, bw, stride, tid, nthr); break;
+    case 8:  row_last_stage_store<8>(P, buf, oS, SY, nbatch, tw, u, el, mask_mode, add, x0, y0, bw, stride, tid, nthr); break;
+#ifndef CB_MAXRADIX8
+    case 12: row_last_stage_store<12>(P, buf, oS, SY, nbatch, tw, u, el, mask_mode, add, x0, y0, bw, stride, tid, nthr); break;
+    case 16: row_last_stage_store<16>(P, buf, oS, SY, nbatch, tw, u, el, mask_mode, add, x0, y0, bw, stride, tid, nthr); break;
+#endif
+    default: break;
+    }
+}
+
 // split step of the packed real transform: Z (scrambled) -> X[k], k = 0..Lx, X[k] at row posx[k] (k<Lx), X[Lx] at row Lx
+// items per thread whose loads are issued together in the split / merge steps (measured on B200: 1 is best -- with 4 or
+// 8 the index arrays go to local memory and the step gets 4x slower, gpurun_out/pt_w5: 3.5k -> 14.6k cycles)
+#ifndef CB_SMB
+#define CB_SMB 1
+#endif
 template <class B, class TW, class PX>
 CB_HD void row_split(const ConvPlan &P, B buf, uint32_t oS, int SY, int nbatch, TW twx, PX posx, int tid, int nthr)
 {
-    const int L = P.Lx, npair = L / 2 + 1;
+    const int L = P.Lx;
+    // k = 0 (-> X[0], X[L]) and the self-paired k = L/2
+    for (int b = tid; b < nbatch; b += nthr) {
+        cd a = buf.ld(oS + b);
+        buf.st(oS + b, make_double2(a.x + a.y, 0.0));
+        buf.st(oS + (uint32_t) L * SY + b, make_double2(a.x - a.y, 0.0));
+        if (L > 1 && (L & 1) == 0) {
+            const uint32_t ia = oS + (uint32_t) posx.ld(L / 2) * SY + b;
+            buf.st(ia, cconj(buf.ld(ia)));
+        }
+    }
+    // pairs (k, L-k), k = 1 .. (L-1)/2: the loads of CB_SMB items are issued before the first store
+    const int npair = (L - 1) / 2;
     const int items = npair * nbatch;
     const uint32_t mg = div_magic(nbatch);
-    for (int w = tid; w < items; w += nthr) {
-        const uint32_t k = fdiv(w, mg), b = w - k * nbatch;
-        if (k == 0) {
-            cd a = buf.ld(oS + b);
-            buf.st(oS + b, make_double2(a.x + a.y, 0.0));
-            buf.st(oS + (uint32_t) L * SY + b, make_double2(a.x - a.y, 0.0));
-        } else if (2 * (int) k == L) {
-            const uint32_t ia = oS + (uint32_t) posx.ld(k) * SY + b;
-            buf.st(ia, cconj(buf.ld(ia)));
-        } else {
-            const uint32_t ia = oS + (uint32_t) posx.ld(k) * SY + b, ib = oS + (uint32_t) posx.ld(L - k) * SY + b;
-            cd a = buf.ld(ia), bb = buf.ld(ib);
-            cd e = make_double2(0.5 * (a.x + bb.x), 0.5 * (a.y - bb.y));          // (a + conj b)/2
-            cd d = make_double2(0.5 * (a.x - bb.x), 0.5 * (a.y + bb.y));          // (a - conj b)/2
-            cd t = cmul(twx.ld(k), make_double2(d.y, -d.x));                     // w^k * (-i) d
-            buf.st(ia, cadd(e, t));
-            buf.st(ib, cconj(csub(e, t)));
+    for (int w0 = tid; w0 < items; w0 += CB_SMB * nthr) {
+        cd a[CB_SMB], bb[CB_SMB], tw[CB_SMB];
+        uint32_t ia[CB_SMB], ib[CB_SMB];
+#pragma unroll
+        for (int i = 0; i < CB_SMB; i++) {
+            const int w = w0 + i * nthr;
+            if (w < items) {
+                const uint32_t k = fdiv(w, mg) + 1, b = w - (k - 1) * nbatch;
+                ia[i] = oS + (uint32_t) posx.ld(k) * SY + b; ib[i] = oS + (uint32_t) posx.ld(L - k) * SY + b;
+                tw[i] = twx.ld(k);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < CB_SMB; i++)
+            if (w0 + i * nthr < items) { a[i] = buf.ld(ia[i]); bb[i] = buf.ld(ib[i]); }
+#pragma unroll
+        for (int i = 0; i < CB_SMB; i++) {
+            if (w0 + i * nthr < items) {
+                cd e = make_double2(0.5 * (a[i].x + bb[i].x), 0.5 * (a[i].y - bb[i].y));          // (a + conj b)/2
+                cd d = make_double2(0.5 * (a[i].x - bb[i].x), 0.5 * (a[i].y + bb[i].y));          // (a - conj b)/2
+                cd t = cmul(tw[i], make_double2(d.y, -d.x));                                 // w^k * (-i) d
+                buf.st(ia[i], cadd(e, t));
+                buf.st(ib[i], cconj(csub(e, t)));
+            }
         }
     }
 }
@@ -318,27 +443,44 @@ CB_HD void row_split(const ConvPlan &P, B buf, uint32_t oS, int SY, int nbatch, 
 template <class B, class TW, class PX>
 CB_HD void row_merge(const ConvPlan &P, B buf, uint32_t oS, int SY, int nbatch, TW twx, PX posx, int tid, int nthr)
 {
-    const int L = P.Lx, npair = L / 2 + 1;
-    const int items = npair * nbatch;
-    const uint32_t mg = div_magic(nbatch);
-    for (int w = tid; w < items; w += nthr) {
-        const uint32_t k = fdiv(w, mg), b = w - k * nbatch;
-        if (k == 0) {
-            cd p = buf.ld(oS + b), q = buf.ld(oS + (uint32_t) L * SY + b);
-            cd u = make_double2(p.x + q.x, p.y - q.y), d = make_double2(p.x - q.x, p.y + q.y);
-            buf.st(oS + b, make_double2(u.x - d.y, u.y + d.x));                  // u + i d
-        } else if (2 * (int) k == L) {
-            const uint32_t ia = oS + (uint32_t) posx.ld(k) * SY + b;
+    const int L = P.Lx;
+    for (int b = tid; b < nbatch; b += nthr) {
+        cd p = buf.ld(oS + b), q = buf.ld(oS + (uint32_t) L * SY + b);
+        cd u = make_double2(p.x + q.x, p.y - q.y), d = make_double2(p.x - q.x, p.y + q.y);
+        buf.st(oS + b, make_double2(u.x - d.y, u.y + d.x));                      // u + i d
+        if (L > 1 && (L & 1) == 0) {
+            const uint32_t ia = oS + (uint32_t) posx.ld(L / 2) * SY + b;
             cd a = buf.ld(ia);
             buf.st(ia, make_double2(2.0 * a.x, -2.0 * a.y));
-        } else {
-            const uint32_t ia = oS + (uint32_t) posx.ld(k) * SY + b, ib = oS + (uint32_t) posx.ld(L - k) * SY + b;
-            cd p = buf.ld(ia), q = buf.ld(ib);
-            cd u = make_double2(p.x + q.x, p.y - q.y);                           // p + conj q
-            cd d = make_double2(p.x - q.x, p.y + q.y);                           // p - conj q
-            cd v = cmulc(make_double2(-d.y, d.x), twx.ld(k));                    // i d conj(w^k)
-            buf.st(ia, cadd(u, v));
-            buf.st(ib, cconj(csub(u, v)));
+        }
+    }
+    const int npair = (L - 1) / 2;
+    const int items = npair * nbatch;
+    const uint32_t mg = div_magic(nbatch);
+    for (int w0 = tid; w0 < items; w0 += CB_SMB * nthr) {
+        cd p[CB_SMB], q[CB_SMB], tw[CB_SMB];
+        uint32_t ia[CB_SMB], ib[CB_SMB];
+#pragma unroll
+        for (int i = 0; i < CB_SMB; i++) {
+            const int w = w0 + i * nthr;
+            if (w < items) {
+                const uint32_t k = fdiv(w, mg) + 1, b = w - (k - 1) * nbatch;
+                ia[i] = oS + (uint32_t) posx.ld(k) * SY + b; ib[i] = oS + (uint32_t) posx.ld(L - k) * SY + b;
+                tw[i] = twx.ld(k);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < CB_SMB; i++)
+            if (w0 + i * nthr < items) { p[i] = buf.ld(ia[i]); q[i] = buf.ld(ib[i]); }
+#pragma unroll
+        for (int i = 0; i < CB_SMB; i++) {
+            if (w0 + i * nthr < items) {
+                cd u = make_double2(p[i].x + q[i].x, p[i].y - q[i].y);                       // p + conj q
+                cd d = make_double2(p[i].x - q[i].x, p[i].y + q[i].y);                       // p - conj q
+                cd v = cmulc(make_double2(-d.y, d.x), tw[i]);                            // i d conj(w^k)
+                buf.st(ia[i], cadd(u, v));
+                buf.st(ib[i], cconj(csub(u, v)));
+            }
         }
     }
 }

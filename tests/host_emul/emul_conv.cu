@@ -61,8 +61,7 @@ static int emul_conv_impl(int mx, int my, const double *p, const double *cfblk, 
         RowSrc src = { p, 0, mx, my, 0, 0, P.Fx, P.Fy, 0 };
         CB_CONV_FORWARD_ROWS(P.my, src);
         CB_CONV_COLUMNS_PRODUCT(P.my, chat.data());
-        CB_CONV_INVERSE_ROWS(P.my);
-        CB_PHASE(row_store(P, BUF, oS, SY, u, el, mask_mode, add, tid, nthr));
+        CB_CONV_INVERSE_ROWS_STORE(P.my, u, el, mask_mode, add, 0, 0, mx, mx);
     }
     return 0;
 }

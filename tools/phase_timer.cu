@@ -47,8 +47,7 @@ k_prof(ConvPlan P, const double *p, const cd *chat, double *u, int ncase)
 #else
         CB_CONV_FORWARD_ROWS(P.my, src);
         CB_CONV_COLUMNS_PRODUCT(P.my, chat);
-        CB_CONV_INVERSE_ROWS(P.my);
-        CB_PHASE(row_store(P, BUF, oS, SY, u + (size_t) ic * P.npot, (const int *) nullptr, 0, 0, tid, nthr));
+        CB_CONV_INVERSE_ROWS_STORE(P.my, u + (size_t) ic * P.npot, (const int *) nullptr, 0, 0, 0, 0, P.mx, P.mx);
 #endif
     }
     if (tid == 0 && blockIdx.x == 0) { for (int i = 0; i < np_; i++) g_t[i] = tt_[i]; g_n = np_; }
