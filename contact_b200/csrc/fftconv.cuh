@@ -102,33 +102,47 @@ template <class B> struct ViewCrop {         // column chunk written straight ba
 // one FFT stage over a batch of transforms (in place when in and out view the same buffer).
 // INV = false: decimation in frequency (butterfly, then twiddle); INV = true: its inverse, decimation in time.
 // ------------------------------------------------------------------------------------------------------------
-// core loop with all constants supplied: items = cnt * nbatch butterflies, m = ns / R, twiddle step tstep
-template <int R, bool INV, class VI, class VO, class TW>
-CB_HD void fft_stage_core(VI in, VO out, int nbatch, int items, int m, int tstep, uint32_t mg_b, uint32_t mg_m, TW tw,
-                          int tid, int nthr)
+// core loop with all constants supplied: items = cnt * nbatch butterflies, m = ns / R, twiddle step tstep.
+// PR = 1: first DIF stage of a transform whose upper half of the input is zero (zero-padded tractions: n_in <= L/2), the
+//         inputs x[R/2..R-1] are not loaded and the butterfly leaves their additions out;
+// PR = 2: last DIT stage of a transform of which only the upper half of the output is kept (result rows Fy..Fy+my-1): the
+//         outputs x[0..R/2-1] are neither completed nor stored.  Both give the results of PR = 0.
+template <int R, bool INV, int PR, class VI, class VO, class TW>
+CB_HD void fft_stage_core_p(VI in, VO out, int nbatch, int items, int m, int tstep, uint32_t mg_b, uint32_t mg_m, TW tw,
+                            int tid, int nthr)
 {
     const int ns = m * R;
+    constexpr bool half_in = (PR == 1) && DftHalfIn<R, INV>::ok;
+    constexpr int NL = half_in ? R / 2 : R;
+    constexpr int S0 = (PR == 2 && R % 2 == 0) ? R / 2 : 0;
     for (int w = tid; w < items; w += nthr) {
         const uint32_t g = fdiv(w, mg_b), c = w - g * nbatch;
         const uint32_t blk = fdiv(g, mg_m), j = g - blk * m;
         const uint32_t e0 = blk * ns + j;
         cd x[R];
 #pragma unroll
-        for (int q = 0; q < R; q++) x[q] = in.ld(e0 + q * m, c);
+        for (int q = 0; q < NL; q++) x[q] = in.ld(e0 + q * m, c);
         if (INV && m > 1) {
             const int t = tstep * j;
 #pragma unroll
-            for (int q = 1; q < R; q++) x[q] = cmulc(x[q], tw.ld(t * q));
+            for (int q = 1; q < NL; q++) x[q] = cmulc(x[q], tw.ld(t * q));
         }
-        Dft<R, INV>::run(x);
+        if (half_in) DftHalfIn<R, INV>::run(x); else Dft<R, INV>::run(x);
         if (!INV && m > 1) {
             const int t = tstep * j;
 #pragma unroll
-            for (int q = 1; q < R; q++) x[q] = cmul(x[q], tw.ld(t * q));
+            for (int q = (S0 > 1 ? S0 : 1); q < R; q++) x[q] = cmul(x[q], tw.ld(t * q));
         }
 #pragma unroll
-        for (int q = 0; q < R; q++) out.st(e0 + q * m, c, x[q]);
+        for (int q = S0; q < R; q++) out.st(e0 + q * m, c, x[q]);
     }
+}
+
+template <int R, bool INV, class VI, class VO, class TW>
+CB_HD void fft_stage_core(VI in, VO out, int nbatch, int items, int m, int tstep, uint32_t mg_b, uint32_t mg_m, TW tw,
+                          int tid, int nthr)
+{
+    fft_stage_core_p<R, INV, 0>(in, out, nbatch, items, m, tstep, mg_b, mg_m, tw, tid, nthr);
 }
 
 template <int R, bool INV, class VI, class VO, class TW>
@@ -214,6 +228,15 @@ template <bool INV, class VI, class VO, class TW>
 CB_HD void fft_stage_k(int r, VI in, VO out, int nbatch, uint32_t mg_b, const StageK &k, TW tw, int tid, int nthr)
 {
 #define CB_CALL_(RR) fft_stage_core<RR, INV>(in, out, nbatch, k.cnt * nbatch, k.m, k.tstep, mg_b, k.mg_m, tw, tid, nthr)
+    CB_RADIX_SWITCH(r, CB_CALL_)
+#undef CB_CALL_
+}
+
+// pruned first (PR = 1, forward) / last (PR = 2, inverse) stage of the column transforms of a product
+template <bool INV, int PR, class VI, class VO, class TW>
+CB_HD void fft_stage_kp(int r, VI in, VO out, int nbatch, uint32_t mg_b, const StageK &k, TW tw, int tid, int nthr)
+{
+#define CB_CALL_(RR) fft_stage_core_p<RR, INV, PR>(in, out, nbatch, k.cnt * nbatch, k.m, k.tstep, mg_b, k.mg_m, tw, tid, nthr)
     CB_RADIX_SWITCH(r, CB_CALL_)
 #undef CB_CALL_
 }
