@@ -320,12 +320,13 @@ inline int hertz_setup(Problem &p)
 // contac (m_scontc.f90:37-216) for a batch of problems: host set-up, ONE device launch per coefficient class, gather
 // wall-clock split of the last calculate_batch call (s): [0] host set-up of the cases, [1] coefficient transforms (cached),
 // [2] device allocation + uploads, [3] solver kernel(s), [4] output products + downloads, [5] total
-inline double *batch_timing() { static double t[6] = { 0, 0, 0, 0, 0, 0 }; return t; }
+// split of [4]: [6] us products incl. their buffers, [7] downloads, [8] host post-processing, [9] device frees
+inline double *batch_timing() { static double t[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 }; return t; }
 
 inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int> &ierr)
 {
     double *bt = batch_timing();
-    for (int k = 0; k < 6; k++) bt[k] = 0.0;
+    for (int k = 0; k < 10; k++) bt[k] = 0.0;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
     const size_t nb = probs.size();
@@ -472,6 +473,7 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
             for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) { c.chatA[a][b] = cs.d_chat[SET_CS][a][b]; c.chatV[a][b] = cs.d_chat[is_roll ? SET_CV : SET_CS][a][b]; }
             for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) c.chatSV[a][b] = is_roll ? cs.d_chat[SET_CSV][a][b] : nullptr;
             if (is_roll) { c.cfv11 = cs.d_cf[SET_CSV] + 0 * nblk; c.cfv12 = cs.d_cf[SET_CSV] + 3 * nblk; c.cfv22 = cs.d_cf[SET_CSV] + 4 * nblk; }
+            c.cf13 = cs.nt_cpl ? cs.d_cf[SET_CS] + 6 * nblk : nullptr; c.cf23 = cs.nt_cpl ? cs.d_cf[SET_CS] + 7 * nblk : nullptr;
             c.cf12 = cs.d_cf[SET_CS] + 3 * nblk; c.dq = dq_e; c.dx = p.dx; c.gausei = p.gausei; c.omegah = p.omegah; c.omegas = p.omegas;
             c.chatM11 = cs.d_chat[SET_MS][0][0]; c.chatM22 = cs.d_chat[SET_MS][1][1];
             if (p.tang == 3 && p.gausei == 5) {                          // cntc_setsolverflags, contact_addon.f90:1220-1250
@@ -539,6 +541,8 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
             std::vector<double> h_us((size_t) 3 * npot * n);
             cudaMemcpy(h_us.data(), d_us, sizeof(double) * h_us.size(), cudaMemcpyDeviceToHost);
             cudaFree(d_us); cudaFree(d_pb);
+            auto to1 = now();
+            bt[6] += secs(tg3, to1);
             for (int i = 0; i < n; i++) {
                 Problem &p = *probs[ks[i]];
                 const ContactCase &c = hc[i];
@@ -546,6 +550,12 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
                 cudaMemcpy(p.el.data(), c.nrm.el, sizeof(int) * npot, cudaMemcpyDeviceToHost);
                 cudaMemcpy(p.ps.data(), c.ps, sizeof(double) * 3 * npot, cudaMemcpyDeviceToHost);
                 if (p.tang != 0) cudaMemcpy(p.ss.data(), c.ss, sizeof(double) * 2 * npot, cudaMemcpyDeviceToHost);
+            }
+            auto to2 = now();
+            bt[7] += secs(to1, to2);
+            for (int i = 0; i < n; i++) {
+                Problem &p = *probs[ks[i]];
+                const ContactCase &c = hc[i];
                 if (p.tang >= 2) p.dq_eff = c.dq;
                 p.us.assign(h_us.begin() + (size_t) i * 3 * npot, h_us.begin() + (size_t) (i + 1) * 3 * npot);
                 p.hs.assign(3 * (size_t) npot, 0.0);
@@ -574,13 +584,16 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
                 } else { p.fcntc[0] = p.fcntc[1] = 0.0; p.mztrue = 0.0; }
                 p.fcntc[2] = p.fntrue;
                 p.solved = true;
-                if (c.tstatus & 1) { last_error() = "TANG: the case needs a solver that the B200 path does not serve (ConvexGS with DQ > DX, or a Gauss-Seidel solver -- also as the fall-back of a stagnating GDsteady -- on a grid beyond one CTA)"; ierr[ks[i]] = CNTC_err_other; }
+                if (c.tstatus & 1) { last_error() = "TANG: the case needs a solver that the B200 path does not serve (a Gauss-Seidel solver -- also as the fall-back of a stagnating GDsteady -- on a grid beyond one CTA)"; ierr[ks[i]] = CNTC_err_other; }
                 else if (p.itnorm < 0 || (p.status & 1)) ierr[ks[i]] = CNTC_err_norm;
                 else if (p.ittang < 0) ierr[ks[i]] = CNTC_err_tang;
                 else ierr[ks[i]] = count_at_boundary(p);              // contact_addon.f90:3885-3891
             }
+            bt[8] += secs(to2, now());
         }
+        auto tf0 = now();
         cudaFree(d_buf); cudaFree(d_el); cudaFree(d_cases); cudaFree(d_next);
+        bt[9] += secs(tf0, now());
         bt[4] += secs(tg3, now());
     }
     const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -831,6 +844,7 @@ int cb200_eldiv0(int mx, int my, double dx, double dy, double gg1, double gg2, d
 // iteration counters of the last case: out[0..6] = itnorm, itcg (NormCG), ittang, itgs (tangential solver iterations),
 // ncon, number of tangential solver calls nr_n, outer iterations; nr_itcg[0..nr_n) = iterations per solver call (at most lenarr)
 int cb200_batch_timing(double *out) { for (int k = 0; k < 6; k++) out[k] = batch_timing()[k]; return 0; }
+int cb200_batch_timing_output(double *out) { for (int k = 0; k < 4; k++) out[k] = batch_timing()[6 + k]; return 0; }
 
 int cb200_get_iterations(int ire, int icp, int *out, int lenarr, int *nr_itcg)
 {

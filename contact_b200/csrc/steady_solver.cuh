@@ -125,6 +125,11 @@ struct SteadyArgs {
     int maxgs;
     int convex;             // 0: SteadyGS on the traction differences; 1: ConvexGS on the tractions (cnvxgs)
     int sym;                // coefficient blocks have the quadrant symmetry of cs (false for csv = cs - cv)
+    // leading-edge equations of cnvxgs in steady rolling with dq > dx (m_solvpt.f90:2583, 2632-2668; m_leadedge.f90:336-394)
+    int ledge;              // 1: elements with facdt < 0.9999 use s = ws + A_cs p_t - ubnd and the 2x2 matrix of cs
+    const double *facdt;    // [n] fraction of the step spent in contact (sxbnd), defines ii2j > 0
+    const double *cs11, *cs12, *cs22, *cs13, *cs23;   // spatial blocks of cs (13, 23: null without n-t coupling)
+    double *ub;             // [2][n] ubnd per leading-edge position, stored at the last interior element of the run
 };
 
 // shared-memory carve-up for the sweep.  q: coefficient table (quadrant [3][my][mx] for the symmetric cs, half plane
@@ -314,9 +319,38 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
     int itgs = 0;
     double dif = 2.0, difid = 1.0, dif1 = 0.0;
     unsigned long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0, tp4 = 0, tp5 = 0, tp6 = 0;
+    // leading-edge elements: 2x2 matrix of cs (coefs instead of coefsv, :2665-2669)
+    const bool ledge = convex && a.ledge != 0;
+    const size_t oc = (size_t) a.cmy * (2 * a.cmx) + a.cmx;
+    const double l00 = ledge ? a.cs11[oc] * a.ga_inv : 0.0, l01 = ledge ? a.cs12[oc] * a.ga_inv : 0.0,
+                 l11 = ledge ? a.cs22[oc] * a.ga_inv : 0.0;
     while (dif >= difid && itgs < a.maxgs) {
         itgs++;
         double dsum = 0.0;                                     // lane 0 of warp 0 only
+        if (ledge) {
+            // subnd (m_leadedge.f90:336-394) at the start of every sweep (:2583): displacement difference of the current
+            // tractions (all three directions, cs) at the first exterior element behind each C -> E transition
+            // (facdx = 1); one warp per transition, row sum over the compact contact list with a fixed shuffle tree
+            const int wid = tid >> 5, nw = nt >> 5;
+            for (int k = wid; k < ncon; k += nw) {
+                const int ii = a.iel[k], iy = ii / mx, ix = ii - iy * mx;
+                if (ix != mx - 1 && el[ii + 1] >= 1) continue;
+                double ux = 0.0, uy = 0.0;
+                if (ix + 3 <= mx) {
+                    for (int kk = lane; kk < ncon; kk += 32) {
+                        const int jj = a.iel[kk], jy = jj / mx, jx = jj - jy * mx;
+                        const size_t o = (size_t) (iy - jy + a.cmy) * (2 * a.cmx) + (ix + 1 - jx) + a.cmx;
+                        const double px = psx[jj], py = psy[jj], c12 = a.cs12[o];
+                        ux += a.cs11[o] * px + c12 * py; uy += c12 * px + a.cs22[o] * py;
+                        if (a.cs13) { const double pn = psn[jj]; ux += a.cs13[o] * pn; uy += a.cs23[o] * pn; }
+                    }
+                    for (int o = 16; o > 0; o >>= 1) { ux += __shfl_xor_sync(full, ux, o); uy += __shfl_xor_sync(full, uy, o); }
+                    ux *= a.ga_inv; uy *= a.ga_inv;
+                }
+                if (lane == 0) { a.ub[ii] = ux; a.ub[n + ii] = uy; }
+            }
+            __syncthreads();
+        }
         for (int iy = 0; iy < my; iy++) {
             const int k0 = s.rowk(iy), k1 = s.rowk(iy + 1);
             if (k1 == k0) continue;
@@ -353,18 +387,40 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
                         if (L0 == 32) { while (jxs > 0 && s.el(jxs) == EL_ADHES) jxs--; }
                         if (jxs < 0) jxs = 0;
                     }
+                    // leading-edge element (ii2j > 0): the shift is A_cs p_t - ubnd instead of A_csv p_t (:2654-2658); the
+                    // row sum over the contact list is taken by the warp -- this row from shared memory, the others
+                    // from the tractions in global memory, which are current after every row
+                    const bool zl = ledge && active && a.facdt[iy * mx + ix] < 0.9999;
+                    double lsx = 0.0, lsy = 0.0;
+                    if (zl) {
+                        for (int kk = lane; kk < ncon; kk += 32) {
+                            const int jj = a.iel[kk], jy = jj / mx, jx = jj - jy * mx;
+                            const size_t o = (size_t) (iy - jy + a.cmy) * (2 * a.cmx) + (ix - jx) + a.cmx;
+                            const double qx = (jy == iy) ? s.psx(jx) : psx[jj], qy = (jy == iy) ? s.psy(jx) : psy[jj];
+                            const double c12 = a.cs12[o];
+                            lsx += a.cs11[o] * qx + c12 * qy; lsy += c12 * qx + a.cs22[o] * qy;
+                        }
+                        for (int o = 16; o > 0; o >>= 1) { lsx += __shfl_xor_sync(full, lsx, o); lsy += __shfl_xor_sync(full, lsy, o); }
+                        lsx *= a.ga_inv; lsy *= a.ga_inv;
+                    }
                     double px = 0.0, py = 0.0;
                     if (lane == 0) {
                         s.ictl(0, my) = 0;
                         if (active) {
                             double c00, c01, c11;
-                            if (convex) { c00 = q00; c01 = q01; c11 = q11; }   // cnvxgs: coefs / coefsv, :2519-2541
+                            if (zl) { c00 = l00; c01 = l01; c11 = l11; }
+                            else if (convex) { c00 = q00; c01 = q01; c11 = q11; }   // cnvxgs: coefs / coefsv, :2519-2541
                             else {                                              // stdygs: c(0) - c(jx - ix), :3010-3040
                                 double t00, t01, t11;
                                 T.row0(jxs - ix, t00, t01, t11);
                                 c00 = q00 - t00; c01 = q01 - t01; c11 = q11 - t11;
                             }
                             double sx = s.wsx(ix) + s.urx(ix), sy = s.wsy(ix) + s.ury(ix);
+                            if (zl) {
+                                int ixb = ix;
+                                while (ixb < mx - 1 && s.el(ixb + 1) >= 1) ixb++;
+                                sx = s.wsx(ix) + lsx - a.ub[iy * mx + ixb]; sy = s.wsy(ix) + lsy - a.ub[n + iy * mx + ixb];
+                            }
                             const double pox = s.psx(ix), poy = s.psy(ix);
                             px = pox; py = poy;
                             plstrc_dev(e, c00, c01, c01, c11, a.eps, a.omegah, a.omegas, px, py, s.bnd(ix), sx, sy);

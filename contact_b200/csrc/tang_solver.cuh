@@ -38,6 +38,7 @@ struct ContactCase {
     double omegah, omegas;          // relaxation factors of the Gauss-Seidel solvers (set by stang)
     const cd *chatSV[2][2];         // transformed csv = cs - cv blocks (steady rolling with ConvexGS)
     const double *cfv11, *cfv12, *cfv22;   // spatial blocks of csv
+    const double *cf13, *cf23;      // spatial blocks cs(1,3), cs(2,3) (null without n-t coupling): ubnd of the leading edge
     int solver_eff;                 // 0 TangCG, 1 SteadyGS, 2 ConvexGS, 3 GDsteady (set by stang, m_stang.f90:144-191)
     GdParams gd;                    // G = 5
     double *gwork;                  // 16 n doubles of GDsteady work space (null unless G = 5)
@@ -345,6 +346,8 @@ __device__ int solve_once_dev(const X &x, ContactCase &c, const double *wstot, d
         a.cmx = c.nrm.cmx; a.cmy = c.nrm.cmy;
         a.ga_inv = c.nrm.ga_inv; a.mu = c.fstat; a.eps = c.nrm.eps; a.omegah = c.omegah; a.omegas = c.omegas; a.maxgs = c.nrm.maxgs;
         a.convex = convex ? 1 : 0; a.sym = sv ? 0 : 1;
+        a.ledge = (sv && c.dq > c.dx) ? 1 : 0; a.facdt = c.twork;             // facdt of stang_dev
+        a.cs11 = c.cf11; a.cs12 = c.cf12; a.cs22 = c.cf22; a.cs13 = c.cf13; a.cs23 = c.cf23; a.ub = a.ug;
         if (ncon <= 6 * CB_THREADS) info = stdygs_dev<6>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
         else if (ncon <= 12 * CB_THREADS) info = stdygs_dev<12>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
         else info = stdygs_dev<22>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
@@ -462,9 +465,9 @@ __device__ int stang_dev(const X &x, ContactCase &c, double fntrue, int &itgs_to
         const int k = (int) cnt[0];
         int solver = ssrol ? (c.gausei == 5 ? 3 : (c.gausei != 2 ? 1 : 2)) : (c.gausei != 2 ? 0 : 2);
         if (cnt[1] > 0.0 && (solver == 1 || solver == 3)) solver = 2;          // no exterior elements at the trailing edge
-        // ConvexGS with dq > dx needs the leading-edge equations (ii2j > 0), not served; the Gauss-Seidel solvers exist on
-        // the one-CTA-per-case path only
-        bool refuse = (solver == 2 && ssrol && c.dq > c.dx * (1.0 + 1e-4)) || ((solver == 1 || solver == 2) && !X::kBlock) ||
+        // the Gauss-Seidel solvers exist on the one-CTA-per-case path only (ConvexGS with dq > dx: leading-edge equations
+        // inside stdygs_dev)
+        bool refuse = ((solver == 1 || solver == 2) && !X::kBlock) ||
                       (solver == 3 && c.gwork == nullptr);
         if (refuse) { if (x.leader()) c.tstatus |= 1; x.sync(); itgs_tot = 0; return -1; }
         double oh = c.omegah, os = c.omegas;

@@ -51,7 +51,11 @@ def batch_timing():
     import ctypes as C
     out = (C.c_double * 6)()
     _check(load_library().cb200_batch_timing(out))
-    return dict(zip(("setup", "coefficients", "upload", "kernel", "output", "total"), [round(v, 5) for v in out]))
+    d = dict(zip(("setup", "coefficients", "upload", "kernel", "output", "total"), [round(v, 5) for v in out]))
+    out2 = (C.c_double * 4)()
+    _check(load_library().cb200_batch_timing_output(out2))
+    d["output_split"] = dict(zip(("products", "downloads", "host", "free"), [round(v, 5) for v in out2]))
+    return d
 
 
 def gd_prof(reset=True):

@@ -168,6 +168,7 @@ int cb200_get_iterations(int ire, int icp, int *out, int lenarr, int *nr_itcg);
  * transforms (cached per grid and material), [2] device allocation + uploads, [3] solver kernel(s), [4] output products +
  * downloads, [5] total */
 int cb200_batch_timing(double *out);
+int cb200_batch_timing_output(double *out);   /* split of the output phase: us products, downloads, host post-processing, device frees (s) */
 
 /* last error message of the calling thread (NUL-terminated, owned by the library) */
 const char *cb200_last_error(void);

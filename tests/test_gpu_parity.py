@@ -532,6 +532,44 @@ def test_convexgs_steady_rolling_cnvxgs_1c(cb, O, mbench):
     cb.cntc_finalize(ire)
 
 
+@pytest.mark.parametrize("material", ["steel", "dissimilar"])
+@pytest.mark.parametrize("dq", [0.5, 0.3])
+def test_convexgs_steady_rolling_leading_edge(cb, O, material, dq):
+    """T=3, G=2 with a rolling step DQ > DX: the elements within DQ of the leading edge get equation (1b) of
+    m_stang.f90:809 -- shift = w + A_cs p - ubnd with ubnd from subnd (m_leadedge.f90:336-394) refreshed at every sweep
+    (m_solvpt.f90:2583, 2632-2668) -- the others the interior equation with csv.  Dissimilar materials add the normal
+    pressures to ubnd (cs(1,3), cs(2,3)) and a Panagiotopoulos alternation around it."""
+    g = dict(mx=34, my=27, xl=-3.4, yl=-2.7, dx=0.2, dy=0.2, ibase=1, prmudf=[0.004, 0.0, 0.006, 0.0, 0.0, 0.0])
+    gg, poiss = ((82000.0, 82000.0), (0.28, 0.28)) if material == "steel" else ((82000.0, 40000.0), (0.28, 0.35))
+    maxout = 1 if material == "steel" else 10
+    ire, icp = 66, 1
+    _setup_rolling(cb, ire, g, gg, poiss, fn=9.0e3, fstat=0.25, maxgs=500, maxin=50, maxnr=30, maxout=maxout, eps=1e-6)
+    cb.cntc_setsolverflags(ire, icp, 2, [500, 50, 30, maxout, 0], [1e-6, 0.9, 0.9, 1.1])
+    cb.cntc_setrollingstepsize(ire, icp, 0.0, dq)
+    cb.cntc_setcreepages(ire, icp, 0.0006, 0.0004, 0.0002)
+    ierr = cb.cntc_calculate(ire, icp)
+    assert ierr == 0, (ierr, cb.lib.last_error())
+    ref = O.contac(g, gg, poiss, tang=3, norm=1, force3=0, fn=9.0e3, cksi=0.0006, ceta=0.0004, cphi=0.0002, fstat=0.25,
+                   fkin=0.25, maxgs=500, maxin=50, maxnr=30, maxout=maxout, eps=1e-6, chi=0.0, dq=dq, gausei=2, omegah=0.9,
+                   omegas=0.9)
+    assert ref["ierror"] == 0
+    # the leading-edge equations matter: the interior equation alone (DQ = DX) gives other forces
+    ref_dx = O.contac(g, gg, poiss, tang=3, norm=1, force3=0, fn=9.0e3, cksi=0.0006, ceta=0.0004, cphi=0.0002, fstat=0.25,
+                      fkin=0.25, maxgs=500, maxin=50, maxnr=30, maxout=maxout, eps=1e-6, chi=0.0, dq=0.2, gausei=2,
+                      omegah=0.9, omegas=0.9)
+    assert abs(ref["fy"] - ref_dx["fy"]) > 1e-4
+    its = cb.lowlevel.get_iterations(ire, icp)
+    el = cb.cntc_getelementdivision(ire, icp).ravel()
+    assert its["itgs"] == ref["itgs_tang"] and its["itout"] == ref["itout"]
+    assert np.array_equal(el, ref["el"])
+    pn, px, py = cb.cntc_gettractions(ire, icp)
+    s_ = np.abs(ref["ps"][:2]).max()
+    assert np.abs(px.ravel() - ref["ps"][0]).max() < 1e-8 * s_ and np.abs(py.ravel() - ref["ps"][1]).max() < 1e-8 * s_
+    fn, tx, ty, mz = cb.cntc_getcontactforces(ire, icp)
+    assert abs(tx / (0.25 * fn) - ref["fx"]) < 1e-9 and abs(ty / (0.25 * fn) - ref["fy"]) < 1e-9
+    cb.cntc_finalize(ire)
+
+
 def test_convexgs_shift(cb, O):
     """T=1 with G=2: ConvexGS on the tractions with the coefficients cs (m_stang.f90:176-181)."""
     c = cases.CATTANEO2
