@@ -146,6 +146,20 @@ def rolling_sweep_leg(cb, n, rank_offset, gausei=0):
     return out
 
 
+def sweep4096_leg(cb, rank, world, total=4096, chunk=888):
+    """BASELINE config 5: the 4096-case creepage / lateral-shift sweep on the mbench 71x81 grid (T=3, GDsteady as in
+    today's perfc_test/tang_problm_*c.inp), a fixed total sharded over the ranks (contiguous blocks, no data-path
+    collective), each rank in chunks of at most `chunk` cases per cntc_calculate_batch call (result elements are 1..999)."""
+    lo, hi = (total * rank) // world, (total * (rank + 1)) // world
+    s, kms, n, err, fb, its = 0.0, 0.0, 0, 0, 0, 0.0
+    for a in range(lo, hi, chunk):
+        m = min(chunk, hi - a)
+        r = rolling_sweep_leg(cb, m, a, gausei=5)
+        s += r["s"]; kms += r["solver_kernel_ms"]; n += m; err += r["errors"]; fb += r["fallbacks_to_steadygs"]
+        its += r["mean_itgs"] * m
+    return {"cases": n, "s": s, "solver_kernel_ms": kms, "errors": err, "fallbacks_to_steadygs": fb, "mean_itgd": its / max(1, n)}
+
+
 def spence71_leg(cb):
     """perfc_test/spence71_8281pt.inp itself (BASELINE config: 69 cases in sequence on the 91x91 grid, dissimilar
     materials, Panagiotopoulos process, 11-depth subsurface block per case) through the .inp reader and cntc_calculate /
@@ -386,6 +400,7 @@ def run_gpu(args):
     if roll and roll_gd:                     # the two solvers on the same cases: largest difference of the total forces
         f0, f5 = roll.pop("_forces"), roll_gd.pop("_forces")
         roll_gd["max_rel_force_diff_vs_steadygs"] = float(np.abs(f5 - f0).max() / np.abs(f0).max())
+    sweep = sweep4096_leg(cb, rank, world) if (args.sweep4096 and not args.skip_extra) else None
     large = large_grid_leg(cb, torch) if (rank == 0 and not args.skip_extra) else None
     sp71 = spence71_leg(cb) if (rank == 0 and not args.skip_extra) else None
     gdl = gdsteady_leg(cb) if (rank == 0 and not args.skip_extra) else None
@@ -403,7 +418,8 @@ def run_gpu(args):
 
     roll_s = roll["s"] if roll else 0.0
     rollgd_s = roll_gd["s"] if roll_gd else 0.0
-    t = torch.tensor([ms_total, e2e_s, kernel_ms, nprod, roll_s, rollgd_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, e2e_s, kernel_ms, nprod, roll_s, rollgd_s, sweep["s"] if sweep else 0.0,
+                      sweep["solver_kernel_ms"] if sweep else 0.0], dtype=torch.float64, device=dev)
     tmax = t.clone()
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -470,6 +486,13 @@ def run_gpu(args):
             out["rolling_sweep"] = roll
         if roll_gd:
             out["rolling_sweep_gdsteady"] = roll_gd
+        if sweep:
+            out["sweep4096"] = {"cases_total": 4096, "s": float(tmax[6]), "cases_per_s": 4096 / float(tmax[6]),
+                                "solver_kernel_ms_max_rank": float(tmax[7]), "cases_this_rank": sweep["cases"],
+                                "errors_this_rank": sweep["errors"], "fallbacks_this_rank": sweep["fallbacks_to_steadygs"],
+                                "mean_itgd_this_rank": sweep["mean_itgd"], "scaling": "strong",
+                                "note": "BASELINE config 5: 4096 mbench 71x81 cases (PEN and creepage draws of seed 20240229), T=3 GDsteady, "
+                                        "eps 1e-5, host buffers through cntc_calculate_batch in chunks of <= 888 cases; wall clock, max over ranks"}
         if large:
             large["frac_hbm"] = large["alg_GBps"] / hbm_peak
             large["frac_fp64"] = large["nominal_TFLOPs"] / fp64_peak if fp64_peak > 0 else None
@@ -573,6 +596,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cases", type=int, default=0, help="cases per GPU per step (default 8 x SM count)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg (0 = skip)")
+    ap.add_argument("--no-sweep4096", dest="sweep4096", action="store_false",
+                    help="skip BASELINE config 5 at full size (4096 rolling cases sharded over the ranks, ~5 s on one GPU)")
     ap.add_argument("--skip-extra", action="store_true", help="skip the rolling-sweep and 575x647 legs")
     args = ap.parse_args()
     if args.impl == "reference":

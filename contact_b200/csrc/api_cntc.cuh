@@ -202,7 +202,6 @@ inline int count_at_boundary(const Problem &p)
 inline int check_scope(const Problem &p)
 {
     if (p.tang == 2 && fabs(p.chi) > 0.01) { last_error() = "transient rolling (T=2): only CHI = 0 is served by the B200 path"; return CNTC_err_other; }
-    if (p.tang == 2 && p.dq > p.dx * (1.0 + 1e-4)) { last_error() = "transient rolling (T=2) with DQ > DX needs the leading-edge equations, which the B200 path does not serve"; return CNTC_err_other; }
     if (p.tang != 0 && p.frclaw != 0) { last_error() = "L-digit: only Coulomb friction (L=0)"; return CNTC_err_other; }
     if (p.tang == 3 && p.gausei == 2 && fabs(p.chi) > 0.01) { last_error() = "ConvexGS in steady rolling: only CHI = 0 is served by the B200 path"; return CNTC_err_other; }
     if (p.tang == 3 && p.gausei == 5 && fabs(p.chi) > 0.01) { last_error() = "GDsteady: only CHI = 0 is served by the B200 path"; return CNTC_err_other; }

@@ -494,17 +494,45 @@ __device__ int stang_dev(const X &x, ContactCase &c, double fntrue, int &itgs_to
     // stang_rhs (:749-951): wsfix = -facdt hs_t + A_tn pn - A'_tn p'n - A'_tt p'_t on C; shifts: facdt = 1, previous
     // tractions p'; steady rolling: p' = p with the shifted coefficients cv, A'_tt p'_t left to the solver
     nprod += conv_multi(x, c.chatA, ps, 2, 2, u1, 0, 1, el, 1, 0);
+    // transient rolling with dq > dx: near the leading edge (ii2j > 0, i.e. facdt < 0.9999) equation (1b) replaces the
+    // displacements of the previous time u' = A' p' by ubnd = subnd(p', cs) (m_stang.f90:888-925, m_leadedge.f90:336-394):
+    // the displacement of p' (all three directions, coefficients cs) at the first exterior element behind the C -> E
+    // transition of the row -- taken from ONE unmasked product A_cs p' instead of a row sum per transition
+    const bool tledge = (c.tang == 2 && c.dq > c.dx);
     if (ssrol) {
         nprod += conv_multi(x, c.chatV, ps, 2, 2, u2, 0, 1, el, 1);
         for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) if (el[i] >= 1) { u1[i] -= u2[i]; u1[n + i] -= u2[n + i]; }
         x.sync();
     } else if (c.pv) {
+        if (tledge) {
+            const int mx = x.plan().mx;
+            nprod += conv_multi(x, c.chatA, c.pv, 0, 2, u2, 0, 1, el, 0);
+            for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) if (el[i] >= 1) {      // wstot: usn - ubnd, used below
+                const int ix = (int) (i % mx);
+                int ixb = ix;
+                while (ixb < mx - 1 && el[i - ix + ixb + 1] >= 1) ixb++;
+                const bool ok = ixb + 3 <= mx;                                               // else ubnd = 0 (:364-366)
+                wstot[i] = u1[i] - (ok ? u2[i - ix + ixb + 1] : 0.0);
+                wstot[n + i] = u1[n + i] - (ok ? u2[n + i - ix + ixb + 1] : 0.0);
+            }
+            x.sync();
+        }
         nprod += conv_multi(x, c.chatV, c.pv, 2, 2, u2, 0, 1, el, 1);
         for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) if (el[i] >= 1) { u1[i] -= u2[i]; u1[n + i] -= u2[n + i]; }
         x.sync();
         nprod += conv_multi(x, c.chatV, c.pv, 0, 1, u2, 0, 1, el, 1);
         for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) if (el[i] >= 1) { u1[i] -= u2[i]; u1[n + i] -= u2[n + i]; }
         x.sync();
+        if (tledge) {                                       // u2 is free now: facdt lives there during the TANG loop
+            facdt = u2;
+            sxbnd_facdt_x(x, x.plan().mx, x.plan().my, el, c.dx, c.dq, 1.0, facdt);
+            for (size_t i = x.first(); i < (size_t) (n); i += x.stride())
+                if (el[i] >= 1 && facdt[i] < 0.9999) { u1[i] = wstot[i]; u1[n + i] = wstot[n + i]; }
+            x.sync();
+        }
+    } else if (tledge) {                                    // from rest (p' = 0): u' = ubnd = 0, only facdt differs from 1
+        facdt = u2;
+        sxbnd_facdt_x(x, x.plan().mx, x.plan().my, el, c.dx, c.dq, 1.0, facdt);
     }
     for (size_t i = x.first(); i < (size_t) (n); i += x.stride()) {
         const bool in = el[i] >= 1;

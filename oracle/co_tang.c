@@ -165,10 +165,11 @@ void co_tangcg(co_ctx *cx, int npot, int maxcg, double eps, const double *ws, co
 #undef PROJ_T
 }
 
-/* m_stang.f90:749-951: shifts (T=1: facdt = 1, previous tractions pv with cv = cs) and steady rolling (T=3: uvn from the
- * current pressures with the shifted coefficients cv, uvt left to the solver); no leading-edge correction (ii2j = 0) */
+/* m_stang.f90:749-951: shifts (T=1: facdt = 1, previous tractions pv with cv = cs), transient rolling (T=2: near the
+ * leading edge, ii2j > 0, equation (1b): u' replaced by ubnd = subnd(pv, cs), :888-925) and steady rolling (T=3: uvn from
+ * the current pressures with the shifted coefficients cv, uvt and ubnd left to the solver) */
 static void tang_rhs(co_ctx *cx, int npot, int is_ssrol, const double *facdt, const co_eldiv *igs, const double *hs,
-                     const double *ps, const double *pv, co_inflcf *cs, co_inflcf *cv, double *wsfix)
+                     const double *ps, const double *pv, co_inflcf *cs, co_inflcf *cv, co_leadedge *lg, double *wsfix)
 {
     double *usn = (double *) calloc(3L * npot, sizeof(double)), *uvn = (double *) calloc(3L * npot, sizeof(double));
     double *uvt = (double *) calloc(3L * npot, sizeof(double));
@@ -178,13 +179,24 @@ static void tang_rhs(co_ctx *cx, int npot, int is_ssrol, const double *facdt, co
         co_vecaijpj(cx, igs, CO_ALLINT, uvt, CO_TANG, pv, igs, CO_TANG, cv);
     } else
         co_vecaijpj(cx, igs, CO_ALLINT, uvn, CO_TANG, ps, igs, CO_Z, cv);
+    if (!is_ssrol) {
+        /* :892 subnd(cgrid, pv, cs, ledg): the row sums run over the element division of pv (previous time); pv is zero
+         * outside it, so the whole grid gives the same sums */
+        co_eldiv all;
+        co_eldiv_init(&all, igs->mx, igs->my);
+        for (int i = 0; i < npot; i++) all.el[i] = CO_ADHES;
+        co_areas(&all);
+        co_subnd(cx, igs->mx, igs->my, pv, &all, cs, lg);
+        co_eldiv_free(&all);
+    }
     for (int k = 0; k < 2; k++)
         for (int i = 0; i < npot; i++)
             if (igs->el[i] >= CO_ADHES) {
                 const long o = (long) k * npot + i;
                 const double wsrig = -facdt[i] * hs[o];
-                if (!is_ssrol) wsfix[o] = wsrig + usn[o] - uvn[o] - uvt[o];
-                else wsfix[o] = wsrig + usn[o] - uvn[o];
+                if (is_ssrol) wsfix[o] = wsrig + usn[o] - uvn[o];
+                else if (lg->ii2j[i] <= 0) wsfix[o] = wsrig + usn[o] - uvn[o] - uvt[o];
+                else wsfix[o] = wsrig + usn[o] - lg->ubnd[2 * lg->ii2j[i] + k];            /* :918-924 */
             }
     free(usn); free(uvn); free(uvt);
 }
@@ -336,7 +348,7 @@ static int stang(co_ctx *cx, co_case *c, int npot, co_inflcf *cs, co_inflcf *cv,
         memcpy(facdt, lg.facdt, sizeof(double) * npot);
     }
     for (int i = 0; i < npot; i++) mus[i] = c->fstat;
-    tang_rhs(cx, npot, is_ssrol, facdt, igs, hs, ps, pv, cs, cv, wsfix);
+    tang_rhs(cx, npot, is_ssrol, facdt, igs, hs, ps, pv, cs, cv, &lg, wsfix);
     while (!zready && ittang < c->maxin) {                                                /* :376 */
         ittang++;
         zready = 1;
@@ -411,8 +423,8 @@ int co_contac(co_case *c)
             dq = c->dx;
         }
     }
-    /* not restated: rolling directions other than +x; transient rolling with the leading-edge equations (dq > dx) */
-    if ((is_roll && fabs(chi) > 0.01) || (c->tang == 2 && dq > c->dx * (1.0 + 1e-4))) { co_ctx_free(cx); return -99; }
+    /* not restated: rolling directions other than +x */
+    if (is_roll && fabs(chi) > 0.01) { co_ctx_free(cx); return -99; }
     co_sgencr(&mat, mx, my, c->dx, c->dy, is_roll, chi, dq, &cs, &cv, &csv, &ms);
     double *x = (double *) malloc(sizeof(double) * npot), *y = (double *) malloc(sizeof(double) * npot);
     double *hs = (double *) calloc(3L * npot, sizeof(double)), *ps = (double *) calloc(3L * npot, sizeof(double));

@@ -1060,17 +1060,20 @@ def test_inp_sequence_spence71_golden(cb):
     print("spence71_8281pt.inp: 69 cases with subsurface stresses in %.2f s" % dt)
 
 
-def test_transient_rolling_sequence(cb, O):
+@pytest.mark.parametrize("dq,material", [(0.2, "steel"), (0.5, "steel"), (0.5, "dissimilar")])
+def test_transient_rolling_sequence(cb, O, dq, material):
     """T=2 (transient rolling, TangCG with the shifted coefficients cv acting on the previous tractions): a sequence of
     steps from rest (P=0, I=1) against the oracle step by step.  No golden file of the reference covers T=2 on a
-    module-3 grid; the oracle itself is checked by the property that the sequence converges to the T=3 steady state."""
+    module-3 grid; the oracle itself is checked by the property that the sequence converges to the T=3 steady state.
+    DQ = 2.5 DX: the elements within DQ of the leading edge use ubnd = subnd(p', cs) instead of u' (m_stang.f90:888-925);
+    dissimilar materials add the previous pressures to ubnd."""
     g = dict(mx=34, my=27, xl=-3.4, yl=-2.7, dx=0.2, dy=0.2, ibase=1, prmudf=[0.004, 0.0, 0.006, 0.0, 0.0, 0.0])
-    gg, poiss = (82000.0, 82000.0), (0.28, 0.28)
+    gg, poiss = ((82000.0, 82000.0), (0.28, 0.28)) if material == "steel" else ((82000.0, 40000.0), (0.28, 0.35))
     kw = dict(norm=1, force3=0, fn=9.0e3, cksi=0.0012, ceta=0.0004, cphi=0.0002, fstat=0.25, fkin=0.25, maxgs=500, maxin=50,
-              maxnr=30, maxout=1, eps=1e-6, chi=0.0, dq=0.2)
+              maxnr=30, maxout=1, eps=1e-6, chi=0.0, dq=dq)
     ire, icp = 91, 1
     _setup_rolling(cb, ire, g, gg, poiss, fn=9.0e3, fstat=0.25, maxgs=500, maxin=50, maxnr=30, maxout=1, eps=1e-6, force=0)
-    cb.cntc_setrollingstepsize(ire, icp, 0.0, 0.2)
+    cb.cntc_setrollingstepsize(ire, icp, 0.0, dq)
     cb.cntc_setcreepages(ire, icp, 0.0012, 0.0004, 0.0002)
     el = ps = None
     fx_hist = []

@@ -185,6 +185,27 @@ def test_transient_rolling_converges_to_steady_state():
     assert np.abs(ps[:2] - rs["ps"][:2]).max() < 0.03 * np.abs(rs["ps"][:2]).max()
 
 
+def test_transient_rolling_leading_edge_converges_to_convexgs_steady_state():
+    """DQ = 2.5 DX: the elements within DQ of the leading edge take equation (1b) of m_stang.f90:809 -- in T=2 through the
+    right-hand side (ubnd = subnd(pv, cs), m_stang.f90:888-925), in T=3 inside ConvexGS (subnd(ps, cs) per sweep,
+    m_solvpt.f90:2583, 2654-2658).  No golden file covers either ("parity unpinned"); the two independent restatements pin
+    each other: the transient sequence from rest converges to the steady state of ConvexGS at the same DQ."""
+    g = dict(mx=20, my=15, xl=-2.0, yl=-1.5, dx=0.2, dy=0.2, ibase=1, prmudf=[0.012, 0.0, 0.018, 0.0, 0.0, 0.0])
+    kw = dict(norm=1, force3=0, fn=1.5e3, cksi=0.0015, ceta=0.0005, cphi=0.0, fstat=0.25, fkin=0.25, maxgs=500, maxin=50, maxnr=30,
+              maxout=1, eps=1e-6, chi=0.0, dq=0.5)
+    rs = O.contac(g, cases.STEEL["gg"], cases.STEEL["poiss"], tang=3, gausei=2, omegah=0.9, omegas=0.9, **kw)
+    assert rs["ierror"] == 0
+    el = ps = None
+    for k in range(30):
+        extra = {} if el is None else dict(iestim=1, el_in=el, ps_in=ps, pv_in=ps)
+        r = O.contac(g, cases.STEEL["gg"], cases.STEEL["poiss"], tang=2, gausei=0, **kw, **extra)
+        assert r["ierror"] == 0
+        el, ps = r["el"].copy(), r["ps"].copy()
+    assert abs(r["fx"] - rs["fx"]) < 2e-5 and abs(r["fy"] - rs["fy"]) < 2e-5
+    assert np.array_equal(el, rs["el"])
+    assert np.abs(ps[:2] - rs["ps"][:2]).max() < 1e-4 * np.abs(rs["ps"][:2]).max()
+
+
 def test_gdsteady_converges_to_steadygs(mbench):
     """perfc_test/tang_problm_1c.inp with the solver record of tang_problm_8c.inp:9 (G=5, GDsteady, gdsteady.f90).  No golden
     file of the reference runs GDsteady ("parity unpinned" for its iteration count): the restatement is pinned by reaching
