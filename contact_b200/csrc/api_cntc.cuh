@@ -6,6 +6,8 @@
 // (m_global_data.f90:463-526).  Control digits outside the B200 hot-path scope are rejected with an error code
 // (never abort): see DESIGN.md "scope".
 #pragma once
+#include <thread>
+#include <atomic>
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -322,8 +324,51 @@ inline int hertz_setup(Problem &p)
 // split of [4]: [6] us products incl. their buffers, [7] downloads, [8] host post-processing, [9] device frees
 inline double *batch_timing() { static double t[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 }; return t; }
 
+// independent per-case host work (copies into the problems' own vectors, force sums) over a few host threads
+template <class F> inline void host_parallel_for(int n, F fn)
+{
+    const int nt = std::max(1, std::min({ n / 16, (int) std::thread::hardware_concurrency(), 16 }));
+    if (nt <= 1) { for (int i = 0; i < n; i++) fn(i); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++)
+        th.emplace_back([=, &fn] { for (int i = (int) ((long) n * t / nt); i < (int) ((long) n * (t + 1) / nt); i++) fn(i); });
+    for (auto &x : th) x.join();
+}
+
+// Device and pinned-host work space of calculate_batch, kept between calls and grown on demand: a sweep that arrives in
+// chunks (result elements are limited to 1..999) pays for cudaMalloc / cudaFree / cudaHostAlloc once.  The device part is
+// cleared at every call, so a case never sees data of an earlier one.  Guarded by `mu`: one batch at a time per process.
+struct BatchPool {
+    std::mutex mu;
+    double *d_buf = nullptr, *d_us = nullptr, *d_pb = nullptr, *h_fld = nullptr, *h_us = nullptr;
+    int *d_el = nullptr, *d_next = nullptr, *h_el = nullptr;
+    ContactCase *d_cases = nullptr;
+    size_t c_buf = 0, c_us = 0, c_pb = 0, c_el = 0, c_cases = 0, c_hfld = 0, c_hus = 0, c_hel = 0;
+};
+inline BatchPool &batch_pool() { static BatchPool p; return p; }
+template <class T> inline bool pool_dev(T *&ptr, size_t &cap, size_t need)
+{
+    if (need <= cap) return true;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; cap = 0;
+    if (cudaMalloc(&ptr, need * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return false; }
+    cap = need;
+    return true;
+}
+template <class T> inline bool pool_pinned(T *&ptr, size_t &cap, size_t need)
+{
+    if (need <= cap) return true;
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr; cap = 0;
+    if (cudaMallocHost(&ptr, need * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return false; }
+    cap = need;
+    return true;
+}
+
 inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int> &ierr)
 {
+    BatchPool &BP = batch_pool();
+    std::lock_guard<std::mutex> pool_lock(BP.mu);
     double *bt = batch_timing();
     for (int k = 0; k < 10; k++) bt[k] = 0.0;
     auto now = [] { return std::chrono::steady_clock::now(); };
@@ -430,15 +475,17 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
         bool any_gd = false;
         for (size_t k : ks) any_gd = any_gd || (probs[k]->tang == 3 && probs[k]->gausei == 5);
         const size_t per = (size_t) (any_gd ? 60 : 44) * npot;
-        double *d_buf = nullptr; int *d_el = nullptr, *d_next = nullptr; ContactCase *d_cases = nullptr;
-        if (cudaMalloc(&d_buf, sizeof(double) * per * n) != cudaSuccess || cudaMalloc(&d_el, sizeof(int) * (size_t) n * npot) != cudaSuccess ||
-            cudaMalloc(&d_cases, sizeof(ContactCase) * n) != cudaSuccess || cudaMalloc(&d_next, sizeof(int)) != cudaSuccess) {
+        if (!pool_dev(BP.d_buf, BP.c_buf, per * n) || !pool_dev(BP.d_el, BP.c_el, (size_t) n * npot) ||
+            !pool_dev(BP.d_cases, BP.c_cases, (size_t) n) || (!BP.d_next && cudaMalloc(&BP.d_next, sizeof(int)) != cudaSuccess) ||
+            !pool_dev(BP.d_us, BP.c_us, (size_t) 3 * npot * n) || !pool_dev(BP.d_pb, BP.c_pb, (size_t) 3 * npot * n) ||
+            !pool_pinned(BP.h_fld, BP.c_hfld, (size_t) 6 * npot * n) || !pool_pinned(BP.h_us, BP.c_hus, (size_t) 3 * npot * n) ||
+            !pool_pinned(BP.h_el, BP.c_hel, (size_t) npot * n)) {
             last_error() = "device allocation failed"; fail(CNTC_err_other);
-            cudaFree(d_buf); cudaFree(d_el); cudaFree(d_cases); cudaFree(d_next);
             continue;
         }
+        double *d_buf = BP.d_buf; int *d_el = BP.d_el, *d_next = BP.d_next; ContactCase *d_cases = BP.d_cases;
+        cudaMemsetAsync(d_buf, 0, sizeof(double) * per * n, 0);
         std::vector<ContactCase> hc(n);
-        std::vector<double> stage((size_t) 6 * npot);
         const size_t nblk = (size_t) 4 * cs.mx * cs.my;
         double c00[2] = { 0, 0 };
         cudaMemcpy(&c00[0], cs.d_cf[SET_CS] + 0 * nblk + (size_t) cs.my * 2 * cs.mx + cs.mx, sizeof(double), cudaMemcpyDeviceToHost);
@@ -487,7 +534,9 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
             c.cf11 = cs.d_cf[SET_CS] + 0 * nblk; c.cf22 = cs.d_cf[SET_CS] + 4 * nblk;
             c.c11 = c00[0]; c.c22 = c00[1]; c.ga = cs.ga;
             // host inputs: hs_n, hst (set_tang_rhs, m_sdis.f90:498-583; shifts: dq = 1), ps
-            std::copy(hs[ks[i]].begin(), hs[ks[i]].end(), stage.begin());
+            double *stage = BP.h_fld + (size_t) i * 6 * npot;       // pinned staging [n][6 npot], one strided upload below
+            std::fill(stage, stage + 6 * (size_t) npot, 0.0);
+            std::copy(hs[ks[i]].begin(), hs[ks[i]].end(), stage);
             // rolling: spin pole shifted by facphi*dq along the rolling direction (facphi = 1/6, m_sinput.f90:789-793)
             const double dq = dq_e, facphi = 1.0 / 6.0;
             const double xofs = is_roll ? cos(chi_e) * dq * facphi : 0.0, yofs = is_roll ? sin(chi_e) * dq * facphi : 0.0;
@@ -499,11 +548,11 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
                 if (p.force3 <= 1) wy += p.ceta;
                 stage[npot + ii] = -dq * wx; stage[2 * (size_t) npot + ii] = -dq * wy;
             }
-            std::copy(p.ps.begin(), p.ps.end(), stage.begin() + 3 * (size_t) npot);
-            cudaMemcpy(base, stage.data(), sizeof(double) * 6 * npot, cudaMemcpyHostToDevice);
-            cudaMemcpy(nc.el, el0[ks[i]].data(), sizeof(int) * npot, cudaMemcpyHostToDevice);
+            std::copy(p.ps.begin(), p.ps.end(), stage + 3 * (size_t) npot);
+            std::copy(el0[ks[i]].begin(), el0[ks[i]].end(), BP.h_el + (size_t) i * npot);
         }
-        cudaMemset(d_buf + 6 * (size_t) npot, 0, 0);
+        cudaMemcpy2DAsync(d_buf, sizeof(double) * per, BP.h_fld, sizeof(double) * 6 * npot, sizeof(double) * 6 * npot, n, cudaMemcpyHostToDevice, 0);
+        cudaMemcpyAsync(d_el, BP.h_el, sizeof(int) * (size_t) npot * n, cudaMemcpyHostToDevice, 0);
         cudaMemcpy(d_cases, hc.data(), sizeof(ContactCase) * n, cudaMemcpyHostToDevice);
         cudaMemset(d_next, 0, sizeof(int));
         auto tg2 = now();
@@ -532,31 +581,37 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
         else {
             cudaMemcpy(hc.data(), d_cases, sizeof(ContactCase) * n, cudaMemcpyDeviceToHost);
             // soutpt (m_soutpt.f90:378-398): us = A ps on the contact area, all directions
-            double *d_us = nullptr, *d_pb = nullptr;
-            cudaMalloc(&d_us, sizeof(double) * 3 * (size_t) npot * n); cudaMalloc(&d_pb, sizeof(double) * 3 * (size_t) npot * n);
-            cudaMemset(d_us, 0, sizeof(double) * 3 * (size_t) npot * n);
-            for (int i = 0; i < n; i++) cudaMemcpy(d_pb + (size_t) i * 3 * npot, hc[i].ps, sizeof(double) * 3 * npot, cudaMemcpyDeviceToDevice);
+            double *d_us = BP.d_us, *d_pb = BP.d_pb;
+            cudaMemsetAsync(d_us, 0, sizeof(double) * 3 * (size_t) npot * n, 0);
+            // tractions of all cases [n][3][npot] (the case records are `per` doubles apart)
+            cudaMemcpy2DAsync(d_pb, sizeof(double) * 3 * npot, d_buf + 3 * (size_t) npot, sizeof(double) * per, sizeof(double) * 3 * npot, n,
+                              cudaMemcpyDeviceToDevice, 0);
             rc = vecaijpj_dev(cs, SET_CS, n, -8, any_tang ? -3 : 3, any_tang ? -3 : 3, d_pb, d_el, d_us, 0);
-            std::vector<double> h_us((size_t) 3 * npot * n);
-            cudaMemcpy(h_us.data(), d_us, sizeof(double) * h_us.size(), cudaMemcpyDeviceToHost);
-            cudaFree(d_us); cudaFree(d_pb);
+            cudaMemcpyAsync(BP.h_us, d_us, sizeof(double) * 3 * (size_t) npot * n, cudaMemcpyDeviceToHost, 0);
             auto to1 = now();
             bt[6] += secs(tg3, to1);
-            for (int i = 0; i < n; i++) {
+            // one strided download of ps (3 npot) + ss (2 npot) of every case and one of the element divisions, into pinned memory
+            cudaMemcpy2DAsync(BP.h_fld, sizeof(double) * 5 * npot, d_buf + 3 * (size_t) npot, sizeof(double) * per, sizeof(double) * 5 * npot, n,
+                              cudaMemcpyDeviceToHost, 0);
+            cudaMemcpyAsync(BP.h_el, d_el, sizeof(int) * (size_t) npot * n, cudaMemcpyDeviceToHost, 0);
+            cudaStreamSynchronize(0);
+            const double *h_us = BP.h_us;
+            host_parallel_for(n, [&](int i) {
                 Problem &p = *probs[ks[i]];
-                const ContactCase &c = hc[i];
-                p.el.resize(npot); p.ps.assign(3 * (size_t) npot, 0.0); p.ss.assign(3 * (size_t) npot, 0.0);
-                cudaMemcpy(p.el.data(), c.nrm.el, sizeof(int) * npot, cudaMemcpyDeviceToHost);
-                cudaMemcpy(p.ps.data(), c.ps, sizeof(double) * 3 * npot, cudaMemcpyDeviceToHost);
-                if (p.tang != 0) cudaMemcpy(p.ss.data(), c.ss, sizeof(double) * 2 * npot, cudaMemcpyDeviceToHost);
-            }
+                const double *f = BP.h_fld + (size_t) i * 5 * npot;
+                p.el.assign(BP.h_el + (size_t) i * npot, BP.h_el + (size_t) (i + 1) * npot);
+                p.ps.assign(f, f + 3 * (size_t) npot);
+                p.ss.assign(3 * (size_t) npot, 0.0);
+                if (p.tang != 0) std::copy(f + 3 * (size_t) npot, f + 5 * (size_t) npot, p.ss.begin());
+            });
             auto to2 = now();
             bt[7] += secs(to1, to2);
-            for (int i = 0; i < n; i++) {
+            std::atomic<int> unserved(0);
+            host_parallel_for(n, [&](int i) {
                 Problem &p = *probs[ks[i]];
                 const ContactCase &c = hc[i];
                 if (p.tang >= 2) p.dq_eff = c.dq;
-                p.us.assign(h_us.begin() + (size_t) i * 3 * npot, h_us.begin() + (size_t) (i + 1) * 3 * npot);
+                p.us.assign(h_us + (size_t) i * 3 * npot, h_us + (size_t) (i + 1) * 3 * npot);
                 p.hs.assign(3 * (size_t) npot, 0.0);
                 std::copy(hs[ks[i]].begin(), hs[ks[i]].end(), p.hs.begin() + 2 * (size_t) npot);
                 p.pen = c.nrm.pen; p.fntrue = c.nrm.fntrue; p.itcg = c.nrm.itcg; p.itnorm = c.nrm.itnorm; p.ncon = c.nrm.ncon;
@@ -583,15 +638,15 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
                 } else { p.fcntc[0] = p.fcntc[1] = 0.0; p.mztrue = 0.0; }
                 p.fcntc[2] = p.fntrue;
                 p.solved = true;
-                if (c.tstatus & 1) { last_error() = "TANG: the case needs a solver that the B200 path does not serve (a Gauss-Seidel solver -- also as the fall-back of a stagnating GDsteady -- on a grid beyond one CTA)"; ierr[ks[i]] = CNTC_err_other; }
+                if (c.tstatus & 1) { unserved = 1; ierr[ks[i]] = CNTC_err_other; }
                 else if (p.itnorm < 0 || (p.status & 1)) ierr[ks[i]] = CNTC_err_norm;
                 else if (p.ittang < 0) ierr[ks[i]] = CNTC_err_tang;
                 else ierr[ks[i]] = count_at_boundary(p);              // contact_addon.f90:3885-3891
-            }
+            });
+            if (unserved) last_error() = "TANG: the case needs a solver that the B200 path does not serve (a Gauss-Seidel solver -- also as the fall-back of a stagnating GDsteady -- on a grid beyond one CTA)";
             bt[8] += secs(to2, now());
         }
-        auto tf0 = now();
-        cudaFree(d_buf); cudaFree(d_el); cudaFree(d_cases); cudaFree(d_next);
+        auto tf0 = now();                                          // (buffers stay in the pool)
         bt[9] += secs(tf0, now());
         bt[4] += secs(tg3, now());
     }
@@ -1219,6 +1274,12 @@ void cntc_finalizelast(void)
     Registry &R = registry();
     std::lock_guard<std::mutex> lk(R.mu);
     R.res.clear();
+    BatchPool &BP = batch_pool();                              // release the work space of calculate_batch
+    std::lock_guard<std::mutex> pl(BP.mu);
+    cudaFree(BP.d_buf); cudaFree(BP.d_us); cudaFree(BP.d_pb); cudaFree(BP.d_el); cudaFree(BP.d_next); cudaFree(BP.d_cases);
+    cudaFreeHost(BP.h_fld); cudaFreeHost(BP.h_us); cudaFreeHost(BP.h_el);
+    BP.d_buf = BP.d_us = BP.d_pb = BP.h_fld = BP.h_us = nullptr; BP.d_el = BP.d_next = BP.h_el = nullptr; BP.d_cases = nullptr;
+    BP.c_buf = BP.c_us = BP.c_pb = BP.c_el = BP.c_cases = BP.c_hfld = BP.c_hus = BP.c_hel = 0;
 }
 
 }  // extern "C"
