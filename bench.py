@@ -151,13 +151,16 @@ def sweep4096_leg(cb, rank, world, total=4096, chunk=888):
     today's perfc_test/tang_problm_*c.inp), a fixed total sharded over the ranks (contiguous blocks, no data-path
     collective), each rank in chunks of at most `chunk` cases per cntc_calculate_batch call (result elements are 1..999)."""
     lo, hi = (total * rank) // world, (total * (rank + 1)) // world
-    s, kms, n, err, fb, its = 0.0, 0.0, 0, 0, 0, 0.0
+    s, kms, n, err, fb, its, splits = 0.0, 0.0, 0, 0, 0, 0.0, []
     for a in range(lo, hi, chunk):
         m = min(chunk, hi - a)
         r = rolling_sweep_leg(cb, m, a, gausei=5)
         s += r["s"]; kms += r["solver_kernel_ms"]; n += m; err += r["errors"]; fb += r["fallbacks_to_steadygs"]
         its += r["mean_itgs"] * m
-    return {"cases": n, "s": s, "solver_kernel_ms": kms, "errors": err, "fallbacks_to_steadygs": fb, "mean_itgd": its / max(1, n)}
+        w = r["wall_split_s"]
+        splits.append([m] + [round(w[k], 4) for k in ("setup", "coefficients", "upload", "kernel", "output", "total")] + [round(r["s"], 4)])
+    return {"cases": n, "s": s, "solver_kernel_ms": kms, "errors": err, "fallbacks_to_steadygs": fb, "mean_itgd": its / max(1, n),
+            "chunks": splits}
 
 
 def spence71_leg(cb):
@@ -491,6 +494,8 @@ def run_gpu(args):
                                 "solver_kernel_ms_max_rank": float(tmax[7]), "cases_this_rank": sweep["cases"],
                                 "errors_this_rank": sweep["errors"], "fallbacks_this_rank": sweep["fallbacks_to_steadygs"],
                                 "mean_itgd_this_rank": sweep["mean_itgd"], "scaling": "strong",
+                                "chunks_this_rank": {"columns": ["cases", "setup", "coefficients", "upload", "kernel", "output", "total", "wall"],
+                                                     "rows": sweep["chunks"]},
                                 "note": "BASELINE config 5: 4096 mbench 71x81 cases (PEN and creepage draws of seed 20240229), T=3 GDsteady, "
                                         "eps 1e-5, host buffers through cntc_calculate_batch in chunks of <= 888 cases; wall clock, max over ranks"}
         if large:

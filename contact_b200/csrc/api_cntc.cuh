@@ -490,7 +490,7 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
         double c00[2] = { 0, 0 };
         cudaMemcpy(&c00[0], cs.d_cf[SET_CS] + 0 * nblk + (size_t) cs.my * 2 * cs.mx + cs.mx, sizeof(double), cudaMemcpyDeviceToHost);
         cudaMemcpy(&c00[1], cs.d_cf[SET_CS] + 4 * nblk + (size_t) cs.my * 2 * cs.mx + cs.mx, sizeof(double), cudaMemcpyDeviceToHost);
-        for (int i = 0; i < n; i++) {
+        host_parallel_for(n, [&](int i) {                            // per-case records and pinned staging: independent
             Problem &p = *probs[ks[i]];
             double *base = d_buf + per * i;
             ContactCase &c = hc[i];
@@ -550,7 +550,7 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
             }
             std::copy(p.ps.begin(), p.ps.end(), stage + 3 * (size_t) npot);
             std::copy(el0[ks[i]].begin(), el0[ks[i]].end(), BP.h_el + (size_t) i * npot);
-        }
+        });
         cudaMemcpy2DAsync(d_buf, sizeof(double) * per, BP.h_fld, sizeof(double) * 6 * npot, sizeof(double) * 6 * npot, n, cudaMemcpyHostToDevice, 0);
         cudaMemcpyAsync(d_el, BP.h_el, sizeof(int) * (size_t) npot * n, cudaMemcpyHostToDevice, 0);
         cudaMemcpy(d_cases, hc.data(), sizeof(ContactCase) * n, cudaMemcpyHostToDevice);
