@@ -387,6 +387,12 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
         combine_material(p.mat);
         if (p.ncase <= 1) p.pvtime = 2;                                   // check_case, m_scontc.f90:268-274
         if (p.ipotcn < 0 && (ierr[k] = hertz_setup(p))) continue;         // contac, m_scontc.f90:81-91
+    }
+    // the O(npot) part of the set-up is independent per case: over host threads
+    host_parallel_for((int) nb, [&](int kk) {
+        const size_t k = (size_t) kk;
+        if (ierr[k]) return;
+        Problem &p = *probs[k];
         undeformed_distance(p, hs[k]);
         const int npot = p.mx * p.my;
         const bool have_prev = p.solved && (int) p.el.size() == npot && (int) p.ps.size() == 3 * npot;
@@ -425,6 +431,10 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
             for (int i = 0; i < npot; i++) if (hs[k][i] > (double) 1e29f) el0[k][i] = 0;
         }
         pen0[k] = pen;
+    });
+    for (size_t k = 0; k < nb; k++) {
+        if (ierr[k]) continue;
+        Problem &p = *probs[k];
         if (p.ret > 1) { ierr[k] = 0; continue; }                        // R=2,3: checks only
         CoefSet *cs = nullptr;
         double chi_e, dq_e;
@@ -475,11 +485,14 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
         bool any_gd = false;
         for (size_t k : ks) any_gd = any_gd || (probs[k]->tang == 3 && probs[k]->gausei == 5);
         const size_t per = (size_t) (any_gd ? 60 : 44) * npot;
+        // pinned staging is bounded (48 MB of case records): page-locking hundreds of MB costs more than the transfers, and
+        // far more when several ranks of one host do it at once; the cases move in groups of `gcap`
+        const int gcap = std::max(1, std::min(n, (int) ((size_t) (48u << 20) / (sizeof(double) * 6 * npot))));
         if (!pool_dev(BP.d_buf, BP.c_buf, per * n) || !pool_dev(BP.d_el, BP.c_el, (size_t) n * npot) ||
             !pool_dev(BP.d_cases, BP.c_cases, (size_t) n) || (!BP.d_next && cudaMalloc(&BP.d_next, sizeof(int)) != cudaSuccess) ||
             !pool_dev(BP.d_us, BP.c_us, (size_t) 3 * npot * n) || !pool_dev(BP.d_pb, BP.c_pb, (size_t) 3 * npot * n) ||
-            !pool_pinned(BP.h_fld, BP.c_hfld, (size_t) 6 * npot * n) || !pool_pinned(BP.h_us, BP.c_hus, (size_t) 3 * npot * n) ||
-            !pool_pinned(BP.h_el, BP.c_hel, (size_t) npot * n)) {
+            !pool_pinned(BP.h_fld, BP.c_hfld, (size_t) 6 * npot * gcap) || !pool_pinned(BP.h_us, BP.c_hus, (size_t) 3 * npot * gcap) ||
+            !pool_pinned(BP.h_el, BP.c_hel, (size_t) npot * gcap)) {
             last_error() = "device allocation failed"; fail(CNTC_err_other);
             continue;
         }
@@ -490,7 +503,10 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
         double c00[2] = { 0, 0 };
         cudaMemcpy(&c00[0], cs.d_cf[SET_CS] + 0 * nblk + (size_t) cs.my * 2 * cs.mx + cs.mx, sizeof(double), cudaMemcpyDeviceToHost);
         cudaMemcpy(&c00[1], cs.d_cf[SET_CS] + 4 * nblk + (size_t) cs.my * 2 * cs.mx + cs.mx, sizeof(double), cudaMemcpyDeviceToHost);
-        host_parallel_for(n, [&](int i) {                            // per-case records and pinned staging: independent
+        for (int g0 = 0; g0 < n; g0 += gcap) {
+        const int gm = std::min(gcap, n - g0);
+        host_parallel_for(gm, [&](int j) {                           // per-case records and pinned staging: independent
+            const int i = g0 + j;
             Problem &p = *probs[ks[i]];
             double *base = d_buf + per * i;
             ContactCase &c = hc[i];
@@ -534,7 +550,7 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
             c.cf11 = cs.d_cf[SET_CS] + 0 * nblk; c.cf22 = cs.d_cf[SET_CS] + 4 * nblk;
             c.c11 = c00[0]; c.c22 = c00[1]; c.ga = cs.ga;
             // host inputs: hs_n, hst (set_tang_rhs, m_sdis.f90:498-583; shifts: dq = 1), ps
-            double *stage = BP.h_fld + (size_t) i * 6 * npot;       // pinned staging [n][6 npot], one strided upload below
+            double *stage = BP.h_fld + (size_t) j * 6 * npot;       // pinned staging [gcap][6 npot], one strided upload per group
             std::fill(stage, stage + 6 * (size_t) npot, 0.0);
             std::copy(hs[ks[i]].begin(), hs[ks[i]].end(), stage);
             // rolling: spin pole shifted by facphi*dq along the rolling direction (facphi = 1/6, m_sinput.f90:789-793)
@@ -549,10 +565,12 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
                 stage[npot + ii] = -dq * wx; stage[2 * (size_t) npot + ii] = -dq * wy;
             }
             std::copy(p.ps.begin(), p.ps.end(), stage + 3 * (size_t) npot);
-            std::copy(el0[ks[i]].begin(), el0[ks[i]].end(), BP.h_el + (size_t) i * npot);
+            std::copy(el0[ks[i]].begin(), el0[ks[i]].end(), BP.h_el + (size_t) j * npot);
         });
-        cudaMemcpy2DAsync(d_buf, sizeof(double) * per, BP.h_fld, sizeof(double) * 6 * npot, sizeof(double) * 6 * npot, n, cudaMemcpyHostToDevice, 0);
-        cudaMemcpyAsync(d_el, BP.h_el, sizeof(int) * (size_t) npot * n, cudaMemcpyHostToDevice, 0);
+        cudaMemcpy2DAsync(d_buf + per * g0, sizeof(double) * per, BP.h_fld, sizeof(double) * 6 * npot, sizeof(double) * 6 * npot, gm, cudaMemcpyHostToDevice, 0);
+        cudaMemcpyAsync(d_el + (size_t) g0 * npot, BP.h_el, sizeof(int) * (size_t) npot * gm, cudaMemcpyHostToDevice, 0);
+        cudaStreamSynchronize(0);                                   // the staging is refilled by the next group
+        }
         cudaMemcpy(d_cases, hc.data(), sizeof(ContactCase) * n, cudaMemcpyHostToDevice);
         cudaMemset(d_next, 0, sizeof(int));
         auto tg2 = now();
@@ -587,23 +605,26 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
             cudaMemcpy2DAsync(d_pb, sizeof(double) * 3 * npot, d_buf + 3 * (size_t) npot, sizeof(double) * per, sizeof(double) * 3 * npot, n,
                               cudaMemcpyDeviceToDevice, 0);
             rc = vecaijpj_dev(cs, SET_CS, n, -8, any_tang ? -3 : 3, any_tang ? -3 : 3, d_pb, d_el, d_us, 0);
-            cudaMemcpyAsync(BP.h_us, d_us, sizeof(double) * 3 * (size_t) npot * n, cudaMemcpyDeviceToHost, 0);
             auto to1 = now();
             bt[6] += secs(tg3, to1);
-            // one strided download of ps (3 npot) + ss (2 npot) of every case and one of the element divisions, into pinned memory
-            cudaMemcpy2DAsync(BP.h_fld, sizeof(double) * 5 * npot, d_buf + 3 * (size_t) npot, sizeof(double) * per, sizeof(double) * 5 * npot, n,
-                              cudaMemcpyDeviceToHost, 0);
-            cudaMemcpyAsync(BP.h_el, d_el, sizeof(int) * (size_t) npot * n, cudaMemcpyDeviceToHost, 0);
-            cudaStreamSynchronize(0);
-            const double *h_us = BP.h_us;
-            host_parallel_for(n, [&](int i) {
-                Problem &p = *probs[ks[i]];
-                const double *f = BP.h_fld + (size_t) i * 5 * npot;
-                p.el.assign(BP.h_el + (size_t) i * npot, BP.h_el + (size_t) (i + 1) * npot);
-                p.ps.assign(f, f + 3 * (size_t) npot);
-                p.ss.assign(3 * (size_t) npot, 0.0);
-                if (p.tang != 0) std::copy(f + 3 * (size_t) npot, f + 5 * (size_t) npot, p.ss.begin());
-            });
+            // per group of cases: one strided download of ps (3 npot) + ss (2 npot), one of us and one of the element divisions
+            for (int g0 = 0; g0 < n; g0 += gcap) {
+                const int gm = std::min(gcap, n - g0);
+                cudaMemcpyAsync(BP.h_us, d_us + (size_t) g0 * 3 * npot, sizeof(double) * 3 * (size_t) npot * gm, cudaMemcpyDeviceToHost, 0);
+                cudaMemcpy2DAsync(BP.h_fld, sizeof(double) * 5 * npot, d_buf + per * g0 + 3 * (size_t) npot, sizeof(double) * per, sizeof(double) * 5 * npot, gm,
+                                  cudaMemcpyDeviceToHost, 0);
+                cudaMemcpyAsync(BP.h_el, d_el + (size_t) g0 * npot, sizeof(int) * (size_t) npot * gm, cudaMemcpyDeviceToHost, 0);
+                cudaStreamSynchronize(0);
+                host_parallel_for(gm, [&](int j) {
+                    Problem &p = *probs[ks[g0 + j]];
+                    const double *f = BP.h_fld + (size_t) j * 5 * npot;
+                    p.el.assign(BP.h_el + (size_t) j * npot, BP.h_el + (size_t) (j + 1) * npot);
+                    p.ps.assign(f, f + 3 * (size_t) npot);
+                    p.ss.assign(3 * (size_t) npot, 0.0);
+                    if (p.tang != 0) std::copy(f + 3 * (size_t) npot, f + 5 * (size_t) npot, p.ss.begin());
+                    p.us.assign(BP.h_us + (size_t) j * 3 * npot, BP.h_us + (size_t) (j + 1) * 3 * npot);
+                });
+            }
             auto to2 = now();
             bt[7] += secs(to1, to2);
             std::atomic<int> unserved(0);
@@ -611,7 +632,6 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
                 Problem &p = *probs[ks[i]];
                 const ContactCase &c = hc[i];
                 if (p.tang >= 2) p.dq_eff = c.dq;
-                p.us.assign(h_us + (size_t) i * 3 * npot, h_us + (size_t) (i + 1) * 3 * npot);
                 p.hs.assign(3 * (size_t) npot, 0.0);
                 std::copy(hs[ks[i]].begin(), hs[ks[i]].end(), p.hs.begin() + 2 * (size_t) npot);
                 p.pen = c.nrm.pen; p.fntrue = c.nrm.fntrue; p.itcg = c.nrm.itcg; p.itnorm = c.nrm.itnorm; p.ncon = c.nrm.ncon;

@@ -1026,6 +1026,47 @@ def test_inp_tang_problm_c_gdsteady(cb, O):
     assert res[0]["nslip"] == 1872 and res[0]["ncon"] == 3148          # perfc_test/get_times.ref_out:7, :25
 
 
+LEDGE_INP_CASE = """
+ 3  MODULE
+  %(P)d03100          P-B-T-N-F-S
+  022020          L-D-C-M-Z-E
+  %(G)d%(I)d0241          G-I-A-O-W-R
+   500  50    30     1      1e-6      MAXGS , MAXIN , MAXNR , MAXOUT, EPS
+%(relax)s  9000.     0.0006      0.0004       0.0002        FN, CKSI, CETA, CPHI
+  0.250       0.250                                 FSTAT, FKIN
+  0.000       0.500      30000.                     CHI, DQ, VELOC
+  0.280       0.280      82000.      82000.         POISS 1,2,  GG 1,2
+    1                                               IPOTCN
+   34   27   -3.400     -2.700   0.200   0.200      MX,MY,XL,YL,DX,DY
+       1           1                                IBASE, IPLAN
+   0.004  0.0  0.006  0.0  0.0  0.0
+"""
+
+
+def test_inp_leading_edge_dq_gt_dx(cb, O):
+    """.inp text with DQ = 2.5 DX: a steady-rolling case with ConvexGS (G=2: leading-edge equations inside the solver) followed
+    by three transient steps (T=2, P=0, I=1, TangCG: ubnd in the right-hand side), reader + cntc_calculate against the oracle
+    run from the same parsed cases."""
+    from contact_b200 import inp as INP
+    from tests import inp_oracle
+    relax = "   0.90       0.90     0     1.10               OMEGAH, OMEGAS, INISLP, OMGSLP\n"
+    text = LEDGE_INP_CASE.replace("%(P)d03100", "203100") % dict(G=2, I=0, relax=relax)
+    step = LEDGE_INP_CASE.replace("%(P)d03100", "002100") % dict(G=0, I=1, relax="")
+    text = text + step * 3 + " 0  MODULE\n"
+    cases_ = INP.parse_inp(text)
+    assert [c["T"] for c in cases_] == [3, 2, 2, 2] and all(c["roll"]["dq"] == 0.5 for c in cases_)
+    res = INP.run_inp(text, ire=85)
+    ref = inp_oracle.run_cases(cases_)
+    assert [r["ierror"] for r in res] == [0] * 4, [r.get("message") for r in res]
+    assert ref[0]["itgs_tang"] == 49                                  # ConvexGS sweeps of the oracle on this case
+    for r, o in zip(res, ref):
+        assert o["ierror"] == 0
+        assert np.array_equal(r["el"].ravel(), o["el"])
+        assert r["its"]["itgs"] == o["itgs_tang"]
+        s_ = np.abs(o["ps"][:2]).max()
+        assert np.abs(r["px"].ravel() - o["ps"][0]).max() < 1e-6 * s_ and np.abs(r["py"].ravel() - o["ps"][1]).max() < 1e-6 * s_
+
+
 def test_inp_sequence_cattaneo(cb, O):
     """examples/cattaneo.inp: Hertzian input (IPOTCN=-3) and the Cattaneo shift with prescribed forces, against
     examples/cattaneo.ref_out."""
