@@ -17,9 +17,25 @@ def _sources():
     return out
 
 
+STAMP = os.path.join(LIBDIR, "build_stamp.txt")
+
+
+def _digest():
+    """Content hash of all sources: the staleness test (mtimes miss an edit made while a 4-minute nvcc run is under way)."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in _sources():
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def needs_build():
     if not os.path.exists(SO):
         return True
+    if os.path.exists(STAMP):
+        return open(STAMP).read().strip() != _digest()
     t = os.path.getmtime(SO)
     return any(os.path.getmtime(s) > t for s in _sources())
 
@@ -28,6 +44,7 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return SO
     os.makedirs(LIBDIR, exist_ok=True)
+    digest = _digest()                      # of the sources as they are when the compiler starts
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
            "-Xcompiler", "-fPIC", "-shared", "-o", SO, os.path.join(CSRC, "contact_addon_b200.cu")]
@@ -40,6 +57,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libcontact_addon_b200.so")
     if verbose:
         sys.stderr.write(r.stderr)
+    with open(STAMP, "w") as fh:
+        fh.write(digest + "\n")
     return SO
 
 
