@@ -152,8 +152,10 @@ def sweep4096_leg(cb, rank, world, total=4096, chunk=888):
     collective), each rank in chunks of at most `chunk` cases per cntc_calculate_batch call (result elements are 1..999)."""
     lo, hi = (total * rank) // world, (total * (rank + 1)) // world
     s, kms, n, err, fb, its, splits = 0.0, 0.0, 0, 0, 0, 0.0, []
-    for a in range(lo, hi, chunk):
-        m = min(chunk, hi - a)
+    nch = max(1, -(-(hi - lo) // chunk))                   # equal chunks (a short last chunk would leave most SMs idle)
+    bounds = [lo + ((hi - lo) * k) // nch for k in range(nch + 1)]
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        m = b - a
         r = rolling_sweep_leg(cb, m, a, gausei=5)
         s += r["s"]; kms += r["solver_kernel_ms"]; n += m; err += r["errors"]; fb += r["fallbacks_to_steadygs"]
         its += r["mean_itgs"] * m
