@@ -215,6 +215,8 @@ inline int check_scope(const Problem &p)
     if (p.iplan != 1) { last_error() = "IPLAN: only the unrestricted planform"; return CNTC_err_other; }
     if (p.ibase != 1 && p.ibase != 2 && p.ibase != 3 && p.ibase != 9) { last_error() = "invalid IBASE"; return CNTC_err_input; }
     if (p.ibase == 9 && (int) p.prmudf.size() < p.mx * p.my) { last_error() = "IBASE=9 needs npot values"; return CNTC_err_input; }
+    if (p.tang != 0 && (p.rztang == 9 || p.exrhs_len > 0)) { last_error() = "E-digit: extra rigid slip (cntc_setextrarigidslip) is not served by the B200 path"; return CNTC_err_other; }
+    if (p.heat_meth >= 1) { last_error() = "H-digit: temperature calculation is outside the hot-path scope"; return CNTC_err_other; }
     return 0;
 }
 
@@ -330,8 +332,13 @@ template <class F> inline void host_parallel_for(int n, F fn)
     const int nt = std::max(1, std::min({ n / 16, (int) std::thread::hardware_concurrency(), 16 }));
     if (nt <= 1) { for (int i = 0; i < n; i++) fn(i); return; }
     std::vector<std::thread> th;
+    int dev = -1;
+    cudaGetDevice(&dev);                             // new threads start on device 0: keep the workers on the caller's device
     for (int t = 0; t < nt; t++)
-        th.emplace_back([=, &fn] { for (int i = (int) ((long) n * t / nt); i < (int) ((long) n * (t + 1) / nt); i++) fn(i); });
+        th.emplace_back([=, &fn] {
+            if (dev >= 0) cudaSetDevice(dev);
+            for (int i = (int) ((long) n * t / nt); i < (int) ((long) n * (t + 1) / nt); i++) fn(i);
+        });
     for (auto &x : th) x.join();
 }
 
@@ -441,7 +448,7 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
         roll_stepsize(p, chi_e, dq_e);
         // latency mode: a single case (the usual call pattern of a multibody code, and of case sequences) would occupy one
         // of 148 SMs on the batched path; with a grid of some size it runs faster spread over the whole GPU
-        const int whole = (nb == 1 && p.tang != 3 && p.mx * p.my >= 1024 && p.mx >= 16 && p.my >= 16) ? 1 : 0;
+        const int whole = (nb == 1 && p.tang != 3 && !(p.tang != 0 && p.gausei == 2) && p.mx * p.my >= 1024 && p.mx >= 16 && p.my >= 16) ? 1 : 0;
         int rc = get_coefset(p.mx, p.my, p.dx, p.dy, p.mat, p.tang >= 2 ? 1 : 0, chi_e, dq_e, 0, &cs, whole);
         if (rc) { ierr[k] = rc; continue; }
         // grids beyond one CTA's shared memory go to the whole-GPU path, which serves T = 0 and T = 1 (TangCG)
@@ -578,8 +585,19 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
         NormBatch &NB = norm_batch();                               // events around the solver kernel(s): cb200_snorm_kernel_ms
         if (!NB.ev0) { cudaEventCreate(&NB.ev0); cudaEventCreate(&NB.ev1); }
         cudaEventRecord(NB.ev0, 0);
+        cudaError_t le = cudaSuccess;
         if (cs.hp.fits) {
-            k_contac_batch<<<launch_blocks(n), CB_THREADS, P.smem_bytes + steady_extra_smem(P)>>>(P, d_cases, n, d_next);
+            // the Gauss-Seidel sweep arrays need room behind the FFT layout on small grids: only when such a case is present
+            bool any_gs = false;
+            for (size_t k : ks) any_gs = any_gs || probs[k]->tang == 3 || (probs[k]->tang != 0 && probs[k]->gausei == 2);
+            const size_t smem = (size_t) P.smem_bytes + (any_gs ? steady_extra_smem(P) : 0);
+            if (smem > (size_t) kSmemMax) {
+                last_error() = "grid shape needs more shared memory than one CTA has for the Gauss-Seidel sweep (thin or 2-D grid)";
+                fail(CNTC_err_discr);
+                continue;
+            }
+            k_contac_batch<<<launch_blocks(n), CB_THREADS, smem>>>(P, d_cases, n, d_next);
+            le = cudaGetLastError();
             engine().launches++;
         } else {
             LargeCtx X;
@@ -587,7 +605,8 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
             for (int i = 0; i < n; i++) {                              // one cooperative whole-GPU launch per case
                 ContactCase *cp = d_cases + i;
                 void *args[] = { (void *) &X, (void *) &cp };
-                cudaLaunchCooperativeKernel((void *) k_lg_contac, dim3(engine().num_sms), dim3(CB_THREADS), args, (size_t) cs.lp.smem_bytes, 0);
+                const cudaError_t ce = cudaLaunchCooperativeKernel((void *) k_lg_contac, dim3(engine().num_sms), dim3(CB_THREADS), args, (size_t) cs.lp.smem_bytes, 0);
+                if (ce != cudaSuccess && le == cudaSuccess) le = ce;
                 engine().launches++;
             }
         }
@@ -595,7 +614,8 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
         cudaError_t e = cudaDeviceSynchronize();
         auto tg3 = now();
         bt[3] += secs(tg2, tg3);
-        if (e != cudaSuccess) { last_error() = std::string("k_contac_batch: ") + cudaGetErrorString(e); fail(CNTC_err_other); }
+        if (le != cudaSuccess) { last_error() = std::string("solver kernel launch: ") + cudaGetErrorString(le); fail(CNTC_err_other); }
+        else if (e != cudaSuccess) { last_error() = std::string("k_contac_batch: ") + cudaGetErrorString(e); fail(CNTC_err_other); }
         else {
             cudaMemcpy(hc.data(), d_cases, sizeof(ContactCase) * n, cudaMemcpyDeviceToHost);
             // soutpt (m_soutpt.f90:378-398): us = A ps on the contact area, all directions
@@ -605,6 +625,7 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
             cudaMemcpy2DAsync(d_pb, sizeof(double) * 3 * npot, d_buf + 3 * (size_t) npot, sizeof(double) * per, sizeof(double) * 3 * npot, n,
                               cudaMemcpyDeviceToDevice, 0);
             rc = vecaijpj_dev(cs, SET_CS, n, -8, any_tang ? -3 : 3, any_tang ? -3 : 3, d_pb, d_el, d_us, 0);
+            if (rc) { fail(rc); continue; }
             auto to1 = now();
             bt[6] += secs(tg3, to1);
             // per group of cases: one strided download of ps (3 npot) + ss (2 npot), one of us and one of the element divisions

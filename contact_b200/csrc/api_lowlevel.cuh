@@ -121,6 +121,7 @@ struct NormBatch {            // persistent device workspace of the batched NORM
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;     // bracket the solver kernel alone (roofline timing)
     // staging for the host-buffer entry point
     long stage_cap = 0;
+    int scal_cap = 0;
     double *s_hs = nullptr, *s_pn = nullptr, *s_un = nullptr, *s_scal = nullptr;
     int *s_el = nullptr;
     cudaStream_t pipe[3] = { nullptr, nullptr, nullptr };   // host-buffer entry point: chunks of the batch alternate over these
@@ -271,7 +272,7 @@ inline int subsurf_batch_dev(CoefSet &cs, int ncase, int nz, const double *z, co
     for (int i = 0; i < nz; i++) if (z[i] < 0.0) A.neg_mask |= (1 << i);
     A.ps = d_ps; A.chat = chat; A.vr = B.d_vr; A.table = d_table;
     A.gg[0] = gg[0]; A.gg[1] = gg[1]; A.poiss[0] = poiss[0]; A.poiss[1] = poiss[1];
-    A.next = B.d_next; A.chat_len = P.chat_len;
+    A.next = B.d_next; A.chat_len = (long) plan_chat_len(P);
     CB_CUDA(cudaMemsetAsync(B.d_next, 0, sizeof(int), st));
     k_subsurf_batch<<<nblk, CB_THREADS, P.smem_bytes, st>>>(P, A);
     E.launches++;
@@ -393,14 +394,19 @@ int cb200_snorm_batch(int handle, int ncase, int ic_norm, int maxgs, int maxin, 
     NormBatch &B = norm_batch();
     const long n = (long) ncase * cs->hp.p.npot;
     if (n > B.stage_cap) {
-        cudaFree(B.s_hs); cudaFree(B.s_pn); cudaFree(B.s_un); cudaFree(B.s_scal); cudaFree(B.s_el);
+        cudaFree(B.s_hs); cudaFree(B.s_pn); cudaFree(B.s_un); cudaFree(B.s_el);
         B.stage_cap = 0;
         CB_CUDA(cudaMalloc(&B.s_hs, sizeof(double) * n));
         CB_CUDA(cudaMalloc(&B.s_pn, sizeof(double) * n));
         CB_CUDA(cudaMalloc(&B.s_un, sizeof(double) * n));
-        CB_CUDA(cudaMalloc(&B.s_scal, sizeof(double) * 8 * ncase));
         CB_CUDA(cudaMalloc(&B.s_el, sizeof(int) * n));
         B.stage_cap = n;
+    }
+    if (ncase > B.scal_cap) {                       // per-case scalars: their own capacity (many cases on a small grid)
+        cudaFree(B.s_scal);
+        B.scal_cap = 0;
+        CB_CUDA(cudaMalloc(&B.s_scal, sizeof(double) * 8 * (size_t) ncase));
+        B.scal_cap = ncase;
     }
     // The batch is cut into chunks (multiples of the SM count: one CTA per case) that alternate over three streams, so
     // that the host->device copy of chunk k+1 and the device->host copy of chunk k-1 run on the copy engines while the

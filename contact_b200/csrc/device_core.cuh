@@ -1,6 +1,7 @@
 // device_core.cuh -- shared-memory view, fused convolution as a device function, deterministic block reductions.
 #pragma once
 #include "fftconv_warp.cuh"
+#include "fftconv2.cuh"
 
 #ifndef CB_THREADS
 #define CB_THREADS 384
@@ -28,11 +29,47 @@ __device__ __forceinline__ Smem smem_view(const ConvPlan &P, unsigned char *base
     return s;
 }
 
+// ---- typed shared-memory accessor of the warp-resident product: element i = 16-byte unit i of the dynamic shared
+//      memory window (ld.shared.v2.f64 / st.shared.v2.f64, never a generic load) ----
+extern __shared__ __align__(16) unsigned char cb_smem_window[];
+struct ShBuf {
+    __device__ __forceinline__ cd ld(uint32_t i) const { return reinterpret_cast<const cd *>(cb_smem_window)[i]; }
+    __device__ __forceinline__ void st(uint32_t i, cd v) const { reinterpret_cast<cd *>(cb_smem_window)[i] = v; }
+};
+
+// ---- bulk-async copy (TMA engine, cp.async.bulk) + mbarrier: used to fetch a plan's twiddle tables ----
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tCB_WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra CB_DONE_%=;\n\tbra CB_WAIT_%=;\n\tCB_DONE_%=:\n\t}" :: "r"(bar), "r"(parity) : "memory");
+}
+
+// Control words of the table cache, kept in the reduction scratch (red[112..113] of the kernel's own plan, common to
+// the products of all level plans of a launch): one mbarrier, the id of the plan whose tables are resident, the parity
+// of the barrier's next phase.
+#define CB_HDR_SLOT 112
+__device__ __forceinline__ volatile int *conv_hdr(const Smem &s) { return reinterpret_cast<volatile int *>(s.red + CB_HDR_SLOT + 1); }
+__device__ __forceinline__ uint32_t conv_hdr_bar(const Smem &s) { return (uint32_t) __cvta_generic_to_shared(s.red + CB_HDR_SLOT); }
+
+// anything else that writes into the S / W window of the plan (the Gauss-Seidel sweep arrays) must forget the tables
+__device__ __forceinline__ void conv_tables_invalidate(const Smem &s) { if (threadIdx.x == 0) conv_hdr(s)[0] = -1; }
+
 __device__ __forceinline__ void smem_load_tables(const ConvPlan &P, const Smem &s)
 {
-    for (int k = threadIdx.x; k < 2 * P.Fx; k += blockDim.x) s.twx[k] = P.twx[k];
-    for (int k = threadIdx.x; k < 2 * P.Fy; k += blockDim.x) s.twy[k] = P.twy[k];
-    for (int k = threadIdx.x; k < P.Lx; k += blockDim.x) s.posx[k] = P.posx[k];
+    if (threadIdx.x == 0) {
+        mbar_init(conv_hdr_bar(s), 1);
+        conv_hdr(s)[0] = -1; conv_hdr(s)[1] = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
 }
 
@@ -47,9 +84,42 @@ __device__ unsigned long long g_conv_prof[4];
 // (smaller) transform size Fx >= bw, Fy >= bh and ITS transformed coefficients: what the reference does for AllInt
 // products (bounding box of the contact area, m_aijpj.f90:774-793).  p must vanish outside the box; u is written inside
 // the box only.  The plan's tables are (re)loaded into shared memory first -- plans of different sizes share the buffer.
+// Warp-resident product (fftconv2.cuh) on the box (x0, y0, bw x bh): rows | columns | rows with one block barrier after
+// each; the plan's twiddle tables are fetched by a bulk-async copy when another plan's are resident.
+__device__ __noinline__ void conv2_box_dev(const ConvPlan &P, const Smem &sm, const double *p, const cd *chat, double *u,
+                                           const int *el, int mask_mode, int add, int x0, int y0, int bw, int bh, int stride)
+{
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const long long t_in = (tid == 0 && blockIdx.x == 0) ? clock64() : 0;
+    const Conv2Plan &c = P.c2;
+    volatile int *hdr = conv_hdr(sm);
+    if (hdr[0] != c.id) {                                       // uniform over the CTA
+        const int par = hdr[1];
+        const uint32_t bar = conv_hdr_bar(sm);
+        __syncthreads();                                        // all have read the control words
+        if (tid == 0) {
+            hdr[0] = c.id; hdr[1] = par ^ 1;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar, (uint32_t) c.tab_len * 16u);
+            bulk_g2s(sm.a0 + (uint32_t) c.off_tab, c.tab, (uint32_t) c.tab_len * 16u, bar);
+        }
+        mbar_wait(bar, (uint32_t) par);
+    }
+    const ShBuf buf;
+    c2_rows_fwd(P, buf, p + (size_t) y0 * stride + x0, bw, bh, stride, warp);
+    __syncthreads();
+    c2_cols(P, buf, chat, bh, bh, warp);
+    __syncthreads();
+    c2_rows_inv(P, buf, u, el, mask_mode, add, x0, y0, bw, bh, stride, warp);
+    __syncthreads();
+    if (tid == 0 && blockIdx.x == 0) { g_conv_prof[0] += 1; g_conv_prof[1] += (unsigned long long) (clock64() - t_in); }
+}
+
 __device__ __noinline__ void conv_box_dev(const ConvPlan &P, const Smem &sm, const double *p, const cd *chat, double *u,
                                           const int *el, int mask_mode, int add, int x0, int y0, int bw, int bh, int stride)
 {
+    if (P.c2.ok) { conv2_box_dev(P, sm, p, chat, u, el, mask_mode, add, x0, y0, bw, bh, stride); return; }
+    conv_tables_invalidate(sm);                                 // this path overwrites the window of the other one
     const int tid = threadIdx.x, nthr = blockDim.x;
     const long long t_in = (tid == 0 && blockIdx.x == 0) ? clock64() : 0;
     typedef MemBuf<cd> CB_BUF;

@@ -169,6 +169,34 @@ inline int build_chat_large(CoefSet &cs, int set, int ik, int jk, cudaStream_t s
     return 0;
 }
 
+// cd elements of one transformed block in the layout the plan's product reads
+inline size_t plan_chat_len(const ConvPlan &P) { return P.c2.ok ? (size_t) P.c2.chat_len : (size_t) P.chat_len; }
+
+// transform nblk consecutive spatial blocks (4 cmx cmy doubles each) into chat (plan_chat_len each); synchronises st
+inline int launch_build_chat(const ConvPlan &P, const double *cf, int nblk, int cmx, int cmy, double scale, cd *chat,
+                             cudaStream_t st)
+{
+    Engine &E = engine();
+    cd *scr = nullptr;
+    if (P.c2.ok) {
+        const int n = 2 * P.Fy * (P.Fx + 1);
+        CB_CUDA(cudaMalloc(&scr, sizeof(cd) * (size_t) n * nblk));
+        CB_CUDA(cudaMemsetAsync(chat, 0, sizeof(cd) * plan_chat_len(P) * nblk, st));      // padding columns of the last group
+        k_chat2_rows<<<dim3(grid1d(n, 128), nblk), 128, 0, st>>>(P, cf, cmx, cmy, scr);
+        k_chat2_cols<<<dim3(grid1d(n, 128), nblk), 128, 0, st>>>(P, scr, scale, chat);
+        E.launches += 2;
+    } else {
+        const size_t nscr = (size_t) (P.Lx + 1) * 2 * P.Fy + (size_t) P.Ly * P.C;
+        CB_CUDA(cudaMalloc(&scr, sizeof(cd) * nscr * nblk));
+        k_build_chat<<<nblk, CB_THREADS, 64, st>>>(P, cf, cmx, cmy, scale, scr, chat);
+        E.launches++;
+    }
+    CB_CUDA(cudaGetLastError());
+    CB_CUDA(cudaStreamSynchronize(st));
+    CB_CUDA(cudaFree(scr));
+    return 0;
+}
+
 // ---- coefficient transform of one block ----
 inline int build_chat(CoefSet &cs, int set, int ik, int jk, cudaStream_t st)
 {
@@ -176,17 +204,12 @@ inline int build_chat(CoefSet &cs, int set, int ik, int jk, cudaStream_t st)
     if (cs.d_chat[set][ik - 1][jk - 1]) return 0;
     if (!cs.hp.fits) return build_chat_large(cs, set, ik, jk, st);
     const ConvPlan &P = cs.hp.p;
-    cd *chat = nullptr, *SWg = nullptr;
-    CB_CUDA(cudaMalloc(&chat, sizeof(cd) * (size_t) P.chat_len));
-    CB_CUDA(cudaMalloc(&SWg, sizeof(cd) * ((size_t) (P.Lx + 1) * 2 * P.Fy + (size_t) P.Ly * P.C)));
+    cd *chat = nullptr;
+    CB_CUDA(cudaMalloc(&chat, sizeof(cd) * plan_chat_len(P)));
     const double *blk = cs.d_cf[set] + (size_t) ((jk - 1) * 3 + (ik - 1)) * 4 * cs.mx * cs.my;
     const double scale = cs.ga_inv / (4.0 * P.Fx * P.Fy);
-    const int smem = (2 * P.Fx + 2 * P.Fy) * 16 + P.Lx * 2 + 64;
-    k_build_chat<<<1, CB_THREADS, smem, st>>>(P, blk, cs.mx, cs.my, scale, SWg, chat);
-    E.launches++;
-    CB_CUDA(cudaGetLastError());
-    CB_CUDA(cudaStreamSynchronize(st));
-    CB_CUDA(cudaFree(SWg));
+    int rc = launch_build_chat(P, blk, 1, cs.mx, cs.my, scale, chat, st);
+    if (rc) return rc;
     cs.d_chat[set][ik - 1][jk - 1] = chat;
     cs.n_chat_built++;
     return 0;
@@ -230,6 +253,12 @@ inline int build_levels(CoefSet &cs, cudaStream_t st, bool tang = false)
                 CB_CUDA(cudaMemcpyAsync(twy, hp.twy.data(), sizeof(cd) * hp.twy.size(), cudaMemcpyHostToDevice, st));
                 CB_CUDA(cudaMemcpyAsync(posx, hp.posx.data(), sizeof(unsigned short) * hp.posx.size(), cudaMemcpyHostToDevice, st));
                 P.twx = twx; P.twy = twy; P.posx = posx;
+                if (P.c2.ok) {
+                    cd *tab2;
+                    CB_CUDA(cudaMalloc(&tab2, sizeof(cd) * hp.tab2.size()));
+                    CB_CUDA(cudaMemcpyAsync(tab2, hp.tab2.data(), sizeof(cd) * hp.tab2.size(), cudaMemcpyHostToDevice, st));
+                    P.c2.tab = tab2;
+                }
                 L.P = P;
             }
         CB_CUDA(cudaMalloc(&cs.d_lev, sizeof(ConvLevel) * h.size()));
@@ -241,24 +270,19 @@ inline int build_levels(CoefSet &cs, cudaStream_t st, bool tang = false)
     CB_CUDA(cudaMemcpy(h.data(), cs.d_lev, sizeof(ConvLevel) * h.size(), cudaMemcpyDeviceToHost));
     for (size_t l = 1; l < h.size(); l++) {
         const ConvPlan &P = h[l].P;
-        const size_t nscr = (size_t) (P.Lx + 1) * 2 * P.Fy + (size_t) P.Ly * P.C;
         for (int set = 0; set < 2; set++) {
             const bool have33 = h[l].chat[set][2][2] != nullptr, have11 = h[l].chat[set][0][0] != nullptr;
             if (have33 && (!tang || have11)) continue;
-            cd *chat = nullptr, *scr = nullptr;
-            CB_CUDA(cudaMalloc(&chat, sizeof(cd) * 9 * (size_t) P.chat_len));
-            CB_CUDA(cudaMalloc(&scr, sizeof(cd) * 9 * nscr));
-            k_build_chat<<<9, CB_THREADS, 64, st>>>(P, cs.d_cf[set ? SET_MS : SET_CS], cs.mx, cs.my, cs.ga_inv / (4.0 * P.Fx * P.Fy), scr, chat);
-            E.launches++;
-            CB_CUDA(cudaGetLastError());
-            CB_CUDA(cudaStreamSynchronize(st));
-            CB_CUDA(cudaFree(scr));
+            cd *chat = nullptr;
+            CB_CUDA(cudaMalloc(&chat, sizeof(cd) * 9 * plan_chat_len(P)));
+            int rcb = launch_build_chat(P, cs.d_cf[set ? SET_MS : SET_CS], 9, cs.mx, cs.my, cs.ga_inv / (4.0 * P.Fx * P.Fy), chat, st);
+            if (rcb) return rcb;
             for (int jk = 0; jk < 3; jk++) for (int ik = 0; ik < 3; ik++) {
                 const bool diag = ik == jk, nt = (ik == 2) != (jk == 2);
                 if (set == 1 && !diag) continue;                       // the preconditioner has diagonal blocks only
                 if (nt && !cs.nt_cpl) continue;
                 if (set == 1 && !cs.prec_ready[ik]) continue;          // ms(ik,ik) not built: leave null -> full grid
-                h[l].chat[set][ik][jk] = chat + (size_t) (jk * 3 + ik) * P.chat_len;
+                h[l].chat[set][ik][jk] = chat + (size_t) (jk * 3 + ik) * plan_chat_len(P);
             }
         }
     }
@@ -328,7 +352,7 @@ inline int get_coefset(int mx, int my, double dx, double dy, Material mat, int i
     cs->ga = mat.ga; cs->ga_inv = 1.0 / mat.ga;
     cs->nt_cpl = !(fabs(mat.ak) < 1e-6);                             // m_visc.f90:239-243
     if (!make_plan(mx, my, cs->hp)) { last_error() = "unsupported grid size for the FFT product"; delete cs; return -34; }
-    if (whole_gpu) cs->hp.fits = false;
+    if (whole_gpu) { cs->hp.fits = false; cs->hp.p.c2.ok = 0; }
     ConvPlan &P = cs->hp.p;
     CB_CUDA(cudaMalloc(&cs->d_twx, sizeof(cd) * cs->hp.twx.size()));
     CB_CUDA(cudaMalloc(&cs->d_twy, sizeof(cd) * cs->hp.twy.size()));
@@ -337,6 +361,12 @@ inline int get_coefset(int mx, int my, double dx, double dy, Material mat, int i
     CB_CUDA(cudaMemcpyAsync(cs->d_twy, cs->hp.twy.data(), sizeof(cd) * cs->hp.twy.size(), cudaMemcpyHostToDevice, st));
     CB_CUDA(cudaMemcpyAsync(cs->d_posx, cs->hp.posx.data(), sizeof(unsigned short) * cs->hp.posx.size(), cudaMemcpyHostToDevice, st));
     P.twx = cs->d_twx; P.twy = cs->d_twy; P.posx = cs->d_posx;
+    if (P.c2.ok) {
+        cd *tab2;
+        CB_CUDA(cudaMalloc(&tab2, sizeof(cd) * cs->hp.tab2.size()));
+        CB_CUDA(cudaMemcpyAsync(tab2, cs->hp.tab2.data(), sizeof(cd) * cs->hp.tab2.size(), cudaMemcpyHostToDevice, st));
+        P.c2.tab = tab2;
+    }
     if (!cs->hp.fits) {
         if (!make_large_plan(P, E.num_sms, cs->lp)) { last_error() = "grid too large for the whole-GPU FFT product"; delete cs; return -34; }
         CB_CUDA(cudaMalloc(&cs->d_T, sizeof(cd) * (size_t) (P.Lx + 1) * cs->lp.ldT));
@@ -382,20 +412,20 @@ inline int build_subsurf_chat(CoefSet &cs, const std::vector<double> &z, const d
     const ConvPlan &P = cs.hp.p;
     const int nz = (int) z.size();
     const long nblk = 4L * cs.mx * cs.my;
-    cd *chat = nullptr, *scr = nullptr; double *cf = nullptr;
-    const size_t nscr = (size_t) (P.Lx + 1) * 2 * P.Fy + (size_t) P.Ly * P.C;
-    CB_CUDA(cudaMalloc(&chat, sizeof(cd) * (size_t) nz * 36 * P.chat_len));
-    CB_CUDA(cudaMalloc(&scr, sizeof(cd) * nscr * 36));
+    cd *chat = nullptr; double *cf = nullptr;
+    const size_t clen = plan_chat_len(P);
+    CB_CUDA(cudaMalloc(&chat, sizeof(cd) * (size_t) nz * 36 * clen));
     CB_CUDA(cudaMalloc(&cf, sizeof(double) * 36 * nblk));
     for (int iz = 0; iz < nz; iz++) {
         const int neg = z[iz] >= 0.0 ? 1 : -1, ia = neg > 0 ? 0 : 1;
         k_subsurf_coef<<<grid1d(nblk, 64), 64, 0, st>>>(cs.mx, cs.my, cs.key.dx, cs.key.dy, gg[ia], poiss[ia], z[iz], neg, cf);
-        k_build_chat<<<36, CB_THREADS, 64, st>>>(P, cf, cs.mx, cs.my, 1.0 / (4.0 * P.Fx * P.Fy), scr, chat + (size_t) iz * 36 * P.chat_len);
-        E.launches += 2;
+        E.launches++;
+        int rcb = launch_build_chat(P, cf, 36, cs.mx, cs.my, 1.0 / (4.0 * P.Fx * P.Fy), chat + (size_t) iz * 36 * clen, st);
+        if (rcb) return rcb;
     }
     CB_CUDA(cudaGetLastError());
     CB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(scr); cudaFree(cf);
+    cudaFree(cf);
     cs.subs_chat[key] = chat;
     *out = chat;
     return 0;

@@ -36,6 +36,24 @@ struct StageK {
     uint32_t mg_m;              // div_magic(m)
 };
 
+// Plan of the warp-resident product (fftconv2.cuh): row transforms Lx = Ax * Bx, column transforms Ly = Ay * By, every
+// transform stays inside one warp (private W slot, __syncwarp only); filled by make_plan, ok = 0: not available for
+// this size (the block-wide phase sequence of conv_sequence.inc serves it then).
+struct Conv2Plan {
+    int ok, id;                 // id: unique per plan (tables cached in shared memory between products of the same plan)
+    int Ax, Bx, blkx, nux;      // rows: radices, slot block stride (Bx | 1), units per row in the split stage
+    int RG, rowlen;             // rows per warp group, slot elements per row (Ax * blkx)
+    int Ay, By, blky;           // columns: radices, slot block stride (By | 1)
+    int G, ngrp, collen;        // columns per warp group, groups, slot elements per column (Ay * blky)
+    int slot_len, nslot;        // elements per warp slot, warps that own one
+    int chat_len;               // ngrp * G * Ly  (cd elements per coefficient block, layout [grp][k2][c][k1])
+    int tab_len;                // cd elements of the twiddle tables
+    int o_t1x, o_tsx, o_tmx, o_tay;   // offsets (elements) of the tables inside tab
+    int off_S, off_W, off_tab;  // byte offsets into dynamic shared memory
+    uint32_t mg_Bx, mg_nux, mg_By, mg_Ay;
+    const cd *tab;              // device copy of the tables
+};
+
 struct ConvPlan {
     int mx, my, npot;
     int Fx, Fy;                 // half sizes of the padded array (opt_fft_size)
@@ -59,6 +77,7 @@ struct ConvPlan {
     int wslots;                 // warps that own a W slot
     int wslot_len;              // cd elements per W slot (padded layout, ViewSk)
     uint32_t mg_G, mg_gpc;      // division magics
+    Conv2Plan c2;               // warp-resident product (fftconv2.cuh)
 };
 
 // ---- exact division of small non-negative integers by a run-time constant: q = (n * magic) >> 32 ----

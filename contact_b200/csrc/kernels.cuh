@@ -1,37 +1,12 @@
 // kernels.cuh -- __global__ entry points of the B200 hot path.
 #pragma once
+#include "chat_kernels.cuh"
 #include "norm_solver.cuh"
 #include "subsurf.cuh"
 #include "tang_solver.cuh"
 #include "large_solver.cuh"
 
 namespace cb200 {
-
-// ---- coefficient transform C^ (one CTA, scratch in global memory; runs once per grid/material/block) ----
-__global__ void __launch_bounds__(CB_THREADS, 1)
-k_build_chat(ConvPlan P, const double *cfblk0, int cmx, int cmy, double scale, cd *SWg0, cd *chat0)
-{
-    // one CTA per coefficient block: blockIdx.x selects the block, its scratch and its output
-    const size_t nscr = (size_t) (P.Lx + 1) * 2 * P.Fy + (size_t) P.Ly * P.C;
-    const double *cfblk = cfblk0 + (size_t) blockIdx.x * 4 * cmx * cmy;
-    cd *SWg = SWg0 + (size_t) blockIdx.x * nscr;
-    cd *chat = chat0 + (size_t) blockIdx.x * P.chat_len;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    // only the tables live in shared memory here; reuse the plan's offsets relative to off_twx
-    const MemBuf<const cd> twx = { P.twx }, twy = { P.twy };        // tables straight from global (one-off kernel)
-    const MemBuf<const unsigned short> posx = { P.posx };
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    typedef MemBuf<cd> CB_BUF;
-    const CB_BUF BUF = { SWg };                                   // scratch: S region, then W region
-    const int SY = 2 * P.Fy;
-    const uint32_t oS = 0u, oW = (uint32_t) (P.Lx + 1) * SY;
-    RowSrc src;
-    src.base = cfblk; src.kind = 1;
-    src.mx = min(P.Fx, P.mx); src.my = min(P.Fy, P.my);          // m_aijpj.f90:896-898
-    src.cmx = cmx; src.cmy = cmy; src.Fx = P.Fx; src.Fy = P.Fy; src.row0 = 0; src.stride = 0;
-    CB_CONV_FORWARD_ROWS(2 * P.Fy, src);
-    CB_CONV_COLUMNS_DUMP(2 * P.Fy, chat, scale);
-}
 
 // ---- Boussinesq-Cerruti influence coefficients, piecewise-constant elements ----
 // Device restatement of the closed forms of elascf_pcwcns (/root/reference/src/m_visc.f90:431-604); one thread per

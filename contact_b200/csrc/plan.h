@@ -2,10 +2,11 @@
 // opt_fft_size restates the reference's size chooser (/root/reference/src/m_aijpj.f90:1022-1119) because the padded
 // size is part of the reference's semantics (it fixes which transform lengths occur); everything else is new.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <vector>
-#include "fftconv.cuh"
+#include "fftconv2.cuh"
 
 namespace cb200 {
 
@@ -75,6 +76,7 @@ inline bool choose_radices(int L, int *nst, int *rad)
 
 struct HostPlan {
     ConvPlan p;
+    std::vector<cd> tab2;          // twiddle tables of the warp-resident product (Conv2Plan::tab)
     std::vector<cd> twx, twy;
     std::vector<unsigned short> posx;
     bool fits;           // whole product fits one CTA's shared memory
@@ -94,6 +96,86 @@ inline void dif_positions(int L, int ns, const int *r, std::vector<unsigned shor
         }
         pos[k] = (unsigned short) p;
     }
+}
+
+// ---- plan of the warp-resident product (fftconv2.cuh) ----
+// cost model used to pick radices and group sizes: FP64 instructions of a radix-R butterfly incl. its twiddles
+inline double c2_bfly_cost(int R) { return R <= 1 ? 0.0 : 3.3 * R * std::log2((double) R) + 4.0 * R; }
+
+inline int c2_next_id() { static int id = 0; return ++id; }
+
+// fills hp.p.c2 and hp.tab2; returns false (c2.ok = 0) when the size is not served (the block-wide path runs then).
+// `end` returns the first byte behind the layout.
+inline bool make_plan2(HostPlan &hp, int smem_limit, long *end)
+{
+    ConvPlan &P = hp.p;
+    Conv2Plan &c = P.c2;
+    std::memset(&c, 0, sizeof(c));
+    *end = 0;
+    if (!hp.fits || P.Lx < 4 || P.Ly < 8) return false;
+    // radices: rows Lx = Ax * Bx, columns Ly = Ay * By (Ay even: the pruned column stages need it)
+    int bestx = 1 << 30, besty = 1 << 30;
+    for (int A = 2; A <= 18; A++) {
+        if (P.Lx % A == 0 && c2_radix_a(A) && c2_radix_b(P.Lx / A) && P.Lx / A <= 9) {
+            const int B = P.Lx / A;
+            const int sc = ((A & 1) ? 100 : 0) + std::abs(A - B) + (B > 8 ? 10 : 0) + (B == 1 ? 50 : 0);
+            if (sc < bestx) { bestx = sc; c.Ax = A; c.Bx = B; }
+        }
+        if (P.Ly % A == 0 && (A & 1) == 0 && c2_radix_a(A) && c2_radix_b(P.Ly / A)) {
+            const int B = P.Ly / A;
+            const int sc = std::abs(A - B) + (B > 12 ? 10 : 0) + (B > A ? 5 : 0) + (B == 1 ? 50 : 0);
+            if (sc < besty) { besty = sc; c.Ay = A; c.By = B; }
+        }
+    }
+    if (c.Ax == 0 || c.Ay == 0) return false;
+    c.blkx = c.Bx | 1; c.blky = c.By | 1;
+    c.nux = (c.Ax & 1) ? (c.Ax + 1) / 2 : c.Ax / 2;
+    c.rowlen = c.Ax * c.blkx; c.collen = c.Ay * c.blky;
+    // tables
+    c.o_t1x = 0;
+    c.o_tsx = c.o_t1x + (c.Ax - 1) * c.Bx;
+    c.o_tmx = c.o_tsx + c.nux * c.Bx;
+    c.o_tay = c.o_tmx + c.Bx;
+    c.tab_len = c.o_tay + (c.Ay - 1) * c.By;
+    const long bytesS = (long) (P.Fx + 1) * P.SY * 16, bytesT = (long) c.tab_len * 16;
+    const long avail = (long) smem_limit - 1024 - bytesS - bytesT;
+    // group sizes: minimise the estimated issue time of one product over the warps that get a slot
+    const double cA = c2_bfly_cost(c.Ay), cM = 2.0 * c2_bfly_cost(c.By) + 4.0 * c.By;
+    const double cR1 = c2_bfly_cost(c.Ax), cR2 = 2.0 * c2_bfly_cost(c.Bx) + 14.0 * c.Bx;
+    double best = 1e300;
+    for (int G = 1; G <= 8; G++)
+        for (int RG = 1; RG <= 8; RG++) {
+            const long slot = std::max((long) RG * c.rowlen, (long) G * c.collen);
+            long ns = avail / (slot * 16);
+            if (ns > kPlanWarps) ns = kPlanWarps;
+            if (ns < 1) continue;
+            const int ngrp = (P.Fx + 1 + G - 1) / G, nrg = (P.my + RG - 1) / RG;
+            auto rounds = [](int items) { return (double) ((items + 31) / 32); };
+            const double tc = std::ceil((double) ngrp / ns) * (2.0 * rounds(G * c.By) * cA + rounds(G * c.Ay) * cM);
+            const double tr = std::ceil((double) nrg / ns) * 2.0 * (rounds(RG * c.Bx) * cR1 + rounds(RG * c.nux) * cR2);
+            const double t = tc + tr;
+            if (t < best * (1.0 - 1e-9)) { best = t; c.G = G; c.RG = RG; c.slot_len = (int) slot; c.nslot = (int) ns; }
+        }
+    if (c.G == 0 || c.nslot < 4) { std::memset(&c, 0, sizeof(c)); return false; }
+    c.ngrp = (P.Fx + 1 + c.G - 1) / c.G;
+    c.chat_len = c.ngrp * c.G * P.Ly;
+    c.off_S = 0;
+    c.off_W = (int) bytesS;
+    c.off_tab = c.off_W + c.nslot * c.slot_len * 16;
+    *end = (long) c.off_tab + bytesT;
+    c.mg_Bx = div_magic((uint32_t) c.Bx); c.mg_nux = div_magic((uint32_t) c.nux);
+    c.mg_By = div_magic((uint32_t) c.By); c.mg_Ay = div_magic((uint32_t) c.Ay);
+    // twiddle tables, laid out [q][j] so that the lanes of a warp read consecutive entries
+    const double pi = 3.14159265358979323846;
+    hp.tab2.assign((size_t) c.tab_len, make_double2(1.0, 0.0));
+    auto w = [&](double num, double den) { return make_double2(std::cos(-2.0 * pi * num / den), std::sin(-2.0 * pi * num / den)); };
+    for (int q = 1; q < c.Ax; q++) for (int j = 0; j < c.Bx; j++) hp.tab2[c.o_t1x + (q - 1) * c.Bx + j] = w((double) j * q, P.Lx);
+    for (int k2 = 0; k2 < c.Bx; k2++) for (int u = 0; u < c.nux; u++) hp.tab2[c.o_tsx + k2 * c.nux + u] = w(u + c.Ax * k2, 2.0 * P.Lx);
+    for (int k2 = 0; k2 < c.Bx; k2++) hp.tab2[c.o_tmx + k2] = w(0.5 * c.Ax + c.Ax * k2, 2.0 * P.Lx);
+    for (int q = 1; q < c.Ay; q++) for (int j = 0; j < c.By; j++) hp.tab2[c.o_tay + (q - 1) * c.By + j] = w((double) j * q, P.Ly);
+    c.id = c2_next_id();
+    c.ok = 1;
+    return true;
 }
 
 inline bool make_plan(int mx, int my, HostPlan &hp, int smem_limit = kSmemMax)
@@ -153,6 +235,12 @@ inline bool make_plan(int mx, int my, HostPlan &hp, int smem_limit = kSmemMax)
     P.off_posx = P.off_twy + 2 * P.Fy * 16;
     P.off_red = P.off_posx + ((P.Lx * 2 + 15) / 16) * 16;
     P.smem_bytes = P.off_red + 1024;
+    // warp-resident product: same shared-memory window, the reduction scratch sits behind both layouts
+    long end2 = 0;
+    if (make_plan2(hp, smem_limit, &end2)) {
+        const int e2 = (int) ((end2 + 15) / 16) * 16;
+        if (e2 > P.off_red) { P.off_red = e2; P.smem_bytes = P.off_red + 1024; }
+    }
     return true;
 }
 

@@ -263,6 +263,7 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
     // shared memory is ours now (S and W regions of the FFT layout)
     SteadySmem s;
     steady_carve(P, reinterpret_cast<unsigned char *>(sm.S), a.sym, s);
+    conv_tables_invalidate(sm);                                     // the sweep arrays overwrite the product's window
     if (s.q) {
         if (a.sym) {
             for (int i = tid; i < n; i += nt) {

@@ -350,7 +350,8 @@ __device__ int solve_once_dev(const X &x, ContactCase &c, const double *wstot, d
         a.cs11 = c.cf11; a.cs12 = c.cf12; a.cs22 = c.cf22; a.cs13 = c.cf13; a.cs23 = c.cf23; a.ub = a.ug;
         if (ncon <= 6 * CB_THREADS) info = stdygs_dev<6>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
         else if (ncon <= 12 * CB_THREADS) info = stdygs_dev<12>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
-        else info = stdygs_dev<22>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
+        else if (ncon <= 22 * CB_THREADS) info = stdygs_dev<22>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
+        else { if (x.leader()) c.tstatus |= 1; info = 1; }       // more contact elements than the register-resident sweep holds: refused
         }
     } else if (c.solver_eff == 0)
         tangcg_dev(x, c, wstot, c.nrm.maxgs, c.nrm.eps, it, err, nprod);

@@ -78,11 +78,11 @@ extern "C" int emul_conv_warp(int mx, int my, const double *p, const double *cfb
 // radix butterflies against a naive DFT
 extern "C" double emul_radix_error(int R, int inv)
 {
-    cd x[16], y[16];
+    cd x[18], y[18];
     double err = 0.0;
     for (int q = 0; q < R; q++) { x[q] = make_double2(0.3 + 0.7 * q - 0.05 * q * q, -0.2 + 0.11 * q * q * q / 7.0); y[q] = x[q]; }
 #define RUN(RR) case RR: if (inv) Dft<RR, true>::run(y); else Dft<RR, false>::run(y); break;
-    switch (R) { RUN(2) RUN(3) RUN(4) RUN(5) RUN(6) RUN(7) RUN(8) RUN(9) RUN(12) RUN(16) default: return -1; }
+    switch (R) { RUN(2) RUN(3) RUN(4) RUN(5) RUN(6) RUN(7) RUN(8) RUN(9) RUN(12) RUN(16) RUN(10) RUN(18) default: return -1; }
     const double pi = 3.14159265358979323846, sg = inv ? 1.0 : -1.0;
     for (int k = 0; k < R; k++) {
         double re = 0, im = 0;
@@ -93,5 +93,58 @@ extern "C" double emul_radix_error(int R, int inv)
         }
         err = fmax(err, fmax(fabs(re - y[k].x), fabs(im - y[k].y)));
     }
+    return err;
+}
+
+// ---- warp-resident product (fftconv2.cuh): the three passes stepped warp by warp, lanes looped; coefficient transform by
+//      the dense DFT entries the device builder kernels use.  Box (x0, y0, bw x bh) of the mx x my grid; plan of (pmx, pmy).
+extern "C" int emul_plan2_info(int mx, int my, int *out)
+{
+    HostPlan hp;
+    if (!make_plan(mx, my, hp)) return -1;
+    const Conv2Plan &c = hp.p.c2;
+    const int v[16] = { c.ok, c.Ax, c.Bx, c.Ay, c.By, c.G, c.RG, c.nslot, c.slot_len, c.ngrp, c.chat_len, c.tab_len,
+                        hp.p.smem_bytes, hp.p.off_red, c.off_tab, c.nux };
+    for (int i = 0; i < 16; i++) out[i] = v[i];
+    return 0;
+}
+
+extern "C" int emul_conv2(int pmx, int pmy, int mx, const double *p, const double *cfblk, int cmx, int cmy, double scale,
+                          const int *el, int mask_mode, int add, double *u, int x0, int y0, int bw, int bh, int nwarps)
+{
+    HostPlan hp;
+    if (!make_plan(pmx, pmy, hp)) return -1;
+    const ConvPlan &P = hp.p;
+    const Conv2Plan &c = P.c2;
+    if (!c.ok) return -2;
+    // C^ in the layout [group][k2][column][k1]
+    std::vector<cd> chat((size_t) c.chat_len, make_double2(0.0, 0.0));
+    {
+        RowSrc src = { cfblk, 1, P.Fx < cmx ? P.Fx : cmx, P.Fy < cmy ? P.Fy : cmy, cmx, cmy, P.Fx, P.Fy, 0, 0 };
+        std::vector<cd> T((size_t) 2 * P.Fy * (P.Fx + 1));
+        for (int iy = 0; iy < 2 * P.Fy; iy++)
+            for (int kx = 0; kx <= P.Fx; kx++) T[(size_t) iy * (P.Fx + 1) + kx] = c2_chat_row_entry(P, src, iy, kx, hp.twx.data());
+        for (int kx = 0; kx <= P.Fx; kx++)
+            for (int ky = 0; ky < 2 * P.Fy; ky++)
+                chat[c2_chat_index(P, kx, ky)] = c2_chat_col_entry(P, T.data(), kx, ky, hp.twy.data(), scale / (4.0 * P.Fx * P.Fy));
+    }
+    std::vector<cd> sm((size_t) (P.off_red / 16) + 64, make_double2(1e300, -1e300));   // poisoned: stale reads show up
+    for (int i = 0; i < c.tab_len; i++) sm[c.off_tab / 16 + i] = hp.tab2[i];
+    const MemBuf<cd> buf = { sm.data() };
+    for (int w = 0; w < nwarps; w++) c2_rows_fwd(P, buf, p + (size_t) y0 * mx + x0, bw, bh, mx, w);
+    for (int w = 0; w < nwarps; w++) c2_cols(P, buf, chat.data(), bh, bh, w);
+    for (int w = 0; w < nwarps; w++) c2_rows_inv(P, buf, u, el, mask_mode, add, x0, y0, bw, bh, mx, w);
+    return 0;
+}
+
+// input-pruned butterflies against the full ones on half-zero input
+extern "C" double emul_halfin_error(int R, int inv)
+{
+    cd x[18], y[18];
+    for (int q = 0; q < R; q++) { x[q] = q < R / 2 ? make_double2(0.3 + 0.7 * q, -0.2 + 0.11 * q * q) : make_double2(0.0, 0.0); y[q] = x[q]; }
+#define RUNH(RR) case RR: if (inv) { DftHalfIn<RR, true>::run(y); Dft<RR, true>::run(x); } else { DftHalfIn<RR, false>::run(y); Dft<RR, false>::run(x); } break;
+    switch (R) { RUNH(4) RUNH(6) RUNH(8) RUNH(10) RUNH(12) RUNH(16) RUNH(18) default: return -1; }
+    double err = 0.0;
+    for (int k = 0; k < R; k++) err = fmax(err, fmax(fabs(x[k].x - y[k].x), fabs(x[k].y - y[k].y)));
     return err;
 }
