@@ -34,7 +34,7 @@ __global__ void k_fill_masked(double *u, const int *el, int mask_mode, double va
 
 // Strided batched product: case ic reads p + ic*pstride, writes u + ic*ustride, mask el + ic*npot
 __global__ void __launch_bounds__(CB_THREADS, 1)
-k_conv_batch_strided(ConvPlan P, const double *p, long pstride, const cd *chat, double *u, long ustride,
+k_conv_batch_strided(const __grid_constant__ ConvPlan P, const double *p, long pstride, const cd *chat, double *u, long ustride,
                      const int *el, int mask_mode, int add, int ncase)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];

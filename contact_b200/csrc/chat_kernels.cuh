@@ -53,7 +53,7 @@ __global__ void k_chat2_cols(ConvPlan P, const cd *T0, double scale, cd *chat0)
     if (t >= n) return;
     const int ky = t / ld, kx = t - ky * ld;
     chat0[(size_t) blockIdx.y * P.c2.chat_len + c2_chat_index(P, kx, ky)] =
-        c2_chat_col_entry(P, T0 + (size_t) blockIdx.y * n, kx, ky, P.twy, scale);
+        c2_chat_value(P, T0 + (size_t) blockIdx.y * n, kx, ky, P.twy, scale);
 }
 
 }  // namespace cb200

@@ -35,6 +35,9 @@ extern __shared__ __align__(16) unsigned char cb_smem_window[];
 struct ShBuf {
     __device__ __forceinline__ cd ld(uint32_t i) const { return reinterpret_cast<const cd *>(cb_smem_window)[i]; }
     __device__ __forceinline__ void st(uint32_t i, cd v) const { reinterpret_cast<cd *>(cb_smem_window)[i] = v; }
+    __device__ __forceinline__ cd ldz(uint32_t i, bool ok) const { return ok ? ld(i) : make_double2(0.0, 0.0); }
+    __device__ __forceinline__ void stp(uint32_t i, cd v, bool ok) const { if (ok) st(i, v); }
+    __device__ __forceinline__ int ldi(uint32_t w) const { return reinterpret_cast<const int *>(cb_smem_window)[w]; }
 };
 
 // ---- bulk-async copy (TMA engine, cp.async.bulk) + mbarrier: used to fetch a plan's twiddle tables ----
@@ -118,7 +121,9 @@ __device__ __noinline__ void conv2_box_dev(const ConvPlan &P, const Smem &sm, co
 __device__ __noinline__ void conv_box_dev(const ConvPlan &P, const Smem &sm, const double *p, const cd *chat, double *u,
                                           const int *el, int mask_mode, int add, int x0, int y0, int bw, int bh, int stride)
 {
+#ifndef CB_NO_CONV2
     if (P.c2.ok) { conv2_box_dev(P, sm, p, chat, u, el, mask_mode, add, x0, y0, bw, bh, stride); return; }
+#endif
     conv_tables_invalidate(sm);                                 // this path overwrites the window of the other one
     const int tid = threadIdx.x, nthr = blockDim.x;
     const long long t_in = (tid == 0 && blockIdx.x == 0) ? clock64() : 0;

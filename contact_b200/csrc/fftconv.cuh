@@ -42,13 +42,16 @@ struct StageK {
 struct Conv2Plan {
     int ok, id;                 // id: unique per plan (tables cached in shared memory between products of the same plan)
     int Ax, Bx, blkx, nux;      // rows: radices, slot block stride (Bx | 1), units per row in the split stage
-    int RG, rowlen;             // rows per warp group, slot elements per row (Ax * blkx)
+    int RG, rowlen;             // rows per warp group, slot elements per row (Ax * blkx + padding)
     int Ay, By, blky;           // columns: radices, slot block stride (By | 1)
-    int G, ngrp, collen;        // columns per warp group, groups, slot elements per column (Ay * blky)
+    int G, ngrp, collen;        // columns per warp group, groups, slot elements per column (Ay * blky + padding)
+    int SY;                     // row stride of S[kx][iy] (>= my; padded so that column and row stages hit distinct banks)
+    uint32_t mg_G, mg_RG;
     int slot_len, nslot;        // elements per warp slot, warps that own one
-    int chat_len;               // ngrp * G * Ly  (cd elements per coefficient block, layout [grp][k2][c][k1])
+    int chat_len;               // ngrp * G * Ly  (cd elements per coefficient block, layout [grp][k2][k1][c])
     int tab_len;                // cd elements of the twiddle tables
     int o_t1x, o_tsx, o_tmx, o_tay;   // offsets (elements) of the tables inside tab
+    int o_kr, o_kc;             // offsets (elements) of the stage constants of the row / column stages inside tab
     int off_S, off_W, off_tab;  // byte offsets into dynamic shared memory
     uint32_t mg_Bx, mg_nux, mg_By, mg_Ay;
     const cd *tab;              // device copy of the tables
@@ -98,6 +101,9 @@ template <class T> struct MemBuf {          // any memory through a (restrict-fr
     T *p;                                   // shared memory when the pointer was derived with __cvta_shared_to_generic
     CB_HD T ld(uint32_t i) const { return p[i]; }
     CB_HD void st(uint32_t i, T v) const { p[i] = v; }
+    CB_HD T ldz(uint32_t i, bool ok) const { return ok ? p[i] : T(); }      // predicated load, zero when off
+    CB_HD void stp(uint32_t i, T v, bool ok) const { if (ok) p[i] = v; }    // predicated store
+    CB_HD int ldi(uint32_t w) const { return reinterpret_cast<const int *>(p)[w]; }   // 32-bit word w of the window
 };
 
 // ---- 2-D views used by the FFT stages: element e of transform c ----

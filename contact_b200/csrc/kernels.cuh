@@ -122,7 +122,7 @@ __global__ void k_cplx_real_scaled(const cd *in, double *out, long n, double sca
 
 // ---- batched NORM solve: one CTA per contact problem ----
 __global__ void __launch_bounds__(CB_THREADS, 1)
-k_snorm_batch(ConvPlan P, NormCase *cases, int ncase, int *next_case)
+k_snorm_batch(const __grid_constant__ ConvPlan P, NormCase *cases, int ncase, int *next_case)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem sm = smem_view(P, smem_raw);
@@ -144,7 +144,7 @@ k_snorm_batch(ConvPlan P, NormCase *cases, int ncase, int *next_case)
 
 // ---- batched contact cases (NORM + TANG alternation), one CTA per case, dynamic queue ----
 __global__ void __launch_bounds__(CB_THREADS, 1)
-k_contac_batch(ConvPlan P, ContactCase *cases, int ncase, int *next_case)
+k_contac_batch(const __grid_constant__ ConvPlan P, ContactCase *cases, int ncase, int *next_case)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem sm = smem_view(P, smem_raw);

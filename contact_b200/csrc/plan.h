@@ -116,12 +116,12 @@ inline bool make_plan2(HostPlan &hp, int smem_limit, long *end)
     // radices: rows Lx = Ax * Bx, columns Ly = Ay * By (Ay even: the pruned column stages need it)
     int bestx = 1 << 30, besty = 1 << 30;
     for (int A = 2; A <= 18; A++) {
-        if (P.Lx % A == 0 && c2_radix_a(A) && c2_radix_b(P.Lx / A) && P.Lx / A <= 9) {
+        if (P.Lx % A == 0 && c2_row_class(A, P.Lx / A)) {
             const int B = P.Lx / A;
             const int sc = ((A & 1) ? 100 : 0) + std::abs(A - B) + (B > 8 ? 10 : 0) + (B == 1 ? 50 : 0);
             if (sc < bestx) { bestx = sc; c.Ax = A; c.Bx = B; }
         }
-        if (P.Ly % A == 0 && (A & 1) == 0 && c2_radix_a(A) && c2_radix_b(P.Ly / A)) {
+        if (P.Ly % A == 0 && (A & 1) == 0 && c2_col_class(A, P.Ly / A)) {
             const int B = P.Ly / A;
             const int sc = std::abs(A - B) + (B > 12 ? 10 : 0) + (B > A ? 5 : 0) + (B == 1 ? 50 : 0);
             if (sc < besty) { besty = sc; c.Ay = A; c.By = B; }
@@ -130,41 +130,117 @@ inline bool make_plan2(HostPlan &hp, int smem_limit, long *end)
     if (c.Ax == 0 || c.Ay == 0) return false;
     c.blkx = c.Bx | 1; c.blky = c.By | 1;
     c.nux = (c.Ax & 1) ? (c.Ax + 1) / 2 : c.Ax / 2;
-    c.rowlen = c.Ax * c.blkx; c.collen = c.Ay * c.blky;
     // tables
     c.o_t1x = 0;
     c.o_tsx = c.o_t1x + (c.Ax - 1) * c.Bx;
     c.o_tmx = c.o_tsx + c.nux * c.Bx;
     c.o_tay = c.o_tmx + c.Bx;
-    c.tab_len = c.o_tay + (c.Ay - 1) * c.By;
-    const long bytesS = (long) (P.Fx + 1) * P.SY * 16, bytesT = (long) c.tab_len * 16;
-    const long avail = (long) smem_limit - 1024 - bytesS - bytesT;
-    // group sizes: minimise the estimated issue time of one product over the warps that get a slot
+    c.o_kr = c.o_tay + (c.Ay - 1) * c.By;                       // stage constants behind the twiddles (20 words = 5 elements each)
+    c.o_kc = c.o_kr + CB2_KWORDS / 4;
+    c.tab_len = c.o_kc + CB2_KWORDS / 4;
+    const long bytesT = (long) c.tab_len * 16;
+    // group sizes: minimise the estimated FP64 issue time of one product over the warps that get a slot (the paddings
+    // below may still take a slot away on the largest grids; they are chosen afterwards)
     const double cA = c2_bfly_cost(c.Ay), cM = 2.0 * c2_bfly_cost(c.By) + 4.0 * c.By;
     const double cR1 = c2_bfly_cost(c.Ax), cR2 = 2.0 * c2_bfly_cost(c.Bx) + 14.0 * c.Bx;
-    double best = 1e300;
-    for (int G = 1; G <= 8; G++)
-        for (int RG = 1; RG <= 8; RG++) {
-            const long slot = std::max((long) RG * c.rowlen, (long) G * c.collen);
-            long ns = avail / (slot * 16);
-            if (ns > kPlanWarps) ns = kPlanWarps;
-            if (ns < 1) continue;
-            const int ngrp = (P.Fx + 1 + G - 1) / G, nrg = (P.my + RG - 1) / RG;
-            auto rounds = [](int items) { return (double) ((items + 31) / 32); };
-            const double tc = std::ceil((double) ngrp / ns) * (2.0 * rounds(G * c.By) * cA + rounds(G * c.Ay) * cM);
-            const double tr = std::ceil((double) nrg / ns) * 2.0 * (rounds(RG * c.Bx) * cR1 + rounds(RG * c.nux) * cR2);
-            const double t = tc + tr;
-            if (t < best * (1.0 - 1e-9)) { best = t; c.G = G; c.RG = RG; c.slot_len = (int) slot; c.nslot = (int) ns; }
-        }
-    if (c.G == 0 || c.nslot < 4) { std::memset(&c, 0, sizeof(c)); return false; }
-    c.ngrp = (P.Fx + 1 + c.G - 1) / c.G;
-    c.chat_len = c.ngrp * c.G * P.Ly;
+    {
+        const long avail = (long) smem_limit - 1024 - (long) P.Fx * P.my * 16 - bytesT;
+        double best = 1e300;
+        for (int G = 1; G <= 8; G++)
+            for (int RG = 1; RG <= 8 && G != 6; RG *= 2) {       // G = 6: no stride keeps 8 lanes on 8 bank groups                  // rows per group: a power of two (lane order of the split stage)
+                const long slot = std::max((long) RG * c.Ax * c.blkx, (long) std::max(G, 2) * c.Ay * c.blky);
+                long ns = avail / (slot * 16);
+                if (ns > kPlanWarps) ns = kPlanWarps;
+                if (ns < 1) continue;
+                const int ngrp = (P.Fx + G - 1) / G, nrg = (P.my + RG - 1) / RG;
+                auto rounds = [](int items) { return (double) ((items + 31) / 32); };
+                const double tc = std::ceil((double) ngrp / ns) * (2.0 * rounds(G * c.By) * cA + rounds(G * c.Ay) * cM);
+                const double tr = std::ceil((double) nrg / ns) * 2.0 * (rounds(RG * c.Bx) * cR1 + rounds(RG * c.nux) * cR2);
+                if (tc + tr < best * (1.0 - 1e-9)) { best = tc + tr; c.G = G; c.RG = RG; }
+            }
+        if (c.G == 0) { std::memset(&c, 0, sizeof(c)); return false; }
+    }
+    // paddings of the S row stride and of the slot strides: the 16-byte accesses of a quarter warp should fall into 8
+    // distinct bank groups.  Every candidate is scored with the wavefronts of the access patterns of all stages (lane ->
+    // element address, exactly as the stage functions of fftconv2.cuh compute them), under the shared-memory budget.
+    {
+        auto wf = [](const std::vector<long> &addr) {            // wavefronts of one warp-wide 16-byte access
+            long tot = 0;
+            for (size_t q0 = 0; q0 < addr.size(); q0 += 8) {
+                int cnt[8] = { 0 }; long seen[8][8];
+                for (size_t l = q0; l < q0 + 8 && l < addr.size(); l++) {
+                    const int b = (int) (((addr[l] % 8) + 8) % 8); bool dup = false;
+                    for (int z = 0; z < cnt[b]; z++) dup = dup || seen[b][z] == addr[l];
+                    if (!dup) seen[b][cnt[b]++] = addr[l];
+                }
+                int m = 0; for (int b = 0; b < 8; b++) m = std::max(m, cnt[b]);
+                tot += m;
+            }
+            return tot;
+        };
+        const int nlc = std::min(32, c.G * c.By), nlm = std::min(32, c.G * c.Ay);
+        const int nl1 = std::min(32, c.RG * c.Bx), nl2 = std::min(32, c.RG * c.nux);
+        auto ka = [&](int u) { return u; };
+        auto kb = [&](int u) { return u == 0 ? ((c.Ax & 1) ? 0 : c.Ax / 2) : c.Ax - u; };
+        double best = 1e300;
+        int bSY = 0, brow = 0, bcol = 0, bns = 0;
+        for (int ps = 0; ps < 8; ps++)
+            for (int pr = 0; pr < 8; pr++)
+                for (int pc = 0; pc < 8; pc++) {
+                    const long SY = P.my + ps, rowlen = (long) c.Ax * c.blkx + pr, collen = (long) c.Ay * c.blky + pc;
+                    const long slot = std::max((long) c.RG * rowlen, (long) std::max(c.G, 2) * collen);
+                    const long avail = (long) smem_limit - 1024 - (long) P.Fx * SY * 16 - bytesT;
+                    long ns = avail / (slot * 16);
+                    if (ns > kPlanWarps) ns = kPlanWarps;
+                    if (ns < 1) continue;
+                    std::vector<long> a;
+                    double cost = 0.0;
+                    // columns, stages A / C: lane -> (cc = L % G, j = L / G)
+                    a.assign(nlc, 0); for (int L = 0; L < nlc; L++) a[L] = (L % c.G) * SY + L / c.G;
+                    cost += (double) c.Ay * wf(a);                                   // S: Ay/2 loads + Ay/2 stores
+                    a.assign(nlc, 0); for (int L = 0; L < nlc; L++) a[L] = (L % c.G) * collen + L / c.G;
+                    cost += 2.0 * c.Ay * wf(a);                                      // slot: Ay stores + Ay loads
+                    // columns, stage M: lane -> (cc = L % G, k1 = L / G)
+                    a.assign(nlm, 0); for (int L = 0; L < nlm; L++) a[L] = (L % c.G) * collen + (long) (L / c.G) * c.blky;
+                    cost += 2.0 * c.By * wf(a) * (double) nlm / std::max(1, nlc);    // per column the M items outnumber the A items
+                    cost *= (double) P.Fx / c.G;
+                    double rc = 0.0;
+                    // rows, first / last stage: lane -> (j = L % Bx, r = L / Bx)
+                    a.assign(nl1, 0); for (int L = 0; L < nl1; L++) a[L] = (L % c.Bx) + (L / c.Bx) * rowlen;
+                    rc += 2.0 * c.Ax * wf(a);
+                    // rows, split / merge stage: lane -> (r = L % RG, u = L / RG), blocks ka(u) and kb(u)
+                    double w2 = 0.0;
+                    a.assign(nl2, 0); for (int L = 0; L < nl2; L++) a[L] = (L % c.RG) * rowlen + (long) ka(L / c.RG) * c.blkx;
+                    w2 += wf(a);
+                    a.assign(nl2, 0); for (int L = 0; L < nl2; L++) a[L] = (L % c.RG) * rowlen + (long) kb(L / c.RG) * c.blkx;
+                    w2 += wf(a);
+                    rc += 2.0 * c.Bx * w2;                                           // slot: Bx loads per block (fwd) + Bx stores (inv)
+                    double w3 = 0.0;
+                    a.assign(nl2, 0); for (int L = 0; L < nl2; L++) a[L] = (long) ka(L / c.RG) * SY + L % c.RG;
+                    w3 += wf(a);
+                    a.assign(nl2, 0); for (int L = 0; L < nl2; L++) a[L] = (long) kb(L / c.RG) * SY + L % c.RG;
+                    w3 += wf(a);
+                    rc += 2.0 * c.Bx * w3;                                           // S: Bx stores per block (fwd) + Bx loads (inv)
+                    rc *= (double) P.my / c.RG;
+                    cost = (cost + rc) * (double) kPlanWarps / (double) ns;          // fewer slots: fewer warps at work
+                    cost *= 1.0 + 1e-4 * (ps + pr + pc);                             // ties: least padding
+                    if (cost < best) { best = cost; bSY = (int) SY; brow = (int) rowlen; bcol = (int) collen; bns = (int) ns; }
+                }
+        if (bns < 4) { std::memset(&c, 0, sizeof(c)); return false; }
+        c.SY = bSY; c.rowlen = brow; c.collen = bcol; c.nslot = bns;
+        c.slot_len = std::max(c.RG * c.rowlen, std::max(c.G, 2) * c.collen);      // two columns at least: scratch of the packed column
+    }
+    // S holds the columns kx = 0 .. Fx-1: column 0 is the packed pair (kx = 0, kx = Fx), both real after the row split
+    const long bytesS = (long) P.Fx * c.SY * 16;
+    c.ngrp = (P.Fx + c.G - 1) / c.G;
+    c.chat_len = ((P.Fx + 1 + c.G - 1) / c.G) * c.G * P.Ly;       // coefficient columns 0 .. Fx (column Fx holds Q)
     c.off_S = 0;
     c.off_W = (int) bytesS;
     c.off_tab = c.off_W + c.nslot * c.slot_len * 16;
     *end = (long) c.off_tab + bytesT;
     c.mg_Bx = div_magic((uint32_t) c.Bx); c.mg_nux = div_magic((uint32_t) c.nux);
     c.mg_By = div_magic((uint32_t) c.By); c.mg_Ay = div_magic((uint32_t) c.Ay);
+    c.mg_G = div_magic((uint32_t) c.G); c.mg_RG = div_magic((uint32_t) c.RG);
     // twiddle tables, laid out [q][j] so that the lanes of a warp read consecutive entries
     const double pi = 3.14159265358979323846;
     hp.tab2.assign((size_t) c.tab_len, make_double2(1.0, 0.0));
@@ -173,6 +249,12 @@ inline bool make_plan2(HostPlan &hp, int smem_limit, long *end)
     for (int k2 = 0; k2 < c.Bx; k2++) for (int u = 0; u < c.nux; u++) hp.tab2[c.o_tsx + k2 * c.nux + u] = w(u + c.Ax * k2, 2.0 * P.Lx);
     for (int k2 = 0; k2 < c.Bx; k2++) hp.tab2[c.o_tmx + k2] = w(0.5 * c.Ax + c.Ax * k2, 2.0 * P.Lx);
     for (int q = 1; q < c.Ay; q++) for (int j = 0; j < c.By; j++) hp.tab2[c.o_tay + (q - 1) * c.By + j] = w((double) j * q, P.Ly);
+    {   // the constants of the stage functions, as the device reads them (C2K, CB2_KWORDS 32-bit words per block)
+        static_assert(sizeof(C2K) == CB2_KWORDS * 4, "C2K layout");
+        const C2K kr = c2k_rows(P), kc = c2k_cols(P);
+        std::memcpy(&hp.tab2[c.o_kr], &kr, sizeof(C2K));
+        std::memcpy(&hp.tab2[c.o_kc], &kc, sizeof(C2K));
+    }
     c.id = c2_next_id();
     c.ok = 1;
     return true;

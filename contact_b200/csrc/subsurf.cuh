@@ -193,7 +193,7 @@ struct SubsArgs {
 
 // one CTA per (case, depth) work item, dynamic queue
 __global__ void __launch_bounds__(CB_THREADS, 1)
-k_subsurf_batch(ConvPlan P, SubsArgs A)
+k_subsurf_batch(const __grid_constant__ ConvPlan P, SubsArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem sm = smem_view(P, smem_raw);

@@ -3,10 +3,54 @@
 // algorithm (indexing, digit-reversed C^ layout, split/merge steps) against the oracle without a GPU.
 #include <vector>
 #include <cstdio>
+#include <cstdint>
+#include <algorithm>
+// ---- shared-memory wavefront model of the warp-resident product ----
+// TraceBuf records, per lane, the sequence of 16-byte shared-memory accesses of one stage (the lanes are stepped one after
+// the other, every lane issues the same instruction sequence).  A 16-byte access is served per quarter-warp (8 lanes); a
+// quarter needs as many wavefronts as the largest number of DISTINCT addresses that fall into one of the 8 bank groups.
+struct TraceLog { std::vector<std::vector<uint32_t>> lane; long wf = 0, ideal = 0, instr = 0; long swf[10] = { 0 }, sideal[10] = { 0 }; int stage = 0; };
+static TraceLog *g_trace = nullptr;
+static int g_trace_lane = 0;
+static void trace_flush(TraceLog &t)
+{
+    size_t n = 0;
+    for (auto &l : t.lane) n = std::max(n, l.size());
+    for (size_t k = 0; k < n; k++) {
+        int active = 0;
+        for (int q = 0; q < 4; q++) {
+            int cnt[8] = { 0 }; uint32_t seen[8][8]; int any = 0;
+            for (int l = 8 * q; l < 8 * q + 8; l++) {
+                if (t.lane[l].size() <= k) continue;
+                const uint32_t a = t.lane[l][k]; if (a == 0xFFFFFFFFu) continue;
+                const int b = a & 7; bool dup = false;
+                for (int z = 0; z < cnt[b]; z++) dup = dup || seen[b][z] == a;
+                if (!dup) seen[b][cnt[b]++] = a;
+                any = 1; active++;
+            }
+            int m = 0; for (int b = 0; b < 8; b++) m = std::max(m, cnt[b]);
+            t.wf += m; t.swf[t.stage] += m; (void) any;
+        }
+        t.ideal += (active + 7) / 8; t.sideal[t.stage] += (active + 7) / 8; t.instr++;
+    }
+    for (auto &l : t.lane) l.clear();
+}
+#define CB2_TICK(i) do { if (g_trace) g_trace->stage = (i); } while (0)
+#define CB2_LANE_BEGIN(lane) (g_trace_lane = (lane))
+#define CB2_LANES_END() do { if (g_trace) trace_flush(*g_trace); } while (0)
 #include "../../contact_b200/csrc/plan.h"
 #include "../../contact_b200/csrc/fftconv_warp.cuh"
 
 using namespace cb200;
+
+struct TraceBuf {
+    cd *p;
+    cd ld(uint32_t i) const { if (g_trace) g_trace->lane[g_trace_lane].push_back(i); return p[i]; }
+    void st(uint32_t i, cd v) const { if (g_trace) g_trace->lane[g_trace_lane].push_back(i); p[i] = v; }
+    int ldi(uint32_t w) const { return reinterpret_cast<const int *>(p)[w]; }
+    cd ldz(uint32_t i, bool ok) const { if (g_trace) g_trace->lane[g_trace_lane].push_back(ok ? i : 0xFFFFFFFFu); return ok ? p[i] : make_double2(0.0, 0.0); }
+    void stp(uint32_t i, cd v, bool ok) const { if (g_trace) g_trace->lane[g_trace_lane].push_back(ok ? i : 0xFFFFFFFFu); if (ok) p[i] = v; }
+};
 
 #define CB_PHASE(call) do { for (int tid = 0; tid < nthr; tid++) { call; } } while (0)
 #include "../../contact_b200/csrc/conv_sequence.inc"
@@ -126,7 +170,7 @@ extern "C" int emul_conv2(int pmx, int pmy, int mx, const double *p, const doubl
             for (int kx = 0; kx <= P.Fx; kx++) T[(size_t) iy * (P.Fx + 1) + kx] = c2_chat_row_entry(P, src, iy, kx, hp.twx.data());
         for (int kx = 0; kx <= P.Fx; kx++)
             for (int ky = 0; ky < 2 * P.Fy; ky++)
-                chat[c2_chat_index(P, kx, ky)] = c2_chat_col_entry(P, T.data(), kx, ky, hp.twy.data(), scale / (4.0 * P.Fx * P.Fy));
+                chat[c2_chat_index(P, kx, ky)] = c2_chat_value(P, T.data(), kx, ky, hp.twy.data(), scale / (4.0 * P.Fx * P.Fy));
     }
     std::vector<cd> sm((size_t) (P.off_red / 16) + 64, make_double2(1e300, -1e300));   // poisoned: stale reads show up
     for (int i = 0; i < c.tab_len; i++) sm[c.off_tab / 16 + i] = hp.tab2[i];
@@ -147,4 +191,29 @@ extern "C" double emul_halfin_error(int R, int inv)
     double err = 0.0;
     for (int k = 0; k < R; k++) err = fmax(err, fmax(fabs(x[k].x - y[k].x), fabs(x[k].y - y[k].y)));
     return err;
+}
+
+// out[0..5]: modelled / ideal wavefronts of rows fwd, columns, rows inv of one full-grid product; out[6..25]: per stage
+extern "C" int emul_conv2_wavefronts(int mx, int my, long *out)
+{
+    HostPlan hp;
+    if (!make_plan(mx, my, hp) || !hp.p.c2.ok) return -1;
+    const ConvPlan &P = hp.p;
+    const Conv2Plan &c = P.c2;
+    std::vector<cd> chat((size_t) c.chat_len, make_double2(1.0, 0.0));
+    std::vector<cd> sm((size_t) (P.off_red / 16) + 64, make_double2(0.0, 0.0));
+    for (int i = 0; i < c.tab_len; i++) sm[c.off_tab / 16 + i] = hp.tab2[i];
+    std::vector<double> p((size_t) mx * my, 1.0), u((size_t) mx * my, 0.0);
+    const TraceBuf buf = { sm.data() };
+    TraceLog t; t.lane.resize(32);
+    g_trace = &t;
+    for (int w = 0; w < 12; w++) c2_rows_fwd(P, buf, p.data(), mx, my, mx, w);
+    out[0] = t.wf; out[1] = t.ideal; t.wf = t.ideal = 0;
+    for (int w = 0; w < 12; w++) c2_cols(P, buf, chat.data(), my, my, w);
+    out[2] = t.wf; out[3] = t.ideal; t.wf = t.ideal = 0;
+    for (int w = 0; w < 12; w++) c2_rows_inv(P, buf, u.data(), nullptr, 0, 0, 0, 0, mx, my, mx, w);
+    out[4] = t.wf; out[5] = t.ideal;
+    for (int i = 0; i < 10; i++) { out[6 + 2 * i] = t.swf[i]; out[7 + 2 * i] = t.sideal[i]; }
+    g_trace = nullptr;
+    return 0;
 }

@@ -7,6 +7,20 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
+#include <cuda_runtime.h>
+// per-stage cycle counters of warp CB2_TW of CTA 0: g_tk[i] accumulates the cycles since the previous tick
+__device__ unsigned long long g_tk[16];
+#ifndef CB2_TW
+#define CB2_TW 0
+#endif
+#if defined(__CUDA_ARCH__) && !defined(CB2_NOTICK)
+// fire-and-forget reductions (RED): the instrumented warp must not wait for global memory, it would become the slowest
+#define CB2_TICK_INIT() long long c2_tl_ = clock64()
+#define CB2_TICK(i) do { if (blockIdx.x == 0 && threadIdx.x == 32 * CB2_TW) { const long long t_ = clock64(); atomicAdd(&g_tk[i], (unsigned long long) (t_ - c2_tl_)); c2_tl_ = t_; } } while (0)
+#else
+#define CB2_TICK_INIT()
+#define CB2_TICK(i)
+#endif
 #include "../contact_b200/csrc/plan.h"
 #include "../contact_b200/csrc/chat_kernels.cuh"
 using namespace cb200;
@@ -14,7 +28,7 @@ using namespace cb200;
 __device__ unsigned long long g_ph[8];
 
 __global__ void __launch_bounds__(CB_THREADS, 1)
-k_prod(ConvPlan P, const double *p, const cd *chat, double *u, const int *el, int mask_mode, int ncase, int bw, int bh)
+k_prod(const __grid_constant__ ConvPlan P, const double *p, const cd *chat, double *u, const int *el, int mask_mode, int ncase, int bw, int bh)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem sm = smem_view(P, smem_raw);
@@ -25,7 +39,7 @@ k_prod(ConvPlan P, const double *p, const cd *chat, double *u, const int *el, in
 
 // the warp-resident passes with a clock after each block barrier
 __global__ void __launch_bounds__(CB_THREADS, 1)
-k_prod_phases(ConvPlan P, const double *p, const cd *chat, double *u, int ncase)
+k_prod_phases(const __grid_constant__ ConvPlan P, const double *p, const cd *chat, double *u, int ncase)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem sm = smem_view(P, smem_raw);
@@ -61,6 +75,8 @@ k_prod_phases(ConvPlan P, const double *p, const cd *chat, double *u, int ncase)
     if (tid == 0 && blockIdx.x == 0) { g_ph[0] = a0; g_ph[1] = a1; g_ph[2] = a2; g_ph[3] = n; }
 }
 
+__global__ void k_spin(long long cycles) { const long long t0 = clock64(); while (clock64() - t0 < cycles) { } }
+
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("%s:%d %s\n", __FILE__, __LINE__, cudaGetErrorString(e_)); return 1; } } while (0)
 
 static int upload_plan(HostPlan &hp)
@@ -88,6 +104,7 @@ int main(int argc, char **argv)
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
     const int nsm = prop.multiProcessorCount, ncase = nsm * per_sm, npot = mx * my;
     HostPlan h2; if (!make_plan(mx, my, h2)) { printf("no plan\n"); return 1; }
+    if (argc > 6 && atoi(argv[6]) > 0 && atoi(argv[6]) < h2.p.c2.nslot) h2.p.c2.nslot = atoi(argv[6]);   // experiment: fewer warps at work
     HostPlan h1 = h2; h1.p.c2.ok = 0;                                // the block-wide path with the same layout offsets
     if (upload_plan(h2)) return 1;
     h1.p.twx = h2.p.twx; h1.p.twy = h2.p.twy; h1.p.posx = h2.p.posx;
@@ -131,6 +148,12 @@ int main(int argc, char **argv)
     CK(cudaFuncSetAttribute(k_prod_phases, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     float ms1 = 0, ms2 = 0;
+    {   // SM clock actually delivered: 20 M cycles of spinning on every SM against the event clock
+        k_spin<<<nsm, 32>>>(2000000); CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(e0)); k_spin<<<nsm, 32>>>(20000000); CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+        CK(cudaEventElapsedTime(&ms1, e0, e1));
+        printf("SM clock under a light load: %.0f MHz (nominal %.0f)\n", 20000000.0 / ms1 * 1e-3, prop.clockRate * 1e-3);
+    }
     for (int mode = 0; mode < 2; mode++) {
         for (int rep = 0; rep < 3; rep++) {
             CK(cudaEventRecord(e0));
@@ -159,6 +182,12 @@ int main(int argc, char **argv)
         CK(cudaMemcpyFromSymbol(ph, g_ph, sizeof(ph)));
         printf("warp-resident passes of CTA 0, cycles per product: rows fwd %.0f | columns %.0f | rows inv %.0f\n",
                (double) ph[0] / ph[3], (double) ph[1] / ph[3], (double) ph[2] / ph[3]);
+        unsigned long long tk[16];
+        CK(cudaMemcpyFromSymbol(tk, g_tk, sizeof(tk)));
+        const double np_ = (double) ph[3] + 2.0 * 3 * ((ncase + nsm - 1) / nsm);   // k_prod launches of CTA 0 tick too
+        printf("warp %d of CTA 0, cycles per product and stage (all launches): rowf1 %.0f rowf2 %.0f | colA %.0f colM %.0f colC %.0f | rowi1 %.0f rowi2 %.0f | waiting at barriers etc. %.0f\n",
+               CB2_TW, tk[1] / np_, tk[2] / np_, tk[4] / np_, tk[5] / np_, tk[6] / np_, tk[8] / np_, tk[9] / np_,
+               (tk[0] + tk[3] + tk[7]) / np_);
     }
     return 0;
 }
