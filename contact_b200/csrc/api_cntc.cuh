@@ -528,7 +528,7 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
             nc.cf33 = cs.d_cf[SET_CS] + 8 * nblk; nc.cmx = cs.mx; nc.cmy = cs.my; nc.ga_inv = cs.ga_inv;
             nc.ic_norm = p.norm; nc.maxgs = p.maxgs; nc.maxin = p.maxin; nc.eps = p.eps; nc.dxdy = p.dx * p.dy;
             nc.pen = pen0[ks[i]]; nc.fntrue = p.fntrue;
-            nc.lev = cs.d_lev; nc.nlx = cs.nlx; nc.nly = cs.nly;
+            nc.lev = cs.d_lev; nc.nlx = cs.nlx; nc.nly = cs.nly; nc.stage_bytes = cs.stage_bytes();
             c.tang = p.tang; c.force3 = p.force3; c.maxnr = p.maxnr; c.maxout = p.maxout;
             c.cksi = p.cksi; c.ceta = p.ceta; c.fxrel = p.fxrel; c.fyrel = p.fyrel; c.fstat = p.fstat;
             if (!p.solved || p.iestim == 0 || p.iestim == 2) { if (p.force3 >= 1) c.cksi = 1e-6; if (p.force3 == 2) c.ceta = 0.0; }   // m_sdis.f90:760-762

@@ -226,7 +226,7 @@ inline int snorm_batch_dev(CoefSet &cs, int ncase, int ic_norm, int maxgs, int m
     proto.ga_inv = cs.ga_inv;
     proto.ic_norm = ic_norm; proto.maxgs = maxgs; proto.maxin = maxin; proto.eps = eps;
     proto.dxdy = cs.key.dx * cs.key.dy;
-    proto.lev = cs.d_lev; proto.nlx = cs.nlx; proto.nly = cs.nly;
+    proto.lev = cs.d_lev; proto.nlx = cs.nlx; proto.nly = cs.nly; proto.stage_bytes = cs.stage_bytes();
     if (!cs.hp.fits) return snorm_large_dev(cs, ncase, proto, d_hs, d_el, d_pn, d_un, d_scal, st);
     k_norm_pack<<<grid1d(ncase, 128), 128, 0, st>>>(d_cases, ncase, P.npot, d_hs, d_el, d_pn, d_un, d_scal, d_work, proto);
     CB_CUDA(cudaMemsetAsync(d_next, 0, sizeof(int), st));
@@ -294,6 +294,16 @@ int cb200_conv_prof(unsigned long long *out, int reset)
     if (rc) return rc;
     CB_CUDA(cudaMemcpyFromSymbol(out, g_conv_prof, sizeof(unsigned long long) * 4));
     if (reset) { unsigned long long z[4] = { 0 }; CB_CUDA(cudaMemcpyToSymbol(g_conv_prof, z, sizeof(z))); }
+    return 0;
+}
+
+// all 32 counters (slots 4..31: sections of the solver kernels of CTA 0, see CB_T)
+int cb200_solver_prof(unsigned long long *out, int reset)
+{
+    int rc = engine_init();
+    if (rc) return rc;
+    CB_CUDA(cudaMemcpyFromSymbol(out, g_conv_prof, sizeof(unsigned long long) * 32));
+    if (reset) { unsigned long long z[32] = { 0 }; CB_CUDA(cudaMemcpyToSymbol(g_conv_prof, z, sizeof(z))); }
     return 0;
 }
 int cb200_steady_prof(unsigned long long *out, int reset)

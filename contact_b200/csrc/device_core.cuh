@@ -50,10 +50,21 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// try_wait suspends the thread for a bounded time per attempt.  A copy that never completes (a byte-count or parity
+// bug) traps after ~2 s of waiting instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
-    asm volatile("{\n\t.reg .pred p;\n\tCB_WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-                 "@p bra CB_DONE_%=;\n\tbra CB_WAIT_%=;\n\tCB_DONE_%=:\n\t}" :: "r"(bar), "r"(parity) : "memory");
+    uint32_t done = 0;
+    long long t0 = 0;
+    for (uint32_t tries = 0; !done; tries++) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && (tries & 1023u) == 1023u) {
+            const long long t = clock64();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 4000000000ll) __trap();
+        }
+    }
 }
 
 // Control words of the table cache, kept in the reduction scratch (red[112..113] of the kernel's own plan, common to
@@ -70,7 +81,9 @@ __device__ __forceinline__ void smem_load_tables(const ConvPlan &P, const Smem &
 {
     if (threadIdx.x == 0) {
         mbar_init(conv_hdr_bar(s), 1);
+        mbar_init(conv_hdr_bar(s) + 16u, 1);                        // staged vector passes (VecStage)
         conv_hdr(s)[0] = -1; conv_hdr(s)[1] = 0;
+        *reinterpret_cast<volatile int *>(s.red + CB_HDR_SLOT + 3) = 0;       // parity of the staging barrier's next phase
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -78,7 +91,10 @@ __device__ __forceinline__ void smem_load_tables(const ConvPlan &P, const Smem &
 
 // cycle counters of CTA 0 (development aid, read with cb200_conv_prof): [0] products, [1] cycles inside conv_dev,
 // [2] cycles of the whole solver kernels
-__device__ unsigned long long g_conv_prof[4];
+__device__ unsigned long long g_conv_prof[32];
+// section timer of CTA 0, thread 0: CB_T(k) adds the cycles since the previous mark to g_conv_prof[k] (slots 4..31: solver sections)
+#define CB_T_INIT() long long cb_tl_ = clock64()
+#define CB_T(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long t__ = clock64(); g_conv_prof[k] += (unsigned long long) (t__ - cb_tl_); cb_tl_ = t__; } } while (0)
 
 #define CB_PHASE(call) do { call; __syncthreads(); } while (0)
 #include "conv_sequence.inc"
@@ -89,8 +105,10 @@ __device__ unsigned long long g_conv_prof[4];
 // the box only.  The plan's tables are (re)loaded into shared memory first -- plans of different sizes share the buffer.
 // Warp-resident product (fftconv2.cuh) on the box (x0, y0, bw x bh): rows | columns | rows with one block barrier after
 // each; the plan's twiddle tables are fetched by a bulk-async copy when another plan's are resident.
-__device__ __noinline__ void conv2_box_dev(const ConvPlan &P, const Smem &sm, const double *p, const cd *chat, double *u,
-                                           const int *el, int mask_mode, int add, int x0, int y0, int bw, int bh, int stride)
+// Optional fused element-wise work (ConvFuse, by value: registers across the call); returns the fused masked sum (or 0).
+__device__ __noinline__ double conv2_box_dev(const ConvPlan &P, const Smem &sm, const double *p, const cd *chat, double *u,
+                                             const int *el, int mask_mode, int add, int x0, int y0, int bw, int bh, int stride,
+                                             const ConvFuse fuse)
 {
     const int tid = threadIdx.x, warp = tid >> 5;
     const long long t_in = (tid == 0 && blockIdx.x == 0) ? clock64() : 0;
@@ -107,22 +125,34 @@ __device__ __noinline__ void conv2_box_dev(const ConvPlan &P, const Smem &sm, co
             bulk_g2s(sm.a0 + (uint32_t) c.off_tab, c.tab, (uint32_t) c.tab_len * 16u, bar);
         }
         mbar_wait(bar, (uint32_t) par);
+        if (tid == 0 && blockIdx.x == 0) { g_conv_prof[18] += (unsigned long long) (clock64() - t_in); g_conv_prof[19] += 1; }
     }
     const ShBuf buf;
-    c2_rows_fwd(P, buf, p + (size_t) y0 * stride + x0, bw, bh, stride, warp);
+    const bool f_in = fuse.in_mode != 0, f_sum = fuse.out_sum != 0;
+    c2_rows_fwd(P, buf, p + (size_t) y0 * stride + x0, bw, bh, stride, warp,
+                f_in ? el + (size_t) y0 * stride + x0 : nullptr, fuse.in_shift, fuse.in_mode);
     __syncthreads();
     c2_cols(P, buf, chat, bh, bh, warp);
     __syncthreads();
-    c2_rows_inv(P, buf, u, el, mask_mode, add, x0, y0, bw, bh, stride, warp);
+    c2_rows_inv(P, buf, u, el, mask_mode, add, x0, y0, bw, bh, stride, warp, fuse.out_sub, f_sum ? 1 : 0);
     __syncthreads();
+    double s_ = 0.0;
+    if (f_sum) {                                                // per-warp partials, summed in warp order by every thread
+        const uint32_t osum = (uint32_t) (c.off_tab / 16 + c.tab_len);
+        const int nw = c.nslot;
+        for (int w = 0; w < nw; w++) s_ += buf.ld(osum + (uint32_t) w).x;
+    }
     if (tid == 0 && blockIdx.x == 0) { g_conv_prof[0] += 1; g_conv_prof[1] += (unsigned long long) (clock64() - t_in); }
+    return s_;
 }
+
+__device__ __forceinline__ ConvFuse conv_no_fuse() { ConvFuse f; f.in_mode = 0; f.in_shift = 0.0; f.out_sub = nullptr; f.out_sum = 0; f.sum = 0.0; return f; }
 
 __device__ __noinline__ void conv_box_dev(const ConvPlan &P, const Smem &sm, const double *p, const cd *chat, double *u,
                                           const int *el, int mask_mode, int add, int x0, int y0, int bw, int bh, int stride)
 {
 #ifndef CB_NO_CONV2
-    if (P.c2.ok) { conv2_box_dev(P, sm, p, chat, u, el, mask_mode, add, x0, y0, bw, bh, stride); return; }
+    if (P.c2.ok) { conv2_box_dev(P, sm, p, chat, u, el, mask_mode, add, x0, y0, bw, bh, stride, conv_no_fuse()); return; }
 #endif
     conv_tables_invalidate(sm);                                 // this path overwrites the window of the other one
     const int tid = threadIdx.x, nthr = blockDim.x;

@@ -79,6 +79,12 @@ struct CoefSet {
     ConvLevel *d_lev = nullptr;
     int nlx = 0, nly = 0;
     bool lev_tang = false;
+    // bytes at the bottom of the shared-memory window below the tables of every plan of this set (staged vector passes)
+    int stage_bytes() const {
+        int b = hp.p.c2.ok ? hp.p.c2.off_tab : hp.p.off_red;
+        for (const HostPlan &l : lev_hp) if (l.p.c2.ok && l.p.c2.off_tab < b) b = l.p.c2.off_tab;
+        return b;
+    }
 };
 
 struct Engine {
@@ -243,7 +249,7 @@ inline int build_levels(CoefSet &cs, cudaStream_t st, bool tang = false)
                 memset(&L, 0, sizeof(L));
                 if (lx == 0 && ly == 0) { L.P = cs.hp.p; continue; }
                 // the level plans live in the dynamic shared memory that the kernels are launched with for the full-size plan
-                if (!make_plan(fx[lx], fy[ly], hp, cs.hp.p.smem_bytes) || !hp.fits) { last_error() = "internal: level plan does not fit"; return -99; }
+                if (!make_plan(fx[lx], fy[ly], hp, cs.hp.p.smem_bytes, c2_tab_end(cs.hp.p)) || !hp.fits) { last_error() = "internal: level plan does not fit"; return -99; }
                 ConvPlan &P = hp.p;
                 cd *twx, *twy; unsigned short *posx;
                 CB_CUDA(cudaMalloc(&twx, sizeof(cd) * hp.twx.size()));

@@ -146,6 +146,29 @@ CB_HD void c2_merge_pair(cd p, cd q, cd w, cd &zk, cd &zlk)
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Element-wise work fused into the first and the last stage of a product (the solvers' masked BLAS-1 passes that touch
+// exactly what the product reads or writes, m_gridfunc.f90:936-1591): every input element is loaded by exactly one lane
+// of the first row stage and every output element is produced by exactly one lane of the last one.
+//   input : on the elements with el_i >= 1, written back: p_i := p_i - in_shift (in_mode 1, gf3_proj_avg of the search
+//           direction) or p_i := in_shift * p_i (in_mode 2, rescaling the pressures to the prescribed force);
+//   output: u_i := u_i - out_sub[i] (a right-hand side), and the sum of the new u_i over the elements with el_i >= 1
+//           (the mean that the next projection needs) -- reduced per warp by a fixed shuffle tree, per CTA in warp order.
+struct ConvFuse {
+    int in_mode;             // 0: none, 1: shift, 2: scale the masked input and store it back
+    double in_shift;
+    const double *out_sub;   // null: nothing subtracted
+    int out_sum;             // 1: return the masked sum of the output in `sum`
+    double sum;
+};
+
+#ifdef __CUDA_ARCH__
+#define CB2_NL 1
+#define CB2_LI(lane) 0
+#else
+#define CB2_NL 32
+#define CB2_LI(lane) (lane)
+#endif
+
 // Local memory is poison here: with 227 KB of the SM given to shared memory, L1 keeps ~24 KB, a local word of 384
 // threads is 12 cache lines, so every spill or stack access is an L2 round trip (measured: plan fields read from a stack
 // copy cost 15 %, 2 KB of spills 17 %).  Hence: plan constants by value in registers (C2K), stage functions inlined into
@@ -160,7 +183,8 @@ CB_HD void c2_merge_pair(cd p, cd q, cd w, cd &zk, cd &zlk)
 // stage 1: item (r, j), j < Bx: x[q] = z[j + Bx q] = (row[2n], row[2n+1]); radix-Ax butterfly; y[k1] *= w_Lx^(j k1);
 //          slot[r][k1 * blkx + j]
 template <int A, class B>
-CB_HD void c2_rowf1(uint32_t ok, B buf, uint32_t oslot, const double *src, int nrows, int bw, int stride, int lane)
+CB_HD void c2_rowf1(uint32_t ok, B buf, uint32_t oslot, const double *src, int nrows, int bw, int stride, int lane,
+                    const int *el_src = nullptr, double shift = 0.0, int in_mode = 1)
 {
     const C2K k = c2k_load(buf, ok);
     const int Bx = k.B, items = nrows * Bx;
@@ -174,6 +198,16 @@ CB_HD void c2_rowf1(uint32_t ok, B buf, uint32_t oslot, const double *src, int n
         for (int q = 0; q < NL; q++) {
             const int col = 2 * (int) (j + q * Bx);
             x[q] = make_double2(col < bw ? row[col] : 0.0, col + 1 < bw ? row[col + 1] : 0.0);
+        }
+        if (el_src != nullptr) {                       // fused input pass: masked shift, written back (ConvFuse::in_mode)
+            const int *erow = el_src + (size_t) r * stride;
+            double *wrow = const_cast<double *>(row);
+#pragma unroll
+            for (int q = 0; q < NL; q++) {
+                const int col = 2 * (int) (j + q * Bx);
+                if (col < bw && erow[col] >= 1) { x[q].x = in_mode == 2 ? shift * x[q].x : x[q].x - shift; wrow[col] = x[q].x; }
+                if (col + 1 < bw && erow[col + 1] >= 1) { x[q].y = in_mode == 2 ? shift * x[q].y : x[q].y - shift; wrow[col + 1] = x[q].y; }
+            }
         }
         const uint32_t o = oslot + r * k.len + j, t = k.o_t1 + j;
 #pragma unroll
@@ -302,7 +336,8 @@ CB_HD void c2_rowi1(uint32_t ok, B buf, uint32_t oslot, uint32_t oS, int row0, i
 // of u / el (row stride `stride`); mask_mode 1: only elements with el >= 1 (AllInt), add: u += result
 template <int A, class B>
 CB_HD void c2_rowi2(uint32_t ok, B buf, uint32_t oslot, double *u, const int *el, int mask_mode,
-                    int add, int x0, int y0, int bw, int stride, int row0, int nrows, int lane)
+                    int add, int x0, int y0, int bw, int stride, int row0, int nrows, int lane,
+                    const double *sub = nullptr, double *acc = nullptr)
 {
     const C2K k = c2k_load(buf, ok);
     const int Bx = k.B, items = nrows * Bx, Fx = k.Fx;
@@ -310,6 +345,22 @@ CB_HD void c2_rowi2(uint32_t ok, B buf, uint32_t oslot, double *u, const int *el
     for (int i = lane; i < items; i += 32) {
         const uint32_t r = fdiv((uint32_t) i, k.mg_B), j = (uint32_t) i - r * Bx;
         const uint32_t o = oslot + r * k.len + j, t = k.o_t1 + j;
+        // what the masked store needs from global memory (element division, right-hand side) is requested first: the L2
+        // round trip runs while the butterfly does
+        const size_t r0 = (size_t) (y0 + row0 + (int) r) * stride + x0;
+        constexpr int NZ = 2 * (A - Q0);
+        int ev[NZ]; double sv[NZ]; uint32_t okv = 0u;
+#pragma unroll
+        for (int q = Q0; q < A; q++) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int z_ = 2 * (q - Q0) + h, ic = 2 * (int) (j + q * Bx) - Fx + h;
+                const bool inb = ic >= 0 && ic < bw;
+                if (inb) okv |= 1u << z_;
+                ev[z_] = (inb && el != nullptr) ? el[r0 + ic] : 1;
+                sv[z_] = (inb && sub != nullptr) ? sub[r0 + ic] : 0.0;
+            }
+        }
         cd x[A], tw[A > 1 ? A - 1 : 1];
 #pragma unroll
         for (int q = 0; q < A; q++) x[q] = buf.ld(o + q * k.blk);
@@ -318,14 +369,26 @@ CB_HD void c2_rowi2(uint32_t ok, B buf, uint32_t oslot, double *u, const int *el
 #pragma unroll
         for (int q = 1; q < A; q++) x[q] = cmulc(x[q], tw[q - 1]);
         Dft<A, true>::run(x);
-        const size_t r0 = (size_t) (y0 + row0 + (int) r) * stride + x0;
+        // masked store (+ fused output pass, ConvFuse: right-hand side subtracted, sum over the contact area)
+        double a_ = 0.0;
 #pragma unroll
         for (int q = Q0; q < A; q++) {
-            const int ix = 2 * (int) (j + q * Bx) - Fx;
-            if (ix >= 0 && ix < bw && !(mask_mode == 1 && el[r0 + ix] < 1)) u[r0 + ix] = add ? u[r0 + ix] + x[q].x : x[q].x;
-            if (ix + 1 >= 0 && ix + 1 < bw && !(mask_mode == 1 && el[r0 + ix + 1] < 1))
-                u[r0 + ix + 1] = add ? u[r0 + ix + 1] + x[q].y : x[q].y;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int z_ = 2 * (q - Q0) + h;
+                if (okv & (1u << z_)) {
+                    const int ic = 2 * (int) (j + q * Bx) - Fx + h, e = ev[z_];
+                    if (!(mask_mode == 1 && e < 1)) {
+                        double v = h ? x[q].y : x[q].x;
+                        if (add) v += u[r0 + ic];
+                        if (sub != nullptr) v -= sv[z_];
+                        u[r0 + ic] = v;
+                        if (e >= 1) a_ += v;
+                    }
+                }
+            }
         }
+        if (acc != nullptr) *acc += a_;
     }
 }
 
@@ -378,9 +441,7 @@ CB_HD void c2_colM(uint32_t ok, B buf, uint32_t oslot, const cd *chat_g, int nco
         const cd *hp = chat_g + k1 * k.G + cc;        // (k2 * A + k1) * G + cc
         cd h[Bq], x[Bq];
 #pragma unroll
-        for (int q = 0; q < Bq; q++) {
-            h[q] = c2_ldg_early(hp + q * GA);
-        }
+        for (int q = 0; q < Bq; q++) h[q] = c2_ldg_early(hp + q * GA);
         const uint32_t o = oslot + cc * k.len + k1 * k.blk;
 #pragma unroll
         for (int q = 0; q < Bq; q++) x[q] = buf.ld(o + q);
@@ -504,7 +565,8 @@ CB_HD C2Pass c2_pass_cols(const ConvPlan &P)
 }
 
 template <int AX, int BX, class B>
-CB_HNI void c2_rows_fwd_t(const C2Pass a, B buf, const double *base, int bw, int bh, int stride, int warp)
+CB_HNI void c2_rows_fwd_t(const C2Pass a, B buf, const double *base, int bw, int bh, int stride, int warp,
+                          const int *el_in, double shift, int in_mode)
 {
     if (warp >= a.nslot) return;
     const uint32_t ok = a.ok, oS = a.oS, oslot = a.oW + (uint32_t) (warp * a.slot_len);
@@ -515,7 +577,7 @@ CB_HNI void c2_rows_fwd_t(const C2Pass a, B buf, const double *base, int bw, int
         const int nr = bh - r0 < RG ? bh - r0 : RG;
         const double *src = base + (size_t) r0 * stride;
         CB2_TICK(0);
-        CB2_LANES((c2_rowf1<AX>(ok, buf, oslot, src, nr, bw, stride, lane)));
+        CB2_LANES((c2_rowf1<AX>(ok, buf, oslot, src, nr, bw, stride, lane, el_in ? el_in + (size_t) r0 * stride : nullptr, shift, in_mode)));
         CB2_TICK(1);
         CB2_LANES((c2_rowf2<BX>(ok, buf, oslot, oS, r0, nr, lane)));
         CB2_TICK(2);
@@ -538,6 +600,8 @@ CB_HNI void c2_cols_t(const C2Pass a, B buf, const cd *chat, int n_in, int n_out
         CB2_LANES((c2_colA<AY>(ok, buf, oslot, oScol, nc, n_in, lane)));
         CB2_TICK(4);
         if (g != 0) {
+            // (requesting the coefficients before stage A was tried: the 48 registers they hold through stage A spill to
+            //  local memory, columns 41 k -> 47 k cycles per 91x91 product)
             CB2_LANES((c2_colM<BY>(ok, buf, oslot, chat_g, nc, lane)));
             CB2_TICK(5);
             CB2_LANES((c2_colC<AY>(ok, buf, oslot, oScol, nc, n_out, lane)));
@@ -561,8 +625,10 @@ CB_HNI void c2_cols_t(const C2Pass a, B buf, const cd *chat, int n_in, int n_out
 
 template <int AX, int BX, class B>
 CB_HNI void c2_rows_inv_t(const C2Pass a, B buf, double *u, const int *el, int mask_mode, int add, int x0, int y0, int bw,
-                          int bh, int stride, int warp)
+                          int bh, int stride, int warp, const double *sub, int want_sum, uint32_t osum)
 {
+    double acc[CB2_NL];
+    for (int l = 0; l < CB2_NL; l++) acc[l] = 0.0;
     if (warp >= a.nslot) return;
     const uint32_t ok = a.ok, oS = a.oS, oslot = a.oW + (uint32_t) (warp * a.slot_len);
     const int RG = a.RG, nslot = a.nslot;
@@ -573,8 +639,22 @@ CB_HNI void c2_rows_inv_t(const C2Pass a, B buf, double *u, const int *el, int m
         CB2_TICK(7);
         CB2_LANES((c2_rowi1<BX>(ok, buf, oslot, oS, r0, nr, lane)));
         CB2_TICK(8);
-        CB2_LANES((c2_rowi2<AX>(ok, buf, oslot, u, el, mask_mode, add, x0, y0, bw, stride, r0, nr, lane)));
+        CB2_LANES((c2_rowi2<AX>(ok, buf, oslot, u, el, mask_mode, add, x0, y0, bw, stride, r0, nr, lane, sub,
+                                want_sum ? &acc[CB2_LI(lane)] : nullptr)));
         CB2_TICK(9);
+    }
+    if (want_sum) {
+        // per-warp partial of the fused masked sum: fixed shuffle tree, lane 0 stores it behind the tables (element osum + warp)
+#ifdef __CUDA_ARCH__
+        double s_ = acc[0];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s_ += __shfl_xor_sync(0xffffffffu, s_, o);
+        if ((threadIdx.x & 31u) == 0) buf.st(osum + (uint32_t) warp, make_double2(s_, 0.0));
+#else
+        double s_ = 0.0;
+        for (int l = 0; l < 32; l++) s_ += acc[l];
+        buf.st(osum + (uint32_t) warp, make_double2(s_, 0.0));
+#endif
     }
 }
 
@@ -599,11 +679,12 @@ CB_HD bool c2_col_class(int A, int Bq)
 }
 
 template <class B>
-CB_HD void c2_rows_fwd(const ConvPlan &P, B buf, const double *base, int bw, int bh, int stride, int warp)
+CB_HD void c2_rows_fwd(const ConvPlan &P, B buf, const double *base, int bw, int bh, int stride, int warp,
+                       const int *el_in = nullptr, double shift = 0.0, int in_mode = 1)
 {
     const C2Pass a = c2_pass_rows(P);
     switch (P.c2.Ax * 32 + P.c2.Bx) {
-#define CB2_X_(ax, bx) case ax * 32 + bx: c2_rows_fwd_t<ax, bx>(a, buf, base, bw, bh, stride, warp); break;
+#define CB2_X_(ax, bx) case ax * 32 + bx: c2_rows_fwd_t<ax, bx>(a, buf, base, bw, bh, stride, warp, el_in, shift, in_mode); break;
     CB2_ROW_CLASSES(CB2_X_)
 #undef CB2_X_
     default: break;
@@ -624,11 +705,12 @@ CB_HD void c2_cols(const ConvPlan &P, B buf, const cd *chat, int n_in, int n_out
 
 template <class B>
 CB_HD void c2_rows_inv(const ConvPlan &P, B buf, double *u, const int *el, int mask_mode, int add, int x0, int y0, int bw,
-                       int bh, int stride, int warp)
+                       int bh, int stride, int warp, const double *sub = nullptr, int want_sum = 0)
 {
     const C2Pass a = c2_pass_rows(P);
+    const uint32_t osum = (uint32_t) (P.c2.off_tab / 16 + P.c2.tab_len);        // per-warp partial sums behind the tables
     switch (P.c2.Ax * 32 + P.c2.Bx) {
-#define CB2_X_(ax, bx) case ax * 32 + bx: c2_rows_inv_t<ax, bx>(a, buf, u, el, mask_mode, add, x0, y0, bw, bh, stride, warp); break;
+#define CB2_X_(ax, bx) case ax * 32 + bx: c2_rows_inv_t<ax, bx>(a, buf, u, el, mask_mode, add, x0, y0, bw, bh, stride, warp, sub, want_sum, osum); break;
     CB2_ROW_CLASSES(CB2_X_)
 #undef CB2_X_
     default: break;

@@ -99,6 +99,8 @@ inline void dif_positions(int L, int ns, const int *r, std::vector<unsigned shor
 }
 
 // ---- plan of the warp-resident product (fftconv2.cuh) ----
+inline int c2_tab_end(const ConvPlan &P) { return P.c2.ok ? P.c2.off_tab + (P.c2.tab_len + kPlanWarps) * 16 : 0; }
+
 // cost model used to pick radices and group sizes: FP64 instructions of a radix-R butterfly incl. its twiddles
 inline double c2_bfly_cost(int R) { return R <= 1 ? 0.0 : 3.3 * R * std::log2((double) R) + 4.0 * R; }
 
@@ -106,7 +108,7 @@ inline int c2_next_id() { static int id = 0; return ++id; }
 
 // fills hp.p.c2 and hp.tab2; returns false (c2.ok = 0) when the size is not served (the block-wide path runs then).
 // `end` returns the first byte behind the layout.
-inline bool make_plan2(HostPlan &hp, int smem_limit, long *end)
+inline bool make_plan2(HostPlan &hp, int smem_limit, long *end, int tab_end = 0)
 {
     ConvPlan &P = hp.p;
     Conv2Plan &c = P.c2;
@@ -138,7 +140,7 @@ inline bool make_plan2(HostPlan &hp, int smem_limit, long *end)
     c.o_kr = c.o_tay + (c.Ay - 1) * c.By;                       // stage constants behind the twiddles (20 words = 5 elements each)
     c.o_kc = c.o_kr + CB2_KWORDS / 4;
     c.tab_len = c.o_kc + CB2_KWORDS / 4;
-    const long bytesT = (long) c.tab_len * 16;
+    const long bytesT = (long) (c.tab_len + kPlanWarps) * 16;       // + one partial sum per warp (fused output reductions)
     // group sizes: minimise the estimated FP64 issue time of one product over the warps that get a slot (the paddings
     // below may still take a slot away on the largest grids; they are chosen afterwards)
     const double cA = c2_bfly_cost(c.Ay), cM = 2.0 * c2_bfly_cost(c.By) + 4.0 * c.By;
@@ -237,6 +239,12 @@ inline bool make_plan2(HostPlan &hp, int smem_limit, long *end)
     c.off_S = 0;
     c.off_W = (int) bytesS;
     c.off_tab = c.off_W + c.nslot * c.slot_len * 16;
+    if (tab_end > 0) {
+        // plan of a ladder level: its tables end where those of the full-grid plan end, so that the window below the tables
+        // of ALL plans of a launch is free between products (staged vector passes, norm_solver.cuh)
+        if (tab_end - (int) bytesT < c.off_tab) { std::memset(&c, 0, sizeof(c)); return false; }
+        c.off_tab = tab_end - (int) bytesT;
+    }
     *end = (long) c.off_tab + bytesT;
     c.mg_Bx = div_magic((uint32_t) c.Bx); c.mg_nux = div_magic((uint32_t) c.nux);
     c.mg_By = div_magic((uint32_t) c.By); c.mg_Ay = div_magic((uint32_t) c.Ay);
@@ -260,7 +268,7 @@ inline bool make_plan2(HostPlan &hp, int smem_limit, long *end)
     return true;
 }
 
-inline bool make_plan(int mx, int my, HostPlan &hp, int smem_limit = kSmemMax)
+inline bool make_plan(int mx, int my, HostPlan &hp, int smem_limit = kSmemMax, int tab_end = 0)
 {
     ConvPlan &P = hp.p;
     std::memset(&P, 0, sizeof(P));
@@ -319,7 +327,7 @@ inline bool make_plan(int mx, int my, HostPlan &hp, int smem_limit = kSmemMax)
     P.smem_bytes = P.off_red + 1024;
     // warp-resident product: same shared-memory window, the reduction scratch sits behind both layouts
     long end2 = 0;
-    if (make_plan2(hp, smem_limit, &end2)) {
+    if (make_plan2(hp, smem_limit, &end2, tab_end)) {
         const int e2 = (int) ((end2 + 15) / 16) * 16;
         if (e2 > P.off_red) { P.off_red = e2; P.smem_bytes = P.off_red + 1024; }
     }

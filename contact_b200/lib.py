@@ -92,6 +92,7 @@ PROTOTYPES = {
     "cb200_batch_timing": (I, [C.POINTER(C.c_double)]),
     "cb200_batch_timing_output": (I, [C.POINTER(C.c_double)]),
     "cb200_conv_prof": (I, [C.POINTER(C.c_ulonglong), I]),
+    "cb200_solver_prof": (I, [C.POINTER(C.c_ulonglong), I]),
     "cb200_opt_fft_size": (I, [I]),
     "cb200_coefset_create": (I, [I, I, D, D, D, D, D, D, I, D, D]),
     "cb200_coefset_get_block": (I, [I, I, I, I, dp]),

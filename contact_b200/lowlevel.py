@@ -38,6 +38,23 @@ def conv_prof(reset=True):
     return dict(products=out[0], conv_cycles=out[1], kernel_cycles=out[2])
 
 
+SOLVER_SECTIONS = {4: "normcg set-up", 5: "first residual (product + passes)", 6: "product z = M r", 7: "pass A (z, dots)",
+                   8: "pass B (v)", 9: "product q = A v", 10: "pass C (q, dots)", 11: "pass D (ps, release)",
+                   12: "release bookkeeping / rescale", 13: "product d = A p - rhs", 14: "pass E (residual, entry, box)",
+                   15: "snorm before normcg", 16: "snorm after normcg", 18: "waiting for twiddle tables", 19: "table loads (count)"}
+
+
+def solver_prof(reset=True):
+    """All 32 cycle counters of CTA 0 as {label: cycles} (development aid; see CB_T in csrc/device_core.cuh)."""
+    import ctypes as C
+    out = (C.c_ulonglong * 32)()
+    _check(load_library().cb200_solver_prof(out, 1 if reset else 0))
+    d = dict(products=out[0], conv_cycles=out[1], kernel_cycles=out[2])
+    for k, name in SOLVER_SECTIONS.items():
+        d[name] = out[k]
+    return d
+
+
 def steady_prof(reset=True):
     """Cycle counters of the SteadyGS element step: dict(steps, plstrc, reintegrate, update, calls)."""
     import ctypes as C

@@ -177,6 +177,8 @@ long cb200_num_launches(void);
 /* cycle counters of CTA 0 since the last reset: out[0] fused products, [1] cycles inside them, [2] cycles of
  * k_snorm_batch (development aid for the roofline analysis) */
 int cb200_conv_prof(unsigned long long *out, int reset);
+/* all 32 cycle counters of CTA 0 (slots 4..31: sections of the solver kernels); development aid */
+int cb200_solver_prof(unsigned long long *out, int reset);
 /* cycle counters of the SteadyGS element step summed over all CTAs since the last reset: out[0] element steps,
  * [1] cycles in the per-element solve (plstrc), [2] re-integration, [3] rank-1 updates + barriers, [4] solver calls */
 int cb200_steady_prof(unsigned long long *out, int reset);

@@ -126,7 +126,25 @@ def write_tang_problm_c():
               open(os.path.join(HERE, "tang_problm_c_sequence.json"), "w"), indent=0)
 
 
+def write_test_table():
+    """testbank/test_table_mx11.ref_fx: 3220 Hertzian creepage cases on an 11x11 grid (NormCG + SteadyGS), Fx, Fy, Mz relative
+    to mu Fn (Mz also to cp) with 6 decimals and the slip share; case order of src/test_table.f90:196-292."""
+    lines = open(os.path.join(REF, "testbank/test_table_mx11.ref_fx")).read().splitlines()
+    hz, rows = [], []
+    for l in lines:
+        m = re.match(r"iell=(\d+), a/b=\s*([\d.]+): rho=\s*([\d.Ee+-]+)\s*, cp=\s*([\d.Ee+-]+)", l)
+        if m:
+            hz.append(dict(iell=int(m.group(1)), aob=float(m.group(2)), rho=float(m.group(3)), cp=float(m.group(4))))
+        m = re.match(r"Fx=\s*([-\d.]+), Fy=\s*([-\d.]+), Mz=\s*([-\d.]+), %Slip=\s*([\d.]+)", l)
+        if m:
+            rows.append([float(m.group(1)), float(m.group(2)), float(m.group(3)), float(m.group(4))])
+    assert len(hz) == 5 and len(rows) == 5 * 4 * 7 * 23
+    json.dump(dict(source="testbank/test_table_mx11.ref_fx (driver: src/test_table.f90)", hertz=hz, columns=["fx", "fy", "mz", "pct_slip"],
+                   rows=rows), open(os.path.join(HERE, "test_table_mx11.json"), "w"))
+
+
 if __name__ == "__main__":
+    write_test_table()
     write_tang_problm_c()
     write_sequences()
     write_spence71()

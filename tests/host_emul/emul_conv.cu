@@ -19,17 +19,17 @@ static void trace_flush(TraceLog &t)
     for (size_t k = 0; k < n; k++) {
         int active = 0;
         for (int q = 0; q < 4; q++) {
-            int cnt[8] = { 0 }; uint32_t seen[8][8]; int any = 0;
+            int cnt[8] = { 0 }; uint32_t seen[8][8];
             for (int l = 8 * q; l < 8 * q + 8; l++) {
                 if (t.lane[l].size() <= k) continue;
                 const uint32_t a = t.lane[l][k]; if (a == 0xFFFFFFFFu) continue;
                 const int b = a & 7; bool dup = false;
                 for (int z = 0; z < cnt[b]; z++) dup = dup || seen[b][z] == a;
                 if (!dup) seen[b][cnt[b]++] = a;
-                any = 1; active++;
+                active++;
             }
             int m = 0; for (int b = 0; b < 8; b++) m = std::max(m, cnt[b]);
-            t.wf += m; t.swf[t.stage] += m; (void) any;
+            t.wf += m; t.swf[t.stage] += m;
         }
         t.ideal += (active + 7) / 8; t.sideal[t.stage] += (active + 7) / 8; t.instr++;
     }
@@ -153,8 +153,22 @@ extern "C" int emul_plan2_info(int mx, int my, int *out)
     return 0;
 }
 
+// fuse: in_mode (0 none, 1 shift, 2 scale) with in_val on the elements el >= 1 of the box, written back to p; out_sub
+// (null: none) subtracted from the result; *out_sum receives the sum of the stored result over el >= 1 (null: not wanted)
+extern "C" int emul_conv2_fused(int pmx, int pmy, int mx, double *p, const double *cfblk, int cmx, int cmy, double scale,
+                                const int *el, int mask_mode, int add, double *u, int x0, int y0, int bw, int bh, int nwarps,
+                                int in_mode, double in_val, const double *out_sub, double *out_sum);
+
 extern "C" int emul_conv2(int pmx, int pmy, int mx, const double *p, const double *cfblk, int cmx, int cmy, double scale,
                           const int *el, int mask_mode, int add, double *u, int x0, int y0, int bw, int bh, int nwarps)
+{
+    return emul_conv2_fused(pmx, pmy, mx, const_cast<double *>(p), cfblk, cmx, cmy, scale, el, mask_mode, add, u, x0, y0, bw, bh,
+                            nwarps, 0, 0.0, nullptr, nullptr);
+}
+
+extern "C" int emul_conv2_fused(int pmx, int pmy, int mx, double *p, const double *cfblk, int cmx, int cmy, double scale,
+                                const int *el, int mask_mode, int add, double *u, int x0, int y0, int bw, int bh, int nwarps,
+                                int in_mode, double in_val, const double *out_sub, double *out_sum)
 {
     HostPlan hp;
     if (!make_plan(pmx, pmy, hp)) return -1;
@@ -175,9 +189,15 @@ extern "C" int emul_conv2(int pmx, int pmy, int mx, const double *p, const doubl
     std::vector<cd> sm((size_t) (P.off_red / 16) + 64, make_double2(1e300, -1e300));   // poisoned: stale reads show up
     for (int i = 0; i < c.tab_len; i++) sm[c.off_tab / 16 + i] = hp.tab2[i];
     const MemBuf<cd> buf = { sm.data() };
-    for (int w = 0; w < nwarps; w++) c2_rows_fwd(P, buf, p + (size_t) y0 * mx + x0, bw, bh, mx, w);
+    for (int w = 0; w < nwarps; w++)
+        c2_rows_fwd(P, buf, p + (size_t) y0 * mx + x0, bw, bh, mx, w, in_mode ? el + (size_t) y0 * mx + x0 : nullptr, in_val, in_mode);
     for (int w = 0; w < nwarps; w++) c2_cols(P, buf, chat.data(), bh, bh, w);
-    for (int w = 0; w < nwarps; w++) c2_rows_inv(P, buf, u, el, mask_mode, add, x0, y0, bw, bh, mx, w);
+    for (int w = 0; w < nwarps; w++) c2_rows_inv(P, buf, u, el, mask_mode, add, x0, y0, bw, bh, mx, w, out_sub, out_sum ? 1 : 0);
+    if (out_sum) {                                   // per-warp partials behind the tables, summed in warp order (conv2_box_dev)
+        double s_ = 0.0;
+        for (int w = 0; w < c.nslot && w < nwarps; w++) s_ += sm[c.off_tab / 16 + c.tab_len + w].x;
+        *out_sum = s_;
+    }
     return 0;
 }
 
