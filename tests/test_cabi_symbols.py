@@ -73,3 +73,20 @@ def test_no_cpu_fallback(dll):
     with pytest.raises(cb.lowlevel.CB200Error):
         cb.lowlevel.CoefSet(5, 5, 0.1, 0.1)
     cb.cntc_finalize(902)
+
+
+def test_fortran_interface_file_is_current_and_complete():
+    """include/contact_addon_b200.ifc (ISO_C_BINDING interface block, the counterpart of the reference's src/contact_addon.ifc)
+    is what tools/gen_ifc.py derives from the C header, and it declares every cntc_* / subs_* entry point of the header."""
+    import importlib.util
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_ifc", os.path.join(root, "tools", "gen_ifc.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    text = open(os.path.join(root, "include", "contact_addon_b200.ifc")).read()
+    assert text == gen.render()
+    declared = set(re.findall(r"bind\(c, name='(\w+)'\)", text))
+    header = {name for name, _, _ in gen.prototypes()}
+    assert declared == header and len(declared) >= 66 and "cntc_calculate_batch" in declared
+    assert len(re.findall(r"^end subroutine ", text, flags=re.M)) == len(declared)

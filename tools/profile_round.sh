@@ -17,6 +17,8 @@ for f in prof_snorm prof_large prof_gd; do
     ncu -i gpurun_out/${f}_${TAG}.ncu-rep --page raw --csv > gpurun_out/${f}_${TAG}.raw.csv 2>/dev/null
 done
 ncu -i gpurun_out/prof_snorm_${TAG}.ncu-rep --page source --csv > gpurun_out/prof_snorm_${TAG}.source.csv 2>/dev/null
+ncu -i gpurun_out/prof_snorm_${TAG}.ncu-rep --page source --print-source cuda --csv > gpurun_out/prof_snorm_${TAG}.cuda.csv 2>/dev/null
+gzip -f gpurun_out/prof_snorm_${TAG}.cuda.csv
 ls -la gpurun_out/*.ncu-rep
 # keep the merge under the 64 MiB limit
 for f in gpurun_out/*.ncu-rep; do s=$(stat -c %s $f); if [ $s -gt 25000000 ]; then rm -f $f; fi; done
