@@ -62,6 +62,7 @@ struct Problem {
     int gd_meth = 1, gd_kdown = 3, gd_kdowfb = 1, gd_fallback = 0, gd_ntrial = 0;
     // results
     int ncase = 0, itnorm = 0, ittang = 0, itcg = 0, ncon = 0, nadh = 0, nslip = 0, status = 0, itout = 0;
+    double pan_dif[16] = { 0 }, pan_difid[16] = { 0 };
     std::vector<int> el;
     std::vector<double> ps, us, hs, ss;  // [3][npot]
     std::vector<double> pv;              // [3][npot] tractions of the previous time instance (set_prev_data)
@@ -324,7 +325,7 @@ inline int hertz_setup(Problem &p)
 // wall-clock split of the last calculate_batch call (s): [0] host set-up of the cases, [1] coefficient transforms (cached),
 // [2] device allocation + uploads, [3] solver kernel(s), [4] output products + downloads, [5] total
 // split of [4]: [6] us products incl. their buffers, [7] downloads, [8] host post-processing, [9] device frees
-inline double *batch_timing() { static double t[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 }; return t; }
+inline double *batch_timing() { static double t[CB_MAX_DEVICES][10] = { { 0 } }; return t[current_device()]; }
 
 // independent per-case host work (copies into the problems' own vectors, force sums) over a few host threads
 template <class F> inline void host_parallel_for(int n, F fn)
@@ -352,7 +353,7 @@ struct BatchPool {
     ContactCase *d_cases = nullptr;
     size_t c_buf = 0, c_us = 0, c_pb = 0, c_el = 0, c_cases = 0, c_hfld = 0, c_hus = 0, c_hel = 0;
 };
-inline BatchPool &batch_pool() { static BatchPool p; return p; }
+inline BatchPool &batch_pool() { static BatchPool p[CB_MAX_DEVICES]; return p[current_device()]; }
 template <class T> inline bool pool_dev(T *&ptr, size_t &cap, size_t need)
 {
     if (need <= cap) return true;
@@ -657,6 +658,7 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
                 std::copy(hs[ks[i]].begin(), hs[ks[i]].end(), p.hs.begin() + 2 * (size_t) npot);
                 p.pen = c.nrm.pen; p.fntrue = c.nrm.fntrue; p.itcg = c.nrm.itcg; p.itnorm = c.nrm.itnorm; p.ncon = c.nrm.ncon;
                 p.status = c.nrm.status; p.ittang = c.ittang; p.itgs = c.itgs; p.itout = c.itout; p.nadh = c.nadh; p.nslip = c.nslip;
+                for (int k = 0; k < 16; k++) { p.pan_dif[k] = c.pan_dif[k]; p.pan_difid[k] = c.pan_difid[k]; }
                 p.nr_itcg.assign(c.nr_itcg, c.nr_itcg + std::min(c.nr_n, (int) CB_MAXNR_LOG));
                 p.gd_fallback = c.gd_fallback; p.gd_ntrial = c.gd_ntrial;
                 for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) p.sens_nr[a][b] = c.sens[a][b];
@@ -951,6 +953,29 @@ int cb200_get_iterations(int ire, int icp, int *out, int lenarr, int *nr_itcg)
     return 0;
 }
 
+// Replace the stored solution of a problem (element division and tractions [3][npot]: x, y, n) -- the state that the next case
+// of a sequence starts from (I and P digits).  The reference keeps this state inside gd and offers no setter; the parity tests use
+// it to run every stage of a sequence from the oracle's previous stage, so that differences cannot accumulate over the stages.
+int cb200_set_state(int ire, int icp, int npot, const int *el, const double *ps)
+{
+    int e; Problem *p = activate(ire, icp, &e);
+    if (!p) return e;
+    if (npot != p->mx * p->my) { last_error() = "cb200_set_state: npot does not match the grid of the problem"; return CNTC_err_input; }
+    p->el.assign(el, el + npot);
+    p->ps.assign(ps, ps + 3 * (size_t) npot);
+    p->solved = true;
+    return 0;
+}
+
+int cb200_get_outer_history(int ire, int icp, int lenarr, double *dif, double *difid)
+{
+    int e; Problem *p = activate(ire, icp, &e);
+    if (!p) return e;
+    const int n = std::min(16, p->itout);
+    for (int k = 0; k < n && k < lenarr; k++) { dif[k] = p->pan_dif[k]; difid[k] = p->pan_difid[k]; }
+    return n;
+}
+
 void cntc_calculate(int *ire, int *icp, int *ierror)
 {
     Problem *p = activate(*ire, *icp, ierror);
@@ -963,6 +988,37 @@ void cntc_calculate(int *ire, int *icp, int *ierror)
     *ierror = ie[0];
 }
 
+} // extern "C" (helpers of the multi-device fan-out follow)
+inline std::vector<int> &fanout_list() { static std::vector<int> f; return f; }
+inline bool &fanout_env_done() { static bool b = false; return b; }
+inline std::vector<int> fanout_devices()
+{
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!fanout_env_done()) {
+        fanout_env_done() = true;
+        const char *e = getenv("CONTACT_B200_DEVICES");
+        int ndev = 0;
+        if (e && *e && cudaGetDeviceCount(&ndev) == cudaSuccess) {
+            std::vector<int> &F = fanout_list();
+            std::string s(e);
+            if (s == "all") { for (int d = 0; d < ndev && d < CB_MAX_DEVICES; d++) F.push_back(d); }
+            else if (s.find(',') == std::string::npos) { const int n = atoi(e); for (int d = 0; d < n && d < ndev && d < CB_MAX_DEVICES; d++) F.push_back(d); }
+            else {
+                size_t a = 0;
+                while (a < s.size()) {
+                    size_t b = s.find(',', a); if (b == std::string::npos) b = s.size();
+                    const int d = atoi(s.substr(a, b - a).c_str());
+                    if (d >= 0 && d < ndev && d < CB_MAX_DEVICES) F.push_back(d);
+                    a = b + 1;
+                }
+            }
+        }
+    }
+    return fanout_list();
+}
+extern "C" {
+
 void cntc_calculate_batch(int *nre, int *ire, int *icp, int *ierror)
 {
     std::vector<Problem *> v;
@@ -974,8 +1030,52 @@ void cntc_calculate_batch(int *nre, int *ire, int *icp, int *ierror)
     int rc = engine_init();
     if (rc) { for (int k = 0; k < *nre; k++) ierror[k] = rc; return; }
     std::vector<int> ie;
-    calculate_batch(v, ie);
+    const std::vector<int> devs = fanout_devices();
+    const size_t nd = std::min(devs.size(), v.size() / 8);          // a device is worth its set-up from a handful of cases on
+    if (nd <= 1) calculate_batch(v, ie);
+    else {
+        // The batched case scheduler across the GPUs of one box: contiguous shards of the case list, one host thread per device,
+        // no inter-GPU traffic (every device builds and caches the coefficient transforms of the classes it meets); the results
+        // land in the callers' Problem records, i.e. the "final gather" is the join.
+        int dev0 = 0;
+        cudaGetDevice(&dev0);
+        ie.assign(v.size(), 0);
+        std::vector<std::string> errs(nd);
+        std::vector<std::thread> th;
+        for (size_t d = 0; d < nd; d++)
+            th.emplace_back([&, d] {
+                const size_t lo = v.size() * d / nd, hi = v.size() * (d + 1) / nd;
+                std::vector<Problem *> part(v.begin() + lo, v.begin() + hi);
+                std::vector<int> pe;
+                int r = cudaSetDevice(devs[d]) == cudaSuccess ? engine_init() : CNTC_err_other;
+                if (r) pe.assign(part.size(), r);
+                else calculate_batch(part, pe);
+                for (size_t i = 0; i < part.size(); i++) ie[lo + i] = pe[i];
+                errs[d] = last_error();                              // thread-local: hand the message to the caller's thread
+            });
+        for (auto &t : th) t.join();
+        cudaSetDevice(dev0);
+        for (size_t d = 0; d < nd; d++) if (!errs[d].empty()) last_error() = errs[d];
+    }
     for (size_t i = 0; i < v.size(); i++) ierror[pos[i]] = ie[i];
+}
+
+/* Devices that cntc_calculate_batch spreads a batch over: n <= 0 or 1 = the calling thread's current device only (default);
+ * n > 1 = devices 0 .. n-1 (or the list devs[0..n-1] when given).  Also settable by the environment variable
+ * CONTACT_B200_DEVICES = "all" | n | "0,2,3" read at the first batch.  Returns the number of devices in use. */
+int cb200_set_devices(int n, const int *devs)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { last_error() = "contact_addon_b200: no CUDA device available"; return -99; }
+    std::vector<int> &F = fanout_list();
+    F.clear();
+    for (int k = 0; k < n; k++) {
+        const int d = devs ? devs[k] : k;
+        if (d < 0 || d >= ndev || d >= CB_MAX_DEVICES) { F.clear(); last_error() = "cb200_set_devices: no such device"; return CNTC_err_input; }
+        F.push_back(d);
+    }
+    fanout_env_done() = true;
+    return F.empty() ? 1 : (int) F.size();
 }
 
 void cntc_getnumelements(int *ire, int *icp, int *mx, int *my)

@@ -155,7 +155,7 @@ __global__ void k_norm_unpack(const NormCase *cases, int ncase, double *scal)
 }
 
 // u_n = A_zz p_n on the contact area after the solve (soutpt, m_soutpt.f90:378-385), batched
-inline NormBatch &norm_batch() { static NormBatch b; return b; }
+inline NormBatch &norm_batch() { static NormBatch b[CB_MAX_DEVICES]; return b[current_device()]; }
 
 // grids beyond one CTA: one cooperative whole-GPU launch per case (cases run one after the other)
 inline int snorm_large_dev(CoefSet &cs, int ncase, NormCase proto, const double *d_hs, int *d_el, double *d_pn,
@@ -249,7 +249,7 @@ inline int snorm_batch_dev(CoefSet &cs, int ncase, int ic_norm, int maxgs, int m
 
 // ---- batched subsurface evaluation on device buffers ----
 struct SubsBatch { double *d_vr = nullptr; long cap = 0; int *d_next = nullptr; };
-inline SubsBatch &subs_batch() { static SubsBatch b; return b; }
+inline SubsBatch &subs_batch() { static SubsBatch b[CB_MAX_DEVICES]; return b[current_device()]; }
 
 inline int subsurf_batch_dev(CoefSet &cs, int ncase, int nz, const double *z, const double gg[2], const double poiss[2],
                              const double *d_ps, double *d_table, cudaStream_t st)
@@ -294,6 +294,17 @@ int cb200_conv_prof(unsigned long long *out, int reset)
     if (rc) return rc;
     CB_CUDA(cudaMemcpyFromSymbol(out, g_conv_prof, sizeof(unsigned long long) * 4));
     if (reset) { unsigned long long z[4] = { 0 }; CB_CUDA(cudaMemcpyToSymbol(g_conv_prof, z, sizeof(z))); }
+    return 0;
+}
+
+// work counters of all CTAs since the last reset: out[0] products, [1] nominal flops of the products at the transform sizes used,
+// [2] algorithmic bytes of the products (17 per box element), [3] Gauss-Seidel row-sum units ncon (ncon + 2 my) summed over sweeps
+int cb200_work_counters(unsigned long long *out, int reset)
+{
+    int rc = engine_init();
+    if (rc) return rc;
+    CB_CUDA(cudaMemcpyFromSymbol(out, g_work, sizeof(unsigned long long) * 4));
+    if (reset) { unsigned long long z[4] = { 0 }; CB_CUDA(cudaMemcpyToSymbol(g_work, z, sizeof(z))); }
     return 0;
 }
 

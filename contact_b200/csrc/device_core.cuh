@@ -96,6 +96,18 @@ __device__ unsigned long long g_conv_prof[32];
 #define CB_T_INIT() long long cb_tl_ = clock64()
 #define CB_T(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long t__ = clock64(); g_conv_prof[k] += (unsigned long long) (t__ - cb_tl_); cb_tl_ = t__; } } while (0)
 
+// work accounting of ALL CTAs (read with cb200_work_counters): one atomic per product by thread 0 --
+// [0] products, [1] nominal flops at the transform size actually used (the contact-box level, not the full grid),
+// [2] algorithmic bytes 17 per element of the box (8 in, 8 out, 1 mask: SURVEY 8(d) B_batched at the box size)
+__device__ unsigned long long g_work[4];
+__device__ __forceinline__ void work_count(const ConvPlan &P, int bw, int bh)
+{
+    if (threadIdx.x == 0) {
+        atomicAdd(&g_work[0], 1ull); atomicAdd(&g_work[1], (unsigned long long) P.nom_flops);
+        atomicAdd(&g_work[2], 17ull * (unsigned long long) (bw * bh));
+    }
+}
+
 #define CB_PHASE(call) do { call; __syncthreads(); } while (0)
 #include "conv_sequence.inc"
 
@@ -112,6 +124,7 @@ __device__ __noinline__ double conv2_box_dev(const ConvPlan &P, const Smem &sm, 
 {
     const int tid = threadIdx.x, warp = tid >> 5;
     const long long t_in = (tid == 0 && blockIdx.x == 0) ? clock64() : 0;
+    work_count(P, bw, bh);
     const Conv2Plan &c = P.c2;
     volatile int *hdr = conv_hdr(sm);
     if (hdr[0] != c.id) {                                       // uniform over the CTA
@@ -155,6 +168,7 @@ __device__ __noinline__ void conv_box_dev(const ConvPlan &P, const Smem &sm, con
     if (P.c2.ok) { conv2_box_dev(P, sm, p, chat, u, el, mask_mode, add, x0, y0, bw, bh, stride, conv_no_fuse()); return; }
 #endif
     conv_tables_invalidate(sm);                                 // this path overwrites the window of the other one
+    work_count(P, bw, bh);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const long long t_in = (tid == 0 && blockIdx.x == 0) ? clock64() : 0;
     typedef MemBuf<cd> CB_BUF;

@@ -97,7 +97,12 @@ struct Engine {
     long launches = 0;            // kernels launched by this library (for bench "gpu_launches")
 };
 
-inline Engine &engine() { static Engine e; return e; }
+// One instance per CUDA device: the calling thread's current device selects it.  cntc_calculate_batch can fan a batch out over
+// several devices (one host thread per device, cb200_set_devices): each device has its own coefficient cache, work-space pool,
+// events and kernel attributes, so the per-device threads share nothing but the problem registry.
+#define CB_MAX_DEVICES 16
+inline int current_device() { int d = 0; if (cudaGetDevice(&d) != cudaSuccess) d = 0; return (d >= 0 && d < CB_MAX_DEVICES) ? d : 0; }
+inline Engine &engine() { static Engine e[CB_MAX_DEVICES]; return e[current_device()]; }
 
 inline int engine_init()
 {

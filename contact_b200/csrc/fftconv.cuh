@@ -81,6 +81,7 @@ struct ConvPlan {
     int wslot_len;              // cd elements per W slot (padded layout, ViewSk)
     uint32_t mg_G, mg_gpc;      // division magics
     Conv2Plan c2;               // warp-resident product (fftconv2.cuh)
+    unsigned int nom_flops;     // nominal flops of ONE product with this plan: 2 * 2.5 N log2 N + 6 S, N = 4 Fx Fy, S = (Fx+1) 2Fy (work accounting)
 };
 
 // ---- exact division of small non-negative integers by a run-time constant: q = (n * magic) >> 32 ----

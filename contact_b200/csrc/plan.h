@@ -325,6 +325,7 @@ inline bool make_plan(int mx, int my, HostPlan &hp, int smem_limit = kSmemMax, i
     P.off_posx = P.off_twy + 2 * P.Fy * 16;
     P.off_red = P.off_posx + ((P.Lx * 2 + 15) / 16) * 16;
     P.smem_bytes = P.off_red + 1024;
+    { const double N = 4.0 * P.Fx * P.Fy, S = (P.Fx + 1) * 2.0 * P.Fy; P.nom_flops = (unsigned int) (5.0 * N * log2(N) + 6.0 * S); }
     // warp-resident product: same shared-memory window, the reduction scratch sits behind both layouts
     long end2 = 0;
     if (make_plan2(hp, smem_limit, &end2, tab_end)) {

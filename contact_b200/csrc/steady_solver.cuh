@@ -327,6 +327,8 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
                  l11 = ledge ? a.cs22[oc] * a.ga_inv : 0.0;
     while (dif >= difid && itgs < a.maxgs) {
         itgs++;
+        // work accounting: a sweep is 2 ncon row sums over (ncon + 2 my) 2 columns in the reference
+        if (threadIdx.x == 0) atomicAdd(&g_work[3], (unsigned long long) ncon * (unsigned long long) (ncon + 2 * P.my));
         double dsum = 0.0;                                     // lane 0 of warp 0 only
         if (ledge) {
             // subnd (m_leadedge.f90:336-394) at the start of every sweep (:2583): displacement difference of the current

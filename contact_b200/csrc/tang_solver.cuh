@@ -49,6 +49,7 @@ struct ContactCase {
     double nr_cksi[CB_MAXNR_LOG], nr_ceta[CB_MAXNR_LOG], nr_fx[CB_MAXNR_LOG], nr_fy[CB_MAXNR_LOG];
     double fx, fy, sens[2][2];
     int nadh, nslip;
+    double pan_dif[16], pan_difid[16];  // dif / difid of panprc's convergence test per outer iteration (m_scontc.f90:510-513)
     int tstatus;                    // bit 0: the case needs a solver outside this path (ConvexGS / GDsteady)
 };
 
@@ -619,6 +620,7 @@ __device__ void panprc_dev(const X &x, ContactCase &c)
             dif = sqrt(s[0] / fmax(1.0, s[2]));
             difid = 5.0 * c.nrm.eps * sqrt(s[1] / fmax(1.0, s[2]));
         }
+        if (x.leader() && itout <= 16) { c.pan_dif[itout - 1] = dif; c.pan_difid[itout - 1] = difid; }
     }
     int nadh, nslip;
     count_el(x, el, n, nadh, nslip);

@@ -210,8 +210,10 @@ def resolve_cases(cases):
     return out
 
 
-def run_inp(text, ire=1, icp=1, api=None, with_fields=True):
-    """Run all cases of an .inp text through the cntc_* interface; returns one result dict per case."""
+def run_inp(text, ire=1, icp=1, api=None, with_fields=True, subs_cases=None, before_case=None):
+    """Run all cases of an .inp text through the cntc_* interface; returns one result dict per case.
+    subs_cases: case numbers whose subsurface tables are fetched (None: all cases, when with_fields).
+    before_case(n): called just before cntc_calculate of case n (1-based), after all its inputs are set."""
     if api is None:
         import contact_b200 as api
     cb = api
@@ -265,11 +267,14 @@ def run_inp(text, ire=1, icp=1, api=None, with_fields=True):
         else:
             cb.cntc_setcreepages(ire, icp, 0.0, 0.0, k[3])
             cb.cntc_settangentialforces(ire, icp, k[1], k[2])
+        if before_case is not None:
+            before_case(n)
         t0 = time.perf_counter()
         ierr = cb.cntc_calculate(ire, icp)
         res = dict(case=n, ierror=ierr, wall_s=time.perf_counter() - t0)
         if ierr >= 0:
             its = cb.lowlevel.get_iterations(ire, icp)
+            its["outer_history"] = cb.lowlevel.get_outer_history(ire, icp)
             el = cb.cntc_getelementdivision(ire, icp)
             fn, tx, ty, mz = cb.cntc_getcontactforces(ire, icp)
             res.update(its=its, ncon=int((el >= 1).sum()), nadh=int((el == 1).sum()), nslip=int((el == 2).sum()),
@@ -292,7 +297,7 @@ def run_inp(text, ire=1, icp=1, api=None, with_fields=True):
                 t0 = time.perf_counter()
                 res["subs_ierror"] = cb.subs_calculate(ire, icp)
                 res["subs_wall_s"] = time.perf_counter() - t0
-                if with_fields and res["subs_ierror"] == 0:
+                if with_fields and res["subs_ierror"] == 0 and (subs_cases is None or n in subs_cases):
                     res["subs"] = [cb.subs_getresults(ire, icp, ib, list(range(1, 22))) for ib in range(1, len(c["subs"]) + 1)]
         else:
             res["message"] = cb.lib.last_error()

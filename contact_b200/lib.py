@@ -84,6 +84,9 @@ PROTOTYPES = {
     "cntc_finalizelast": (None, []),
     "cntc_calculate_batch": (None, [ip, ip, ip, ip]),
     "cb200_get_iterations": (I, [I, I, ip, I, ip]),
+    "cb200_get_outer_history": (I, [I, I, I, dp, dp]),
+    "cb200_set_state": (I, [I, I, I, ip, dp]),
+    "cb200_set_devices": (I, [I, ip]),
     "cb200_last_error": (C.c_char_p, []),
     "cb200_num_launches": (L, []),
     "cb200_num_sms": (I, []),
@@ -92,6 +95,7 @@ PROTOTYPES = {
     "cb200_batch_timing": (I, [C.POINTER(C.c_double)]),
     "cb200_batch_timing_output": (I, [C.POINTER(C.c_double)]),
     "cb200_conv_prof": (I, [C.POINTER(C.c_ulonglong), I]),
+    "cb200_work_counters": (I, [C.POINTER(C.c_ulonglong), I]),
     "cb200_solver_prof": (I, [C.POINTER(C.c_ulonglong), I]),
     "cb200_opt_fft_size": (I, [I]),
     "cb200_coefset_create": (I, [I, I, D, D, D, D, D, D, I, D, D]),

@@ -38,6 +38,14 @@ def conv_prof(reset=True):
     return dict(products=out[0], conv_cycles=out[1], kernel_cycles=out[2])
 
 
+def work_counters(reset=True):
+    """Work of all CTAs since the last reset: products, their nominal flops and algorithmic bytes at the transform sizes
+    actually used, Gauss-Seidel row-sum units (ncon (ncon + 2 my) per sweep)."""
+    out = (C.c_ulonglong * 4)()
+    _check(load_library().cb200_work_counters(out, 1 if reset else 0))
+    return dict(products=int(out[0]), product_flops=int(out[1]), product_bytes=int(out[2]), gs_units=int(out[3]))
+
+
 SOLVER_SECTIONS = {4: "normcg set-up", 5: "first residual (product + passes)", 6: "product z = M r", 7: "pass A (z, dots)",
                    8: "pass B (v)", 9: "product q = A v", 10: "pass C (q, dots)", 11: "pass D (ps, release)",
                    12: "release bookkeeping / rescale", 13: "product d = A p - rhs", 14: "pass E (residual, entry, box)",
@@ -193,6 +201,30 @@ def get_iterations(ire, icp=1):
     _check(load_library().cb200_get_iterations(ire, icp, out, 64, log))
     return dict(itnorm=out[0], itcg=out[1], ittang=out[2], itgs=out[3], ncon=out[4], nr_itcg=list(log[:out[5]]), itout=out[6],
                 gd_trials=(out[7] if out[7] >= 0 else -out[7] - 1), gd_fallback=int(out[7] < 0))
+
+
+def set_state(ire, icp, el, ps):
+    """Test hook: the stored solution (el (npot,), ps (3, npot): x, y, n) that the next case of a sequence starts from."""
+    el = np.ascontiguousarray(el, dtype=np.int32).ravel(); ps = np.ascontiguousarray(ps, dtype=np.float64).reshape(3, -1)
+    _check(load_library().cb200_set_state(ire, icp, el.size, el.ctypes.data_as(C.POINTER(C.c_int)), ps.ctypes.data_as(C.POINTER(C.c_double))))
+
+
+def set_devices(n, devs=None):
+    """Devices cntc_calculate_batch spreads a batch over (1: the current device only); returns the number in use."""
+    arr = None if devs is None else (C.c_int * len(devs))(*devs)
+    r = load_library().cb200_set_devices(int(n), arr)
+    if r < 0:
+        _check(r)
+    return r
+
+
+def get_outer_history(ire, icp=1):
+    """(dif, difid) of panprc's convergence test per outer iteration of the last solve"""
+    d = (C.c_double * 16)(); e = (C.c_double * 16)()
+    n = load_library().cb200_get_outer_history(ire, icp, 16, d, e)
+    if n < 0:
+        _check(n)
+    return list(d[:n]), list(e[:n])
 
 
 def snorm_kernel_ms():

@@ -163,6 +163,17 @@ void cntc_calculate_batch(int *nre, int *ire, int *icp, int *ierror);
  * line-search trials (negated - 1 when a stagnating GDsteady fell back to SteadyGS, m_solvpt.f90:474-484); nr_itcg =
  * iterations per solver call (Newton-Raphson log) */
 int cb200_get_iterations(int ire, int icp, int *out, int lenarr, int *nr_itcg);
+/* Devices that cntc_calculate_batch spreads a batch over (the batched case scheduler across the GPUs of one box: contiguous shards
+ * of the case list, one host thread per device, no inter-GPU traffic).  n <= 1: the calling thread's current device only (default);
+ * n > 1: devices 0..n-1, or devs[0..n-1] when devs is not NULL.  The environment variable CONTACT_B200_DEVICES = all | n | "0,2,3"
+ * does the same for callers that cannot be changed (Fortran, python_intfc).  Returns the number of devices in use or a negative code. */
+int cb200_set_devices(int n, const int *devs);
+/* test hook: replace the stored solution (element division, tractions [3][npot] x, y, n) that the next case of a sequence
+ * starts from (I and P digits) */
+int cb200_set_state(int ire, int icp, int npot, const int *el, const double *ps);
+/* dif, difid of the convergence test of the outer (Panagiotopoulos) loop, m_scontc.f90:510-513, one pair per outer iteration
+ * of the last cntc_calculate (at most 16); returns their number */
+int cb200_get_outer_history(int ire, int icp, int lenarr, double *dif, double *difid);
 
 /* wall-clock split (s) of the last cntc_calculate / cntc_calculate_batch call: out[0] host set-up of the cases, [1] coefficient
  * transforms (cached per grid and material), [2] device allocation + uploads, [3] solver kernel(s), [4] output products +
@@ -177,6 +188,9 @@ long cb200_num_launches(void);
 /* cycle counters of CTA 0 since the last reset: out[0] fused products, [1] cycles inside them, [2] cycles of
  * k_snorm_batch (development aid for the roofline analysis) */
 int cb200_conv_prof(unsigned long long *out, int reset);
+/* work accounting over all CTAs since the last reset: out[0] products, out[1] nominal flops of those products at the transform
+ * size each one used (contact-box level), out[2] algorithmic bytes (17 per box element), out[3] Gauss-Seidel row-sum units */
+int cb200_work_counters(unsigned long long *out, int reset);
 /* all 32 cycle counters of CTA 0 (slots 4..31: sections of the solver kernels); development aid */
 int cb200_solver_prof(unsigned long long *out, int reset);
 /* cycle counters of the SteadyGS element step summed over all CTAs since the last reset: out[0] element steps,

@@ -495,6 +495,7 @@ int co_contac(co_case *c)
         for (int i = 0; i < npot; i++) {
             if (igs.el[i] <= CO_EXTER) { ps[i] = 0.0; ps[npot + i] = 0.0; ps[2L * npot + i] = 0.0; } else ncon++;
         }
+        if (itout <= 16) { c->pan_dif[itout - 1] = 0.0; c->pan_difid[itout - 1] = difid; }
         if (c->tang == 0 || ncon <= 0) dif = 0.0;
         else {
             int it = stang(cx, c, npot, &cs, &cv, &csv, &ms, hs, pv, x, &igs, ps, ss, dxdy, muscal, fntrue, dq, sens, &itgs);
@@ -506,6 +507,7 @@ int co_contac(co_case *c)
             dif = sqrt(s1 / (cnt > 1 ? cnt : 1));
             difid = 5.0 * c->eps * sqrt(s2 / (cnt > 1 ? cnt : 1));
             memcpy(po1, ps, sizeof(double) * 3 * npot);
+            if (itout <= 16) { c->pan_dif[itout - 1] = dif; c->pan_difid[itout - 1] = difid; }
         }
     }
     /* soutpt forces (m_soutpt.f90:424-436) */

@@ -188,6 +188,7 @@ typedef struct {
     int    itout;                       /* out: outer (Panagiotopoulos) iterations */
     double gd[8];                       /* G = 5: fdecay, betath, kdowfb, d_ifc, d_lin, d_cns, d_slp, pow_s (as in the .inp record) */
     int    gd_fallback;                 /* out: GDsteady stagnated, SteadyGS was used (m_solvpt.f90:474-484) */
+    double pan_dif[16], pan_difid[16];  /* out: dif / difid of the convergence test of panprc (m_scontc.f90:510-513), per outer iteration */
 } co_case;
 /* parameters of GDsteady after solv_input (m_sinput.f90:649-680) */
 typedef struct { int gd_meth, kdown, kdowfb; double fdecay, betath, d_ifc, d_lin, d_cns, d_slp, pow_s; } co_gdparams;

@@ -267,7 +267,8 @@ class Case(C.Structure):
                 ("iestim", C.c_int), ("el_in", c_int_p), ("ps_in", c_dbl_p), ("pv_in", c_dbl_p),
                 ("ipotcn", C.c_int), ("hz_a1", C.c_double), ("hz_b1", C.c_double), ("hz_aa", C.c_double),
                 ("hz_bb", C.c_double), ("hz_scale", C.c_double), ("itout", C.c_int),
-                ("gd", C.c_double * 8), ("gd_fallback", C.c_int)]
+                ("gd", C.c_double * 8), ("gd_fallback", C.c_int),
+                ("pan_dif", C.c_double * 16), ("pan_difid", C.c_double * 16)]
 
 
 def contac(g, gg, poiss, tang=0, norm=0, force3=0, pen=0.0, fn=0.0, cksi=0.0, ceta=0.0, cphi=0.0, fxrel=0.0, fyrel=0.0,
@@ -311,4 +312,5 @@ def contac(g, gg, poiss, tang=0, norm=0, force3=0, pen=0.0, fn=0.0, cksi=0.0, ce
                 grid=dict(mx=c.mx, my=c.my, xl=c.xl, yl=c.yl, dx=c.dx, dy=c.dy), hz=dict(a1=c.hz_a1, b1=c.hz_b1, aa=c.hz_aa, bb=c.hz_bb),
                 itnorm=c.itnorm, ittang=c.ittang, itout=c.itout, itcg_norm=c.itcg_norm, itgs_tang=c.itgs_tang,
                 nr_itcg=list(c.nr_itcg[:n]), nr_cksi=list(c.nr_cksi[:n]), nr_ceta=list(c.nr_ceta[:n]), nr_fx=list(c.nr_fx[:n]),
-                nr_fy=list(c.nr_fy[:n]), n_prod=c.n_prod, gd_fallback=c.gd_fallback)
+                nr_fy=list(c.nr_fy[:n]), n_prod=c.n_prod, gd_fallback=c.gd_fallback,
+                pan_dif=list(c.pan_dif[:min(16, c.itout)]), pan_difid=list(c.pan_difid[:min(16, c.itout)]))

@@ -43,3 +43,65 @@ def microbench_p(mx, my, ncase, seed=7):
     p = np.zeros((ncase, 3, mx * my))
     p[:] = rng.standard_normal((ncase, 3, mx * my)) * el
     return p, np.tile(el, (ncase, 1))
+
+
+# ---- reference input files as committed, parsed sequences (tests/golden/*_sequence.json, made by make_fixtures.py) ----
+def sequence(name):
+    import json, os
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "%s_sequence.json" % name)))
+
+
+def inp_text_from_cases(name):
+    """The GPU box has no /root/reference: rebuild an equivalent .inp text from the committed parsed cases."""
+    d = sequence(name)
+    out = []
+    for c in d["cases"]:
+        out.append(" 3 MODULE")
+        out.append(" %d%d%d%d%d%d" % (c["P"], c["B"], c["T"], c["N"], c["F"], c["S"]))
+        out.append(" %d%d%d%d%d%d%d" % (c["V"], c["L"], c["D"], c["C"], c["M"], c["Z"], c["E"]))
+        out.append(" %d%d%d%d%d%d%d%d" % (0, c["H"], c["G"], c["I"], c["A"], c["O"], c["W"], c["R"]))      # X = 0: no debug record
+        if "solver" in c:
+            s = c["solver"]
+            out.append(" %d %d %d %d %r" % (s["maxgs"], s["maxin"], s["maxnr"], s["maxout"], s["eps"]))
+            if c["G"] in (2, 3):
+                out.append(" %r %r %d %r" % (s["omegah"], s["omegas"], s["inislp"], s["omgslp"]))
+            elif c["G"] == 4:
+                out.append(" %d %r" % (s["inislp"], s["omgslp"]))
+            elif c["G"] == 5:                                   # FDECAY BETATH KDOWFB D_IFC D_LIN D_CNS D_SLP POW_S
+                gd = s["gdsteady"]
+                out.append(" %r %r %d %r %r %r %r %r" % (gd[0], gd[1], int(gd[2]), gd[3], gd[4], gd[5], gd[6], gd[7]))
+        out.append(" " + " ".join(repr(v) for v in c["kin"]))
+        if "fric" in c:
+            out.append(" %r %r" % tuple(c["fric"]))
+        if "roll" in c:
+            out.append(" %r %r %r" % (c["roll"]["chi"], c["roll"]["dq"], c["roll"]["veloc"]))
+        if "mater" in c:
+            out.append(" %r %r %r %r" % (c["mater"]["poiss"][0], c["mater"]["poiss"][1], c["mater"]["gg"][0], c["mater"]["gg"][1]))
+        if "potcon" in c:
+            p = c["potcon"]
+            out.append(" %d" % p["ipotcn"])
+            if p["ipotcn"] < 0:
+                out.append(" %d %d %r %r %r" % (p["mx"], p["my"], p["p1"], p["p2"], p["scale"]))
+            else:
+                out.append(" %d %d " % (p["mx"], p["my"]) + " ".join(repr(v) for v in p["prm"]))
+        if "geom" in c:
+            out.append(" %d %d" % (c["geom"]["ibase"], c["geom"]["iplan"]))
+            prm = c["geom"]["prm"]
+            if c["geom"]["ibase"] == 2:                         # NN XM RM Y1 DY1, then the NN profile heights
+                out.append(" %d %r %r %r %r" % (int(prm[0]), prm[1], prm[2], prm[3], prm[4]))
+                prm = prm[5:]
+            out.append(" " + " ".join(repr(v) for v in prm))
+        if c["S"] >= 2:
+            out.append(" 0 0")
+        if c["S"] >= 3:
+            for b in c["subs"]:
+                out.append(" %d" % b["isubs"])
+                if b["isubs"] in (2, 6):
+                    out.append(" %d %d %d" % tuple(b["ix"])); out.append(" %d %d %d" % tuple(b["iy"]))
+                if b["isubs"] <= 3:
+                    out.append(" %d %r %r" % tuple(b["zparam"]))
+                else:
+                    out.append(" %d" % len(b["z"])); out.append(" " + " ".join(repr(v) for v in b["z"]))
+            out.append(" 0")
+    out.append(" 0 MODULE")
+    return "\n".join(out) + "\n", d

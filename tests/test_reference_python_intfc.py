@@ -102,7 +102,7 @@ def test_unmodified_python_intfc_solves_cattaneo(tmp_path):
     el = cntc.getelementdivision(ire, icp)
     pen = cntc.getpenetration(ire, icp)
     pmax = cntc.getmaximumpressure(ire, icp)
-    carea, harea, sarea = cntc.getcontactpatchareas(ire, icp)
+    carea, harea, sarea, parea = cntc.getcontactpatchareas(ire, icp)
     fn, fx, fy, mz = cntc.getcontactforces(ire, icp)
     un, ux, uy = cntc.getdisplacements(ire, icp)
     print("RESULT " + json.dumps(dict(pn=pn.ravel().tolist(), el=np.asarray(el).ravel().astype(int).tolist(), pen=float(pen),
