@@ -1,6 +1,7 @@
 // api_lowlevel.cuh -- cb200_* entry points: kernel-level C-ABI (plain pointers and sizes).
 #pragma once
 #include "engine.cuh"
+#include "aijpj.cuh"
 
 namespace cb200 {
 
@@ -394,6 +395,41 @@ int cb200_vecaijpj(int handle, int set, int ncase, int iigs, int ikarg, int jkar
     if (!rc) { cudaError_t e = cudaMemcpy(u, d_u, sizeof(double) * n3, cudaMemcpyDeviceToHost); if (e != cudaSuccess) { last_error() = cudaGetErrorString(e); rc = -99; } }
     cudaFree(d_p); cudaFree(d_u); if (d_el) cudaFree(d_el);
     return rc;
+}
+
+// gf3_AijPj (m_aijpj.f90:99-254) for npts elements of one case: out[k] = displacement in direction ik of element ii[k] (0-based)
+// due to the tractions p [3][npot] in the directions jkarg (1..3, -2 tangential, -3 all), with the coefficient set `set`;
+// the n-t blocks are skipped when the materials are similar (nt_cpl false), as in the reference (:121-141).  Host arrays.
+int cb200_aijpj(int handle, int set, int ik, int jkarg, int npts, const int *ii, const double *p, const int *el, double *out)
+{
+    CoefSet *cs = set_from_handle(handle);
+    if (!cs) return -99;
+    if (set < 0 || set > 3 || !cs->d_cf[set]) { last_error() = "coefficient set not available"; return -99; }
+    if (ik < 1 || ik > 3) { last_error() = "invalid direction ik"; return -39; }
+    if (npts < 1) return 0;
+    int jk0, jk1;
+    dir_range(jkarg, jk0, jk1);
+    if (!cs->nt_cpl) {
+        if (jkarg == -3) { if (ik <= 2) jk1 = 2; else jk0 = 3; }
+        else if (jkarg == -2) { if (ik == 3) jk1 = 0; }
+        else if (jk0 <= jk1) { if (ik <= 2) jk1 = std::min(2, jk1); else jk0 = 3; }
+    }
+    const int mx = cs->mx, my = cs->my, npot = mx * my;
+    for (int k = 0; k < npts; k++) if (ii[k] < 0 || ii[k] >= npot) { last_error() = "cb200_aijpj: element index out of range"; return -39; }
+    double *d_p = nullptr, *d_out = nullptr; int *d_el = nullptr, *d_ii = nullptr;
+    CB_CUDA(cudaMalloc(&d_p, sizeof(double) * 3 * npot)); CB_CUDA(cudaMalloc(&d_out, sizeof(double) * npts));
+    CB_CUDA(cudaMalloc(&d_el, sizeof(int) * npot)); CB_CUDA(cudaMalloc(&d_ii, sizeof(int) * npts));
+    cudaMemcpy(d_p, p, sizeof(double) * 3 * npot, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_el, el, sizeof(int) * npot, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_ii, ii, sizeof(int) * npts, cudaMemcpyHostToDevice);
+    const int blocks = std::min(npts, 8 * std::max(1, engine().num_sms));
+    k_aijpj<<<blocks, 256, sizeof(double) * 3 * my>>>(mx, my, cs->d_cf[set], cs->ga_inv, ik, jk0, jk1, d_p, d_el, d_ii, npts, d_out);
+    engine().launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, sizeof(double) * npts, cudaMemcpyDeviceToHost);
+    cudaFree(d_p); cudaFree(d_out); cudaFree(d_el); cudaFree(d_ii);
+    if (e != cudaSuccess) { last_error() = std::string("k_aijpj: ") + cudaGetErrorString(e); return -99; }
+    return 0;
 }
 
 int cb200_snorm_batch_dev(int handle, int ncase, int ic_norm, int maxgs, int maxin, double eps, const double *d_hs,

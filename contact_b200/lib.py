@@ -102,6 +102,7 @@ PROTOTYPES = {
     "cb200_coefset_get_block": (I, [I, I, I, I, dp]),
     "cb200_coefset_plan": (I, [I, ip]),
     "cb200_vecaijpj": (I, [I, I, I, I, I, I, dp, ip, dp]),
+    "cb200_aijpj": (I, [I, I, I, I, I, ip, dp, ip, dp]),
     "cb200_vecaijpj_dev": (I, [I, I, I, I, I, I, V, V, V, V]),
     "cb200_snorm_batch_dev": (I, [I, I, I, I, I, D, V, V, V, V, V, V]),
     "cb200_eldiv0": (I, [I, I, D, D, D, D, D, D, I, dp, I, D, D, dp, ip, dp]),

@@ -129,6 +129,16 @@ class CoefSet:
                                              u.ctypes.data_as(C.POINTER(C.c_double))))
         return u
 
+    def aijpj(self, ii, ik, p, el, jkarg=-3, set_=SET_CS):
+        """gf3_AijPj: direct row sums for the 0-based elements ii of one case; p (3, npot), el (npot,). Returns (len(ii),)."""
+        ii = np.ascontiguousarray(ii, dtype=np.int32); p = np.ascontiguousarray(p, dtype=np.float64)
+        el = np.ascontiguousarray(el, dtype=np.int32)
+        out = np.zeros(ii.size)
+        _check(load_library().cb200_aijpj(self.h, set_, ik, jkarg, ii.size, ii.ctypes.data_as(C.POINTER(C.c_int)),
+                                          p.ctypes.data_as(C.POINTER(C.c_double)), el.ctypes.data_as(C.POINTER(C.c_int)),
+                                          out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
     def vecaijpj_dev(self, d_p, d_el, d_u, iigs=ALLELM, ikarg=3, jkarg=3, set_=SET_CS, stream=None):
         """DEVICE buffers (torch CUDA tensors: d_p, d_u float64 (ncase,3,npot); d_el int32 (ncase,npot) or None)."""
         ncase = d_p.shape[0]

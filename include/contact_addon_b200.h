@@ -219,6 +219,10 @@ int cb200_coefset_plan(int handle, int *out);
 /* VecAijPj (m_aijpj.f90:258-451) for ncase independent right-hand sides sharing one coefficient set.
  * p, u: [ncase][3][npot] (direction-major per case, x fastest); el: [ncase][npot] or NULL;
  * iigs -9 (AllElm) / -8 (AllInt); ikarg, jkarg: 1..3, -2 (tangential), -3 (all).  HOST buffers. */
+/* gf3_AijPj (m_aijpj.f90:99-254), the direct row sum: out[k] = displacement in direction ik (1..3) of element ii[k] (0-based) due to
+ * the tractions p [3][npot] in the directions jkarg (1..3, -2 = tangential, -3 = all) over the column range of the element division
+ * el [npot] (contact elements plus one neighbour per row), times 1/G.  Host arrays; npts elements of one case per call. */
+int cb200_aijpj(int handle, int set, int ik, int jkarg, int npts, const int *ii, const double *p, const int *el, double *out);
 int cb200_vecaijpj(int handle, int set, int ncase, int iigs, int ikarg, int jkarg, const double *p, const int *el,
                    double *u);
 /* same with DEVICE buffers, asynchronous on `stream` (a cudaStream_t passed as void*) */
