@@ -282,6 +282,36 @@ def gdsteady_leg(cb):
     return out
 
 
+def steadygs_large_leg(cb, with_4c=False):
+    """perfc_test/tang_problm_2c (143x161) and, on request, tang_problm_4c (287x323) with the default solver (T=3, G=0: SteadyGS) on
+    the whole-GPU path: the direct form of the sweep (one O(ncon) row sum per element step, CTA 0; golden ItGS 90 / 151, 97 s /
+    2210 s on the 2016 host, perfc_test/get_times.ref_out:26-27)."""
+    out = {}
+    for name, (mx, my, dx) in (("tang_problm_2c", (143, 161, 0.05)), ("tang_problm_4c", (287, 323, 0.025)))[:2 if with_4c else 1]:
+        g = mbench_grid(mx, my, dx)
+        ire = 902
+        cb.cntc_initialize(ire, 3)
+        cb.cntc_setflags(ire, 1, [cb.CNTC["ic_tang"], cb.CNTC["ic_force"], cb.CNTC["ic_iestim"]], [3, 0, 0])
+        cb.cntc_setsolverflags(ire, 1, 0, [1000, 100, 30, 1], [1e-7])
+        cb.cntc_setmaterialparameters(ire, 1, 0, [0.28, 0.28, 82000.0, 82000.0])
+        cb.cntc_setfrictionmethod(ire, 1, 0, [0.3, 0.3])
+        cb.cntc_setpotcontact(ire, 1, 1, [g["mx"], g["my"], g["xl"], g["yl"], g["dx"], g["dy"]])
+        cb.cntc_setundeformeddistc(ire, 1, 2, g["prmudf"])
+        cb.cntc_setpenetration(ire, 1, g["pen"])
+        cb.cntc_setrollingstepsize(ire, 1, 0.0, dx)
+        cb.cntc_setcreepages(ire, 1, 0.0005, 0.0, 0.0003)
+        t0 = time.perf_counter()
+        ierr = cb.cntc_calculate(ire, 1)
+        wall = time.perf_counter() - t0
+        its = cb.lowlevel.get_iterations(ire, 1)
+        el = cb.cntc_getelementdivision(ire, 1).ravel()
+        out[name] = {"ierror": int(ierr), "wall_s": wall, "itgs": its["itgs"], "ncon": int((el >= 1).sum()), "nslip": int((el == 2).sum()),
+                     "golden": {"tang_problm_2c": "nslp 7735, ItGS 90, 97 s (2016 host); oracle today: ItGS 91, 61 s on one core here",
+                                "tang_problm_4c": "nslp 30181, ItGS 151, 2210 s (2016 host)"}[name]}
+        cb.cntc_finalize(ire)
+    return out
+
+
 def large_grid_leg(cb, torch):
     """575x647 grid of perfc_test/norm_problm_8p.inp / tang_problm_8c.inp: stand-alone 1x1 products (three grid-wide
     phases over the L2-resident spectrum) and the whole NORM solve in one cooperative launch."""
@@ -539,6 +569,7 @@ def run_gpu(args):
     large = large_grid_leg(cb, torch) if (rank == 0 and not args.skip_extra) else None
     sp71 = spence71_leg(cb) if (rank == 0 and not args.skip_extra) else None
     gdl = gdsteady_leg(cb) if (rank == 0 and not args.skip_extra) else None
+    gsl = steadygs_large_leg(cb, args.gs_4c) if (rank == 0 and not args.skip_extra) else None
 
     roll_s = roll["s"] if roll else 0.0
     rollgd_s = roll_gd["s"] if roll_gd else 0.0
@@ -644,6 +675,8 @@ def run_gpu(args):
             out["spence71_inp"] = sp71
         if gdl:
             out["gdsteady_large"] = gdl
+        if gsl:
+            out["steadygs_large"] = gsl
         if args.cpu_seconds > 0:
             out["cpu_baseline"] = cpu_baseline(args.cpu_seconds, threads=1)
         print(json.dumps(out))
@@ -802,6 +835,7 @@ def main():
     ap.add_argument("--no-sweep4096", dest="sweep4096", action="store_false",
                     help="skip BASELINE config 5 at full size (4096 rolling cases sharded over the ranks, ~5 s on one GPU)")
     ap.add_argument("--skip-extra", action="store_true", help="skip the rolling-sweep and 575x647 legs")
+    ap.add_argument("--gs-4c", action="store_true", help="steadygs_large leg: also tang_problm_4c with G=0 (minutes)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -46,7 +46,9 @@ def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     digest = _digest()                      # of the sources as they are when the compiler starts
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda", "--split-compile", "0",
+    # (no --split-compile: it halves the build time but the split ptxas units cost 20 % on k_snorm_batch -- 47.2 k against 58.4 k
+    #  solves/s on the same box, gpurun_out/ab_split.log -- through spills in the warp-resident product)
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
            "-Xcompiler", "-fPIC", "-shared", "-o", SO, os.path.join(CSRC, "contact_addon_b200.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas")

@@ -63,6 +63,7 @@ struct Problem {
     // results
     int ncase = 0, itnorm = 0, ittang = 0, itcg = 0, ncon = 0, nadh = 0, nslip = 0, status = 0, itout = 0;
     double pan_dif[16] = { 0 }, pan_difid[16] = { 0 };
+    double mxtrue = 0, mytrue = 0, elen = 0, frpow = 0;      // soutpt: moments about x and y, elastic energy, frictional power
     std::vector<int> el;
     std::vector<double> ps, us, hs, ss;  // [3][npot]
     std::vector<double> pv;              // [3][npot] tractions of the previous time instance (set_prev_data)
@@ -453,7 +454,6 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
         int rc = get_coefset(p.mx, p.my, p.dx, p.dy, p.mat, p.tang >= 2 ? 1 : 0, chi_e, dq_e, 0, &cs, whole);
         if (rc) { ierr[k] = rc; continue; }
         // grids beyond one CTA's shared memory go to the whole-GPU path, which serves T = 0 and T = 1 (TangCG)
-        if (!cs->hp.fits && p.tang == 3 && p.gausei != 5) { last_error() = "grid too large for the single-CTA SteadyGS solver (the whole-GPU path serves T=0 and T=1)"; ierr[k] = CNTC_err_discr; continue; }
         groups[cs].push_back(k);
     }
     bt[0] = secs(t0, now());
@@ -603,10 +603,20 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
         } else {
             LargeCtx X;
             X.L = cs.lp; X.T = cs.d_T; X.gpart = cs.d_gpart; X.prof = nullptr;
+            // Gauss-Seidel cases (T = 3 with G != 5, G = 2, or the fall-back of a stagnating GDsteady): row arrays of the sweep in
+            // the phase buffers of the product when they fit in front of the reduction scratch, behind them otherwise
+            const size_t gs_fixed = steady_fixed_bytes(cs.mx, cs.my);
+            X.gs_off = gs_fixed + 1024 <= (size_t) cs.lp.smem_bytes ? 0 : cs.lp.smem_bytes;
+            const size_t lsmem = (size_t) cs.lp.smem_bytes + (X.gs_off ? gs_fixed : 0);
+            if (lsmem > (size_t) kSmemMax) {
+                last_error() = "grid rows too long for the shared-memory row arrays of the Gauss-Seidel sweep";
+                fail(CNTC_err_discr);
+                continue;
+            }
             for (int i = 0; i < n; i++) {                              // one cooperative whole-GPU launch per case
                 ContactCase *cp = d_cases + i;
                 void *args[] = { (void *) &X, (void *) &cp };
-                const cudaError_t ce = cudaLaunchCooperativeKernel((void *) k_lg_contac, dim3(engine().num_sms), dim3(CB_THREADS), args, (size_t) cs.lp.smem_bytes, 0);
+                const cudaError_t ce = cudaLaunchCooperativeKernel((void *) k_lg_contac, dim3(engine().num_sms), dim3(CB_THREADS), args, lsmem, 0);
                 if (ce != cudaSuccess && le == cudaSuccess) le = ce;
                 engine().launches++;
             }
@@ -670,6 +680,20 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
                     sx += p.ps[ii]; sy += p.ps[npot + ii]; mz += -p.ps[ii] * y + p.ps[npot + ii] * x;
                 }
                 const double dxdy = p.dx * p.dy;
+                {   // m_soutpt.f90:438-457: moments of the pressures about the x and y axes, elastic energy 0.5e-3 dxdy (us, ps) on C,
+                    // frictional power dxdy (ps, ss)_t / (1e3 dt) with the shift in the slip area only (:470-500)
+                    double smx = 0, smy = 0, se = 0, sf = 0;
+                    for (int iy = 0; iy < p.my; iy++) for (int ix = 0; ix < p.mx; ix++) {
+                        const int ii = iy * p.mx + ix;
+                        const double x = p.xc1 + ix * p.dx, y = p.yc1 + iy * p.dy, pn = p.ps[2 * (size_t) npot + ii];
+                        smx += pn * y; smy += pn * x;
+                        if (p.el[ii] >= 1) for (int k = 0; k < 3; k++) se += p.us[(size_t) k * npot + ii] * p.ps[(size_t) k * npot + ii];
+                        if (p.el[ii] == 2) sf += p.ps[ii] * p.ss[ii] + p.ps[npot + ii] * p.ss[npot + ii];
+                    }
+                    p.mxtrue = dxdy * smx; p.mytrue = -dxdy * smy; p.elen = 0.5 * 1e-3 * dxdy * se;
+                    const double dt = p.tang >= 2 ? (p.tang >= 2 && p.dq_eff > 0 ? p.dq_eff : p.dq) / std::max(1e-30, p.veloc) : p.dt;
+                    p.frpow = p.tang != 0 ? dxdy * sf / (1e3 * std::max(1e-30, dt)) : 0.0;
+                }
                 if (p.tang != 0) {                                       // m_soutpt.f90:424-450
                     if (p.force3 == 0) p.fxrel = dxdy * sx / (p.fntrue * muscal + 1e-20);
                     if (p.force3 <= 1) p.fyrel = dxdy * sy / (p.fntrue * muscal + 1e-20);
@@ -964,6 +988,31 @@ int cb200_set_state(int ire, int icp, int npot, const int *el, const double *ps)
     p->el.assign(el, el + npot);
     p->ps.assign(ps, ps + 3 * (size_t) npot);
     p->solved = true;
+    return 0;
+}
+
+// soutpt scalars that the reference writes to its .out file only (m_soutpt.f90:424-500): out = Fn, Fx, Fy, Mx, My, Mz, elastic
+// energy [J], frictional power [W], largest pressure, deformed distance is returned by cb200_get_deformed_distance
+int cb200_get_soutpt(int ire, int icp, int lenarr, double *out)
+{
+    int e; Problem *p = activate(ire, icp, &e);
+    if (!p) return e;
+    double pmax = 0.0;
+    const size_t npot = (size_t) p->mx * p->my;
+    if (p->ps.size() == 3 * npot) for (size_t i = 0; i < npot; i++) pmax = std::max(pmax, p->ps[2 * npot + i]);
+    const double v[9] = { p->fcntc[2], p->fcntc[0], p->fcntc[1], p->mxtrue, p->mytrue, p->mztrue, p->elen, p->frpow, pmax };
+    for (int k = 0; k < lenarr && k < 9; k++) out[k] = v[k];
+    return 0;
+}
+
+// deformed distance hs - pen + us_n of all elements (m_soutpt.f90:459-468; the reference stores it in ss(:,n))
+int cb200_get_deformed_distance(int ire, int icp, int lenarr, double *out)
+{
+    int e; Problem *p = activate(ire, icp, &e);
+    if (!p) return e;
+    const size_t npot = (size_t) p->mx * p->my;
+    if (p->hs.size() != 3 * npot || p->us.size() != 3 * npot) { last_error() = "no solution available (run cntc_calculate first)"; return CNTC_err_other; }
+    for (size_t i = 0; i < npot && (int) i < lenarr; i++) out[i] = p->hs[2 * npot + i] - p->pen + p->us[2 * npot + i];
     return 0;
 }
 

@@ -124,7 +124,6 @@ __device__ __noinline__ double conv2_box_dev(const ConvPlan &P, const Smem &sm, 
 {
     const int tid = threadIdx.x, warp = tid >> 5;
     const long long t_in = (tid == 0 && blockIdx.x == 0) ? clock64() : 0;
-    work_count(P, bw, bh);
     const Conv2Plan &c = P.c2;
     volatile int *hdr = conv_hdr(sm);
     if (hdr[0] != c.id) {                                       // uniform over the CTA
@@ -155,6 +154,7 @@ __device__ __noinline__ double conv2_box_dev(const ConvPlan &P, const Smem &sm, 
         const int nw = c.nslot;
         for (int w = 0; w < nw; w++) s_ += buf.ld(osum + (uint32_t) w).x;
     }
+    work_count(P, bw, bh);                                      // at the end: no register pressure on the passes above
     if (tid == 0 && blockIdx.x == 0) { g_conv_prof[0] += 1; g_conv_prof[1] += (unsigned long long) (clock64() - t_in); }
     return s_;
 }

@@ -181,6 +181,7 @@ struct LargeCtx {
     cd *T;
     double *gpart;         // [2][gridDim][8] partial sums of the grid reductions
     unsigned long long *prof;   // optional cycle counters
+    int gs_off;                 // byte offset of the Gauss-Seidel row arrays in the dynamic shared memory (stdygs_dev<1, true>)
 };
 
 __device__ void lg_conv(const LargeCtx &X, uint32_t a0, const double *p, const cd *chat, double *u, const int *el,
@@ -504,6 +505,7 @@ struct GridCtx {
     double *redp;
     cg::grid_group &grid;
     int &phase;
+    unsigned char *sraw;        // dynamic shared memory of this CTA
     static constexpr bool kBlock = false;
     __device__ __forceinline__ int n() const { return X.L.P.npot; }
     __device__ __forceinline__ const ConvPlan &plan() const { return X.L.P; }
@@ -537,7 +539,7 @@ k_lg_contac(LargeCtx X, ContactCase *cp)
     const uint32_t a0 = (uint32_t) __cvta_generic_to_shared(smem_raw);
     double *red = reinterpret_cast<double *>(smem_raw + X.L.smem_bytes - 1024);
     int phase = 0;
-    const GridCtx x = { X, a0, red, grid, phase };
+    const GridCtx x = { X, a0, red, grid, phase, smem_raw };
     panprc_dev(x, *cp);
 }
 

@@ -118,6 +118,9 @@ struct SteadyArgs {
     double *dp;             // [2][n] traction differences (global scratch)
     double *ug;             // [2][n] scratch for the FFT evaluation of U
     int *iel;               // [n] compact list of contact elements
+    int *isp;               // direct form: [my + 2] row offsets, then the list of all elements of the column ranges
+                            // [row1st - 1, rowlst + 1] (the reference's range of gf3_AijPj: the traction differences of SteadyGS do
+                            // not vanish at the exterior element in front of a contact run); room for my + 2 + n ints
     const cd *(*chatA)[3];  // transformed cs blocks
     const double *cf11, *cf12, *cf22;
     int cmx, cmy;
@@ -227,9 +230,17 @@ struct SteadyTab {
 // per-element solve, all 32 lanes keep the row's own displacement differences up to date and re-integrate the row
 // with a warp scan -- while the net change of the row is applied to the register-resident U of all other rows once
 // per row by the whole CTA.
-template <int KMAX>
+//
+// DIRECT = true: the form for contact areas that do not fit the register-resident U (more than 22 x 384 elements, or a grid on
+// the whole-GPU path).  No U is kept: before every element step the whole CTA evaluates the reference's row sum
+// U_i = (1/G) sum_j A(i - j) xp_j over the compact contact list (gf3_AijPj, m_aijpj.f90:99-254; the current row from shared
+// memory, the other rows from global memory / L2, coefficients from the spatial blocks in L2), then warp 0 performs the
+// element step exactly as in the register form.  No rank-1 updates, no FFT products, no coefficient table in shared
+// memory: O(ncon) work per element like the reference, any grid size.  `sbase`: shared memory for the row arrays
+// (steady_fixed_bytes), used instead of the plan's layout.
+template <int KMAX, bool DIRECT = false>
 __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const SteadyArgs &a, int *el, double *ps, double *ss,
-                          int ncon, int &itgs_out, double &err_out, int &nprod)
+                          int ncon, int &itgs_out, double &err_out, int &nprod, unsigned char *sbase = nullptr)
 {
     const int n = P.npot, mx = P.mx, my = P.my, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
     const unsigned full = 0xffffffffu;
@@ -251,6 +262,7 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
     const double facnel = (double) sqrtf(__fdiv_rn((float) n, (float) ncon));
 
     // U = A_tt xp on the contact area by four FFT products (fresh at every solver call)
+    if constexpr (!DIRECT)
     for (int ik = 0; ik < 2; ik++) {
         bool ladd = false;
         for (int jk = 0; jk < 2; jk++) {
@@ -262,8 +274,18 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
 
     // shared memory is ours now (S and W regions of the FFT layout)
     SteadySmem s;
-    steady_carve(P, reinterpret_cast<unsigned char *>(sm.S), a.sym, s);
-    conv_tables_invalidate(sm);                                     // the sweep arrays overwrite the product's window
+    if constexpr (DIRECT) {
+        if (sbase == nullptr) {                                     // one-CTA path: the place steady_carve would choose
+            sbase = reinterpret_cast<unsigned char *>(sm.S);
+            if (steady_fixed_bytes(P.mx, P.my) > (size_t) P.off_twx) sbase += P.smem_bytes;
+            conv_tables_invalidate(sm);
+        }
+        double *d = reinterpret_cast<double *>(sbase);
+        s.q = nullptr; s.r0 = d; s.row = d + 6 * mx; s.irow = reinterpret_cast<int *>(d + 6 * mx + 15 * mx + 8); s.mx = mx;
+    } else {
+        steady_carve(P, reinterpret_cast<unsigned char *>(sm.S), a.sym, s);
+        conv_tables_invalidate(sm);                                 // the sweep arrays overwrite the product's window
+    }
     if (s.q) {
         if (a.sym) {
             for (int i = tid; i < n; i += nt) {
@@ -301,6 +323,29 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
     }
     __syncthreads();
 
+    int nsp = 0;
+    if constexpr (DIRECT) {                                       // column ranges of the row sums (contact area is fixed in TANG)
+        int *spk = a.isp, *spl = a.isp + my + 2;
+        for (int iy = tid; iy < my; iy += nt) {
+            int first = mx, last = -1;
+            for (int ix = 0; ix < mx; ix++) if (el[iy * mx + ix] >= 1) { if (first == mx) first = ix; last = ix; }
+            spk[iy + 1] = last < 0 ? 0 : min(mx - 1, last + 1) - max(0, first - 1) + 1;
+        }
+        __syncthreads();
+        if (tid == 0) { spk[0] = 0; for (int iy = 0; iy < my; iy++) spk[iy + 1] += spk[iy]; }
+        __syncthreads();
+        for (int iy = tid; iy < my; iy += nt) {
+            const int cnt = spk[iy + 1] - spk[iy];
+            if (cnt > 0) {
+                int first = 0;
+                while (el[iy * mx + first] < 1) first++;
+                const int j0 = max(0, first - 1);
+                for (int q = 0; q < cnt; q++) spl[spk[iy] + q] = iy * mx + j0 + q;
+            }
+        }
+        __syncthreads();
+        nsp = spk[my];
+    }
     // registers: my contact elements k = tid + m nt
     double Ux[KMAX], Uy[KMAX];
     int ixy[KMAX];
@@ -308,7 +353,7 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
     for (int m = 0; m < KMAX; m++) {
         const int k = tid + m * nt;
         Ux[m] = 0.0; Uy[m] = 0.0; ixy[m] = -1;
-        if (k < ncon) {
+        if (!DIRECT && k < ncon) {
             const int ii = a.iel[k], iy = ii / mx;
             ixy[m] = (ii - iy * mx) | (iy << 16);
             Ux[m] = a.ug[ii]; Uy[m] = a.ug[n + ii];
@@ -316,6 +361,7 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
     }
     double q00, q01, q11;
     T.row0(0, q00, q01, q11);
+    const uint32_t mg_mx = div_magic((uint32_t) mx);
 
     int itgs = 0;
     double dif = 2.0, difid = 1.0, dif1 = 0.0;
@@ -371,8 +417,26 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
                 if (ixy[m] >= 0 && (ixy[m] >> 16) == iy) { s.urx(ixy[m] & 0xffff) = Ux[m]; s.ury(ixy[m] & 0xffff) = Uy[m]; }
             __syncthreads();
 
-            if (tid < 32) {                                    // ---- warp 0: the Gauss-Seidel steps of this row ----
+            if (DIRECT || tid < 32) {                          // ---- warp 0: the Gauss-Seidel steps of this row ----
                 for (int k = k0; k < k1; k++) {
+                    if constexpr (DIRECT) {                    // whole CTA: row sum of element k over the contact list
+                        const int ixd = s.cix(k - k0);
+                        double us[2] = { 0.0, 0.0 };
+                        const int *spl = a.isp + my + 2;
+                        for (int kk = tid; kk < nsp; kk += nt) {
+                            const int jj = spl[kk], jy = (int) fdiv((uint32_t) jj, mg_mx), jx = jj - jy * mx;
+                            const size_t o = (size_t) (iy - jy + a.cmy) * (2 * a.cmx) + (ixd - jx) + a.cmx;
+                            double qx, qy;
+                            if (jy == iy) { qx = convex ? s.psx(jx) : s.dpx(jx); qy = convex ? s.psy(jx) : s.dpy(jx); }
+                            else { qx = xp[jj]; qy = xp[n + jj]; }
+                            const double c12 = a.cf12[o];
+                            us[0] += a.cf11[o] * qx + c12 * qy; us[1] += c12 * qx + a.cf22[o] * qy;
+                        }
+                        block_sum<2>(us, red);
+                        if (tid == 0) { s.urx(ixd) = us[0] * a.ga_inv; s.ury(ixd) = us[1] * a.ga_inv; }
+                        __syncthreads();
+                    }
+                    if (!DIRECT || tid < 32) {
                     const unsigned long long ta = clock64();
                     const int ix = s.cix(k - k0);
                     int e = s.el(ix);
@@ -516,7 +580,7 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
                     const unsigned long long tc = clock64();
                     // in-row rank-1 updates: keep the displacement differences of this row current, accumulate the net
                     // change of the row for the other rows
-                    const int nch = s.ictl(0, my);
+                    const int nch = DIRECT ? 0 : s.ictl(0, my);
                     for (int c = 0; c < nch; c++) {
                         const int jx = s.chj(c);
                         const double ex = s.chx(c), ey = s.chy(c);
@@ -537,9 +601,12 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
                     }
                     __syncwarp();
                     if (lane == 0) { const unsigned long long td = clock64(); tp0++; tp1 += tb - ta; tp2 += tc - tb; tp3 += td - tc; tp5 += nch; }
+                    }
+                    if constexpr (DIRECT) __syncthreads();     // the row arrays changed by warp 0 feed the next row sum
                 }
                 // compact the net changes of this row for the update of the other rows
                 int cnt = 0;
+                if (!DIRECT)
                 for (int base = 0; base < mx; base += 32) {
                     const int jx = base + lane;
                     const double ex = jx < mx ? s.ddx(jx) : 0.0, ey = jx < mx ? s.ddy(jx) : 0.0;
@@ -548,14 +615,15 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
                     if (nz) { const int pos = cnt + __popc(mk & ((1u << lane) - 1u)); s.chj(pos) = jx; s.chx(pos) = ex; s.chy(pos) = ey; }
                     cnt += __popc(mk);
                 }
-                if (lane == 0) { s.ictl(1, my) = cnt; tp6 += cnt; }
+                if (!DIRECT && lane == 0) { s.ictl(1, my) = cnt; tp6 += cnt; }
             }
             __syncthreads();
 
             // ---- whole CTA: apply the net change of row iy to the elements of all other rows ----
             const unsigned long long te = clock64();
-            const int ncl = s.ictl(1, my);
-            if (s.q && a.sym) {                                // quadrant table in shared memory: the fast path
+            const int ncl = DIRECT ? 0 : s.ictl(1, my);
+            if (DIRECT) { }
+            else if (s.q && a.sym) {                                // quadrant table in shared memory: the fast path
 #pragma unroll
                 for (int m = 0; m < KMAX; m++) {
                     const int iym = ixy[m] >> 16, ixm = ixy[m] & 0xffff;

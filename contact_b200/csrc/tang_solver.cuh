@@ -50,6 +50,7 @@ struct ContactCase {
     double fx, fy, sens[2][2];
     int nadh, nslip;
     double pan_dif[16], pan_difid[16];  // dif / difid of panprc's convergence test per outer iteration (m_scontc.f90:510-513)
+    int gs_info, gs_it; double gs_err;  // result of a Gauss-Seidel solve by CTA 0 on the whole-GPU path, for the other CTAs
     int tstatus;                    // bit 0: the case needs a solver outside this path (ConvexGS / GDsteady)
 };
 
@@ -326,13 +327,13 @@ __device__ int solve_once_dev(const X &x, ContactCase &c, const double *wstot, d
         int lstagn = 0;
         it = gdsteady_dev(x, c, wstot, c.nrm.maxgs, c.nrm.eps, err, lstagn, nprod);
         if (lstagn) {                                                          // stagnation: SteadyGS takes over
-            if (x.leader()) { c.gd_fallback++; if (!X::kBlock) c.tstatus |= 1; }
+            if (x.leader()) c.gd_fallback++;
             x.sync();
-            if (X::kBlock) use_gs = true; else info = 3;
+            use_gs = true;
         }
     }
     if (use_gs) {                                                              // SteadyGS / ConvexGS
-        if constexpr (X::kBlock) {
+        {
         int nadh, nslip;
         count_el(x, c.nrm.el, n, nadh, nslip);
         const int ncon = nadh + nslip;
@@ -342,6 +343,7 @@ __device__ int solve_once_dev(const X &x, ContactCase &c, const double *wstot, d
         SteadyArgs a;
         a.ws = wstot; a.dp = c.twork + 3 * (size_t) n; a.ug = c.twork + 5 * (size_t) n;
         a.iel = reinterpret_cast<int *>(c.twork + 7 * (size_t) n);
+        a.isp = reinterpret_cast<int *>(c.twork + 8 * (size_t) n);          // (TangCG's vectors live here; it does not run beside a sweep)
         a.chatA = sv ? chat_sv : c.chatA;
         a.cf11 = sv ? c.cfv11 : c.cf11; a.cf12 = sv ? c.cfv12 : c.cf12; a.cf22 = sv ? c.cfv22 : c.cf22;
         a.cmx = c.nrm.cmx; a.cmy = c.nrm.cmy;
@@ -349,10 +351,26 @@ __device__ int solve_once_dev(const X &x, ContactCase &c, const double *wstot, d
         a.convex = convex ? 1 : 0; a.sym = sv ? 0 : 1;
         a.ledge = (sv && c.dq > c.dx) ? 1 : 0; a.facdt = c.twork;             // facdt of stang_dev
         a.cs11 = c.cf11; a.cs12 = c.cf12; a.cs22 = c.cf22; a.cs13 = c.cf13; a.cs23 = c.cf23; a.ub = a.ug;
-        if (ncon <= 6 * CB_THREADS) info = stdygs_dev<6>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
-        else if (ncon <= 12 * CB_THREADS) info = stdygs_dev<12>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
-        else if (ncon <= 22 * CB_THREADS) info = stdygs_dev<22>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
-        else { if (x.leader()) c.tstatus |= 1; info = 1; }       // more contact elements than the register-resident sweep holds: refused
+        if constexpr (X::kBlock) {
+            if (ncon <= 6 * CB_THREADS) info = stdygs_dev<6>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
+            else if (ncon <= 12 * CB_THREADS) info = stdygs_dev<12>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
+            else if (ncon <= 22 * CB_THREADS) info = stdygs_dev<22>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
+            else info = stdygs_dev<1, true>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);   // direct row sums
+        } else {
+            // whole-GPU path: the sweep is one sequential chain of element steps, each with an O(ncon) row sum -- CTA 0 runs it
+            // (direct form), the other CTAs wait at the grid barrier; the result reaches them through the case record
+            if (blockIdx.x == 0) {
+                Smem sm0;
+                sm0.S = nullptr; sm0.W = nullptr; sm0.twx = nullptr; sm0.twy = nullptr; sm0.posx = nullptr; sm0.red = x.red(); sm0.a0 = 0;
+                int it0 = 0; double err0 = 0.0;
+                const int inf0 = stdygs_dev<1, true>(x.plan(), sm0, a, c.nrm.el, c.ps, c.ss, ncon, it0, err0, nprod, x.sraw + x.X.gs_off);
+                if (threadIdx.x == 0) { c.gs_info = inf0; c.gs_it = it0; c.gs_err = err0; }
+            }
+            x.sync();
+            info = *reinterpret_cast<volatile int *>(&c.gs_info); it = *reinterpret_cast<volatile int *>(&c.gs_it);
+            err = *reinterpret_cast<volatile double *>(&c.gs_err);
+            x.sync();
+        }
         }
     } else if (c.solver_eff == 0)
         tangcg_dev(x, c, wstot, c.nrm.maxgs, c.nrm.eps, it, err, nprod);
@@ -469,8 +487,7 @@ __device__ int stang_dev(const X &x, ContactCase &c, double fntrue, int &itgs_to
         if (cnt[1] > 0.0 && (solver == 1 || solver == 3)) solver = 2;          // no exterior elements at the trailing edge
         // the Gauss-Seidel solvers exist on the one-CTA-per-case path only (ConvexGS with dq > dx: leading-edge equations
         // inside stdygs_dev)
-        bool refuse = ((solver == 1 || solver == 2) && !X::kBlock) ||
-                      (solver == 3 && c.gwork == nullptr);
+        bool refuse = (solver == 3 && c.gwork == nullptr);
         if (refuse) { if (x.leader()) c.tstatus |= 1; x.sync(); itgs_tot = 0; return -1; }
         double oh = c.omegah, os = c.omegas;
         if (c.gausei == 0 || c.gausei == 4 || c.gausei == 5) {

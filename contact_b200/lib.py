@@ -86,6 +86,8 @@ PROTOTYPES = {
     "cb200_get_iterations": (I, [I, I, ip, I, ip]),
     "cb200_get_outer_history": (I, [I, I, I, dp, dp]),
     "cb200_set_state": (I, [I, I, I, ip, dp]),
+    "cb200_get_soutpt": (I, [I, I, I, dp]),
+    "cb200_get_deformed_distance": (I, [I, I, I, dp]),
     "cb200_set_devices": (I, [I, ip]),
     "cb200_last_error": (C.c_char_p, []),
     "cb200_num_launches": (L, []),

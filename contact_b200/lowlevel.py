@@ -228,6 +228,19 @@ def set_devices(n, devs=None):
     return r
 
 
+def get_soutpt(ire, icp=1):
+    """soutpt scalars (m_soutpt.f90:424-500): dict fn, fx, fy, mx, my, mz, elen, frpow, pmax"""
+    o = (C.c_double * 9)()
+    _check(load_library().cb200_get_soutpt(ire, icp, 9, o))
+    return dict(zip(("fn", "fx", "fy", "mx", "my", "mz", "elen", "frpow", "pmax"), list(o)))
+
+
+def get_deformed_distance(ire, icp, npot):
+    o = np.zeros(npot)
+    _check(load_library().cb200_get_deformed_distance(ire, icp, npot, o.ctypes.data_as(C.POINTER(C.c_double))))
+    return o
+
+
 def get_outer_history(ire, icp=1):
     """(dif, difid) of panprc's convergence test per outer iteration of the last solve"""
     d = (C.c_double * 16)(); e = (C.c_double * 16)()

@@ -163,6 +163,11 @@ void cntc_calculate_batch(int *nre, int *ire, int *icp, int *ierror);
  * line-search trials (negated - 1 when a stagnating GDsteady fell back to SteadyGS, m_solvpt.f90:474-484); nr_itcg =
  * iterations per solver call (Newton-Raphson log) */
 int cb200_get_iterations(int ire, int icp, int *out, int lenarr, int *nr_itcg);
+/* soutpt results that the reference prints to the .out file only (m_soutpt.f90:424-500): out[0..8] = Fn, Fx, Fy, Mx, My, Mz,
+ * elastic energy, frictional power, maximum pressure (CONTACT units) */
+int cb200_get_soutpt(int ire, int icp, int lenarr, double *out);
+/* deformed distance hs - pen + un of all elements (m_soutpt.f90:459-468) */
+int cb200_get_deformed_distance(int ire, int icp, int lenarr, double *out);
 /* Devices that cntc_calculate_batch spreads a batch over (the batched case scheduler across the GPUs of one box: contiguous shards
  * of the case list, one host thread per device, no inter-GPU traffic).  n <= 1: the calling thread's current device only (default);
  * n > 1: devices 0..n-1, or devs[0..n-1] when devs is not NULL.  The environment variable CONTACT_B200_DEVICES = all | n | "0,2,3"

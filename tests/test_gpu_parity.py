@@ -818,6 +818,48 @@ def test_gdsteady_batch_sweep_agrees_with_steadygs(cb, mbench):
         assert np.abs(f5[:3] - f0[:3]).max() < 2e-5 * np.abs(f0[:3]).max()
 
 
+def test_soutpt_scalars_and_deformed_distance(cb, O):
+    """soutpt (m_soutpt.f90:424-500) beyond the forces: moments about x and y, elastic energy, frictional power and the deformed
+    distance hs - pen + un of a steady-rolling case, against the same formulas evaluated on the ORACLE's fields (tractions, slip)
+    and displacements from the oracle's influence product."""
+    g = dict(mx=34, my=27, xl=-3.4, yl=-2.7, dx=0.2, dy=0.2, ibase=1, prmudf=[0.004, 0.0, 0.006, 0.0, 0.0, 0.0])
+    gg, poiss = (82000.0, 40000.0), (0.28, 0.35)                      # dissimilar: all nine blocks contribute to us
+    ire, icp = 93, 1
+    _setup_rolling(cb, ire, g, gg, poiss, fn=9.0e3, fstat=0.25, maxgs=500, maxin=50, maxnr=30, maxout=5, eps=1e-6)
+    cb.cntc_setreferencevelocity(ire, icp, 30000.0)
+    cb.cntc_setrollingstepsize(ire, icp, 0.0, 0.2)
+    cb.cntc_setcreepages(ire, icp, 0.0012, 0.0004, 0.0002)
+    assert cb.cntc_calculate(ire, icp) == 0, cb.lib.last_error()
+    ref = O.contac(g, gg, poiss, tang=3, norm=1, force3=0, fn=9.0e3, cksi=0.0012, ceta=0.0004, cphi=0.0002, fstat=0.25, fkin=0.25,
+                   maxgs=500, maxin=50, maxnr=30, maxout=5, eps=1e-6, chi=0.0, dq=0.2)
+    assert ref["ierror"] == 0
+    npot = g["mx"] * g["my"]
+    el = cb.cntc_getelementdivision(ire, icp).ravel()
+    assert np.array_equal(el, ref["el"])
+    X, Y = cases.grid_xy(g["mx"], g["my"], g["xl"], g["yl"], g["dx"], g["dy"])
+    dxdy = g["dx"] * g["dy"]
+    m = O.mater(gg=gg, poiss=poiss)
+    cs, cv, csv, ms = O.sgencr(m, g["mx"], g["my"], g["dx"], g["dy"], is_roll=True, chi=0.0, dq=0.2)
+    igs = O.EldivBuf(g["mx"], g["my"], ref["el"])
+    us = np.zeros((3, npot))
+    O.vecaijpj(O.Ctx(fullbox=True), igs, -8, us, -3, np.ascontiguousarray(ref["ps"]), -3, cs)
+    O.inflcf_free(cs, cv, csv, ms)
+    con, slip = ref["el"] >= 1, ref["el"] == 2
+    want = dict(mx=dxdy * (ref["ps"][2] * Y).sum(), my=-dxdy * (ref["ps"][2] * X).sum(),
+                mz=dxdy * (-(ref["ps"][0] * Y).sum() + (ref["ps"][1] * X).sum()),
+                elen=0.5e-3 * dxdy * (us[:, con] * ref["ps"][:, con]).sum(),
+                frpow=dxdy * (ref["ps"][0][slip] * ref["ss"][0][slip] + ref["ps"][1][slip] * ref["ss"][1][slip]).sum() / (1e3 * 0.2 / 30000.0),
+                pmax=ref["ps"][2].max(), fn=9.0e3)
+    got = cb.lowlevel.get_soutpt(ire, icp)
+    for k, v in want.items():
+        assert abs(got[k] - v) <= 2e-6 * max(abs(v), 1e-3 * abs(want["fn"])), (k, got[k], v)
+    h = cases.quadratic_h(g)
+    hd = cb.lowlevel.get_deformed_distance(ire, icp, npot)
+    assert np.abs(hd[con] - (h - ref["pen"] + us[2])[con]).max() < 1e-6 * abs(ref["pen"])
+    assert np.abs(hd[con]).max() < 1e-4 * abs(ref["pen"])                 # in contact the deformed distance vanishes
+    cb.cntc_finalize(ire)
+
+
 @pytest.mark.parametrize("gausei", [0, 5])
 def test_sweep4096_draws_against_oracle(cb, O, mbench, gausei):
     """BASELINE config 5 (sweep-4096): the first 12 draws of the seeded sweep -- mbench 71x81, PEN (1 + 0.1 u),
@@ -862,7 +904,7 @@ def test_sweep4096_draws_against_oracle(cb, O, mbench, gausei):
 def test_gdsteady_stagnation_falls_back_to_steadygs(cb, O, mbench):
     """tang_solver (m_solvpt.f90:459-484): when GDsteady reports stagnation -- here forced by MAXGS = 40 on tang_problm_1c --
     SteadyGS takes over from GDsteady's tractions.  One-CTA path: same switch, same sweeps and element division as the
-    oracle.  Whole-GPU path (143x163): the Gauss-Seidel solvers do not exist there, the case is refused with a message."""
+    oracle."""
     g = dict(mx=71, my=81, xl=-3.55, yl=-6.15, dx=0.1, dy=0.1, ibase=2, prmudf=np.array(mbench["prmudf"]))
     ire, icp = 66, 1
     _setup_rolling(cb, ire, g, cases.STEEL["gg"], cases.STEEL["poiss"], pen=mbench["pen"])
@@ -883,12 +925,85 @@ def test_gdsteady_stagnation_falls_back_to_steadygs(cb, O, mbench):
     s = np.abs(ref["ps"][:2]).max()
     assert np.abs(px.ravel() - ref["ps"][0]).max() < 1e-7 * s and np.abs(py.ravel() - ref["ps"][1]).max() < 1e-7 * s
     cb.cntc_finalize(ire)
-    g2 = dict(mx=143, my=163, xl=-3.55, yl=-6.15, dx=0.05, dy=0.05, ibase=2, prmudf=np.array(mbench["prmudf"]))
-    _setup_rolling(cb, ire, g2, cases.STEEL["gg"], cases.STEEL["poiss"], pen=mbench["pen"])
-    _gd_flags(cb, ire, icp, GD_8C, maxgs=10)
+    cb.cntc_finalize(ire)
+
+
+def test_steadygs_direct_form_beyond_register_capacity(cb, O):
+    """100x100 grid (fits one CTA) with a full-width contact of 8700 elements: more than the 22 x 384 elements the register-
+    resident sweep holds, so the one-CTA path uses the direct form of the sweep (row sums per element step).  Six sweeps of
+    SteadyGS against the oracle: element division bit-exact, tractions to 1e-9 -- a strict check of the sweep itself."""
+    g = dict(mx=100, my=100, xl=-5.0, yl=-5.0, dx=0.1, dy=0.1, ibase=1, prmudf=[0.0011, 0.0, 0.00001, 0.0, 0.0, 0.0])
+    ire, icp = 68, 1
+    _setup_rolling(cb, ire, g, cases.STEEL["gg"], cases.STEEL["poiss"], pen=0.050, maxgs=6, eps=1e-6)
+    cb.cntc_setrollingstepsize(ire, icp, 0.0, 0.1)
+    cb.cntc_setcreepages(ire, icp, 0.0008, 0.0002, 0.0001)
+    ierr = cb.cntc_calculate(ire, icp)
+    ref = O.contac(g, cases.STEEL["gg"], cases.STEEL["poiss"], tang=3, norm=0, force3=0, pen=0.050, cksi=0.0008, ceta=0.0002,
+                   cphi=0.0001, fstat=0.3, fkin=0.3, maxgs=6, maxin=100, maxnr=30, maxout=1, eps=1e-6, chi=0.0, dq=0.1, gausei=0)
+    assert (ierr < 0) == (ref["ierror"] < 0), (ierr, ref["ierror"], cb.lib.last_error())
+    its = cb.lowlevel.get_iterations(ire, icp)
+    el = cb.cntc_getelementdivision(ire, icp).ravel()
+    assert int((ref["el"] >= 1).sum()) == 8700 and its["itgs"] == ref["itgs_tang"] == 6
+    assert np.array_equal(el, ref["el"]), int((el != ref["el"]).sum())
+    pn, px, py = cb.cntc_gettractions(ire, icp)
+    s_ = np.abs(ref["ps"]).max()
+    assert max(np.abs(px.ravel() - ref["ps"][0]).max(), np.abs(py.ravel() - ref["ps"][1]).max()) < 1e-9 * s_
+    cb.cntc_finalize(ire)
+
+
+def test_steadygs_whole_gpu_tang_problm_2c(cb, mbench):
+    """perfc_test/tang_problm_2c with the default solver (T=3, G=0: SteadyGS) on the 143x161 grid, which does not fit one CTA:
+    whole-GPU path with the direct form of the sweep (stdygs_dev<1, true>: row sums gf3_AijPj over the reference's column ranges
+    per element step, m_solvpt.f90:2825-3254).  Golden perfc_test/get_times.ref_out:26 (2016 revision): nslp = 7735, ItGS = 90.
+    The oracle (current source, 61 s on a core: committed fixture tests/golden/steadygs_2c.json) needs 91 sweeps; the device must
+    reproduce the oracle: same count, element division identical by checksum (it is also the division GDsteady reaches on this
+    problem, tests/golden/gdsteady_mbench.json), forces and traction sums to 1e-9."""
+    import hashlib
+    import json
+    here = os.path.dirname(__file__)
+    fx = json.load(open(os.path.join(here, "golden", "steadygs_2c.json")))
+    gd = json.load(open(os.path.join(here, "golden", "gdsteady_mbench.json")))["2c"]
+    g = dict(mx=143, my=161, xl=-3.55, yl=-6.15, dx=0.05, dy=0.05, ibase=2, prmudf=np.array(mbench["prmudf"]))
+    ire, icp = 67, 1
+    _setup_rolling(cb, ire, g, cases.STEEL["gg"], cases.STEEL["poiss"], pen=mbench["pen"])
     cb.cntc_setrollingstepsize(ire, icp, 0.0, 0.05)
     cb.cntc_setcreepages(ire, icp, 0.0005, 0.0, 0.0003)
-    assert cb.cntc_calculate(ire, icp) == -99 and "Gauss-Seidel" in cb.lib.last_error()
+    ierr = cb.cntc_calculate(ire, icp)
+    assert ierr == 0, (ierr, cb.lib.last_error())
+    its = cb.lowlevel.get_iterations(ire, icp)
+    el = cb.cntc_getelementdivision(ire, icp).ravel().astype(np.int8)
+    assert int((el >= 1).sum()) == fx["ncon"] == 12902 and int((el == 2).sum()) == fx["nslip"] == 7735
+    assert its["itgs"] == fx["itgs"] and abs(its["itgs"] - 90) <= 1, (its, fx["itgs"])
+    assert hashlib.sha1(el.tobytes()).hexdigest() == fx["el_sha1"] == gd["el_sha1"]
+    fn, tx, ty, mz = cb.cntc_getcontactforces(ire, icp)
+    assert abs(tx / (0.3 * fn) - fx["fx"]) < 1e-9 and abs(ty / (0.3 * fn) - fx["fy"]) < 1e-9
+    pn, px, py = cb.cntc_gettractions(ire, icp)
+    assert abs(px.sum() - fx["ps_sum"][0]) < 1e-9 * abs(fx["ps_sum"][0]) and abs(py.sum() - fx["ps_sum"][1]) < 1e-9 * abs(fx["ps_sum"][1])
+    cb.cntc_finalize(ire)
+
+
+def test_gdsteady_stagnation_falls_back_on_whole_gpu(cb, O, mbench):
+    """The same switch on the whole-GPU path (143x161): GDsteady stopped by MAXGS = 12 reports stagnation, SteadyGS (direct form)
+    takes over for its MAXGS sweeps and the case ends like the oracle's: same error code, fall-back count and element division."""
+    g2 = dict(mx=143, my=161, xl=-3.55, yl=-6.15, dx=0.05, dy=0.05, ibase=2, prmudf=np.array(mbench["prmudf"]))
+    ire, icp = 66, 1
+    _setup_rolling(cb, ire, g2, cases.STEEL["gg"], cases.STEEL["poiss"], pen=mbench["pen"])
+    _gd_flags(cb, ire, icp, GD_8C, maxgs=12)
+    cb.cntc_setrollingstepsize(ire, icp, 0.0, 0.05)
+    cb.cntc_setcreepages(ire, icp, 0.0005, 0.0, 0.0003)
+    ierr = cb.cntc_calculate(ire, icp)
+    ref = O.contac(g2, cases.STEEL["gg"], cases.STEEL["poiss"], tang=3, norm=0, force3=0, pen=mbench["pen"], cksi=0.0005,
+                   ceta=0.0, cphi=0.0003, fstat=0.3, fkin=0.3, maxgs=12, maxin=100, maxnr=30, maxout=1, eps=1e-7,
+                   nn=mbench["nn"], chi=0.0, dq=0.05, gausei=5, gd=GD_8C)
+    its = cb.lowlevel.get_iterations(ire, icp)
+    assert ref["gd_fallback"] == 1 and its["gd_fallback"] == 1
+    assert (ierr < 0) == (ref["ierror"] < 0) and (ierr >= 0 or ierr == ref["ierror"]), (ierr, ref["ierror"], cb.lib.last_error())
+    assert its["itgs"] == ref["itgs_tang"], (its, ref["itgs_tang"])
+    el = cb.cntc_getelementdivision(ire, icp).ravel()
+    assert np.array_equal(el, ref["el"]), int((el != ref["el"]).sum())
+    pn, px, py = cb.cntc_gettractions(ire, icp)
+    s_ = np.abs(ref["ps"][:2]).max()
+    assert np.abs(px.ravel() - ref["ps"][0]).max() < 1e-7 * s_ and np.abs(py.ravel() - ref["ps"][1]).max() < 1e-7 * s_
     cb.cntc_finalize(ire)
 
 

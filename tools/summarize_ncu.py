@@ -71,10 +71,27 @@ def to_bytes(u, v):
 
 traffic = to_bytes(*m["dram__bytes_read.sum"]) + to_bytes(*m["dram__bytes_write.sum"])
 ncase = 148
-json.dump({"k_snorm_batch": {"dram_bytes_per_case": traffic / ncase, "cases_in_capture": ncase,
-                             "source": "profiles/ncu_%s.txt" % tag}}, open("profiles/traffic_%s.json" % tag, "w"))
+tj = {"k_snorm_batch": {"dram_bytes_per_case": traffic / ncase, "cases_in_capture": ncase, "source": "profiles/ncu_%s.txt" % tag}}
 out.append("")
 out.append("dram traffic per launch (148 cases): %.1f MB = %.2f MB per case" % (traffic / 1e6, traffic / 1e6 / ncase))
+
+# 2b. the headline kernel: k_contac_batch on 148 complete hertz-91 contact cases (N=1, T=3, G=0)
+raw = page("prof_contac", tag, "raw")
+rr = list(csv.reader(raw.splitlines()))
+if len(rr) >= 3:
+    hh, units, vals = rr[0], rr[1], rr[2]
+    out.append("")
+    out.append("# ncu --set full --clock-control none -k regex:k_contac_batch : python bench.py --contact-cases 148 --steps 1 --warmup 3 (hertz-91, T=3, G=0)")
+    mc = {}
+    for i, n in enumerate(hh):
+        if n in want:
+            out.append("%-90s %-12s %s" % (n, units[i], vals[i]))
+            mc[n] = (units[i], vals[i])
+    tc = to_bytes(*mc["dram__bytes_read.sum"]) + to_bytes(*mc["dram__bytes_write.sum"])
+    tj["k_contac_batch"] = {"dram_bytes_per_case": tc / ncase, "cases_in_capture": ncase, "source": "profiles/ncu_%s.txt" % tag}
+    out.append("")
+    out.append("dram traffic per launch (148 cases): %.1f MB = %.2f MB per case" % (tc / 1e6, tc / 1e6 / ncase))
+json.dump(tj, open("profiles/traffic_%s.json" % tag, "w"))
 
 # 3. the three phase kernels of the whole-GPU product (575x647), one launch each
 for name, title in (("prof_large", "# ncu --set full --clock-control none -k regex:k_lg_ : python tools/large_product_only.py (575x647, 1x1 product)"),
