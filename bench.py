@@ -511,7 +511,7 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     # ---- headline: complete hertz-91 contact cases (N=1, T=3, G=0) through the drop-in path ----
-    ncase = args.contact_cases if args.contact_cases > 0 else 2 * nsm          # two waves of one CTA per case
+    ncase = args.contact_cases if args.contact_cases > 0 else 4 * nsm          # four waves of one CTA per case (dynamic queue)
     ncase = min(ncase, 999)                                                     # result elements are 1..999
     ires = list(range(1, ncase + 1))
     draws = hertz91_draws(ncase, offset=rank * ncase)
@@ -566,6 +566,17 @@ def run_gpu(args):
         f0, f5 = roll.pop("_forces"), roll_gd.pop("_forces")
         roll_gd["max_rel_force_diff_vs_steadygs"] = float(np.abs(f5 - f0).max() / np.abs(f0).max())
     sweep = sweep4096_leg(cb, rank, world) if (args.sweep4096 and not args.skip_extra) else None
+    inlib = None
+    if world == 1 and args.inlib_devices > 1 and torch.cuda.device_count() >= args.inlib_devices:
+        # the batched case scheduler inside the library: one process, every cntc_calculate_batch call cut into contiguous shards over the
+        # devices (one host thread each); first pass warms the per-device coefficient caches and work-space pools
+        nd = ll.set_devices(args.inlib_devices)
+        sweep4096_leg(cb, 0, 1, total=2 * 888)
+        r = sweep4096_leg(cb, 0, 1)
+        ll.set_devices(1)
+        inlib = {"devices": nd, "cases_total": r["cases"], "s": r["s"], "cases_per_s": r["cases"] / r["s"], "errors": r["errors"],
+                 "chunks": r["chunks"], "note": "BASELINE config 5 through ONE process: cb200_set_devices(n), result elements 1..999 => chunks of "
+                                                "<= 888 cases per call, each call spread over the devices; wall clock"}
     large = large_grid_leg(cb, torch) if (rank == 0 and not args.skip_extra) else None
     sp71 = spence71_leg(cb) if (rank == 0 and not args.skip_extra) else None
     gdl = gdsteady_leg(cb) if (rank == 0 and not args.skip_extra) else None
@@ -677,6 +688,8 @@ def run_gpu(args):
             out["gdsteady_large"] = gdl
         if gsl:
             out["steadygs_large"] = gsl
+        if inlib:
+            out["sweep4096_inlib"] = inlib
         if args.cpu_seconds > 0:
             out["cpu_baseline"] = cpu_baseline(args.cpu_seconds, threads=1)
         print(json.dumps(out))
@@ -814,7 +827,7 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": workload_config(2 * nsm, args.gpus),
+           "config": workload_config(4 * nsm, args.gpus),
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                             "sample": "%d complete hertz-91 contact cases per step (N=1, T=3, G=0), one case per thread (test_table.f90 "
                                       "pattern), CPU restatement of the reference algorithm (oracle/, gcc -O3, own FFT instead of MKL)" % per_step,
@@ -830,11 +843,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cases", type=int, default=0, help="norm_only leg: cases per GPU per step (default 8 x SM count)")
-    ap.add_argument("--contact-cases", type=int, default=0, help="headline: complete contact cases per GPU per step (default 2 x SM count, <= 999)")
+    ap.add_argument("--contact-cases", type=int, default=0, help="headline: complete contact cases per GPU per step (default 4 x SM count, <= 999)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg (0 = skip)")
     ap.add_argument("--no-sweep4096", dest="sweep4096", action="store_false",
                     help="skip BASELINE config 5 at full size (4096 rolling cases sharded over the ranks, ~5 s on one GPU)")
     ap.add_argument("--skip-extra", action="store_true", help="skip the rolling-sweep and 575x647 legs")
+    ap.add_argument("--inlib-devices", type=int, default=0, help="single process: also run the 4096-case sweep with the library's own "
+                    "scheduler spreading each cntc_calculate_batch call over this many GPUs (cb200_set_devices)")
     ap.add_argument("--gs-4c", action="store_true", help="steadygs_large leg: also tang_problm_4c with G=0 (minutes)")
     args = ap.parse_args()
     if args.impl == "reference":

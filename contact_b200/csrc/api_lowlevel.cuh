@@ -74,8 +74,8 @@ inline int vecaijpj_dev(CoefSet &cs, int set, int ncase, int iigs, int ikarg, in
     if (!cs.d_cf[set]) { last_error() = "coefficient set not available"; return -99; }
     const int mask_mode = (iigs == -8) ? 1 : 0;
     if (mask_mode == 1 && !d_el) { last_error() = "AllInt product needs an element division"; return -99; }
-    static bool attr = false;
-    if (!attr) { CB_CUDA(cudaFuncSetAttribute(k_conv_batch_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax)); attr = true; }
+    static bool attr[CB_MAX_DEVICES] = { false };               // function attributes are per device
+    if (!attr[current_device()]) { CB_CUDA(cudaFuncSetAttribute(k_conv_batch_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax)); attr[current_device()] = true; }
     int ik0, ik1, jk0, jk1;
     dir_range(ikarg, ik0, ik1); dir_range(jkarg, jk0, jk1);
     const long cstride = 3L * P.npot;
@@ -202,7 +202,8 @@ inline int snorm_batch_dev(CoefSet &cs, int ncase, int ic_norm, int maxgs, int m
     NormBatch &B = norm_batch();
     if (!B.d_next) CB_CUDA(cudaMalloc(&B.d_next, sizeof(int) * CB_NEXT_SLOTS));
     if (!B.ev0) { CB_CUDA(cudaEventCreate(&B.ev0)); CB_CUDA(cudaEventCreate(&B.ev1)); }
-    static long cap_bytes = 0;
+    static long cap_bytes_dev[CB_MAX_DEVICES] = { 0 };
+    long &cap_bytes = cap_bytes_dev[current_device()];
     const int ntot = total > ncase ? total : ncase;
     const long need = (long) ntot * 9 * P.npot * sizeof(double);
     if (ntot > B.cap || need > cap_bytes) {
@@ -237,8 +238,8 @@ inline int snorm_batch_dev(CoefSet &cs, int ncase, int ic_norm, int maxgs, int m
     k_norm_unpack<<<grid1d(ncase, 128), 128, 0, st>>>(d_cases, ncase, d_scal);
     E.launches += 3;
     if (d_un) {
-        static bool attr = false;
-        if (!attr) { CB_CUDA(cudaFuncSetAttribute(k_conv_batch_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax)); attr = true; }
+        static bool attr[CB_MAX_DEVICES] = { false };
+        if (!attr[current_device()]) { CB_CUDA(cudaFuncSetAttribute(k_conv_batch_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax)); attr[current_device()] = true; }
         CB_CUDA(cudaMemsetAsync(d_un, 0, sizeof(double) * (size_t) ncase * P.npot, st));
         k_conv_batch_strided<<<launch_blocks(ncase), CB_THREADS, P.smem_bytes, st>>>(
             P, d_pn, P.npot, proto.chatA, d_un, P.npot, d_el, 1, 0, ncase);

@@ -141,6 +141,12 @@ struct SteadyArgs {
 struct SteadySmem {
     double *q, *r0, *row;      // table (or null), dy = 0 rows [3][2mx], per-row arrays [15][mx] + 8 scalars
     int *irow;                 // int arrays [3][mx], then rowk[my+2], ictl[8]
+    double *lst;               // two net-change lists of finished rows [2][2][mx] (x, y), see the pipelined update of the other rows
+    int *ilst;                 // their element positions [2][mx] and lengths [2]
+    __device__ __forceinline__ double &lx(int b, int j) const { return lst[(2 * b) * mx + j]; }
+    __device__ __forceinline__ double &ly(int b, int j) const { return lst[(2 * b + 1) * mx + j]; }
+    __device__ __forceinline__ int &lj(int b, int j) const { return ilst[b * mx + j]; }
+    __device__ __forceinline__ int &lcnt(int b) const { return ilst[2 * mx + b]; }
     int mx;
     // accessors: one base pointer + multiples of mx (keeps the register footprint small)
     __device__ __forceinline__ double &psx(int j) const { return row[j]; }
@@ -169,7 +175,8 @@ struct SteadySmem {
 // bytes of the row arrays etc. (without the coefficient table)
 __host__ __device__ __forceinline__ size_t steady_fixed_bytes(int mx, int my)
 {
-    return ((size_t) (6 * mx + 15 * mx + 8)) * 8 + ((size_t) (3 * mx + my + 10)) * 4 + 64;
+    return ((size_t) (6 * mx + 15 * mx + 8)) * 8 + ((((size_t) (3 * mx + my + 10)) * 4 + 7) & ~(size_t) 7) + (size_t) (4 * mx) * 8 +
+           (size_t) (2 * mx + 4) * 4 + 64;
 }
 
 // extra dynamic shared memory that a launch must provide beyond the FFT plan's: for small grids the S/W regions of the
@@ -193,6 +200,8 @@ __device__ __forceinline__ void steady_carve(const ConvPlan &P, unsigned char *b
     s.r0 = d; d += 6 * mx;
     s.row = d;
     s.irow = reinterpret_cast<int *>(d + 15 * mx + 8);
+    s.lst = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(s.irow) + ((((size_t) (3 * mx + my + 10)) * 4 + 7) & ~(size_t) 7));
+    s.ilst = reinterpret_cast<int *>(s.lst + 4 * mx);
     s.mx = (int) mx;
 }
 
@@ -231,7 +240,7 @@ struct SteadyTab {
 // with a warp scan -- while the net change of the row is applied to the register-resident U of all other rows once
 // per row by the whole CTA.
 //
-// DIRECT = true: the form for contact areas that do not fit the register-resident U (more than 22 x 384 elements, or a grid on
+// DIRECT = true: the form for contact areas that do not fit the register-resident U (more than 22 x 352 elements, or a grid on
 // the whole-GPU path).  No U is kept: before every element step the whole CTA evaluates the reference's row sum
 // U_i = (1/G) sum_j A(i - j) xp_j over the compact contact list (gf3_AijPj, m_aijpj.f90:99-254; the current row from shared
 // memory, the other rows from global memory / L2, coefficients from the spatial blocks in L2), then warp 0 performs the
@@ -282,6 +291,7 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
         }
         double *d = reinterpret_cast<double *>(sbase);
         s.q = nullptr; s.r0 = d; s.row = d + 6 * mx; s.irow = reinterpret_cast<int *>(d + 6 * mx + 15 * mx + 8); s.mx = mx;
+        s.lst = nullptr; s.ilst = nullptr;
     } else {
         steady_carve(P, reinterpret_cast<unsigned char *>(sm.S), a.sym, s);
         conv_tables_invalidate(sm);                                 // the sweep arrays overwrite the product's window
@@ -346,14 +356,15 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
         __syncthreads();
         nsp = spk[my];
     }
-    // registers: my contact elements k = tid + m nt
+    // registers: my contact elements k = (tid - 32) + m (nt - 32).  Warp 0 owns none: it walks the rows while the other warps
+    // apply the net change of the previous row to their elements (pipelined update below)
     double Ux[KMAX], Uy[KMAX];
     int ixy[KMAX];
 #pragma unroll
     for (int m = 0; m < KMAX; m++) {
-        const int k = tid + m * nt;
+        const int k = (tid - 32) + m * (nt - 32);
         Ux[m] = 0.0; Uy[m] = 0.0; ixy[m] = -1;
-        if (!DIRECT && k < ncon) {
+        if (!DIRECT && tid >= 32 && k < ncon) {
             const int ii = a.iel[k], iy = ii / mx;
             ixy[m] = (ii - iy * mx) | (iy << 16);
             Ux[m] = a.ug[ii]; Uy[m] = a.ug[n + ii];
@@ -371,6 +382,58 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
     const size_t oc = (size_t) a.cmy * (2 * a.cmx) + a.cmx;
     const double l00 = ledge ? a.cs11[oc] * a.ga_inv : 0.0, l01 = ledge ? a.cs12[oc] * a.ga_inv : 0.0,
                  l11 = ledge ? a.cs22[oc] * a.ga_inv : 0.0;
+    // pipelined update of the other rows (register form): the compacted net-change list of a finished row lives in one of two
+    // shared-memory buffers; apply_list adds its effect to this thread's elements in the rows selected by `sel`
+    int par = 0, pend_par = 0, pend_row = -1;
+    auto apply_list = [&](int b, int src, auto sel) {
+        const int ncl = s.lcnt(b);
+        if (ncl == 0) return;
+        if (s.q && a.sym) {                                    // quadrant table in shared memory: the fast path
+#pragma unroll
+            for (int m = 0; m < KMAX; m++) {
+                const int iym = ixy[m] >> 16, ixm = ixy[m] & 0xffff;
+                if (ixy[m] >= 0 && sel(iym)) {
+                    const int dy = iym - src;
+                    const double *r11 = s.q + abs(dy) * mx, *r12 = r11 + n, *r22 = r12 + n;
+                    const bool ny = dy < 0;
+                    double ux0 = 0.0, uy0 = 0.0, ux1 = 0.0, uy1 = 0.0;
+                    int c = 0;
+                    for (; c + 1 < ncl; c += 2) {
+                        const int d0 = ixm - s.lj(b, c), d1 = ixm - s.lj(b, c + 1);
+                        const int a0 = abs(d0), a1 = abs(d1);
+                        const double e0x = s.lx(b, c), e0y = s.ly(b, c), e1x = s.lx(b, c + 1), e1y = s.ly(b, c + 1);
+                        const double g0 = r11[a0], h0 = ((d0 < 0) != ny) ? -r12[a0] : r12[a0], k0_ = r22[a0];
+                        const double g1 = r11[a1], h1 = ((d1 < 0) != ny) ? -r12[a1] : r12[a1], k1_ = r22[a1];
+                        ux0 += g0 * e0x + h0 * e0y; uy0 += h0 * e0x + k0_ * e0y;
+                        ux1 += g1 * e1x + h1 * e1y; uy1 += h1 * e1x + k1_ * e1y;
+                    }
+                    if (c < ncl) {
+                        const int d0 = ixm - s.lj(b, c), a0 = abs(d0);
+                        const double e0x = s.lx(b, c), e0y = s.ly(b, c);
+                        const double g0 = r11[a0], h0 = ((d0 < 0) != ny) ? -r12[a0] : r12[a0], k0_ = r22[a0];
+                        ux0 += g0 * e0x + h0 * e0y; uy0 += h0 * e0x + k0_ * e0y;
+                    }
+                    Ux[m] += ux0 + ux1; Uy[m] += uy0 + uy1;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < KMAX; m++) {
+                const int iym = ixy[m] >> 16, ixm = ixy[m] & 0xffff;
+                if (ixy[m] >= 0 && sel(iym)) {
+                    double ux = 0.0, uy = 0.0;
+                    for (int c = 0; c < ncl; c++) {
+                        double c11, c12, c22;
+                        T.get(ixm - s.lj(b, c), iym - src, c11, c12, c22);
+                        const double ex = s.lx(b, c), ey = s.ly(b, c);
+                        ux += c11 * ex + c12 * ey;
+                        uy += c12 * ex + c22 * ey;
+                    }
+                    Ux[m] += ux; Uy[m] += uy;
+                }
+            }
+        }
+    };
     while (dif >= difid && itgs < a.maxgs) {
         itgs++;
         // work accounting: a sweep is 2 ncon row sums over (ncon + 2 my) 2 columns in the reference
@@ -612,61 +675,26 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
                     const double ex = jx < mx ? s.ddx(jx) : 0.0, ey = jx < mx ? s.ddy(jx) : 0.0;
                     const bool nz = (ex != 0.0 || ey != 0.0);
                     const unsigned mk = __ballot_sync(full, nz);
-                    if (nz) { const int pos = cnt + __popc(mk & ((1u << lane) - 1u)); s.chj(pos) = jx; s.chx(pos) = ex; s.chy(pos) = ey; }
+                    if (nz) { const int pos = cnt + __popc(mk & ((1u << lane) - 1u)); s.lj(par, pos) = jx; s.lx(par, pos) = ex; s.ly(par, pos) = ey; }
                     cnt += __popc(mk);
                 }
-                if (!DIRECT && lane == 0) { s.ictl(1, my) = cnt; tp6 += cnt; }
+                if (!DIRECT && lane == 0) { s.lcnt(par) = cnt; tp6 += cnt; }
+            } else if (pend_row >= 0) {
+                // ---- warps 1.. meanwhile: the net change of the PREVIOUS row goes to the elements of all other rows.  This pass is
+                // shared-memory-bandwidth bound (three table entries per pair), the chain of warp 0 is latency bound: they overlap.
+                // (This row received it before it was staged; the previous row keeps its own U in shared memory.)
+                apply_list(pend_par, pend_row, [&](int r) { return r != pend_row && r != iy; });
             }
             __syncthreads();
 
-            // ---- whole CTA: apply the net change of row iy to the elements of all other rows ----
+            // ---- whole CTA: the net change of row iy goes to the NEXT row with contact only (it is staged next); all other rows
+            // receive it while warp 0 walks that next row ----
             const unsigned long long te = clock64();
-            const int ncl = DIRECT ? 0 : s.ictl(1, my);
-            if (DIRECT) { }
-            else if (s.q && a.sym) {                                // quadrant table in shared memory: the fast path
-#pragma unroll
-                for (int m = 0; m < KMAX; m++) {
-                    const int iym = ixy[m] >> 16, ixm = ixy[m] & 0xffff;
-                    if (ixy[m] >= 0 && iym != iy) {
-                        const int dy = iym - iy;
-                        const double *r11 = s.q + abs(dy) * mx, *r12 = r11 + n, *r22 = r12 + n;
-                        const bool ny = dy < 0;
-                        double ux0 = 0.0, uy0 = 0.0, ux1 = 0.0, uy1 = 0.0;
-                        int c = 0;
-                        for (; c + 1 < ncl; c += 2) {
-                            const int d0 = ixm - s.chj(c), d1 = ixm - s.chj(c + 1);
-                            const int a0 = abs(d0), a1 = abs(d1);
-                            const double e0x = s.chx(c), e0y = s.chy(c), e1x = s.chx(c + 1), e1y = s.chy(c + 1);
-                            const double g0 = r11[a0], h0 = ((d0 < 0) != ny) ? -r12[a0] : r12[a0], k0_ = r22[a0];
-                            const double g1 = r11[a1], h1 = ((d1 < 0) != ny) ? -r12[a1] : r12[a1], k1_ = r22[a1];
-                            ux0 += g0 * e0x + h0 * e0y; uy0 += h0 * e0x + k0_ * e0y;
-                            ux1 += g1 * e1x + h1 * e1y; uy1 += h1 * e1x + k1_ * e1y;
-                        }
-                        if (c < ncl) {
-                            const int d0 = ixm - s.chj(c), a0 = abs(d0);
-                            const double e0x = s.chx(c), e0y = s.chy(c);
-                            const double g0 = r11[a0], h0 = ((d0 < 0) != ny) ? -r12[a0] : r12[a0], k0_ = r22[a0];
-                            ux0 += g0 * e0x + h0 * e0y; uy0 += h0 * e0x + k0_ * e0y;
-                        }
-                        Ux[m] += ux0 + ux1; Uy[m] += uy0 + uy1;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int m = 0; m < KMAX; m++) {
-                    const int iym = ixy[m] >> 16, ixm = ixy[m] & 0xffff;
-                    if (ixy[m] >= 0 && iym != iy) {
-                        double ux = 0.0, uy = 0.0;
-                        for (int c = 0; c < ncl; c++) {
-                            double c11, c12, c22;
-                            T.get(ixm - s.chj(c), iym - iy, c11, c12, c22);
-                            const double ex = s.chx(c), ey = s.chy(c);
-                            ux += c11 * ex + c12 * ey;
-                            uy += c12 * ex + c22 * ey;
-                        }
-                        Ux[m] += ux; Uy[m] += uy;
-                    }
-                }
+            if constexpr (!DIRECT) {
+                int nx = iy;
+                do { nx = (nx + 1 == my) ? 0 : nx + 1; } while (nx != iy && s.rowk(nx + 1) == s.rowk(nx));
+                if (nx != iy) apply_list(par, iy, [&](int r) { return r == nx; });
+                pend_row = iy; pend_par = par; par ^= 1;
             }
 #pragma unroll
             for (int m = 0; m < KMAX; m++)

@@ -352,9 +352,10 @@ __device__ int solve_once_dev(const X &x, ContactCase &c, const double *wstot, d
         a.ledge = (sv && c.dq > c.dx) ? 1 : 0; a.facdt = c.twork;             // facdt of stang_dev
         a.cs11 = c.cf11; a.cs12 = c.cf12; a.cs22 = c.cf22; a.cs13 = c.cf13; a.cs23 = c.cf23; a.ub = a.ug;
         if constexpr (X::kBlock) {
-            if (ncon <= 6 * CB_THREADS) info = stdygs_dev<6>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
-            else if (ncon <= 12 * CB_THREADS) info = stdygs_dev<12>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
-            else if (ncon <= 22 * CB_THREADS) info = stdygs_dev<22>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
+            const int nown = CB_THREADS - 32;                    // warp 0 owns no elements (it walks the rows)
+            if (ncon <= 6 * nown) info = stdygs_dev<6>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
+            else if (ncon <= 12 * nown) info = stdygs_dev<12>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
+            else if (ncon <= 22 * nown) info = stdygs_dev<22>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);
             else info = stdygs_dev<1, true>(x.plan(), x.smem(), a, c.nrm.el, c.ps, c.ss, ncon, it, err, nprod);   // direct row sums
         } else {
             // whole-GPU path: the sweep is one sequential chain of element steps, each with an O(ncon) row sum -- CTA 0 runs it

@@ -929,7 +929,7 @@ def test_gdsteady_stagnation_falls_back_to_steadygs(cb, O, mbench):
 
 
 def test_steadygs_direct_form_beyond_register_capacity(cb, O):
-    """100x100 grid (fits one CTA) with a full-width contact of 8700 elements: more than the 22 x 384 elements the register-
+    """100x100 grid (fits one CTA) with a full-width contact of 8700 elements: more than the 22 x 352 elements the register-
     resident sweep holds, so the one-CTA path uses the direct form of the sweep (row sums per element step).  Six sweeps of
     SteadyGS against the oracle: element division bit-exact, tractions to 1e-9 -- a strict check of the sweep itself."""
     g = dict(mx=100, my=100, xl=-5.0, yl=-5.0, dx=0.1, dy=0.1, ibase=1, prmudf=[0.0011, 0.0, 0.00001, 0.0, 0.0, 0.0])
