@@ -139,37 +139,46 @@ struct SteadyArgs {
 // [3][my][2mx] for csv, null when it does not fit: blocks are then read from global memory); r0: the dy = 0 rows of the
 // three blocks for dx in [-mx, mx) (in-row updates and the element's own 2x2 matrix)
 struct SteadySmem {
-    double *q, *r0, *row;      // table (or null), dy = 0 rows [3][2mx], per-row arrays [15][mx] + 8 scalars
-    int *irow;                 // int arrays [3][mx], then rowk[my+2], ictl[8]
-    double *lst;               // two net-change lists of finished rows [2][2][mx] (x, y), see the pipelined update of the other rows
-    int *ilst;                 // their element positions [2][mx] and lengths [2]
-    __device__ __forceinline__ double &lx(int b, int j) const { return lst[(2 * b) * mx + j]; }
-    __device__ __forceinline__ double &ly(int b, int j) const { return lst[(2 * b + 1) * mx + j]; }
-    __device__ __forceinline__ int &lj(int b, int j) const { return ilst[b * mx + j]; }
-    __device__ __forceinline__ int &lcnt(int b) const { return ilst[2 * mx + b]; }
+    // All arrays are addressed as 32-bit element offsets into the CTA's shared-memory window (typed ld.shared / st.shared: the
+    // sweep is one warp's dependent instruction chain, and generic 64-bit addressing cost a third of its instructions).
+    uint32_t oq, or0, orow;    // (doubles) table (hasq), dy = 0 rows [3][2mx], per-row arrays [15][mx] + 8 scalars
+    uint32_t oirow;            // (ints) int arrays [3][mx], then rowk[my+2], ictl[8]
+    uint32_t olst;             // (doubles) two net-change lists of finished rows [2][2][mx] (x, y): pipelined update of the other rows
+    uint32_t oilst;            // (ints) their element positions [2][mx] and lengths [2]
+    int hasq;
+    __device__ __forceinline__ double *wd() const { return reinterpret_cast<double *>(cb_smem_window); }
+    __device__ __forceinline__ int *wi() const { return reinterpret_cast<int *>(cb_smem_window); }
+    __device__ __forceinline__ double *q() const { return wd() + oq; }
+    __device__ __forceinline__ double *r0() const { return wd() + or0; }
+    __device__ __forceinline__ double *row() const { return wd() + orow; }
+    __device__ __forceinline__ int *irow() const { return wi() + oirow; }
+    __device__ __forceinline__ double &lx(int b, int j) const { return wd()[olst + (2 * b) * mx + j]; }
+    __device__ __forceinline__ double &ly(int b, int j) const { return wd()[olst + (2 * b + 1) * mx + j]; }
+    __device__ __forceinline__ int &lj(int b, int j) const { return wi()[oilst + b * mx + j]; }
+    __device__ __forceinline__ int &lcnt(int b) const { return wi()[oilst + 2 * mx + b]; }
     int mx;
     // accessors: one base pointer + multiples of mx (keeps the register footprint small)
-    __device__ __forceinline__ double &psx(int j) const { return row[j]; }
-    __device__ __forceinline__ double &psy(int j) const { return row[mx + j]; }
-    __device__ __forceinline__ double &dpx(int j) const { return row[2 * mx + j]; }
-    __device__ __forceinline__ double &dpy(int j) const { return row[3 * mx + j]; }
-    __device__ __forceinline__ double &bnd(int j) const { return row[4 * mx + j]; }
-    __device__ __forceinline__ double &wsx(int j) const { return row[5 * mx + j]; }
-    __device__ __forceinline__ double &wsy(int j) const { return row[6 * mx + j]; }
-    __device__ __forceinline__ double &ssx(int j) const { return row[7 * mx + j]; }
-    __device__ __forceinline__ double &ssy(int j) const { return row[8 * mx + j]; }
-    __device__ __forceinline__ double &urx(int j) const { return row[9 * mx + j]; }
-    __device__ __forceinline__ double &ury(int j) const { return row[10 * mx + j]; }
-    __device__ __forceinline__ double &ddx(int j) const { return row[11 * mx + j]; }
-    __device__ __forceinline__ double &ddy(int j) const { return row[12 * mx + j]; }
-    __device__ __forceinline__ double &chx(int j) const { return row[13 * mx + j]; }
-    __device__ __forceinline__ double &chy(int j) const { return row[14 * mx + j]; }
-    __device__ __forceinline__ double &scal(int j) const { return row[15 * mx + j]; }
-    __device__ __forceinline__ int &el(int j) const { return irow[j]; }
-    __device__ __forceinline__ int &chj(int j) const { return irow[mx + j]; }
-    __device__ __forceinline__ int &cix(int j) const { return irow[2 * mx + j]; }
-    __device__ __forceinline__ int &rowk(int j) const { return irow[3 * mx + j]; }
-    __device__ __forceinline__ int &ictl(int j, int my) const { return irow[3 * mx + my + 2 + j]; }
+    __device__ __forceinline__ double &psx(int j) const { return row()[j]; }
+    __device__ __forceinline__ double &psy(int j) const { return row()[mx + j]; }
+    __device__ __forceinline__ double &dpx(int j) const { return row()[2 * mx + j]; }
+    __device__ __forceinline__ double &dpy(int j) const { return row()[3 * mx + j]; }
+    __device__ __forceinline__ double &bnd(int j) const { return row()[4 * mx + j]; }
+    __device__ __forceinline__ double &wsx(int j) const { return row()[5 * mx + j]; }
+    __device__ __forceinline__ double &wsy(int j) const { return row()[6 * mx + j]; }
+    __device__ __forceinline__ double &ssx(int j) const { return row()[7 * mx + j]; }
+    __device__ __forceinline__ double &ssy(int j) const { return row()[8 * mx + j]; }
+    __device__ __forceinline__ double &urx(int j) const { return row()[9 * mx + j]; }
+    __device__ __forceinline__ double &ury(int j) const { return row()[10 * mx + j]; }
+    __device__ __forceinline__ double &ddx(int j) const { return row()[11 * mx + j]; }
+    __device__ __forceinline__ double &ddy(int j) const { return row()[12 * mx + j]; }
+    __device__ __forceinline__ double &chx(int j) const { return row()[13 * mx + j]; }
+    __device__ __forceinline__ double &chy(int j) const { return row()[14 * mx + j]; }
+    __device__ __forceinline__ double &scal(int j) const { return row()[15 * mx + j]; }
+    __device__ __forceinline__ int &el(int j) const { return irow()[j]; }
+    __device__ __forceinline__ int &chj(int j) const { return irow()[mx + j]; }
+    __device__ __forceinline__ int &cix(int j) const { return irow()[2 * mx + j]; }
+    __device__ __forceinline__ int &rowk(int j) const { return irow()[3 * mx + j]; }
+    __device__ __forceinline__ int &ictl(int j, int my) const { return irow()[3 * mx + my + 2 + j]; }
 };
 
 // bytes of the row arrays etc. (without the coefficient table)
@@ -187,6 +196,21 @@ __host__ __device__ __forceinline__ size_t steady_extra_smem(const ConvPlan &P)
     return fixed <= (size_t) P.off_twx ? 0 : fixed;
 }
 
+// offsets of the sweep arrays for a region that starts at `base` (a pointer into this CTA's dynamic shared memory)
+__device__ __forceinline__ void steady_offsets(unsigned char *base, size_t tab_doubles, int mx, int my, SteadySmem &s)
+{
+    const uint32_t b = (uint32_t) __cvta_generic_to_shared(base) - (uint32_t) __cvta_generic_to_shared(cb_smem_window);
+    uint32_t d = b >> 3;                                            // base is 16-byte aligned
+    s.hasq = tab_doubles > 0 ? 1 : 0;
+    s.oq = d; d += (uint32_t) tab_doubles;
+    s.or0 = d; d += 6u * mx;
+    s.orow = d;
+    s.oirow = (d + 15u * mx + 8u) * 2u;
+    s.olst = (((s.oirow + 3u * mx + my + 10u) * 4u + 7u) & ~7u) >> 3;
+    s.oilst = (s.olst + 4u * mx) * 2u;
+    s.mx = mx;
+}
+
 __device__ __forceinline__ void steady_carve(const ConvPlan &P, unsigned char *base, int sym, SteadySmem &s)
 {
     const size_t n = P.npot, mx = P.mx, my = P.my;
@@ -194,26 +218,19 @@ __device__ __forceinline__ void steady_carve(const ConvPlan &P, unsigned char *b
     const size_t tabsz = (sym ? 3 : 6) * n * 8;
     const bool tab = tabsz + fixed <= (size_t) P.off_twx;
     if (fixed > (size_t) P.off_twx) base += P.smem_bytes;      // behind the plan's layout (see steady_extra_smem)
-    double *d = reinterpret_cast<double *>(base);
-    s.q = tab ? d : nullptr;
-    if (tab) d += (sym ? 3 : 6) * n;
-    s.r0 = d; d += 6 * mx;
-    s.row = d;
-    s.irow = reinterpret_cast<int *>(d + 15 * mx + 8);
-    s.lst = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(s.irow) + ((((size_t) (3 * mx + my + 10)) * 4 + 7) & ~(size_t) 7));
-    s.ilst = reinterpret_cast<int *>(s.lst + 4 * mx);
-    s.mx = (int) mx;
+    steady_offsets(base, tab ? (sym ? 3 : 6) * n : 0, (int) mx, (int) my, s);
 }
 
 // coefficient lookup A_tt(dx, dy): c11, c12 (= c21), c22, already times 1/G
 struct SteadyTab {
-    const double *q, *r0;
+    uint32_t oq, or0;                       // (doubles) offsets of the table (0xffffffff: none) and of the dy = 0 rows in the shared window
     const double *cf11, *cf12, *cf22;
     int n, mx, cmx, cmy, sym;
     double ga_inv;
     __device__ __forceinline__ void get(int dx, int dy, double &c11, double &c12, double &c22) const
     {
-        if (q) {
+        const double *q = reinterpret_cast<const double *>(cb_smem_window) + oq;
+        if (oq != 0xffffffffu) {
             if (sym) {                                      // even (c11, c22) / odd (c12) in x and in y
                 const int o = abs(dy) * mx + abs(dx);
                 c11 = q[o]; c12 = q[n + o]; c22 = q[2 * n + o];
@@ -229,7 +246,7 @@ struct SteadyTab {
         }
     }
     __device__ __forceinline__ void row0(int dx, double &c11, double &c12, double &c22) const
-    { const int o = dx + mx; c11 = r0[o]; c12 = r0[2 * mx + o]; c22 = r0[4 * mx + o]; }
+    { const double *r0 = reinterpret_cast<const double *>(cb_smem_window) + or0; const int o = dx + mx; c11 = r0[o]; c12 = r0[2 * mx + o]; c22 = r0[4 * mx + o]; }
 };
 
 // Gauss-Seidel sweeps of stdygs (convex = 0) or cnvxgs (convex = 1): returns info (0 ok, 1 maxgs reached,
@@ -289,34 +306,32 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
             if (steady_fixed_bytes(P.mx, P.my) > (size_t) P.off_twx) sbase += P.smem_bytes;
             conv_tables_invalidate(sm);
         }
-        double *d = reinterpret_cast<double *>(sbase);
-        s.q = nullptr; s.r0 = d; s.row = d + 6 * mx; s.irow = reinterpret_cast<int *>(d + 6 * mx + 15 * mx + 8); s.mx = mx;
-        s.lst = nullptr; s.ilst = nullptr;
+        steady_offsets(sbase, 0, mx, my, s);
     } else {
         steady_carve(P, reinterpret_cast<unsigned char *>(sm.S), a.sym, s);
         conv_tables_invalidate(sm);                                 // the sweep arrays overwrite the product's window
     }
-    if (s.q) {
+    if (s.hasq) {
         if (a.sym) {
             for (int i = tid; i < n; i += nt) {
                 const int ay = i / mx, ax = i - ay * mx;
                 const size_t o = (size_t) (ay + a.cmy) * (2 * a.cmx) + ax + a.cmx;
-                s.q[i] = a.cf11[o] * a.ga_inv; s.q[n + i] = a.cf12[o] * a.ga_inv; s.q[2 * n + i] = a.cf22[o] * a.ga_inv;
+                s.q()[i] = a.cf11[o] * a.ga_inv; s.q()[n + i] = a.cf12[o] * a.ga_inv; s.q()[2 * n + i] = a.cf22[o] * a.ga_inv;
             }
         } else {
             for (int i = tid; i < 2 * n; i += nt) {
                 const int ay = i / (2 * mx), dx = i - ay * 2 * mx - mx;
                 const size_t o = (size_t) (ay + a.cmy) * (2 * a.cmx) + dx + a.cmx;
-                s.q[i] = a.cf11[o] * a.ga_inv; s.q[2 * n + i] = a.cf12[o] * a.ga_inv; s.q[4 * n + i] = a.cf22[o] * a.ga_inv;
+                s.q()[i] = a.cf11[o] * a.ga_inv; s.q()[2 * n + i] = a.cf12[o] * a.ga_inv; s.q()[4 * n + i] = a.cf22[o] * a.ga_inv;
             }
         }
     }
     for (int i = tid; i < 2 * mx; i += nt) {
         const size_t o = (size_t) a.cmy * (2 * a.cmx) + (i - mx) + a.cmx;
-        s.r0[i] = a.cf11[o] * a.ga_inv; s.r0[2 * mx + i] = a.cf12[o] * a.ga_inv; s.r0[4 * mx + i] = a.cf22[o] * a.ga_inv;
+        s.r0()[i] = a.cf11[o] * a.ga_inv; s.r0()[2 * mx + i] = a.cf12[o] * a.ga_inv; s.r0()[4 * mx + i] = a.cf22[o] * a.ga_inv;
     }
     SteadyTab T;
-    T.q = s.q; T.r0 = s.r0; T.cf11 = a.cf11; T.cf12 = a.cf12; T.cf22 = a.cf22; T.n = n; T.mx = mx; T.cmx = a.cmx; T.cmy = a.cmy;
+    T.oq = s.hasq ? s.oq : 0xffffffffu; T.or0 = s.or0; T.cf11 = a.cf11; T.cf12 = a.cf12; T.cf22 = a.cf22; T.n = n; T.mx = mx; T.cmx = a.cmx; T.cmy = a.cmy;
     T.sym = a.sym; T.ga_inv = a.ga_inv;
     // compact list of contact elements in sweep order + row offsets
     for (int iy = tid; iy < my; iy += nt) {
@@ -388,13 +403,13 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
     auto apply_list = [&](int b, int src, auto sel) {
         const int ncl = s.lcnt(b);
         if (ncl == 0) return;
-        if (s.q && a.sym) {                                    // quadrant table in shared memory: the fast path
+        if (s.hasq && a.sym) {                                 // quadrant table in shared memory: the fast path
 #pragma unroll
             for (int m = 0; m < KMAX; m++) {
                 const int iym = ixy[m] >> 16, ixm = ixy[m] & 0xffff;
                 if (ixy[m] >= 0 && sel(iym)) {
                     const int dy = iym - src;
-                    const double *r11 = s.q + abs(dy) * mx, *r12 = r11 + n, *r22 = r12 + n;
+                    const double *r11 = s.q() + abs(dy) * mx, *r12 = r11 + n, *r22 = r12 + n;
                     const bool ny = dy < 0;
                     double ux0 = 0.0, uy0 = 0.0, ux1 = 0.0, uy1 = 0.0;
                     int c = 0;
@@ -481,6 +496,14 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
             __syncthreads();
 
             if (DIRECT || tid < 32) {                          // ---- warp 0: the Gauss-Seidel steps of this row ----
+                // rows of up to 96 elements: the row's own U and its accumulated net changes live in the registers of warp 0
+                // (lane l holds elements l, l + 32, l + 64) for the whole walk -- no shared-memory round trip per change
+                const bool rr3 = !DIRECT && mx <= 96;
+                double urx_[3] = { 0.0, 0.0, 0.0 }, ury_[3] = { 0.0, 0.0, 0.0 }, ddx_[3] = { 0.0, 0.0, 0.0 }, ddy_[3] = { 0.0, 0.0, 0.0 };
+                if (rr3) {
+#pragma unroll
+                    for (int r = 0; r < 3; r++) { const int ixp = min(lane + 32 * r, mx - 1); urx_[r] = s.urx(ixp); ury_[r] = s.ury(ixp); }
+                }
                 for (int k = k0; k < k1; k++) {
                     if constexpr (DIRECT) {                    // whole CTA: row sum of element k over the contact list
                         const int ixd = s.cix(k - k0);
@@ -534,6 +557,12 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
                         lsx *= a.ga_inv; lsy *= a.ga_inv;
                     }
                     double px = 0.0, py = 0.0;
+                    double ucx, ucy;                                // U of this element
+                    if (rr3) {
+                        const int rq = ix >> 5;
+                        const double vx = rq == 0 ? urx_[0] : (rq == 1 ? urx_[1] : urx_[2]), vy = rq == 0 ? ury_[0] : (rq == 1 ? ury_[1] : ury_[2]);
+                        ucx = __shfl_sync(full, vx, ix & 31); ucy = __shfl_sync(full, vy, ix & 31);
+                    } else { ucx = s.urx(ix); ucy = s.ury(ix); }
                     if (lane == 0) {
                         s.ictl(0, my) = 0;
                         if (active) {
@@ -545,7 +574,7 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
                                 T.row0(jxs - ix, t00, t01, t11);
                                 c00 = q00 - t00; c01 = q01 - t01; c11 = q11 - t11;
                             }
-                            double sx = s.wsx(ix) + s.urx(ix), sy = s.wsy(ix) + s.ury(ix);
+                            double sx = s.wsx(ix) + ucx, sy = s.wsy(ix) + ucy;
                             if (zl) {
                                 int ixb = ix;
                                 while (ixb < mx - 1 && s.el(ixb + 1) >= 1) ixb++;
@@ -647,6 +676,17 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
                     for (int c = 0; c < nch; c++) {
                         const int jx = s.chj(c);
                         const double ex = s.chx(c), ey = s.chy(c);
+                        if (rr3) {
+                            double c11[3], c12[3], c22[3];
+#pragma unroll
+                            for (int r = 0; r < 3; r++) T.row0(min(lane + 32 * r, mx - 1) - jx, c11[r], c12[r], c22[r]);
+#pragma unroll
+                            for (int r = 0; r < 3; r++) {
+                                urx_[r] = urx_[r] + (c11[r] * ex + c12[r] * ey); ury_[r] = ury_[r] + (c12[r] * ex + c22[r] * ey);
+                                if (lane + 32 * r == jx) { ddx_[r] += ex; ddy_[r] += ey; }
+                            }
+                            continue;
+                        }
                         if (lane == 0) { s.ddx(jx) += ex; s.ddy(jx) += ey; }
                         for (int base = 0; base < mx; base += 96) {             // 3 elements per lane, loads first; the
                             double c11[3], c12[3], c22[3], u0[3], u1[3];        // exterior elements are updated too (unused)
@@ -667,12 +707,18 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
                     }
                     if constexpr (DIRECT) __syncthreads();     // the row arrays changed by warp 0 feed the next row sum
                 }
+                if (rr3) {                                      // the row's U back to shared memory for its owners
+#pragma unroll
+                    for (int r = 0; r < 3; r++) { const int ixp = lane + 32 * r; if (ixp < mx) { s.urx(ixp) = urx_[r]; s.ury(ixp) = ury_[r]; } }
+                }
                 // compact the net changes of this row for the update of the other rows
                 int cnt = 0;
                 if (!DIRECT)
                 for (int base = 0; base < mx; base += 32) {
                     const int jx = base + lane;
-                    const double ex = jx < mx ? s.ddx(jx) : 0.0, ey = jx < mx ? s.ddy(jx) : 0.0;
+                    const int rb = base >> 5;
+                    const double dxr = rb == 0 ? ddx_[0] : (rb == 1 ? ddx_[1] : ddx_[2]), dyr = rb == 0 ? ddy_[0] : (rb == 1 ? ddy_[1] : ddy_[2]);
+                    const double ex = jx < mx ? (rr3 ? dxr : s.ddx(jx)) : 0.0, ey = jx < mx ? (rr3 ? dyr : s.ddy(jx)) : 0.0;
                     const bool nz = (ex != 0.0 || ey != 0.0);
                     const unsigned mk = __ballot_sync(full, nz);
                     if (nz) { const int pos = cnt + __popc(mk & ((1u << lane) - 1u)); s.lj(par, pos) = jx; s.lx(par, pos) = ex; s.ly(par, pos) = ey; }
