@@ -250,7 +250,7 @@ inline int snorm_batch_dev(CoefSet &cs, int ncase, int ic_norm, int maxgs, int m
 }
 
 // ---- batched subsurface evaluation on device buffers ----
-struct SubsBatch { double *d_vr = nullptr; long cap = 0; int *d_next = nullptr; };
+struct SubsBatch { double *d_vr = nullptr; long cap = 0; int *d_next = nullptr; double *s_ps = nullptr, *s_t = nullptr; long cap_ps = 0, cap_t = 0; };
 inline SubsBatch &subs_batch() { static SubsBatch b[CB_MAX_DEVICES]; return b[current_device()]; }
 
 inline int subsurf_batch_dev(CoefSet &cs, int ncase, int nz, const double *z, const double gg[2], const double poiss[2],
@@ -562,13 +562,15 @@ int cb200_subsurf_batch(int handle, int ncase, int nz, const double *z, double g
     if (!cs) return -99;
     if (ncase < 1 || nz < 1) return 0;
     const size_t n3 = (size_t) ncase * 3 * cs->hp.p.npot, nt = (size_t) ncase * nz * cs->hp.p.npot * 18;
-    double *d_ps = nullptr, *d_t = nullptr;
-    CB_CUDA(cudaMalloc(&d_ps, sizeof(double) * n3));
-    CB_CUDA(cudaMalloc(&d_t, sizeof(double) * nt));
+    // staging buffers kept between calls (a sequence of cases asks for the same block after every case: cudaMalloc / cudaFree per
+    // call cost far more than the kernel once the process holds gigabytes of work space)
+    SubsBatch &B = subs_batch();
+    if ((long) n3 > B.cap_ps) { if (B.s_ps) cudaFree(B.s_ps); B.s_ps = nullptr; B.cap_ps = 0; CB_CUDA(cudaMalloc(&B.s_ps, sizeof(double) * n3)); B.cap_ps = (long) n3; }
+    if ((long) nt > B.cap_t) { if (B.s_t) cudaFree(B.s_t); B.s_t = nullptr; B.cap_t = 0; CB_CUDA(cudaMalloc(&B.s_t, sizeof(double) * nt)); B.cap_t = (long) nt; }
+    double *d_ps = B.s_ps, *d_t = B.s_t;
     CB_CUDA(cudaMemcpy(d_ps, ps, sizeof(double) * n3, cudaMemcpyHostToDevice));
     int rc = cb200_subsurf_batch_dev(handle, ncase, nz, z, gg1, gg2, poiss1, poiss2, d_ps, d_t, nullptr);
     if (!rc) { cudaError_t e = cudaMemcpy(table, d_t, sizeof(double) * nt, cudaMemcpyDeviceToHost); if (e != cudaSuccess) { last_error() = cudaGetErrorString(e); rc = -99; } }
-    cudaFree(d_ps); cudaFree(d_t);
     return rc;
 }
 
