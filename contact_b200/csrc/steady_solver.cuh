@@ -249,6 +249,290 @@ struct SteadyTab {
     { const double *r0 = reinterpret_cast<const double *>(cb_smem_window) + or0; const int o = dx + mx; c11 = r0[o]; c12 = r0[2 * mx + o]; c22 = r0[4 * mx + o]; }
 };
 
+// profiling counters of the element step (tools/steady_timing*.py): compiled in with -DCB_STEADY_PROF only -- six 64-bit counters and
+// four clock reads per element step cost the walking warp ~25 local-memory accesses per step (they do not fit its registers)
+#ifdef CB_STEADY_PROF
+#define CB_GS_PROF(...) __VA_ARGS__
+#else
+#define CB_GS_PROF(...)
+#endif
+
+// row-invariant state of a sweep for the warp that walks the rows
+struct GsWalk {
+    SteadySmem s;
+    SteadyTab T;
+    const SteadyArgs *a;
+    const double *xp, *psx, *psy;      // global memory: traction differences / tractions of the other rows (direct form, leading edge)
+    double *red;
+    double q00, q01, q11, l00, l01, l11;
+    int n, mx, my, ncon, nsp;
+    uint32_t mg_mx;
+    int convex, ledge;
+};
+
+// The Gauss-Seidel steps of grid row iy (contact elements k0..k1-1 of the compact list) and the compaction of the row's net changes
+// into list buffer `par`: called by warp 0 alone (register form) or by the whole CTA (DIRECT: block-wide row sum before every step).
+// A function of its own, not inlined: the walking warp's dependent instruction chain then gets the whole register file -- inside
+// stdygs_dev the register-resident U of the other warps (5 KMAX registers in every thread) pushed ~110 local-memory accesses per
+// element step into the chain (ncu source counters, profiles/steadygs_chain_r02e.txt).  Returns the updated sum of squared changes.
+template <bool DIRECT>
+__device__ __noinline__ double gs_walk_row(const GsWalk &w, const int iy, const int k0, const int k1, const int itgs, const int par,
+                                           double dsum, unsigned long long *tp)
+{
+    const SteadySmem s = w.s;
+    const SteadyTab T = w.T;
+    const SteadyArgs &a = *w.a;
+    const int n = w.n, mx = w.mx, my = w.my, ncon = w.ncon, nsp = w.nsp, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    const uint32_t mg_mx = w.mg_mx;
+    const unsigned full = 0xffffffffu;
+    const bool convex = w.convex != 0, ledge = w.ledge != 0;
+    const double *xp = w.xp, *psx = w.psx, *psy = w.psy;
+    double *red = w.red;
+    const double q00 = w.q00, q01 = w.q01, q11 = w.q11, l00 = w.l00, l01 = w.l01, l11 = w.l11;
+    (void) tp; (void) ncon; (void) nsp; (void) nt; (void) mg_mx; (void) xp; (void) red;
+    // rows of up to 96 elements: the row's own U and its accumulated net changes live in the registers of warp 0
+    // (lane l holds elements l, l + 32, l + 64) for the whole walk -- no shared-memory round trip per change
+    const bool rr3 = !DIRECT && mx <= 96;
+    double urx_[3] = { 0.0, 0.0, 0.0 }, ury_[3] = { 0.0, 0.0, 0.0 }, ddx_[3] = { 0.0, 0.0, 0.0 }, ddy_[3] = { 0.0, 0.0, 0.0 };
+    if (rr3) {
+#pragma unroll
+        for (int r = 0; r < 3; r++) { const int ixp = min(lane + 32 * r, mx - 1); urx_[r] = s.urx(ixp); ury_[r] = s.ury(ixp); }
+    }
+    for (int k = k0; k < k1; k++) {
+        if constexpr (DIRECT) {                    // whole CTA: row sum of element k over the contact list
+            const int ixd = s.cix(k - k0);
+            double us[2] = { 0.0, 0.0 };
+            const int *spl = a.isp + my + 2;
+            // batches of 6 pairs per thread with all loads of a batch in flight at once: the list, the tractions of the
+            // other rows and the coefficients come from L2 (two dependent round trips per pair otherwise)
+            for (int kk = tid; kk < nsp; kk += 6 * nt) {
+                int jj[6];
+#pragma unroll
+                for (int u = 0; u < 6; u++) jj[u] = (kk + u * nt < nsp) ? spl[kk + u * nt] : -1;
+                double qx[6], qy[6], c11[6], c12[6], c22[6];
+#pragma unroll
+                for (int u = 0; u < 6; u++) {
+                    const int j = jj[u] < 0 ? 0 : jj[u];
+                    const int jy = (int) fdiv((uint32_t) j, mg_mx), jx = j - jy * mx;
+                    const size_t o = (size_t) (iy - jy + a.cmy) * (2 * a.cmx) + (ixd - jx) + a.cmx;
+                    if (jy == iy) { qx[u] = convex ? s.psx(jx) : s.dpx(jx); qy[u] = convex ? s.psy(jx) : s.dpy(jx); }
+                    else { qx[u] = xp[j]; qy[u] = xp[n + j]; }
+                    c11[u] = a.cf11[o]; c12[u] = a.cf12[o]; c22[u] = a.cf22[o];
+                }
+#pragma unroll
+                for (int u = 0; u < 6; u++)
+                    if (jj[u] >= 0) { us[0] += c11[u] * qx[u] + c12[u] * qy[u]; us[1] += c12[u] * qx[u] + c22[u] * qy[u]; }
+            }
+            block_sum<2>(us, red);
+            if (tid == 0) { s.urx(ixd) = us[0] * a.ga_inv; s.ury(ixd) = us[1] * a.ga_inv; }
+            __syncthreads();
+        }
+        if (!DIRECT || tid < 32) {
+        CB_GS_PROF(const unsigned long long ta = clock64();)
+        const int ix = s.cix(k - k0);
+        int e = s.el(ix);
+        // cnvxgs :2626: after 1000 iterations the slip elements are skipped every other iteration
+        const bool active = (!convex || itgs <= 1000 || (itgs & 1) == 0 || e == EL_ADHES);
+        // run of adhesion elements directly to the left of ix (lanes look at ix-1, ix-2, ...): gives the
+        // element jx of the 2x2 matrix (stdygs :3010-3040) and the first window of the re-integration
+        int ej0 = -1, L0 = 0, jxs = ix - 1;
+        if (!convex) {
+            const int jj = ix - 1 - lane;
+            ej0 = (jj >= 0) ? s.el(jj) : -1;
+            const unsigned na = __ballot_sync(full, ej0 != EL_ADHES);
+            L0 = na ? __ffs(na) - 1 : 32;
+            jxs = ix - 1 - L0;
+            if (L0 == 32) { while (jxs > 0 && s.el(jxs) == EL_ADHES) jxs--; }
+            if (jxs < 0) jxs = 0;
+        }
+        // leading-edge element (ii2j > 0): the shift is A_cs p_t - ubnd instead of A_csv p_t (:2654-2658); the
+        // row sum over the contact list is taken by the warp -- this row from shared memory, the others
+        // from the tractions in global memory, which are current after every row
+        const bool zl = ledge && active && a.facdt[iy * mx + ix] < 0.9999;
+        double lsx = 0.0, lsy = 0.0;
+        if (zl) {
+            for (int kk = lane; kk < ncon; kk += 32) {
+                const int jj = a.iel[kk], jy = jj / mx, jx = jj - jy * mx;
+                const size_t o = (size_t) (iy - jy + a.cmy) * (2 * a.cmx) + (ix - jx) + a.cmx;
+                const double qx = (jy == iy) ? s.psx(jx) : psx[jj], qy = (jy == iy) ? s.psy(jx) : psy[jj];
+                const double c12 = a.cs12[o];
+                lsx += a.cs11[o] * qx + c12 * qy; lsy += c12 * qx + a.cs22[o] * qy;
+            }
+            for (int o = 16; o > 0; o >>= 1) { lsx += __shfl_xor_sync(full, lsx, o); lsy += __shfl_xor_sync(full, lsy, o); }
+            lsx *= a.ga_inv; lsy *= a.ga_inv;
+        }
+        double px = 0.0, py = 0.0;
+        double ucx, ucy;                                // U of this element
+        if (rr3) {
+            const int rq = ix >> 5;
+            const double vx = rq == 0 ? urx_[0] : (rq == 1 ? urx_[1] : urx_[2]), vy = rq == 0 ? ury_[0] : (rq == 1 ? ury_[1] : ury_[2]);
+            ucx = __shfl_sync(full, vx, ix & 31); ucy = __shfl_sync(full, vy, ix & 31);
+        } else { ucx = s.urx(ix); ucy = s.ury(ix); }
+        if (lane == 0) {
+            s.ictl(0, my) = 0;
+            if (active) {
+                double c00, c01, c11;
+                if (zl) { c00 = l00; c01 = l01; c11 = l11; }
+                else if (convex) { c00 = q00; c01 = q01; c11 = q11; }   // cnvxgs: coefs / coefsv, :2519-2541
+                else {                                              // stdygs: c(0) - c(jx - ix), :3010-3040
+                    double t00, t01, t11;
+                    T.row0(jxs - ix, t00, t01, t11);
+                    c00 = q00 - t00; c01 = q01 - t01; c11 = q11 - t11;
+                }
+                double sx = s.wsx(ix) + ucx, sy = s.wsy(ix) + ucy;
+                if (zl) {
+                    int ixb = ix;
+                    while (ixb < mx - 1 && s.el(ixb + 1) >= 1) ixb++;
+                    sx = s.wsx(ix) + lsx - a.ub[iy * mx + ixb]; sy = s.wsy(ix) + lsy - a.ub[n + iy * mx + ixb];
+                }
+                const double pox = s.psx(ix), poy = s.psy(ix);
+                px = pox; py = poy;
+                plstrc_dev(e, c00, c01, c01, c11, a.eps, a.omegah, a.omegas, px, py, s.bnd(ix), sx, sy);
+                const double ex = px - pox, ey = py - poy;
+                dsum += ex * ex + ey * ey;
+                if (ex != 0.0 || ey != 0.0) { s.chj(0) = ix; s.chx(0) = ex; s.chy(0) = ey; s.ictl(0, my) = 1; }
+                s.psx(ix) = px; s.psy(ix) = py; s.ssx(ix) = sx; s.ssy(ix) = sy; s.el(ix) = e;
+                if (!convex) { s.dpx(ix) += ex; s.dpy(ix) += ey; }
+            }
+        }
+        CB_GS_PROF(const unsigned long long tb = clock64();)
+        __syncwarp();
+        if (!convex && active) {
+            // re-integrate dp -> ps to the left (:3089-3126) with a warp scan: lanes 0.. take the elements
+            // ix-1, ix-2, ...; the chain of adhesion elements follows the new traction, it ends at the
+            // first element that does not change, at a clamped element or at the first non-adhesion element
+            double rx = __shfl_sync(full, px, 0), ry = __shfl_sync(full, py, 0);
+            int jj0 = ix - 1;
+            bool done = false, first = true;
+            while (!done && jj0 >= 0) {
+                const int jj = jj0 - lane;
+                int ej, L;
+                if (first) { ej = ej0; L = L0; first = false; }
+                else {
+                    ej = (jj >= 0) ? s.el(jj) : -1;
+                    const unsigned notadh = __ballot_sync(full, ej != EL_ADHES);
+                    L = notadh ? __ffs(notadh) - 1 : 32;
+                }
+                double ax = (lane < L) ? s.dpx(jj) : 0.0, ay = (lane < L) ? s.dpy(jj) : 0.0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double tx = __shfl_up_sync(full, ax, o), ty = __shfl_up_sync(full, ay, o);
+                    if (lane >= o) { ax += tx; ay += ty; }
+                }
+                double nx = rx + ax, ny = ry + ay;
+                const double pb = (lane < L) ? fmin(s.bnd(jj), 1e20) : 0.0;
+                const bool clamp = lane < L && (nx * nx + ny * ny > pb * pb);
+                const unsigned cm = __ballot_sync(full, clamp);
+                const int Lc = cm ? __ffs(cm) - 1 : L;              // lanes < Lc keep the scanned values
+                const bool same = lane < Lc && nx == s.psx(jj) && ny == s.psy(jj);
+                const unsigned smk = __ballot_sync(full, same);
+                const int Ls = smk ? __ffs(smk) - 1 : 32;
+                if (lane < Lc && lane <= Ls) { s.psx(jj) = nx; s.psy(jj) = ny; }
+                if (Ls < Lc) { done = true; break; }
+                // traction of the element to the right of lane Lc
+                const int src = Lc > 0 ? Lc - 1 : 0;
+                const double qx = __shfl_sync(full, nx, src), qy = __shfl_sync(full, ny, src);
+                const double prx = Lc > 0 ? qx : rx, pry = Lc > 0 ? qy : ry;
+                if (Lc < L) {                                       // lane Lc: adhesion element beyond its bound
+                    double cxn = 0.0, cyn = 0.0;
+                    int stop = 0;
+                    if (lane == Lc) {
+                        double mx_ = prx + s.dpx(jj), my_ = pry + s.dpy(jj);
+                        const double t = pb / sqrt(mx_ * mx_ + my_ * my_);
+                        mx_ *= t; my_ *= t;
+                        const double ndx = mx_ - prx, ndy = my_ - pry;
+                        const int c = s.ictl(0, my);
+                        s.chj(c) = jj; s.chx(c) = ndx - s.dpx(jj); s.chy(c) = ndy - s.dpy(jj); s.ictl(0, my) = c + 1;
+                        s.dpx(jj) = ndx; s.dpy(jj) = ndy;
+                        stop = (mx_ == s.psx(jj) && my_ == s.psy(jj));
+                        s.psx(jj) = mx_; s.psy(jj) = my_;
+                        cxn = mx_; cyn = my_;
+                    }
+                    rx = __shfl_sync(full, cxn, Lc); ry = __shfl_sync(full, cyn, Lc);
+                    done = __shfl_sync(full, stop, Lc) != 0;
+                    jj0 -= Lc + 1;
+                    __syncwarp();
+                } else if (L < 32) {                                // lane L: the chain's terminator
+                    if (lane == L && jj >= 0) {
+                        double ndx, ndy;
+                        bool upd = true;
+                        if (ej >= EL_SLIP) { ndx = s.psx(jj) - prx; ndy = s.psy(jj) - pry; }
+                        else if (s.el(jj + 1) >= EL_ADHES) { ndx = -prx; ndy = -pry; }
+                        else { upd = false; ndx = 0.0; ndy = 0.0; }
+                        if (upd) {
+                            const double cx = ndx - s.dpx(jj), cy = ndy - s.dpy(jj);
+                            if (cx != 0.0 || cy != 0.0) { const int c = s.ictl(0, my); s.chj(c) = jj; s.chx(c) = cx; s.chy(c) = cy; s.ictl(0, my) = c + 1; }
+                            s.dpx(jj) = ndx; s.dpy(jj) = ndy;
+                        }
+                    }
+                    done = true;
+                } else {                                            // 32 adhesion elements done, next window
+                    rx = __shfl_sync(full, nx, 31); ry = __shfl_sync(full, ny, 31);
+                    jj0 -= 32;
+                    __syncwarp();
+                }
+            }
+            __syncwarp();
+        }
+        CB_GS_PROF(const unsigned long long tc = clock64();)
+        // in-row rank-1 updates: keep the displacement differences of this row current, accumulate the net
+        // change of the row for the other rows
+        const int nch = DIRECT ? 0 : s.ictl(0, my);
+        for (int c = 0; c < nch; c++) {
+            const int jx = s.chj(c);
+            const double ex = s.chx(c), ey = s.chy(c);
+            if (rr3) {
+                double c11[3], c12[3], c22[3];
+#pragma unroll
+                for (int r = 0; r < 3; r++) T.row0(min(lane + 32 * r, mx - 1) - jx, c11[r], c12[r], c22[r]);
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    urx_[r] = urx_[r] + (c11[r] * ex + c12[r] * ey); ury_[r] = ury_[r] + (c12[r] * ex + c22[r] * ey);
+                    if (lane + 32 * r == jx) { ddx_[r] += ex; ddy_[r] += ey; }
+                }
+                continue;
+            }
+            if (lane == 0) { s.ddx(jx) += ex; s.ddy(jx) += ey; }
+            for (int base = 0; base < mx; base += 96) {             // 3 elements per lane, loads first; the
+                double c11[3], c12[3], c22[3], u0[3], u1[3];        // exterior elements are updated too (unused)
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    const int ixp = min(base + lane + 32 * r, mx - 1);
+                    T.row0(ixp - jx, c11[r], c12[r], c22[r]); u0[r] = s.urx(ixp); u1[r] = s.ury(ixp);
+                }
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    const int ixp = base + lane + 32 * r;
+                    if (ixp < mx) { s.urx(ixp) = u0[r] + (c11[r] * ex + c12[r] * ey); s.ury(ixp) = u1[r] + (c12[r] * ex + c22[r] * ey); }
+                }
+            }
+        }
+        __syncwarp();
+        CB_GS_PROF(if (lane == 0) { const unsigned long long td = clock64(); tp[1] += tb - ta; tp[2] += tc - tb; tp[3] += td - tc; tp[5] += nch; })
+        }
+        if constexpr (DIRECT) __syncthreads();     // the row arrays changed by warp 0 feed the next row sum
+    }
+    if (rr3) {                                      // the row's U back to shared memory for its owners
+#pragma unroll
+        for (int r = 0; r < 3; r++) { const int ixp = lane + 32 * r; if (ixp < mx) { s.urx(ixp) = urx_[r]; s.ury(ixp) = ury_[r]; } }
+    }
+    // compact the net changes of this row for the update of the other rows
+    int cnt = 0;
+    if (!DIRECT)
+    for (int base = 0; base < mx; base += 32) {
+        const int jx = base + lane;
+        const int rb = base >> 5;
+        const double dxr = rb == 0 ? ddx_[0] : (rb == 1 ? ddx_[1] : ddx_[2]), dyr = rb == 0 ? ddy_[0] : (rb == 1 ? ddy_[1] : ddy_[2]);
+        const double ex = jx < mx ? (rr3 ? dxr : s.ddx(jx)) : 0.0, ey = jx < mx ? (rr3 ? dyr : s.ddy(jx)) : 0.0;
+        const bool nz = (ex != 0.0 || ey != 0.0);
+        const unsigned mk = __ballot_sync(full, nz);
+        if (nz) { const int pos = cnt + __popc(mk & ((1u << lane) - 1u)); s.lj(par, pos) = jx; s.lx(par, pos) = ex; s.ly(par, pos) = ey; }
+        cnt += __popc(mk);
+    }
+    if (!DIRECT && lane == 0) { s.lcnt(par) = cnt; CB_GS_PROF(tp[6] += cnt;) }
+    return dsum;
+}
+
 // Gauss-Seidel sweeps of stdygs (convex = 0) or cnvxgs (convex = 1): returns info (0 ok, 1 maxgs reached,
 // 2 stagnation, 3 divergence).  All threads of the CTA must call.
 //
@@ -391,7 +675,12 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
 
     int itgs = 0;
     double dif = 2.0, difid = 1.0, dif1 = 0.0;
-    unsigned long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0, tp4 = 0, tp5 = 0, tp6 = 0;
+#ifdef CB_STEADY_PROF
+    unsigned long long tpw_[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, *tpw = tpw_;
+#else
+    unsigned long long *tpw = nullptr;
+#endif
+    unsigned long long nstep = 0;                              // element steps of this call (thread 0)
     // leading-edge elements: 2x2 matrix of cs (coefs instead of coefsv, :2665-2669)
     const bool ledge = convex && a.ledge != 0;
     const size_t oc = (size_t) a.cmy * (2 * a.cmx) + a.cmx;
@@ -449,8 +738,13 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
             }
         }
     };
+    GsWalk w;                                                  // what the walking warp needs (gs_walk_row)
+    w.s = s; w.T = T; w.a = &a; w.xp = xp; w.psx = psx; w.psy = psy; w.red = red;
+    w.q00 = q00; w.q01 = q01; w.q11 = q11; w.l00 = l00; w.l01 = l01; w.l11 = l11;
+    w.n = n; w.mx = mx; w.my = my; w.ncon = ncon; w.nsp = nsp; w.mg_mx = mg_mx; w.convex = convex ? 1 : 0; w.ledge = ledge ? 1 : 0;
     while (dif >= difid && itgs < a.maxgs) {
         itgs++;
+        nstep += ncon;
         // work accounting: a sweep is 2 ncon row sums over (ncon + 2 my) 2 columns in the reference
         if (threadIdx.x == 0) atomicAdd(&g_work[3], (unsigned long long) ncon * (unsigned long long) (ncon + 2 * P.my));
         double dsum = 0.0;                                     // lane 0 of warp 0 only
@@ -496,235 +790,7 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
             __syncthreads();
 
             if (DIRECT || tid < 32) {                          // ---- warp 0: the Gauss-Seidel steps of this row ----
-                // rows of up to 96 elements: the row's own U and its accumulated net changes live in the registers of warp 0
-                // (lane l holds elements l, l + 32, l + 64) for the whole walk -- no shared-memory round trip per change
-                const bool rr3 = !DIRECT && mx <= 96;
-                double urx_[3] = { 0.0, 0.0, 0.0 }, ury_[3] = { 0.0, 0.0, 0.0 }, ddx_[3] = { 0.0, 0.0, 0.0 }, ddy_[3] = { 0.0, 0.0, 0.0 };
-                if (rr3) {
-#pragma unroll
-                    for (int r = 0; r < 3; r++) { const int ixp = min(lane + 32 * r, mx - 1); urx_[r] = s.urx(ixp); ury_[r] = s.ury(ixp); }
-                }
-                for (int k = k0; k < k1; k++) {
-                    if constexpr (DIRECT) {                    // whole CTA: row sum of element k over the contact list
-                        const int ixd = s.cix(k - k0);
-                        double us[2] = { 0.0, 0.0 };
-                        const int *spl = a.isp + my + 2;
-                        for (int kk = tid; kk < nsp; kk += nt) {
-                            const int jj = spl[kk], jy = (int) fdiv((uint32_t) jj, mg_mx), jx = jj - jy * mx;
-                            const size_t o = (size_t) (iy - jy + a.cmy) * (2 * a.cmx) + (ixd - jx) + a.cmx;
-                            double qx, qy;
-                            if (jy == iy) { qx = convex ? s.psx(jx) : s.dpx(jx); qy = convex ? s.psy(jx) : s.dpy(jx); }
-                            else { qx = xp[jj]; qy = xp[n + jj]; }
-                            const double c12 = a.cf12[o];
-                            us[0] += a.cf11[o] * qx + c12 * qy; us[1] += c12 * qx + a.cf22[o] * qy;
-                        }
-                        block_sum<2>(us, red);
-                        if (tid == 0) { s.urx(ixd) = us[0] * a.ga_inv; s.ury(ixd) = us[1] * a.ga_inv; }
-                        __syncthreads();
-                    }
-                    if (!DIRECT || tid < 32) {
-                    const unsigned long long ta = clock64();
-                    const int ix = s.cix(k - k0);
-                    int e = s.el(ix);
-                    // cnvxgs :2626: after 1000 iterations the slip elements are skipped every other iteration
-                    const bool active = (!convex || itgs <= 1000 || (itgs & 1) == 0 || e == EL_ADHES);
-                    // run of adhesion elements directly to the left of ix (lanes look at ix-1, ix-2, ...): gives the
-                    // element jx of the 2x2 matrix (stdygs :3010-3040) and the first window of the re-integration
-                    int ej0 = -1, L0 = 0, jxs = ix - 1;
-                    if (!convex) {
-                        const int jj = ix - 1 - lane;
-                        ej0 = (jj >= 0) ? s.el(jj) : -1;
-                        const unsigned na = __ballot_sync(full, ej0 != EL_ADHES);
-                        L0 = na ? __ffs(na) - 1 : 32;
-                        jxs = ix - 1 - L0;
-                        if (L0 == 32) { while (jxs > 0 && s.el(jxs) == EL_ADHES) jxs--; }
-                        if (jxs < 0) jxs = 0;
-                    }
-                    // leading-edge element (ii2j > 0): the shift is A_cs p_t - ubnd instead of A_csv p_t (:2654-2658); the
-                    // row sum over the contact list is taken by the warp -- this row from shared memory, the others
-                    // from the tractions in global memory, which are current after every row
-                    const bool zl = ledge && active && a.facdt[iy * mx + ix] < 0.9999;
-                    double lsx = 0.0, lsy = 0.0;
-                    if (zl) {
-                        for (int kk = lane; kk < ncon; kk += 32) {
-                            const int jj = a.iel[kk], jy = jj / mx, jx = jj - jy * mx;
-                            const size_t o = (size_t) (iy - jy + a.cmy) * (2 * a.cmx) + (ix - jx) + a.cmx;
-                            const double qx = (jy == iy) ? s.psx(jx) : psx[jj], qy = (jy == iy) ? s.psy(jx) : psy[jj];
-                            const double c12 = a.cs12[o];
-                            lsx += a.cs11[o] * qx + c12 * qy; lsy += c12 * qx + a.cs22[o] * qy;
-                        }
-                        for (int o = 16; o > 0; o >>= 1) { lsx += __shfl_xor_sync(full, lsx, o); lsy += __shfl_xor_sync(full, lsy, o); }
-                        lsx *= a.ga_inv; lsy *= a.ga_inv;
-                    }
-                    double px = 0.0, py = 0.0;
-                    double ucx, ucy;                                // U of this element
-                    if (rr3) {
-                        const int rq = ix >> 5;
-                        const double vx = rq == 0 ? urx_[0] : (rq == 1 ? urx_[1] : urx_[2]), vy = rq == 0 ? ury_[0] : (rq == 1 ? ury_[1] : ury_[2]);
-                        ucx = __shfl_sync(full, vx, ix & 31); ucy = __shfl_sync(full, vy, ix & 31);
-                    } else { ucx = s.urx(ix); ucy = s.ury(ix); }
-                    if (lane == 0) {
-                        s.ictl(0, my) = 0;
-                        if (active) {
-                            double c00, c01, c11;
-                            if (zl) { c00 = l00; c01 = l01; c11 = l11; }
-                            else if (convex) { c00 = q00; c01 = q01; c11 = q11; }   // cnvxgs: coefs / coefsv, :2519-2541
-                            else {                                              // stdygs: c(0) - c(jx - ix), :3010-3040
-                                double t00, t01, t11;
-                                T.row0(jxs - ix, t00, t01, t11);
-                                c00 = q00 - t00; c01 = q01 - t01; c11 = q11 - t11;
-                            }
-                            double sx = s.wsx(ix) + ucx, sy = s.wsy(ix) + ucy;
-                            if (zl) {
-                                int ixb = ix;
-                                while (ixb < mx - 1 && s.el(ixb + 1) >= 1) ixb++;
-                                sx = s.wsx(ix) + lsx - a.ub[iy * mx + ixb]; sy = s.wsy(ix) + lsy - a.ub[n + iy * mx + ixb];
-                            }
-                            const double pox = s.psx(ix), poy = s.psy(ix);
-                            px = pox; py = poy;
-                            plstrc_dev(e, c00, c01, c01, c11, a.eps, a.omegah, a.omegas, px, py, s.bnd(ix), sx, sy);
-                            const double ex = px - pox, ey = py - poy;
-                            dsum += ex * ex + ey * ey;
-                            if (ex != 0.0 || ey != 0.0) { s.chj(0) = ix; s.chx(0) = ex; s.chy(0) = ey; s.ictl(0, my) = 1; }
-                            s.psx(ix) = px; s.psy(ix) = py; s.ssx(ix) = sx; s.ssy(ix) = sy; s.el(ix) = e;
-                            if (!convex) { s.dpx(ix) += ex; s.dpy(ix) += ey; }
-                        }
-                    }
-                    const unsigned long long tb = clock64();
-                    __syncwarp();
-                    if (!convex && active) {
-                        // re-integrate dp -> ps to the left (:3089-3126) with a warp scan: lanes 0.. take the elements
-                        // ix-1, ix-2, ...; the chain of adhesion elements follows the new traction, it ends at the
-                        // first element that does not change, at a clamped element or at the first non-adhesion element
-                        double rx = __shfl_sync(full, px, 0), ry = __shfl_sync(full, py, 0);
-                        int jj0 = ix - 1;
-                        bool done = false, first = true;
-                        while (!done && jj0 >= 0) {
-                            const int jj = jj0 - lane;
-                            int ej, L;
-                            if (first) { ej = ej0; L = L0; first = false; }
-                            else {
-                                ej = (jj >= 0) ? s.el(jj) : -1;
-                                const unsigned notadh = __ballot_sync(full, ej != EL_ADHES);
-                                L = notadh ? __ffs(notadh) - 1 : 32;
-                            }
-                            double ax = (lane < L) ? s.dpx(jj) : 0.0, ay = (lane < L) ? s.dpy(jj) : 0.0;
-#pragma unroll
-                            for (int o = 1; o < 32; o <<= 1) {
-                                const double tx = __shfl_up_sync(full, ax, o), ty = __shfl_up_sync(full, ay, o);
-                                if (lane >= o) { ax += tx; ay += ty; }
-                            }
-                            double nx = rx + ax, ny = ry + ay;
-                            const double pb = (lane < L) ? fmin(s.bnd(jj), 1e20) : 0.0;
-                            const bool clamp = lane < L && (nx * nx + ny * ny > pb * pb);
-                            const unsigned cm = __ballot_sync(full, clamp);
-                            const int Lc = cm ? __ffs(cm) - 1 : L;              // lanes < Lc keep the scanned values
-                            const bool same = lane < Lc && nx == s.psx(jj) && ny == s.psy(jj);
-                            const unsigned smk = __ballot_sync(full, same);
-                            const int Ls = smk ? __ffs(smk) - 1 : 32;
-                            if (lane < Lc && lane <= Ls) { s.psx(jj) = nx; s.psy(jj) = ny; }
-                            if (Ls < Lc) { done = true; break; }
-                            // traction of the element to the right of lane Lc
-                            const int src = Lc > 0 ? Lc - 1 : 0;
-                            const double qx = __shfl_sync(full, nx, src), qy = __shfl_sync(full, ny, src);
-                            const double prx = Lc > 0 ? qx : rx, pry = Lc > 0 ? qy : ry;
-                            if (Lc < L) {                                       // lane Lc: adhesion element beyond its bound
-                                double cxn = 0.0, cyn = 0.0;
-                                int stop = 0;
-                                if (lane == Lc) {
-                                    double mx_ = prx + s.dpx(jj), my_ = pry + s.dpy(jj);
-                                    const double t = pb / sqrt(mx_ * mx_ + my_ * my_);
-                                    mx_ *= t; my_ *= t;
-                                    const double ndx = mx_ - prx, ndy = my_ - pry;
-                                    const int c = s.ictl(0, my);
-                                    s.chj(c) = jj; s.chx(c) = ndx - s.dpx(jj); s.chy(c) = ndy - s.dpy(jj); s.ictl(0, my) = c + 1;
-                                    s.dpx(jj) = ndx; s.dpy(jj) = ndy;
-                                    stop = (mx_ == s.psx(jj) && my_ == s.psy(jj));
-                                    s.psx(jj) = mx_; s.psy(jj) = my_;
-                                    cxn = mx_; cyn = my_;
-                                }
-                                rx = __shfl_sync(full, cxn, Lc); ry = __shfl_sync(full, cyn, Lc);
-                                done = __shfl_sync(full, stop, Lc) != 0;
-                                jj0 -= Lc + 1;
-                                __syncwarp();
-                            } else if (L < 32) {                                // lane L: the chain's terminator
-                                if (lane == L && jj >= 0) {
-                                    double ndx, ndy;
-                                    bool upd = true;
-                                    if (ej >= EL_SLIP) { ndx = s.psx(jj) - prx; ndy = s.psy(jj) - pry; }
-                                    else if (s.el(jj + 1) >= EL_ADHES) { ndx = -prx; ndy = -pry; }
-                                    else { upd = false; ndx = 0.0; ndy = 0.0; }
-                                    if (upd) {
-                                        const double cx = ndx - s.dpx(jj), cy = ndy - s.dpy(jj);
-                                        if (cx != 0.0 || cy != 0.0) { const int c = s.ictl(0, my); s.chj(c) = jj; s.chx(c) = cx; s.chy(c) = cy; s.ictl(0, my) = c + 1; }
-                                        s.dpx(jj) = ndx; s.dpy(jj) = ndy;
-                                    }
-                                }
-                                done = true;
-                            } else {                                            // 32 adhesion elements done, next window
-                                rx = __shfl_sync(full, nx, 31); ry = __shfl_sync(full, ny, 31);
-                                jj0 -= 32;
-                                __syncwarp();
-                            }
-                        }
-                        __syncwarp();
-                    }
-                    const unsigned long long tc = clock64();
-                    // in-row rank-1 updates: keep the displacement differences of this row current, accumulate the net
-                    // change of the row for the other rows
-                    const int nch = DIRECT ? 0 : s.ictl(0, my);
-                    for (int c = 0; c < nch; c++) {
-                        const int jx = s.chj(c);
-                        const double ex = s.chx(c), ey = s.chy(c);
-                        if (rr3) {
-                            double c11[3], c12[3], c22[3];
-#pragma unroll
-                            for (int r = 0; r < 3; r++) T.row0(min(lane + 32 * r, mx - 1) - jx, c11[r], c12[r], c22[r]);
-#pragma unroll
-                            for (int r = 0; r < 3; r++) {
-                                urx_[r] = urx_[r] + (c11[r] * ex + c12[r] * ey); ury_[r] = ury_[r] + (c12[r] * ex + c22[r] * ey);
-                                if (lane + 32 * r == jx) { ddx_[r] += ex; ddy_[r] += ey; }
-                            }
-                            continue;
-                        }
-                        if (lane == 0) { s.ddx(jx) += ex; s.ddy(jx) += ey; }
-                        for (int base = 0; base < mx; base += 96) {             // 3 elements per lane, loads first; the
-                            double c11[3], c12[3], c22[3], u0[3], u1[3];        // exterior elements are updated too (unused)
-#pragma unroll
-                            for (int r = 0; r < 3; r++) {
-                                const int ixp = min(base + lane + 32 * r, mx - 1);
-                                T.row0(ixp - jx, c11[r], c12[r], c22[r]); u0[r] = s.urx(ixp); u1[r] = s.ury(ixp);
-                            }
-#pragma unroll
-                            for (int r = 0; r < 3; r++) {
-                                const int ixp = base + lane + 32 * r;
-                                if (ixp < mx) { s.urx(ixp) = u0[r] + (c11[r] * ex + c12[r] * ey); s.ury(ixp) = u1[r] + (c12[r] * ex + c22[r] * ey); }
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    if (lane == 0) { const unsigned long long td = clock64(); tp0++; tp1 += tb - ta; tp2 += tc - tb; tp3 += td - tc; tp5 += nch; }
-                    }
-                    if constexpr (DIRECT) __syncthreads();     // the row arrays changed by warp 0 feed the next row sum
-                }
-                if (rr3) {                                      // the row's U back to shared memory for its owners
-#pragma unroll
-                    for (int r = 0; r < 3; r++) { const int ixp = lane + 32 * r; if (ixp < mx) { s.urx(ixp) = urx_[r]; s.ury(ixp) = ury_[r]; } }
-                }
-                // compact the net changes of this row for the update of the other rows
-                int cnt = 0;
-                if (!DIRECT)
-                for (int base = 0; base < mx; base += 32) {
-                    const int jx = base + lane;
-                    const int rb = base >> 5;
-                    const double dxr = rb == 0 ? ddx_[0] : (rb == 1 ? ddx_[1] : ddx_[2]), dyr = rb == 0 ? ddy_[0] : (rb == 1 ? ddy_[1] : ddy_[2]);
-                    const double ex = jx < mx ? (rr3 ? dxr : s.ddx(jx)) : 0.0, ey = jx < mx ? (rr3 ? dyr : s.ddy(jx)) : 0.0;
-                    const bool nz = (ex != 0.0 || ey != 0.0);
-                    const unsigned mk = __ballot_sync(full, nz);
-                    if (nz) { const int pos = cnt + __popc(mk & ((1u << lane) - 1u)); s.lj(par, pos) = jx; s.lx(par, pos) = ex; s.ly(par, pos) = ey; }
-                    cnt += __popc(mk);
-                }
-                if (!DIRECT && lane == 0) { s.lcnt(par) = cnt; tp6 += cnt; }
+                dsum = gs_walk_row<DIRECT>(w, iy, k0, k1, itgs, par, dsum, tpw);
             } else if (pend_row >= 0) {
                 // ---- warps 1.. meanwhile: the net change of the PREVIOUS row goes to the elements of all other rows.  This pass is
                 // shared-memory-bandwidth bound (three table entries per pair), the chain of warp 0 is latency bound: they overlap.
@@ -735,7 +801,7 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
 
             // ---- whole CTA: the net change of row iy goes to the NEXT row with contact only (it is staged next); all other rows
             // receive it while warp 0 walks that next row ----
-            const unsigned long long te = clock64();
+            CB_GS_PROF(const unsigned long long te = clock64();)
             if constexpr (!DIRECT) {
                 int nx = iy;
                 do { nx = (nx + 1 == my) ? 0 : nx + 1; } while (nx != iy && s.rowk(nx + 1) == s.rowk(nx));
@@ -751,7 +817,7 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
                 if (!convex) { a.dp[ii] = s.dpx(jx); a.dp[n + ii] = s.dpy(jx); }
                 ss[ii] = s.ssx(jx); ss[n + ii] = s.ssy(jx); el[ii] = s.el(jx);
             }
-            if (tid == 0) tp4 += clock64() - te;
+            CB_GS_PROF(if (tid == 0) tpw[4] += clock64() - te;)
             __syncthreads();
         }
         if (tid == 0) s.scal(2) = dsum;
@@ -771,9 +837,9 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
     if (itgs >= a.maxgs && conv > 1.0) info = 3;
     itgs_out = itgs; err_out = dif;
     if (tid == 0) {
-        atomicAdd(&g_steady_prof[0], tp0); atomicAdd(&g_steady_prof[1], tp1); atomicAdd(&g_steady_prof[2], tp2);
-        atomicAdd(&g_steady_prof[3], tp3); atomicAdd(&g_steady_prof[4], 1ull); atomicAdd(&g_steady_prof[5], tp4);
-        atomicAdd(&g_steady_prof[6], tp5); atomicAdd(&g_steady_prof[7], tp6);
+        atomicAdd(&g_steady_prof[0], nstep); atomicAdd(&g_steady_prof[4], 1ull);
+        CB_GS_PROF(atomicAdd(&g_steady_prof[1], tpw[1]); atomicAdd(&g_steady_prof[2], tpw[2]); atomicAdd(&g_steady_prof[3], tpw[3]);
+                   atomicAdd(&g_steady_prof[5], tpw[4]); atomicAdd(&g_steady_prof[6], tpw[5]); atomicAdd(&g_steady_prof[7], tpw[6]);)
     }
     __syncthreads();
     return info;
