@@ -272,11 +272,9 @@ struct GsWalk {
 
 // The Gauss-Seidel steps of grid row iy (contact elements k0..k1-1 of the compact list) and the compaction of the row's net changes
 // into list buffer `par`: called by warp 0 alone (register form) or by the whole CTA (DIRECT: block-wide row sum before every step).
-// A function of its own, not inlined: the walking warp's dependent instruction chain then gets the whole register file -- inside
-// stdygs_dev the register-resident U of the other warps (5 KMAX registers in every thread) pushed ~110 local-memory accesses per
-// element step into the chain (ncu source counters, profiles/steadygs_chain_r02e.txt).  Returns the updated sum of squared changes.
+// Inlined into the WALKER / DIRECT instantiations of gs_sweeps (see there).  Returns the updated sum of squared changes.
 template <bool DIRECT>
-__device__ __noinline__ double gs_walk_row(const GsWalk &w, const int iy, const int k0, const int k1, const int itgs, const int par,
+__device__ __forceinline__ double gs_walk_row(const GsWalk &w, const int iy, const int k0, const int k1, const int itgs, const int par,
                                            double dsum, unsigned long long *tp)
 {
     const SteadySmem s = w.s;
@@ -533,128 +531,46 @@ __device__ __noinline__ double gs_walk_row(const GsWalk &w, const int iy, const 
     return dsum;
 }
 
-// Gauss-Seidel sweeps of stdygs (convex = 0) or cnvxgs (convex = 1): returns info (0 ok, 1 maxgs reached,
-// 2 stagnation, 3 divergence).  All threads of the CTA must call.
-//
-// Row-blocked organisation: the elements of one grid row are processed by warp 0 alone -- lane 0 runs the scalar
-// per-element solve, all 32 lanes keep the row's own displacement differences up to date and re-integrate the row
-// with a warp scan -- while the net change of the row is applied to the register-resident U of all other rows once
-// per row by the whole CTA.
-//
-// DIRECT = true: the form for contact areas that do not fit the register-resident U (more than 22 x 352 elements, or a grid on
-// the whole-GPU path).  No U is kept: before every element step the whole CTA evaluates the reference's row sum
-// U_i = (1/G) sum_j A(i - j) xp_j over the compact contact list (gf3_AijPj, m_aijpj.f90:99-254; the current row from shared
-// memory, the other rows from global memory / L2, coefficients from the spatial blocks in L2), then warp 0 performs the
-// element step exactly as in the register form.  No rank-1 updates, no FFT products, no coefficient table in shared
-// memory: O(ncon) work per element like the reference, any grid size.  `sbase`: shared memory for the row arrays
-// (steady_fixed_bytes), used instead of the plan's layout.
-template <int KMAX, bool DIRECT = false>
-__device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const SteadyArgs &a, int *el, double *ps, double *ss,
-                          int ncon, int &itgs_out, double &err_out, int &nprod, unsigned char *sbase = nullptr)
+// what the sweeps need from the set-up in stdygs_dev, and their results (identical in all threads)
+struct GsSweep {
+    const ConvPlan *P;
+    const SteadyArgs *a;
+    SteadySmem s;
+    SteadyTab T;
+    int *el;
+    double *ps, *ss, *red;
+    const double *xp;
+    int ncon, nsp;
+    double facnel;
+    int itgs;
+    double dif, dif1;
+};
+
+// The sweeps themselves, in three roles with the same barrier sequence:
+//   WALKER (warp 0 of the register form): walks the rows (gs_walk_row), owns no contact elements -- an instantiation of its own so
+//          that the dependent instruction chain of the walk has the whole register file (inside one function with the owners the
+//          chain made ~110 local-memory accesses per element step: the row's U and the counters did not fit beside 5 KMAX registers
+//          of register-resident U that warp 0 never uses);
+//   owner  (warps 1.., register form): KMAX contact elements per thread with their U in registers, rank-1 updates by apply_list;
+//   DIRECT (whole CTA): no U, block-wide row sum before every element step.
+template <int KMAX, bool DIRECT, bool WALKER>
+__device__ __noinline__ void gs_sweeps(GsSweep &g)
 {
+    constexpr bool OWN = !DIRECT && !WALKER;
+    const ConvPlan &P = *g.P;
+    const SteadyArgs &a = *g.a;
+    const SteadySmem s = g.s;
+    const SteadyTab T = g.T;
+    int *el = g.el;
+    double *ps = g.ps, *ss = g.ss, *red = g.red;
+    const double *xp = g.xp;
+    const int ncon = g.ncon, nsp = g.nsp;
+    const double facnel = g.facnel;
     const int n = P.npot, mx = P.mx, my = P.my, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
     const unsigned full = 0xffffffffu;
     double *psx = ps, *psy = ps + n, *psn = ps + 2 * (size_t) n;
-    double *red = sm.red;
-
-    // SteadyGS: traction differences along the rolling direction (x ascending = towards the leading edge), :2900-2915;
-    // ConvexGS works on the tractions themselves
     const bool convex = a.convex != 0;
-    const double *xp = convex ? ps : a.dp;
-    if (!convex) {
-        for (int i = tid; i < n; i += nt) {
-            const int ix = i % mx;
-            a.dp[i] = (ix != mx - 1) ? psx[i] - psx[i + 1] : psx[i];
-            a.dp[n + i] = (ix != mx - 1) ? psy[i] - psy[i + 1] : psy[i];
-        }
-    }
-    __syncthreads();
-    const double facnel = (double) sqrtf(__fdiv_rn((float) n, (float) ncon));
-
-    // U = A_tt xp on the contact area by four FFT products (fresh at every solver call)
-    if constexpr (!DIRECT)
-    for (int ik = 0; ik < 2; ik++) {
-        bool ladd = false;
-        for (int jk = 0; jk < 2; jk++) {
-            if (a.chatA[ik][jk] == nullptr) continue;
-            conv_dev(P, sm, xp + (size_t) jk * n, a.chatA[ik][jk], a.ug + (size_t) ik * n, el, 1, ladd ? 1 : 0);
-            ladd = true; nprod++;
-        }
-    }
-
-    // shared memory is ours now (S and W regions of the FFT layout)
-    SteadySmem s;
-    if constexpr (DIRECT) {
-        if (sbase == nullptr) {                                     // one-CTA path: the place steady_carve would choose
-            sbase = reinterpret_cast<unsigned char *>(sm.S);
-            if (steady_fixed_bytes(P.mx, P.my) > (size_t) P.off_twx) sbase += P.smem_bytes;
-            conv_tables_invalidate(sm);
-        }
-        steady_offsets(sbase, 0, mx, my, s);
-    } else {
-        steady_carve(P, reinterpret_cast<unsigned char *>(sm.S), a.sym, s);
-        conv_tables_invalidate(sm);                                 // the sweep arrays overwrite the product's window
-    }
-    if (s.hasq) {
-        if (a.sym) {
-            for (int i = tid; i < n; i += nt) {
-                const int ay = i / mx, ax = i - ay * mx;
-                const size_t o = (size_t) (ay + a.cmy) * (2 * a.cmx) + ax + a.cmx;
-                s.q()[i] = a.cf11[o] * a.ga_inv; s.q()[n + i] = a.cf12[o] * a.ga_inv; s.q()[2 * n + i] = a.cf22[o] * a.ga_inv;
-            }
-        } else {
-            for (int i = tid; i < 2 * n; i += nt) {
-                const int ay = i / (2 * mx), dx = i - ay * 2 * mx - mx;
-                const size_t o = (size_t) (ay + a.cmy) * (2 * a.cmx) + dx + a.cmx;
-                s.q()[i] = a.cf11[o] * a.ga_inv; s.q()[2 * n + i] = a.cf12[o] * a.ga_inv; s.q()[4 * n + i] = a.cf22[o] * a.ga_inv;
-            }
-        }
-    }
-    for (int i = tid; i < 2 * mx; i += nt) {
-        const size_t o = (size_t) a.cmy * (2 * a.cmx) + (i - mx) + a.cmx;
-        s.r0()[i] = a.cf11[o] * a.ga_inv; s.r0()[2 * mx + i] = a.cf12[o] * a.ga_inv; s.r0()[4 * mx + i] = a.cf22[o] * a.ga_inv;
-    }
-    SteadyTab T;
-    T.oq = s.hasq ? s.oq : 0xffffffffu; T.or0 = s.or0; T.cf11 = a.cf11; T.cf12 = a.cf12; T.cf22 = a.cf22; T.n = n; T.mx = mx; T.cmx = a.cmx; T.cmy = a.cmy;
-    T.sym = a.sym; T.ga_inv = a.ga_inv;
-    // compact list of contact elements in sweep order + row offsets
-    for (int iy = tid; iy < my; iy += nt) {
-        int cnt = 0;
-        for (int ix = 0; ix < mx; ix++) cnt += (el[iy * mx + ix] >= 1);
-        s.rowk(iy + 1) = cnt;
-    }
-    __syncthreads();
-    if (tid == 0) { s.rowk(0) = 0; for (int iy = 0; iy < my; iy++) s.rowk(iy + 1) += s.rowk(iy); }
-    __syncthreads();
-    for (int iy = tid; iy < my; iy += nt) {
-        int k = s.rowk(iy);
-        for (int ix = 0; ix < mx; ix++) if (el[iy * mx + ix] >= 1) a.iel[k++] = iy * mx + ix;
-    }
-    __syncthreads();
-
-    int nsp = 0;
-    if constexpr (DIRECT) {                                       // column ranges of the row sums (contact area is fixed in TANG)
-        int *spk = a.isp, *spl = a.isp + my + 2;
-        for (int iy = tid; iy < my; iy += nt) {
-            int first = mx, last = -1;
-            for (int ix = 0; ix < mx; ix++) if (el[iy * mx + ix] >= 1) { if (first == mx) first = ix; last = ix; }
-            spk[iy + 1] = last < 0 ? 0 : min(mx - 1, last + 1) - max(0, first - 1) + 1;
-        }
-        __syncthreads();
-        if (tid == 0) { spk[0] = 0; for (int iy = 0; iy < my; iy++) spk[iy + 1] += spk[iy]; }
-        __syncthreads();
-        for (int iy = tid; iy < my; iy += nt) {
-            const int cnt = spk[iy + 1] - spk[iy];
-            if (cnt > 0) {
-                int first = 0;
-                while (el[iy * mx + first] < 1) first++;
-                const int j0 = max(0, first - 1);
-                for (int q = 0; q < cnt; q++) spl[spk[iy] + q] = iy * mx + j0 + q;
-            }
-        }
-        __syncthreads();
-        nsp = spk[my];
-    }
+    (void) lane; (void) full; (void) nsp;
     // registers: my contact elements k = (tid - 32) + m (nt - 32).  Warp 0 owns none: it walks the rows while the other warps
     // apply the net change of the previous row to their elements (pipelined update below)
     double Ux[KMAX], Uy[KMAX];
@@ -663,7 +579,7 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
     for (int m = 0; m < KMAX; m++) {
         const int k = (tid - 32) + m * (nt - 32);
         Ux[m] = 0.0; Uy[m] = 0.0; ixy[m] = -1;
-        if (!DIRECT && tid >= 32 && k < ncon) {
+        if (OWN && tid >= 32 && k < ncon) {
             const int ii = a.iel[k], iy = ii / mx;
             ixy[m] = (ii - iy * mx) | (iy << 16);
             Ux[m] = a.ug[ii]; Uy[m] = a.ug[n + ii];
@@ -784,12 +700,14 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
                 s.ddx(jx) = 0.0; s.ddy(jx) = 0.0;
             }
             for (int k = k0 + tid; k < k1; k += nt) s.cix(k - k0) = a.iel[k] - iy * mx;
+            if constexpr (OWN) {
 #pragma unroll
-            for (int m = 0; m < KMAX; m++)
-                if (ixy[m] >= 0 && (ixy[m] >> 16) == iy) { s.urx(ixy[m] & 0xffff) = Ux[m]; s.ury(ixy[m] & 0xffff) = Uy[m]; }
+                for (int m = 0; m < KMAX; m++)
+                    if (ixy[m] >= 0 && (ixy[m] >> 16) == iy) { s.urx(ixy[m] & 0xffff) = Ux[m]; s.ury(ixy[m] & 0xffff) = Uy[m]; }
+            }
             __syncthreads();
 
-            if (DIRECT || tid < 32) {                          // ---- warp 0: the Gauss-Seidel steps of this row ----
+            if constexpr (!OWN) {                              // ---- warp 0 (whole CTA: direct form): the Gauss-Seidel steps of this row ----
                 dsum = gs_walk_row<DIRECT>(w, iy, k0, k1, itgs, par, dsum, tpw);
             } else if (pend_row >= 0) {
                 // ---- warps 1.. meanwhile: the net change of the PREVIOUS row goes to the elements of all other rows.  This pass is
@@ -805,12 +723,14 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
             if constexpr (!DIRECT) {
                 int nx = iy;
                 do { nx = (nx + 1 == my) ? 0 : nx + 1; } while (nx != iy && s.rowk(nx + 1) == s.rowk(nx));
-                if (nx != iy) apply_list(par, iy, [&](int r) { return r == nx; });
+                if constexpr (OWN) { if (nx != iy) apply_list(par, iy, [&](int r) { return r == nx; }); }
                 pend_row = iy; pend_par = par; par ^= 1;
             }
+            if constexpr (OWN) {
 #pragma unroll
-            for (int m = 0; m < KMAX; m++)
-                if (ixy[m] >= 0 && (ixy[m] >> 16) == iy) { Ux[m] = s.urx(ixy[m] & 0xffff); Uy[m] = s.ury(ixy[m] & 0xffff); }
+                for (int m = 0; m < KMAX; m++)
+                    if (ixy[m] >= 0 && (ixy[m] >> 16) == iy) { Ux[m] = s.urx(ixy[m] & 0xffff); Uy[m] = s.ury(ixy[m] & 0xffff); }
+            }
             for (int jx = tid; jx < mx; jx += nt) {            // write the row back
                 const int ii = iy * mx + jx;
                 psx[ii] = s.psx(jx); psy[ii] = s.psy(jx);
@@ -829,6 +749,143 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
         if (itgs == 1) dif1 = dif;
         __syncthreads();
     }
+    g.itgs = itgs; g.dif = dif; g.dif1 = dif1;
+    if (tid == 0) {
+        atomicAdd(&g_steady_prof[0], nstep); atomicAdd(&g_steady_prof[4], 1ull);
+        CB_GS_PROF(atomicAdd(&g_steady_prof[1], tpw[1]); atomicAdd(&g_steady_prof[2], tpw[2]); atomicAdd(&g_steady_prof[3], tpw[3]);
+                   atomicAdd(&g_steady_prof[5], tpw[4]); atomicAdd(&g_steady_prof[6], tpw[5]); atomicAdd(&g_steady_prof[7], tpw[6]);)
+    }
+}
+
+// Gauss-Seidel sweeps of stdygs (convex = 0) or cnvxgs (convex = 1): returns info (0 ok, 1 maxgs reached,
+// 2 stagnation, 3 divergence).  All threads of the CTA must call.
+//
+// Row-blocked organisation: the elements of one grid row are processed by warp 0 alone -- lane 0 runs the scalar
+// per-element solve, all 32 lanes keep the row's own displacement differences up to date and re-integrate the row
+// with a warp scan -- while the net change of the row is applied to the register-resident U of all other rows once
+// per row by the whole CTA.
+//
+// DIRECT = true: the form for contact areas that do not fit the register-resident U (more than 22 x 352 elements, or a grid on
+// the whole-GPU path).  No U is kept: before every element step the whole CTA evaluates the reference's row sum
+// U_i = (1/G) sum_j A(i - j) xp_j over the compact contact list (gf3_AijPj, m_aijpj.f90:99-254; the current row from shared
+// memory, the other rows from global memory / L2, coefficients from the spatial blocks in L2), then warp 0 performs the
+// element step exactly as in the register form.  No rank-1 updates, no FFT products, no coefficient table in shared
+// memory: O(ncon) work per element like the reference, any grid size.  `sbase`: shared memory for the row arrays
+// (steady_fixed_bytes), used instead of the plan's layout.
+template <int KMAX, bool DIRECT = false>
+__device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const SteadyArgs &a, int *el, double *ps, double *ss,
+                          int ncon, int &itgs_out, double &err_out, int &nprod, unsigned char *sbase = nullptr)
+{
+    const int n = P.npot, mx = P.mx, my = P.my, tid = threadIdx.x, nt = blockDim.x;
+    double *psx = ps, *psy = ps + n;
+    double *red = sm.red;
+
+    // SteadyGS: traction differences along the rolling direction (x ascending = towards the leading edge), :2900-2915;
+    // ConvexGS works on the tractions themselves
+    const bool convex = a.convex != 0;
+    const double *xp = convex ? ps : a.dp;
+    if (!convex) {
+        for (int i = tid; i < n; i += nt) {
+            const int ix = i % mx;
+            a.dp[i] = (ix != mx - 1) ? psx[i] - psx[i + 1] : psx[i];
+            a.dp[n + i] = (ix != mx - 1) ? psy[i] - psy[i + 1] : psy[i];
+        }
+    }
+    __syncthreads();
+    const double facnel = (double) sqrtf(__fdiv_rn((float) n, (float) ncon));
+
+    // U = A_tt xp on the contact area by four FFT products (fresh at every solver call)
+    if constexpr (!DIRECT)
+    for (int ik = 0; ik < 2; ik++) {
+        bool ladd = false;
+        for (int jk = 0; jk < 2; jk++) {
+            if (a.chatA[ik][jk] == nullptr) continue;
+            conv_dev(P, sm, xp + (size_t) jk * n, a.chatA[ik][jk], a.ug + (size_t) ik * n, el, 1, ladd ? 1 : 0);
+            ladd = true; nprod++;
+        }
+    }
+
+    // shared memory is ours now (S and W regions of the FFT layout)
+    SteadySmem s;
+    if constexpr (DIRECT) {
+        if (sbase == nullptr) {                                     // one-CTA path: the place steady_carve would choose
+            sbase = reinterpret_cast<unsigned char *>(sm.S);
+            if (steady_fixed_bytes(P.mx, P.my) > (size_t) P.off_twx) sbase += P.smem_bytes;
+            conv_tables_invalidate(sm);
+        }
+        steady_offsets(sbase, 0, mx, my, s);
+    } else {
+        steady_carve(P, reinterpret_cast<unsigned char *>(sm.S), a.sym, s);
+        conv_tables_invalidate(sm);                                 // the sweep arrays overwrite the product's window
+    }
+    if (s.hasq) {
+        if (a.sym) {
+            for (int i = tid; i < n; i += nt) {
+                const int ay = i / mx, ax = i - ay * mx;
+                const size_t o = (size_t) (ay + a.cmy) * (2 * a.cmx) + ax + a.cmx;
+                s.q()[i] = a.cf11[o] * a.ga_inv; s.q()[n + i] = a.cf12[o] * a.ga_inv; s.q()[2 * n + i] = a.cf22[o] * a.ga_inv;
+            }
+        } else {
+            for (int i = tid; i < 2 * n; i += nt) {
+                const int ay = i / (2 * mx), dx = i - ay * 2 * mx - mx;
+                const size_t o = (size_t) (ay + a.cmy) * (2 * a.cmx) + dx + a.cmx;
+                s.q()[i] = a.cf11[o] * a.ga_inv; s.q()[2 * n + i] = a.cf12[o] * a.ga_inv; s.q()[4 * n + i] = a.cf22[o] * a.ga_inv;
+            }
+        }
+    }
+    for (int i = tid; i < 2 * mx; i += nt) {
+        const size_t o = (size_t) a.cmy * (2 * a.cmx) + (i - mx) + a.cmx;
+        s.r0()[i] = a.cf11[o] * a.ga_inv; s.r0()[2 * mx + i] = a.cf12[o] * a.ga_inv; s.r0()[4 * mx + i] = a.cf22[o] * a.ga_inv;
+    }
+    SteadyTab T;
+    T.oq = s.hasq ? s.oq : 0xffffffffu; T.or0 = s.or0; T.cf11 = a.cf11; T.cf12 = a.cf12; T.cf22 = a.cf22; T.n = n; T.mx = mx; T.cmx = a.cmx; T.cmy = a.cmy;
+    T.sym = a.sym; T.ga_inv = a.ga_inv;
+    // compact list of contact elements in sweep order + row offsets
+    for (int iy = tid; iy < my; iy += nt) {
+        int cnt = 0;
+        for (int ix = 0; ix < mx; ix++) cnt += (el[iy * mx + ix] >= 1);
+        s.rowk(iy + 1) = cnt;
+    }
+    __syncthreads();
+    if (tid == 0) { s.rowk(0) = 0; for (int iy = 0; iy < my; iy++) s.rowk(iy + 1) += s.rowk(iy); }
+    __syncthreads();
+    for (int iy = tid; iy < my; iy += nt) {
+        int k = s.rowk(iy);
+        for (int ix = 0; ix < mx; ix++) if (el[iy * mx + ix] >= 1) a.iel[k++] = iy * mx + ix;
+    }
+    __syncthreads();
+
+    int nsp = 0;
+    if constexpr (DIRECT) {                                       // column ranges of the row sums (contact area is fixed in TANG)
+        int *spk = a.isp, *spl = a.isp + my + 2;
+        for (int iy = tid; iy < my; iy += nt) {
+            int first = mx, last = -1;
+            for (int ix = 0; ix < mx; ix++) if (el[iy * mx + ix] >= 1) { if (first == mx) first = ix; last = ix; }
+            spk[iy + 1] = last < 0 ? 0 : min(mx - 1, last + 1) - max(0, first - 1) + 1;
+        }
+        __syncthreads();
+        if (tid == 0) { spk[0] = 0; for (int iy = 0; iy < my; iy++) spk[iy + 1] += spk[iy]; }
+        __syncthreads();
+        for (int iy = tid; iy < my; iy += nt) {
+            const int cnt = spk[iy + 1] - spk[iy];
+            if (cnt > 0) {
+                int first = 0;
+                while (el[iy * mx + first] < 1) first++;
+                const int j0 = max(0, first - 1);
+                for (int q = 0; q < cnt; q++) spl[spk[iy] + q] = iy * mx + j0 + q;
+            }
+        }
+        __syncthreads();
+        nsp = spk[my];
+    }
+    GsSweep g;
+    g.P = &P; g.a = &a; g.s = s; g.T = T; g.el = el; g.ps = ps; g.ss = ss; g.red = red; g.xp = xp; g.ncon = ncon; g.nsp = nsp;
+    g.facnel = facnel; g.itgs = 0; g.dif = 2.0; g.dif1 = 0.0;
+    if constexpr (DIRECT) gs_sweeps<1, true, false>(g);
+    else if (tid < 32) gs_sweeps<1, false, true>(g);           // warp 0 walks the rows,
+    else gs_sweeps<KMAX, false, false>(g);                     // warps 1.. own the contact elements
+    const int itgs = g.itgs;
+    const double dif = g.dif, dif1 = g.dif1;
     double conv = 1.0;
     if (dif * dif1 != 0.0 && itgs > 1) conv = exp(log(dif / dif1) / (itgs - 1));
     int info = 0;
@@ -836,11 +893,6 @@ __device__ __noinline__ int stdygs_dev(const ConvPlan &P, const Smem &sm, const 
     if (itgs >= a.maxgs && conv > 0.997) info = 2;
     if (itgs >= a.maxgs && conv > 1.0) info = 3;
     itgs_out = itgs; err_out = dif;
-    if (tid == 0) {
-        atomicAdd(&g_steady_prof[0], nstep); atomicAdd(&g_steady_prof[4], 1ull);
-        CB_GS_PROF(atomicAdd(&g_steady_prof[1], tpw[1]); atomicAdd(&g_steady_prof[2], tpw[2]); atomicAdd(&g_steady_prof[3], tpw[3]);
-                   atomicAdd(&g_steady_prof[5], tpw[4]); atomicAdd(&g_steady_prof[6], tpw[5]); atomicAdd(&g_steady_prof[7], tpw[6]);)
-    }
     __syncthreads();
     return info;
 }
