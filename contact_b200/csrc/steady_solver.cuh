@@ -221,6 +221,15 @@ __device__ __forceinline__ void steady_carve(const ConvPlan &P, unsigned char *b
     steady_offsets(base, tab ? (sym ? 3 : 6) * n : 0, (int) mx, (int) my, s);
 }
 
+// load from a table in shared memory that is constant during the sweeps, by its 32-bit shared-space byte address (no address
+// derivation per access, free to be scheduled across the sweep's stores)
+__device__ __forceinline__ double lds_const(uint32_t addr)
+{
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
 // coefficient lookup A_tt(dx, dy): c11, c12 (= c21), c22, already times 1/G
 struct SteadyTab {
     uint32_t oq, or0;                       // (doubles) offsets of the table (0xffffffff: none) and of the dy = 0 rows in the shared window
@@ -291,6 +300,11 @@ __device__ __forceinline__ double gs_walk_row(const GsWalk &w, const int iy, con
     // rows of up to 96 elements: the row's own U and its accumulated net changes live in the registers of warp 0
     // (lane l holds elements l, l + 32, l + 64) for the whole walk -- no shared-memory round trip per change
     const bool rr3 = !DIRECT && mx <= 96;
+    // byte addresses of the dy = 0 rows (constant during the sweeps): entry dx of block b is at r0a + 8 dx + r0s b
+    const uint32_t r0a = (uint32_t) __cvta_generic_to_shared(cb_smem_window) + 8u * (T.or0 + (uint32_t) mx), r0s = 16u * (uint32_t) mx;
+    uint32_t r0l[3];                                // ... of this lane's three columns of the row
+#pragma unroll
+    for (int r = 0; r < 3; r++) r0l[r] = r0a + 8u * (uint32_t) min(lane + 32 * r, mx - 1);
     double urx_[3] = { 0.0, 0.0, 0.0 }, ury_[3] = { 0.0, 0.0, 0.0 }, ddx_[3] = { 0.0, 0.0, 0.0 }, ddy_[3] = { 0.0, 0.0, 0.0 };
     if (rr3) {
 #pragma unroll
@@ -373,8 +387,8 @@ __device__ __forceinline__ double gs_walk_row(const GsWalk &w, const int iy, con
                 if (zl) { c00 = l00; c01 = l01; c11 = l11; }
                 else if (convex) { c00 = q00; c01 = q01; c11 = q11; }   // cnvxgs: coefs / coefsv, :2519-2541
                 else {                                              // stdygs: c(0) - c(jx - ix), :3010-3040
-                    double t00, t01, t11;
-                    T.row0(jxs - ix, t00, t01, t11);
+                    const uint32_t ad = r0a + 8u * (uint32_t) (jxs - ix);
+                    const double t00 = lds_const(ad), t01 = lds_const(ad + r0s), t11 = lds_const(ad + 2u * r0s);
                     c00 = q00 - t00; c01 = q01 - t01; c11 = q11 - t11;
                 }
                 double sx = s.wsx(ix) + ucx, sy = s.wsy(ix) + ucy;
@@ -481,8 +495,12 @@ __device__ __forceinline__ double gs_walk_row(const GsWalk &w, const int iy, con
             const double ex = s.chx(c), ey = s.chy(c);
             if (rr3) {
                 double c11[3], c12[3], c22[3];
+                const uint32_t jo = 8u * (uint32_t) jx;
 #pragma unroll
-                for (int r = 0; r < 3; r++) T.row0(min(lane + 32 * r, mx - 1) - jx, c11[r], c12[r], c22[r]);
+                for (int r = 0; r < 3; r++) {
+                    const uint32_t ad = r0l[r] - jo;
+                    c11[r] = lds_const(ad); c12[r] = lds_const(ad + r0s); c22[r] = lds_const(ad + 2u * r0s);
+                }
 #pragma unroll
                 for (int r = 0; r < 3; r++) {
                     urx_[r] = urx_[r] + (c11[r] * ex + c12[r] * ey); ury_[r] = ury_[r] + (c12[r] * ex + c22[r] * ey);

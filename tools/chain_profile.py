@@ -1,44 +1,46 @@
-"""Dynamic instruction profile of the SteadyGS element-step chain (warp 0 of a CTA) from an `ncu --page source --csv` export of
-k_contac_batch joined with the nvdisasm line table of the same cubin (see tools/sass_line_profile.py for the two inputs):
-   python tools/chain_profile.py prof.source.csv.gz sass_lines.txt <element steps in the capture>
-Prints, for the source-line range of gs_walk_row (steady_solver.cuh), warp-level instructions executed per element step by opcode,
-the local-memory accesses (register spills, stack arguments) per step, and the hottest source lines."""
+"""Dynamic instruction profile of the SteadyGS walker warp (gs_sweeps<1, false, true>: warp 0 of a CTA) from an
+`ncu --section SourceCounters --page source --csv` export of k_contac_batch joined with the nvdisasm line table of the same cubin:
+   cuobjdump -xelf all libcontact_addon_b200.so ; nvdisasm -g -c contact_addon_b200.sm_100a.cubin > sass_lines.txt
+   python tools/chain_profile.py prof.source.csv.gz sass_lines.txt <element steps in the capture> [function-name substring]
+Prints warp-level instructions executed per element step by opcode, local-memory accesses per step, the stall-reason split of the
+function's samples and the source lines with the most samples."""
 import collections, csv, gzip, re, sys
 src_csv, dis, steps = sys.argv[1], sys.argv[2], float(sys.argv[3])
-lo, hi = (int(sys.argv[4]), int(sys.argv[5])) if len(sys.argv) > 5 else (0, 0)
+want = sys.argv[4] if len(sys.argv) > 4 else "gs_sweepsILi1ELb0ELb1"
 kern = "k_contac_batch"
 rows = list(csv.reader(gzip.open(src_csv, "rt") if src_csv.endswith(".gz") else open(src_csv)))
 h = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[h]; col = {n: i for i, n in enumerate(hdr)}
 ncu = [r for r in rows[h + 1:] if len(r) >= len(hdr)]
+stall = [n for n in hdr if n.startswith("stall_") and "Not Issued" not in n]
 lines = []; cur = None; inside = False; fn = ""
 for l in open(dis):
     if l.startswith("//---") and ".text." in l:
         inside = kern in l; continue
     if not inside: continue
     if l.startswith("$") and l.rstrip().endswith(":"):
-        fn = l; continue
+        fn = l.strip(); continue
     m = re.match(r'\s*//## File "([^"]+)", line (\d+)', l)
     if m: cur = (m.group(1).split("/")[-1], int(m.group(2))); continue
     m = re.match(r"\s+/\*([0-9a-f]+)\*/\s+(.*?);", l)
     if m: lines.append((cur, m.group(2).strip(), fn))
 assert len(ncu) == len(lines), (len(ncu), len(lines))
-# the instantiation with the most executed instructions among the functions whose name contains gs_walk_row (or, for builds
-# before the walk was a function of its own, the given source-line range of stdygs_dev)
-per_fn = collections.Counter()
+op = collections.Counter(); ln_ex = collections.Counter(); ln_smp = collections.Counter(); st = collections.Counter()
+tot = smp = nstat = 0
 for (key, ins, f), r in zip(lines, ncu):
-    if "gs_walk_row" in f or (lo and key and key[0] == "steady_solver.cuh" and lo <= key[1] <= hi and "stdygs_dev" in f):
-        per_fn[f] += int(r[col["Instructions Executed"]] or 0)
-best = per_fn.most_common(1)[0][0]
-op = collections.Counter(); ln = collections.Counter(); tot = 0
-for (key, ins, f), r in zip(lines, ncu):
-    if f != best: continue
-    if lo and not (key and key[0] == "steady_solver.cuh" and lo <= key[1] <= hi) and "gs_walk_row" not in f: continue
-    ex = int(r[col["Instructions Executed"]] or 0)
+    if want not in f: continue
+    ex = int(r[col["Instructions Executed"]] or 0); sm = int(r[col["# Samples"]] or 0)
     o = ins.split()[1] if ins.startswith("@") else ins.split()[0]
-    op[o.split(".")[0]] += ex; ln[key] += ex; tot += ex
-print("function:", best.strip()[:60], "...", best.strip()[-70:])
+    op[o.split(".")[0]] += ex; ln_ex[key] += ex; ln_smp[key] += sm; tot += ex; smp += sm; nstat += 1
+    for n in stall:
+        v = int(r[col[n]] or 0)
+        if v: st[n[6:]] += v
+print("function: ...%s (%d SASS instructions)" % (want, nstat))
 print("warp instructions per element step: %.0f" % (tot / steps))
-print("by opcode:", ", ".join("%s %.0f" % (o, c / steps) for o, c in op.most_common(24)))
-print("local memory per step: LDL %.1f, STL %.1f" % (op["LDL"] / steps, op["STL"] / steps))
-print("hottest lines:", ", ".join("%s:%d %.0f" % (k[0], k[1], c / steps) for k, c in ln.most_common(14) if k))
+print("by opcode:", ", ".join("%s %.0f" % (o, c / steps) for o, c in op.most_common(26)))
+print("local memory per element step: LDL %.2f, STL %.2f" % (op["LDL"] / steps, op["STL"] / steps))
+ssum = sum(st.values())
+print("stall reasons of the function's %d samples:" % smp, ", ".join("%s %.0f%%" % (k, 100.0 * v / ssum) for k, v in st.most_common(8)))
+print("lines by samples (share of the function, instructions per step):")
+for k, c in ln_smp.most_common(16):
+    if k: print("   %s:%d  %.1f%%  %.1f" % (k[0], k[1], 100.0 * c / smp, ln_ex[k] / steps))
