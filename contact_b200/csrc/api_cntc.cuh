@@ -460,6 +460,18 @@ inline void calculate_batch(const std::vector<Problem *> &probs, std::vector<int
     for (auto &g : groups) {
         auto tg0 = now();
         CoefSet &cs = *g.first;
+        // Longest case first: the kernel hands the cases of a group to the CTAs through one queue in the order of this list, and a
+        // contact case costs ~ (contact elements) x (Gauss-Seidel sweeps), anything from 0.1 to 1 s on one SM, so with more cases
+        // than SMs the order decides how long the last CTAs run alone.  A-priori key (nothing of an earlier solve is used): solver
+        // class first (Gauss-Seidel / tangential / normal only), then the load (normal force, or approach when that is prescribed).
+        if (g.second.size() > (size_t) launch_blocks((int) g.second.size())) {
+            auto cost = [&](size_t k) {
+                const Problem &q = *probs[k];
+                const double cls = q.tang == 3 ? 2.0 : (q.tang != 0 ? 1.0 : 0.0);
+                return std::make_pair(cls, q.norm == 1 ? q.fntrue : pen0[k]);
+            };
+            std::stable_sort(g.second.begin(), g.second.end(), [&](size_t a, size_t b) { return cost(a) > cost(b); });
+        }
         const std::vector<size_t> &ks = g.second;
         const int n = (int) ks.size(), npot = cs.mx * cs.my;
         const ConvPlan &P = cs.hp.p;

@@ -380,6 +380,7 @@ __device__ __forceinline__ double gs_walk_row(const GsWalk &w, const int iy, con
             const double vx = rq == 0 ? urx_[0] : (rq == 1 ? urx_[1] : urx_[2]), vy = rq == 0 ? ury_[0] : (rq == 1 ? ury_[1] : ury_[2]);
             ucx = __shfl_sync(full, vx, ix & 31); ucy = __shfl_sync(full, vy, ix & 31);
         } else { ucx = s.urx(ix); ucy = s.ury(ix); }
+        const double pox = s.psx(ix), poy = s.psy(ix);  // all lanes: the element's own change is applied from registers (rr3)
         if (lane == 0) {
             s.ictl(0, my) = 0;
             if (active) {
@@ -397,18 +398,37 @@ __device__ __forceinline__ double gs_walk_row(const GsWalk &w, const int iy, con
                     while (ixb < mx - 1 && s.el(ixb + 1) >= 1) ixb++;
                     sx = s.wsx(ix) + lsx - a.ub[iy * mx + ixb]; sy = s.wsy(ix) + lsy - a.ub[n + iy * mx + ixb];
                 }
-                const double pox = s.psx(ix), poy = s.psy(ix);
                 px = pox; py = poy;
                 plstrc_dev(e, c00, c01, c01, c11, a.eps, a.omegah, a.omegas, px, py, s.bnd(ix), sx, sy);
                 const double ex = px - pox, ey = py - poy;
                 dsum += ex * ex + ey * ey;
-                if (ex != 0.0 || ey != 0.0) { s.chj(0) = ix; s.chx(0) = ex; s.chy(0) = ey; s.ictl(0, my) = 1; }
+                if (!rr3 && (ex != 0.0 || ey != 0.0)) { s.chj(0) = ix; s.chx(0) = ex; s.chy(0) = ey; s.ictl(0, my) = 1; }
                 s.psx(ix) = px; s.psy(ix) = py; s.ssx(ix) = sx; s.ssy(ix) = sy; s.el(ix) = e;
                 if (!convex) { s.dpx(ix) += ex; s.dpy(ix) += ey; }
             }
         }
         CB_GS_PROF(const unsigned long long tb = clock64();)
         __syncwarp();
+        if (rr3 && active) {
+            // the element's own change, first in the order of the change list: every lane forms it from the broadcast new traction
+            // and updates its three columns of the row at once -- no trip through the list in shared memory, and the update's
+            // loads and FMAs are independent of the re-integration scan that follows
+            const double ex = __shfl_sync(full, px, 0) - pox, ey = __shfl_sync(full, py, 0) - poy;
+            if (ex != 0.0 || ey != 0.0) {
+                double c11[3], c12[3], c22[3];
+                const uint32_t jo = 8u * (uint32_t) ix;
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    const uint32_t ad = r0l[r] - jo;
+                    c11[r] = lds_const(ad); c12[r] = lds_const(ad + r0s); c22[r] = lds_const(ad + 2u * r0s);
+                }
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    urx_[r] = urx_[r] + (c11[r] * ex + c12[r] * ey); ury_[r] = ury_[r] + (c12[r] * ex + c22[r] * ey);
+                    if (lane + 32 * r == ix) { ddx_[r] += ex; ddy_[r] += ey; }
+                }
+            }
+        }
         if (!convex && active) {
             // re-integrate dp -> ps to the left (:3089-3126) with a warp scan: lanes 0.. take the elements
             // ix-1, ix-2, ...; the chain of adhesion elements follows the new traction, it ends at the

@@ -22,3 +22,7 @@ for rep in range(2):
     print("rep %d: %d cases in %.3f s (kernel %.1f ms); mean itgs %.1f, ncon %.0f" % (rep, n, dt, kms, np.mean([t["itgs"] for t in its]), np.mean([t["ncon"] for t in its])))
     print("   cycles per element step: plstrc %.0f, re-integration %.0f, in-row update %.0f, other rows %.0f (%d steps, %d calls); changes per step %.2f" % (
         pr["plstrc"] / pr["steps"], pr["reintegrate"] / pr["steps"], pr["update"] / pr["steps"], pr["rowupdate"] / pr["steps"], pr["steps"], pr["calls"], pr["changes"] / pr["steps"]))
+if "--dump" in sys.argv:                                          # per-case inputs and work (scheduler cost model)
+    import json
+    json.dump({"draws": [list(map(float, d)) for d in draws], "itgs": [int(t["itgs"]) for t in its], "ncon": [int(t["ncon"]) for t in its]},
+              open(os.path.join(ROOT, "gpurun_out", "h91_case_work.json"), "w"))
