@@ -1459,3 +1459,48 @@ def test_interface_errors_and_short_buffers(cb):
     L.cntc_getfielddata(C.c_int(ire), C.c_int(1), C.c_int(cb.CNTC["fld_pn"]), n, short.ctypes.data_as(C.POINTER(C.c_double)))
     assert (short[4:] == -7.0).all() and (short[:4] >= 0.0).all()       # only lenarr entries written
     cb.cntc_finalize(ire)
+
+
+def test_batch_order_independent_of_scheduling(cb):
+    """calculate_batch sorts a group longest-case-first when it holds more cases than the GPU has SMs (the kernel's case queue follows
+    that order).  The sort must not be visible in the results: 480 mixed cases (160 normal-only and 320 steady rolling -- two
+    groups, both beyond 148 --, seeded loads and creepages, 19x19 cattaneo grid) in ONE call against the same cases in four calls
+    of 120 (no group beyond 148, no sort): tractions, element divisions and forces bit-identical, case by case."""
+    c = cases.CATTANEO2
+    g = dict(mx=c["mx"], my=c["my"], xl=c["xl"], yl=c["yl"], dx=c["dx"], dy=c["dy"], ibase=1, prmudf=c["prmudf"])
+    n, npart = 480, 120
+    u = np.random.default_rng(7).uniform(-1.0, 1.0, size=(n, 4))
+
+    def setup(ire, i):
+        _setup_rolling(cb, ire, g, c["gg"], c["poiss"], fn=c["fn"] * (1.0 + 0.3 * u[i, 0]), eps=1e-6)
+        if i % 3 == 0:
+            cb.cntc_setflags(ire, 1, [cb.CNTC["ic_tang"]], [0])
+        else:
+            cb.cntc_setrollingstepsize(ire, 1, 0.0, g["dx"])
+            cb.cntc_setcreepages(ire, 1, 2e-3 * u[i, 1], 2e-3 * u[i, 2], 3e-4 * u[i, 3])
+
+    def collect(ires):
+        return [(np.concatenate([a.ravel() for a in cb.cntc_gettractions(ire, 1)]), cb.cntc_getelementdivision(ire, 1).ravel().copy(),
+                 np.array(cb.cntc_getcontactforces(ire, 1))) for ire in ires]
+
+    ires = list(range(200, 200 + n))
+    for i, ire in enumerate(ires):
+        setup(ire, i)
+    ierr = cb.cntc_calculate_batch(ires, 1)
+    assert (ierr == 0).all(), (ierr, cb.lib.last_error())
+    one = collect(ires)
+    for ire in ires:
+        cb.cntc_finalize(ire)
+    two = []
+    for h in range(n // npart):
+        part = ires[npart * h:npart * (h + 1)]
+        for ire in part:
+            setup(ire, ire - 200)
+        ierr = cb.cntc_calculate_batch(part, 1)
+        assert (ierr == 0).all(), (ierr, cb.lib.last_error())
+        two += collect(part)
+        for ire in part:
+            cb.cntc_finalize(ire)
+    assert any(int((el == 2).sum()) > 0 for _, el, _ in one)          # the rolling cases do slip
+    for (p1, e1, f1), (p2, e2, f2) in zip(one, two):
+        assert np.array_equal(e1, e2) and np.array_equal(p1, p2) and np.array_equal(f1, f2)
