@@ -381,6 +381,7 @@ __device__ __forceinline__ double gs_walk_row(const GsWalk &w, const int iy, con
             ucx = __shfl_sync(full, vx, ix & 31); ucy = __shfl_sync(full, vy, ix & 31);
         } else { ucx = s.urx(ix); ucy = s.ury(ix); }
         const double pox = s.psx(ix), poy = s.psy(ix);  // all lanes: the element's own change is applied from registers (rr3)
+        __syncwarp();                                   // every lane has read el, ps of this element before lane 0 rewrites them
         if (lane == 0) {
             s.ictl(0, my) = 0;
             if (active) {
