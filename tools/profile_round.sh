@@ -20,6 +20,14 @@ for f in prof_snorm prof_contac prof_large prof_gd; do
 done
 ncu -i gpurun_out/prof_snorm_${TAG}.ncu-rep --page source --csv > gpurun_out/prof_snorm_${TAG}.source.csv 2>/dev/null
 ncu -i gpurun_out/prof_contac_${TAG}.ncu-rep --page source --csv > gpurun_out/prof_contac_${TAG}.source.csv 2>/dev/null
+# source counters of the SteadyGS sweeps (one wave of hertz-91 cases): input of tools/chain_profile.py -> profiles/steadygs_chain_*.txt
+ncu --section SourceCounters --section WarpStateStats --clock-control none --import-source on -k regex:k_contac_batch -c 1 -f \
+    -o gpurun_out/prof_gs_${TAG} python tools/steady_timing_h91.py 148 > gpurun_out/prof_gs_${TAG}.out 2>&1
+ncu -i gpurun_out/prof_gs_${TAG}.ncu-rep --page source --csv > gpurun_out/prof_gs_${TAG}.source.csv 2>/dev/null
+gzip -f gpurun_out/prof_gs_${TAG}.source.csv
+# race / memory checks of the sweeps
+compute-sanitizer --tool racecheck --print-limit 20 python tools/sanitize_steady.py > gpurun_out/sanitize_racecheck_${TAG}.log 2>&1
+compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_steady.py > gpurun_out/sanitize_memcheck_${TAG}.log 2>&1
 ls -la gpurun_out/*.ncu-rep
 # keep the merge under the 64 MiB limit
 for f in gpurun_out/*.ncu-rep; do s=$(stat -c %s $f); if [ $s -gt 20000000 ]; then rm -f $f; fi; done
