@@ -10,7 +10,9 @@
 // elements), the tangential coefficient blocks live in shared memory as one quadrant table (c11, c22 even, c12 odd
 // in x and y: 3 npot doubles instead of 16 npot), and every change of dp is applied to all elements as a rank-1
 // update (same flops as the row sum, no reduction, no global-memory traffic in the sweep).  The sequential part of
-// the Gauss-Seidel step (plstrc + re-integration of the current row) runs on one thread out of shared memory.
+// the Gauss-Seidel step (plstrc + re-integration of the current row) is walked by warp 0 alone, in an instantiation of
+// its own (gs_sweeps<1, false, true>: no U registers, no local memory on the chain), while warps 1.. own the contact
+// elements and apply the finished rows' net changes (gs_sweeps<KMAX, false, false>); same barrier sequence in both.
 // U is (re)computed from scratch with four FFT products at the start of every solver call.
 #pragma once
 #include "norm_solver.cuh"
